@@ -1,0 +1,228 @@
+// api.cu -- extern "C" entry points of libswarm_b200.so (see include/swarm_b200.h).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "tile_kernels.cuh"
+
+namespace swarm {
+cudaError_t launch_tile(int mode, const TileParams& p, cudaStream_t stream);
+cudaError_t launch_reset_grid(const SwarmConfig& c, int cols, int rows, const float* centers, float* state,
+                              cudaStream_t stream);
+long long csr_workspace_bytes(int n, long long E);
+cudaError_t launch_csr_from_edges(int n, long long E, const int64_t* edge_src, const int64_t* edge_dst, int32_t* row_ptr,
+                                  int32_t* src, int32_t* perm, void* workspace, long long workspace_bytes,
+                                  cudaStream_t stream);
+cudaError_t launch_gatq_csr(int n, const float* weights, const float* x, const int32_t* row_ptr, const int32_t* src,
+                            float* q, float* rows, cudaStream_t stream);
+long long gatq_workspace_bytes(int n);
+
+namespace {
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return SWARM_OK;
+  return fail(SWARM_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// largest float q with sqrtf(q) <= dmin: makes the squared-distance pre-filter exactly equivalent to
+// the reference's `vector_norm(delta) <= dist_min` test on the rounded norm.
+float sq_threshold(float dmin) {
+  float q = dmin * dmin;
+  while (sqrtf(q) > dmin) q = std::nextafterf(q, 0.0f);
+  while (sqrtf(std::nextafterf(q, INFINITY)) <= dmin) q = std::nextafterf(q, INFINITY);
+  return q;
+}
+
+int validate(const SwarmConfig* cfg, bool need_graph) {
+  if (!cfg) return fail(SWARM_ERR_INVALID_ARG, "cfg is NULL");
+  if (cfg->num_envs <= 0) return fail(SWARM_ERR_INVALID_ARG, "num_envs must be positive");
+  if (cfg->n_agents <= 0) return fail(SWARM_ERR_INVALID_ARG, "n_agents must be positive");
+  if (cfg->scenario != SWARM_SCENARIO_GOTO && cfg->scenario != SWARM_SCENARIO_OBSTACLE_AVOIDANCE)
+    return fail(SWARM_ERR_INVALID_ARG, "unknown scenario id");
+  if (cfg->n_agents > kTileThreads)
+    return fail(SWARM_ERR_UNSUPPORTED, "n_agents > 128 is not supported by the env-tile kernels");
+  if (need_graph) {
+    if (cfg->graph_mode != SWARM_GRAPH_COMPLETE && cfg->graph_mode != SWARM_GRAPH_KNN)
+      return fail(SWARM_ERR_INVALID_ARG, "unknown graph mode");
+    if (cfg->graph_mode == SWARM_GRAPH_KNN) {
+      // torch.topk raises "selected index k out of range" for k > n (simulator.py:19 with n_agents < 10)
+      if (cfg->knn_k <= 0 || cfg->knn_k > cfg->n_agents)
+        return fail(SWARM_ERR_INVALID_ARG, "selected index k out of range");
+    }
+  }
+  return SWARM_OK;
+}
+
+int fill_params(TileParams& p, const SwarmConfig* cfg, int mode) {
+  std::memset(&p, 0, sizeof(p));
+  p.cfg = *cfg;
+  const int n = cfg->n_agents;
+  p.epb = kTileThreads / n;
+  p.ticks = 1;
+  const bool knn = cfg->graph_mode == SWARM_GRAPH_KNN;
+  p.maxdeg = knn ? (n + cfg->knn_k + 1) : n;
+  p.edges_per_env = (int32_t)swarm_edges_per_env(cfg);
+  p.one_minus_drag = (float)(1.0 - (double)cfg->drag);
+  p.dmin_aa = cfg->agent_radius + cfg->agent_radius;
+  p.dmin_ao = cfg->landmark_radius + cfg->agent_radius;
+  p.qmax_aa = sq_threshold(p.dmin_aa);
+  p.qmax_ao = sq_threshold(p.dmin_ao);
+  const TileLayout L = tile_layout(mode, kTileThreads, n, cfg->knn_k, p.maxdeg, cfg->graph_mode);
+  if (L.total > 227 * 1024) return fail(SWARM_ERR_UNSUPPORTED, "shared-memory tile exceeds 227 KB for this (N, k)");
+  return SWARM_OK;
+}
+}  // namespace
+}  // namespace swarm
+
+using namespace swarm;
+
+extern "C" {
+
+int swarm_abi_version(void) { return SWARM_ABI_VERSION; }
+
+const char* swarm_last_error(void) { return g_last_error.c_str(); }
+
+void swarm_default_config(SwarmConfig* cfg, int32_t scenario, int32_t num_envs, int32_t n_agents) {
+  if (!cfg) return;
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->grid_spacing = 0.15;
+  cfg->num_envs = num_envs;
+  cfg->n_agents = n_agents;
+  cfg->scenario = scenario;
+  cfg->graph_mode = SWARM_GRAPH_COMPLETE;
+  cfg->knn_k = 10;
+  cfg->dt = 0.1f;
+  cfg->drag = 0.25f;
+  cfg->collision_force = 100.0f;
+  cfg->contact_margin = 1e-3f;
+  cfg->agent_radius = 0.05f;
+  cfg->landmark_radius = 0.05f;
+  cfg->goal_x = -0.8f;
+  cfg->goal_y = 0.8f;
+  cfg->obstacle_x = -0.1f;
+  cfg->obstacle_y = 0.1f;
+  cfg->hit_distance = 0.2f;
+  cfg->penalty_distance = 1.0f;
+  cfg->obstacle_weight = 2.5f;
+}
+
+int64_t swarm_edges_per_env(const SwarmConfig* cfg) {
+  if (!cfg) return 0;
+  const int64_t n = cfg->n_agents;
+  if (cfg->graph_mode == SWARM_GRAPH_KNN) return 2 * (int64_t)cfg->knn_k * n + 1;
+  return n * (n - 1) + 1;
+}
+
+int swarm_reset_grid(const SwarmConfig* cfg, const float* centers, float* state, void* stream) {
+  if (int rc = validate(cfg, false)) return rc;
+  if (!centers || !state) return fail(SWARM_ERR_INVALID_ARG, "centers/state is NULL");
+  const int n = cfg->n_agents;
+  const int cols = (int)std::ceil(std::sqrt((double)n));     // math.ceil(math.sqrt(num_points))
+  const int rows = (int)std::ceil((double)n / (double)cols);  // math.ceil(num_points / num_cols)
+  return check_cuda(launch_reset_grid(*cfg, cols, rows, centers, state, (cudaStream_t)stream), "swarm_reset_grid");
+}
+
+int swarm_sim_step(const SwarmConfig* cfg, const float* state_in, const int32_t* actions, float* state_out,
+                   float* rewards, uint8_t* flags, uint32_t* contact, float* obs, float* dist, void* stream) {
+  if (int rc = validate(cfg, false)) return rc;
+  if (!state_in || !actions || !state_out) return fail(SWARM_ERR_INVALID_ARG, "state_in/actions/state_out is NULL");
+  if (contact && cfg->n_agents > 32) return fail(SWARM_ERR_UNSUPPORTED, "contact masks need n_agents <= 32");
+  TileParams p;
+  if (int rc = fill_params(p, cfg, MODE_STEP)) return rc;
+  p.state_in = state_in;
+  p.state_out = state_out;
+  p.actions_in = actions;
+  p.rewards_out = rewards;
+  p.flags_out = flags;
+  p.contact_out = contact;
+  p.obs_out = obs;
+  p.dist_out = dist;
+  return check_cuda(launch_tile(MODE_STEP, p, (cudaStream_t)stream), "swarm_sim_step");
+}
+
+int swarm_graph_build(const SwarmConfig* cfg, const float* state, int32_t* edges, int32_t* neighbours, void* stream) {
+  if (int rc = validate(cfg, true)) return rc;
+  if (!state) return fail(SWARM_ERR_INVALID_ARG, "state is NULL");
+  if (!edges && !neighbours) return fail(SWARM_ERR_INVALID_ARG, "no output requested");
+  TileParams p;
+  if (int rc = fill_params(p, cfg, MODE_GRAPH)) return rc;
+  p.state_in = state;
+  p.edges_out = edges;
+  p.nbr_out = neighbours;
+  return check_cuda(launch_tile(MODE_GRAPH, p, (cudaStream_t)stream), "swarm_graph_build");
+}
+
+int swarm_gatq_forward(const SwarmConfig* cfg, const float* weights, const float* state, float* q, int32_t* actions,
+                       void* stream) {
+  if (int rc = validate(cfg, true)) return rc;
+  if (!weights || !state) return fail(SWARM_ERR_INVALID_ARG, "weights/state is NULL");
+  if (!q && !actions) return fail(SWARM_ERR_INVALID_ARG, "no output requested");
+  TileParams p;
+  if (int rc = fill_params(p, cfg, MODE_FORWARD)) return rc;
+  p.weights = weights;
+  p.state_in = state;
+  p.q_out = q;
+  p.act_out = actions;
+  return check_cuda(launch_tile(MODE_FORWARD, p, (cudaStream_t)stream), "swarm_gatq_forward");
+}
+
+int64_t swarm_gatq_workspace_bytes(int32_t n_nodes) { return n_nodes > 0 ? gatq_workspace_bytes(n_nodes) : 0; }
+
+int swarm_gatq_forward_csr(int32_t n_nodes, const float* weights, const float* x, const int32_t* row_ptr,
+                           const int32_t* src, float* q, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (n_nodes < 0) return fail(SWARM_ERR_INVALID_ARG, "n_nodes must be >= 0");
+  if (n_nodes == 0) return SWARM_OK;
+  if (!weights || !x || !row_ptr || !q || !workspace) return fail(SWARM_ERR_INVALID_ARG, "NULL argument");
+  if (workspace_bytes < gatq_workspace_bytes(n_nodes)) return fail(SWARM_ERR_INVALID_ARG, "workspace too small");
+  float* rows = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  return check_cuda(launch_gatq_csr(n_nodes, weights, x, row_ptr, src, q, rows, (cudaStream_t)stream),
+                    "swarm_gatq_forward_csr");
+}
+
+int64_t swarm_csr_workspace_bytes(int32_t n_nodes, int64_t n_edges) {
+  if (n_nodes <= 0 || n_edges < 0) return 0;
+  return csr_workspace_bytes(n_nodes, n_edges);
+}
+
+int swarm_csr_from_edges(int32_t n_nodes, int64_t n_edges, const int64_t* edge_src, const int64_t* edge_dst,
+                         int32_t* row_ptr, int32_t* src, int32_t* perm, void* workspace, int64_t workspace_bytes,
+                         void* stream) {
+  if (n_nodes <= 0 || n_edges < 0) return fail(SWARM_ERR_INVALID_ARG, "n_nodes must be > 0 and n_edges >= 0");
+  if (n_edges >= (1LL << 31)) return fail(SWARM_ERR_UNSUPPORTED, "more than 2^31 - 1 edges");
+  if (!edge_src || !edge_dst || !row_ptr || !src || !perm || !workspace)
+    return fail(SWARM_ERR_INVALID_ARG, "NULL argument");
+  if (workspace_bytes < csr_workspace_bytes(n_nodes, n_edges)) return fail(SWARM_ERR_INVALID_ARG, "workspace too small");
+  return check_cuda(launch_csr_from_edges(n_nodes, n_edges, edge_src, edge_dst, row_ptr, src, perm, workspace,
+                                          workspace_bytes, (cudaStream_t)stream),
+                    "swarm_csr_from_edges");
+}
+
+int swarm_rollout(const SwarmConfig* cfg, const float* weights, float* state, int32_t ticks,
+                  const int32_t* forced_actions, float* returns, int32_t* hits, const SwarmTrace* trace, void* stream) {
+  if (int rc = validate(cfg, true)) return rc;
+  if (!weights || !state) return fail(SWARM_ERR_INVALID_ARG, "weights/state is NULL");
+  if (ticks < 0) return fail(SWARM_ERR_INVALID_ARG, "ticks must be >= 0");
+  if (ticks == 0) return SWARM_OK;
+  if (trace && trace->contact && cfg->n_agents > 32)
+    return fail(SWARM_ERR_UNSUPPORTED, "contact masks need n_agents <= 32");
+  TileParams p;
+  if (int rc = fill_params(p, cfg, MODE_ROLLOUT)) return rc;
+  p.weights = weights;
+  p.state_in = state;
+  p.state_out = state;
+  p.ticks = ticks;
+  p.actions_in = forced_actions;
+  p.returns = returns;
+  p.hits = hits;
+  if (trace) p.trace = *trace;
+  return check_cuda(launch_tile(MODE_ROLLOUT, p, (cudaStream_t)stream), "swarm_rollout");
+}
+
+}  // extern "C"

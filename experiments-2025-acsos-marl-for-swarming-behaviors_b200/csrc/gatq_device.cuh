@@ -1,0 +1,116 @@
+// gatq_device.cuh -- per-node pieces of the GAT Q-network (src/training/train_gcn_dqn.py:50-70 on
+// torch_geometric 2.5.3 GATConv), shared by the env-tile kernels and the generic CSR kernels.
+// `sw` is the shared-memory weight block in the k-major layout of tile_kernels.cuh (TW_*).
+//
+// Dense contractions run as sequential-k FFMA chains from 0 with the bias added afterwards (the order a
+// BLAS micro-kernel uses for these tiny shapes); element-wise steps that torch executes as separate ops
+// (message = alpha * h_j, scatter-add, + bias) are kept as separately rounded operations.
+#ifndef SWARM_GATQ_DEVICE_CUH
+#define SWARM_GATQ_DEVICE_CUH
+
+#include "tile_kernels.cuh"
+
+namespace swarm {
+
+// h = x W0^T (GATConv.lin, no bias); alpha_src = <h, att_src>, alpha_dst = <h, att_dst>
+__device__ __forceinline__ void gat_project(const float (&x)[7], const float* __restrict__ sw, float (&h)[32],
+                                            float& asrc, float& adst) {
+#pragma unroll
+  for (int cc = 0; cc < 32; ++cc) h[cc] = 0.0f;
+  const float4* w0 = reinterpret_cast<const float4*>(sw + TW_W0T);
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const float4 w = w0[k * 8 + c4];
+      h[4 * c4 + 0] = fmaf(x[k], w.x, h[4 * c4 + 0]);
+      h[4 * c4 + 1] = fmaf(x[k], w.y, h[4 * c4 + 1]);
+      h[4 * c4 + 2] = fmaf(x[k], w.z, h[4 * c4 + 2]);
+      h[4 * c4 + 3] = fmaf(x[k], w.w, h[4 * c4 + 3]);
+    }
+  }
+  asrc = 0.0f;
+  adst = 0.0f;
+  const float* as = sw + TW_ATT_S;
+  const float* ad = sw + TW_ATT_D;
+#pragma unroll
+  for (int cc = 0; cc < 32; ++cc) {
+    asrc = __fadd_rn(asrc, __fmul_rn(h[cc], as[cc]));
+    adst = __fadd_rn(adst, __fmul_rn(h[cc], ad[cc]));
+  }
+}
+
+// LeakyReLU(0.2) attention logit of edge j -> i
+__device__ __forceinline__ float gat_logit(float asrc_j, float adst_i) {
+  const float z = __fadd_rn(asrc_j, adst_i);
+  return z > 0.0f ? z : __fmul_rn(z, 0.2f);
+}
+
+// out += alpha * h_j  (message rounded, then accumulated: torch scatter-add order)
+__device__ __forceinline__ void gat_accumulate(float (&out)[32], float alpha, const float4* __restrict__ hj) {
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4) {
+    const float4 v = hj[c4];
+    out[4 * c4 + 0] = __fadd_rn(out[4 * c4 + 0], __fmul_rn(alpha, v.x));
+    out[4 * c4 + 1] = __fadd_rn(out[4 * c4 + 1], __fmul_rn(alpha, v.y));
+    out[4 * c4 + 2] = __fadd_rn(out[4 * c4 + 2], __fmul_rn(alpha, v.z));
+    out[4 * c4 + 3] = __fadd_rn(out[4 * c4 + 3], __fmul_rn(alpha, v.w));
+  }
+}
+
+// (aggregate + conv1.bias) -> tanh -> lin1 -> ReLU -> lin2; returns argmax (first maximum wins)
+__device__ __forceinline__ int gat_head(float (&a1)[32], const float* __restrict__ sw, float (&q)[9]) {
+  const float* b0 = sw + TW_B0;
+#pragma unroll
+  for (int cc = 0; cc < 32; ++cc) a1[cc] = tanhf(__fadd_rn(a1[cc], b0[cc]));
+
+  float a2[32];
+#pragma unroll
+  for (int cc = 0; cc < 32; ++cc) a2[cc] = 0.0f;
+  const float4* w1 = reinterpret_cast<const float4*>(sw + TW_W1T);
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const float4 w = w1[k * 8 + c4];
+      a2[4 * c4 + 0] = fmaf(a1[k], w.x, a2[4 * c4 + 0]);
+      a2[4 * c4 + 1] = fmaf(a1[k], w.y, a2[4 * c4 + 1]);
+      a2[4 * c4 + 2] = fmaf(a1[k], w.z, a2[4 * c4 + 2]);
+      a2[4 * c4 + 3] = fmaf(a1[k], w.w, a2[4 * c4 + 3]);
+    }
+  }
+  const float* b1 = sw + TW_B1;
+#pragma unroll
+  for (int cc = 0; cc < 32; ++cc) a2[cc] = fmaxf(__fadd_rn(a2[cc], b1[cc]), 0.0f);
+
+  float qq[kW2Pad];
+#pragma unroll
+  for (int a = 0; a < kW2Pad; ++a) qq[a] = 0.0f;
+  const float4* w2 = reinterpret_cast<const float4*>(sw + TW_W2T);
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+#pragma unroll
+    for (int a4 = 0; a4 < 3; ++a4) {
+      const float4 w = w2[k * 3 + a4];
+      qq[4 * a4 + 0] = fmaf(a2[k], w.x, qq[4 * a4 + 0]);
+      qq[4 * a4 + 1] = fmaf(a2[k], w.y, qq[4 * a4 + 1]);
+      qq[4 * a4 + 2] = fmaf(a2[k], w.z, qq[4 * a4 + 2]);
+      qq[4 * a4 + 3] = fmaf(a2[k], w.w, qq[4 * a4 + 3]);
+    }
+  }
+  const float* b2 = sw + TW_B2;
+  float best = 0.0f;
+  int action = 0;
+#pragma unroll
+  for (int a = 0; a < 9; ++a) {
+    q[a] = __fadd_rn(qq[a], b2[a]);
+    if (a == 0 || q[a] > best) {
+      best = q[a];
+      action = a;
+    }
+  }
+  return action;
+}
+
+}  // namespace swarm
+#endif

@@ -1,0 +1,100 @@
+// swarm_device.cuh -- device-side building blocks shared by every kernel of the swarm hot path.
+//
+// Rounding discipline: the reference executes the world step as a chain of separately
+// rounded float32 torch ops, with the 2-norm evaluated as sqrtf(fmaf(y, y, x*x)).  All physics / reward
+// arithmetic below therefore uses the __f*_rn intrinsics (never contracted into FMAs by nvcc) in exactly
+// that order, which makes positions, velocities, rewards, contact masks and kNN edge lists bit-identical
+// to the CPU oracle whenever no contact force is active (the contact magnitude goes through
+// logaddexp = log1p(exp(.)), whose CUDA and SLEEF implementations differ in the last ulp).
+#ifndef SWARM_DEVICE_CUH
+#define SWARM_DEVICE_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/swarm_b200.h"
+
+namespace swarm {
+
+// ---- 2-norm exactly like torch.linalg.vector_norm over two floats -------------------------------
+__device__ __forceinline__ float norm2(float x, float y) {
+  return __fsqrt_rn(__fmaf_rn(y, y, __fmul_rn(x, x)));
+}
+
+// ---- vmas Environment._set_action for discrete_action_nvec = [3, 3] -----------------------------
+// flat a -> (a / 3, a % 3); index 0 -> 0, 1 -> -1, 2 -> +1
+__device__ __forceinline__ float action_component(int idx) {
+  return idx == 0 ? 0.0f : (idx == 1 ? -1.0f : 1.0f);
+}
+__device__ __forceinline__ void decode_action(int a, float& ux, float& uy) {
+  ux = action_component(a / 3);
+  uy = action_component(a % 3);
+}
+
+// ---- vmas World._get_constraint_forces, sphere-sphere, force on the entity at (ax, ay) ----------
+// delta = a - b; dist_min = r_a + r_b; k = contact_margin
+//   pen   = logaddexp(0, (dist_min - d) / k) * k
+//   force = ((collision_force * delta) / (d > 0 ? d : 1e-8)) * pen; 0 if d < 1e-6 or d > dist_min
+// Returns true when the pair passes vmas' collides() pre-filter (d <= dist_min), i.e. when the force
+// (possibly zero) is added to the accumulator.
+__device__ __forceinline__ bool contact_force(float ax, float ay, float bx, float by, float dist_min,
+                                              float collision_force, float k, float& fx, float& fy) {
+  const float dx = __fsub_rn(ax, bx);
+  const float dy = __fsub_rn(ay, by);
+  const float d = norm2(dx, dy);
+  fx = 0.0f;
+  fy = 0.0f;
+  if (!(d <= dist_min)) return false;
+  if (d < 1e-6f) return true;
+  const float z = __fdiv_rn(__fsub_rn(dist_min, d), k);
+  // torch.logaddexp(0, z) = max(0, z) + log1p(exp(-|0 - z|));  z >= 0 here
+  const float pen = __fmul_rn(__fadd_rn(fmaxf(0.0f, z), log1pf(expf(-fabsf(z)))), k);
+  const float dd = d > 0.0f ? d : 1e-8f;
+  fx = __fmul_rn(__fdiv_rn(__fmul_rn(collision_force, dx), dd), pen);
+  fy = __fmul_rn(__fdiv_rn(__fmul_rn(collision_force, dy), dd), pen);
+  return true;
+}
+
+// ---- vmas World._integrate_state (substeps = 1, mass = 1) ----------------------------------------
+__device__ __forceinline__ void integrate(float4& s, float fx, float fy, float dt, float one_minus_drag) {
+  float vx = __fmul_rn(s.z, one_minus_drag);
+  float vy = __fmul_rn(s.w, one_minus_drag);
+  vx = __fadd_rn(vx, __fmul_rn(__fdiv_rn(fx, 1.0f), dt));
+  vy = __fadd_rn(vy, __fmul_rn(__fdiv_rn(fy, 1.0f), dt));
+  s.x = __fadd_rn(s.x, __fmul_rn(vx, dt));
+  s.y = __fadd_rn(s.y, __fmul_rn(vy, dt));
+  s.z = vx;
+  s.w = vy;
+}
+
+// ---- scenario reward pieces ------------------------------------------------------------------------
+// distance_to_goal_reward (go_to:117-122, oa:138-144): returns ||p - goal||
+__device__ __forceinline__ float goal_distance(float x, float y, const SwarmConfig& c) {
+  return norm2(__fsub_rn(x, c.goal_x), __fsub_rn(y, c.goal_y));
+}
+// world.get_distance(agent, obstacle): centre distance minus the two radii, one after the other
+__device__ __forceinline__ float obstacle_distance(float x, float y, const SwarmConfig& c) {
+  const float d = norm2(__fsub_rn(x, c.obstacle_x), __fsub_rn(y, c.obstacle_y));
+  return __fsub_rn(__fsub_rn(d, c.agent_radius), c.landmark_radius);
+}
+// ObstacleAvoidanceScenario.reward (oa:135-152): -d_goal + w * (-(pen - d_obs) if d_obs <= pen else 0)
+__device__ __forceinline__ float oa_reward(float d_goal, float d_obs, const SwarmConfig& c, uint8_t& flags) {
+  float avoid = 0.0f;
+  if (d_obs <= c.penalty_distance) {
+    avoid = -__fsub_rn(c.penalty_distance, d_obs);
+    flags |= SWARM_FLAG_PENALTY;
+  }
+  if (d_obs <= c.hit_distance) flags |= SWARM_FLAG_HIT;
+  return __fadd_rn(-d_goal, __fmul_rn(c.obstacle_weight, avoid));
+}
+
+// ---- generate_grid (go_to:52-80): offsets are Python doubles, cast to f32, added to the f32 centre ----
+__device__ __forceinline__ float2 grid_position(float cx, float cy, int i, int cols, int rows, double spacing) {
+  const int r = i / cols, q = i % cols;
+  const double ox = ((double)q - (double)(cols - 1) / 2.0) * spacing;
+  const double oy = ((double)r - (double)(rows - 1) / 2.0) * spacing;
+  return make_float2(__fadd_rn(cx, (float)ox), __fadd_rn(cy, (float)oy));
+}
+
+}  // namespace swarm
+#endif  // SWARM_DEVICE_CUH

@@ -1,0 +1,113 @@
+// tile_kernels.cuh -- parameter block + shared-memory layout of the "env tile" kernel family
+// (one thread per agent, floor(threads / N) whole envs per CTA, N <= 128).
+#ifndef SWARM_TILE_KERNELS_CUH
+#define SWARM_TILE_KERNELS_CUH
+
+#include "swarm_device.cuh"
+
+namespace swarm {
+
+constexpr int kTileThreads = 128;
+constexpr int kHPad = 36;        // padded row of the hidden tile (floats); keeps float4 alignment, spreads banks
+constexpr int kW2Pad = 12;       // lin2 rows padded 9 -> 12 so a k-slice is three float4
+
+// kernel-side weight layout in shared memory (k-major = transposed, so one float4 feeds 4 output channels)
+enum {
+  TW_W0T = 0,                      // [7][32]
+  TW_ATT_S = TW_W0T + 7 * 32,      // [32]
+  TW_ATT_D = TW_ATT_S + 32,        // [32]
+  TW_B0 = TW_ATT_D + 32,           // [32]
+  TW_W1T = TW_B0 + 32,             // [32][32]
+  TW_B1 = TW_W1T + 32 * 32,        // [32]
+  TW_W2T = TW_B1 + 32,             // [32][12]
+  TW_B2 = TW_W2T + 32 * kW2Pad,    // [12]
+  TW_COUNT = TW_B2 + kW2Pad
+};
+
+// global packed weights (state-dict order) -> shared, transposed to k-major
+__device__ __forceinline__ void stage_weights(const float* __restrict__ g, float* __restrict__ s, int tid, int nthreads) {
+  for (int idx = tid; idx < TW_COUNT; idx += nthreads) {
+    float v = 0.0f;
+    if (idx < TW_ATT_S) {                       // W0T[k][c] = conv1.lin.weight[c][k]
+      const int k = idx / 32, c = idx % 32;
+      v = g[SWARM_W_CONV_LIN + c * 7 + k];
+    } else if (idx < TW_ATT_D) {
+      v = g[SWARM_W_ATT_SRC + (idx - TW_ATT_S)];
+    } else if (idx < TW_B0) {
+      v = g[SWARM_W_ATT_DST + (idx - TW_ATT_D)];
+    } else if (idx < TW_W1T) {
+      v = g[SWARM_W_CONV_BIAS + (idx - TW_B0)];
+    } else if (idx < TW_B1) {                   // W1T[k][c] = lin1.weight[c][k]
+      const int r = idx - TW_W1T, k = r / 32, c = r % 32;
+      v = g[SWARM_W_LIN1 + c * 32 + k];
+    } else if (idx < TW_W2T) {
+      v = g[SWARM_W_LIN1_BIAS + (idx - TW_B1)];
+    } else if (idx < TW_B2) {                   // W2T[k][a] = lin2.weight[a][k], a padded to 12
+      const int r = idx - TW_W2T, k = r / kW2Pad, a = r % kW2Pad;
+      v = a < 9 ? g[SWARM_W_LIN2 + a * 32 + k] : 0.0f;
+    } else {
+      const int a = idx - TW_B2;
+      v = a < 9 ? g[SWARM_W_LIN2_BIAS + a] : 0.0f;
+    }
+    s[idx] = v;
+  }
+}
+
+enum TileMode { MODE_ROLLOUT = 0, MODE_FORWARD = 1, MODE_STEP = 2, MODE_GRAPH = 3 };
+
+struct TileParams {
+  SwarmConfig cfg;
+  const float* weights;          // packed state-dict order (SWARM_W_*)
+  const float* state_in;
+  float* state_out;
+  const int32_t* actions_in;     // MODE_STEP: [B*N]; MODE_ROLLOUT: optional forced actions [ticks][B*N]
+  float* returns;                // MODE_ROLLOUT: [B*N] +=
+  int32_t* hits;                 // MODE_ROLLOUT: [B] +=
+  SwarmTrace trace;              // MODE_ROLLOUT, optional
+  float* q_out;                  // MODE_FORWARD
+  int32_t* act_out;              // MODE_FORWARD
+  float* rewards_out;            // MODE_STEP
+  uint8_t* flags_out;            // MODE_STEP
+  uint32_t* contact_out;         // MODE_STEP
+  float* obs_out;                // MODE_STEP
+  float* dist_out;               // MODE_STEP
+  int32_t* edges_out;            // MODE_GRAPH
+  int32_t* nbr_out;              // MODE_GRAPH
+  int32_t ticks;
+  int32_t epb;                   // envs per block
+  int32_t maxdeg;                // max in-degree of the graph (rows of the per-thread edge scratch)
+  int32_t edges_per_env;
+  float one_minus_drag;
+  float dmin_aa, dmin_ao;        // contact distances agent-agent / agent-obstacle (sum of radii, f32 add)
+  float qmax_aa, qmax_ao;        // largest squared distance whose rounded sqrt is <= dmin (exact pre-filter)
+};
+
+// byte offsets of the dynamic shared memory regions
+struct TileLayout {
+  int w, st, h, asrc, wt, inl, deg, kv, ki, nbr, red, total;
+};
+
+__host__ __device__ inline int tile_align16(int x) { return (x + 15) & ~15; }
+
+__host__ __device__ inline TileLayout tile_layout(int mode, int threads, int n, int k, int maxdeg, int graph_mode) {
+  TileLayout L;
+  int off = 0;
+  const bool q = (mode == MODE_ROLLOUT || mode == MODE_FORWARD);
+  const bool knn = (graph_mode == SWARM_GRAPH_KNN) && (q || mode == MODE_GRAPH);
+  L.w = off;    off = tile_align16(off + (q ? TW_COUNT * 4 : 0));
+  L.st = off;   off = tile_align16(off + 2 * threads * 16);
+  L.h = off;    off = tile_align16(off + (q ? threads * kHPad * 4 : 0));
+  L.asrc = off; off = tile_align16(off + (q ? threads * 4 : 0));
+  L.wt = off;   off = tile_align16(off + (q ? maxdeg * threads * 4 : 0));
+  L.inl = off;  off = tile_align16(off + (q ? maxdeg * threads : 0));
+  L.deg = off;  off = tile_align16(off + (q ? threads : 0));
+  L.kv = off;   off = tile_align16(off + (knn ? n * threads * 4 : 0));
+  L.ki = off;   off = tile_align16(off + (knn ? n * threads : 0));
+  L.nbr = off;  off = tile_align16(off + (knn ? k * threads : 0));
+  L.red = off;  off = tile_align16(off + threads * 4);
+  L.total = off;
+  return L;
+}
+
+}  // namespace swarm
+#endif

@@ -1,0 +1,110 @@
+"""The Q-network seam: ``GCN`` with the reference's nn.Module interface and state-dict key set.
+
+Mirrors src/training/train_gcn_dqn.py:50-70 -- ``GCN(input_dim, hidden_dim, output_dim)`` holding
+``conv1 = GATConv(input_dim, hidden_dim, add_self_loops=False, bias=True)``, ``lin1``, ``lin2`` and
+``forward(data)`` reading ``data.x`` / ``data.edge_index``.  Parameter names, shapes and initialisation
+(including the order and count of RNG draws) match torch_geometric 2.5.3 + torch so that
+the shipped ``data/models/*.pth`` load and seeded runs consume the generator identically.  The forward
+(and backward) arithmetic runs in libswarm_b200.so; there is no PyTorch implementation behind it.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+
+_FEAT, _HIDDEN, _ACTIONS = 7, 32, 9
+
+
+def _glorot(t: torch.Tensor) -> None:
+    # torch_geometric.nn.inits.glorot: U(-a, a), a = sqrt(6 / (fan_in + fan_out)) on the last two dims
+    a = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
+    t.data.uniform_(-a, a)
+
+
+class _Projection(nn.Module):
+    """torch_geometric Linear(bias=False, weight_initializer='glorot'): key ``weight`` [out, in]."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        _glorot(self.weight)
+
+
+class GATConv(nn.Module):
+    """Parameter container for GATConv(in, out, heads=1, add_self_loops=False, bias=True)
+    (train:53).  Keys: ``att_src`` [1,1,out], ``att_dst`` [1,1,out], ``bias`` [out], ``lin.weight``
+    [out,in].  The projection is initialised twice, like torch_geometric (Linear.__init__ followed by
+    GATConv.reset_parameters)."""
+
+    def __init__(self, in_channels: int, out_channels: int, heads: int = 1, add_self_loops: bool = False,
+                 bias: bool = True):
+        super().__init__()
+        if heads != 1 or add_self_loops or not bias:
+            raise NotImplementedError("the swarm_b200 kernels implement GATConv(heads=1, add_self_loops=False, bias=True)")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin = _Projection(in_channels, out_channels)
+        self.att_src = nn.Parameter(torch.empty(1, 1, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, 1, out_channels))
+        self.bias = nn.Parameter(torch.empty(out_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        self.lin.reset_parameters()
+        _glorot(self.att_src)
+        _glorot(self.att_dst)
+        self.bias.data.zero_()
+
+
+class _GatQFunction(torch.autograd.Function):
+    """packed weights f32[1673], x f32[n,7], CSR-by-target -> Q f32[n,9] through the CUDA kernels."""
+
+    @staticmethod
+    def forward(ctx, packed, x, row_ptr, src):
+        q = ops.gatq_forward_csr(packed, x, row_ptr, src)
+        ctx.save_for_backward(packed, x, row_ptr, src)
+        return q
+
+    @staticmethod
+    def backward(ctx, grad_q):
+        packed, x, row_ptr, src = ctx.saved_tensors
+        from . import dqn
+        grad_w = dqn.gatq_backward_csr(packed, x, row_ptr, src, grad_q.contiguous())
+        return grad_w, None, None, None
+
+
+class GCN(nn.Module):
+    """train_gcn_dqn.py:50-70.  ``forward(data)`` accepts anything with ``x`` f32[n,7] and ``edge_index``
+    int64[2,E] (a ``Data`` / ``Batch`` of this package or of torch_geometric)."""
+
+    def __init__(self, input_dim: int = _FEAT, hidden_dim: int = _HIDDEN, output_dim: int = _ACTIONS):
+        super().__init__()
+        if (input_dim, hidden_dim, output_dim) != (_FEAT, _HIDDEN, _ACTIONS):
+            raise NotImplementedError(
+                f"the swarm_b200 kernels are specialised for GCN({_FEAT}, {_HIDDEN}, {_ACTIONS}) "
+                f"(train_gcn_dqn.py:79-82), got ({input_dim}, {hidden_dim}, {output_dim})")
+        self.conv1 = GATConv(input_dim, hidden_dim, add_self_loops=False, bias=True)
+        self.lin1 = nn.Linear(hidden_dim, hidden_dim)
+        self.lin2 = nn.Linear(hidden_dim, output_dim)
+
+    def packed_weights(self) -> torch.Tensor:
+        """float[1673] in the C ABI's SWARM_W_* order (differentiable w.r.t. the parameters)."""
+        return torch.cat([self.conv1.lin.weight.reshape(-1), self.conv1.att_src.reshape(-1),
+                          self.conv1.att_dst.reshape(-1), self.conv1.bias.reshape(-1),
+                          self.lin1.weight.reshape(-1), self.lin1.bias.reshape(-1),
+                          self.lin2.weight.reshape(-1), self.lin2.bias.reshape(-1)])
+
+    def forward(self, data) -> torch.Tensor:
+        x, edge_index = data.x, data.edge_index
+        if not x.is_cuda:
+            raise _lib.SwarmError("GCN.forward runs on CUDA tensors only (swarm_b200 has no CPU fallback); "
+                                  "move the model and the graph to a B200")
+        row_ptr, src, _ = ops.csr_from_edges(edge_index, x.shape[0])
+        return _GatQFunction.apply(self.packed_weights(), x.contiguous(), row_ptr, src)

@@ -1,0 +1,174 @@
+"""Thin tensor-level wrappers over the C ABI (include/swarm_b200.h).
+
+Tensors are only containers for device memory here: every function validates shapes/dtypes, passes raw
+pointers plus the current CUDA stream to libswarm_b200.so and returns the output tensors.  Nothing
+is computed in PyTorch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import SwarmConfig, SwarmTrace, check, lib, ptr, stream_ptr
+
+
+def make_config(scenario: int, num_envs: int, n_agents: int, graph_mode: int = _lib.GRAPH_COMPLETE,
+                knn_k: int = 10) -> SwarmConfig:
+    cfg = _lib.default_config(scenario, num_envs, n_agents)
+    cfg.graph_mode = graph_mode
+    cfg.knn_k = knn_k
+    return cfg
+
+
+def clone_config(cfg: SwarmConfig, **updates) -> SwarmConfig:
+    out = SwarmConfig()
+    C.memmove(C.byref(out), C.byref(cfg), C.sizeof(SwarmConfig))
+    for k, v in updates.items():
+        setattr(out, k, v)
+    return out
+
+
+def edges_per_env(cfg: SwarmConfig) -> int:
+    return int(lib().swarm_edges_per_env(C.byref(cfg)))
+
+
+def _expect(t: torch.Tensor, dtype: torch.dtype, numel: int, name: str) -> None:
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if t.numel() != numel:
+        raise ValueError(f"{name}: expected {numel} elements, got {t.numel()}")
+
+
+def reset_grid(cfg: SwarmConfig, centers: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """centers f32[B,2] -> state f32[B,N,4]."""
+    B, N = cfg.num_envs, cfg.n_agents
+    _expect(centers, torch.float32, B * 2, "centers")
+    state = out if out is not None else torch.empty(B, N, 4, dtype=torch.float32, device=centers.device)
+    _expect(state, torch.float32, B * N * 4, "state")
+    check(lib().swarm_reset_grid(C.byref(cfg), ptr(centers), ptr(state), stream_ptr(centers.device)))
+    return state
+
+
+def sim_step(cfg: SwarmConfig, state: torch.Tensor, actions: torch.Tensor, *, state_out: Optional[torch.Tensor] = None,
+             want_obs: bool = True, want_contact: bool = False) -> Dict[str, torch.Tensor]:
+    """One world step.  state f32[B,N,4], actions int32[B,N] -> dict(state, rewards, flags, [contact], [obs])."""
+    B, N = cfg.num_envs, cfg.n_agents
+    _expect(state, torch.float32, B * N * 4, "state")
+    _expect(actions, torch.int32, B * N, "actions")
+    dev = state.device
+    out_state = state_out if state_out is not None else torch.empty_like(state)
+    rewards = torch.empty(B, N, dtype=torch.float32, device=dev)
+    flags = torch.empty(B, N, dtype=torch.uint8, device=dev)
+    contact = torch.empty(B, N, dtype=torch.int32, device=dev) if want_contact else None
+    obs = torch.empty(B, N, 6, dtype=torch.float32, device=dev) if want_obs else None
+    dist = torch.empty(B, N, 2, dtype=torch.float32, device=dev)
+    check(lib().swarm_sim_step(C.byref(cfg), ptr(state), ptr(actions), ptr(out_state), ptr(rewards), ptr(flags),
+                               ptr(contact), ptr(obs), ptr(dist), stream_ptr(dev)))
+    res = {"state": out_state, "rewards": rewards, "flags": flags, "dist": dist}
+    if contact is not None:
+        res["contact"] = contact
+    if obs is not None:
+        res["obs"] = obs
+    return res
+
+
+def graph_build(cfg: SwarmConfig, state: torch.Tensor, want_neighbours: bool = False
+                ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """edges int32[B,2,E] (env-local ids) and, for kNN, the topk index table int32[B,N,k]."""
+    B, N = cfg.num_envs, cfg.n_agents
+    _expect(state, torch.float32, B * N * 4, "state")
+    E = edges_per_env(cfg)
+    edges = torch.empty(B, 2, E, dtype=torch.int32, device=state.device)
+    nbr = None
+    if want_neighbours and cfg.graph_mode == _lib.GRAPH_KNN:
+        nbr = torch.empty(B, N, cfg.knn_k, dtype=torch.int32, device=state.device)
+    check(lib().swarm_graph_build(C.byref(cfg), ptr(state), ptr(edges), ptr(nbr), stream_ptr(state.device)))
+    return edges, nbr
+
+
+def gatq_forward(cfg: SwarmConfig, weights: torch.Tensor, state: torch.Tensor, want_q: bool = True,
+                 want_actions: bool = True) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """Structured GCN.forward on the per-env graph: q f32[B,N,9], greedy actions int32[B,N]."""
+    B, N = cfg.num_envs, cfg.n_agents
+    _expect(state, torch.float32, B * N * 4, "state")
+    _expect(weights, torch.float32, _lib.W_COUNT, "weights")
+    dev = state.device
+    q = torch.empty(B, N, 9, dtype=torch.float32, device=dev) if want_q else None
+    act = torch.empty(B, N, dtype=torch.int32, device=dev) if want_actions else None
+    check(lib().swarm_gatq_forward(C.byref(cfg), ptr(weights), ptr(state), ptr(q), ptr(act), stream_ptr(dev)))
+    return q, act
+
+
+def rollout(cfg: SwarmConfig, weights: torch.Tensor, state: torch.Tensor, ticks: int, *,
+            forced_actions: Optional[torch.Tensor] = None, returns: Optional[torch.Tensor] = None,
+            hits: Optional[torch.Tensor] = None, trace: Optional[Dict[str, bool]] = None
+            ) -> Dict[str, torch.Tensor]:
+    """Fused greedy rollout, in place on ``state``.  ``trace`` names the per-tick records to keep
+    (any of state, actions, q, rewards, flags, contact, edges, dist)."""
+    B, N = cfg.num_envs, cfg.n_agents
+    _expect(state, torch.float32, B * N * 4, "state")
+    _expect(weights, torch.float32, _lib.W_COUNT, "weights")
+    dev = state.device
+    if forced_actions is not None:
+        _expect(forced_actions, torch.int32, ticks * B * N, "forced_actions")
+    if returns is None:
+        returns = torch.zeros(B, N, dtype=torch.float32, device=dev)
+    if hits is None:
+        hits = torch.zeros(B, dtype=torch.int32, device=dev)
+    _expect(returns, torch.float32, B * N, "returns")
+    _expect(hits, torch.int32, B, "hits")
+    out: Dict[str, torch.Tensor] = {"state": state, "returns": returns, "hits": hits}
+    tr = None
+    if trace:
+        tr = SwarmTrace()
+        E = edges_per_env(cfg)
+        shapes = {"state": ((ticks, B, N, 4), torch.float32), "actions": ((ticks, B, N), torch.int32),
+                  "q": ((ticks, B, N, 9), torch.float32), "rewards": ((ticks, B, N), torch.float32),
+                  "flags": ((ticks, B, N), torch.uint8), "contact": ((ticks, B, N), torch.int32),
+                  "edges": ((ticks, B, 2, E), torch.int32), "dist": ((ticks, B, N, 2), torch.float32)}
+        for name, on in trace.items():
+            if not on:
+                continue
+            shape, dt = shapes[name]
+            t = torch.empty(shape, dtype=dt, device=dev)
+            setattr(tr, name, ptr(t))
+            out["trace_" + name] = t
+    check(lib().swarm_rollout(C.byref(cfg), ptr(weights), ptr(state), int(ticks), ptr(forced_actions), ptr(returns),
+                              ptr(hits), C.byref(tr) if tr is not None else None, stream_ptr(dev)))
+    return out
+
+
+def csr_from_edges(edge_index: torch.Tensor, n_nodes: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """edge_index int64[2,E] -> (row_ptr int32[n+1], src int32[E], perm int32[E]), edges grouped by target,
+    each group in edge-list order."""
+    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise TypeError("edge_index must be int64[2, E]")
+    dev = edge_index.device
+    E = edge_index.shape[1]
+    ei = edge_index.contiguous()
+    row_ptr = torch.empty(n_nodes + 1, dtype=torch.int32, device=dev)
+    src = torch.empty(E, dtype=torch.int32, device=dev)
+    perm = torch.empty(E, dtype=torch.int32, device=dev)
+    wb = int(lib().swarm_csr_workspace_bytes(n_nodes, E))
+    ws = torch.empty(max(wb, 1), dtype=torch.uint8, device=dev)
+    check(lib().swarm_csr_from_edges(n_nodes, E, ptr(ei[0]), ptr(ei[1]), ptr(row_ptr), ptr(src), ptr(perm), ptr(ws), wb,
+                                     stream_ptr(dev)))
+    return row_ptr, src, perm
+
+
+def gatq_forward_csr(weights: torch.Tensor, x: torch.Tensor, row_ptr: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    """Generic GCN.forward: x f32[n,7] + CSR-by-target -> q f32[n,9]."""
+    n = x.shape[0]
+    _expect(x, torch.float32, n * 7, "x")
+    _expect(weights, torch.float32, _lib.W_COUNT, "weights")
+    _expect(row_ptr, torch.int32, n + 1, "row_ptr")
+    dev = x.device
+    q = torch.empty(n, 9, dtype=torch.float32, device=dev)
+    wb = int(lib().swarm_gatq_workspace_bytes(n))
+    ws = torch.empty(max(wb, 1), dtype=torch.uint8, device=dev)
+    check(lib().swarm_gatq_forward_csr(n, ptr(weights), ptr(x.contiguous()), ptr(row_ptr), ptr(src), ptr(q), ptr(ws), wb,
+                                       stream_ptr(dev)))
+    return q
