@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/s of the swarm hot path (world step + per-step graph + GAT-Q forward + greedy
+argmax) on N B200s, next to the reference-structured CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1] / SURVEY.md 8d "C2"): ObstacleAvoidance, 12 agents, 4 096 envs per GPU,
+complete graph + (0,0) self loop (E = 133), weights of experiment_ObstacleAvoidance-seed_0, start centres
+(0.6,-0.6) + N(0, 0.1^2) from torch.Generator(cpu).manual_seed(rank).  One *step* = one 100-tick greedy
+episode of all envs: reset_grid launch + one fused rollout launch (state stays on chip for the 100 ticks).
+``value`` is timed with the inputs resident in HBM; ``e2e`` goes through the public API with pinned host
+buffers (centres in, per-agent returns + per-env hit counts out) inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_AGENTS = 12
+ENVS_PER_GPU = 4096
+TICKS = 100
+BYTES_PER_AGENT_STEP = 40.0       # fused step+graph+Q without a Q dump: state in/out 32 B, action 4 B, reward 4 B
+FLOPS_PER_AGENT_STEP = 4200.0     # N = 12, complete graph
+METRIC = "agent-steps/s (VMAS step + graph + GNN-Q fwd)"
+
+
+def load_weights():
+    models = np.load(os.path.join(ROOT, "tests", "golden", "models.npz"))
+    pre = "ObstacleAvoidance/0/"
+    return {k[len(pre):]: torch.from_numpy(models[k]) for k in models.files if k.startswith(pre)}
+
+
+def draw_centers(seed: int, num_envs: int) -> torch.Tensor:
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.tensor([0.6, -0.6]) + 0.1 * torch.randn(num_envs, 2, generator=g)
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks line")
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [c for c in sm if c >= 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arms (oracle port of the reference's per-tick loop, num_envs = 1)
+# ----------------------------------------------------------------------------------------------
+def _cpu_episode(args):
+    """One greedy episode of the single-env oracle; returns (agent_steps, seconds)."""
+    seed, ticks = args
+    torch.set_num_threads(1)
+    from oracle import swarm_oracle as so
+    params = load_weights()
+    world = so.OracleWorld(so.OBSTACLE_AVOIDANCE, N_AGENTS, random=True)
+    torch.manual_seed(seed)
+    obs = world.reset()
+    ei = so.graph_complete(N_AGENTS)
+    t0 = time.perf_counter()
+    for _ in range(ticks):
+        x = so.node_features(obs)
+        with torch.no_grad():
+            actions = torch.argmax(so.gatq_forward(params, x, so.graph_complete(N_AGENTS)), dim=1)
+        world.step(actions)
+        obs = world.observations()
+    return N_AGENTS * ticks, time.perf_counter() - t0
+
+
+def cpu_baseline_single(target_seconds: float = 12.0):
+    done, secs, ep = 0, 0.0, 0
+    while secs < target_seconds:
+        n, s = _cpu_episode((ep, TICKS))
+        done += n
+        secs += s
+        ep += 1
+    return {"value": done / secs, "unit": "agent-steps/s", "cores": 1, "kind": "port",
+            "sample": f"{ep} greedy 100-tick episodes of one 12-agent ObstacleAvoidance env (complete graph), "
+                      f"oracle/swarm_oracle.py, torch CPU 1 thread, {secs:.1f} s"}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference-structured CPU path (oracle port; vmas / torch_geometric are not
+    installable here) on all host cores, one single-env process per core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    ticks = 25                                            # bounded sample: a quarter episode per process per step
+    with ctx.Pool(cores) as pool:
+        for w in range(args.warmup):
+            pool.map(_cpu_episode, [(1000 * w + i, ticks) for i in range(cores)])
+        t0 = time.perf_counter()
+        total = 0
+        for s in range(args.steps):
+            res = pool.map(_cpu_episode, [(1000 * (s + 10) + i, ticks) for i in range(cores)])
+            total += sum(r[0] for r in res)
+        dt = time.perf_counter() - t0
+    value = total / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+                             "sample": f"per step: {cores} processes x {ticks} ticks of one 12-agent env each "
+                                       "(reference-structured per-tick loop, oracle/swarm_oracle.py)"},
+            "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus: int):
+    return {"workload": "ObstacleAvoidance N=12, 4096 envs/GPU, complete graph + self loop (E=133), greedy GAT-Q "
+                        "policy (experiment_ObstacleAvoidance-seed_0), one step = 100-tick episode of all envs",
+            "envs_per_gpu": ENVS_PER_GPU, "n_agents": N_AGENTS, "ticks_per_step": TICKS, "graph": "complete",
+            "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"env-sharded x{n_gpus}, no collective"}
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import swarm_b200 as sb
+    from swarm_b200 import ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, N, T = ENVS_PER_GPU, N_AGENTS, TICKS
+    cfg = ops.make_config(sb._lib.SCENARIO_OBSTACLE_AVOIDANCE, B, N, sb._lib.GRAPH_COMPLETE)
+    weights = sb.pack_weights(load_weights(), dev)
+    centers_host = draw_centers(rank, B).pin_memory()
+    centers = centers_host.to(dev)
+    state = torch.empty(B, N, 4, device=dev)
+    returns = torch.zeros(B, N, device=dev)
+    hits = torch.zeros(B, dtype=torch.int32, device=dev)
+    returns_host = torch.empty(B, N).pin_memory()
+    hits_host = torch.empty(B, dtype=torch.int32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step_resident():
+        ops.reset_grid(cfg, centers, out=state)
+        ops.rollout(cfg, weights, state, T, returns=returns, hits=hits)
+
+    def step_e2e():
+        c = centers_host.to(dev, non_blocking=True)
+        returns.zero_()
+        hits.zero_()
+        ops.reset_grid(cfg, c, out=state)
+        ops.rollout(cfg, weights, state, T, returns=returns, hits=hits)
+        returns_host.copy_(returns, non_blocking=True)
+        hits_host.copy_(hits, non_blocking=True)
+        stream.synchronize()
+        return float(returns_host[0, 0])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, kernel_events=None):
+        evs = []
+        barrier()
+        for _ in range(steps):
+            flush.zero_()                                    # L2 flush, outside the timed events
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            fn()
+            b.record(stream)
+            evs.append((a, b))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+        step_e2e()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_res = timed(step_resident, args.steps)
+
+    # the dominant kernel alone (rollout launch), CUDA events on the launching stream
+    kev = []
+    barrier()
+    for _ in range(args.steps):
+        ops.reset_grid(cfg, centers, out=state)
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        ops.rollout(cfg, weights, state, T, returns=returns, hits=hits)
+        b.record(stream)
+        kev.append((a, b))
+    barrier()
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    agent_steps = world * B * N * T * args.steps
+    value = agent_steps / (ms_res * 1e-3)
+    e2e_value = agent_steps / (ms_e2e * 1e-3)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak_gbs, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = BYTES_PER_AGENT_STEP * B * N * T / (kernel_ms * 1e-3) / 1e9
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    fp32_achieved = FLOPS_PER_AGENT_STEP * B * N * T / (kernel_ms * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+        "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": B * 2 * 4,
+                "d2h_bytes_per_step": B * N * 4 + B * 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": 2 * args.steps,
+        "roofline": {"kernel": "tile_kernel<MODE_ROLLOUT>", "bound": "hbm", "achieved": achieved, "peak": peak_gbs,
+                     "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                     "kernel_ms": kernel_ms,
+                     "note": "the fused rollout keeps state on chip for 100 ticks and is FP32-issue bound "
+                             "(SURVEY.md 8d); algorithmic bytes = 40 B/agent-step"},
+        "roofline_fp32": {"achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_achieved / fp32_peak,
+                          "flops_per_agent_step": FLOPS_PER_AGENT_STEP,
+                          "peak_source": f"148 SMs x 128 FMA lanes x 2 x {sm_mhz:.0f} MHz (sampled under load)"},
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline_single()
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
