@@ -7,6 +7,7 @@ through the ``swarm_b200`` alias module at the repository root (``import swarm_b
 """
 from . import _build, _lib, ops                                   # noqa: F401
 from ._lib import SwarmConfig, SwarmError, pack_weights, unpack_weights   # noqa: F401
+from .dqn import DQNTrainer, GraphReplayBuffer, set_seed          # noqa: F401
 from .env import Environment, make_env                            # noqa: F401
 from .gcn import GCN, GATConv                                     # noqa: F401
 from .graph import Batch, Data, create_graph_from_observations    # noqa: F401
@@ -14,4 +15,4 @@ from .scenarios import BaseScenario, GoToPositionScenario, ObstacleAvoidanceScen
 
 __all__ = ["make_env", "Environment", "GCN", "GATConv", "Data", "Batch", "create_graph_from_observations",
            "BaseScenario", "GoToPositionScenario", "ObstacleAvoidanceScenario", "SwarmConfig", "SwarmError",
-           "pack_weights", "unpack_weights", "ops"]
+           "pack_weights", "unpack_weights", "ops", "DQNTrainer", "GraphReplayBuffer", "set_seed"]

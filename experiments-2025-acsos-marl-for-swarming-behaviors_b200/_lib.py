@@ -45,6 +45,17 @@ class SwarmTrace(C.Structure):
                 ("flags", C.c_void_p), ("contact", C.c_void_p), ("edges", C.c_void_p), ("dist", C.c_void_p)]
 
 
+class SwarmReplay(C.Structure):
+    _fields_ = [("state", C.c_void_p), ("next_state", C.c_void_p), ("actions", C.c_void_p), ("rewards", C.c_void_p),
+                ("capacity", C.c_int64)]
+
+
+class SwarmRolloutOptions(C.Structure):
+    _fields_ = [("forced_actions", C.c_void_p), ("epsilon", C.c_float), ("rng_seed", C.c_uint64),
+                ("rng_tick0", C.c_int64), ("replay", C.POINTER(SwarmReplay)), ("replay_cursor", C.c_int64),
+                ("env_offset", C.c_int64)]
+
+
 class SwarmError(RuntimeError):
     pass
 
@@ -64,8 +75,19 @@ _SIGNATURES = {
     "swarm_gatq_forward_csr": (C.c_int, [C.c_int32] + [C.c_void_p] * 5 + [C.c_void_p, C.c_int64, C.c_void_p]),
     "swarm_csr_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64]),
     "swarm_csr_from_edges": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]),
-    "swarm_rollout": (C.c_int, [C.POINTER(SwarmConfig), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
-                                C.c_void_p, C.POINTER(SwarmTrace), C.c_void_p]),
+    "swarm_rollout": (C.c_int, [C.POINTER(SwarmConfig), C.c_void_p, C.c_void_p, C.c_int32,
+                                C.POINTER(SwarmRolloutOptions), C.c_void_p, C.c_void_p, C.POINTER(SwarmTrace),
+                                C.c_void_p]),
+    "swarm_replay_push": (C.c_int, [C.POINTER(SwarmConfig), C.POINTER(SwarmReplay), C.c_int64] + [C.c_void_p] * 5),
+    "swarm_replay_gather": (C.c_int, [C.POINTER(SwarmConfig), C.POINTER(SwarmReplay), C.c_void_p, C.c_int32]
+                            + [C.c_void_p] * 5),
+    "swarm_dqn_workspace_bytes": (C.c_int64, [C.POINTER(SwarmConfig), C.c_int32]),
+    "swarm_dqn_grad": (C.c_int, [C.POINTER(SwarmConfig), C.c_void_p, C.c_void_p, C.POINTER(SwarmReplay), C.c_void_p,
+                                 C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int64, C.c_void_p]),
+    "swarm_adam_clip_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
+                                       C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
 }
 
 

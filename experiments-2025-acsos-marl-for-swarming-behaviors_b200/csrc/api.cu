@@ -17,6 +17,19 @@ cudaError_t launch_csr_from_edges(int n, long long E, const int64_t* edge_src, c
 cudaError_t launch_gatq_csr(int n, const float* weights, const float* x, const int32_t* row_ptr, const int32_t* src,
                             float* q, float* rows, cudaStream_t stream);
 long long gatq_workspace_bytes(int n);
+cudaError_t launch_replay_push(const SwarmReplay& r, long long cursor, int B, int N, const float* state,
+                               const int32_t* actions, const float* rewards, const float* next_state,
+                               cudaStream_t stream);
+cudaError_t launch_replay_gather(const SwarmReplay& r, const int64_t* indices, int G, int N, float* state,
+                                 int32_t* actions, float* rewards, float* next_state, cudaStream_t stream);
+long long dqn_workspace_bytes(const SwarmConfig& c, int n_graphs);
+int dqn_smem_bytes(const SwarmConfig& c);
+cudaError_t launch_dqn_grad(const SwarmConfig& c, const float* w_online, const float* w_target, const SwarmReplay& batch,
+                            const int64_t* indices, int n_graphs, float gamma, float loss_scale, float* grad, float* loss,
+                            float* td, void* workspace, cudaStream_t stream);
+cudaError_t launch_adam_clip(float* w, const float* grad, float* m, float* v, long long step, double lr, double beta1,
+                             double beta2, double eps, double max_norm, float* target, float* grad_norm,
+                             cudaStream_t stream);
 
 namespace {
 thread_local std::string g_last_error;
@@ -205,7 +218,7 @@ int swarm_csr_from_edges(int32_t n_nodes, int64_t n_edges, const int64_t* edge_s
 }
 
 int swarm_rollout(const SwarmConfig* cfg, const float* weights, float* state, int32_t ticks,
-                  const int32_t* forced_actions, float* returns, int32_t* hits, const SwarmTrace* trace, void* stream) {
+                  const SwarmRolloutOptions* opts, float* returns, int32_t* hits, const SwarmTrace* trace, void* stream) {
   if (int rc = validate(cfg, true)) return rc;
   if (!weights || !state) return fail(SWARM_ERR_INVALID_ARG, "weights/state is NULL");
   if (ticks < 0) return fail(SWARM_ERR_INVALID_ARG, "ticks must be >= 0");
@@ -218,11 +231,94 @@ int swarm_rollout(const SwarmConfig* cfg, const float* weights, float* state, in
   p.state_in = state;
   p.state_out = state;
   p.ticks = ticks;
-  p.actions_in = forced_actions;
   p.returns = returns;
   p.hits = hits;
+  if (opts) {
+    if (opts->epsilon < 0.0f || opts->epsilon > 1.0f) return fail(SWARM_ERR_INVALID_ARG, "epsilon must be in [0, 1]");
+    p.actions_in = opts->forced_actions;
+    p.epsilon = opts->epsilon;
+    p.rng_seed = opts->rng_seed;
+    p.rng_tick0 = opts->rng_tick0;
+    p.env_offset = opts->env_offset;
+    if (opts->replay) {
+      const SwarmReplay& r = *opts->replay;
+      if (!r.state || !r.next_state || !r.actions || !r.rewards || r.capacity <= 0)
+        return fail(SWARM_ERR_INVALID_ARG, "replay ring has NULL arrays or no capacity");
+      if ((int64_t)ticks * cfg->num_envs > r.capacity)
+        return fail(SWARM_ERR_INVALID_ARG, "ticks * num_envs exceeds the replay capacity (slots would be overwritten inside one call)");
+      p.replay = r;
+      p.replay_cursor = opts->replay_cursor % r.capacity;
+    }
+  }
   if (trace) p.trace = *trace;
   return check_cuda(launch_tile(MODE_ROLLOUT, p, (cudaStream_t)stream), "swarm_rollout");
+}
+
+int swarm_replay_push(const SwarmConfig* cfg, const SwarmReplay* replay, int64_t cursor, const float* state,
+                      const int32_t* actions, const float* rewards, const float* next_state, void* stream) {
+  if (int rc = validate(cfg, false)) return rc;
+  if (!replay || !replay->state || !replay->next_state || !replay->actions || !replay->rewards || replay->capacity <= 0)
+    return fail(SWARM_ERR_INVALID_ARG, "replay ring has NULL arrays or no capacity");
+  if (!state || !actions || !rewards || !next_state) return fail(SWARM_ERR_INVALID_ARG, "NULL transition array");
+  if (cfg->num_envs > replay->capacity) return fail(SWARM_ERR_INVALID_ARG, "num_envs exceeds the replay capacity");
+  if (cursor < 0) return fail(SWARM_ERR_INVALID_ARG, "cursor must be >= 0");
+  return check_cuda(launch_replay_push(*replay, cursor % replay->capacity, cfg->num_envs, cfg->n_agents, state, actions,
+                                       rewards, next_state, (cudaStream_t)stream),
+                    "swarm_replay_push");
+}
+
+int swarm_replay_gather(const SwarmConfig* cfg, const SwarmReplay* replay, const int64_t* indices, int32_t n_graphs,
+                        float* state, int32_t* actions, float* rewards, float* next_state, void* stream) {
+  if (!cfg || cfg->n_agents <= 0) return fail(SWARM_ERR_INVALID_ARG, "cfg is NULL or n_agents <= 0");
+  if (!replay || !replay->state || !replay->next_state || !replay->actions || !replay->rewards)
+    return fail(SWARM_ERR_INVALID_ARG, "replay ring has NULL arrays");
+  if (n_graphs < 0) return fail(SWARM_ERR_INVALID_ARG, "n_graphs must be >= 0");
+  if (n_graphs == 0) return SWARM_OK;
+  if (!indices || !state || !actions || !rewards || !next_state) return fail(SWARM_ERR_INVALID_ARG, "NULL argument");
+  return check_cuda(launch_replay_gather(*replay, indices, n_graphs, cfg->n_agents, state, actions, rewards, next_state,
+                                         (cudaStream_t)stream),
+                    "swarm_replay_gather");
+}
+
+static int validate_dqn(const SwarmConfig* cfg, int32_t n_graphs) {
+  if (!cfg) return fail(SWARM_ERR_INVALID_ARG, "cfg is NULL");
+  SwarmConfig c = *cfg;
+  c.num_envs = n_graphs > 0 ? n_graphs : 1;
+  if (int rc = validate(&c, true)) return rc;
+  if (n_graphs <= 0) return fail(SWARM_ERR_INVALID_ARG, "n_graphs must be positive");
+  if (dqn_smem_bytes(c) > 227 * 1024)
+    return fail(SWARM_ERR_UNSUPPORTED, "the DQN gradient tile exceeds 227 KB of shared memory for this (N, k)");
+  return SWARM_OK;
+}
+
+int64_t swarm_dqn_workspace_bytes(const SwarmConfig* cfg, int32_t n_graphs) {
+  if (validate_dqn(cfg, n_graphs) != SWARM_OK) return 0;
+  return dqn_workspace_bytes(*cfg, n_graphs);
+}
+
+int swarm_dqn_grad(const SwarmConfig* cfg, const float* online_weights, const float* target_weights,
+                   const SwarmReplay* batch, const int64_t* indices, int32_t n_graphs, float gamma, float loss_scale,
+                   float* grad, float* loss, float* td, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (int rc = validate_dqn(cfg, n_graphs)) return rc;
+  if (!online_weights || !target_weights || !grad || !loss || !workspace) return fail(SWARM_ERR_INVALID_ARG, "NULL argument");
+  if (!batch || !batch->state || !batch->next_state || !batch->actions || !batch->rewards)
+    return fail(SWARM_ERR_INVALID_ARG, "batch has NULL arrays");
+  if (workspace_bytes < dqn_workspace_bytes(*cfg, n_graphs)) return fail(SWARM_ERR_INVALID_ARG, "workspace too small");
+  return check_cuda(launch_dqn_grad(*cfg, online_weights, target_weights, *batch, indices, n_graphs, gamma, loss_scale,
+                                    grad, loss, td, workspace, (cudaStream_t)stream),
+                    "swarm_dqn_grad");
+}
+
+int swarm_adam_clip_step(float* weights, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t step, double lr,
+                         double beta1, double beta2, double eps, double max_norm, float* target_weights,
+                         float* grad_norm, void* stream) {
+  if (!weights || !grad || !exp_avg || !exp_avg_sq) return fail(SWARM_ERR_INVALID_ARG, "NULL argument");
+  if (step < 1) return fail(SWARM_ERR_INVALID_ARG, "step is 1-based");
+  if (!(lr >= 0.0) || !(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || !(eps >= 0.0))
+    return fail(SWARM_ERR_INVALID_ARG, "invalid Adam hyper-parameter");     // torch.optim.Adam's ValueError checks
+  return check_cuda(launch_adam_clip(weights, grad, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, max_norm,
+                                     target_weights, grad_norm, (cudaStream_t)stream),
+                    "swarm_adam_clip_step");
 }
 
 }  // extern "C"

@@ -58,13 +58,13 @@ __device__ __forceinline__ void gat_accumulate(float (&out)[32], float alpha, co
   }
 }
 
-// (aggregate + conv1.bias) -> tanh -> lin1 -> ReLU -> lin2; returns argmax (first maximum wins)
-__device__ __forceinline__ int gat_head(float (&a1)[32], const float* __restrict__ sw, float (&q)[9]) {
+// (aggregate + conv1.bias) -> tanh -> lin1 -> ReLU -> lin2; returns argmax (first maximum wins).
+// On return a1 holds u = tanh(agg + b0) and a2 holds r = relu(W1 u + b1) (kept for the backward pass).
+__device__ __forceinline__ int gat_head_keep(float (&a1)[32], float (&a2)[32], const float* __restrict__ sw, float (&q)[9]) {
   const float* b0 = sw + TW_B0;
 #pragma unroll
   for (int cc = 0; cc < 32; ++cc) a1[cc] = tanhf(__fadd_rn(a1[cc], b0[cc]));
 
-  float a2[32];
 #pragma unroll
   for (int cc = 0; cc < 32; ++cc) a2[cc] = 0.0f;
   const float4* w1 = reinterpret_cast<const float4*>(sw + TW_W1T);
@@ -110,6 +110,11 @@ __device__ __forceinline__ int gat_head(float (&a1)[32], const float* __restrict
     }
   }
   return action;
+}
+
+__device__ __forceinline__ int gat_head(float (&a1)[32], const float* __restrict__ sw, float (&q)[9]) {
+  float a2[32];
+  return gat_head_keep(a1, a2, sw, q);
 }
 
 }  // namespace swarm

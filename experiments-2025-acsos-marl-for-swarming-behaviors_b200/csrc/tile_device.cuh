@@ -1,0 +1,185 @@
+// tile_device.cuh -- device functions of the env-tile scheme (thread = agent, CTA = floor(128/N) envs),
+// shared by the rollout / forward / step / graph kernels (tile_kernels.cu) and the DQN gradient kernel
+// (dqn_kernels.cu).
+#ifndef SWARM_TILE_DEVICE_CUH
+#define SWARM_TILE_DEVICE_CUH
+
+#include "gatq_device.cuh"
+#include "knn_select.h"
+
+namespace swarm {
+
+struct SmemPairs {
+  float* v;
+  uint8_t* x;
+  int stride;
+  __device__ __forceinline__ KnnPair get(int j) const {
+    KnnPair p;
+    p.v = v[j * stride];
+    p.i = x[j * stride];
+    return p;
+  }
+  __device__ __forceinline__ void set(int j, const KnnPair& p) {
+    v[j * stride] = p.v;
+    x[j * stride] = (uint8_t)p.i;
+  }
+};
+
+// Position of this thread inside the tile
+struct TileThread {
+  int tid, el, i, envbase;
+  long long env, gidx;
+  bool active;
+};
+
+__device__ __forceinline__ TileThread tile_thread(int n_agents, int epb, long long num_envs) {
+  TileThread t;
+  t.tid = threadIdx.x;
+  t.el = t.tid / n_agents;
+  t.i = t.tid - t.el * n_agents;
+  t.env = (long long)blockIdx.x * epb + t.el;
+  t.active = (t.el < epb) && (t.env < num_envs);
+  t.envbase = t.el * n_agents;
+  t.gidx = t.env * n_agents + t.i;
+  return t;
+}
+
+// Shared-memory views used by the graph + GAT forward
+struct TileGraphSmem {
+  float* sh;        // [T][kHPad] projected features
+  float* sas;       // [T] alpha_src
+  float* swt;       // [maxdeg][T] per-thread edge scratch (logit -> exp -> alpha)
+  uint8_t* sin;     // [maxdeg][T] in-edge sources (env-local ids), edge-list order
+  float* skv;       // [N][T] kNN distance rows
+  uint8_t* ski;     // [N][T] kNN index rows
+  uint8_t* snbr;    // [K][T] topk result rows
+};
+
+// complete graph (train:101-108): sources into node d in edge-list order are 0..N-1 without d; node 0
+// additionally receives the final (0,0) self loop.  Returns the in-degree.
+__device__ __forceinline__ int tile_in_edges_complete(const TileGraphSmem& g, const TileThread& t, int N) {
+  const int T = kTileThreads;
+  int deg = 0;
+  for (int j = 0; j < N; ++j)
+    if (j != t.i) g.sin[(deg++) * T + t.tid] = (uint8_t)j;
+  if (t.i == 0) g.sin[(deg++) * T + t.tid] = 0;
+  return deg;
+}
+
+// kNN rows (simulator.py:17-19): distance_to_i = ||x[:, :2] - x[i, :2]||, topk(k, largest=False) with
+// torch's CPU tie order.  `pos` is the env-tile state buffer (float4 per thread).  Ends with a block barrier.
+__device__ __forceinline__ void tile_knn_rows(const TileGraphSmem& g, const TileThread& t, const float4* pos,
+                                              const float4& s, int N, int K) {
+  const int T = kTileThreads;
+  if (t.active) {
+    SmemPairs row{g.skv + t.tid, g.ski + t.tid, T};
+    for (int j = 0; j < N; ++j) {
+      const float4 o = pos[t.envbase + j];
+      KnnPair pr;
+      pr.v = norm2(__fsub_rn(o.x, s.x), __fsub_rn(o.y, s.y));
+      pr.i = j;
+      row.set(j, pr);
+    }
+    knn_topk_smallest(row, N, K);
+    for (int r = 0; r < K; ++r) g.snbr[r * T + t.tid] = g.ski[r * T + t.tid];
+  }
+  __syncthreads();
+}
+
+// in-edges of node d = i in edge-list order (simulator.py:20-24): for each row ii, slot r with
+// a = topk[ii][r]: edge (ii -> a) then edge (a -> ii); finally (0 -> 0).
+__device__ __forceinline__ int tile_in_edges_knn(const TileGraphSmem& g, const TileThread& t, int N, int K) {
+  const int T = kTileThreads;
+  int deg = 0;
+  for (int ii = 0; ii < N; ++ii) {
+    for (int r = 0; r < K; ++r) {
+      const int a = g.snbr[r * T + t.envbase + ii];
+      if (a == t.i) g.sin[(deg++) * T + t.tid] = (uint8_t)ii;
+      if (ii == t.i) g.sin[(deg++) * T + t.tid] = (uint8_t)a;
+    }
+  }
+  if (t.i == 0) g.sin[(deg++) * T + t.tid] = 0;
+  return deg;
+}
+
+// edge list export (env-local ids) in the reference's order
+__device__ __forceinline__ void tile_write_edges(const TileGraphSmem& g, const TileThread& t, int N, int K, bool knn,
+                                                 int E, int32_t* eout) {
+  const int T = kTileThreads;
+  int32_t* r0 = eout + t.env * 2 * E;
+  int32_t* r1 = r0 + E;
+  const int i = t.i;
+  if (knn) {
+    for (int r = 0; r < K; ++r) {
+      const int a = g.snbr[r * T + t.tid];
+      const int e = (i * K + r) * 2;
+      r0[e] = i; r1[e] = a;
+      r0[e + 1] = a; r1[e + 1] = i;
+    }
+  } else {
+    for (int j = i + 1; j < N; ++j) {
+      const int e = 2 * (i * N - (i * (i + 1)) / 2 + (j - i - 1));
+      r0[e] = i; r1[e] = j;
+      r0[e + 1] = j; r1[e + 1] = i;
+    }
+  }
+  if (i == 0) { r0[E - 1] = 0; r1[E - 1] = 0; }
+}
+
+// GATConv forward for the node of this thread: projects x, publishes (h, alpha_src) to the tile, runs the
+// edge softmax over the in-edge list in edge-list order (torch_geometric.utils.softmax: max, exp(z - max),
+// sum + 1e-16, divide) and aggregates.  On return agg = sum_e alpha_e h_j (bias not yet added), the attention
+// coefficients alpha_e are left in g.swt[e][tid], and adst is this node's alpha_dst.  Contains one barrier.
+__device__ __forceinline__ void tile_gat_conv(const TileGraphSmem& g, const TileThread& t, const float* sw,
+                                              const float (&x)[7], int deg, float (&agg)[32], float& adst) {
+  const int T = kTileThreads;
+  adst = 0.0f;
+  if (t.active) {
+    float h[32];
+    float asrc;
+    gat_project(x, sw, h, asrc, adst);
+    float4* hrow = reinterpret_cast<float4*>(g.sh + t.tid * kHPad);
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) hrow[c4] = make_float4(h[4 * c4], h[4 * c4 + 1], h[4 * c4 + 2], h[4 * c4 + 3]);
+    g.sas[t.tid] = asrc;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int cc = 0; cc < 32; ++cc) agg[cc] = 0.0f;
+  if (t.active) {
+    float m = -INFINITY;
+    for (int e = 0; e < deg; ++e) {
+      const float z = gat_logit(g.sas[t.envbase + g.sin[e * T + t.tid]], adst);
+      g.swt[e * T + t.tid] = z;
+      m = fmaxf(m, z);
+    }
+    float den = 0.0f;
+    for (int e = 0; e < deg; ++e) {
+      const float w = expf(__fsub_rn(g.swt[e * T + t.tid], m));
+      g.swt[e * T + t.tid] = w;
+      den = __fadd_rn(den, w);
+    }
+    den = __fadd_rn(den, 1e-16f);
+    for (int e = 0; e < deg; ++e) {
+      const int j = g.sin[e * T + t.tid];
+      const float alpha = __fdiv_rn(g.swt[e * T + t.tid], den);
+      g.swt[e * T + t.tid] = alpha;
+      gat_accumulate(agg, alpha, reinterpret_cast<const float4*>(g.sh + (t.envbase + j) * kHPad));
+    }
+  }
+}
+
+// counter-based RNG for device-side exploration (documented deviation from the reference's Python
+// Mersenne stream, train:164-165; parity tests inject the action stream instead)
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ uint64_t rng_draw(uint64_t seed, uint64_t env, uint64_t tick, uint32_t lane) {
+  return splitmix64(splitmix64(seed ^ (env * 0xD1342543DE82EF95ull)) ^ (tick * 0xA24BAED4963EE407ull) ^ lane);
+}
+
+}  // namespace swarm
+#endif

@@ -4,36 +4,48 @@
 // agent needs from its swarm (partner positions, projected features, attention terms, kNN rows) is
 // exchanged through shared memory and no env ever straddles a CTA.  The same device code is
 // instantiated in four modes:
-//   MODE_ROLLOUT  T x [graph -> GAT-Q -> argmax -> world step], state resident in registers
-//                 (simulator.py:59-93 / train_gcn_dqn.py:153-178 inner loops)
+//   MODE_ROLLOUT  T x [graph -> GAT-Q -> (eps-)greedy -> world step (-> replay push)], state resident in
+//                 registers (simulator.py:59-93 / train_gcn_dqn.py:153-178 inner loops)
 //   MODE_FORWARD  graph -> GAT-Q (-> argmax) once                         (train_gcn_dqn.py:59-70)
 //   MODE_STEP     one world step with given actions                       (vmas Environment.step)
 //   MODE_GRAPH    edge list / neighbour table export                      (train:94-110, simulator:9-26)
 // so the stand-alone kernels and the fused rollout are consistent by construction.
-#include "gatq_device.cuh"
-#include "knn_select.h"
+#include "tile_device.cuh"
 
 namespace swarm {
 
-namespace {
-
-struct SmemPairs {
-  float* v;
-  uint8_t* x;
-  int stride;
-  __device__ __forceinline__ KnnPair get(int j) const {
-    KnnPair p;
-    p.v = v[j * stride];
-    p.i = x[j * stride];
-    return p;
+// One world step for the agent of this thread: action decode, contact forces (obstacle first, then
+// agents in entity order), integration.  `pos` = pre-step states of the tile.
+__device__ __forceinline__ void tile_world_step(const TileParams& p, const TileThread& t, const float4* pos, int action,
+                                                float4& s, uint8_t& flags, uint32_t& cmask) {
+  const SwarmConfig& c = p.cfg;
+  float fx, fy, gx, gy;
+  decode_action(action, fx, fy);          // F = 0 + u
+  if (c.scenario == SWARM_SCENARIO_OBSTACLE_AVOIDANCE) {
+    const float dx = __fsub_rn(s.x, c.obstacle_x), dy = __fsub_rn(s.y, c.obstacle_y);
+    if (__fmaf_rn(dy, dy, __fmul_rn(dx, dx)) <= p.qmax_ao) {
+      if (contact_force(s.x, s.y, c.obstacle_x, c.obstacle_y, p.dmin_ao, c.collision_force, c.contact_margin, gx, gy)) {
+        fx = __fadd_rn(fx, gx);
+        fy = __fadd_rn(fy, gy);
+        flags |= SWARM_FLAG_OBSTACLE_CONTACT;
+      }
+    }
   }
-  __device__ __forceinline__ void set(int j, const KnnPair& p) {
-    v[j * stride] = p.v;
-    x[j * stride] = (uint8_t)p.i;
+  const int N = c.n_agents;
+  for (int j = 0; j < N; ++j) {
+    if (j == t.i) continue;
+    const float4 o = pos[t.envbase + j];
+    const float dx = __fsub_rn(s.x, o.x), dy = __fsub_rn(s.y, o.y);
+    if (__fmaf_rn(dy, dy, __fmul_rn(dx, dx)) <= p.qmax_aa) {
+      if (contact_force(s.x, s.y, o.x, o.y, p.dmin_aa, c.collision_force, c.contact_margin, gx, gy)) {
+        fx = __fadd_rn(fx, gx);
+        fy = __fadd_rn(fy, gy);
+        if (j < 32) cmask |= (1u << j);
+      }
+    }
   }
-};
-
-}  // namespace
+  integrate(s, fx, fy, c.dt, p.one_minus_drag);
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(kTileThreads) tile_kernel(const __grid_constant__ TileParams p) {
@@ -47,161 +59,73 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(const __grid_constan
   const int N = c.n_agents;
   const int K = c.knn_k;
   const bool knn = (c.graph_mode == SWARM_GRAPH_KNN) && (kQ || MODE == MODE_GRAPH);
-  const int tid = threadIdx.x;
-  const int el = tid / N;
-  const int i = tid - el * N;
-  const long long env = (long long)blockIdx.x * p.epb + el;
-  const bool active = (el < p.epb) && (env < c.num_envs);
-  const int envbase = el * N;
-  const long long gidx = env * N + i;
+  const TileThread t = tile_thread(N, p.epb, c.num_envs);
+  const int tid = t.tid;
   const long long BN = (long long)c.num_envs * N;
 
   const TileLayout L = tile_layout(MODE, T, N, K, p.maxdeg, c.graph_mode);
   float* sw = reinterpret_cast<float*>(smem + L.w);
   float4* sst = reinterpret_cast<float4*>(smem + L.st);
-  float* sh = reinterpret_cast<float*>(smem + L.h);
-  float* sas = reinterpret_cast<float*>(smem + L.asrc);
-  float* swt = reinterpret_cast<float*>(smem + L.wt);
-  uint8_t* sin = smem + L.inl;
-  uint8_t* sdeg = smem + L.deg;
-  float* skv = reinterpret_cast<float*>(smem + L.kv);
-  uint8_t* ski = smem + L.ki;
-  uint8_t* snbr = smem + L.nbr;
   float* sred = reinterpret_cast<float*>(smem + L.red);
+  TileGraphSmem g;
+  g.sh = reinterpret_cast<float*>(smem + L.h);
+  g.sas = reinterpret_cast<float*>(smem + L.asrc);
+  g.swt = reinterpret_cast<float*>(smem + L.wt);
+  g.sin = smem + L.inl;
+  g.skv = reinterpret_cast<float*>(smem + L.kv);
+  g.ski = smem + L.ki;
+  g.snbr = smem + L.nbr;
 
   if (kQ) stage_weights(p.weights, sw, tid, T);
 
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (active) s = reinterpret_cast<const float4*>(p.state_in)[gidx];
+  if (t.active) s = reinterpret_cast<const float4*>(p.state_in)[t.gidx];
 
   int deg = 0;
-  if (kQ && !knn && active) {
-    // complete graph (train:101-108): sources into node d in edge-list order are 0..N-1 without d;
-    // node 0 additionally receives the final (0,0) self loop.
-    for (int j = 0; j < N; ++j)
-      if (j != i) sin[(deg++) * T + tid] = (uint8_t)j;
-    if (i == 0) sin[(deg++) * T + tid] = 0;
-  }
+  if (kQ && !knn && t.active) deg = tile_in_edges_complete(g, t, N);
 
   float ret = 0.0f;
   int myhits = 0;
 
   for (int tick = 0; tick < p.ticks; ++tick) {
-    const int buf = tick & 1;
-    sst[buf * T + tid] = s;
+    const float4* pos = sst + (tick & 1) * T;
+    sst[(tick & 1) * T + tid] = s;
     __syncthreads();
 
-    float q[9];
     int action = 0;
 
-    // ------------------------------------------------------------------ graph (kNN) ----------
+    // ------------------------------------------------------------------ graph ----------------
     if (knn) {
-      if (active) {
-        // simulator.py:17-19: distance_to_i = ||x[:, :2] - x[i, :2]||, topk(k, largest=False)
-        SmemPairs row{skv + tid, ski + tid, T};
-        for (int j = 0; j < N; ++j) {
-          const float4 o = sst[buf * T + envbase + j];
-          KnnPair pr;
-          pr.v = norm2(__fsub_rn(o.x, s.x), __fsub_rn(o.y, s.y));
-          pr.i = j;
-          row.set(j, pr);
-        }
-        knn_topk_smallest(row, N, K);
-        for (int r = 0; r < K; ++r) snbr[r * T + tid] = ski[r * T + tid];
-      }
-      __syncthreads();
-      if (kQ && active) {
-        // in-edges of node d = i in edge-list order: for each row ii, slot r with a = topk[ii][r]:
-        // edge (ii -> a) then edge (a -> ii); finally (0 -> 0).
-        deg = 0;
-        for (int ii = 0; ii < N; ++ii) {
-          for (int r = 0; r < K; ++r) {
-            const int a = snbr[r * T + envbase + ii];
-            if (a == i) sin[(deg++) * T + tid] = (uint8_t)ii;
-            if (ii == i) sin[(deg++) * T + tid] = (uint8_t)a;
-          }
-        }
-        if (i == 0) sin[(deg++) * T + tid] = 0;
-      }
+      tile_knn_rows(g, t, pos, s, N, K);
+      if (kQ && t.active) deg = tile_in_edges_knn(g, t, N, K);
     }
-
     if (kGraphOut) {
       int32_t* eout = nullptr;
       if (MODE == MODE_GRAPH) eout = p.edges_out;
       else if (p.trace.edges) eout = p.trace.edges + (long long)tick * c.num_envs * 2 * p.edges_per_env;
-      if (eout && active) {
-        const int E = p.edges_per_env;
-        int32_t* r0 = eout + env * 2 * E;
-        int32_t* r1 = r0 + E;
-        if (knn) {
-          for (int r = 0; r < K; ++r) {
-            const int a = snbr[r * T + tid];
-            const int e = (i * K + r) * 2;
-            r0[e] = i; r1[e] = a;
-            r0[e + 1] = a; r1[e + 1] = i;
-          }
-        } else {
-          for (int j = i + 1; j < N; ++j) {
-            const int e = 2 * (i * N - (i * (i + 1)) / 2 + (j - i - 1));
-            r0[e] = i; r1[e] = j;
-            r0[e + 1] = j; r1[e + 1] = i;
-          }
-        }
-        if (i == 0) { r0[E - 1] = 0; r1[E - 1] = 0; }
-      }
-      if (MODE == MODE_GRAPH && knn && p.nbr_out && active)
-        for (int r = 0; r < K; ++r) p.nbr_out[gidx * K + r] = snbr[r * T + tid];
+      if (eout && t.active) tile_write_edges(g, t, N, K, knn, p.edges_per_env, eout);
+      if (MODE == MODE_GRAPH && knn && p.nbr_out && t.active)
+        for (int r = 0; r < K; ++r) p.nbr_out[t.gidx * K + r] = g.snbr[r * T + tid];
     }
 
     // ------------------------------------------------------------------ GAT-Q forward --------
     if (kQ) {
-      float tdst = 0.0f;
-      if (active) {
-        // node features (train:95-99): [pos, vel, goal, agent id]
-        const float x[7] = {s.x, s.y, s.z, s.w, c.goal_x, c.goal_y, (float)i};
-        float h[32];
-        float asrc;
-        gat_project(x, sw, h, asrc, tdst);
-        float4* hrow = reinterpret_cast<float4*>(sh + tid * kHPad);
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) hrow[c4] = make_float4(h[4 * c4], h[4 * c4 + 1], h[4 * c4 + 2], h[4 * c4 + 3]);
-        sas[tid] = asrc;
-      }
-      __syncthreads();
-
-      if (active) {
-        // edge softmax over the in-edges of this node, in edge-list order (torch_geometric.utils.softmax):
-        // max, exp(z - max), sum + 1e-16, divide
-        float m = -INFINITY;
-        for (int e = 0; e < deg; ++e) {
-          const float z = gat_logit(sas[envbase + sin[e * T + tid]], tdst);
-          swt[e * T + tid] = z;
-          m = fmaxf(m, z);
-        }
-        float den = 0.0f;
-        for (int e = 0; e < deg; ++e) {
-          const float w = expf(__fsub_rn(swt[e * T + tid], m));
-          swt[e * T + tid] = w;
-          den = __fadd_rn(den, w);
-        }
-        den = __fadd_rn(den, 1e-16f);
-        float a1[32];
-#pragma unroll
-        for (int cc = 0; cc < 32; ++cc) a1[cc] = 0.0f;
-        for (int e = 0; e < deg; ++e) {
-          const int j = sin[e * T + tid];
-          const float alpha = __fdiv_rn(swt[e * T + tid], den);
-          gat_accumulate(a1, alpha, reinterpret_cast<const float4*>(sh + (envbase + j) * kHPad));
-        }
+      // node features (train:95-99): [pos, vel, goal, agent id]
+      const float x[7] = {s.x, s.y, s.z, s.w, c.goal_x, c.goal_y, (float)t.i};
+      float a1[32];
+      float adst;
+      tile_gat_conv(g, t, sw, x, deg, a1, adst);
+      if (t.active) {
+        float q[9];
         action = gat_head(a1, sw, q);
         if (MODE == MODE_FORWARD) {
           if (p.q_out) {
 #pragma unroll
-            for (int a = 0; a < 9; ++a) p.q_out[gidx * 9 + a] = q[a];
+            for (int a = 0; a < 9; ++a) p.q_out[t.gidx * 9 + a] = q[a];
           }
-          if (p.act_out) p.act_out[gidx] = action;
+          if (p.act_out) p.act_out[t.gidx] = action;
         } else if (p.trace.q) {
-          float* tq = p.trace.q + ((long long)tick * BN + gidx) * 9;
+          float* tq = p.trace.q + ((long long)tick * BN + t.gidx) * 9;
 #pragma unroll
           for (int a = 0; a < 9; ++a) tq[a] = q[a];
         }
@@ -210,94 +134,79 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(const __grid_constan
 
     // ------------------------------------------------------------------ world step ------------
     if (kStep) {
-      if (active) {
+      float reward = 0.0f;
+      if (t.active) {
         if (MODE == MODE_STEP) {
-          action = p.actions_in[gidx];
-        } else if (p.actions_in) {
-          const int fa = p.actions_in[(long long)tick * BN + gidx];
-          if (fa >= 0) action = fa;
+          action = p.actions_in[t.gidx];
+        } else {
+          if (p.epsilon > 0.0f) {
+            // train:164-165: one coin per tick for the whole swarm, then one uniform action per agent
+            const unsigned long long genv = (unsigned long long)(p.env_offset + t.env);
+            const unsigned long long gt = (unsigned long long)(p.rng_tick0 + tick);
+            const float coin = (float)(rng_draw(p.rng_seed, genv, gt, 0xFFFFu) >> 40) * (1.0f / 16777216.0f);
+            if (coin < p.epsilon) action = (int)(((rng_draw(p.rng_seed, genv, gt, (uint32_t)t.i) >> 32) * 9ull) >> 32);
+          }
+          if (p.actions_in) {
+            const int fa = p.actions_in[(long long)tick * BN + t.gidx];
+            if (fa >= 0) action = fa;
+          }
         }
-        float fx, fy;
-        decode_action(action, fx, fy);          // F = 0 + u
+        const float4 s_prev = s;
         uint8_t flags = 0;
         uint32_t cmask = 0;
-        float gx, gy;
-        if (c.scenario == SWARM_SCENARIO_OBSTACLE_AVOIDANCE) {
-          // vmas entity order: the obstacle landmark precedes the agents
-          const float dx = __fsub_rn(s.x, c.obstacle_x), dy = __fsub_rn(s.y, c.obstacle_y);
-          if (__fmaf_rn(dy, dy, __fmul_rn(dx, dx)) <= p.qmax_ao) {
-            if (contact_force(s.x, s.y, c.obstacle_x, c.obstacle_y, p.dmin_ao, c.collision_force,
-                              c.contact_margin, gx, gy)) {
-              fx = __fadd_rn(fx, gx);
-              fy = __fadd_rn(fy, gy);
-              flags |= SWARM_FLAG_OBSTACLE_CONTACT;
-            }
-          }
-        }
-        for (int j = 0; j < N; ++j) {
-          if (j == i) continue;
-          const float4 o = sst[buf * T + envbase + j];
-          const float dx = __fsub_rn(s.x, o.x), dy = __fsub_rn(s.y, o.y);
-          if (__fmaf_rn(dy, dy, __fmul_rn(dx, dx)) <= p.qmax_aa) {
-            if (contact_force(s.x, s.y, o.x, o.y, p.dmin_aa, c.collision_force, c.contact_margin, gx, gy)) {
-              fx = __fadd_rn(fx, gx);
-              fy = __fadd_rn(fy, gy);
-              if (j < 32) cmask |= (1u << j);
-            }
-          }
-        }
-        integrate(s, fx, fy, c.dt, p.one_minus_drag);
+        tile_world_step(p, t, pos, action, s, flags, cmask);
 
         // scenario.reward(agent) on the post-step state
         const float dgoal = goal_distance(s.x, s.y, c);
-        float reward;
         float dobs = 0.0f;
         if (c.scenario == SWARM_SCENARIO_OBSTACLE_AVOIDANCE) {
           dobs = obstacle_distance(s.x, s.y, c);
           reward = oa_reward(dgoal, dobs, c, flags);
-        } else {
-          sred[tid] = dgoal;
-          reward = 0.0f;
-        }
-        // (GoTo's collective reward needs every agent's distance: completed after the barrier below)
-        if (c.scenario == SWARM_SCENARIO_OBSTACLE_AVOIDANCE) {
-          ret = __fadd_rn(ret, reward);
           myhits += (flags & SWARM_FLAG_HIT) ? 1 : 0;
-          if (MODE == MODE_STEP) {
-            if (p.rewards_out) p.rewards_out[gidx] = reward;
-          } else if (p.trace.rewards) {
-            p.trace.rewards[(long long)tick * BN + gidx] = reward;
-          }
+        } else {
+          sred[tid] = dgoal;     // GoTo's collective reward needs every agent's distance: finished below
         }
         if (MODE == MODE_STEP) {
-          reinterpret_cast<float4*>(p.state_out)[gidx] = s;
-          if (p.flags_out) p.flags_out[gidx] = flags;
-          if (p.contact_out) p.contact_out[gidx] = cmask;
+          reinterpret_cast<float4*>(p.state_out)[t.gidx] = s;
+          if (p.flags_out) p.flags_out[t.gidx] = flags;
+          if (p.contact_out) p.contact_out[t.gidx] = cmask;
           if (p.obs_out) {
-            float* o = p.obs_out + gidx * 6;
+            float* o = p.obs_out + t.gidx * 6;
             o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.w; o[4] = c.goal_x; o[5] = c.goal_y;
           }
-          if (p.dist_out) reinterpret_cast<float2*>(p.dist_out)[gidx] = make_float2(dgoal, dobs);
+          if (p.dist_out) reinterpret_cast<float2*>(p.dist_out)[t.gidx] = make_float2(dgoal, dobs);
         } else {
-          const long long tb = (long long)tick * BN + gidx;
+          const long long tb = (long long)tick * BN + t.gidx;
           if (p.trace.state) reinterpret_cast<float4*>(p.trace.state)[tb] = s;
           if (p.trace.actions) p.trace.actions[tb] = action;
           if (p.trace.flags) p.trace.flags[tb] = flags;
           if (p.trace.contact) p.trace.contact[tb] = cmask;
           if (p.trace.dist) reinterpret_cast<float2*>(p.trace.dist)[tb] = make_float2(dgoal, dobs);
+          if (p.replay.state) {
+            // GraphReplayBuffer.push (train:171-172), state-only transition
+            const long long slot = (p.replay_cursor + (long long)tick * c.num_envs + t.env) % p.replay.capacity;
+            const long long ri = slot * N + t.i;
+            reinterpret_cast<float4*>(p.replay.state)[ri] = s_prev;
+            reinterpret_cast<float4*>(p.replay.next_state)[ri] = s;
+            p.replay.actions[ri] = (uint8_t)action;
+          }
         }
       }
       if (c.scenario == SWARM_SCENARIO_GOTO) {
         // collective reward (go_to:108-115): 0 + (-d_0) + (-d_1) + ... in agent order, same for all agents
         __syncthreads();
-        if (active) {
-          float reward = 0.0f;
-          for (int a = 0; a < N; ++a) reward = __fadd_rn(reward, -sred[envbase + a]);
-          ret = __fadd_rn(ret, reward);
-          if (MODE == MODE_STEP) {
-            if (p.rewards_out) p.rewards_out[gidx] = reward;
-          } else if (p.trace.rewards) {
-            p.trace.rewards[(long long)tick * BN + gidx] = reward;
+        if (t.active)
+          for (int a = 0; a < N; ++a) reward = __fadd_rn(reward, -sred[t.envbase + a]);
+      }
+      if (t.active) {
+        ret = __fadd_rn(ret, reward);
+        if (MODE == MODE_STEP) {
+          if (p.rewards_out) p.rewards_out[t.gidx] = reward;
+        } else {
+          if (p.trace.rewards) p.trace.rewards[(long long)tick * BN + t.gidx] = reward;
+          if (p.replay.state) {
+            const long long slot = (p.replay_cursor + (long long)tick * c.num_envs + t.env) % p.replay.capacity;
+            p.replay.rewards[slot * N + t.i] = reward;
           }
         }
       }
@@ -305,21 +214,76 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(const __grid_constan
   }
 
   if (MODE == MODE_ROLLOUT) {
-    if (active) {
-      reinterpret_cast<float4*>(p.state_out)[gidx] = s;
-      if (p.returns) p.returns[gidx] = __fadd_rn(p.returns[gidx], ret);
+    if (t.active) {
+      reinterpret_cast<float4*>(p.state_out)[t.gidx] = s;
+      if (p.returns) p.returns[t.gidx] = __fadd_rn(p.returns[t.gidx], ret);
     }
     if (p.hits) {
       __syncthreads();
       reinterpret_cast<int*>(sred)[tid] = myhits;
       __syncthreads();
-      if (active && i == 0) {
+      if (t.active && t.i == 0) {
         int tot = 0;
-        for (int a = 0; a < N; ++a) tot += reinterpret_cast<int*>(sred)[envbase + a];
-        p.hits[env] += tot;
+        for (int a = 0; a < N; ++a) tot += reinterpret_cast<int*>(sred)[t.envbase + a];
+        p.hits[t.env] += tot;
       }
     }
   }
+}
+
+// ---- replay ring copies ---------------------------------------------------------------------
+__global__ void __launch_bounds__(256) replay_push_kernel(SwarmReplay r, long long cursor, int B, int N,
+                                                          const float4* __restrict__ state,
+                                                          const int32_t* __restrict__ actions,
+                                                          const float* __restrict__ rewards,
+                                                          const float4* __restrict__ next_state) {
+  const long long total = (long long)B * N;
+  for (long long gI = (long long)blockIdx.x * blockDim.x + threadIdx.x; gI < total; gI += (long long)gridDim.x * blockDim.x) {
+    const long long b = gI / N;
+    const int i = (int)(gI - b * N);
+    const long long ri = ((cursor + b) % r.capacity) * N + i;
+    reinterpret_cast<float4*>(r.state)[ri] = state[gI];
+    reinterpret_cast<float4*>(r.next_state)[ri] = next_state[gI];
+    r.actions[ri] = (uint8_t)actions[gI];
+    r.rewards[ri] = rewards[gI];
+  }
+}
+
+__global__ void __launch_bounds__(256) replay_gather_kernel(SwarmReplay r, const int64_t* __restrict__ indices, int G,
+                                                            int N, float4* __restrict__ state,
+                                                            int32_t* __restrict__ actions, float* __restrict__ rewards,
+                                                            float4* __restrict__ next_state) {
+  const long long total = (long long)G * N;
+  for (long long gI = (long long)blockIdx.x * blockDim.x + threadIdx.x; gI < total; gI += (long long)gridDim.x * blockDim.x) {
+    const long long b = gI / N;
+    const int i = (int)(gI - b * N);
+    const long long ri = indices[b] * N + i;
+    state[gI] = reinterpret_cast<const float4*>(r.state)[ri];
+    next_state[gI] = reinterpret_cast<const float4*>(r.next_state)[ri];
+    actions[gI] = r.actions[ri];
+    rewards[gI] = r.rewards[ri];
+  }
+}
+
+static int copy_blocks(long long total) {
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  return blocks < 1 ? 1 : (int)blocks;
+}
+
+cudaError_t launch_replay_push(const SwarmReplay& r, long long cursor, int B, int N, const float* state,
+                               const int32_t* actions, const float* rewards, const float* next_state,
+                               cudaStream_t stream) {
+  replay_push_kernel<<<copy_blocks((long long)B * N), 256, 0, stream>>>(
+      r, cursor, B, N, reinterpret_cast<const float4*>(state), actions, rewards, reinterpret_cast<const float4*>(next_state));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_replay_gather(const SwarmReplay& r, const int64_t* indices, int G, int N, float* state,
+                                 int32_t* actions, float* rewards, float* next_state, cudaStream_t stream) {
+  replay_gather_kernel<<<copy_blocks((long long)G * N), 256, 0, stream>>>(
+      r, indices, G, N, reinterpret_cast<float4*>(state), actions, rewards, reinterpret_cast<float4*>(next_state));
+  return cudaGetLastError();
 }
 
 // explicit instantiations + launcher

@@ -73,6 +73,12 @@ struct TileParams {
   float* dist_out;               // MODE_STEP
   int32_t* edges_out;            // MODE_GRAPH
   int32_t* nbr_out;              // MODE_GRAPH
+  SwarmReplay replay;            // MODE_ROLLOUT, optional (state == nullptr: no push)
+  long long replay_cursor;
+  long long env_offset;
+  unsigned long long rng_seed;
+  long long rng_tick0;
+  float epsilon;
   int32_t ticks;
   int32_t epb;                   // envs per block
   int32_t maxdeg;                // max in-degree of the graph (rows of the per-thread edge scratch)

@@ -1,0 +1,297 @@
+"""DQN training at the reference's Python seam (src/training/train_gcn_dqn.py:25-48, 72-231).
+
+``GraphReplayBuffer`` and ``DQNTrainer`` keep the reference's class / method names, argument meaning and
+bookkeeping (epsilon schedule, target sync, CSV layout incl. its row quirk), while every tensor operation
+runs in libswarm_b200.so: world step, replay push / sample, TD target, loss, backward, clip, Adam.
+
+Two drivers:
+  * ``DQNTrainer.train_model(config)``  -- the reference loop for ``num_envs = 1`` with the reference's Python
+    ``random`` stream for exploration and sampling; reproduces the shipped ``data/stats/*.csv`` rows.
+  * ``DQNTrainer.train_model_batched(config)`` -- B envs per tick with the device RNG, fused
+    rollout-tick + replay push, G graphs per update (throughput mode).
+"""
+from __future__ import annotations
+
+import csv
+import os
+import random
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .gcn import GCN
+from .graph import Batch, Data, node_features, stack_observations
+
+
+def gatq_backward_csr(packed, x, row_ptr, src, grad_q):
+    raise NotImplementedError(
+        "autograd through GCN.forward on an arbitrary graph is not implemented; DQN gradients come from the fused "
+        "swarm_dqn_grad kernel (swarm_b200.dqn.DQNTrainer / ops.dqn_grad)")
+
+
+class GraphReplayBuffer:
+    """train:25-48 on a device ring.  ``push`` takes what the reference pushes (graph, actions, rewards,
+    next graph) or raw states; ``sample`` draws with Python's ``random.sample`` exactly like the reference."""
+
+    def __init__(self, capacity: int, n_agents: Optional[int] = None, device=None):
+        self.capacity = int(capacity)
+        self.ring: Optional[ops.ReplayRing] = None
+        if n_agents is not None and device is not None:
+            self.ring = ops.ReplayRing(self.capacity, n_agents, device)
+
+    @property
+    def position(self) -> int:
+        return 0 if self.ring is None else self.ring.position
+
+    def _ensure(self, n_agents: int, device) -> ops.ReplayRing:
+        if self.ring is None:
+            self.ring = ops.ReplayRing(self.capacity, n_agents, device)
+        return self.ring
+
+    @staticmethod
+    def _state_of(g) -> torch.Tensor:
+        x = g.x if hasattr(g, "x") else g
+        return x[..., :4].reshape(1, -1, 4).contiguous()
+
+    def push(self, graph_observation, actions, rewards, next_graph_observation) -> None:
+        s, s2 = self._state_of(graph_observation), self._state_of(next_graph_observation)
+        n, dev = s.shape[1], s.device
+        ring = self._ensure(n, dev)
+        cfg = ops.make_config(_lib.SCENARIO_GOTO, 1, n)
+        a = torch.as_tensor(actions).reshape(1, n).to(device=dev, dtype=torch.int32)
+        r = torch.as_tensor(rewards, dtype=torch.float32).reshape(1, n).to(dev)
+        ops.replay_push(cfg, ring, s, a.contiguous(), r.contiguous(), s2)
+
+    def sample_indices(self, batch_size: int) -> List[int]:
+        # random.sample(self.buffer, k) consumes the Mersenne stream as a function of (len, k) only
+        return random.sample(range(len(self)), batch_size)
+
+    def sample(self, batch_size: int):
+        """(Batch observations, actions int64[G*N], rewards f32[G*N], Batch next observations), train:38-45."""
+        ring = self.ring
+        idx = torch.tensor(self.sample_indices(batch_size), dtype=torch.int64, device=ring.state.device)
+        b = ops.replay_gather(ring, idx)
+        goal = getattr(self, "goal", (-0.8, 0.8))
+
+        def graphs(state):
+            G, N, _ = state.shape
+            gl = torch.tensor(goal, dtype=torch.float32, device=state.device).view(1, 1, 2).expand(G, N, 2)
+            x = node_features(torch.cat([state, gl], dim=2)).view(G, N, 7)
+            cfg = ops.make_config(_lib.SCENARIO_GOTO, G, N, _lib.GRAPH_COMPLETE)
+            edges, _ = ops.graph_build(cfg, state.contiguous())
+            return Batch.from_data_list([Data(x=x[g_], edge_index=edges[g_].to(torch.int64)) for g_ in range(G)])
+
+        return graphs(b["state"]), b["actions"].reshape(-1).long(), b["rewards"].reshape(-1), graphs(b["next_state"])
+
+    def __len__(self) -> int:
+        return 0 if self.ring is None else len(self.ring)
+
+
+class DQNTrainer:
+    """train:72-231.  ``env`` is a swarm_b200 Environment (``make_env``)."""
+
+    def __init__(self, env, seed, models_path, stats_path, experiment, graph_mode: str = "complete", knn_k: int = 10,
+                 replay_capacity: int = 1000000):
+        self.env = env
+        self.seed = seed
+        self.models_path = models_path
+        self.stats_path = stats_path
+        self.experiment = experiment
+        self.n_input = self.env.observation_space["agent0"].shape[0] + 1
+        self.n_output = env.action_space["agent0"].n
+        dev = env.device
+        # constructors run on the CPU generator exactly like the reference (2 x 1 865 uniform draws)
+        self.model = GCN(input_dim=self.n_input, hidden_dim=32, output_dim=self.n_output)
+        self.target_model = GCN(input_dim=self.n_input, hidden_dim=32, output_dim=self.n_output)
+        self.target_model.load_state_dict(self.model.state_dict())
+        self.model.to(dev)
+        self.target_model.to(dev)
+        # packed device weights are the training state; the nn.Modules are refreshed from them on demand
+        self.w = _lib.pack_weights(self.model.state_dict(), dev)
+        self.w_target = self.w.clone()
+        self.exp_avg = torch.zeros_like(self.w)
+        self.exp_avg_sq = torch.zeros_like(self.w)
+        self.opt_step = 0
+        self.lr, self.betas, self.eps, self.max_norm = 0.001, (0.9, 0.999), 1e-8, 1.0
+        self.replay_buffer = GraphReplayBuffer(replay_capacity, env.n_agents, dev)
+        gm = {"complete": _lib.GRAPH_COMPLETE, "knn": _lib.GRAPH_KNN}[graph_mode]
+        self.graph_cfg = ops.clone_config(env.world.cfg, graph_mode=gm, knn_k=knn_k)
+        self.episode_rewards: List[torch.Tensor] = []
+        self.episode_losses: List[float] = []
+        self.episode_obstacle_hits: List[float] = []
+        self.rewards_buffer: List[torch.Tensor] = []
+        self.obstacle_hits_buffer: List[float] = []
+        self._grad = torch.empty_like(self.w)
+        self._loss = torch.empty(1, dtype=torch.float32, device=dev)
+
+    # -- reference API ---------------------------------------------------------------------------
+    def create_graph_from_observations(self, observations: Dict[str, torch.Tensor]) -> Data:
+        """train:94-110 (complete graph + (0,0)); edge list built by swarm_graph_build."""
+        obs = stack_observations(observations)
+        B, N, _ = obs.shape
+        cfg = ops.clone_config(self.graph_cfg, num_envs=B)
+        edges, _ = ops.graph_build(cfg, obs[:, :, :4].contiguous())
+        offs = (torch.arange(B, device=obs.device, dtype=torch.int64) * N).view(B, 1, 1)
+        ei = (edges.to(torch.int64) + offs).permute(1, 0, 2).reshape(2, -1).contiguous()
+        return Data(x=node_features(obs), edge_index=ei)
+
+    def sync_modules(self) -> None:
+        """Copy the packed training weights back into the nn.Modules (for state_dict / torch.save)."""
+        self.model.load_state_dict(_lib.unpack_weights(self.w))
+        self.target_model.load_state_dict(_lib.unpack_weights(self.w_target))
+
+    def train_step_dqn(self, batch_size, model=None, target_model=None, ticks=0, gamma=0.99, update_target_every=10,
+                       indices: Optional[torch.Tensor] = None):
+        """train:112-137.  ``model`` / ``target_model`` are accepted for signature parity; the packed weights
+        of this trainer are what is trained."""
+        if len(self.replay_buffer) < batch_size:
+            print("Not enough samples in the replay buffer")
+            return 0
+        ring = self.replay_buffer.ring
+        if indices is None:
+            indices = torch.tensor(self.replay_buffer.sample_indices(batch_size), dtype=torch.int64, device=self.w.device)
+        cfg = ops.clone_config(self.graph_cfg, num_envs=batch_size)
+        ops.dqn_grad(cfg, self.w, self.w_target, ring, indices, batch_size, gamma=gamma, grad=self._grad, loss=self._loss)
+        self.opt_step += 1
+        sync = (ticks % update_target_every == 0)
+        if sync:
+            print("Updating target model")
+        ops.adam_clip_step(self.w, self._grad, self.exp_avg, self.exp_avg_sq, self.opt_step, self.lr, self.betas, self.eps,
+                           self.max_norm, target=self.w_target if sync else None)
+        return self._loss.item()
+
+    def _policy_actions(self) -> torch.Tensor:
+        """argmax_a Q(s) for the env's current state with the online weights (train:161-162,167)."""
+        cfg = ops.clone_config(self.graph_cfg, num_envs=self.env.num_envs)
+        _, act = ops.gatq_forward(cfg, self.w, self.env.world.state, want_q=False)
+        return act
+
+    def train_model(self, config):
+        """train:139-204 for num_envs = 1, Python ``random`` exploration/sampling like the reference."""
+        if self.env.num_envs != 1:
+            raise ValueError("train_model mirrors the reference's num_envs = 1 loop; use train_model_batched")
+        initial_epsilon = config["epsilon"]
+        epsilon_decay = config["epsilon_decay"]
+        min_epsilon = config["min_epsilon"]
+        episodes = config["episodes"]
+        ticks = 0
+        epsilon = initial_epsilon
+        n = self.env.n_agents
+        world = self.env.world
+        for episode in range(episodes):
+            self.env.reset()
+            episode_loss = 0
+            total_episode_reward = torch.zeros(n)
+            for _ in range(self.env.max_steps):
+                ticks += 1
+                state = world.state.clone()
+                if random.random() < epsilon:
+                    actions = torch.tensor([random.randint(0, 8) for _ in range(n)], dtype=torch.int32,
+                                           device=world.device).view(1, n)
+                else:
+                    actions = self._policy_actions()
+                _, rewards, done, _ = self.env.step(actions)
+                rewards_dev = world.last["rewards"]
+                ring = self.replay_buffer.ring
+                ops.replay_push(world.cfg, ring, state, actions.contiguous(), rewards_dev, world.state)
+                loss = self.train_step_dqn(32, self.model, self.target_model, ticks, update_target_every=200)
+                episode_loss += loss
+                total_episode_reward += (rewards_dev.reshape(n).cpu() / n)
+            epsilon = max(min_epsilon, initial_epsilon * np.exp(-epsilon_decay * episode))
+            average_loss = episode_loss / self.env.max_steps
+            self.episode_losses.append(average_loss)
+            self.rewards_buffer.append(total_episode_reward[0])
+            if (episode + 1) % 10 == 0:
+                self.episode_rewards.append(sum(self.rewards_buffer) / 10)
+                self.rewards_buffer = []
+                self.episode_obstacle_hits.append(sum(self.obstacle_hits_buffer) / 10)
+                self.obstacle_hits_buffer = []
+            if config.get("verbose", True):
+                print(f"Episode {episode}, Loss: {average_loss}, Reward: {total_episode_reward.sum().item()}, Epsilon: {epsilon}")
+        self.sync_modules()
+        if config.get("save", True):
+            os.makedirs(self.models_path, exist_ok=True)
+            torch.save(self.model.state_dict(), f"{self.models_path}/experiment_{self.experiment}-seed_{self.seed}.pth")
+            self.save_metrics_to_csv()
+
+    def train_model_batched(self, config) -> Dict[str, float]:
+        """B envs per tick: fused [Q -> eps-greedy -> step -> replay push] kernel, then one update of
+        ``graphs_per_update`` transitions sampled uniformly on the device.  Same schedule as train:139-204
+        (epsilon per episode, hard target sync every ``update_target_every`` ticks)."""
+        env, world = self.env, self.env.world
+        B, n, dev = env.num_envs, env.n_agents, env.device
+        G = int(config.get("graphs_per_update", 32))
+        update_target_every = int(config.get("update_target_every", 200))
+        gamma = float(config.get("gamma", 0.99))
+        episodes = config["episodes"]
+        epsilon = config["epsilon"]
+        ring = self.replay_buffer.ring
+        cfg = ops.clone_config(self.graph_cfg, num_envs=B)
+        gcfg = ops.clone_config(self.graph_cfg, num_envs=G)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(int(config.get("sample_seed", self.seed)))
+        env_offset = int(config.get("env_offset", 0))
+        ticks = 0
+        returns = torch.zeros(B, n, dtype=torch.float32, device=dev)
+        hits = torch.zeros(B, dtype=torch.int32, device=dev)
+        stats = {}
+        for episode in range(episodes):
+            env.reset()
+            returns.zero_()
+            hits.zero_()
+            for _ in range(env.max_steps):
+                ticks += 1
+                ops.rollout(cfg, self.w, world.state, 1, returns=returns, hits=hits, epsilon=epsilon, rng_seed=self.seed,
+                            rng_tick0=ticks, env_offset=env_offset, replay=ring)
+                if len(ring) >= G:
+                    idx = torch.randint(0, len(ring), (G,), generator=gen, device=dev, dtype=torch.int64)
+                    ops.dqn_grad(gcfg, self.w, self.w_target, ring, idx, G, gamma=gamma, grad=self._grad, loss=self._loss)
+                    self.opt_step += 1
+                    ops.adam_clip_step(self.w, self._grad, self.exp_avg, self.exp_avg_sq, self.opt_step, self.lr, self.betas,
+                                       self.eps, self.max_norm,
+                                       target=self.w_target if ticks % update_target_every == 0 else None)
+            epsilon = max(config["min_epsilon"], config["epsilon"] * np.exp(-config["epsilon_decay"] * episode))
+            stats = {"episode": episode, "mean_return_agent0": float(returns[:, 0].mean() / n),
+                     "loss": float(self._loss.item()) if self.opt_step else 0.0, "hits_per_env": float(hits.float().mean())}
+            self.episode_losses.append(stats["loss"])
+            self.rewards_buffer.append(torch.tensor(stats["mean_return_agent0"]))
+            if (episode + 1) % 10 == 0:
+                self.episode_rewards.append(sum(self.rewards_buffer) / 10)
+                self.rewards_buffer = []
+            if config.get("verbose", False):
+                print(stats)
+        self.sync_modules()
+        return stats
+
+    def evaluate_policy(self, eval_episodes):
+        """train:206-223 (greedy episodes, mean agent-0 return)."""
+        total = 0
+        n = self.env.n_agents
+        cfg = ops.clone_config(self.graph_cfg, num_envs=self.env.num_envs)
+        for _ in range(eval_episodes):
+            self.env.reset()
+            out = ops.rollout(cfg, self.w, self.env.world.state, self.env.max_steps)
+            total += out["returns"][0, 0].item()
+        return total / eval_episodes
+
+    def save_metrics_to_csv(self):
+        """train:225-231, including its row quirk (Loss column = episode_losses[i // 10])."""
+        os.makedirs(self.stats_path, exist_ok=True)
+        with open(f"{self.stats_path}/experiment_{self.experiment}-seed_{self.seed}.csv", mode="w", newline="") as file:
+            writer = csv.writer(file)
+            writer.writerow(["Episode", "Reward", "Loss"])
+            for i in range(len(self.episode_losses)):
+                if (i + 1) % 10 == 0:
+                    writer.writerow([i, self.episode_rewards[i // 10].item(), self.episode_losses[i // 10]])
+
+
+def set_seed(seed):
+    """train:233-239."""
+    random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False

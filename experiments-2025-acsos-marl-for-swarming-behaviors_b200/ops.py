@@ -12,7 +12,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import SwarmConfig, SwarmTrace, check, lib, ptr, stream_ptr
+from ._lib import SwarmConfig, SwarmReplay, SwarmRolloutOptions, SwarmTrace, check, lib, ptr, stream_ptr
 
 
 def make_config(scenario: int, num_envs: int, n_agents: int, graph_mode: int = _lib.GRAPH_COMPLETE,
@@ -102,12 +102,37 @@ def gatq_forward(cfg: SwarmConfig, weights: torch.Tensor, state: torch.Tensor, w
     return q, act
 
 
+class ReplayRing:
+    """Device replay ring of whole-swarm transitions (GraphReplayBuffer, train:25-48), state-only SoA."""
+
+    def __init__(self, capacity: int, n_agents: int, device):
+        self.capacity, self.n_agents = int(capacity), int(n_agents)
+        self.state = torch.zeros(capacity, n_agents, 4, dtype=torch.float32, device=device)
+        self.next_state = torch.zeros(capacity, n_agents, 4, dtype=torch.float32, device=device)
+        self.actions = torch.zeros(capacity, n_agents, dtype=torch.uint8, device=device)
+        self.rewards = torch.zeros(capacity, n_agents, dtype=torch.float32, device=device)
+        self.position = 0          # next slot to write (train:30,36)
+        self.size = 0              # len(buffer)
+
+    def struct(self) -> SwarmReplay:
+        return SwarmReplay(ptr(self.state), ptr(self.next_state), ptr(self.actions), ptr(self.rewards), self.capacity)
+
+    def advance(self, n: int) -> None:
+        self.position = (self.position + n) % self.capacity
+        self.size = min(self.capacity, self.size + n)
+
+    def __len__(self) -> int:
+        return self.size
+
+
 def rollout(cfg: SwarmConfig, weights: torch.Tensor, state: torch.Tensor, ticks: int, *,
             forced_actions: Optional[torch.Tensor] = None, returns: Optional[torch.Tensor] = None,
-            hits: Optional[torch.Tensor] = None, trace: Optional[Dict[str, bool]] = None
-            ) -> Dict[str, torch.Tensor]:
-    """Fused greedy rollout, in place on ``state``.  ``trace`` names the per-tick records to keep
-    (any of state, actions, q, rewards, flags, contact, edges, dist)."""
+            hits: Optional[torch.Tensor] = None, trace: Optional[Dict[str, bool]] = None,
+            epsilon: float = 0.0, rng_seed: int = 0, rng_tick0: int = 0, env_offset: int = 0,
+            replay: Optional[ReplayRing] = None) -> Dict[str, torch.Tensor]:
+    """Fused (epsilon-)greedy rollout, in place on ``state``.  ``trace`` names the per-tick records to keep
+    (any of state, actions, q, rewards, flags, contact, edges, dist).  With ``replay`` every tick's B
+    transitions are pushed into the ring (and its cursor advanced)."""
     B, N = cfg.num_envs, cfg.n_agents
     _expect(state, torch.float32, B * N * 4, "state")
     _expect(weights, torch.float32, _lib.W_COUNT, "weights")
@@ -136,9 +161,92 @@ def rollout(cfg: SwarmConfig, weights: torch.Tensor, state: torch.Tensor, ticks:
             t = torch.empty(shape, dtype=dt, device=dev)
             setattr(tr, name, ptr(t))
             out["trace_" + name] = t
-    check(lib().swarm_rollout(C.byref(cfg), ptr(weights), ptr(state), int(ticks), ptr(forced_actions), ptr(returns),
+    opts = SwarmRolloutOptions()
+    opts.forced_actions = ptr(forced_actions)
+    opts.epsilon = float(epsilon)
+    opts.rng_seed = int(rng_seed) & 0xFFFFFFFFFFFFFFFF
+    opts.rng_tick0 = int(rng_tick0)
+    opts.env_offset = int(env_offset)
+    rstruct = None
+    if replay is not None:
+        if replay.n_agents != N:
+            raise ValueError("replay ring was built for a different n_agents")
+        rstruct = replay.struct()
+        opts.replay = C.pointer(rstruct)
+        opts.replay_cursor = replay.position
+    check(lib().swarm_rollout(C.byref(cfg), ptr(weights), ptr(state), int(ticks), C.byref(opts), ptr(returns),
                               ptr(hits), C.byref(tr) if tr is not None else None, stream_ptr(dev)))
+    if replay is not None:
+        replay.advance(ticks * B)
     return out
+
+
+def replay_push(cfg: SwarmConfig, ring: ReplayRing, state: torch.Tensor, actions: torch.Tensor,
+                rewards: torch.Tensor, next_state: torch.Tensor) -> None:
+    """GraphReplayBuffer.push for the B envs of cfg (train:32-36)."""
+    B, N = cfg.num_envs, cfg.n_agents
+    _expect(state, torch.float32, B * N * 4, "state")
+    _expect(next_state, torch.float32, B * N * 4, "next_state")
+    _expect(actions, torch.int32, B * N, "actions")
+    _expect(rewards, torch.float32, B * N, "rewards")
+    rs = ring.struct()
+    check(lib().swarm_replay_push(C.byref(cfg), C.byref(rs), ring.position, ptr(state), ptr(actions), ptr(rewards),
+                                  ptr(next_state), stream_ptr(state.device)))
+    ring.advance(B)
+
+
+def replay_gather(ring: ReplayRing, indices: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """GraphReplayBuffer.sample materialisation (train:38-45) for the given slot indices int64[G]."""
+    if indices.dtype != torch.int64:
+        raise TypeError("indices must be int64")
+    G, N, dev = indices.numel(), ring.n_agents, ring.state.device
+    cfg = make_config(_lib.SCENARIO_GOTO, max(G, 1), N)
+    out = {"state": torch.empty(G, N, 4, dtype=torch.float32, device=dev),
+           "actions": torch.empty(G, N, dtype=torch.int32, device=dev),
+           "rewards": torch.empty(G, N, dtype=torch.float32, device=dev),
+           "next_state": torch.empty(G, N, 4, dtype=torch.float32, device=dev)}
+    rs = ring.struct()
+    check(lib().swarm_replay_gather(C.byref(cfg), C.byref(rs), ptr(indices), G, ptr(out["state"]), ptr(out["actions"]),
+                                    ptr(out["rewards"]), ptr(out["next_state"]), stream_ptr(dev)))
+    return out
+
+
+def dqn_grad(cfg: SwarmConfig, online: torch.Tensor, target: torch.Tensor, batch: ReplayRing,
+             indices: Optional[torch.Tensor], n_graphs: int, gamma: float = 0.99, loss_scale: Optional[float] = None,
+             want_td: bool = False, grad: Optional[torch.Tensor] = None, loss: Optional[torch.Tensor] = None
+             ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+    """train_step_dqn's loss + gradient (train:116-124) over n_graphs transitions of ``batch`` (slots
+    ``indices`` if given).  Returns (grad f32[1673], loss f32[1], td f32[G,N] or None)."""
+    N, dev = cfg.n_agents, online.device
+    _expect(online, torch.float32, _lib.W_COUNT, "online weights")
+    _expect(target, torch.float32, _lib.W_COUNT, "target weights")
+    if indices is not None:
+        if indices.dtype != torch.int64 or indices.numel() != n_graphs:
+            raise TypeError("indices must be int64[n_graphs]")
+    if loss_scale is None:
+        loss_scale = 1.0 / (n_graphs * N)
+    grad = grad if grad is not None else torch.empty(_lib.W_COUNT, dtype=torch.float32, device=dev)
+    loss = loss if loss is not None else torch.empty(1, dtype=torch.float32, device=dev)
+    td = torch.empty(n_graphs, N, dtype=torch.float32, device=dev) if want_td else None
+    wb = int(lib().swarm_dqn_workspace_bytes(C.byref(cfg), n_graphs))
+    ws = torch.empty(max(wb, 1), dtype=torch.uint8, device=dev)
+    rs = batch.struct()
+    check(lib().swarm_dqn_grad(C.byref(cfg), ptr(online), ptr(target), C.byref(rs), ptr(indices), n_graphs, float(gamma),
+                               float(loss_scale), ptr(grad), ptr(loss), ptr(td), ptr(ws), wb, stream_ptr(dev)))
+    return grad, loss, td
+
+
+def adam_clip_step(weights: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
+                   step: int, lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+                   max_norm: float = 1.0, target: Optional[torch.Tensor] = None,
+                   grad_norm: Optional[torch.Tensor] = None) -> None:
+    """clip_grad_norm_(max_norm) + torch.optim.Adam step on the packed weights, in place (train:125-126);
+    optionally copies the new weights into ``target`` (train:131-133)."""
+    for name, t in (("weights", weights), ("grad", grad), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
+        _expect(t, torch.float32, _lib.W_COUNT, name)
+    check(lib().swarm_adam_clip_step(ptr(weights), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), int(step), float(lr),
+                                     float(betas[0]), float(betas[1]), float(eps), float(max_norm), ptr(target),
+                                     ptr(grad_norm), stream_ptr(weights.device)))
 
 
 def csr_from_edges(edge_index: torch.Tensor, n_nodes: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:

@@ -143,14 +143,70 @@ int swarm_csr_from_edges(int32_t n_nodes, int64_t n_edges, const int64_t* edge_s
                          int32_t* row_ptr, int32_t* src, int32_t* perm, void* workspace, int64_t workspace_bytes,
                          void* stream);
 
-/* Fused greedy rollout: `ticks` iterations of [graph build -> GCN forward -> argmax -> env step]
- * (the inner loops of simulator.py:59-93 and train_gcn_dqn.py:153-178 without exploration) with the
- * state resident on chip.  state is updated in place; returns float[B*N] accumulates each agent's
- * rewards (+=), hits int32[B] accumulates obstacles_hits() per tick (+=); both optional.
- * forced_actions (optional) int32[ticks][B*N]: entries >= 0 override the greedy action. */
+/* Device replay ring of whole-swarm transitions (GraphReplayBuffer, train_gcn_dqn.py:25-48, capacity 1e6 at
+ * train:86).  Only the world state is stored (37 B per agent and transition); node features and graphs are
+ * rebuilt from it on the fly. */
+typedef struct SwarmReplay {
+  float* state;          /* [capacity][N][4] s                      */
+  float* next_state;     /* [capacity][N][4] s'                     */
+  uint8_t* actions;      /* [capacity][N]    a                      */
+  float* rewards;        /* [capacity][N]    r                      */
+  int64_t capacity;      /* slots (one slot = one env transition)   */
+} SwarmReplay;
+
+typedef struct SwarmRolloutOptions {
+  const int32_t* forced_actions; /* optional [ticks][B*N]; entries >= 0 override the policy's action        */
+  float epsilon;                 /* epsilon-greedy (train:164-167): one coin per env and tick; 0 = greedy   */
+  uint64_t rng_seed;             /* counter-based device RNG stream (seed, env, tick0 + tick)               */
+  int64_t rng_tick0;
+  const SwarmReplay* replay;     /* optional: push (s, a, r, s') of every env and tick (train:171-172) ...  */
+  int64_t replay_cursor;         /* ... at slot (cursor + tick*B + env) mod capacity                        */
+  int64_t env_offset;            /* global index of env 0 (RNG streams of an env shard)                     */
+} SwarmRolloutOptions;
+
+/* Fused rollout: `ticks` iterations of [graph build -> GCN forward -> (epsilon-)greedy argmax -> env step]
+ * (the inner loops of simulator.py:59-93 and train_gcn_dqn.py:153-178) with the state resident on chip.
+ * state is updated in place; returns float[B*N] accumulates each agent's rewards (+=), hits int32[B]
+ * accumulates obstacles_hits() per tick (+=); opts, returns, hits and trace are optional. */
 int swarm_rollout(const SwarmConfig* cfg, const float* weights, float* state, int32_t ticks,
-                  const int32_t* forced_actions, float* returns, int32_t* hits, const SwarmTrace* trace,
+                  const SwarmRolloutOptions* opts, float* returns, int32_t* hits, const SwarmTrace* trace,
                   void* stream);
+
+/* GraphReplayBuffer.push for B envs at once (train:32-36): slots (cursor + b) mod capacity. */
+int swarm_replay_push(const SwarmConfig* cfg, const SwarmReplay* replay, int64_t cursor, const float* state,
+                      const int32_t* actions, const float* rewards, const float* next_state, void* stream);
+
+/* GraphReplayBuffer.sample materialisation (train:38-45): gathers n_graphs slots (indices int64[n_graphs])
+ * into dense arrays state/next_state float[n_graphs][N][4], actions int32[n_graphs][N], rewards
+ * float[n_graphs][N]. */
+int swarm_replay_gather(const SwarmConfig* cfg, const SwarmReplay* replay, const int64_t* indices,
+                        int32_t n_graphs, float* state, int32_t* actions, float* rewards, float* next_state,
+                        void* stream);
+
+/* One DQN loss + gradient (train_step_dqn, train_gcn_dqn.py:116-124) over n_graphs whole-swarm transitions
+ * taken from `batch` (slot g, or slot indices[g] when indices != NULL): values = Q_online(s)[a], targets =
+ * r + gamma * max_a Q_target(s') (no terminal mask), loss = mean((values - targets)^2) over all
+ * n_graphs*N nodes, gradient w.r.t. the 1673 online weights by a hand-written backward pass (deterministic:
+ * per-CTA partial sums reduced in a fixed order, no atomics).  cfg->graph_mode selects the per-env graph;
+ * cfg->num_envs is ignored.  `loss_scale` multiplies the loss (1/total node count; pass the global count when
+ * the batch is one shard of a distributed update).  Outputs: grad float[1673], loss float[1] (both
+ * overwritten); td (optional) float[n_graphs*N] = values - targets.  workspace:
+ * swarm_dqn_workspace_bytes(cfg, n_graphs). */
+int64_t swarm_dqn_workspace_bytes(const SwarmConfig* cfg, int32_t n_graphs);
+int swarm_dqn_grad(const SwarmConfig* cfg, const float* online_weights, const float* target_weights,
+                   const SwarmReplay* batch, const int64_t* indices, int32_t n_graphs, float gamma,
+                   float loss_scale, float* grad, float* loss, float* td, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+
+/* clip_grad_norm_(params, max_norm) + Adam step (train:125-126; torch.optim.Adam defaults lr 1e-3,
+ * betas (0.9, 0.999), eps 1e-8) on the packed weights, in place; exp_avg / exp_avg_sq float[1673];
+ * `step` is the 1-based step count.  The gradient norm follows torch: per-tensor 2-norms, then the 2-norm
+ * of those; clip coefficient max_norm / (norm + 1e-6), clamped to 1.  If target_weights != NULL the updated
+ * weights are also copied there (target_model.load_state_dict, train:131-133).  grad_norm (optional)
+ * float[1] receives the pre-clip norm.  max_norm <= 0 disables clipping. */
+int swarm_adam_clip_step(float* weights, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t step,
+                         double lr, double beta1, double beta2, double eps, double max_norm,
+                         float* target_weights, float* grad_norm, void* stream);
 
 #ifdef __cplusplus
 }
