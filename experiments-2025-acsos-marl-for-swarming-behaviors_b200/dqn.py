@@ -20,7 +20,7 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
-from . import _lib, ops
+from . import _lib, ops, parallel
 from .gcn import GCN
 from .graph import Batch, Data, node_features, stack_observations
 
@@ -231,8 +231,14 @@ class DQNTrainer:
         cfg = ops.clone_config(self.graph_cfg, num_envs=B)
         gcfg = ops.clone_config(self.graph_cfg, num_envs=G)
         gen = torch.Generator(device=dev)
-        gen.manual_seed(int(config.get("sample_seed", self.seed)))
-        env_offset = int(config.get("env_offset", 0))
+        rank = torch.distributed.get_rank() if parallel.world_size() > 1 else 0
+        gen.manual_seed(int(config.get("sample_seed", self.seed)) + 7919 * rank)
+        env_offset = int(config.get("env_offset", rank * B))
+        # env-sharded data parallelism: G graphs per rank, loss = mean over the global batch, gradient summed
+        # over ranks, identical clip + Adam everywhere (weights stay replicated; target sync is local)
+        loss_scale = parallel.global_loss_scale(G, n)
+        parallel.broadcast_weights(self.w)
+        self.w_target.copy_(self.w)
         ticks = 0
         returns = torch.zeros(B, n, dtype=torch.float32, device=dev)
         hits = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -247,7 +253,9 @@ class DQNTrainer:
                             rng_tick0=ticks, env_offset=env_offset, replay=ring)
                 if len(ring) >= G:
                     idx = torch.randint(0, len(ring), (G,), generator=gen, device=dev, dtype=torch.int64)
-                    ops.dqn_grad(gcfg, self.w, self.w_target, ring, idx, G, gamma=gamma, grad=self._grad, loss=self._loss)
+                    ops.dqn_grad(gcfg, self.w, self.w_target, ring, idx, G, gamma=gamma, loss_scale=loss_scale,
+                                 grad=self._grad, loss=self._loss)
+                    parallel.allreduce_gradient(self._grad, self._loss)
                     self.opt_step += 1
                     ops.adam_clip_step(self.w, self._grad, self.exp_avg, self.exp_avg_sq, self.opt_step, self.lr, self.betas,
                                        self.eps, self.max_norm,

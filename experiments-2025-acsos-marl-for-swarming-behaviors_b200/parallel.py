@@ -1,0 +1,84 @@
+"""Multi-GPU plumbing: one process per GPU, envs sharded across ranks, no data-path collective for rollouts.
+
+The reference is single-process; the only exchange the sharded DQN needs is the all-reduce of
+the 1 673-float Q-network gradient per update (6 692 B, latency bound) plus one weight broadcast at start.
+Every rank then applies the identical clip + Adam step to the identical reduced gradient, so the online and
+target weights stay replicated and the hard target sync (train:131-133) is a local copy.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass(frozen=True)
+class EnvShard:
+    """Contiguous env range [offset, offset + count) owned by ``rank`` out of ``total`` envs."""
+    rank: int
+    world: int
+    total: int
+    offset: int
+    count: int
+
+
+def shard_envs(total: int, rank: int, world: int) -> EnvShard:
+    """Split ``total`` envs into ``world`` contiguous ranges whose sizes differ by at most one."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of size {world}")
+    if total < world:
+        raise ValueError(f"cannot shard {total} envs over {world} ranks")
+    base, extra = divmod(total, world)
+    count = base + (1 if rank < extra else 0)
+    offset = rank * base + min(rank, extra)
+    return EnvShard(rank, world, total, offset, count)
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """(rank, world, local_rank) from the torchrun environment; initialises the process group when
+    WORLD_SIZE > 1 (NCCL on GPUs, gloo otherwise)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kwargs = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kwargs["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend, **kwargs)
+    return rank, world, local
+
+
+def world_size() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def broadcast_weights(packed: torch.Tensor, src: int = 0) -> torch.Tensor:
+    """Initial weight broadcast so that every rank starts from rank ``src``'s Q-network."""
+    if world_size() > 1:
+        dist.broadcast(packed, src=src)
+    return packed
+
+
+def allreduce_gradient(grad: torch.Tensor, loss: Optional[torch.Tensor] = None) -> None:
+    """Sum the per-rank partial gradients (each already scaled by 1 / global node count) in place.  With
+    ``loss`` the per-rank partial losses are summed in the same collective round."""
+    if world_size() == 1:
+        return
+    if loss is None:
+        dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+        return
+    buf = torch.cat([grad.reshape(-1), loss.reshape(-1)])
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    grad.copy_(buf[:grad.numel()].reshape(grad.shape))
+    loss.copy_(buf[grad.numel():].reshape(loss.shape))
+
+
+def global_loss_scale(local_graphs: int, n_agents: int) -> float:
+    """1 / (total nodes of the update over all ranks): the mean of train:122 taken over the global batch."""
+    return 1.0 / (local_graphs * world_size() * n_agents)

@@ -1,0 +1,107 @@
+"""The C-ABI shared library: loads, exports every symbol include/swarm_b200.h declares, agrees with the
+ctypes struct layouts, and validates arguments before touching a device (so these run without a GPU)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "swarm_b200.h")
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import swarm_b200
+    swarm_b200._build.build()
+    return swarm_b200
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(swarm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(sb):
+    names = _declared_functions()
+    assert len(names) >= 15
+    lib = C.CDLL(sb._build.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/swarm_b200.h but not exported"
+    # and every declared function has a ctypes signature in the binding
+    assert set(names) == set(sb._lib._SIGNATURES)
+
+
+def test_only_c_abi_is_exported(sb):
+    out = subprocess.run(["nm", "-D", "--defined-only", sb._build.LIB_PATH], capture_output=True, text=True).stdout
+    exported = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    ours = [s for s in exported if s.startswith("swarm_")]
+    assert sorted(ours) == _declared_functions()
+
+
+def test_struct_layout_matches_header(sb, tmp_path):
+    """sizeof / offsetof of the C structs, compiled with gcc from the header, equal the ctypes mirrors."""
+    prog = tmp_path / "layout.c"
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "swarm_b200.h"\nint main(){'
+                    'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(SwarmConfig), offsetof(SwarmConfig, num_envs),'
+                    'offsetof(SwarmConfig, dt), offsetof(SwarmConfig, obstacle_weight), sizeof(SwarmTrace), sizeof(SwarmReplay),'
+                    'sizeof(SwarmRolloutOptions), offsetof(SwarmRolloutOptions, replay), offsetof(SwarmRolloutOptions, env_offset));return 0;}')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
+    L = sb._lib
+    exp = [C.sizeof(L.SwarmConfig), L.SwarmConfig.num_envs.offset, L.SwarmConfig.dt.offset,
+           L.SwarmConfig.obstacle_weight.offset, C.sizeof(L.SwarmTrace), C.sizeof(L.SwarmReplay),
+           C.sizeof(L.SwarmRolloutOptions), L.SwarmRolloutOptions.replay.offset, L.SwarmRolloutOptions.env_offset.offset]
+    assert got == exp
+
+
+def test_default_config_is_the_reference_world(sb):
+    cfg = sb.ops.make_config(sb._lib.SCENARIO_OBSTACLE_AVOIDANCE, 3, 12)
+    import numpy as np
+    f = np.float32
+    assert (cfg.num_envs, cfg.n_agents, cfg.knn_k) == (3, 12, 10)                    # simulator.py:19 ships k = 10
+    assert (cfg.dt, cfg.drag, cfg.collision_force, cfg.contact_margin) == (f(0.1), f(0.25), f(100.0), f(1e-3))
+    assert (cfg.agent_radius, cfg.landmark_radius) == (f(0.05), f(0.05))           # vmas default radius, not agent_radius=0.1
+    assert (cfg.goal_x, cfg.goal_y, cfg.obstacle_x, cfg.obstacle_y) == (f(-0.8), f(0.8), f(-0.1), f(0.1))
+    assert (cfg.hit_distance, cfg.penalty_distance, cfg.obstacle_weight, cfg.grid_spacing) == (f(0.2), f(1.0), f(2.5), 0.15)
+    assert sb.ops.edges_per_env(cfg) == 12 * 11 + 1                                   # complete + (0,0), train:101-108
+    cfg.graph_mode = sb._lib.GRAPH_KNN
+    assert sb.ops.edges_per_env(cfg) == 2 * 10 * 12 + 1                               # simulator.py:15-24
+
+
+def test_argument_validation_without_device(sb):
+    lib = sb._lib.lib()
+    cfg = sb.ops.make_config(sb._lib.SCENARIO_GOTO, 1, 5, sb._lib.GRAPH_KNN, 10)
+    # k > n: torch.topk's error in the reference (simulator.py:19 with n_agents < 10)
+    assert lib.swarm_graph_build(C.byref(cfg), 8, 8, None, None) == -1
+    assert b"selected index k out of range" in lib.swarm_last_error()
+    cfg.knn_k = 5
+    assert lib.swarm_graph_build(C.byref(cfg), None, None, None, None) == -1
+    cfg.n_agents = 500
+    assert lib.swarm_sim_step(C.byref(cfg), 8, 8, 8, None, None, None, None, None, None) == -2
+    assert b"n_agents" in lib.swarm_last_error()
+    cfg.n_agents, cfg.scenario = 5, 7
+    assert lib.swarm_reset_grid(C.byref(cfg), 8, 8, None) == -1
+    assert lib.swarm_adam_clip_step(8, 8, 8, 8, 0, 1e-3, 0.9, 0.999, 1e-8, 1.0, None, None, None) == -1   # step is 1-based
+    assert lib.swarm_adam_clip_step(8, 8, 8, 8, 1, 1e-3, 1.5, 0.999, 1e-8, 1.0, None, None, None) == -1   # beta1 out of range
+    assert lib.swarm_csr_workspace_bytes(10, 100) > 0 and lib.swarm_gatq_workspace_bytes(10) >= 10 * 36 * 4
+
+
+def test_no_cpu_fallback(sb):
+    import torch
+    with pytest.raises(sb.SwarmError, match="CUDA"):
+        sb.make_env(sb.GoToPositionScenario(), num_envs=1, device="cpu", continuous_actions=False, max_steps=5,
+                    dict_spaces=True, seed=0, n_agents=5)
+    with pytest.raises(sb.SwarmError):
+        sb.ops.reset_grid(sb.ops.make_config(0, 2, 5), torch.zeros(2, 2))
+    model = sb.GCN(7, 32, 9)
+    with pytest.raises(sb.SwarmError, match="CUDA"):
+        model(sb.Data(x=torch.zeros(5, 7), edge_index=torch.zeros(2, 3, dtype=torch.long)))
+    # the oracle is test infrastructure: nothing in the product package imports it
+    pkg = os.path.join(ROOT, "experiments-2025-acsos-marl-for-swarming-behaviors_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            assert "oracle" not in open(os.path.join(pkg, f)).read(), f"{f} mentions the oracle"

@@ -1,0 +1,68 @@
+"""csrc/knn_select.h (the tie-exact selection the kNN graph kernel runs per thread) against torch.topk on
+the CPU -- the call the reference makes at src/simulation/simulator.py:19.  Grid start states make exact
+distance ties the common case, so tie-heavy rows are the point of this test."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory):
+    out = tmp_path_factory.mktemp("knn") / "libknn_shim.so"
+    src = os.path.join(ROOT, "tests", "host_shim", "knn_shim.cpp")
+    inc = os.path.join(ROOT, "experiments-2025-acsos-marl-for-swarming-behaviors_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", inc, src, "-o", str(out)], check=True)
+    lib = ctypes.CDLL(str(out))
+    lib.swarm_host_topk_smallest.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    return lib
+
+
+def _ours(lib, values: torch.Tensor, k: int) -> torch.Tensor:
+    rows, n = values.shape
+    v = values.contiguous()
+    out = torch.empty(rows, k, dtype=torch.int32)
+    lib.swarm_host_topk_smallest(v.data_ptr(), rows, n, k, out.data_ptr())
+    return out.long()
+
+
+def _grid_distance_rows(n: int, rng: torch.Generator, jitter: float) -> torch.Tensor:
+    """distance rows of n agents on the scenarios' 0.15-spaced start grid (ties!), optionally perturbed."""
+    cols = int(np.ceil(np.sqrt(n)))
+    pts = torch.tensor([[(i % cols) * 0.15, (i // cols) * 0.15] for i in range(n)], dtype=torch.float32)
+    pts = pts + torch.randn(2, generator=rng)
+    if jitter:
+        pts = pts + jitter * torch.randn(n, 2, generator=rng)
+    return torch.linalg.norm(pts.unsqueeze(0) - pts.unsqueeze(1), dim=-1)      # [i, j] = ||p_j - p_i||
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 16, 20, 29, 32, 64, 100])
+def test_matches_torch_topk_on_grids(shim, n):
+    g = torch.Generator().manual_seed(n)
+    rows = torch.cat([_grid_distance_rows(n, g, j) for j in (0.0, 0.0, 0.0, 1e-3, 0.05)])
+    for k in sorted({1, min(2, n), min(3, n), min(5, n), min(10, n), min(17, n), n}):
+        ref = torch.topk(rows, k, dim=-1, largest=False).indices
+        assert torch.equal(_ours(shim, rows, k), ref), f"n={n} k={k}"
+
+
+@pytest.mark.parametrize("n,k", [(5, 5), (12, 5), (12, 10), (32, 10), (32, 17), (40, 5), (128, 10), (128, 2), (1024, 10), (1024, 17)])
+def test_matches_torch_topk_on_tie_heavy_random_rows(shim, n, k):
+    g = torch.Generator().manual_seed(1000 + n + k)
+    # few distinct values -> massive ties; mixes both torch branches (nth_element+sort, partial_sort for 64k <= n)
+    rows = torch.randint(0, 7, (400, n), generator=g).float() * 0.25
+    rows2 = torch.rand(200, n, generator=g)
+    allrows = torch.cat([rows, rows2])
+    ref = torch.topk(allrows, k, dim=-1, largest=False).indices
+    assert torch.equal(_ours(shim, allrows, k), ref)
+
+
+def test_nan_ordering_matches_torch(shim):
+    rows = torch.tensor([[0.3, float("nan"), 0.1, 0.1, float("nan"), 0.2, 0.0, 5.0]] * 3)
+    for k in (1, 3, 6, 8):
+        ref = torch.topk(rows, k, dim=-1, largest=False).indices
+        assert torch.equal(_ours(shim, rows, k), ref)
