@@ -243,12 +243,12 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-        step_e2e()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+        step_e2e()
     ms_res = timed(step_resident, args.steps)
 
     # the dominant kernel alone (rollout launch), CUDA events on the launching stream
@@ -265,6 +265,7 @@ def run_ours(args):
     barrier()
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
     ms_e2e = timed(step_e2e, args.steps)
+    dqn_stats = measure_dqn(sb, ops, dev, cfg, weights, centers, dist, barrier, stream, rank, world)
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -301,6 +302,7 @@ def run_ours(args):
                           "peak_source": f"148 SMs x 128 FMA lanes x 2 x {sm_mhz:.0f} MHz (sampled under load)"},
         "clocks": clocks,
     }
+    line["dqn"] = dqn_stats
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_single()
     print(json.dumps(line), flush=True)
@@ -308,11 +310,65 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def measure_dqn(sb, ops, dev, cfg, weights, centers, dist, barrier, stream, rank, world, ticks=100):
+    """BASELINE.json configs[1]: full DQN train step on the same envs -- per tick one fused
+    [Q -> eps-greedy -> step -> replay push] launch over all envs, one sample of G whole-swarm transitions, one
+    loss + backward, (gradient all-reduce,) clip + Adam.  Reported for G = 32 (the reference's batch, train:175)
+    and G = 4096 (one update touching as many transitions as one tick produces)."""
+    from swarm_b200 import parallel
+    B, N = cfg.num_envs, cfg.n_agents
+    out = {}
+    for G in (32, 4096):
+        ring = ops.ReplayRing(1 << 20, N, dev)
+        w = weights.clone()
+        w_t = weights.clone()
+        m, v = torch.zeros_like(w), torch.zeros_like(w)
+        grad = torch.empty_like(w)
+        loss = torch.empty(1, device=dev)
+        state = ops.reset_grid(cfg, centers)
+        gcfg = ops.clone_config(cfg, num_envs=G)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(rank)
+        scale = parallel.global_loss_scale(G, N)
+        step = 0
+
+        def tick(t):
+            nonlocal step
+            ops.rollout(cfg, w, state, 1, epsilon=0.3, rng_seed=rank, rng_tick0=t, env_offset=rank * B, replay=ring)
+            idx = torch.randint(0, len(ring), (G,), generator=gen, device=dev, dtype=torch.int64)
+            ops.dqn_grad(gcfg, w, w_t, ring, idx, G, loss_scale=scale, grad=grad, loss=loss)
+            parallel.allreduce_gradient(grad, loss)
+            step += 1
+            ops.adam_clip_step(w, grad, m, v, step, target=w_t if step % 200 == 0 else None)
+
+        for t in range(10):
+            tick(t)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for t in range(ticks):
+            tick(10 + t)
+        b.record(stream)
+        barrier()
+        ms = a.elapsed_time(b)
+        if dist is not None:
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        out[f"G{G}"] = {"graphs_per_update_per_gpu": G, "updates_per_s": ticks / (ms * 1e-3),
+                        "train_agent_steps_per_s": world * B * N * ticks / (ms * 1e-3),
+                        "transitions_trained_per_s": world * G * ticks / (ms * 1e-3), "ms_per_tick": ms / ticks,
+                        "loss": float(loss.item())}
+    out["note"] = ("one train tick = rollout tick of all envs (eps 0.3) + replay push + sample + TD target/loss/backward + "
+                   "grad all-reduce (N>1) + clip + Adam; eager launches, no CUDA graph")
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
