@@ -1,6 +1,7 @@
 // api.cu -- extern "C" entry points of libswarm_b200.so (see include/swarm_b200.h).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -87,7 +88,14 @@ int fill_params(TileParams& p, const SwarmConfig* cfg, int mode) {
   p.dmin_ao = cfg->landmark_radius + cfg->agent_radius;
   p.qmax_aa = sq_threshold(p.dmin_aa);
   p.qmax_ao = sq_threshold(p.dmin_ao);
-  const TileLayout L = tile_layout(mode, kTileThreads, n, cfg->knn_k, p.maxdeg, cfg->graph_mode);
+  // dense contractions on the tensor cores (tcgen05 3xTF32) unless SWARM_TC=0 selects the CUDA-core FFMA path
+  const char* tc_env = std::getenv("SWARM_TC");
+  p.use_tc = (mode == MODE_ROLLOUT || mode == MODE_FORWARD) && !(tc_env && tc_env[0] == '0');
+  TileLayout L = tile_layout(mode, kTileThreads, n, cfg->knn_k, p.maxdeg, cfg->graph_mode, p.use_tc != 0);
+  if (L.total > 227 * 1024 && p.use_tc) {
+    p.use_tc = 0;
+    L = tile_layout(mode, kTileThreads, n, cfg->knn_k, p.maxdeg, cfg->graph_mode, false);
+  }
   if (L.total > 227 * 1024) return fail(SWARM_ERR_UNSUPPORTED, "shared-memory tile exceeds 227 KB for this (N, k)");
   return SWARM_OK;
 }

@@ -126,24 +126,21 @@ __device__ __forceinline__ void tile_write_edges(const TileGraphSmem& g, const T
   if (i == 0) { r0[E - 1] = 0; r1[E - 1] = 0; }
 }
 
-// GATConv forward for the node of this thread: projects x, publishes (h, alpha_src) to the tile, runs the
-// edge softmax over the in-edge list in edge-list order (torch_geometric.utils.softmax: max, exp(z - max),
-// sum + 1e-16, divide) and aggregates.  On return agg = sum_e alpha_e h_j (bias not yet added), the attention
-// coefficients alpha_e are left in g.swt[e][tid], and adst is this node's alpha_dst.  Contains one barrier.
-__device__ __forceinline__ void tile_gat_conv(const TileGraphSmem& g, const TileThread& t, const float* sw,
-                                              const float (&x)[7], int deg, float (&agg)[32], float& adst) {
-  const int T = kTileThreads;
-  adst = 0.0f;
-  if (t.active) {
-    float h[32];
-    float asrc;
-    gat_project(x, sw, h, asrc, adst);
-    float4* hrow = reinterpret_cast<float4*>(g.sh + t.tid * kHPad);
+// Publishes this node's projected features h and alpha_src to the tile (read by its neighbours).
+__device__ __forceinline__ void tile_gat_publish(const TileGraphSmem& g, const TileThread& t, const float (&h)[32],
+                                                 float asrc) {
+  float4* hrow = reinterpret_cast<float4*>(g.sh + t.tid * kHPad);
 #pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) hrow[c4] = make_float4(h[4 * c4], h[4 * c4 + 1], h[4 * c4 + 2], h[4 * c4 + 3]);
-    g.sas[t.tid] = asrc;
-  }
-  __syncthreads();
+  for (int c4 = 0; c4 < 8; ++c4) hrow[c4] = make_float4(h[4 * c4], h[4 * c4 + 1], h[4 * c4 + 2], h[4 * c4 + 3]);
+  g.sas[t.tid] = asrc;
+}
+
+// Edge softmax over the in-edge list of this node in edge-list order (torch_geometric.utils.softmax: max,
+// exp(z - max), sum + 1e-16, divide) followed by the aggregation.  On return agg = sum_e alpha_e h_j (bias not yet
+// added) and the attention coefficients alpha_e are left in g.swt[e][tid].
+__device__ __forceinline__ void tile_gat_attend(const TileGraphSmem& g, const TileThread& t, int deg, float adst,
+                                                float (&agg)[32]) {
+  const int T = kTileThreads;
 #pragma unroll
   for (int cc = 0; cc < 32; ++cc) agg[cc] = 0.0f;
   if (t.active) {
@@ -167,6 +164,21 @@ __device__ __forceinline__ void tile_gat_conv(const TileGraphSmem& g, const Tile
       gat_accumulate(agg, alpha, reinterpret_cast<const float4*>(g.sh + (t.envbase + j) * kHPad));
     }
   }
+}
+
+// GATConv forward for the node of this thread (CUDA-core projection): projects x, publishes (h, alpha_src),
+// one block barrier, then attention + aggregation.  adst is this node's alpha_dst.
+__device__ __forceinline__ void tile_gat_conv(const TileGraphSmem& g, const TileThread& t, const float* sw,
+                                              const float (&x)[7], int deg, float (&agg)[32], float& adst) {
+  adst = 0.0f;
+  if (t.active) {
+    float h[32];
+    float asrc;
+    gat_project(x, sw, h, asrc, adst);
+    tile_gat_publish(g, t, h, asrc);
+  }
+  __syncthreads();
+  tile_gat_attend(g, t, deg, adst, agg);
 }
 
 // counter-based RNG for device-side exploration (documented deviation from the reference's Python

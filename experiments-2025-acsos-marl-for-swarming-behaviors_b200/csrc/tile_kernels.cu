@@ -10,7 +10,7 @@
 //   MODE_STEP     one world step with given actions                       (vmas Environment.step)
 //   MODE_GRAPH    edge list / neighbour table export                      (train:94-110, simulator:9-26)
 // so the stand-alone kernels and the fused rollout are consistent by construction.
-#include "tile_device.cuh"
+#include "tile_tc_device.cuh"
 
 namespace swarm {
 
@@ -47,7 +47,7 @@ __device__ __forceinline__ void tile_world_step(const TileParams& p, const TileT
   integrate(s, fx, fy, c.dt, p.one_minus_drag);
 }
 
-template <int MODE>
+template <int MODE, bool TC>
 __global__ void __launch_bounds__(kTileThreads) tile_kernel(const __grid_constant__ TileParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr bool kQ = (MODE == MODE_ROLLOUT || MODE == MODE_FORWARD);
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(const __grid_constan
   const int tid = t.tid;
   const long long BN = (long long)c.num_envs * N;
 
-  const TileLayout L = tile_layout(MODE, T, N, K, p.maxdeg, c.graph_mode);
+  const TileLayout L = tile_layout(MODE, T, N, K, p.maxdeg, c.graph_mode, TC);
   float* sw = reinterpret_cast<float*>(smem + L.w);
   float4* sst = reinterpret_cast<float4*>(smem + L.st);
   float* sred = reinterpret_cast<float*>(smem + L.red);
@@ -76,7 +76,28 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(const __grid_constan
   g.ski = smem + L.ki;
   g.snbr = smem + L.nbr;
 
-  if (kQ) stage_weights(p.weights, sw, tid, T);
+  TileTcSmem ts;
+  uint32_t tmem = 0, parity = 0;
+  if (TC) {
+    ts.a = smem + L.tc_a;
+    ts.x = smem + L.tc_x;
+    ts.w0 = smem + L.tc_w0;
+    ts.w1 = smem + L.tc_w1;
+    ts.w2 = smem + L.tc_w2;
+    ts.vec = reinterpret_cast<float*>(smem + L.tc_vec);
+    ts.bar = reinterpret_cast<uint64_t*>(smem + L.tc_bar);
+    ts.tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tc_bar + 8);
+    stage_weights_tc(p.weights, ts, tid, T);
+    if (tid == 0) tc::mbar_init(ts.bar, 1);
+    if ((tid >> 5) == 0) tc::tmem_alloc(ts.tmem_slot, kTmemCols);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    tmem = *ts.tmem_slot;
+  } else if (kQ) {
+    stage_weights(p.weights, sw, tid, T);
+  }
 
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (t.active) s = reinterpret_cast<const float4*>(p.state_in)[t.gidx];
@@ -112,12 +133,16 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(const __grid_constan
     if (kQ) {
       // node features (train:95-99): [pos, vel, goal, agent id]
       const float x[7] = {s.x, s.y, s.z, s.w, c.goal_x, c.goal_y, (float)t.i};
-      float a1[32];
-      float adst;
-      tile_gat_conv(g, t, sw, x, deg, a1, adst);
+      float q[9];
+      if (TC) {
+        action = tile_q_forward_tc(g, ts, t, tmem, x, deg, parity, q);
+      } else {
+        float a1[32];
+        float adst;
+        tile_gat_conv(g, t, sw, x, deg, a1, adst);
+        if (t.active) action = gat_head(a1, sw, q);
+      }
       if (t.active) {
-        float q[9];
-        action = gat_head(a1, sw, q);
         if (MODE == MODE_FORWARD) {
           if (p.q_out) {
 #pragma unroll
@@ -229,6 +254,11 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(const __grid_constan
       }
     }
   }
+  if (TC) {
+    tc::fence_before_sync();
+    __syncthreads();
+    if ((tid >> 5) == 0) tc::tmem_dealloc(tmem, kTmemCols);
+  }
 }
 
 // ---- replay ring copies ---------------------------------------------------------------------
@@ -287,28 +317,27 @@ cudaError_t launch_replay_gather(const SwarmReplay& r, const int64_t* indices, i
 }
 
 // explicit instantiations + launcher
-cudaError_t launch_tile(int mode, const TileParams& p, cudaStream_t stream) {
+template <int MODE, bool TC>
+static cudaError_t launch_tile_impl(const TileParams& p, cudaStream_t stream) {
   const SwarmConfig& c = p.cfg;
-  const TileLayout L = tile_layout(mode, kTileThreads, c.n_agents, c.knn_k, p.maxdeg, c.graph_mode);
+  const TileLayout L = tile_layout(MODE, kTileThreads, c.n_agents, c.knn_k, p.maxdeg, c.graph_mode, TC);
   const int grid = (c.num_envs + p.epb - 1) / p.epb;
-  cudaError_t err = cudaSuccess;
-#define SWARM_LAUNCH(M)                                                                              \
-  do {                                                                                               \
-    if (L.total > 48 * 1024) {                                                                       \
-      err = cudaFuncSetAttribute(tile_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total); \
-      if (err != cudaSuccess) return err;                                                            \
-    }                                                                                                \
-    tile_kernel<M><<<grid, kTileThreads, L.total, stream>>>(p);                                      \
-  } while (0)
+  if (L.total > 48 * 1024) {
+    cudaError_t err = cudaFuncSetAttribute(tile_kernel<MODE, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+    if (err != cudaSuccess) return err;
+  }
+  tile_kernel<MODE, TC><<<grid, kTileThreads, L.total, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tile(int mode, const TileParams& p, cudaStream_t stream) {
   switch (mode) {
-    case MODE_ROLLOUT: SWARM_LAUNCH(MODE_ROLLOUT); break;
-    case MODE_FORWARD: SWARM_LAUNCH(MODE_FORWARD); break;
-    case MODE_STEP: SWARM_LAUNCH(MODE_STEP); break;
-    case MODE_GRAPH: SWARM_LAUNCH(MODE_GRAPH); break;
+    case MODE_ROLLOUT: return p.use_tc ? launch_tile_impl<MODE_ROLLOUT, true>(p, stream) : launch_tile_impl<MODE_ROLLOUT, false>(p, stream);
+    case MODE_FORWARD: return p.use_tc ? launch_tile_impl<MODE_FORWARD, true>(p, stream) : launch_tile_impl<MODE_FORWARD, false>(p, stream);
+    case MODE_STEP: return launch_tile_impl<MODE_STEP, false>(p, stream);
+    case MODE_GRAPH: return launch_tile_impl<MODE_GRAPH, false>(p, stream);
     default: return cudaErrorInvalidValue;
   }
-#undef SWARM_LAUNCH
-  return cudaGetLastError();
 }
 
 }  // namespace swarm

@@ -79,6 +79,7 @@ struct TileParams {
   unsigned long long rng_seed;
   long long rng_tick0;
   float epsilon;
+  int32_t use_tc;                // 1: dense contractions on the tensor cores (tcgen05, 3xTF32)
   int32_t ticks;
   int32_t epb;                   // envs per block
   int32_t maxdeg;                // max in-degree of the graph (rows of the per-thread edge scratch)
@@ -90,19 +91,34 @@ struct TileParams {
 
 // byte offsets of the dynamic shared memory regions
 struct TileLayout {
-  int w, st, h, asrc, wt, inl, deg, kv, ki, nbr, red, total;
+  int w, st, h, asrc, wt, inl, deg, kv, ki, nbr, red, tc_a, tc_x, tc_w0, tc_w1, tc_w2, tc_vec, tc_bar, total;
 };
 
 __host__ __device__ inline int tile_align16(int x) { return (x + 15) & ~15; }
+__host__ __device__ inline int tile_align128(int x) { return (x + 127) & ~127; }
 
-__host__ __device__ inline TileLayout tile_layout(int mode, int threads, int n, int k, int maxdeg, int graph_mode) {
+__host__ __device__ inline TileLayout tile_layout(int mode, int threads, int n, int k, int maxdeg, int graph_mode,
+                                                  bool tc = false) {
   TileLayout L;
   int off = 0;
   const bool q = (mode == MODE_ROLLOUT || mode == MODE_FORWARD);
   const bool knn = (graph_mode == SWARM_GRAPH_KNN) && (q || mode == MODE_GRAPH);
-  L.w = off;    off = tile_align16(off + (q ? TW_COUNT * 4 : 0));
+  tc = tc && q;
+  // tensor-core operand tiles first (128-byte aligned); the h tile aliases the A tiles in that mode
+  L.tc_a = off;   off = tile_align128(off + (tc ? 2 * 128 * 32 * 4 : 0));
+  L.tc_x = off;   off = tile_align128(off + (tc ? 2 * 128 * 8 * 4 : 0));
+  L.tc_w0 = off;  off = tile_align128(off + (tc ? 2 * 32 * 8 * 4 : 0));
+  L.tc_w1 = off;  off = tile_align128(off + (tc ? 2 * 32 * 32 * 4 : 0));
+  L.tc_w2 = off;  off = tile_align128(off + (tc ? 2 * 16 * 32 * 4 : 0));
+  L.tc_vec = off; off = tile_align16(off + (tc ? 144 * 4 : 0));
+  L.tc_bar = off; off = tile_align16(off + (tc ? 16 : 0));
+  L.w = off;    off = tile_align16(off + ((q && !tc) ? TW_COUNT * 4 : 0));
   L.st = off;   off = tile_align16(off + 2 * threads * 16);
-  L.h = off;    off = tile_align16(off + (q ? threads * kHPad * 4 : 0));
+  if (tc) {
+    L.h = L.tc_a;
+  } else {
+    L.h = off;  off = tile_align16(off + (q ? threads * kHPad * 4 : 0));
+  }
   L.asrc = off; off = tile_align16(off + (q ? threads * 4 : 0));
   L.wt = off;   off = tile_align16(off + (q ? maxdeg * threads * 4 : 0));
   L.inl = off;  off = tile_align16(off + (q ? maxdeg * threads : 0));

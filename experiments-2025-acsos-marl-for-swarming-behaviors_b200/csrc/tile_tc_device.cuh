@@ -1,0 +1,164 @@
+// tile_tc_device.cuh -- the tensor-core (tcgen05, 3xTF32) variant of the per-tick Q-network forward of the
+// env-tile kernels.  The three dense contractions run as UMMA tiles over the CTA's 128 node rows; attention
+// softmax / aggregation, biases, tanh / ReLU and the argmax stay on the CUDA cores.
+#ifndef SWARM_TILE_TC_DEVICE_CUH
+#define SWARM_TILE_TC_DEVICE_CUH
+
+#include "tc_device.cuh"
+#include "tile_device.cuh"
+
+namespace swarm {
+
+// float offsets inside the small vector block
+enum { TV_ATT_S = 0, TV_ATT_D = 32, TV_B0 = 64, TV_B1 = 96, TV_B2 = 128, TV_COUNT = 144 };
+constexpr int kTmemCols = 64;     // D tiles: [0,32) projection / lin2, [32,64) lin1
+
+struct TileTcSmem {
+  unsigned char* a;      // A tiles: hi at +0 (16 KB), lo at +16 KB; the h tile (g.sh) aliases the start
+  unsigned char* x;      // X tiles [128 x 8]: hi at +0 (4 KB), lo at +4 KB
+  unsigned char* w0;     // [32 x 8]  hi +0 (1 KB), lo +1 KB
+  unsigned char* w1;     // [32 x 32] hi +0 (4 KB), lo +4 KB
+  unsigned char* w2;     // [16 x 32] hi +0 (2 KB), lo +2 KB
+  float* vec;            // TV_*
+  uint64_t* bar;
+  uint32_t* tmem_slot;
+};
+
+constexpr int kTcABytes = 2 * 128 * 32 * 4, kTcXBytes = 2 * 128 * 8 * 4;
+constexpr int kTcW0Bytes = 2 * 32 * 8 * 4, kTcW1Bytes = 2 * 32 * 32 * 4, kTcW2Bytes = 2 * 16 * 32 * 4;
+
+// global packed weights -> split (hi, lo) UMMA B tiles + bias / attention vectors
+__device__ __forceinline__ void stage_weights_tc(const float* __restrict__ gw, const TileTcSmem& s, int tid, int nthreads) {
+  for (int idx = tid; idx < TV_COUNT; idx += nthreads) {
+    float v = 0.0f;
+    if (idx < TV_ATT_D) v = gw[SWARM_W_ATT_SRC + idx];
+    else if (idx < TV_B0) v = gw[SWARM_W_ATT_DST + (idx - TV_ATT_D)];
+    else if (idx < TV_B1) v = gw[SWARM_W_CONV_BIAS + (idx - TV_B0)];
+    else if (idx < TV_B2) v = gw[SWARM_W_LIN1_BIAS + (idx - TV_B1)];
+    else if (idx - TV_B2 < 9) v = gw[SWARM_W_LIN2_BIAS + (idx - TV_B2)];
+    s.vec[idx] = v;
+  }
+  // items: (row n, k-chunk c) of W1 (256), W2 (128), W0 (64)
+  for (int it = tid; it < 448; it += nthreads) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned char* base;
+    int rows, n, c, half;
+    if (it < 256) {
+      n = it >> 3; c = it & 7; rows = 32; base = s.w1; half = kTcW1Bytes / 2;
+      const float* r = gw + SWARM_W_LIN1 + n * 32 + 4 * c;
+      v = make_float4(r[0], r[1], r[2], r[3]);
+    } else if (it < 384) {
+      const int j = it - 256;
+      n = j >> 3; c = j & 7; rows = 16; base = s.w2; half = kTcW2Bytes / 2;
+      if (n < 9) {
+        const float* r = gw + SWARM_W_LIN2 + n * 32 + 4 * c;
+        v = make_float4(r[0], r[1], r[2], r[3]);
+      }
+    } else {
+      const int j = it - 384;
+      n = j >> 1; c = j & 1; rows = 32; base = s.w0; half = kTcW0Bytes / 2;
+      const float* r = gw + SWARM_W_CONV_LIN + n * 7 + 4 * c;
+      v = c == 0 ? make_float4(r[0], r[1], r[2], r[3]) : make_float4(r[0], r[1], r[2], 0.0f);
+    }
+    float4 hi, lo;
+    tc::split4(v, hi, lo);
+    const int off = tc::tile_off(rows, n, c);
+    *reinterpret_cast<float4*>(base + off) = hi;
+    *reinterpret_cast<float4*>(base + half + off) = lo;
+  }
+}
+
+// writes this thread's 32-vector as row `tid` of the A tiles (hi, lo)
+__device__ __forceinline__ void tc_store_a_row(const TileTcSmem& s, int tid, const float (&v)[32]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float4 hi, lo;
+    tc::split4(make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]), hi, lo);
+    const int off = tc::tile_off(128, tid, c);
+    *reinterpret_cast<float4*>(s.a + off) = hi;
+    *reinterpret_cast<float4*>(s.a + kTcABytes / 2 + off) = lo;
+  }
+}
+
+// One UMMA round: every thread has written its operand row; barrier; one elected thread issues the 3xTF32 MMAs
+// and commits to the mbarrier; everybody waits for completion.  `parity` is the per-thread phase bit.
+__device__ __forceinline__ void tc_mma_round(const TileTcSmem& s, uint32_t tmem_d, const unsigned char* a_tile, int a_half,
+                                             const unsigned char* b_tile, int b_half, int b_rows, int ksteps,
+                                             uint32_t& parity) {
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) {
+    tc::fence_after_sync();
+    if (tc::elect_one()) {
+      const uint32_t a = tc::smem_u32(a_tile), b = tc::smem_u32(b_tile);
+      tc::mma_3xtf32(tmem_d, a, a + a_half, b, b + b_half, b_rows, ksteps, tc::make_idesc_tf32(b_rows));
+      tc::mma_commit(s.bar);
+    }
+    __syncwarp();
+  }
+  tc::mbar_wait(s.bar, parity);
+  parity ^= 1u;
+  tc::fence_after_sync();
+}
+
+// Full per-tick Q forward on the tensor cores.  Contains 5 block barriers.  All 128 threads must call it.
+__device__ __forceinline__ int tile_q_forward_tc(const TileGraphSmem& g, const TileTcSmem& s, const TileThread& t,
+                                                 uint32_t tmem, const float (&x)[7], int deg, uint32_t& parity,
+                                                 float (&q)[9]) {
+  const uint32_t lane_addr = tmem + ((uint32_t)(t.tid & ~31) << 16);     // this warp's 32 TMEM lanes
+  // ---- projection h = x W0^T (K padded 7 -> 8) ----
+  {
+    float4 hi, lo;
+    tc::split4(make_float4(x[0], x[1], x[2], x[3]), hi, lo);
+    int off = tc::tile_off(128, t.tid, 0);
+    *reinterpret_cast<float4*>(s.x + off) = hi;
+    *reinterpret_cast<float4*>(s.x + kTcXBytes / 2 + off) = lo;
+    tc::split4(make_float4(x[4], x[5], x[6], 0.0f), hi, lo);
+    off = tc::tile_off(128, t.tid, 1);
+    *reinterpret_cast<float4*>(s.x + off) = hi;
+    *reinterpret_cast<float4*>(s.x + kTcXBytes / 2 + off) = lo;
+  }
+  tc_mma_round(s, tmem, s.x, kTcXBytes / 2, s.w0, kTcW0Bytes / 2, 32, 1, parity);
+  float h[32];
+  tc::tmem_ld32(lane_addr, h);
+  float asrc = 0.0f, adst = 0.0f;
+#pragma unroll
+  for (int cc = 0; cc < 32; ++cc) {
+    asrc = __fadd_rn(asrc, __fmul_rn(h[cc], s.vec[TV_ATT_S + cc]));
+    adst = __fadd_rn(adst, __fmul_rn(h[cc], s.vec[TV_ATT_D + cc]));
+  }
+  if (t.active) tile_gat_publish(g, t, h, asrc);
+  __syncthreads();
+  // ---- attention + aggregation (CUDA cores) ----
+  float a1[32];
+  tile_gat_attend(g, t, deg, adst, a1);
+  __syncthreads();                 // the h tile aliases the A tiles: everyone is done gathering
+#pragma unroll
+  for (int cc = 0; cc < 32; ++cc) a1[cc] = tanhf(__fadd_rn(a1[cc], s.vec[TV_B0 + cc]));
+  tc_store_a_row(s, t.tid, a1);
+  // ---- lin1 + ReLU ----
+  tc_mma_round(s, tmem + 32, s.a, kTcABytes / 2, s.w1, kTcW1Bytes / 2, 32, 4, parity);
+  tc::tmem_ld32(lane_addr + 32, a1);
+#pragma unroll
+  for (int cc = 0; cc < 32; ++cc) a1[cc] = fmaxf(__fadd_rn(a1[cc], s.vec[TV_B1 + cc]), 0.0f);
+  tc_store_a_row(s, t.tid, a1);     // lin1 has completed (mbarrier), the A tiles are free again
+  // ---- lin2 ----
+  tc_mma_round(s, tmem, s.a, kTcABytes / 2, s.w2, kTcW2Bytes / 2, 16, 4, parity);
+  float qq[16];
+  tc::tmem_ld16(lane_addr, qq);
+  float best = 0.0f;
+  int action = 0;
+#pragma unroll
+  for (int a = 0; a < 9; ++a) {
+    q[a] = __fadd_rn(qq[a], s.vec[TV_B2 + a]);
+    if (a == 0 || q[a] > best) {
+      best = q[a];
+      action = a;
+    }
+  }
+  return action;
+}
+
+}  // namespace swarm
+#endif
