@@ -38,7 +38,9 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
 }
 
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));     // round to nearest TF32 (low 13 mantissa bits zero)
+  hi = __uint_as_float(h);
   lo = x - hi;
 }
 
@@ -99,18 +101,23 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// D += A * B^T with the 3xTF32 split: a_hi / a_lo and b_hi / b_lo are the tile base addresses (shared window),
-// `ksteps` = K / 8, a_rows = 128, b_rows = N.  Issued by one elected thread.
+// D = A * B^T with the 3xTF32 split: a_hi / a_lo and b_hi / b_lo are the tile base addresses (shared window),
+// `ksteps` = K / 8, a_rows = 128, b_rows = N.  Issued by one elected thread.  The descriptors of one operand
+// differ only in the start-address field, so they are formed by adding to a base descriptor.
 __device__ __forceinline__ void mma_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
                                            int b_rows, int ksteps, uint32_t idesc) {
   const uint32_t a_lbo = 128 * 16, b_lbo = (uint32_t)b_rows * 16;
+  const uint64_t da_hi = make_desc(a_hi, a_lbo, 128), da_lo = make_desc(a_lo, a_lbo, 128);
+  const uint64_t db_hi = make_desc(b_hi, b_lbo, 128), db_lo = make_desc(b_lo, b_lbo, 128);
+  const uint64_t a_step = (uint64_t)((2 * a_lbo) >> 4), b_step = (uint64_t)((2 * b_lbo) >> 4);
   bool acc = false;
 #pragma unroll
   for (int term = 0; term < 3; ++term) {
-    const uint32_t a = (term == 0) ? a_lo : a_hi;       // lo*hi, hi*lo, hi*hi
-    const uint32_t b = (term == 1) ? b_lo : b_hi;
+    const uint64_t da = (term == 0) ? da_lo : da_hi;       // lo*hi, hi*lo, hi*hi (small terms first)
+    const uint64_t db = (term == 1) ? db_lo : db_hi;
+#pragma unroll 4
     for (int j = 0; j < ksteps; ++j) {
-      mma_tf32(tmem_d, make_desc(a + j * 2 * a_lbo, a_lbo, 128), make_desc(b + j * 2 * b_lbo, b_lbo, 128), idesc, acc);
+      mma_tf32(tmem_d, da + j * a_step, db + j * b_step, idesc, acc);
       acc = true;
     }
   }

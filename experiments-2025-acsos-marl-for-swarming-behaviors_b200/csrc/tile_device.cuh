@@ -138,6 +138,7 @@ __device__ __forceinline__ void tile_gat_publish(const TileGraphSmem& g, const T
 // Edge softmax over the in-edge list of this node in edge-list order (torch_geometric.utils.softmax: max,
 // exp(z - max), sum + 1e-16, divide) followed by the aggregation.  On return agg = sum_e alpha_e h_j (bias not yet
 // added) and the attention coefficients alpha_e are left in g.swt[e][tid].
+template <bool FUSED = false>
 __device__ __forceinline__ void tile_gat_attend(const TileGraphSmem& g, const TileThread& t, int deg, float adst,
                                                 float (&agg)[32]) {
   const int T = kTileThreads;
@@ -161,7 +162,7 @@ __device__ __forceinline__ void tile_gat_attend(const TileGraphSmem& g, const Ti
       const int j = g.sin[e * T + t.tid];
       const float alpha = __fdiv_rn(g.swt[e * T + t.tid], den);
       g.swt[e * T + t.tid] = alpha;
-      gat_accumulate(agg, alpha, reinterpret_cast<const float4*>(g.sh + (t.envbase + j) * kHPad));
+      gat_accumulate<FUSED>(agg, alpha, reinterpret_cast<const float4*>(g.sh + (t.envbase + j) * kHPad));
     }
   }
 }

@@ -125,17 +125,17 @@ __device__ __forceinline__ int tile_q_forward_tc(const TileGraphSmem& g, const T
   float asrc = 0.0f, adst = 0.0f;
 #pragma unroll
   for (int cc = 0; cc < 32; ++cc) {
-    asrc = __fadd_rn(asrc, __fmul_rn(h[cc], s.vec[TV_ATT_S + cc]));
-    adst = __fadd_rn(adst, __fmul_rn(h[cc], s.vec[TV_ATT_D + cc]));
+    asrc = fmaf(h[cc], s.vec[TV_ATT_S + cc], asrc);
+    adst = fmaf(h[cc], s.vec[TV_ATT_D + cc], adst);
   }
   if (t.active) tile_gat_publish(g, t, h, asrc);
   __syncthreads();
   // ---- attention + aggregation (CUDA cores) ----
   float a1[32];
-  tile_gat_attend(g, t, deg, adst, a1);
+  tile_gat_attend<true>(g, t, deg, adst, a1);
   __syncthreads();                 // the h tile aliases the A tiles: everyone is done gathering
 #pragma unroll
-  for (int cc = 0; cc < 32; ++cc) a1[cc] = tanhf(__fadd_rn(a1[cc], s.vec[TV_B0 + cc]));
+  for (int cc = 0; cc < 32; ++cc) a1[cc] = tanh_fast(a1[cc] + s.vec[TV_B0 + cc]);
   tc_store_a_row(s, t.tid, a1);
   // ---- lin1 + ReLU ----
   tc_mma_round(s, tmem + 32, s.a, kTcABytes / 2, s.w1, kTcW1Bytes / 2, 32, 4, parity);
