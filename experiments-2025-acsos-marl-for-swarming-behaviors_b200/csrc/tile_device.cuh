@@ -80,8 +80,33 @@ __device__ __forceinline__ void tile_knn_rows(const TileGraphSmem& g, const Tile
       pr.i = j;
       row.set(j, pr);
     }
-    knn_topk_smallest(row, N, K);
-    for (int r = 0; r < K; ++r) g.snbr[r * T + t.tid] = g.ski[r * T + t.tid];
+    // Fast path: K rounds of "smallest value above the previous pick".  If every pick is unique (no exact distance
+    // tie among the K smallest nor at the K-th / (K+1)-th boundary) the result of *any* correct top-k is this list,
+    // so it equals torch.topk's; the branch-free rounds cost O(K N) uniform instructions.  Any tie (the rule on the
+    // regular start grids) or NaN falls back to the step-for-step libstdc++ emulation, whose tie order is what
+    // torch produces.
+    bool unique = true;
+    float prev = -INFINITY;
+    for (int r = 0; r < K && unique; ++r) {
+      float best = INFINITY;
+      int bi = 0, cnt = 0;
+      bool nan = false;
+      for (int l = 0; l < N; ++l) {
+        const float v = g.skv[l * T + t.tid];
+        nan |= !(v == v);                              // NaN: leave it to the emulation
+        if (v > prev) {
+          if (v < best) { best = v; bi = l; cnt = 1; }
+          else if (v == best) ++cnt;
+        }
+      }
+      unique = (cnt == 1) && !nan;
+      g.snbr[r * T + t.tid] = (uint8_t)bi;
+      prev = best;
+    }
+    if (!unique) {
+      knn_topk_smallest(row, N, K);
+      for (int r = 0; r < K; ++r) g.snbr[r * T + t.tid] = g.ski[r * T + t.tid];
+    }
   }
   __syncthreads();
 }

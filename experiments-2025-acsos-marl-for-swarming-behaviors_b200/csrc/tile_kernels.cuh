@@ -123,8 +123,14 @@ __host__ __device__ inline TileLayout tile_layout(int mode, int threads, int n, 
   L.wt = off;   off = tile_align16(off + (q ? maxdeg * threads * 4 : 0));
   L.inl = off;  off = tile_align16(off + (q ? maxdeg * threads : 0));
   L.deg = off;  off = tile_align16(off + (q ? threads : 0));
-  L.kv = off;   off = tile_align16(off + (knn ? n * threads * 4 : 0));
-  L.ki = off;   off = tile_align16(off + (knn ? n * threads : 0));
+  if (tc && knn && n * threads * 5 <= 2 * 128 * 32 * 4) {
+    // the kNN distance / index rows live only inside tile_knn_rows, when the A tiles are idle: alias them
+    L.kv = L.tc_a;
+    L.ki = L.tc_a + n * threads * 4;
+  } else {
+    L.kv = off;   off = tile_align16(off + (knn ? n * threads * 4 : 0));
+    L.ki = off;   off = tile_align16(off + (knn ? n * threads : 0));
+  }
   L.nbr = off;  off = tile_align16(off + (knn ? k * threads : 0));
   L.red = off;  off = tile_align16(off + threads * 4);
   L.total = off;
