@@ -9,6 +9,7 @@
 
 namespace swarm {
 cudaError_t launch_tile(int mode, const TileParams& p, cudaStream_t stream);
+cudaError_t launch_sim_step(const TileParams& p, cudaStream_t stream);
 cudaError_t launch_reset_grid(const SwarmConfig& c, int cols, int rows, const float* centers, float* state,
                               cudaStream_t stream);
 long long csr_workspace_bytes(int n, long long E);
@@ -165,6 +166,8 @@ int swarm_sim_step(const SwarmConfig* cfg, const float* state_in, const int32_t*
   p.contact_out = contact;
   p.obs_out = obs;
   p.dist_out = dist;
+  // n_agents <= 64: lean streaming kernel (step_kernels.cu); larger swarms: env-tile kernel (same arithmetic)
+  if (cfg->n_agents <= 64) return check_cuda(launch_sim_step(p, (cudaStream_t)stream), "swarm_sim_step");
   return check_cuda(launch_tile(MODE_STEP, p, (cudaStream_t)stream), "swarm_sim_step");
 }
 

@@ -55,12 +55,47 @@ __device__ __forceinline__ bool contact_force(float ax, float ay, float bx, floa
   return true;
 }
 
+// ---- agent-agent contacts of one agent against the N agents of its env ---------------------------------
+// `partners` = positions of the env's agents (float2 or float4 elements, .x/.y used), `self` = own index.
+// Phase 1 is a branch-free sweep that records, 32 partners at a time, which squared distances pass the exact
+// pre-filter q <= qmax (qmax = largest float whose rounded sqrt is <= r_a + r_b, see api.cu); phase 2 -- rare --
+// walks the set bits in ascending partner order and adds the contact forces in vmas' accumulation order.
+template <typename P>
+__device__ __forceinline__ void agent_contacts(const P* __restrict__ partners, int N, int self, float sx, float sy,
+                                               float qmax, float dist_min, float collision_force, float k, float& fx,
+                                               float& fy, uint32_t& cmask) {
+  for (int base = 0; base < N; base += 32) {
+    const int cnt = (N - base < 32) ? (N - base) : 32;
+    uint32_t m = 0;
+#pragma unroll 4
+    for (int j = 0; j < cnt; ++j) {
+      const P o = partners[base + j];
+      const float dx = __fsub_rn(sx, o.x), dy = __fsub_rn(sy, o.y);
+      const float q = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+      m |= (q <= qmax) ? (1u << j) : 0u;
+    }
+    if (self >= base && self < base + 32) m &= ~(1u << (self - base));
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      const P o = partners[base + j];
+      float gx, gy;
+      if (contact_force(sx, sy, o.x, o.y, dist_min, collision_force, k, gx, gy)) {
+        fx = __fadd_rn(fx, gx);
+        fy = __fadd_rn(fy, gy);
+        if (base + j < 32) cmask |= (1u << (base + j));
+      }
+    }
+  }
+}
+
 // ---- vmas World._integrate_state (substeps = 1, mass = 1) ----------------------------------------
+// accel = F / mass with mass = 1.0 is F itself (x / 1.0f == x exactly), so no division is issued.
 __device__ __forceinline__ void integrate(float4& s, float fx, float fy, float dt, float one_minus_drag) {
   float vx = __fmul_rn(s.z, one_minus_drag);
   float vy = __fmul_rn(s.w, one_minus_drag);
-  vx = __fadd_rn(vx, __fmul_rn(__fdiv_rn(fx, 1.0f), dt));
-  vy = __fadd_rn(vy, __fmul_rn(__fdiv_rn(fy, 1.0f), dt));
+  vx = __fadd_rn(vx, __fmul_rn(fx, dt));
+  vy = __fadd_rn(vy, __fmul_rn(fy, dt));
   s.x = __fadd_rn(s.x, __fmul_rn(vx, dt));
   s.y = __fadd_rn(s.y, __fmul_rn(vy, dt));
   s.z = vx;

@@ -129,9 +129,9 @@ __device__ __forceinline__ int tile_in_edges_knn(const TileGraphSmem& g, const T
 
 // edge list export (env-local ids) in the reference's order
 __device__ __forceinline__ void tile_write_edges(const TileGraphSmem& g, const TileThread& t, int N, int K, bool knn,
-                                                 int E, int32_t* eout) {
+                                                 int E, int32_t* eout, long long env_index) {
   const int T = kTileThreads;
-  int32_t* r0 = eout + t.env * 2 * E;
+  int32_t* r0 = eout + env_index * 2 * E;
   int32_t* r1 = r0 + E;
   const int i = t.i;
   if (knn) {

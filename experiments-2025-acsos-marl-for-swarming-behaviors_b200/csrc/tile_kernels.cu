@@ -31,19 +31,8 @@ __device__ __forceinline__ void tile_world_step(const TileParams& p, const TileT
       }
     }
   }
-  const int N = c.n_agents;
-  for (int j = 0; j < N; ++j) {
-    if (j == t.i) continue;
-    const float4 o = pos[t.envbase + j];
-    const float dx = __fsub_rn(s.x, o.x), dy = __fsub_rn(s.y, o.y);
-    if (__fmaf_rn(dy, dy, __fmul_rn(dx, dx)) <= p.qmax_aa) {
-      if (contact_force(s.x, s.y, o.x, o.y, p.dmin_aa, c.collision_force, c.contact_margin, gx, gy)) {
-        fx = __fadd_rn(fx, gx);
-        fy = __fadd_rn(fy, gy);
-        if (j < 32) cmask |= (1u << j);
-      }
-    }
-  }
+  agent_contacts(pos + t.envbase, c.n_agents, t.i, s.x, s.y, p.qmax_aa, p.dmin_aa, c.collision_force, c.contact_margin,
+                 fx, fy, cmask);
   integrate(s, fx, fy, c.dt, p.one_minus_drag);
 }
 
@@ -124,7 +113,22 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(const __grid_constan
       int32_t* eout = nullptr;
       if (MODE == MODE_GRAPH) eout = p.edges_out;
       else if (p.trace.edges) eout = p.trace.edges + (long long)tick * c.num_envs * 2 * p.edges_per_env;
-      if (eout && t.active) tile_write_edges(g, t, N, K, knn, p.edges_per_env, eout);
+      if (MODE == MODE_GRAPH && eout && L.stage) {
+        // stage the tile's edge lists in shared memory, then stream the contiguous [envs][2][E] block out with
+        // coalesced 8-byte stores (E is odd, so the block is only 8-byte aligned)
+        int32_t* stage = reinterpret_cast<int32_t*>(smem + L.stage);
+        if (t.active) tile_write_edges(g, t, N, K, knn, p.edges_per_env, stage, t.el);
+        __syncthreads();
+        const long long env0 = (long long)blockIdx.x * p.epb;
+        const long long envs_here = (c.num_envs - env0 < p.epb) ? (c.num_envs - env0) : p.epb;
+        const long long words = envs_here * 2 * p.edges_per_env;
+        int32_t* dst = eout + env0 * 2 * p.edges_per_env;
+        const long long pairs = words >> 1;
+        for (long long w = tid; w < pairs; w += T) reinterpret_cast<int2*>(dst)[w] = reinterpret_cast<const int2*>(stage)[w];
+        if ((words & 1) && tid == 0) dst[words - 1] = stage[words - 1];
+      } else if (eout && t.active) {
+        tile_write_edges(g, t, N, K, knn, p.edges_per_env, eout, t.env);
+      }
       if (MODE == MODE_GRAPH && knn && p.nbr_out && t.active)
         for (int r = 0; r < K; ++r) p.nbr_out[t.gidx * K + r] = g.snbr[r * T + tid];
     }

@@ -91,7 +91,7 @@ struct TileParams {
 
 // byte offsets of the dynamic shared memory regions
 struct TileLayout {
-  int w, st, h, asrc, wt, inl, deg, kv, ki, nbr, red, tc_a, tc_x, tc_w0, tc_w1, tc_w2, tc_vec, tc_bar, total;
+  int w, st, h, asrc, wt, inl, deg, kv, ki, nbr, red, tc_a, tc_x, tc_w0, tc_w1, tc_w2, tc_vec, tc_bar, stage, total;
 };
 
 __host__ __device__ inline int tile_align16(int x) { return (x + 15) & ~15; }
@@ -133,6 +133,14 @@ __host__ __device__ inline TileLayout tile_layout(int mode, int threads, int n, 
   }
   L.nbr = off;  off = tile_align16(off + (knn ? k * threads : 0));
   L.red = off;  off = tile_align16(off + threads * 4);
+  // MODE_GRAPH: the tile's edge lists are staged here and written out with coalesced stores (0 = does not fit)
+  {
+    const long long e = (graph_mode == SWARM_GRAPH_KNN) ? (2LL * k * n + 1) : ((long long)n * (n - 1) + 1);
+    const long long bytes = (long long)(threads / n) * 2 * e * 4;
+    const bool staged = (mode == MODE_GRAPH) && (off + bytes <= 160 * 1024);
+    L.stage = staged ? off : 0;
+    if (staged) off = tile_align16(off + (int)bytes);
+  }
   L.total = off;
   return L;
 }
