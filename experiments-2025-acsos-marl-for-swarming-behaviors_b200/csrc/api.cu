@@ -10,6 +10,9 @@
 namespace swarm {
 cudaError_t launch_tile(int mode, const TileParams& p, cudaStream_t stream);
 cudaError_t launch_sim_step(const TileParams& p, cudaStream_t stream);
+cudaError_t launch_sim_step_large(const TileParams& p, cudaStream_t stream);
+cudaError_t launch_graph_large(const SwarmConfig& c, const float* state, int32_t* edges, int32_t* nbr, int edges_per_env,
+                               cudaStream_t stream);
 cudaError_t launch_reset_grid(const SwarmConfig& c, int cols, int rows, const float* centers, float* state,
                               cudaStream_t stream);
 long long csr_workspace_bytes(int n, long long E);
@@ -17,7 +20,7 @@ cudaError_t launch_csr_from_edges(int n, long long E, const int64_t* edge_src, c
                                   int32_t* src, int32_t* perm, void* workspace, long long workspace_bytes,
                                   cudaStream_t stream);
 cudaError_t launch_gatq_csr(int n, const float* weights, const float* x, const int32_t* row_ptr, const int32_t* src,
-                            float* q, float* rows, cudaStream_t stream);
+                            float* q, int32_t* actions, float* rows, cudaStream_t stream);
 long long gatq_workspace_bytes(int n);
 cudaError_t launch_replay_push(const SwarmReplay& r, long long cursor, int B, int N, const float* state,
                                const int32_t* actions, const float* rewards, const float* next_state,
@@ -55,14 +58,18 @@ float sq_threshold(float dmin) {
   return q;
 }
 
-int validate(const SwarmConfig* cfg, bool need_graph) {
+constexpr int kMaxLargeAgents = 4096;
+
+int validate(const SwarmConfig* cfg, bool need_graph, bool allow_large = false) {
   if (!cfg) return fail(SWARM_ERR_INVALID_ARG, "cfg is NULL");
   if (cfg->num_envs <= 0) return fail(SWARM_ERR_INVALID_ARG, "num_envs must be positive");
   if (cfg->n_agents <= 0) return fail(SWARM_ERR_INVALID_ARG, "n_agents must be positive");
   if (cfg->scenario != SWARM_SCENARIO_GOTO && cfg->scenario != SWARM_SCENARIO_OBSTACLE_AVOIDANCE)
     return fail(SWARM_ERR_INVALID_ARG, "unknown scenario id");
-  if (cfg->n_agents > kTileThreads)
-    return fail(SWARM_ERR_UNSUPPORTED, "n_agents > 128 is not supported by the env-tile kernels");
+  if (cfg->n_agents > kTileThreads && !allow_large)
+    return fail(SWARM_ERR_UNSUPPORTED, "n_agents > 128 is not supported by the fused env-tile kernels (use swarm_sim_step / "
+                                       "swarm_graph_build / swarm_gatq_forward_csr for large swarms)");
+  if (cfg->n_agents > kMaxLargeAgents) return fail(SWARM_ERR_UNSUPPORTED, "n_agents > 4096");
   if (need_graph) {
     if (cfg->graph_mode != SWARM_GRAPH_COMPLETE && cfg->graph_mode != SWARM_GRAPH_KNN)
       return fail(SWARM_ERR_INVALID_ARG, "unknown graph mode");
@@ -79,7 +86,7 @@ int fill_params(TileParams& p, const SwarmConfig* cfg, int mode) {
   std::memset(&p, 0, sizeof(p));
   p.cfg = *cfg;
   const int n = cfg->n_agents;
-  p.epb = kTileThreads / n;
+  p.epb = n <= kTileThreads ? kTileThreads / n : 1;
   p.ticks = 1;
   const bool knn = cfg->graph_mode == SWARM_GRAPH_KNN;
   p.maxdeg = knn ? (n + cfg->knn_k + 1) : n;
@@ -143,7 +150,7 @@ int64_t swarm_edges_per_env(const SwarmConfig* cfg) {
 }
 
 int swarm_reset_grid(const SwarmConfig* cfg, const float* centers, float* state, void* stream) {
-  if (int rc = validate(cfg, false)) return rc;
+  if (int rc = validate(cfg, false, true)) return rc;
   if (!centers || !state) return fail(SWARM_ERR_INVALID_ARG, "centers/state is NULL");
   const int n = cfg->n_agents;
   const int cols = (int)std::ceil(std::sqrt((double)n));     // math.ceil(math.sqrt(num_points))
@@ -153,7 +160,7 @@ int swarm_reset_grid(const SwarmConfig* cfg, const float* centers, float* state,
 
 int swarm_sim_step(const SwarmConfig* cfg, const float* state_in, const int32_t* actions, float* state_out,
                    float* rewards, uint8_t* flags, uint32_t* contact, float* obs, float* dist, void* stream) {
-  if (int rc = validate(cfg, false)) return rc;
+  if (int rc = validate(cfg, false, true)) return rc;
   if (!state_in || !actions || !state_out) return fail(SWARM_ERR_INVALID_ARG, "state_in/actions/state_out is NULL");
   if (contact && cfg->n_agents > 32) return fail(SWARM_ERR_UNSUPPORTED, "contact masks need n_agents <= 32");
   TileParams p;
@@ -166,15 +173,25 @@ int swarm_sim_step(const SwarmConfig* cfg, const float* state_in, const int32_t*
   p.contact_out = contact;
   p.obs_out = obs;
   p.dist_out = dist;
-  // n_agents <= 64: lean streaming kernel (step_kernels.cu); larger swarms: env-tile kernel (same arithmetic)
+  // n_agents <= 64: lean streaming kernel (step_kernels.cu); <= 128: env-tile kernel; above: one env per CTA row
+  // (large_kernels.cu) -- all three run the same device arithmetic
   if (cfg->n_agents <= 64) return check_cuda(launch_sim_step(p, (cudaStream_t)stream), "swarm_sim_step");
+  if (cfg->n_agents > kTileThreads) return check_cuda(launch_sim_step_large(p, (cudaStream_t)stream), "swarm_sim_step");
   return check_cuda(launch_tile(MODE_STEP, p, (cudaStream_t)stream), "swarm_sim_step");
 }
 
 int swarm_graph_build(const SwarmConfig* cfg, const float* state, int32_t* edges, int32_t* neighbours, void* stream) {
-  if (int rc = validate(cfg, true)) return rc;
+  if (int rc = validate(cfg, true, true)) return rc;
   if (!state) return fail(SWARM_ERR_INVALID_ARG, "state is NULL");
   if (!edges && !neighbours) return fail(SWARM_ERR_INVALID_ARG, "no output requested");
+  if (cfg->n_agents > kTileThreads) {
+    if (cfg->graph_mode == SWARM_GRAPH_KNN && (int64_t)cfg->knn_k * 64 > cfg->n_agents)
+      return fail(SWARM_ERR_UNSUPPORTED,
+                  "kNN for n_agents > 128 implements torch.topk's partial_sort branch only (needs 64 * k <= n_agents)");
+    if (cfg->graph_mode == SWARM_GRAPH_KNN && cfg->knn_k > 64) return fail(SWARM_ERR_UNSUPPORTED, "knn_k > 64");
+    return check_cuda(launch_graph_large(*cfg, state, edges, neighbours, (int)swarm_edges_per_env(cfg), (cudaStream_t)stream),
+                      "swarm_graph_build");
+  }
   TileParams p;
   if (int rc = fill_params(p, cfg, MODE_GRAPH)) return rc;
   p.state_in = state;
@@ -200,13 +217,15 @@ int swarm_gatq_forward(const SwarmConfig* cfg, const float* weights, const float
 int64_t swarm_gatq_workspace_bytes(int32_t n_nodes) { return n_nodes > 0 ? gatq_workspace_bytes(n_nodes) : 0; }
 
 int swarm_gatq_forward_csr(int32_t n_nodes, const float* weights, const float* x, const int32_t* row_ptr,
-                           const int32_t* src, float* q, void* workspace, int64_t workspace_bytes, void* stream) {
+                           const int32_t* src, float* q, int32_t* actions, void* workspace, int64_t workspace_bytes,
+                           void* stream) {
   if (n_nodes < 0) return fail(SWARM_ERR_INVALID_ARG, "n_nodes must be >= 0");
   if (n_nodes == 0) return SWARM_OK;
-  if (!weights || !x || !row_ptr || !q || !workspace) return fail(SWARM_ERR_INVALID_ARG, "NULL argument");
+  if (!weights || !x || !row_ptr || !workspace) return fail(SWARM_ERR_INVALID_ARG, "NULL argument");
+  if (!q && !actions) return fail(SWARM_ERR_INVALID_ARG, "no output requested");
   if (workspace_bytes < gatq_workspace_bytes(n_nodes)) return fail(SWARM_ERR_INVALID_ARG, "workspace too small");
   float* rows = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
-  return check_cuda(launch_gatq_csr(n_nodes, weights, x, row_ptr, src, q, rows, (cudaStream_t)stream),
+  return check_cuda(launch_gatq_csr(n_nodes, weights, x, row_ptr, src, q, actions, rows, (cudaStream_t)stream),
                     "swarm_gatq_forward_csr");
 }
 

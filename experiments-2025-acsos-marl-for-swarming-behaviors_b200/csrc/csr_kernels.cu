@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(kCsrThreads) csr_aggregate_kernel(int n, const
                                                                     const float* __restrict__ rows,
                                                                     const int32_t* __restrict__ row_ptr,
                                                                     const int32_t* __restrict__ src,
-                                                                    float* __restrict__ q_out) {
+                                                                    float* __restrict__ q_out,
+                                                                    int32_t* __restrict__ act_out) {
   __shared__ __align__(16) float sw[TW_COUNT];
   stage_weights(weights, sw, threadIdx.x, kCsrThreads);
   __syncthreads();
@@ -58,9 +59,12 @@ __global__ void __launch_bounds__(kCsrThreads) csr_aggregate_kernel(int n, const
     gat_accumulate(a1, __fdiv_rn(w, den), reinterpret_cast<const float4*>(rows + j * kRow));
   }
   float q[9];
-  gat_head(a1, sw, q);
+  const int action = gat_head(a1, sw, q);
+  if (q_out) {
 #pragma unroll
-  for (int a = 0; a < 9; ++a) q_out[(long long)i * 9 + a] = q[a];
+    for (int a = 0; a < 9; ++a) q_out[(long long)i * 9 + a] = q[a];
+  }
+  if (act_out) act_out[i] = action;
 }
 
 // ---- edge list -> CSR by target, stable ---------------------------------------------------------
@@ -135,10 +139,10 @@ cudaError_t launch_csr_from_edges(int n, long long E, const int64_t* edge_src, c
 }
 
 cudaError_t launch_gatq_csr(int n, const float* weights, const float* x, const int32_t* row_ptr, const int32_t* src,
-                            float* q, float* rows, cudaStream_t stream) {
+                            float* q, int32_t* actions, float* rows, cudaStream_t stream) {
   const int blocks = (n + kCsrThreads - 1) / kCsrThreads;
   csr_project_kernel<<<blocks, kCsrThreads, 0, stream>>>(n, weights, x, rows);
-  csr_aggregate_kernel<<<blocks, kCsrThreads, 0, stream>>>(n, weights, rows, row_ptr, src, q);
+  csr_aggregate_kernel<<<blocks, kCsrThreads, 0, stream>>>(n, weights, rows, row_ptr, src, q, actions);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,263 @@
+// large_kernels.cu -- large swarms (128 < N <= 4096 agents per env; BASELINE config "1024 agents x 1024 envs").
+//
+// An env no longer fits a 128-thread tile, so the path is split into stand-alone kernels that keep one env's
+// positions in shared memory (8 B per agent) and give every agent a thread:
+//   sim_step_large_kernel   vmas Environment.step: O(N) branch-free contact sweep per agent against the env's
+//                           positions in shared memory (same device code as the small-swarm kernels)
+//   goto_reward_large_kernel GoTo's collective reward, summed sequentially in agent order like the reference
+//   knn_large_kernel        simulator.py:9-26 for n >= 64 k, where torch.topk takes its std::partial_sort branch:
+//                           heap_select + sort_heap (csrc/knn_select.h) over a *virtual* row -- the k-element heap
+//                           lives in shared memory, the remaining candidates are streamed and their distances
+//                           computed on the fly (a squared-distance test skips the sqrt for candidates that cannot
+//                           beat the heap top), so no O(N^2) distance matrix is ever stored
+//   complete_edges_kernel   train_gcn_dqn.py:94-110 edge list (closed form)
+// The Q-network then runs through the generic CSR path (csr_kernels.cu).
+#include "knn_select.h"
+#include "tile_kernels.cuh"
+
+namespace swarm {
+
+constexpr int kLargeThreads = 256;
+
+struct LargeStepParams {
+  SwarmConfig cfg;
+  const float4* state_in;
+  const int32_t* actions;
+  float4* state_out;
+  float* rewards;
+  uint8_t* flags;
+  float* obs;
+  float2* dist;
+  float one_minus_drag, dmin_aa, dmin_ao, qmax_aa, qmax_ao;
+};
+
+// grid = (chunks of 256 agents, envs)
+__global__ void __launch_bounds__(kLargeThreads) sim_step_large_kernel(const __grid_constant__ LargeStepParams p) {
+  extern __shared__ float2 spos[];
+  const SwarmConfig& c = p.cfg;
+  const int N = c.n_agents;
+  const long long env = blockIdx.y;
+  const float4* env_state = p.state_in + env * N;
+  for (int j = threadIdx.x; j < N; j += kLargeThreads) {
+    const float4 s = env_state[j];
+    spos[j] = make_float2(s.x, s.y);
+  }
+  __syncthreads();
+  const int i = blockIdx.x * kLargeThreads + threadIdx.x;
+  if (i >= N) return;
+  const long long gidx = env * N + i;
+  float4 s = env_state[i];
+  float fx, fy, gx, gy;
+  decode_action(p.actions[gidx], fx, fy);
+  uint8_t flags = 0;
+  uint32_t cmask = 0;
+  if (c.scenario == SWARM_SCENARIO_OBSTACLE_AVOIDANCE) {
+    const float dx = __fsub_rn(s.x, c.obstacle_x), dy = __fsub_rn(s.y, c.obstacle_y);
+    if (__fmaf_rn(dy, dy, __fmul_rn(dx, dx)) <= p.qmax_ao) {
+      if (contact_force(s.x, s.y, c.obstacle_x, c.obstacle_y, p.dmin_ao, c.collision_force, c.contact_margin, gx, gy)) {
+        fx = __fadd_rn(fx, gx);
+        fy = __fadd_rn(fy, gy);
+        flags |= SWARM_FLAG_OBSTACLE_CONTACT;
+      }
+    }
+  }
+  agent_contacts(spos, N, i, s.x, s.y, p.qmax_aa, p.dmin_aa, c.collision_force, c.contact_margin, fx, fy, cmask);
+  integrate(s, fx, fy, c.dt, p.one_minus_drag);
+  const float dgoal = goal_distance(s.x, s.y, c);
+  float dobs = 0.0f;
+  if (c.scenario == SWARM_SCENARIO_OBSTACLE_AVOIDANCE) {
+    dobs = obstacle_distance(s.x, s.y, c);
+    const float reward = oa_reward(dgoal, dobs, c, flags);
+    if (p.rewards) p.rewards[gidx] = reward;
+  }
+  p.state_out[gidx] = s;
+  if (p.flags) p.flags[gidx] = flags;
+  if (p.obs) {
+    float2* o = reinterpret_cast<float2*>(p.obs + gidx * 6);
+    o[0] = make_float2(s.x, s.y);
+    o[1] = make_float2(s.z, s.w);
+    o[2] = make_float2(c.goal_x, c.goal_y);
+  }
+  if (p.dist) p.dist[gidx] = make_float2(dgoal, dobs);
+}
+
+// GoTo (go_to:108-115): reward = 0 + (-d_0) + (-d_1) + ... summed in agent order, the same value for every agent.
+__global__ void __launch_bounds__(kLargeThreads) goto_reward_large_kernel(SwarmConfig c, const float4* __restrict__ state,
+                                                                          float* __restrict__ rewards) {
+  extern __shared__ float sdg[];
+  __shared__ float total;
+  const int N = c.n_agents;
+  const long long env = blockIdx.x;
+  for (int j = threadIdx.x; j < N; j += kLargeThreads) {
+    const float4 s = state[env * N + j];
+    sdg[j] = goal_distance(s.x, s.y, c);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = 0.0f;
+    for (int a = 0; a < N; ++a) r = __fadd_rn(r, -sdg[a]);
+    total = r;
+  }
+  __syncthreads();
+  const float r = total;
+  for (int j = threadIdx.x; j < N; j += kLargeThreads) rewards[env * N + j] = r;
+}
+
+// ---- kNN, partial_sort branch ------------------------------------------------------------------
+// Virtual (value, index) row of agent `self`: entries [0, K) are the heap in shared memory, entries >= K are
+// computed on demand and never written back (heap_select only ever reads position i once, before overwriting it).
+struct VirtualRow {
+  float* hv;            // heap values  [K][threads]
+  int* hi;              // heap indices [K][threads]
+  const float2* pos;
+  float sx, sy;
+  int K;
+  __device__ __forceinline__ float dist(int j) const {
+    const float2 o = pos[j];
+    return norm2(__fsub_rn(o.x, sx), __fsub_rn(o.y, sy));
+  }
+  __device__ __forceinline__ KnnPair get(int j) const {
+    KnnPair p;
+    if (j < K) {
+      p.v = hv[j * kLargeThreads];
+      p.i = hi[j * kLargeThreads];
+    } else {
+      p.v = dist(j);
+      p.i = j;
+    }
+    return p;
+  }
+  __device__ __forceinline__ void set(int j, const KnnPair& p) {
+    if (j < K) {
+      hv[j * kLargeThreads] = p.v;
+      hi[j * kLargeThreads] = p.i;
+    }
+  }
+};
+
+struct LargeKnnParams {
+  SwarmConfig cfg;
+  const float4* state;
+  int32_t* edges;        // [B][2][E] or nullptr
+  int32_t* nbr;          // [B][N][K] or nullptr
+  int32_t edges_per_env;
+};
+
+// grid = (chunks of 256 agents, envs); dynamic smem: positions float2[N], heap values float[K][256], indices int[K][256]
+__global__ void __launch_bounds__(kLargeThreads) knn_large_kernel(const __grid_constant__ LargeKnnParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SwarmConfig& c = p.cfg;
+  const int N = c.n_agents, K = c.knn_k;
+  float2* spos = reinterpret_cast<float2*>(smem_raw);
+  float* hv = reinterpret_cast<float*>(spos + N);
+  int* hi = reinterpret_cast<int*>(hv + K * kLargeThreads);
+  const long long env = blockIdx.y;
+  for (int j = threadIdx.x; j < N; j += kLargeThreads) {
+    const float4 s = p.state[env * N + j];
+    spos[j] = make_float2(s.x, s.y);
+  }
+  __syncthreads();
+  const int i = blockIdx.x * kLargeThreads + threadIdx.x;
+  if (i >= N) return;
+  VirtualRow row{hv + threadIdx.x, hi + threadIdx.x, spos, spos[i].x, spos[i].y, K};
+  for (int j = 0; j < K; ++j) {
+    KnnPair pr;
+    pr.v = row.dist(j);
+    pr.i = j;
+    row.set(j, pr);
+  }
+  // std::partial_sort(b, b + k, e) = __heap_select + __sort_heap; the select loop is open-coded to skip the sqrt of
+  // candidates whose squared distance already rules them out (q_j >= q_top  =>  d_j >= d_top  =>  !comp)
+  knn_make_heap(row, 0, K);
+  for (int j = K; j < N; ++j) {
+    const float top = hv[threadIdx.x];
+    const float2 o = spos[j];
+    const float dx = __fsub_rn(o.x, row.sx), dy = __fsub_rn(o.y, row.sy);
+    const float q = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+    if (q < __fmul_rn(top, top) * 1.0000005f + 1e-37f) {       // conservative: never skips a candidate with d_j < top
+      KnnPair cand;
+      cand.v = __fsqrt_rn(q);
+      cand.i = j;
+      KnnPair first = row.get(0);
+      if (knn_less(cand, first)) knn_adjust_heap(row, 0, 0, K, cand);     // __pop_heap(first, middle, j)
+    }
+  }
+  knn_sort_heap(row, 0, K);
+  if (p.nbr)
+    for (int r = 0; r < K; ++r) p.nbr[(env * N + i) * K + r] = hi[r * kLargeThreads + threadIdx.x];
+  if (p.edges) {
+    const int E = p.edges_per_env;
+    int32_t* r0 = p.edges + env * 2 * E;
+    int32_t* r1 = r0 + E;
+    for (int r = 0; r < K; ++r) {
+      const int a = hi[r * kLargeThreads + threadIdx.x];
+      const int e = (i * K + r) * 2;
+      r0[e] = i; r1[e] = a;
+      r0[e + 1] = a; r1[e + 1] = i;
+    }
+    if (i == 0) { r0[E - 1] = 0; r1[E - 1] = 0; }
+  }
+}
+
+// complete graph, closed form: pair (i, j), i < j at edges 2p, 2p+1 with p = i N - i(i+1)/2 + (j - i - 1)
+__global__ void __launch_bounds__(kLargeThreads) complete_edges_kernel(int N, int E, int32_t* __restrict__ edges) {
+  const long long env = blockIdx.y;
+  int32_t* r0 = edges + env * 2 * E;
+  int32_t* r1 = r0 + E;
+  const int i = blockIdx.x;
+  const long long base = (long long)i * N - ((long long)i * (i + 1)) / 2;
+  for (int j = i + 1 + threadIdx.x; j < N; j += kLargeThreads) {
+    const long long e = 2 * (base + (j - i - 1));
+    r0[e] = i; r1[e] = j;
+    r0[e + 1] = j; r1[e + 1] = i;
+  }
+  if (i == 0 && threadIdx.x == 0) { r0[E - 1] = 0; r1[E - 1] = 0; }
+}
+
+// ---- launchers ------------------------------------------------------------------------------
+cudaError_t launch_sim_step_large(const TileParams& tp, cudaStream_t stream) {
+  const SwarmConfig& c = tp.cfg;
+  LargeStepParams p;
+  p.cfg = c;
+  p.state_in = reinterpret_cast<const float4*>(tp.state_in);
+  p.actions = tp.actions_in;
+  p.state_out = reinterpret_cast<float4*>(tp.state_out);
+  p.rewards = tp.rewards_out;
+  p.flags = tp.flags_out;
+  p.obs = tp.obs_out;
+  p.dist = reinterpret_cast<float2*>(tp.dist_out);
+  p.one_minus_drag = tp.one_minus_drag;
+  p.dmin_aa = tp.dmin_aa;
+  p.dmin_ao = tp.dmin_ao;
+  p.qmax_aa = tp.qmax_aa;
+  p.qmax_ao = tp.qmax_ao;
+  const dim3 grid((c.n_agents + kLargeThreads - 1) / kLargeThreads, c.num_envs);
+  sim_step_large_kernel<<<grid, kLargeThreads, c.n_agents * sizeof(float2), stream>>>(p);
+  if (c.scenario == SWARM_SCENARIO_GOTO && tp.rewards_out)
+    goto_reward_large_kernel<<<c.num_envs, kLargeThreads, c.n_agents * sizeof(float), stream>>>(
+        c, reinterpret_cast<const float4*>(tp.state_out), tp.rewards_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_graph_large(const SwarmConfig& c, const float* state, int32_t* edges, int32_t* nbr, int edges_per_env,
+                               cudaStream_t stream) {
+  if (c.graph_mode == SWARM_GRAPH_KNN) {
+    LargeKnnParams p;
+    p.cfg = c;
+    p.state = reinterpret_cast<const float4*>(state);
+    p.edges = edges;
+    p.nbr = nbr;
+    p.edges_per_env = edges_per_env;
+    const dim3 grid((c.n_agents + kLargeThreads - 1) / kLargeThreads, c.num_envs);
+    const size_t smem = c.n_agents * sizeof(float2) + (size_t)c.knn_k * kLargeThreads * 8;
+    cudaError_t err = cudaFuncSetAttribute(knn_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    knn_large_kernel<<<grid, kLargeThreads, smem, stream>>>(p);
+  } else if (edges) {
+    const dim3 grid(c.n_agents, c.num_envs);
+    complete_edges_kernel<<<grid, kLargeThreads, 0, stream>>>(c.n_agents, edges_per_env, edges);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace swarm

@@ -267,16 +267,59 @@ def csr_from_edges(edge_index: torch.Tensor, n_nodes: int) -> Tuple[torch.Tensor
     return row_ptr, src, perm
 
 
-def gatq_forward_csr(weights: torch.Tensor, x: torch.Tensor, row_ptr: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
-    """Generic GCN.forward: x f32[n,7] + CSR-by-target -> q f32[n,9]."""
+def gatq_forward_csr(weights: torch.Tensor, x: torch.Tensor, row_ptr: torch.Tensor, src: torch.Tensor,
+                     want_q: bool = True, want_actions: bool = False):
+    """Generic GCN.forward: x f32[n,7] + CSR-by-target -> q f32[n,9] (and / or greedy actions int32[n])."""
     n = x.shape[0]
     _expect(x, torch.float32, n * 7, "x")
     _expect(weights, torch.float32, _lib.W_COUNT, "weights")
     _expect(row_ptr, torch.int32, n + 1, "row_ptr")
     dev = x.device
-    q = torch.empty(n, 9, dtype=torch.float32, device=dev)
+    q = torch.empty(n, 9, dtype=torch.float32, device=dev) if want_q else None
+    act = torch.empty(n, dtype=torch.int32, device=dev) if want_actions else None
     wb = int(lib().swarm_gatq_workspace_bytes(n))
     ws = torch.empty(max(wb, 1), dtype=torch.uint8, device=dev)
-    check(lib().swarm_gatq_forward_csr(n, ptr(weights), ptr(x.contiguous()), ptr(row_ptr), ptr(src), ptr(q), ptr(ws), wb,
-                                       stream_ptr(dev)))
-    return q
+    check(lib().swarm_gatq_forward_csr(n, ptr(weights), ptr(x.contiguous()), ptr(row_ptr), ptr(src), ptr(q), ptr(act),
+                                       ptr(ws), wb, stream_ptr(dev)))
+    if want_q and want_actions:
+        return q, act
+    return q if want_q else act
+
+
+def rollout_large(cfg: SwarmConfig, weights: torch.Tensor, state: torch.Tensor, ticks: int,
+                  returns: Optional[torch.Tensor] = None, hits: Optional[torch.Tensor] = None,
+                  trace_state: bool = False) -> Dict[str, torch.Tensor]:
+    """Greedy rollout for large swarms (n_agents > 128): per tick graph_build -> CSR grouping -> generic GAT-Q
+    forward (argmax) -> world step, all on the device; the per-tick glue (node features, edge offsets, reward
+    accumulation) is tensor plumbing.  In place on ``state``."""
+    B, N = cfg.num_envs, cfg.n_agents
+    dev = state.device
+    if returns is None:
+        returns = torch.zeros(B, N, dtype=torch.float32, device=dev)
+    if hits is None:
+        hits = torch.zeros(B, dtype=torch.int32, device=dev)
+    ids = torch.arange(N, device=dev, dtype=torch.float32).view(1, N, 1).expand(B, N, 1)
+    goal = torch.tensor([cfg.goal_x, cfg.goal_y], dtype=torch.float32, device=dev).view(1, 1, 2).expand(B, N, 2)
+    offs = (torch.arange(B, device=dev, dtype=torch.int64) * N).view(B, 1, 1)
+    trace = []
+    static_csr = None
+    for _ in range(ticks):
+        if cfg.graph_mode == _lib.GRAPH_COMPLETE and static_csr is not None:
+            row_ptr, src = static_csr
+        else:
+            edges, _ = graph_build(cfg, state)
+            ei = (edges.to(torch.int64) + offs).permute(1, 0, 2).reshape(2, -1).contiguous()
+            row_ptr, src, _ = csr_from_edges(ei, B * N)
+            if cfg.graph_mode == _lib.GRAPH_COMPLETE:
+                static_csr = (row_ptr, src)
+        x = torch.cat([state, goal, ids], dim=2).reshape(B * N, 7)
+        act = gatq_forward_csr(weights, x, row_ptr, src, want_q=False, want_actions=True).view(B, N)
+        out = sim_step(cfg, state, act, state_out=state, want_obs=False)
+        returns += out["rewards"]
+        hits += ((out["flags"] & _lib.FLAG_HIT) != 0).sum(dim=1, dtype=torch.int32)
+        if trace_state:
+            trace.append(state.clone())
+    res = {"state": state, "returns": returns, "hits": hits}
+    if trace_state:
+        res["trace_state"] = torch.stack(trace)
+    return res

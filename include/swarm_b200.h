@@ -130,10 +130,12 @@ int swarm_gatq_forward(const SwarmConfig* cfg, const float* weights, const float
 
 /* GCN.forward on an arbitrary graph: x float[n][7]; edges grouped by target in CSR form, each group in
  * edge-list order (row_ptr int32[n+1], src int32[E]).  Used by the nn.Module seam (train_gcn_dqn.py:59-70)
- * for arbitrary Data/Batch inputs.  workspace: swarm_gatq_workspace_bytes(n) bytes of device memory. */
+ * for arbitrary Data/Batch inputs and the Q-network path of large swarms (n_agents > 128).  q float[n][9] and
+ * actions int32[n] (argmax) are optional.  workspace: swarm_gatq_workspace_bytes(n) bytes of device memory. */
 int64_t swarm_gatq_workspace_bytes(int32_t n_nodes);
 int swarm_gatq_forward_csr(int32_t n_nodes, const float* weights, const float* x, const int32_t* row_ptr,
-                           const int32_t* src, float* q, void* workspace, int64_t workspace_bytes, void* stream);
+                           const int32_t* src, float* q, int32_t* actions, void* workspace, int64_t workspace_bytes,
+                           void* stream);
 
 /* Stable grouping of an edge list by target (the order scatter-add sees): edge_src/edge_dst int64[E]
  * (torch_geometric edge_index rows) -> row_ptr int32[n+1], src int32[E], perm int32[E] (perm[p] = position

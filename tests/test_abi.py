@@ -80,9 +80,13 @@ def test_argument_validation_without_device(sb):
     assert b"selected index k out of range" in lib.swarm_last_error()
     cfg.knn_k = 5
     assert lib.swarm_graph_build(C.byref(cfg), None, None, None, None) == -1
-    cfg.n_agents = 500
+    cfg.n_agents = 5000
     assert lib.swarm_sim_step(C.byref(cfg), 8, 8, 8, None, None, None, None, None, None) == -2
     assert b"n_agents" in lib.swarm_last_error()
+    cfg.n_agents = 500                       # large swarms: fused kernels refuse, kNN needs torch's partial_sort branch
+    assert lib.swarm_rollout(C.byref(cfg), 8, 8, 1, None, None, None, None, None) == -2
+    cfg.knn_k = 10
+    assert lib.swarm_graph_build(C.byref(cfg), 8, 8, None, None) == -2 and b"partial_sort" in lib.swarm_last_error()
     cfg.n_agents, cfg.scenario = 5, 7
     assert lib.swarm_reset_grid(C.byref(cfg), 8, 8, None) == -1
     assert lib.swarm_adam_clip_step(8, 8, 8, 8, 0, 1e-3, 0.9, 0.999, 1e-8, 1.0, None, None, None) == -1   # step is 1-based

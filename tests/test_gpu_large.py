@@ -1,0 +1,159 @@
+"""Large swarms (n_agents > 128; BASELINE config "1024 agents per env"): world step, kNN (torch.topk's
+partial_sort branch, 64 k <= n) and complete edge lists, and the generic-CSR Q forward against the oracle."""
+import pytest
+import torch
+
+from helpers import load_params
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _states(scenario, B, N, seed, spread):
+    """Grid starts (4.65 wide for N = 1024) squeezed / jittered so that contacts and non-trivial kNN rows occur."""
+    from oracle import swarm_oracle as so, batched_oracle as bo
+    g = torch.Generator().manual_seed(seed)
+    centers = torch.stack([so.draw_center(scenario, True, g) for _ in range(B)])
+    pos, vel = bo.reset_grid(scenario, centers, N)
+    ctr = pos.mean(dim=1, keepdim=True)
+    pos = ctr + (pos - ctr) * spread
+    pos[1:] += 0.02 * torch.randn(B - 1, N, 2, generator=g)           # env 0 keeps the exact (tie-heavy) grid
+    vel = 0.2 * torch.randn(B, N, 2, generator=g)
+    return pos.contiguous(), vel.contiguous()
+
+
+@pytest.mark.parametrize("scenario", ["go_to", "obstacle_avoidance"])
+@pytest.mark.parametrize("N,B", [(1024, 3), (200, 5), (129, 4)])
+def test_large_sim_step_parity(scenario, N, B):
+    import swarm_b200 as sb
+    from oracle import batched_oracle as bo
+    pos, vel = _states(scenario, B, N, seed=N, spread=0.55)
+    if scenario == "obstacle_avoidance":
+        pos[0] += torch.tensor([-0.1, 0.1]) - pos[0].mean(dim=0)        # park one swarm on the obstacle
+    actions = torch.randint(0, 9, (B, N), generator=torch.Generator().manual_seed(1))
+    # the oracle's pair loop is O(N^2) python: restrict it to what the test needs via a vectorised restatement
+    ref = _vector_step(scenario, pos, vel, actions)
+    cfg = sb.ops.make_config(sb._lib.SCENARIO_GOTO if scenario == "go_to" else sb._lib.SCENARIO_OBSTACLE_AVOIDANCE, B, N)
+    out = sb.ops.sim_step(cfg, torch.cat([pos, vel], 2).contiguous().to(_dev()), actions.to(torch.int32).to(_dev()))
+    st = out["state"].cpu()
+    touched = ref["touched"]
+    assert touched.any() and (~touched).any()
+    assert torch.equal(out["flags"].cpu(), ref["flags"])
+    free = ~touched
+    assert torch.equal(st[..., :2][free], ref["pos"][free]) and torch.equal(st[..., 2:][free], ref["vel"][free])
+    err = ((st[..., :2] - ref["pos"]).abs().max().item(), (st[..., 2:] - ref["vel"]).abs().max().item())
+    assert err[0] <= 1e-6 and err[1] <= 1e-5 * max(1.0, ref["vel"].abs().max().item())
+    if scenario == "obstacle_avoidance":
+        assert torch.equal(out["rewards"].cpu()[free], ref["rewards"][free])
+    else:
+        clean_env = ~touched.any(dim=1)
+        assert torch.equal(out["rewards"].cpu()[clean_env], ref["rewards"][clean_env])
+        assert torch.allclose(out["rewards"].cpu(), ref["rewards"], rtol=1e-6)
+
+
+def _vector_step(scenario, pos, vel, actions):
+    """oracle/batched_oracle.step with the agent-pair loop vectorised over j (same separately rounded torch ops and
+    the same ascending-partner accumulation order); cross-checked against the oracle itself in test below."""
+    from oracle import swarm_oracle as so
+    B, N, _ = pos.shape
+    u = so.decode_action(actions)
+    force = torch.zeros(B, N, 2) + u
+    obstacle = torch.tensor(list(so.OBSTACLE_POS))
+    dmin = torch.tensor(so.SPHERE_RADIUS) + torch.tensor(so.SPHERE_RADIUS)
+    touched = torch.zeros(B, N, dtype=torch.bool)
+    obst_contact = torch.zeros(B, N, dtype=torch.bool)
+    if scenario == so.OBSTACLE_AVOIDANCE:
+        f = so.constraint_force(obstacle.expand(B, N, 2), pos)
+        force = force + (-f)
+        obst_contact = torch.linalg.vector_norm(obstacle - pos, dim=-1) <= dmin
+        touched |= obst_contact
+    d = torch.linalg.vector_norm(pos.unsqueeze(2) - pos.unsqueeze(1), dim=-1)           # [B, i, j]
+    contact = (d <= dmin) & ~torch.eye(N, dtype=torch.bool)
+    touched |= contact.any(dim=2)
+    for b, i in contact.any(dim=2).nonzero().tolist():                                   # few agents: exact ordered sum
+        fi = force[b, i].clone()
+        for j in contact[b, i].nonzero().flatten().tolist():
+            fi = fi + so.constraint_force(pos[b, i:i + 1], pos[b, j:j + 1])[0]
+        force[b, i] = fi
+    v = vel * (1 - so.DRAG)
+    v = v + (force / 1.0) * so.DT
+    p = pos + v * so.DT
+    goal = torch.tensor(list(so.GOAL_POS))
+    d_goal = torch.linalg.vector_norm(p - goal, dim=-1)
+    flags = obst_contact.to(torch.uint8)
+    if scenario == so.GOTO:
+        coll = 0
+        for i in range(N):
+            coll = coll + (-d_goal[:, i])
+        rewards = coll.unsqueeze(1).expand(B, N).clone()
+    else:
+        d_obs = so.get_distance(p, obstacle)
+        avoid = torch.where(d_obs <= so.PENALTY_DISTANCE, -(so.PENALTY_DISTANCE - d_obs), torch.zeros(()))
+        rewards = (-d_goal) + so.OBSTACLE_WEIGHT * avoid
+        flags |= (d_obs <= so.HIT_DISTANCE).to(torch.uint8) * 2
+        flags |= (d_obs <= so.PENALTY_DISTANCE).to(torch.uint8) * 4
+    return {"pos": p, "vel": v, "rewards": rewards, "flags": flags, "touched": touched}
+
+
+def test_vector_step_equals_oracle():
+    """The vectorised restatement used above is bit-identical to the oracle where the oracle is affordable."""
+    from oracle import batched_oracle as bo
+    for scenario in ("go_to", "obstacle_avoidance"):
+        pos, vel = _states(scenario, 4, 40, seed=3, spread=0.6)
+        actions = torch.randint(0, 9, (4, 40), generator=torch.Generator().manual_seed(2))
+        a, b = _vector_step(scenario, pos, vel, actions), bo.step(scenario, pos, vel, actions)
+        assert torch.equal(a["pos"], b["pos"]) and torch.equal(a["vel"], b["vel"]) and torch.equal(a["rewards"], b["rewards"])
+        assert torch.equal(a["flags"], b["flags"])
+
+
+@pytest.mark.parametrize("N,k,B", [(1024, 10, 3), (1024, 16, 2), (640, 10, 3), (129, 2, 4), (4096, 10, 1)])
+def test_large_knn_bitexact(N, k, B):
+    import swarm_b200 as sb
+    from oracle import batched_oracle as bo
+    pos, vel = _states("go_to", B, N, seed=N + k, spread=1.0)
+    nbr_ref = bo.knn_table(pos, k)
+    cfg = sb.ops.make_config(sb._lib.SCENARIO_GOTO, B, N, sb._lib.GRAPH_KNN, k)
+    edges, nbr = sb.ops.graph_build(cfg, torch.cat([pos, vel], 2).contiguous().to(_dev()), want_neighbours=True)
+    assert torch.equal(nbr.cpu().long(), nbr_ref), "topk rows differ (partial_sort branch)"
+    assert torch.equal(edges.cpu().long(), bo.edges_from_knn(nbr_ref))
+
+
+def test_large_complete_edges_and_unsupported_knn():
+    import swarm_b200 as sb
+    from oracle import batched_oracle as bo
+    cfg = sb.ops.make_config(sb._lib.SCENARIO_GOTO, 2, 200, sb._lib.GRAPH_COMPLETE)
+    edges, _ = sb.ops.graph_build(cfg, torch.zeros(2, 200, 4, device=_dev()))
+    assert torch.equal(edges.cpu().long(), bo.edges_complete(2, 200))
+    cfg = sb.ops.make_config(sb._lib.SCENARIO_GOTO, 1, 300, sb._lib.GRAPH_KNN, 10)      # 64 k > n: nth_element branch
+    with pytest.raises(sb.SwarmError, match="partial_sort"):
+        sb.ops.graph_build(cfg, torch.zeros(1, 300, 4, device=_dev()))
+
+
+def test_large_rollout_against_oracle():
+    """C4-shaped greedy rollout (kNN k = 10 on 1 024 agents) for a few ticks: edges and greedy actions of every tick
+    and the trajectory against the (vectorised) oracle."""
+    import swarm_b200 as sb
+    from oracle import batched_oracle as bo
+    B, N, k, T = 2, 1024, 10, 3
+    params = load_params("ObstacleAvoidance", 0)
+    pos, vel = _states("obstacle_avoidance", B, N, seed=9, spread=1.0)
+    vel.zero_()
+    cfg = sb.ops.make_config(sb._lib.SCENARIO_OBSTACLE_AVOIDANCE, B, N, sb._lib.GRAPH_KNN, k)
+    state = torch.cat([pos, vel], 2).contiguous().to(_dev())
+    out = sb.ops.rollout_large(cfg, sb.pack_weights(params, _dev()), state, T, trace_state=True)
+    p, v = pos, vel
+    ret = torch.zeros(B, N)
+    for t in range(T):
+        edges = bo.edges_from_knn(bo.knn_table(p, k))
+        with torch.no_grad():
+            q = bo.gatq(params, p, v, edges)
+        ref = _vector_step("obstacle_avoidance", p, v, torch.argmax(q, dim=2))
+        p, v = ref["pos"], ref["vel"]
+        ret = ret + ref["rewards"]
+        st = out["trace_state"][t].cpu()
+        same = (st[..., :2] == p).all(dim=-1)
+        assert same.float().mean().item() >= 0.999, f"tick {t}: {int((~same).sum())} agents deviate (argmax flips)"
+    assert torch.allclose(out["returns"].cpu(), ret, rtol=1e-4, atol=1e-4)
