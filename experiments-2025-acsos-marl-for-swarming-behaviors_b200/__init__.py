@@ -12,7 +12,8 @@ from .env import Environment, make_env                            # noqa: F401
 from .gcn import GCN, GATConv                                     # noqa: F401
 from .graph import Batch, Data, create_graph_from_observations    # noqa: F401
 from .scenarios import BaseScenario, GoToPositionScenario, ObstacleAvoidanceScenario   # noqa: F401
+from .simulator import Simulator                                   # noqa: F401
 
 __all__ = ["make_env", "Environment", "GCN", "GATConv", "Data", "Batch", "create_graph_from_observations",
            "BaseScenario", "GoToPositionScenario", "ObstacleAvoidanceScenario", "SwarmConfig", "SwarmError",
-           "pack_weights", "unpack_weights", "ops", "DQNTrainer", "GraphReplayBuffer", "set_seed"]
+           "pack_weights", "unpack_weights", "ops", "DQNTrainer", "GraphReplayBuffer", "set_seed", "Simulator"]

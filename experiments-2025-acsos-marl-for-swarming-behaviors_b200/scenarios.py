@@ -167,7 +167,9 @@ class BaseScenario:
         return {"pos_rew": agent.pos_rew, "final_rew": self.final_rew}
 
     def average_distance_to_goal(self) -> torch.Tensor:
-        return torch.mean(self.world.last["dist"][:, :, 0].transpose(0, 1))
+        # torch.mean(torch.stack([agent.distance_to_goal ...])) (go_to:134-135) -- reduced on the host like the
+        # reference (device = cpu there) so the metric is bit-identical; this is a per-tick metric read, not hot path
+        return torch.mean(self.world.last["dist"][:, :, 0].cpu().transpose(0, 1).contiguous())
 
     def set_start_centers(self, centers: Optional[torch.Tensor]) -> None:
         """Batched extension: explicit per-env start centres f32[B,2] used by the next resets instead of
@@ -248,7 +250,7 @@ class ObstacleAvoidanceScenario(BaseScenario):
         w.reset_to_grid(centers, env_index)
 
     def average_distance_to_obstacles(self) -> torch.Tensor:
-        return torch.mean(self.world.last["dist"][:, :, 1].transpose(0, 1))
+        return torch.mean(self.world.last["dist"][:, :, 1].cpu().transpose(0, 1).contiguous())
 
     def obstacles_hits(self) -> torch.Tensor:
         hits = (self.world.last["flags"] & _lib.FLAG_HIT) != 0       # oa:170-173

@@ -1,0 +1,42 @@
+"""BASELINE config C4: 1024 agents x 1024 envs ObstacleAvoidance, kNN k = 10, greedy, 20 ticks."""
+import json, sys, time
+import numpy as np, torch
+sys.path.insert(0, '.')
+import swarm_b200 as sb
+from swarm_b200 import ops
+dev = torch.device('cuda:0')
+B, N, K, T = 1024, 1024, 10, 20
+models = np.load('tests/golden/models.npz')
+pre = 'ObstacleAvoidance/0/'
+w = sb.pack_weights({k[len(pre):]: torch.from_numpy(models[k]) for k in models.files if k.startswith(pre)}, dev)
+cfg = ops.make_config(sb._lib.SCENARIO_OBSTACLE_AVOIDANCE, B, N, sb._lib.GRAPH_KNN, K)
+g = torch.Generator().manual_seed(0)
+centers = (torch.tensor([0.6, -0.6]) + 0.1 * torch.randn(B, 2, generator=g)).to(dev)
+state = ops.reset_grid(cfg, centers)
+ops.rollout_large(cfg, w, state, 2)
+def ev():
+    return torch.cuda.Event(enable_timing=True)
+# per-stage timing of one tick
+ids = torch.arange(N, device=dev, dtype=torch.float32).view(1, N, 1).expand(B, N, 1)
+goal = torch.tensor([cfg.goal_x, cfg.goal_y], device=dev).view(1, 1, 2).expand(B, N, 2)
+offs = (torch.arange(B, device=dev, dtype=torch.int64) * N).view(B, 1, 1)
+stages = {}
+def timed(name, fn):
+    torch.cuda.synchronize(); a, b = ev(), ev(); a.record(); r = fn(); b.record(); torch.cuda.synchronize()
+    stages[name] = stages.get(name, 0.0) + a.elapsed_time(b); return r
+state = ops.reset_grid(cfg, centers)
+for t in range(5):
+    edges, _ = timed('graph_build (kNN k=10)', lambda: ops.graph_build(cfg, state))
+    ei = timed('edge offsets (torch glue)', lambda: (edges.to(torch.int64) + offs).permute(1, 0, 2).reshape(2, -1).contiguous())
+    row_ptr, src, _ = timed('csr_from_edges (cub sort)', lambda: ops.csr_from_edges(ei, B * N))
+    x = timed('node features (torch glue)', lambda: torch.cat([state, goal, ids], dim=2).reshape(B * N, 7))
+    act = timed('gatq_forward_csr', lambda: ops.gatq_forward_csr(w, x, row_ptr, src, want_q=False, want_actions=True).view(B, N))
+    timed('sim_step', lambda: ops.sim_step(cfg, state, act, state_out=state, want_obs=False))
+for k_ in stages: stages[k_] /= 5
+state = ops.reset_grid(cfg, centers)
+torch.cuda.synchronize(); a, b = ev(), ev(); a.record()
+ops.rollout_large(cfg, w, state, T)
+b.record(); torch.cuda.synchronize()
+ms = a.elapsed_time(b)
+print(json.dumps({'config': 'C4 OA N=1024 B=1024 kNN k=10 greedy', 'ticks': T, 'ms_per_tick': ms / T,
+                  'agent_steps_per_s': B * N * T / (ms * 1e-3), 'stage_ms_per_tick': stages}))
