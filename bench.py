@@ -162,7 +162,7 @@ def run_reference_arm(args):
                                        "(reference-structured per-tick loop, oracle/swarm_oracle.py)"},
             "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n_gpus: int):
@@ -305,7 +305,7 @@ def run_ours(args):
     line["dqn"] = dqn_stats
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_single()
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -372,10 +372,25 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: everything else a library prints there (e.g. NCCL's version banner)
+    # is diverted to stderr; the JSON line is written to the original descriptor at the end.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
     else:
         run_ours(args)
+
+
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 if __name__ == "__main__":
