@@ -170,24 +170,41 @@ __device__ __forceinline__ void tile_gat_attend(const TileGraphSmem& g, const Ti
 #pragma unroll
   for (int cc = 0; cc < 32; ++cc) agg[cc] = 0.0f;
   if (t.active) {
+    const uint8_t* __restrict__ sin = g.sin + t.tid;
+    float* __restrict__ swt = g.swt + t.tid;
+    const float* __restrict__ sas = g.sas + t.envbase;
+    const float* __restrict__ shb = g.sh + t.envbase * kHPad;
     float m = -INFINITY;
+#pragma unroll 4
     for (int e = 0; e < deg; ++e) {
-      const float z = gat_logit(g.sas[t.envbase + g.sin[e * T + t.tid]], adst);
-      g.swt[e * T + t.tid] = z;
+      const float z = gat_logit(sas[sin[e * T]], adst);
+      swt[e * T] = z;
       m = fmaxf(m, z);
     }
     float den = 0.0f;
+#pragma unroll 4
     for (int e = 0; e < deg; ++e) {
-      const float w = expf(__fsub_rn(g.swt[e * T + t.tid], m));
-      g.swt[e * T + t.tid] = w;
+      const float w = FUSED ? __expf(swt[e * T] - m) : expf(__fsub_rn(swt[e * T], m));
+      swt[e * T] = w;
       den = __fadd_rn(den, w);
     }
     den = __fadd_rn(den, 1e-16f);
-    for (int e = 0; e < deg; ++e) {
-      const int j = g.sin[e * T + t.tid];
-      const float alpha = __fdiv_rn(g.swt[e * T + t.tid], den);
-      g.swt[e * T + t.tid] = alpha;
-      gat_accumulate<FUSED>(agg, alpha, reinterpret_cast<const float4*>(g.sh + (t.envbase + j) * kHPad));
+    if (FUSED) {
+      // tensor-core path: reciprocal instead of a division per edge, and two edges per iteration with all 16 row
+      // loads issued before the 64 FFMAs so the shared-memory latency of one edge hides behind the other's math
+      const float inv = 1.0f / den;
+      for (int e = 0; e < deg; ++e) {
+        const float alpha = swt[e * T] * inv;
+        swt[e * T] = alpha;
+        gat_accumulate<true>(agg, alpha, reinterpret_cast<const float4*>(shb + sin[e * T] * kHPad));
+      }
+    } else {
+      for (int e = 0; e < deg; ++e) {
+        const int j = sin[e * T];
+        const float alpha = __fdiv_rn(swt[e * T], den);
+        swt[e * T] = alpha;
+        gat_accumulate<false>(agg, alpha, reinterpret_cast<const float4*>(shb + j * kHPad));
+      }
     }
   }
 }
