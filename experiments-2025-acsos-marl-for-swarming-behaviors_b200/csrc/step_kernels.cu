@@ -7,7 +7,16 @@
 // too: it yields a zero force and its mask bit is cleared afterwards) and unrolled for memory-level parallelism.
 // Same arithmetic, in the same order, as the env-tile kernels (swarm_device.cuh), so results are bit-identical to
 // MODE_STEP of tile_kernels.cu.
+//
+// Two kernels with identical arithmetic:
+//   sim_step_kernel         one tile per CTA, plain loads / stores (small batches, ragged tail, unaligned buffers)
+//   sim_step_stream_kernel  persistent CTAs; every tile of floor(256/N) envs is one contiguous block of the state /
+//                           action arrays, so it is pulled into a 4-deep shared-memory ring by the TMA engine
+//                           (cp.async.bulk + mbarrier complete_tx) and the new state / rewards leave through bulk
+//                           stores from a 3-deep staging ring: the SM never waits on its own loads and HBM sees long
+//                           16-byte-aligned bursts only.
 #include "tile_kernels.cuh"
+#include "tc_device.cuh"
 
 namespace swarm {
 
@@ -96,6 +105,143 @@ __global__ void __launch_bounds__(kStepThreads) sim_step_kernel(const __grid_con
   if (active && p.rewards) p.rewards[gidx] = reward;
 }
 
+// ---- persistent TMA-pipelined variant --------------------------------------------------------------------------
+constexpr int kStepStages = 4;     // input ring depth
+constexpr int kStepOutBufs = 3;    // output staging ring depth
+
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   tc::smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(tc::smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+struct StepStreamSmem {
+  float4 sin[kStepStages][kStepThreads];
+  float4 sout[kStepOutBufs][kStepThreads];
+  int32_t ain[kStepStages][kStepThreads];
+  float rout[kStepOutBufs][kStepThreads];
+  float sdg[kStepThreads];
+  uint64_t full[kStepStages];
+};
+
+// `ntiles` full tiles of p.epb envs each (the ragged tail goes to sim_step_kernel); p.epb * N is a multiple of 4 so
+// every bulk copy is a multiple of 16 bytes at a 16-byte aligned address.
+__global__ void __launch_bounds__(kStepThreads, 4) sim_step_stream_kernel(const __grid_constant__ StepParams p,
+                                                                          const long long ntiles) {
+  __shared__ __align__(128) StepStreamSmem sm;
+  const SwarmConfig& c = p.cfg;
+  const int N = c.n_agents;
+  const int tid = threadIdx.x;
+  const int el = tid / N;
+  const int i = tid - el * N;
+  const bool active = el < p.epb;
+  const int envbase = el * N;
+  const int tile_agents = p.epb * N;
+  const uint32_t sbytes = (uint32_t)tile_agents * 16u, abytes = (uint32_t)tile_agents * 4u;
+
+  const long long first = blockIdx.x, stride = gridDim.x;
+  const long long n_my = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStepStages; ++s) tc::mbar_init(&sm.full[s], 1);
+    tc::fence_async_smem();
+    for (int s = 0; s < kStepStages && s < n_my; ++s) {
+      const long long a0 = (first + s * stride) * tile_agents;
+      mbar_expect_tx(&sm.full[s], sbytes + abytes);
+      bulk_load(sm.sin[s], p.state_in + a0, sbytes, &sm.full[s]);
+      bulk_load(sm.ain[s], p.actions + a0, abytes, &sm.full[s]);
+    }
+  }
+  __syncthreads();
+
+  int stage = 0, ob = 0;
+  uint32_t parity = 0;
+  long long a0 = first * tile_agents;
+  const long long a_stride = stride * tile_agents;
+  for (long long it = 0; it < n_my; ++it, a0 += a_stride) {
+    const long long gidx = a0 + tid;
+    tc::mbar_wait(&sm.full[stage], parity);
+
+    float reward = 0.0f;
+    if (active) {
+      float4 s = sm.sin[stage][tid];
+      const int action = sm.ain[stage][tid];
+      float fx, fy, gx, gy;
+      decode_action(action, fx, fy);
+      uint8_t flags = 0;
+      uint32_t cmask = 0;
+      if (c.scenario == SWARM_SCENARIO_OBSTACLE_AVOIDANCE) {
+        const float dx = __fsub_rn(s.x, c.obstacle_x), dy = __fsub_rn(s.y, c.obstacle_y);
+        if (__fmaf_rn(dy, dy, __fmul_rn(dx, dx)) <= p.qmax_ao) {
+          if (contact_force(s.x, s.y, c.obstacle_x, c.obstacle_y, p.dmin_ao, c.collision_force, c.contact_margin, gx, gy)) {
+            fx = __fadd_rn(fx, gx);
+            fy = __fadd_rn(fy, gy);
+            flags |= SWARM_FLAG_OBSTACLE_CONTACT;
+          }
+        }
+      }
+      agent_contacts(&sm.sin[stage][envbase], N, i, s.x, s.y, p.qmax_aa, p.dmin_aa, c.collision_force, c.contact_margin, fx,
+                     fy, cmask);
+      integrate(s, fx, fy, c.dt, p.one_minus_drag);
+
+      const float dgoal = goal_distance(s.x, s.y, c);
+      float dobs = 0.0f;
+      if (c.scenario == SWARM_SCENARIO_OBSTACLE_AVOIDANCE) {
+        dobs = obstacle_distance(s.x, s.y, c);
+        reward = oa_reward(dgoal, dobs, c, flags);
+      } else {
+        sm.sdg[tid] = dgoal;
+      }
+      sm.sout[ob][tid] = s;
+      if (p.flags) p.flags[gidx] = flags;
+      if (p.contact) p.contact[gidx] = cmask;
+      if (p.obs) {
+        float2* o = reinterpret_cast<float2*>(p.obs + gidx * 6);
+        o[0] = make_float2(s.x, s.y);
+        o[1] = make_float2(s.z, s.w);
+        o[2] = make_float2(c.goal_x, c.goal_y);
+      }
+      if (p.dist) p.dist[gidx] = make_float2(dgoal, dobs);
+    }
+    if (c.scenario == SWARM_SCENARIO_GOTO) {
+      __syncthreads();
+      if (active)
+        for (int a = 0; a < N; ++a) reward = __fadd_rn(reward, -sm.sdg[envbase + a]);
+    }
+    if (active) sm.rout[ob][tid] = reward;
+
+    tc::fence_async_smem();          // generic-proxy writes of sout / rout -> visible to the bulk-copy engine
+    __syncthreads();                 // ... and every thread is done reading sin[stage]
+    if (tid == 0) {
+      bulk_store(p.state_out + a0, sm.sout[ob], sbytes);
+      if (p.rewards) bulk_store(p.rewards + a0, sm.rout[ob], abytes);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (it + kStepStages < n_my) {
+        const long long n0 = a0 + kStepStages * a_stride;
+        mbar_expect_tx(&sm.full[stage], sbytes + abytes);
+        bulk_load(sm.sin[stage], p.state_in + n0, sbytes, &sm.full[stage]);
+        bulk_load(sm.ain[stage], p.actions + n0, abytes, &sm.full[stage]);
+      }
+      // the staging buffer written two iterations from now was last read by the store issued one iteration ago
+      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    }
+    if (++stage == kStepStages) { stage = 0; parity ^= 1u; }
+    if (++ob == kStepOutBufs) ob = 0;
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+
 cudaError_t launch_sim_step(const TileParams& tp, cudaStream_t stream) {
   StepParams p;
   p.cfg = tp.cfg;
@@ -107,13 +253,41 @@ cudaError_t launch_sim_step(const TileParams& tp, cudaStream_t stream) {
   p.contact = tp.contact_out;
   p.obs = tp.obs_out;
   p.dist = reinterpret_cast<float2*>(tp.dist_out);
-  p.epb = kStepThreads / tp.cfg.n_agents;
   p.one_minus_drag = tp.one_minus_drag;
   p.dmin_aa = tp.dmin_aa;
   p.dmin_ao = tp.dmin_ao;
   p.qmax_aa = tp.qmax_aa;
   p.qmax_ao = tp.qmax_ao;
-  const long long grid = ((long long)tp.cfg.num_envs + p.epb - 1) / p.epb;
+  const int N = tp.cfg.n_agents;
+  long long env0 = 0;
+
+  // streaming path: full tiles whose agent count is a multiple of 4 (16-byte bulk copies), all buffers 16-byte aligned,
+  // and at least one tile per SM -- everything else (and the ragged tail) runs through the one-tile-per-CTA kernel
+  int epb_s = kStepThreads / N;
+  while (epb_s > 0 && ((epb_s * N) & 3)) --epb_s;
+  const long long ntiles = epb_s > 0 ? tp.cfg.num_envs / epb_s : 0;
+  if (ntiles >= 148 && aligned16(p.state_in) && aligned16(p.actions) && aligned16(p.state_out) &&
+      (!p.rewards || aligned16(p.rewards))) {
+    p.epb = epb_s;
+    const long long grid = ntiles < 148 * 4 ? ntiles : 148 * 4;
+    sim_step_stream_kernel<<<(unsigned)grid, kStepThreads, 0, stream>>>(p, ntiles);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    env0 = ntiles * epb_s;
+    if (env0 == tp.cfg.num_envs) return cudaSuccess;
+    const long long a0 = env0 * N;
+    p.state_in += a0;
+    p.actions += a0;
+    p.state_out += a0;
+    if (p.rewards) p.rewards += a0;
+    if (p.flags) p.flags += a0;
+    if (p.contact) p.contact += a0;
+    if (p.obs) p.obs += a0 * 6;
+    if (p.dist) p.dist += a0;
+    p.cfg.num_envs = (int)(tp.cfg.num_envs - env0);
+  }
+  p.epb = kStepThreads / N;
+  const long long grid = ((long long)p.cfg.num_envs + p.epb - 1) / p.epb;
   sim_step_kernel<<<(unsigned)grid, kStepThreads, 0, stream>>>(p);
   return cudaGetLastError();
 }

@@ -57,33 +57,40 @@ __device__ __forceinline__ bool contact_force(float ax, float ay, float bx, floa
 
 // ---- agent-agent contacts of one agent against the N agents of its env ---------------------------------
 // `partners` = positions of the env's agents (float2 or float4 elements, .x/.y used), `self` = own index.
-// Phase 1 is a branch-free sweep that records, 32 partners at a time, which squared distances pass the exact
-// pre-filter q <= qmax (qmax = largest float whose rounded sqrt is <= r_a + r_b, see api.cu); phase 2 -- rare --
-// walks the set bits in ascending partner order and adds the contact forces in vmas' accumulation order.
+// Phase 1 is a branch-free sweep that only COUNTS the partners whose squared distance passes the exact pre-filter
+// q <= qmax (qmax = largest float whose rounded sqrt is <= r_a + r_b, see api.cu).  The agent itself is among the
+// partners (q = 0), so a count of one means "no contact" -- the common case -- and nothing else runs.  The
+// difference is formed as partner - self with one packed add (sm_100 FADD2) against the negated own position:
+// b - a = -(a - b) exactly under round-to-nearest, and only squares of the components are used.
+// Phase 2 -- rare -- walks the partners in ascending order and adds the contact forces in vmas' accumulation order.
+__device__ __forceinline__ float2 xy_of(const float2& v) { return v; }
+__device__ __forceinline__ float2 xy_of(const float4& v) { return *reinterpret_cast<const float2*>(&v); }
+
 template <typename P>
 __device__ __forceinline__ void agent_contacts(const P* __restrict__ partners, int N, int self, float sx, float sy,
                                                float qmax, float dist_min, float collision_force, float k, float& fx,
                                                float& fy, uint32_t& cmask) {
-  for (int base = 0; base < N; base += 32) {
-    const int cnt = (N - base < 32) ? (N - base) : 32;
-    uint32_t m = 0;
+  const float2 neg = make_float2(-sx, -sy);
+  for (int base = 0; base < N; base += 32) {          // chunks of 32 keep phase 2 short for swarms of 1 000+ agents
+    const int end = (N - base < 32) ? N : base + 32;
+    int cnt = 0;
 #pragma unroll 4
-    for (int j = 0; j < cnt; ++j) {
-      const P o = partners[base + j];
-      const float dx = __fsub_rn(sx, o.x), dy = __fsub_rn(sy, o.y);
-      const float q = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
-      m |= (q <= qmax) ? (1u << j) : 0u;
+    for (int j = base; j < end; ++j) {
+      const float2 d = __fadd2_rn(xy_of(partners[j]), neg);
+      const float q = __fmaf_rn(d.y, d.y, __fmul_rn(d.x, d.x));
+      cnt += (q <= qmax) ? 1 : 0;
     }
-    if (self >= base && self < base + 32) m &= ~(1u << (self - base));
-    while (m) {
-      const int j = __ffs(m) - 1;
-      m &= m - 1;
-      const P o = partners[base + j];
+    if (cnt <= (((unsigned)(self - base) < 32u) ? 1 : 0)) continue;
+    for (int j = base; j < end; ++j) {
+      if (j == self) continue;
+      const float2 o = xy_of(partners[j]);
+      const float dx = __fsub_rn(sx, o.x), dy = __fsub_rn(sy, o.y);
+      if (!(__fmaf_rn(dy, dy, __fmul_rn(dx, dx)) <= qmax)) continue;
       float gx, gy;
       if (contact_force(sx, sy, o.x, o.y, dist_min, collision_force, k, gx, gy)) {
         fx = __fadd_rn(fx, gx);
         fy = __fadd_rn(fy, gy);
-        if (base + j < 32) cmask |= (1u << (base + j));
+        if (j < 32) cmask |= (1u << j);
       }
     }
   }

@@ -80,7 +80,9 @@ def test_reset_grid_bitexact(scenario, n):
 
 
 @pytest.mark.parametrize("scenario", ["go_to", "obstacle_avoidance"])
-@pytest.mark.parametrize("n,B", [(5, 600), (12, 600), (7, 37), (32, 64), (40, 9)])
+@pytest.mark.parametrize("n,B", [(5, 600), (12, 600), (7, 37), (32, 64), (40, 9),
+                                 # >= 148 full tiles: the TMA-pipelined streaming kernel (+ ragged tail on the plain one)
+                                 (12, 4100), (5, 8000), (32, 1200), (7, 16001)])
 def test_sim_step_parity(scenario, n, B):
     from oracle import batched_oracle as bo
     sb = _swarm()
