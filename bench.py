@@ -312,9 +312,11 @@ def run_ours(args):
 
 def measure_dqn(sb, ops, dev, cfg, weights, centers, dist, barrier, stream, rank, world, ticks=100):
     """BASELINE.json configs[1]: full DQN train step on the same envs -- per tick one fused
-    [Q -> eps-greedy -> step -> replay push] launch over all envs, one sample of G whole-swarm transitions, one
-    loss + backward, (gradient all-reduce,) clip + Adam.  Reported for G = 32 (the reference's batch, train:175)
-    and G = 4096 (one update touching as many transitions as one tick produces)."""
+    [Q -> eps-greedy -> step -> replay push] launch over all envs, one on-device draw of G whole-swarm transitions, one
+    loss + backward, (gradient all-reduce,) clip + Adam (+ hard target sync every 200 ticks).  The tick counters live
+    in device memory (swarm_train_tick_grad / _apply), so `ticks` ticks are captured once in a CUDA graph and
+    replayed; the same ticks launched eagerly are timed next to it.  Reported for G = 32 (the reference's batch,
+    train:175) and G = 4096 (one update touching as many transitions as one tick produces)."""
     from swarm_b200 import parallel
     B, N = cfg.num_envs, cfg.n_agents
     out = {}
@@ -323,44 +325,56 @@ def measure_dqn(sb, ops, dev, cfg, weights, centers, dist, barrier, stream, rank
         w = weights.clone()
         w_t = weights.clone()
         m, v = torch.zeros_like(w), torch.zeros_like(w)
-        grad = torch.empty_like(w)
-        loss = torch.empty(1, device=dev)
         state = ops.reset_grid(cfg, centers)
-        gcfg = ops.clone_config(cfg, num_envs=G)
-        gen = torch.Generator(device=dev)
-        gen.manual_seed(rank)
-        scale = parallel.global_loss_scale(G, N)
-        step = 0
+        returns = torch.zeros(B, N, device=dev)
+        hits = torch.zeros(B, dtype=torch.int32, device=dev)
+        tt = ops.TrainTick(cfg, ring, graphs_per_update=G, update_target_every=200,
+                           loss_scale=parallel.global_loss_scale(G, N), rng_seed=rank, sample_seed=1000 + rank,
+                           env_offset=rank * B)
+        tt.load_cursor(0, 0, 0.3)
 
-        def tick(t):
-            nonlocal step
-            ops.rollout(cfg, w, state, 1, epsilon=0.3, rng_seed=rank, rng_tick0=t, env_offset=rank * B, replay=ring)
-            idx = torch.randint(0, len(ring), (G,), generator=gen, device=dev, dtype=torch.int64)
-            ops.dqn_grad(gcfg, w, w_t, ring, idx, G, loss_scale=scale, grad=grad, loss=loss)
-            parallel.allreduce_gradient(grad, loss)
-            step += 1
-            ops.adam_clip_step(w, grad, m, v, step, target=w_t if step % 200 == 0 else None)
+        def tick():
+            tt.grad_phase(w, w_t, state, returns, hits)
+            if world > 1:
+                dist.all_reduce(tt.grad_loss)
+            tt.apply_phase(w, w_t, m, v)
 
-        for t in range(10):
-            tick(t)
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        for t in range(ticks):
-            tick(10 + t)
-        b.record(stream)
-        barrier()
-        ms = a.elapsed_time(b)
-        if dist is not None:
-            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms = float(tt.item())
+        def timed(fn):
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            fn()
+            b.record(stream)
+            barrier()
+            ms = a.elapsed_time(b)
+            if dist is not None:
+                t = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms
+
+        for _ in range(10):
+            tick()
+        ms_eager = timed(lambda: [tick() for _ in range(ticks)])
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(stream)
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(ticks):
+                tick()
+        torch.cuda.synchronize(dev)
+        graph.replay()                      # warm replay
+        ms = timed(graph.replay)
+        cur = tt.read_cursor()
         out[f"G{G}"] = {"graphs_per_update_per_gpu": G, "updates_per_s": ticks / (ms * 1e-3),
                         "train_agent_steps_per_s": world * B * N * ticks / (ms * 1e-3),
                         "transitions_trained_per_s": world * G * ticks / (ms * 1e-3), "ms_per_tick": ms / ticks,
-                        "loss": float(loss.item())}
-    out["note"] = ("one train tick = rollout tick of all envs (eps 0.3) + replay push + sample + TD target/loss/backward + "
-                   "grad all-reduce (N>1) + clip + Adam; eager launches, no CUDA graph")
+                        "ms_per_tick_eager": ms_eager / ticks, "kernels_per_tick": 5 + (1 if world > 1 else 0),
+                        "ticks_done": cur["tick"], "opt_steps_done": cur["opt_step"], "loss": float(tt.loss.item())}
+    out["note"] = ("one train tick = rollout tick of all envs (eps 0.3) + replay push + on-device sample + TD target/loss/"
+                   "backward + grad all-reduce (N>1) + clip + Adam (+ target sync every 200 ticks); %d ticks captured in "
+                   "one CUDA graph (device-resident tick counters), eager launches timed beside it" % ticks)
     return out
 
 

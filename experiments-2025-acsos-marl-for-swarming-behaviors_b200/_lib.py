@@ -56,6 +56,19 @@ class SwarmRolloutOptions(C.Structure):
                 ("env_offset", C.c_int64)]
 
 
+class SwarmTrainCtl(C.Structure):
+    """Host mirror of the 48-byte device struct (only used to document / check the layout)."""
+    _fields_ = [("tick", C.c_int64), ("ring_cursor", C.c_int64), ("ring_size", C.c_int64), ("opt_step", C.c_int64),
+                ("epsilon", C.c_float), ("updating", C.c_int32), ("reserved", C.c_int64)]
+
+
+class SwarmTrainHyper(C.Structure):
+    _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("max_norm", C.c_double), ("rng_seed", C.c_uint64), ("sample_seed", C.c_uint64),
+                ("env_offset", C.c_int64), ("graphs_per_update", C.c_int32), ("update_target_every", C.c_int32),
+                ("gamma", C.c_float), ("loss_scale", C.c_float)]
+
+
 class SwarmError(RuntimeError):
     pass
 
@@ -88,6 +101,10 @@ _SIGNATURES = {
     "swarm_adam_clip_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
                                        C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
+    "swarm_train_tick_grad": (C.c_int, [C.POINTER(SwarmConfig), C.POINTER(SwarmTrainHyper)] + [C.c_void_p] * 6
+                              + [C.POINTER(SwarmReplay)] + [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]),
+    "swarm_train_tick_apply": (C.c_int, [C.POINTER(SwarmConfig), C.POINTER(SwarmTrainHyper)] + [C.c_void_p] * 6
+                               + [C.c_int64, C.c_void_p]),
 }
 
 

@@ -31,10 +31,13 @@ long long dqn_workspace_bytes(const SwarmConfig& c, int n_graphs);
 int dqn_smem_bytes(const SwarmConfig& c);
 cudaError_t launch_dqn_grad(const SwarmConfig& c, const float* w_online, const float* w_target, const SwarmReplay& batch,
                             const int64_t* indices, int n_graphs, float gamma, float loss_scale, float* grad, float* loss,
-                            float* td, void* workspace, cudaStream_t stream);
+                            float* td, void* workspace, cudaStream_t stream, const SwarmTrainCtl* ctl = nullptr);
 cudaError_t launch_adam_clip(float* w, const float* grad, float* m, float* v, long long step, double lr, double beta1,
                              double beta2, double eps, double max_norm, float* target, float* grad_norm,
-                             cudaStream_t stream);
+                             cudaStream_t stream, SwarmTrainCtl* ctl = nullptr, int num_envs = 0,
+                             long long ring_capacity = 1, int update_target_every = 1);
+cudaError_t launch_train_sample(SwarmTrainCtl* ctl, int num_envs, long long capacity, int G, unsigned long long seed,
+                                int64_t* indices, cudaStream_t stream);
 
 namespace {
 thread_local std::string g_last_error;
@@ -349,6 +352,65 @@ int swarm_adam_clip_step(float* weights, const float* grad, float* exp_avg, floa
   return check_cuda(launch_adam_clip(weights, grad, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, max_norm,
                                      target_weights, grad_norm, (cudaStream_t)stream),
                     "swarm_adam_clip_step");
+}
+
+static int validate_hyper(const SwarmTrainHyper* h) {
+  if (!h) return fail(SWARM_ERR_INVALID_ARG, "hyper is NULL");
+  if (h->graphs_per_update <= 0) return fail(SWARM_ERR_INVALID_ARG, "graphs_per_update must be positive");
+  if (h->update_target_every <= 0) return fail(SWARM_ERR_INVALID_ARG, "update_target_every must be positive");
+  if (!(h->lr >= 0.0) || !(h->beta1 >= 0.0 && h->beta1 < 1.0) || !(h->beta2 >= 0.0 && h->beta2 < 1.0) || !(h->eps >= 0.0))
+    return fail(SWARM_ERR_INVALID_ARG, "invalid Adam hyper-parameter");
+  return SWARM_OK;
+}
+
+int swarm_train_tick_grad(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, SwarmTrainCtl* ctl, const float* weights,
+                          const float* target_weights, float* state, float* returns, int32_t* hits,
+                          const SwarmReplay* ring, int64_t* indices, float* grad, float* loss, void* workspace,
+                          int64_t workspace_bytes, void* stream) {
+  if (int rc = validate(cfg, true)) return rc;
+  if (int rc = validate_hyper(hyper)) return rc;
+  if (int rc = validate_dqn(cfg, hyper->graphs_per_update)) return rc;
+  if (!ctl || !weights || !target_weights || !state || !indices || !grad || !loss || !workspace)
+    return fail(SWARM_ERR_INVALID_ARG, "NULL argument");
+  if (!ring || !ring->state || !ring->next_state || !ring->actions || !ring->rewards || ring->capacity <= 0)
+    return fail(SWARM_ERR_INVALID_ARG, "replay ring has NULL arrays or no capacity");
+  if (cfg->num_envs > ring->capacity) return fail(SWARM_ERR_INVALID_ARG, "num_envs exceeds the replay capacity");
+  if (workspace_bytes < dqn_workspace_bytes(*cfg, hyper->graphs_per_update))
+    return fail(SWARM_ERR_INVALID_ARG, "workspace too small");
+  TileParams p;
+  if (int rc = fill_params(p, cfg, MODE_ROLLOUT)) return rc;
+  p.weights = weights;
+  p.state_in = state;
+  p.state_out = state;
+  p.ticks = 1;
+  p.returns = returns;
+  p.hits = hits;
+  p.rng_seed = hyper->rng_seed;
+  p.env_offset = hyper->env_offset;
+  p.replay = *ring;
+  p.ctl = ctl;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = check_cuda(launch_tile(MODE_ROLLOUT, p, st), "swarm_train_tick_grad(rollout)")) return rc;
+  if (int rc = check_cuda(launch_train_sample(ctl, cfg->num_envs, ring->capacity, hyper->graphs_per_update,
+                                              hyper->sample_seed, indices, st),
+                          "swarm_train_tick_grad(sample)"))
+    return rc;
+  return check_cuda(launch_dqn_grad(*cfg, weights, target_weights, *ring, indices, hyper->graphs_per_update, hyper->gamma,
+                                    hyper->loss_scale, grad, loss, nullptr, workspace, st, ctl),
+                    "swarm_train_tick_grad(grad)");
+}
+
+int swarm_train_tick_apply(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, SwarmTrainCtl* ctl, float* weights,
+                           float* target_weights, float* exp_avg, float* exp_avg_sq, const float* grad,
+                           int64_t ring_capacity, void* stream) {
+  if (!cfg || cfg->num_envs <= 0) return fail(SWARM_ERR_INVALID_ARG, "cfg is NULL or num_envs <= 0");
+  if (int rc = validate_hyper(hyper)) return rc;
+  if (!ctl || !weights || !target_weights || !exp_avg || !exp_avg_sq || !grad) return fail(SWARM_ERR_INVALID_ARG, "NULL argument");
+  if (ring_capacity < cfg->num_envs) return fail(SWARM_ERR_INVALID_ARG, "ring_capacity must be >= num_envs");
+  return check_cuda(launch_adam_clip(weights, grad, exp_avg, exp_avg_sq, 1, hyper->lr, hyper->beta1, hyper->beta2,
+                                     hyper->eps, hyper->max_norm, target_weights, nullptr, (cudaStream_t)stream, ctl,
+                                     cfg->num_envs, ring_capacity, hyper->update_target_every),
+                    "swarm_train_tick_apply");
 }
 
 }  // extern "C"

@@ -27,6 +27,7 @@ struct DqnParams {
   float* partials;
   float* td;
   int32_t epb, maxdeg;
+  const SwarmTrainCtl* ctl;   // optional device-resident training cursor: skip when !ctl->updating
 };
 
 struct DqnLayout {
@@ -96,6 +97,8 @@ __global__ void __launch_bounds__(kTileThreads) dqn_grad_kernel(const __grid_con
   const bool knn = c.graph_mode == SWARM_GRAPH_KNN;
   const TileThread t = tile_thread(N, p.epb, p.n_graphs);
   const int tid = t.tid;
+
+  if (p.ctl && !p.ctl->updating) return;      // replay ring not filled yet (train:113-115)
 
   const DqnLayout L = dqn_layout(N, K, p.maxdeg, p.epb, c.graph_mode);
   float* sw_on = reinterpret_cast<float*>(smem + L.w_on);
@@ -388,9 +391,11 @@ __global__ void __launch_bounds__(kTileThreads) dqn_grad_kernel(const __grid_con
 
 // grad[o] = sum over CTAs (in CTA order) of partials[cta][o]; loss = loss_scale * sum of squared TD errors
 __global__ void __launch_bounds__(256) dqn_reduce_kernel(const float* __restrict__ partials, int n_ctas, float loss_scale,
-                                                         float* __restrict__ grad, float* __restrict__ loss) {
+                                                         float* __restrict__ grad, float* __restrict__ loss,
+                                                         const SwarmTrainCtl* __restrict__ ctl) {
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o > SWARM_W_COUNT) return;
+  if (ctl && !ctl->updating) return;
   float acc = 0.0f;
   for (int b = 0; b < n_ctas; ++b) acc += partials[(long long)b * kPartialStride + o];
   if (o < SWARM_W_COUNT) grad[o] = acc;
@@ -412,12 +417,45 @@ struct AdamParams {
   float bc2_sqrt;        // sqrt(1 - beta2^t)
   float eps;
   float max_norm;
+  // device-driven variant (swarm_train_tick_apply): step-dependent scalars are derived from *ctl on the device and
+  // the cursor is advanced at the end
+  SwarmTrainCtl* ctl;
+  double lr, beta1, beta2d;
+  long long ring_capacity;
+  int32_t num_envs;
+  int32_t update_target_every;
 };
 
 __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
   __shared__ double ssq[8][256];
   __shared__ float s_coef;
+  __shared__ float s_neg_step, s_bc2_sqrt;
+  __shared__ int s_update, s_sync;
   const int tid = threadIdx.x;
+  if (p.ctl) {
+    if (tid == 0) {
+      const long long step = p.ctl->opt_step + 1;
+      const double bc1 = 1.0 - pow(p.beta1, (double)step);
+      const double bc2 = 1.0 - pow(p.beta2d, (double)step);
+      s_neg_step = (float)(-(p.lr / bc1));
+      s_bc2_sqrt = (float)sqrt(bc2);
+      s_update = p.ctl->updating;
+      s_sync = ((p.ctl->tick + 1) % p.update_target_every) == 0;
+    }
+    __syncthreads();
+    p.neg_step_size = s_neg_step;
+    p.bc2_sqrt = s_bc2_sqrt;
+    if (!s_sync) p.target = nullptr;
+    if (!s_update) {
+      if (tid == 0) {
+        p.ctl->tick += 1;
+        p.ctl->ring_cursor = (p.ctl->ring_cursor + p.num_envs) % p.ring_capacity;
+        const long long sz = p.ctl->ring_size + p.num_envs;
+        p.ctl->ring_size = sz < p.ring_capacity ? sz : p.ring_capacity;
+      }
+      return;
+    }
+  }
   const int seg_off[9] = {SWARM_W_CONV_LIN, SWARM_W_ATT_SRC, SWARM_W_ATT_DST, SWARM_W_CONV_BIAS, SWARM_W_LIN1,
                           SWARM_W_LIN1_BIAS, SWARM_W_LIN2, SWARM_W_LIN2_BIAS, SWARM_W_COUNT};
   // torch.nn.utils.clip_grad_norm_: norms = [||g_t||_2 for each parameter tensor]; total = ||norms||_2
@@ -468,6 +506,28 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
     p.w[o] = w;
     if (p.target) p.target[o] = w;
   }
+  if (p.ctl && tid == 0) {
+    p.ctl->tick += 1;
+    p.ctl->ring_cursor = (p.ctl->ring_cursor + p.num_envs) % p.ring_capacity;
+    const long long sz = p.ctl->ring_size + p.num_envs;
+    p.ctl->ring_size = sz < p.ring_capacity ? sz : p.ring_capacity;
+    p.ctl->opt_step += 1;
+  }
+}
+
+// ---- replay sampling on the device (GraphReplayBuffer.sample's index draw, train:38-39) ------------------------
+// indices[g] ~ U{0 .. size-1} with size = the ring fill AFTER this tick's push; counter RNG keyed by (seed, tick, g).
+__global__ void __launch_bounds__(256) train_sample_kernel(SwarmTrainCtl* ctl, int num_envs, long long capacity, int G,
+                                                           unsigned long long seed, int64_t* __restrict__ indices) {
+  long long size = ctl->ring_size + num_envs;
+  if (size > capacity) size = capacity;
+  const unsigned long long tick = (unsigned long long)(ctl->tick + 1);
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < G && size > 0) {
+    const uint64_t r = rng_draw(seed, (uint64_t)g, tick, 0x5A17u);
+    indices[g] = (int64_t)__umul64hi(r, (uint64_t)size);
+  }
+  if (g == 0) ctl->updating = (size >= G) ? 1 : 0;
 }
 
 // ---- launchers -------------------------------------------------------------------------------
@@ -486,10 +546,17 @@ int dqn_smem_bytes(const SwarmConfig& c) {
   return dqn_layout(c.n_agents, c.knn_k, dqn_maxdeg(c), epb, c.graph_mode).total;
 }
 
+cudaError_t launch_train_sample(SwarmTrainCtl* ctl, int num_envs, long long capacity, int G, unsigned long long seed,
+                                int64_t* indices, cudaStream_t stream) {
+  train_sample_kernel<<<(G + 255) / 256, 256, 0, stream>>>(ctl, num_envs, capacity, G, seed, indices);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_dqn_grad(const SwarmConfig& c, const float* w_online, const float* w_target, const SwarmReplay& batch,
                             const int64_t* indices, int n_graphs, float gamma, float loss_scale, float* grad, float* loss,
-                            float* td, void* workspace, cudaStream_t stream) {
+                            float* td, void* workspace, cudaStream_t stream, const SwarmTrainCtl* ctl) {
   DqnParams p;
+  p.ctl = ctl;
   p.cfg = c;
   p.w_online = w_online;
   p.w_target = w_target;
@@ -507,14 +574,22 @@ cudaError_t launch_dqn_grad(const SwarmConfig& c, const float* w_online, const f
   if (err != cudaSuccess) return err;
   const int ctas = (n_graphs + p.epb - 1) / p.epb;
   dqn_grad_kernel<<<ctas, kTileThreads, smem, stream>>>(p);
-  dqn_reduce_kernel<<<(SWARM_W_COUNT + 1 + 255) / 256, 256, 0, stream>>>(p.partials, ctas, loss_scale, grad, loss);
+  dqn_reduce_kernel<<<(SWARM_W_COUNT + 1 + 255) / 256, 256, 0, stream>>>(p.partials, ctas, loss_scale, grad, loss, ctl);
   return cudaGetLastError();
 }
 
 cudaError_t launch_adam_clip(float* w, const float* grad, float* m, float* v, long long step, double lr, double beta1,
                              double beta2, double eps, double max_norm, float* target, float* grad_norm,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, SwarmTrainCtl* ctl, int num_envs, long long ring_capacity,
+                             int update_target_every) {
   AdamParams p;
+  p.ctl = ctl;
+  p.lr = lr;
+  p.beta1 = beta1;
+  p.beta2d = beta2;
+  p.num_envs = num_envs;
+  p.ring_capacity = ring_capacity;
+  p.update_target_every = update_target_every > 0 ? update_target_every : 1;
   p.w = w;
   p.grad = grad;
   p.m = m;

@@ -97,6 +97,15 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(const __grid_constan
   float ret = 0.0f;
   int myhits = 0;
 
+  // tick-dependent scalars: launch parameters, or the device-resident training cursor (graph-replayable ticks)
+  float epsilon = p.epsilon;
+  long long rng_tick0 = p.rng_tick0, replay_cursor = p.replay_cursor;
+  if (MODE == MODE_ROLLOUT && p.ctl) {
+    epsilon = p.ctl->epsilon;
+    rng_tick0 = p.ctl->tick + 1;
+    replay_cursor = p.ctl->ring_cursor;
+  }
+
   for (int tick = 0; tick < p.ticks; ++tick) {
     const float4* pos = sst + (tick & 1) * T;
     sst[(tick & 1) * T + tid] = s;
@@ -168,12 +177,12 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(const __grid_constan
         if (MODE == MODE_STEP) {
           action = p.actions_in[t.gidx];
         } else {
-          if (p.epsilon > 0.0f) {
+          if (epsilon > 0.0f) {
             // train:164-165: one coin per tick for the whole swarm, then one uniform action per agent
             const unsigned long long genv = (unsigned long long)(p.env_offset + t.env);
-            const unsigned long long gt = (unsigned long long)(p.rng_tick0 + tick);
+            const unsigned long long gt = (unsigned long long)(rng_tick0 + tick);
             const float coin = (float)(rng_draw(p.rng_seed, genv, gt, 0xFFFFu) >> 40) * (1.0f / 16777216.0f);
-            if (coin < p.epsilon) action = (int)(((rng_draw(p.rng_seed, genv, gt, (uint32_t)t.i) >> 32) * 9ull) >> 32);
+            if (coin < epsilon) action = (int)(((rng_draw(p.rng_seed, genv, gt, (uint32_t)t.i) >> 32) * 9ull) >> 32);
           }
           if (p.actions_in) {
             const int fa = p.actions_in[(long long)tick * BN + t.gidx];
@@ -213,7 +222,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(const __grid_constan
           if (p.trace.dist) reinterpret_cast<float2*>(p.trace.dist)[tb] = make_float2(dgoal, dobs);
           if (p.replay.state) {
             // GraphReplayBuffer.push (train:171-172), state-only transition
-            const long long slot = (p.replay_cursor + (long long)tick * c.num_envs + t.env) % p.replay.capacity;
+            const long long slot = (replay_cursor + (long long)tick * c.num_envs + t.env) % p.replay.capacity;
             const long long ri = slot * N + t.i;
             reinterpret_cast<float4*>(p.replay.state)[ri] = s_prev;
             reinterpret_cast<float4*>(p.replay.next_state)[ri] = s;
@@ -234,7 +243,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(const __grid_constan
         } else {
           if (p.trace.rewards) p.trace.rewards[(long long)tick * BN + t.gidx] = reward;
           if (p.replay.state) {
-            const long long slot = (p.replay_cursor + (long long)tick * c.num_envs + t.env) % p.replay.capacity;
+            const long long slot = (replay_cursor + (long long)tick * c.num_envs + t.env) % p.replay.capacity;
             p.replay.rewards[slot * N + t.i] = reward;
           }
         }

@@ -74,6 +74,7 @@ struct TileParams {
   int32_t* edges_out;            // MODE_GRAPH
   int32_t* nbr_out;              // MODE_GRAPH
   SwarmReplay replay;            // MODE_ROLLOUT, optional (state == nullptr: no push)
+  const SwarmTrainCtl* ctl;      // MODE_ROLLOUT, optional: tick number / ring cursor / epsilon come from device memory
   long long replay_cursor;
   long long env_offset;
   unsigned long long rng_seed;

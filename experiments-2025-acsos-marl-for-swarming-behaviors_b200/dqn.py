@@ -217,52 +217,71 @@ class DQNTrainer:
             self.save_metrics_to_csv()
 
     def train_model_batched(self, config) -> Dict[str, float]:
-        """B envs per tick: fused [Q -> eps-greedy -> step -> replay push] kernel, then one update of
-        ``graphs_per_update`` transitions sampled uniformly on the device.  Same schedule as train:139-204
-        (epsilon per episode, hard target sync every ``update_target_every`` ticks)."""
+        """B envs per tick, G graphs per update (throughput mode).  Same schedule as train:139-204 (epsilon per
+        episode, hard target sync every ``update_target_every`` ticks), device RNG for exploration and sampling.
+
+        Every tick is the pair ``swarm_train_tick_grad`` (fused [Q -> eps-greedy -> step -> replay push], index draw,
+        TD target / loss / backward) + ``swarm_train_tick_apply`` (clip + Adam + target sync), with one gradient
+        all-reduce in between when data-parallel.  The tick counters live on the device, so with
+        ``config["cuda_graph"]`` (default on) the ticks of one episode are captured once in a CUDA graph and each
+        episode is a single graph launch."""
         env, world = self.env, self.env.world
         B, n, dev = env.num_envs, env.n_agents, env.device
         G = int(config.get("graphs_per_update", 32))
-        update_target_every = int(config.get("update_target_every", 200))
-        gamma = float(config.get("gamma", 0.99))
         episodes = config["episodes"]
         epsilon = config["epsilon"]
+        use_graph = bool(config.get("cuda_graph", True))
         ring = self.replay_buffer.ring
         cfg = ops.clone_config(self.graph_cfg, num_envs=B)
-        gcfg = ops.clone_config(self.graph_cfg, num_envs=G)
-        gen = torch.Generator(device=dev)
         rank = torch.distributed.get_rank() if parallel.world_size() > 1 else 0
-        gen.manual_seed(int(config.get("sample_seed", self.seed)) + 7919 * rank)
-        env_offset = int(config.get("env_offset", rank * B))
         # env-sharded data parallelism: G graphs per rank, loss = mean over the global batch, gradient summed
         # over ranks, identical clip + Adam everywhere (weights stay replicated; target sync is local)
-        loss_scale = parallel.global_loss_scale(G, n)
+        tt = ops.TrainTick(cfg, ring, graphs_per_update=G, update_target_every=int(config.get("update_target_every", 200)),
+                           gamma=float(config.get("gamma", 0.99)), loss_scale=parallel.global_loss_scale(G, n),
+                           lr=self.lr, betas=self.betas, eps=self.eps, max_norm=self.max_norm, rng_seed=self.seed,
+                           sample_seed=int(config.get("sample_seed", self.seed)) + 7919 * rank,
+                           env_offset=int(config.get("env_offset", rank * B)))
         parallel.broadcast_weights(self.w)
         self.w_target.copy_(self.w)
-        ticks = 0
+        tt.load_cursor(int(config.get("start_tick", 0)), self.opt_step, epsilon)
         returns = torch.zeros(B, n, dtype=torch.float32, device=dev)
         hits = torch.zeros(B, dtype=torch.int32, device=dev)
+        multi = parallel.world_size() > 1
+
+        def tick():
+            tt.grad_phase(self.w, self.w_target, world.state, returns, hits)
+            if multi:
+                torch.distributed.all_reduce(tt.grad_loss)
+            tt.apply_phase(self.w, self.w_target, self.exp_avg, self.exp_avg_sq)
+
+        graph = None
         stats = {}
         for episode in range(episodes):
             env.reset()
             returns.zero_()
             hits.zero_()
-            for _ in range(env.max_steps):
-                ticks += 1
-                ops.rollout(cfg, self.w, world.state, 1, returns=returns, hits=hits, epsilon=epsilon, rng_seed=self.seed,
-                            rng_tick0=ticks, env_offset=env_offset, replay=ring)
-                if len(ring) >= G:
-                    idx = torch.randint(0, len(ring), (G,), generator=gen, device=dev, dtype=torch.int64)
-                    ops.dqn_grad(gcfg, self.w, self.w_target, ring, idx, G, gamma=gamma, loss_scale=loss_scale,
-                                 grad=self._grad, loss=self._loss)
-                    parallel.allreduce_gradient(self._grad, self._loss)
-                    self.opt_step += 1
-                    ops.adam_clip_step(self.w, self._grad, self.exp_avg, self.exp_avg_sq, self.opt_step, self.lr, self.betas,
-                                       self.eps, self.max_norm,
-                                       target=self.w_target if ticks % update_target_every == 0 else None)
+            tt.set_epsilon(epsilon)
+            if use_graph and graph is None and episode > 0:
+                # capture after one eager episode (kernel attributes set, NCCL communicator warm)
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.graph(graph, stream=side):
+                    for _ in range(env.max_steps):
+                        tick()
+                graph.replay()
+            elif graph is not None:
+                graph.replay()
+            else:
+                for _ in range(env.max_steps):
+                    tick()
             epsilon = max(config["min_epsilon"], config["epsilon"] * np.exp(-config["epsilon_decay"] * episode))
+            cur = tt.read_cursor()
             stats = {"episode": episode, "mean_return_agent0": float(returns[:, 0].mean() / n),
-                     "loss": float(self._loss.item()) if self.opt_step else 0.0, "hits_per_env": float(hits.float().mean())}
+                     "loss": float(tt.loss.item()) if cur["opt_step"] else 0.0, "hits_per_env": float(hits.float().mean()),
+                     "ticks": cur["tick"], "opt_steps": cur["opt_step"]}
+            self.opt_step = cur["opt_step"]
             self.episode_losses.append(stats["loss"])
             self.rewards_buffer.append(torch.tensor(stats["mean_return_agent0"]))
             if (episode + 1) % 10 == 0:
@@ -270,6 +289,8 @@ class DQNTrainer:
                 self.rewards_buffer = []
             if config.get("verbose", False):
                 print(stats)
+        self._grad.copy_(tt.grad)
+        self._loss.copy_(tt.loss)
         self.sync_modules()
         return stats
 

@@ -249,6 +249,74 @@ def adam_clip_step(weights: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Ten
                                      ptr(grad_norm), stream_ptr(weights.device)))
 
 
+class TrainTick:
+    """Device-driven train tick (swarm_train_tick_grad / swarm_train_tick_apply): one iteration of the loop body of
+    train_gcn_dqn.py:153-178 for all B envs, with the tick number, replay cursor / fill, optimiser step and epsilon
+    held in a 48-byte device struct that the kernels advance themselves.  No launch argument changes from tick to
+    tick, so ``grad_phase`` / ``apply_phase`` can be captured in a CUDA graph and replayed (``DQNTrainer``)."""
+
+    CTL_WORDS = 6      # int64 words: tick, ring_cursor, ring_size, opt_step, (epsilon f32 | updating i32), reserved
+
+    def __init__(self, cfg: SwarmConfig, ring: ReplayRing, *, graphs_per_update: int = 32, update_target_every: int = 200,
+                 gamma: float = 0.99, loss_scale: Optional[float] = None, lr: float = 1e-3, betas=(0.9, 0.999),
+                 eps: float = 1e-8, max_norm: float = 1.0, rng_seed: int = 0, sample_seed: int = 0, env_offset: int = 0):
+        dev = ring.state.device
+        self.cfg, self.ring = cfg, ring
+        G = int(graphs_per_update)
+        h = _lib.SwarmTrainHyper()
+        h.lr, h.beta1, h.beta2, h.eps, h.max_norm = float(lr), float(betas[0]), float(betas[1]), float(eps), float(max_norm)
+        h.rng_seed = int(rng_seed) & 0xFFFFFFFFFFFFFFFF
+        h.sample_seed = int(sample_seed) & 0xFFFFFFFFFFFFFFFF
+        h.env_offset = int(env_offset)
+        h.graphs_per_update, h.update_target_every = G, int(update_target_every)
+        h.gamma = float(gamma)
+        h.loss_scale = float(loss_scale) if loss_scale is not None else 1.0 / (G * cfg.n_agents)
+        self.hyper = h
+        assert C.sizeof(_lib.SwarmTrainCtl) == 8 * self.CTL_WORDS
+        self.ctl = torch.zeros(self.CTL_WORDS, dtype=torch.int64, device=dev)
+        self.indices = torch.zeros(G, dtype=torch.int64, device=dev)
+        # gradient and loss share one buffer so that a data-parallel trainer all-reduces both in one collective
+        self.grad_loss = torch.zeros(_lib.W_COUNT + 1, dtype=torch.float32, device=dev)
+        self.grad = self.grad_loss[:_lib.W_COUNT]
+        self.loss = self.grad_loss[_lib.W_COUNT:]
+        gcfg = clone_config(cfg, num_envs=G)
+        self._ws_bytes = int(lib().swarm_dqn_workspace_bytes(C.byref(gcfg), G))
+        self.workspace = torch.empty(max(self._ws_bytes, 256), dtype=torch.uint8, device=dev)
+        self._rstruct = ring.struct()
+
+    # -- cursor <-> host bookkeeping ---------------------------------------------------------------
+    def load_cursor(self, tick: int, opt_step: int, epsilon: float) -> None:
+        """Write the host-side counters (tick, ring position / size, optimiser step, epsilon) into the device cursor."""
+        words = torch.tensor([int(tick), self.ring.position, self.ring.size, int(opt_step), 0, 0], dtype=torch.int64)
+        words.view(torch.float32)[8] = float(epsilon)
+        self.ctl.copy_(words)
+
+    def set_epsilon(self, epsilon: float) -> None:
+        self.ctl.view(torch.float32)[8:9].fill_(float(epsilon))
+
+    def read_cursor(self) -> Dict[str, float]:
+        """Read the device cursor back (one small D2H copy) and update the ring's host-side position / size."""
+        words = self.ctl.cpu()
+        self.ring.position, self.ring.size = int(words[1]), int(words[2])
+        return {"tick": int(words[0]), "opt_step": int(words[3]), "epsilon": float(words.view(torch.float32)[8]),
+                "updating": int(words.view(torch.int32)[9])}
+
+    # -- the two phases -------------------------------------------------------------------------------
+    def grad_phase(self, weights: torch.Tensor, target: torch.Tensor, state: torch.Tensor, returns: torch.Tensor,
+                   hits: torch.Tensor) -> None:
+        dev = state.device
+        check(lib().swarm_train_tick_grad(C.byref(self.cfg), C.byref(self.hyper), ptr(self.ctl), ptr(weights), ptr(target),
+                                          ptr(state), ptr(returns), ptr(hits), C.byref(self._rstruct), ptr(self.indices),
+                                          ptr(self.grad), ptr(self.loss), ptr(self.workspace), self._ws_bytes,
+                                          stream_ptr(dev)))
+
+    def apply_phase(self, weights: torch.Tensor, target: torch.Tensor, exp_avg: torch.Tensor,
+                    exp_avg_sq: torch.Tensor) -> None:
+        check(lib().swarm_train_tick_apply(C.byref(self.cfg), C.byref(self.hyper), ptr(self.ctl), ptr(weights), ptr(target),
+                                           ptr(exp_avg), ptr(exp_avg_sq), ptr(self.grad), self.ring.capacity,
+                                           stream_ptr(weights.device)))
+
+
 def csr_from_edges(edge_index: torch.Tensor, n_nodes: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """edge_index int64[2,E] -> (row_ptr int32[n+1], src int32[E], perm int32[E]), edges grouped by target,
     each group in edge-list order."""

@@ -210,6 +210,51 @@ int swarm_adam_clip_step(float* weights, const float* grad, float* exp_avg, floa
                          double lr, double beta1, double beta2, double eps, double max_norm,
                          float* target_weights, float* grad_norm, void* stream);
 
+/* ---- device-driven train tick -------------------------------------------------------------------------------
+ * One tick of the training loop body (train_gcn_dqn.py:153-178): act (epsilon-greedy on Q_online) -> env step ->
+ * replay push -> sample -> TD target / loss / backward -> clip + Adam (-> hard target sync).  Everything that
+ * changes from tick to tick (tick number, ring cursor / fill, optimiser step, epsilon) lives in a small DEVICE
+ * struct that the kernels read and the last kernel advances, so the host never has to know the tick number:
+ * the launches of one or many ticks can be captured once in a CUDA graph and replayed.
+ * The tick is split in two calls so that a data-parallel trainer can all-reduce `grad` / `loss` in between. */
+typedef struct SwarmTrainCtl {   /* device memory, 48 bytes, zero-initialised by the caller */
+  int64_t tick;          /* ticks completed (the tick being executed is tick + 1, like `ticks += 1` at train:155)   */
+  int64_t ring_cursor;   /* next replay slot                                                                        */
+  int64_t ring_size;     /* filled replay slots                                                                     */
+  int64_t opt_step;      /* optimiser steps done                                                                    */
+  float epsilon;         /* exploration rate of the running episode (the host rewrites it between episodes)         */
+  int32_t updating;      /* set by swarm_train_tick_grad: 1 if the ring holds >= graphs_per_update slots (train:113) */
+  int64_t reserved;
+} SwarmTrainCtl;
+
+typedef struct SwarmTrainHyper {
+  double lr, beta1, beta2, eps, max_norm;   /* torch.optim.Adam defaults + clip_grad_norm_ max_norm (train:85,125)  */
+  uint64_t rng_seed;            /* exploration stream (same stream as swarm_rollout's)                              */
+  uint64_t sample_seed;         /* replay sampling stream                                                           */
+  int64_t env_offset;           /* global index of env 0 of this shard                                              */
+  int32_t graphs_per_update;    /* G (reference: 32, train:175)                                                     */
+  int32_t update_target_every;  /* hard target sync period in ticks (reference: 200, train:175)                     */
+  float gamma;                  /* 0.99                                                                             */
+  float loss_scale;             /* 1 / (global number of nodes in the update batch)                                 */
+} SwarmTrainHyper;
+
+/* Phase 1: rollout tick of all cfg->num_envs envs with the online weights (pushes B transitions at ctl->ring_cursor),
+ * draws graphs_per_update slot indices uniformly from the filled part of the ring (counter RNG keyed by
+ * (sample_seed, tick, g)) into indices int64[G], then gradient + loss of the update batch as swarm_dqn_grad.
+ * workspace: swarm_dqn_workspace_bytes(cfg, G).  If the ring holds fewer than G slots, grad / loss are left
+ * untouched and ctl->updating = 0 (the reference prints "Not enough samples" and skips, train:113-115). */
+int swarm_train_tick_grad(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, SwarmTrainCtl* ctl,
+                          const float* weights, const float* target_weights, float* state, float* returns,
+                          int32_t* hits, const SwarmReplay* ring, int64_t* indices, float* grad, float* loss,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Phase 2: clip_grad_norm_ + Adam on `grad` (bias corrections from ctl->opt_step + 1), target <- online when
+ * (ctl->tick + 1) % update_target_every == 0, then ctl advances: tick += 1, ring_cursor / ring_size += B,
+ * opt_step += updating. */
+int swarm_train_tick_apply(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, SwarmTrainCtl* ctl, float* weights,
+                           float* target_weights, float* exp_avg, float* exp_avg_sq, const float* grad,
+                           int64_t ring_capacity, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

