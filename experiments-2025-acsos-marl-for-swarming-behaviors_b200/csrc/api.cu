@@ -31,13 +31,12 @@ long long dqn_workspace_bytes(const SwarmConfig& c, int n_graphs);
 int dqn_smem_bytes(const SwarmConfig& c);
 cudaError_t launch_dqn_grad(const SwarmConfig& c, const float* w_online, const float* w_target, const SwarmReplay& batch,
                             const int64_t* indices, int n_graphs, float gamma, float loss_scale, float* grad, float* loss,
-                            float* td, void* workspace, cudaStream_t stream, const SwarmTrainCtl* ctl = nullptr);
+                            float* td, void* workspace, cudaStream_t stream, SwarmTrainCtl* ctl = nullptr,
+                            int64_t* indices_out = nullptr, unsigned long long sample_seed = 0, int pushed_envs = 0);
 cudaError_t launch_adam_clip(float* w, const float* grad, float* m, float* v, long long step, double lr, double beta1,
                              double beta2, double eps, double max_norm, float* target, float* grad_norm,
                              cudaStream_t stream, SwarmTrainCtl* ctl = nullptr, int num_envs = 0,
                              long long ring_capacity = 1, int update_target_every = 1);
-cudaError_t launch_train_sample(SwarmTrainCtl* ctl, int num_envs, long long capacity, int G, unsigned long long seed,
-                                int64_t* indices, cudaStream_t stream);
 
 namespace {
 thread_local std::string g_last_error;
@@ -370,7 +369,7 @@ int swarm_train_tick_grad(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, 
   if (int rc = validate(cfg, true)) return rc;
   if (int rc = validate_hyper(hyper)) return rc;
   if (int rc = validate_dqn(cfg, hyper->graphs_per_update)) return rc;
-  if (!ctl || !weights || !target_weights || !state || !indices || !grad || !loss || !workspace)
+  if (!ctl || !weights || !target_weights || !state || !grad || !loss || !workspace)
     return fail(SWARM_ERR_INVALID_ARG, "NULL argument");
   if (!ring || !ring->state || !ring->next_state || !ring->actions || !ring->rewards || ring->capacity <= 0)
     return fail(SWARM_ERR_INVALID_ARG, "replay ring has NULL arrays or no capacity");
@@ -391,12 +390,9 @@ int swarm_train_tick_grad(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, 
   p.ctl = ctl;
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = check_cuda(launch_tile(MODE_ROLLOUT, p, st), "swarm_train_tick_grad(rollout)")) return rc;
-  if (int rc = check_cuda(launch_train_sample(ctl, cfg->num_envs, ring->capacity, hyper->graphs_per_update,
-                                              hyper->sample_seed, indices, st),
-                          "swarm_train_tick_grad(sample)"))
-    return rc;
-  return check_cuda(launch_dqn_grad(*cfg, weights, target_weights, *ring, indices, hyper->graphs_per_update, hyper->gamma,
-                                    hyper->loss_scale, grad, loss, nullptr, workspace, st, ctl),
+  return check_cuda(launch_dqn_grad(*cfg, weights, target_weights, *ring, nullptr, hyper->graphs_per_update, hyper->gamma,
+                                    hyper->loss_scale, grad, loss, nullptr, workspace, st, ctl, indices,
+                                    hyper->sample_seed, cfg->num_envs),
                     "swarm_train_tick_grad(grad)");
 }
 

@@ -27,8 +27,19 @@ struct DqnParams {
   float* partials;
   float* td;
   int32_t epb, maxdeg;
-  const SwarmTrainCtl* ctl;   // optional device-resident training cursor: skip when !ctl->updating
+  int32_t parallel;           // 1: target pass and online pass of a transition run side by side on two thread groups
+  // device-driven tick (swarm_train_tick_grad): slots are drawn here from the ring fill after this tick's push
+  const SwarmTrainCtl* ctl;
+  int64_t* indices_out;       // [n_graphs] the drawn slots (exported for tests / logging)
+  unsigned long long sample_seed;
+  int32_t pushed_envs;        // transitions pushed by this tick's rollout
 };
+
+// ring fill after this tick's push, and whether it allows an update (train:113-115)
+__device__ __forceinline__ long long train_ring_size(const SwarmTrainCtl* ctl, int pushed, long long capacity) {
+  const long long size = ctl->ring_size + pushed;
+  return size < capacity ? size : capacity;
+}
 
 struct DqnLayout {
   int w_on, w_tg, st, h, asrc, wt, wd, inl, kv, ki, nbr, u, r, dp, dob, dh, x, dq, ds, dt, ma, mz, red, total;
@@ -72,12 +83,21 @@ __device__ __forceinline__ void store_row32(float* tile, int row, const float (&
 #pragma unroll
   for (int c4 = 0; c4 < 8; ++c4) r[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
 }
+__device__ __forceinline__ void load_row32(const float* tile, int row, float (&v)[32]) {
+  const float4* r = reinterpret_cast<const float4*>(tile + row * kHPad);
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4) {
+    const float4 q = r[c4];
+    v[4 * c4] = q.x; v[4 * c4 + 1] = q.y; v[4 * c4 + 2] = q.z; v[4 * c4 + 3] = q.w;
+  }
+}
+__device__ __forceinline__ float f4c(const float4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
 
-// acc[0..3] += sum_n A[n*lda + ac] * B[n*ldb + bc .. bc+3]   (A == nullptr: column of ones)
-__device__ __forceinline__ float4 tile_gemm4(const float* A, int lda, int ac, const float* B, int ldb, int bc) {
+// acc[0..3] += sum_{n < rows} A[n*lda + ac] * B[n*ldb + bc .. bc+3]   (A == nullptr: column of ones)
+__device__ __forceinline__ float4 tile_gemm4(const float* A, int lda, int ac, const float* B, int ldb, int bc, int rows) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-  for (int n = 0; n < kTileThreads; ++n) {
+  for (int n = 0; n < rows; ++n) {
     const float a = A ? A[n * lda + ac] : 1.0f;
     const float4 b = *reinterpret_cast<const float4*>(B + n * ldb + bc);
     acc.x = fmaf(a, b.x, acc.x);
@@ -88,6 +108,78 @@ __device__ __forceinline__ float4 tile_gemm4(const float* A, int lda, int ac, co
   return acc;
 }
 
+// (aggregate + conv1.bias) -> tanh -> lin1 -> ReLU -> lin2 with the same arithmetic as gat_head_keep
+// (gatq_device.cuh), but ROLLED: the k loops run four input channels per iteration and read the layer input back
+// from the thread's own shared-memory row, so the body is ~160 instructions instead of ~1 300 fully unrolled.
+// The kernel executes every instruction once per warp, i.e. it streams its own code: size is what it pays for.
+// On return urow = u = tanh(agg + b0), rrow / r = relu(W1 u + b1).
+__device__ __forceinline__ void dqn_head(const float (&agg)[32], float* __restrict__ urow, float* __restrict__ rrow,
+                                         const float* __restrict__ sw, float (&r)[32], float (&q)[9]) {
+  float4* u4 = reinterpret_cast<float4*>(urow);
+  float4* r4 = reinterpret_cast<float4*>(rrow);
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4) u4[c4] = make_float4(agg[4 * c4], agg[4 * c4 + 1], agg[4 * c4 + 2], agg[4 * c4 + 3]);
+  const float4* b0 = reinterpret_cast<const float4*>(sw + TW_B0);
+#pragma unroll 1
+  for (int c4 = 0; c4 < 8; ++c4) {
+    float4 v = u4[c4];
+    const float4 b = b0[c4];
+    v.x = tanhf(__fadd_rn(v.x, b.x));
+    v.y = tanhf(__fadd_rn(v.y, b.y));
+    v.z = tanhf(__fadd_rn(v.z, b.z));
+    v.w = tanhf(__fadd_rn(v.w, b.w));
+    u4[c4] = v;
+  }
+#pragma unroll
+  for (int cc = 0; cc < 32; ++cc) r[cc] = 0.0f;
+  const float4* w1 = reinterpret_cast<const float4*>(sw + TW_W1T);
+#pragma unroll 1
+  for (int k4 = 0; k4 < 8; ++k4) {
+    const float4 uk = u4[k4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float a = f4c(uk, kk);
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 w = w1[(k4 * 4 + kk) * 8 + c4];
+        r[4 * c4 + 0] = fmaf(a, w.x, r[4 * c4 + 0]);
+        r[4 * c4 + 1] = fmaf(a, w.y, r[4 * c4 + 1]);
+        r[4 * c4 + 2] = fmaf(a, w.z, r[4 * c4 + 2]);
+        r[4 * c4 + 3] = fmaf(a, w.w, r[4 * c4 + 3]);
+      }
+    }
+  }
+  const float* b1 = sw + TW_B1;
+#pragma unroll
+  for (int cc = 0; cc < 32; ++cc) r[cc] = fmaxf(__fadd_rn(r[cc], b1[cc]), 0.0f);
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4) r4[c4] = make_float4(r[4 * c4], r[4 * c4 + 1], r[4 * c4 + 2], r[4 * c4 + 3]);
+
+  float qq[kW2Pad];
+#pragma unroll
+  for (int a = 0; a < kW2Pad; ++a) qq[a] = 0.0f;
+  const float4* w2 = reinterpret_cast<const float4*>(sw + TW_W2T);
+#pragma unroll 1
+  for (int k4 = 0; k4 < 8; ++k4) {
+    const float4 rk = r4[k4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float a = f4c(rk, kk);
+#pragma unroll
+      for (int a4 = 0; a4 < 3; ++a4) {
+        const float4 w = w2[(k4 * 4 + kk) * 3 + a4];
+        qq[4 * a4 + 0] = fmaf(a, w.x, qq[4 * a4 + 0]);
+        qq[4 * a4 + 1] = fmaf(a, w.y, qq[4 * a4 + 1]);
+        qq[4 * a4 + 2] = fmaf(a, w.z, qq[4 * a4 + 2]);
+        qq[4 * a4 + 3] = fmaf(a, w.w, qq[4 * a4 + 3]);
+      }
+    }
+  }
+  const float* b2 = sw + TW_B2;
+#pragma unroll
+  for (int a = 0; a < 9; ++a) q[a] = __fadd_rn(qq[a], b2[a]);
+}
+
 __global__ void __launch_bounds__(kTileThreads) dqn_grad_kernel(const __grid_constant__ DqnParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const SwarmConfig& c = p.cfg;
@@ -95,10 +187,23 @@ __global__ void __launch_bounds__(kTileThreads) dqn_grad_kernel(const __grid_con
   const int N = c.n_agents;
   const int K = c.knn_k;
   const bool knn = c.graph_mode == SWARM_GRAPH_KNN;
-  const TileThread t = tile_thread(N, p.epb, p.n_graphs);
+  // Thread groups: el in [0, epb) runs the online network on s (and the backward pass); in `parallel` mode
+  // el in [epb, 2 epb) runs the target network on s' of transition el - epb at the same time, otherwise the online
+  // group runs both passes one after the other.
+  TileThread t = tile_thread(N, p.parallel ? 2 * p.epb : p.epb, p.n_graphs);
   const int tid = t.tid;
-
-  if (p.ctl && !p.ctl->updating) return;      // replay ring not filled yet (train:113-115)
+  const bool tgt_group = p.parallel && t.el >= p.epb;
+  {
+    const int gl = tgt_group ? t.el - p.epb : t.el;
+    t.env = (long long)blockIdx.x * p.epb + gl;
+    t.active = (t.el < (p.parallel ? 2 * p.epb : p.epb)) && (t.env < p.n_graphs);
+    t.gidx = t.env * N + t.i;
+  }
+  long long ring_size = 0;
+  if (p.ctl) {
+    ring_size = train_ring_size(p.ctl, p.pushed_envs, p.batch.capacity);
+    if (ring_size < p.n_graphs) return;        // replay ring not filled yet (train:113-115)
+  }
 
   const DqnLayout L = dqn_layout(N, K, p.maxdeg, p.epb, c.graph_mode);
   float* sw_on = reinterpret_cast<float*>(smem + L.w_on);
@@ -125,6 +230,7 @@ __global__ void __launch_bounds__(kTileThreads) dqn_grad_kernel(const __grid_con
   float* mA = reinterpret_cast<float*>(smem + L.ma);
   float* mZ = reinterpret_cast<float*>(smem + L.mz);
   float* sred = reinterpret_cast<float*>(smem + L.red);
+  const int rows = p.epb * N;                  // node rows of this CTA that can be non-zero (online group)
 
   stage_weights(p.w_online, sw_on, tid, T);
   stage_weights(p.w_target, sw_tg, tid, T);
@@ -133,126 +239,146 @@ __global__ void __launch_bounds__(kTileThreads) dqn_grad_kernel(const __grid_con
   int act = 0;
   float rew = 0.0f;
   if (t.active) {
-    const long long slot = p.indices ? p.indices[t.env] : t.env;
+    long long slot = t.env;
+    if (p.ctl) {
+      // GraphReplayBuffer.sample's index draw (train:38-39) on the device: slot ~ U{0 .. ring_size - 1}, counter RNG
+      // keyed by (sample_seed, tick, graph)
+      const uint64_t rnd = rng_draw(p.sample_seed, (uint64_t)t.env, (uint64_t)(p.ctl->tick + 1), 0x5A17u);
+      slot = (long long)__umul64hi(rnd, (uint64_t)ring_size);
+      if (p.indices_out && t.i == 0 && !tgt_group) p.indices_out[t.env] = slot;
+    } else if (p.indices) {
+      slot = p.indices[t.env];
+    }
     const long long ri = slot * N + t.i;
     s = reinterpret_cast<const float4*>(p.batch.state)[ri];
     s2 = reinterpret_cast<const float4*>(p.batch.next_state)[ri];
     act = p.batch.actions[ri];
     rew = p.batch.rewards[ri];
+  } else if (tid < rows) {
+    // rows of idle threads inside the row range take part in the tile GEMMs below: exact zeros
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* tiles[6] = {g.sh, tU, tR, tDP, tDO, tDH};
+#pragma unroll 1
+    for (int b = 0; b < 6; ++b) {
+      float4* row = reinterpret_cast<float4*>(tiles[b] + tid * kHPad);
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) row[c4] = z;
+    }
+    reinterpret_cast<float4*>(tX + tid * kXPad)[0] = z;
+    reinterpret_cast<float4*>(tX + tid * kXPad)[1] = z;
+#pragma unroll
+    for (int a = 0; a < kW2Pad; ++a) tDQ[tid * kW2Pad + a] = 0.0f;
   }
 
   int deg = 0;
   if (!knn && t.active) deg = tile_in_edges_complete(g, t, N);
-  float agg[32];
-  float adst;
+  float agg[32], r[32];
+  float adst = 0.0f, y = 0.0f, delta = 0.0f, dq = 0.0f;
 
-  // ---------------- target network on s' : y = r + gamma * max_a Q_target(s')  (train:120-121) ------
-  sst[tid] = s2;
-  __syncthreads();
-  if (knn) {
-    tile_knn_rows(g, t, sst, s2, N, K);
-    if (t.active) deg = tile_in_edges_knn(g, t, N, K);
-  }
-  float y = 0.0f;
-  {
-    const float x2[7] = {s2.x, s2.y, s2.z, s2.w, c.goal_x, c.goal_y, (float)t.i};
-    tile_gat_conv(g, t, sw_tg, x2, deg, agg, adst);
+  // target network on s' -> y = r + gamma * max_a Q_target(s')  (train:120-121);
+  // online network on s, activations kept                        (train:119)
+  // sequential mode: pass 0 = target, pass 1 = online on the same threads; parallel mode: one pass, the role is the
+  // thread group's
+  const int npass = p.parallel ? 1 : 2;
+#pragma unroll 1
+  for (int pass = 0; pass < npass; ++pass) {
+    const bool target_role = p.parallel ? tgt_group : (pass == 0);
+    const float4 sp = target_role ? s2 : s;
+    const float* sw = target_role ? sw_tg : sw_on;
+    __syncthreads();                              // weights staged / previous pass done with sst and the h tile
+    sst[tid] = sp;
+    __syncthreads();
+    if (knn) {
+      tile_knn_rows(g, t, sst, sp, N, K);
+      if (t.active) deg = tile_in_edges_knn(g, t, N, K);
+    }
+    const float x[7] = {sp.x, sp.y, sp.z, sp.w, c.goal_x, c.goal_y, (float)t.i};
+    tile_gat_conv(g, t, sw, x, deg, agg, adst);   // alpha_e in g.swt, h rows in g.sh, alpha_src in g.sas
     if (t.active) {
-      float q2[9];
-      gat_head(agg, sw_tg, q2);
-      float qmax = q2[0];
+      float q[9];
+      dqn_head(agg, tU + tid * kHPad, tR + tid * kHPad, sw, r, q);
+      if (target_role) {
+        float qmax = q[0];
 #pragma unroll
-      for (int a = 1; a < 9; ++a) qmax = fmaxf(qmax, q2[a]);
-      y = __fadd_rn(rew, __fmul_rn(p.gamma, qmax));
+        for (int a = 1; a < 9; ++a) qmax = fmaxf(qmax, q[a]);
+        y = __fadd_rn(rew, __fmul_rn(p.gamma, qmax));
+        if (p.parallel) sds[tid] = y;             // handed to the online thread of the same node below
+      } else {
+        float v = q[0];
+#pragma unroll
+        for (int a = 1; a < 9; ++a) v = (act == a) ? q[a] : v;        // values = Q(s).gather(1, a)  (train:119)
+        delta = v;                                                    // minus y below
+        float4* xr = reinterpret_cast<float4*>(tX + tid * kXPad);
+        xr[0] = make_float4(x[0], x[1], x[2], x[3]);
+        xr[1] = make_float4(x[4], x[5], x[6], 0.f);
+      }
     }
   }
-  __syncthreads();
-
-  // ---------------- online network on s, activations kept ----------------------------------------
-  sst[tid] = s;
-  __syncthreads();
-  if (knn) {
-    tile_knn_rows(g, t, sst, s, N, K);
-    if (t.active) deg = tile_in_edges_knn(g, t, N, K);
+  if (p.parallel) {
+    __syncthreads();
+    if (t.active && !tgt_group) y = sds[tid + rows];
+    __syncthreads();                              // sds is reused for d alpha_src below
   }
-  const float x[7] = {s.x, s.y, s.z, s.w, c.goal_x, c.goal_y, (float)t.i};
-  tile_gat_conv(g, t, sw_on, x, deg, agg, adst);        // alpha_e in g.swt, h rows in g.sh, alpha_src in g.sas
-
-  float u[32], r[32], dvec[32];
-  float delta = 0.0f;
-#pragma unroll
-  for (int k = 0; k < 32; ++k) { u[k] = 0.f; r[k] = 0.f; dvec[k] = 0.f; }
-  float dq = 0.0f;
-  if (t.active) {
-#pragma unroll
-    for (int k = 0; k < 32; ++k) u[k] = agg[k];
-    float q[9];
-    gat_head_keep(u, r, sw_on, q);
-    float v = q[0];
-#pragma unroll
-    for (int a = 1; a < 9; ++a) v = (act == a) ? q[a] : v;        // values = Q(s).gather(1, a)  (train:119)
-    delta = __fsub_rn(v, y);
-    dq = 2.0f * delta * p.loss_scale;                               // d mean((v - y)^2) / dv
+  const bool learner = t.active && !tgt_group;    // threads that own a node of the online pass
+  if (learner) {
+    delta = __fsub_rn(delta, y);
+    dq = 2.0f * delta * p.loss_scale;             // d mean((v - y)^2) / dv
     if (p.td) p.td[t.gidx] = delta;
   } else {
-    // rows of inactive threads must be exact zeros: they take part in the tile GEMMs below
-    float4* hrow = reinterpret_cast<float4*>(g.sh + tid * kHPad);
-#pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) hrow[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+    delta = 0.0f;
   }
+  const float* sw = sw_on;
   sred[tid] = delta * delta;
 
-  // publish forward tiles
-  store_row32(tU, tid, u);
-  store_row32(tR, tid, r);
-  {
-    float4* xr = reinterpret_cast<float4*>(tX + tid * kXPad);
-    xr[0] = t.active ? make_float4(x[0], x[1], x[2], x[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    xr[1] = t.active ? make_float4(x[4], x[5], x[6], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float dvec[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) dvec[k] = 0.0f;
+  float dt_i = 0.0f;
+  if (learner) {
     float* dqr = tDQ + tid * kW2Pad;
 #pragma unroll
-    for (int a = 0; a < kW2Pad; ++a) dqr[a] = (t.active && a == act) ? dq : 0.0f;
-  }
+    for (int a = 0; a < kW2Pad; ++a) dqr[a] = (a == act) ? dq : 0.0f;
 
-  // ---------------- backward: lin2 -> ReLU -> lin1 -> tanh ------------------------------------------
-  // dr = W2[a,:]^T dq ; dp = dr * [r > 0]
-#pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    const float dr = sw_on[TW_W2T + k * kW2Pad + act] * dq;
-    dvec[k] = r[k] > 0.0f ? dr : 0.0f;
-  }
-  store_row32(tDP, tid, dvec);
-  // du[k] = sum_c W1[c][k] dp[c] ; do = du * (1 - u^2)
-  {
-    float dO[32];
-    const float4* w1 = reinterpret_cast<const float4*>(sw_on + TW_W1T);
+    // ---------------- backward: lin2 -> ReLU -> lin1 -> tanh ------------------------------------------
+    // dr = W2[a,:]^T dq ; dp = dr * [r > 0]
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
-      float acc = 0.0f;
-#pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 w = w1[k * 8 + c4];
-        acc = fmaf(w.x, dvec[4 * c4 + 0], acc);
-        acc = fmaf(w.y, dvec[4 * c4 + 1], acc);
-        acc = fmaf(w.z, dvec[4 * c4 + 2], acc);
-        acc = fmaf(w.w, dvec[4 * c4 + 3], acc);
-      }
-      dO[k] = acc * (1.0f - u[k] * u[k]);
+      const float dr = sw[TW_W2T + k * kW2Pad + act] * dq;
+      dvec[k] = r[k] > 0.0f ? dr : 0.0f;
     }
-    store_row32(tDO, tid, dO);
+    store_row32(tDP, tid, dvec);
+    // du[k] = sum_c W1[c][k] dp[c] ; do = du * (1 - u^2), four k per iteration through the own rows
+    {
+      const float4* w1 = reinterpret_cast<const float4*>(sw + TW_W1T);
+      const float4* u4 = reinterpret_cast<const float4*>(tU + tid * kHPad);
+      float4* do4 = reinterpret_cast<float4*>(tDO + tid * kHPad);
+#pragma unroll 1
+      for (int k4 = 0; k4 < 8; ++k4) {
+        const float4 uk = u4[k4];
+        float o[4];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) dvec[k] = dO[k];       // dvec = d(out_i) from here on
-  }
+        for (int kk = 0; kk < 4; ++kk) {
+          float acc = 0.0f;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 w = w1[(k4 * 4 + kk) * 8 + c4];
+            acc = fmaf(w.x, dvec[4 * c4 + 0], acc);
+            acc = fmaf(w.y, dvec[4 * c4 + 1], acc);
+            acc = fmaf(w.z, dvec[4 * c4 + 2], acc);
+            acc = fmaf(w.w, dvec[4 * c4 + 3], acc);
+          }
+          const float uu = f4c(uk, kk);
+          o[kk] = acc * (1.0f - uu * uu);
+        }
+        do4[k4] = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      load_row32(tDO, tid, dvec);                   // dvec = d(out_i) from here on
+    }
 
-  // ---------------- backward: aggregation + edge softmax + LeakyReLU ----------------------------------
-  // zero this node's rows of the per-env (target, source) matrices
-  if (t.active) {
+    // ---------------- backward: aggregation + edge softmax + LeakyReLU ----------------------------------
     float* ra = mA + (t.el * N + t.i) * N;
     float* rz = mZ + (t.el * N + t.i) * N;
     for (int j = 0; j < N; ++j) { ra[j] = 0.0f; rz[j] = 0.0f; }
-  }
-  float dt_i = 0.0f;
-  if (t.active) {
     // d alpha_e = <d out_i, h_j> ; softmax backward: d z_e = alpha_e (d alpha_e - sum_e' alpha_e' d alpha_e')
     float dot_sum = 0.0f;
     for (int e = 0; e < deg; ++e) {
@@ -270,8 +396,6 @@ __global__ void __launch_bounds__(kTileThreads) dqn_grad_kernel(const __grid_con
       swd[e * T + tid] = da;
       dot_sum = fmaf(g.swt[e * T + tid], da, dot_sum);
     }
-    float* ra = mA + (t.el * N + t.i) * N;
-    float* rz = mZ + (t.el * N + t.i) * N;
     for (int e = 0; e < deg; ++e) {
       const int j = g.sin[e * T + tid];
       const float alpha = g.swt[e * T + tid];
@@ -288,11 +412,11 @@ __global__ void __launch_bounds__(kTileThreads) dqn_grad_kernel(const __grid_con
 
   // gather in the source role:  d h_j = sum_i A[i][j] d out_i + ds_j att_src + dt_j att_dst
   {
-    float dh[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) dh[k] = 0.0f;
     float ds_j = 0.0f;
-    if (t.active) {
+    if (learner) {
+      float dh[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) dh[k] = 0.0f;
       for (int ii = 0; ii < N; ++ii) {
         const float a = mA[(t.el * N + ii) * N + t.i];
         ds_j += mZ[(t.el * N + ii) * N + t.i];
@@ -306,85 +430,61 @@ __global__ void __launch_bounds__(kTileThreads) dqn_grad_kernel(const __grid_con
           dh[4 * c4 + 3] = fmaf(a, dv.w, dh[4 * c4 + 3]);
         }
       }
-      const float* as = sw_on + TW_ATT_S;
-      const float* ad = sw_on + TW_ATT_D;
+      const float* as = sw + TW_ATT_S;
+      const float* ad = sw + TW_ATT_D;
 #pragma unroll
       for (int k = 0; k < 32; ++k) dh[k] = fmaf(ds_j, as[k], fmaf(dt_i, ad[k], dh[k]));
+      store_row32(tDH, tid, dh);
     }
-    store_row32(tDH, tid, dh);
     sds[tid] = ds_j;
   }
   __syncthreads();            // every tile complete
 
-  // ---------------- weight gradients: tile GEMMs over the 128 node rows -------------------------------
+  // ---------------- weight gradients: tile GEMMs over the CTA's node rows ------------------------------
   float* out = p.partials + (long long)blockIdx.x * kPartialStride;
   constexpr int G_W0 = 64, G_AS = 8, G_AD = 8, G_B0 = 8, G_W1 = 256, G_B1 = 8, G_W2 = 72, G_B2 = 3;
   constexpr int G_TOTAL = G_W0 + G_AS + G_AD + G_B0 + G_W1 + G_B1 + G_W2 + G_B2;
+#pragma unroll 1
   for (int grp = tid; grp < G_TOTAL; grp += T) {
     int gi = grp;
     if (gi < G_W0) {                                   // dW0[c][k] = sum_n DH[n][c] X[n][k]
       const int cc = gi >> 1, k4 = (gi & 1) * 4;
-      const float4 a = tile_gemm4(tDH, kHPad, cc, tX, kXPad, k4);
+      const float4 a = tile_gemm4(tDH, kHPad, cc, tX, kXPad, k4, rows);
       float* o = out + SWARM_W_CONV_LIN + cc * 7 + k4;
       o[0] = a.x; o[1] = a.y; o[2] = a.z;
       if (k4 == 0) o[3] = a.w;
       continue;
     }
     gi -= G_W0;
+    // the remaining groups all write four consecutive outputs of one packed tensor
+    const float* A = nullptr;
+    const float* Bm;
+    int lda = 0, ac = 0, ldb = kHPad, bc, oidx, nout = 4;
     if (gi < G_AS) {                                   // d att_src[c] = sum_n ds[n] H[n][c]
-      const float4 a = tile_gemm4(sds, 1, 0, g.sh, kHPad, gi * 4);
-      float* o = out + SWARM_W_ATT_SRC + gi * 4;
-      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
-      continue;
+      A = sds; lda = 1; Bm = g.sh; bc = gi * 4; oidx = SWARM_W_ATT_SRC + gi * 4;
+    } else if ((gi -= G_AS) < G_AD) {                  // d att_dst[c] = sum_n dt[n] H[n][c]
+      A = sdt; lda = 1; Bm = g.sh; bc = gi * 4; oidx = SWARM_W_ATT_DST + gi * 4;
+    } else if ((gi -= G_AD) < G_B0) {                  // d conv1.bias[c] = sum_n DO[n][c]
+      Bm = tDO; bc = gi * 4; oidx = SWARM_W_CONV_BIAS + gi * 4;
+    } else if ((gi -= G_B0) < G_W1) {                  // dW1[c][k] = sum_n DP[n][c] U[n][k]
+      A = tDP; lda = kHPad; ac = gi >> 3; Bm = tU; bc = (gi & 7) * 4; oidx = SWARM_W_LIN1 + ac * 32 + bc;
+    } else if ((gi -= G_W1) < G_B1) {                  // d lin1.bias[c] = sum_n DP[n][c]
+      Bm = tDP; bc = gi * 4; oidx = SWARM_W_LIN1_BIAS + gi * 4;
+    } else if ((gi -= G_B1) < G_W2) {                  // dW2[a][k] = sum_n DQ[n][a] R[n][k]
+      A = tDQ; lda = kW2Pad; ac = gi >> 3; Bm = tR; bc = (gi & 7) * 4; oidx = SWARM_W_LIN2 + ac * 32 + bc;
+    } else {                                           // d lin2.bias[a] = sum_n DQ[n][a]
+      gi -= G_W2;
+      Bm = tDQ; ldb = kW2Pad; bc = gi * 4; oidx = SWARM_W_LIN2_BIAS + gi * 4;
+      nout = gi < 2 ? 4 : 1;
     }
-    gi -= G_AS;
-    if (gi < G_AD) {                                   // d att_dst[c] = sum_n dt[n] H[n][c]
-      const float4 a = tile_gemm4(sdt, 1, 0, g.sh, kHPad, gi * 4);
-      float* o = out + SWARM_W_ATT_DST + gi * 4;
-      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
-      continue;
-    }
-    gi -= G_AD;
-    if (gi < G_B0) {                                   // d conv1.bias[c] = sum_n DO[n][c]
-      const float4 a = tile_gemm4(nullptr, 0, 0, tDO, kHPad, gi * 4);
-      float* o = out + SWARM_W_CONV_BIAS + gi * 4;
-      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
-      continue;
-    }
-    gi -= G_B0;
-    if (gi < G_W1) {                                   // dW1[c][k] = sum_n DP[n][c] U[n][k]
-      const int cc = gi >> 3, k4 = (gi & 7) * 4;
-      const float4 a = tile_gemm4(tDP, kHPad, cc, tU, kHPad, k4);
-      float* o = out + SWARM_W_LIN1 + cc * 32 + k4;
-      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
-      continue;
-    }
-    gi -= G_W1;
-    if (gi < G_B1) {                                   // d lin1.bias[c] = sum_n DP[n][c]
-      const float4 a = tile_gemm4(nullptr, 0, 0, tDP, kHPad, gi * 4);
-      float* o = out + SWARM_W_LIN1_BIAS + gi * 4;
-      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
-      continue;
-    }
-    gi -= G_B1;
-    if (gi < G_W2) {                                   // dW2[a][k] = sum_n DQ[n][a] R[n][k]
-      const int aa = gi >> 3, k4 = (gi & 7) * 4;
-      const float4 a = tile_gemm4(tDQ, kW2Pad, aa, tR, kHPad, k4);
-      float* o = out + SWARM_W_LIN2 + aa * 32 + k4;
-      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
-      continue;
-    }
-    gi -= G_W2;
-    {                                                  // d lin2.bias[a] = sum_n DQ[n][a]
-      const float4 a = tile_gemm4(nullptr, 0, 0, tDQ, kW2Pad, gi * 4);
-      float* o = out + SWARM_W_LIN2_BIAS + gi * 4;
-      o[0] = a.x;
-      if (gi < 2) { o[1] = a.y; o[2] = a.z; o[3] = a.w; }
-    }
+    const float4 a = tile_gemm4(A, lda, ac, Bm, ldb, bc, rows);
+    float* o = out + oidx;
+    o[0] = a.x;
+    if (nout == 4) { o[1] = a.y; o[2] = a.z; o[3] = a.w; }
   }
   if (tid == 0) {
     float sse = 0.0f;
-    for (int n = 0; n < T; ++n) sse += sred[n];
+    for (int n = 0; n < rows; ++n) sse += sred[n];
     out[SWARM_W_COUNT] = sse;
   }
 }
@@ -392,10 +492,16 @@ __global__ void __launch_bounds__(kTileThreads) dqn_grad_kernel(const __grid_con
 // grad[o] = sum over CTAs (in CTA order) of partials[cta][o]; loss = loss_scale * sum of squared TD errors
 __global__ void __launch_bounds__(256) dqn_reduce_kernel(const float* __restrict__ partials, int n_ctas, float loss_scale,
                                                          float* __restrict__ grad, float* __restrict__ loss,
-                                                         const SwarmTrainCtl* __restrict__ ctl) {
+                                                         SwarmTrainCtl* __restrict__ ctl, int pushed_envs,
+                                                         long long capacity, int n_graphs) {
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ctl) {
+    // device-driven tick: publish whether this tick updates (read by the clip + Adam kernel)
+    const bool upd = train_ring_size(ctl, pushed_envs, capacity) >= n_graphs;
+    if (o == 0) ctl->updating = upd ? 1 : 0;
+    if (!upd) return;
+  }
   if (o > SWARM_W_COUNT) return;
-  if (ctl && !ctl->updating) return;
   float acc = 0.0f;
   for (int b = 0; b < n_ctas; ++b) acc += partials[(long long)b * kPartialStride + o];
   if (o < SWARM_W_COUNT) grad[o] = acc;
@@ -427,22 +533,50 @@ struct AdamParams {
 };
 
 __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
-  __shared__ double ssq[8][256];
-  __shared__ float s_coef;
-  __shared__ float s_neg_step, s_bc2_sqrt;
+  __shared__ double swarp[8][8];            // [segment][warp] partial sums of squares
+  __shared__ float s_coef, s_neg_step, s_bc2_sqrt;
   __shared__ int s_update, s_sync;
-  const int tid = threadIdx.x;
-  if (p.ctl) {
-    if (tid == 0) {
-      const long long step = p.ctl->opt_step + 1;
-      const double bc1 = 1.0 - pow(p.beta1, (double)step);
-      const double bc2 = 1.0 - pow(p.beta2d, (double)step);
-      s_neg_step = (float)(-(p.lr / bc1));
-      s_bc2_sqrt = (float)sqrt(bc2);
-      s_update = p.ctl->updating;
-      s_sync = ((p.ctl->tick + 1) % p.update_target_every) == 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int seg_off[9] = {SWARM_W_CONV_LIN, SWARM_W_ATT_SRC, SWARM_W_ATT_DST, SWARM_W_CONV_BIAS, SWARM_W_LIN1,
+                          SWARM_W_LIN1_BIAS, SWARM_W_LIN2, SWARM_W_LIN2_BIAS, SWARM_W_COUNT};
+  if (p.ctl && tid == 255) {
+    // step-dependent scalars from the device cursor (overlaps with the norm sums of the other threads)
+    const long long step = p.ctl->opt_step + 1;
+    const double bc1 = 1.0 - pow(p.beta1, (double)step);
+    const double bc2 = 1.0 - pow(p.beta2d, (double)step);
+    s_neg_step = (float)(-(p.lr / bc1));
+    s_bc2_sqrt = (float)sqrt(bc2);
+    s_update = p.ctl->updating;
+    s_sync = ((p.ctl->tick + 1) % p.update_target_every) == 0;
+  }
+  // every thread owns the elements tid, tid + 256, ...: one round trip to memory for grad / m / v / w, everything
+  // else from registers
+  constexpr int kPer = (SWARM_W_COUNT + 255) / 256;
+  float g_[kPer], m_[kPer], v_[kPer], w_[kPer];
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    const int o = tid + 256 * i;
+    const bool in = o < SWARM_W_COUNT;
+    g_[i] = in ? p.grad[o] : 0.0f;
+    m_[i] = in ? p.m[o] : 0.0f;
+    v_[i] = in ? p.v[o] : 0.0f;
+    w_[i] = in ? p.w[o] : 0.0f;
+  }
+  // torch.nn.utils.clip_grad_norm_: norms = [||g_t||_2 for each parameter tensor]; total = ||norms||_2
+#pragma unroll
+  for (int sgi = 0; sgi < 8; ++sgi) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const int o = tid + 256 * i;
+      if (o >= seg_off[sgi] && o < seg_off[sgi + 1]) acc += (double)g_[i] * (double)g_[i];
     }
-    __syncthreads();
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+    if (lane == 0) swarp[sgi][warp] = acc;
+  }
+  __syncthreads();
+  if (p.ctl) {
     p.neg_step_size = s_neg_step;
     p.bc2_sqrt = s_bc2_sqrt;
     if (!s_sync) p.target = nullptr;
@@ -456,27 +590,12 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
       return;
     }
   }
-  const int seg_off[9] = {SWARM_W_CONV_LIN, SWARM_W_ATT_SRC, SWARM_W_ATT_DST, SWARM_W_CONV_BIAS, SWARM_W_LIN1,
-                          SWARM_W_LIN1_BIAS, SWARM_W_LIN2, SWARM_W_LIN2_BIAS, SWARM_W_COUNT};
-  // torch.nn.utils.clip_grad_norm_: norms = [||g_t||_2 for each parameter tensor]; total = ||norms||_2
-  for (int sgi = 0; sgi < 8; ++sgi) {
-    double acc = 0.0;
-    for (int o = seg_off[sgi] + tid; o < seg_off[sgi + 1]; o += 256) {
-      const double gval = (double)p.grad[o];
-      acc += gval * gval;
-    }
-    ssq[sgi][tid] = acc;
-  }
-  __syncthreads();
-  for (int stride = 128; stride > 0; stride >>= 1) {
-    if (tid < stride)
-      for (int sgi = 0; sgi < 8; ++sgi) ssq[sgi][tid] += ssq[sgi][tid + stride];
-    __syncthreads();
-  }
   if (tid == 0) {
     double tot = 0.0;
     for (int sgi = 0; sgi < 8; ++sgi) {
-      const float nrm = (float)sqrt(ssq[sgi][0]);
+      double ss = 0.0;
+      for (int w = 0; w < 8; ++w) ss += swarp[sgi][w];
+      const float nrm = (float)sqrt(ss);
       tot += (double)nrm * (double)nrm;
     }
     const float total_norm = (float)sqrt(tot);
@@ -490,17 +609,19 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
   }
   __syncthreads();
   const float coef = s_coef;
-  for (int o = tid; o < SWARM_W_COUNT; o += 256) {
-    const float gval = __fmul_rn(p.grad[o], coef);
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    const int o = tid + 256 * i;
+    if (o >= SWARM_W_COUNT) break;
+    const float gval = __fmul_rn(g_[i], coef);
     // exp_avg.lerp_(grad, 1 - beta1)
-    float m = p.m[o];
-    m = __fadd_rn(m, __fmul_rn(p.lerp_w, __fsub_rn(gval, m)));
+    const float m = __fadd_rn(m_[i], __fmul_rn(p.lerp_w, __fsub_rn(gval, m_[i])));
     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
-    float v = __fmul_rn(p.v[o], p.beta2);
+    float v = __fmul_rn(v_[i], p.beta2);
     v = __fadd_rn(v, __fmul_rn(__fmul_rn(p.one_minus_beta2, gval), gval));
     // denom = sqrt(v) / sqrt(bias_correction2) + eps ; param.addcdiv_(exp_avg, denom, value = -step_size)
     const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), p.bc2_sqrt), p.eps);
-    const float w = __fadd_rn(p.w[o], __fdiv_rn(__fmul_rn(p.neg_step_size, m), denom));
+    const float w = __fadd_rn(w_[i], __fdiv_rn(__fmul_rn(p.neg_step_size, m), denom));
     p.m[o] = m;
     p.v[o] = v;
     p.w[o] = w;
@@ -515,28 +636,22 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
   }
 }
 
-// ---- replay sampling on the device (GraphReplayBuffer.sample's index draw, train:38-39) ------------------------
-// indices[g] ~ U{0 .. size-1} with size = the ring fill AFTER this tick's push; counter RNG keyed by (seed, tick, g).
-__global__ void __launch_bounds__(256) train_sample_kernel(SwarmTrainCtl* ctl, int num_envs, long long capacity, int G,
-                                                           unsigned long long seed, int64_t* __restrict__ indices) {
-  long long size = ctl->ring_size + num_envs;
-  if (size > capacity) size = capacity;
-  const unsigned long long tick = (unsigned long long)(ctl->tick + 1);
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < G && size > 0) {
-    const uint64_t r = rng_draw(seed, (uint64_t)g, tick, 0x5A17u);
-    indices[g] = (int64_t)__umul64hi(r, (uint64_t)size);
-  }
-  if (g == 0) ctl->updating = (size >= G) ? 1 : 0;
-}
-
 // ---- launchers -------------------------------------------------------------------------------
 int dqn_maxdeg(const SwarmConfig& c) {
   return c.graph_mode == SWARM_GRAPH_KNN ? (c.n_agents + c.knn_k + 1) : c.n_agents;
 }
 
+// graphs per CTA: as many as fit (floor(128/N)) for big batches, fewer for small ones so that the update spreads over
+// the SMs (G = 32 -> one graph per CTA) and the tile GEMMs only walk the rows that exist
+int dqn_epb(const SwarmConfig& c, int n_graphs) {
+  const int full = kTileThreads / c.n_agents;
+  int epb = (n_graphs + 147) / 148;
+  if (epb < 1) epb = 1;
+  return epb < full ? epb : full;
+}
+
 long long dqn_workspace_bytes(const SwarmConfig& c, int n_graphs) {
-  const int epb = kTileThreads / c.n_agents;
+  const int epb = dqn_epb(c, n_graphs);
   const long long ctas = (n_graphs + epb - 1) / epb;
   return ctas * kPartialStride * 4 + 256;
 }
@@ -546,17 +661,15 @@ int dqn_smem_bytes(const SwarmConfig& c) {
   return dqn_layout(c.n_agents, c.knn_k, dqn_maxdeg(c), epb, c.graph_mode).total;
 }
 
-cudaError_t launch_train_sample(SwarmTrainCtl* ctl, int num_envs, long long capacity, int G, unsigned long long seed,
-                                int64_t* indices, cudaStream_t stream) {
-  train_sample_kernel<<<(G + 255) / 256, 256, 0, stream>>>(ctl, num_envs, capacity, G, seed, indices);
-  return cudaGetLastError();
-}
-
 cudaError_t launch_dqn_grad(const SwarmConfig& c, const float* w_online, const float* w_target, const SwarmReplay& batch,
                             const int64_t* indices, int n_graphs, float gamma, float loss_scale, float* grad, float* loss,
-                            float* td, void* workspace, cudaStream_t stream, const SwarmTrainCtl* ctl) {
+                            float* td, void* workspace, cudaStream_t stream, SwarmTrainCtl* ctl, int64_t* indices_out,
+                            unsigned long long sample_seed, int pushed_envs) {
   DqnParams p;
   p.ctl = ctl;
+  p.indices_out = indices_out;
+  p.sample_seed = sample_seed;
+  p.pushed_envs = pushed_envs;
   p.cfg = c;
   p.w_online = w_online;
   p.w_target = w_target;
@@ -567,14 +680,16 @@ cudaError_t launch_dqn_grad(const SwarmConfig& c, const float* w_online, const f
   p.loss_scale = loss_scale;
   p.partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
   p.td = td;
-  p.epb = kTileThreads / c.n_agents;
+  p.epb = dqn_epb(c, n_graphs);
+  p.parallel = (2 * p.epb * c.n_agents <= kTileThreads) ? 1 : 0;
   p.maxdeg = dqn_maxdeg(c);
-  const int smem = dqn_smem_bytes(c);
+  const int smem = dqn_layout(c.n_agents, c.knn_k, p.maxdeg, p.epb, c.graph_mode).total;
   cudaError_t err = cudaFuncSetAttribute(dqn_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (err != cudaSuccess) return err;
   const int ctas = (n_graphs + p.epb - 1) / p.epb;
   dqn_grad_kernel<<<ctas, kTileThreads, smem, stream>>>(p);
-  dqn_reduce_kernel<<<(SWARM_W_COUNT + 1 + 255) / 256, 256, 0, stream>>>(p.partials, ctas, loss_scale, grad, loss, ctl);
+  dqn_reduce_kernel<<<(SWARM_W_COUNT + 1 + 255) / 256, 256, 0, stream>>>(p.partials, ctas, loss_scale, grad, loss, ctl,
+                                                                         pushed_envs, batch.capacity, n_graphs);
   return cudaGetLastError();
 }
 

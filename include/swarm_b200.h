@@ -240,7 +240,8 @@ typedef struct SwarmTrainHyper {
 
 /* Phase 1: rollout tick of all cfg->num_envs envs with the online weights (pushes B transitions at ctl->ring_cursor),
  * draws graphs_per_update slot indices uniformly from the filled part of the ring (counter RNG keyed by
- * (sample_seed, tick, g)) into indices int64[G], then gradient + loss of the update batch as swarm_dqn_grad.
+ * (sample_seed, tick, g); exported to indices int64[G] when indices != NULL), then gradient + loss of the update
+ * batch as swarm_dqn_grad.
  * workspace: swarm_dqn_workspace_bytes(cfg, G).  If the ring holds fewer than G slots, grad / loss are left
  * untouched and ctl->updating = 0 (the reference prints "Not enough samples" and skips, train:113-115). */
 int swarm_train_tick_grad(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, SwarmTrainCtl* ctl,

@@ -90,6 +90,8 @@ def test_replay_push_gather_bitexact():
 
 @pytest.mark.parametrize("exp,scenario", [("GoTo", "go_to"), ("ObstacleAvoidance", "obstacle_avoidance")])
 @pytest.mark.parametrize("G,N,mode,k", [(32, 5, "complete", 0), (32, 12, "complete", 0), (100, 12, "knn", 5), (7, 9, "knn", 9),
+                                        (1900, 12, "complete", 0), (1000, 20, "knn", 6),    # sequential-pass tiles
+
                                         (300, 5, "complete", 0), (5, 32, "complete", 0)])
 def test_dqn_grad_parity(exp, scenario, G, N, mode, k):
     import swarm_b200 as sb
