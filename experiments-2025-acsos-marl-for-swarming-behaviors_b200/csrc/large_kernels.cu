@@ -169,17 +169,39 @@ __global__ void __launch_bounds__(kLargeThreads) knn_large_kernel(const __grid_c
   // std::partial_sort(b, b + k, e) = __heap_select + __sort_heap; the select loop is open-coded to skip the sqrt of
   // candidates whose squared distance already rules them out (q_j >= q_top  =>  d_j >= d_top  =>  !comp)
   knn_make_heap(row, 0, K);
-  for (int j = K; j < N; ++j) {
-    const float top = hv[threadIdx.x];
-    const float2 o = spos[j];
-    const float dx = __fsub_rn(o.x, row.sx), dy = __fsub_rn(o.y, row.sy);
-    const float q = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
-    if (q < __fmul_rn(top, top) * 1.0000005f + 1e-37f) {       // conservative: never skips a candidate with d_j < top
-      KnnPair cand;
-      cand.v = __fsqrt_rn(q);
-      cand.i = j;
-      KnnPair first = row.get(0);
-      if (knn_less(cand, first)) knn_adjust_heap(row, 0, 0, K, cand);     // __pop_heap(first, middle, j)
+  // The candidates K .. N-1 are visited in index order, kChunk at a time.  A branch-free sweep (packed subtract, one
+  // compare per candidate) marks those whose squared distance is below the heap top's at the START of the chunk --
+  // the top only ever decreases, so this is a superset of the candidates heap_select would accept -- and only the
+  // marked ones go through the (divergent, ~100-instruction) replace-top path, re-tested against the current top.
+  // A warp therefore pays for max-over-lanes(inserts per chunk) heap updates instead of one per candidate at which
+  // ANY of its 32 lanes inserts.  (Measured on C4: 16 per chunk 3.8 ms, 32: 2.9 ms, 64: 3.5 ms, unchunked: 5.7 ms.)
+  constexpr int kChunk = 32;
+  const float2 neg = make_float2(-row.sx, -row.sy);
+  for (int base = K; base < N; base += kChunk) {
+    const int cnt = (N - base < kChunk) ? (N - base) : kChunk;
+    const float top0 = hv[threadIdx.x];
+    const float thr0 = __fmul_rn(top0, top0) * 1.0000005f + 1e-37f;     // conservative: never drops a candidate with d_j < top
+    uint32_t m = 0;
+#pragma unroll 8
+    for (int u = 0; u < cnt; ++u) {
+      const float2 d = __fadd2_rn(spos[base + u], neg);
+      const float q = __fmaf_rn(d.y, d.y, __fmul_rn(d.x, d.x));
+      m |= (q < thr0) ? (1u << u) : 0u;
+    }
+    while (m) {
+      const int j = base + __ffs(m) - 1;
+      m &= m - 1;
+      const float2 o = spos[j];
+      const float dx = __fsub_rn(o.x, row.sx), dy = __fsub_rn(o.y, row.sy);
+      const float q = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+      const float top = hv[threadIdx.x];
+      if (q < __fmul_rn(top, top) * 1.0000005f + 1e-37f) {
+        KnnPair cand;
+        cand.v = __fsqrt_rn(q);
+        cand.i = j;
+        KnnPair first = row.get(0);
+        if (knn_less(cand, first)) knn_adjust_heap(row, 0, 0, K, cand);     // __pop_heap(first, middle, j)
+      }
     }
   }
   knn_sort_heap(row, 0, K);
