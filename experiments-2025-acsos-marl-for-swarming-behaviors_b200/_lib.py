@@ -59,7 +59,7 @@ class SwarmRolloutOptions(C.Structure):
 class SwarmTrainCtl(C.Structure):
     """Host mirror of the 48-byte device struct (only used to document / check the layout)."""
     _fields_ = [("tick", C.c_int64), ("ring_cursor", C.c_int64), ("ring_size", C.c_int64), ("opt_step", C.c_int64),
-                ("epsilon", C.c_float), ("updating", C.c_int32), ("reserved", C.c_int64)]
+                ("epsilon", C.c_float), ("updating", C.c_int32), ("episode", C.c_int64)]
 
 
 class SwarmTrainHyper(C.Structure):
@@ -67,6 +67,12 @@ class SwarmTrainHyper(C.Structure):
                 ("max_norm", C.c_double), ("rng_seed", C.c_uint64), ("sample_seed", C.c_uint64),
                 ("env_offset", C.c_int64), ("graphs_per_update", C.c_int32), ("update_target_every", C.c_int32),
                 ("gamma", C.c_float), ("loss_scale", C.c_float)]
+
+
+class SwarmResetSpec(C.Structure):
+    _fields_ = [("base_x", C.c_float), ("base_y", C.c_float), ("mean_x", C.c_float), ("mean_y", C.c_float),
+                ("std_x", C.c_float), ("std_y", C.c_float), ("seed", C.c_uint64), ("env_offset", C.c_int64),
+                ("shared_center", C.c_int32), ("pad", C.c_int32)]
 
 
 class SwarmError(RuntimeError):
@@ -103,6 +109,10 @@ _SIGNATURES = {
                                        C.c_void_p]),
     "swarm_train_tick_grad": (C.c_int, [C.POINTER(SwarmConfig), C.POINTER(SwarmTrainHyper)] + [C.c_void_p] * 6
                               + [C.POINTER(SwarmReplay)] + [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]),
+    "swarm_reset_random": (C.c_int, [C.POINTER(SwarmConfig), C.POINTER(SwarmResetSpec), C.c_void_p, C.c_int64,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "swarm_episode_end": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 5 + [C.c_int64, C.c_double, C.c_double,
+                                                                                 C.c_double, C.c_void_p]),
     "swarm_train_tick_apply": (C.c_int, [C.POINTER(SwarmConfig), C.POINTER(SwarmTrainHyper)] + [C.c_void_p] * 6
                                + [C.c_int64, C.c_void_p]),
 }

@@ -15,6 +15,11 @@ cudaError_t launch_graph_large(const SwarmConfig& c, const float* state, int32_t
                                cudaStream_t stream);
 cudaError_t launch_reset_grid(const SwarmConfig& c, int cols, int rows, const float* centers, float* state,
                               cudaStream_t stream);
+cudaError_t launch_reset_random(const SwarmConfig& c, const SwarmResetSpec& sp, int cols, int rows, const SwarmTrainCtl* ctl,
+                                long long episode, float* centers_out, float* state, cudaStream_t stream);
+cudaError_t launch_episode_end(const SwarmConfig& c, SwarmTrainCtl* ctl, float* returns, int32_t* hits, const float* loss,
+                               float* stats, long long max_episodes, double eps0, double decay, double min_eps,
+                               cudaStream_t stream);
 long long csr_workspace_bytes(int n, long long E);
 cudaError_t launch_csr_from_edges(int n, long long E, const int64_t* edge_src, const int64_t* edge_dst, int32_t* row_ptr,
                                   int32_t* src, int32_t* perm, void* workspace, long long workspace_bytes,
@@ -407,6 +412,30 @@ int swarm_train_tick_apply(const SwarmConfig* cfg, const SwarmTrainHyper* hyper,
                                      hyper->eps, hyper->max_norm, target_weights, nullptr, (cudaStream_t)stream, ctl,
                                      cfg->num_envs, ring_capacity, hyper->update_target_every),
                     "swarm_train_tick_apply");
+}
+
+int swarm_reset_random(const SwarmConfig* cfg, const SwarmResetSpec* spec, const SwarmTrainCtl* ctl, int64_t episode,
+                       float* centers_out, float* state, void* stream) {
+  if (int rc = validate(cfg, false, true)) return rc;
+  if (!spec || !state) return fail(SWARM_ERR_INVALID_ARG, "spec/state is NULL");
+  if (!(spec->std_x >= 0.0f) || !(spec->std_y >= 0.0f)) return fail(SWARM_ERR_INVALID_ARG, "std must be >= 0");
+  if (!ctl && episode < 0) return fail(SWARM_ERR_INVALID_ARG, "episode must be >= 0");
+  const int n = cfg->n_agents;
+  const int cols = (int)std::ceil(std::sqrt((double)n));
+  const int rows = (int)std::ceil((double)n / (double)cols);
+  return check_cuda(launch_reset_random(*cfg, *spec, cols, rows, ctl, episode, centers_out, state, (cudaStream_t)stream),
+                    "swarm_reset_random");
+}
+
+int swarm_episode_end(const SwarmConfig* cfg, SwarmTrainCtl* ctl, float* returns, int32_t* hits, const float* loss,
+                      float* stats, int64_t max_episodes, double epsilon0, double epsilon_decay, double min_epsilon,
+                      void* stream) {
+  if (int rc = validate(cfg, false, true)) return rc;
+  if (!ctl || !returns) return fail(SWARM_ERR_INVALID_ARG, "ctl/returns is NULL");
+  if (stats && max_episodes <= 0) return fail(SWARM_ERR_INVALID_ARG, "max_episodes must be positive when stats is given");
+  return check_cuda(launch_episode_end(*cfg, ctl, returns, hits, loss, stats, max_episodes, epsilon0, epsilon_decay,
+                                       min_epsilon, (cudaStream_t)stream),
+                    "swarm_episode_end");
 }
 
 }  // extern "C"

@@ -57,12 +57,13 @@ __device__ __forceinline__ bool contact_force(float ax, float ay, float bx, floa
 
 // ---- agent-agent contacts of one agent against the N agents of its env ---------------------------------
 // `partners` = positions of the env's agents (float2 or float4 elements, .x/.y used), `self` = own index.
-// Phase 1 is a branch-free sweep that only COUNTS the partners whose squared distance passes the exact pre-filter
-// q <= qmax (qmax = largest float whose rounded sqrt is <= r_a + r_b, see api.cu).  The agent itself is among the
-// partners (q = 0), so a count of one means "no contact" -- the common case -- and nothing else runs.  The
-// difference is formed as partner - self with one packed add (sm_100 FADD2) against the negated own position:
-// b - a = -(a - b) exactly under round-to-nearest, and only squares of the components are used.
-// Phase 2 -- rare -- walks the partners in ascending order and adds the contact forces in vmas' accumulation order.
+// Phase 1 is a branch-free sweep that records, 32 partners at a time, which squared distances pass the exact
+// pre-filter q <= qmax (qmax = largest float whose rounded sqrt is <= r_a + r_b, see api.cu).  The difference is
+// formed as partner - self with one packed add (sm_100 FADD2) against the negated own position: b - a = -(a - b)
+// exactly under round-to-nearest, and only squares of the components are used.  Four partners share one shift: their
+// hits are collected in a nibble of immediates first.  Phase 2 walks the set bits in ascending partner order and
+// adds the contact forces in vmas' accumulation order; late in an episode, when the swarm has gathered at the goal,
+// almost every warp has some lane in phase 2, so it has to stay proportional to the number of contacts.
 __device__ __forceinline__ float2 xy_of(const float2& v) { return v; }
 __device__ __forceinline__ float2 xy_of(const float4& v) { return *reinterpret_cast<const float2*>(&v); }
 
@@ -71,26 +72,29 @@ __device__ __forceinline__ void agent_contacts(const P* __restrict__ partners, i
                                                float qmax, float dist_min, float collision_force, float k, float& fx,
                                                float& fy, uint32_t& cmask) {
   const float2 neg = make_float2(-sx, -sy);
-  for (int base = 0; base < N; base += 32) {          // chunks of 32 keep phase 2 short for swarms of 1 000+ agents
+  auto hit = [&](int j) -> bool {
+    const float2 d = __fadd2_rn(xy_of(partners[j]), neg);
+    return __fmaf_rn(d.y, d.y, __fmul_rn(d.x, d.x)) <= qmax;
+  };
+  for (int base = 0; base < N; base += 32) {
     const int end = (N - base < 32) ? N : base + 32;
-    int cnt = 0;
-#pragma unroll 4
-    for (int j = base; j < end; ++j) {
-      const float2 d = __fadd2_rn(xy_of(partners[j]), neg);
-      const float q = __fmaf_rn(d.y, d.y, __fmul_rn(d.x, d.x));
-      cnt += (q <= qmax) ? 1 : 0;
+    uint32_t m = 0;
+    int j = base;
+    for (; j + 4 <= end; j += 4) {
+      const uint32_t nib = (hit(j) ? 1u : 0u) | (hit(j + 1) ? 2u : 0u) | (hit(j + 2) ? 4u : 0u) | (hit(j + 3) ? 8u : 0u);
+      m |= nib << (j - base);
     }
-    if (cnt <= (((unsigned)(self - base) < 32u) ? 1 : 0)) continue;
-    for (int j = base; j < end; ++j) {
-      if (j == self) continue;
-      const float2 o = xy_of(partners[j]);
-      const float dx = __fsub_rn(sx, o.x), dy = __fsub_rn(sy, o.y);
-      if (!(__fmaf_rn(dy, dy, __fmul_rn(dx, dx)) <= qmax)) continue;
+    for (; j < end; ++j) m |= (hit(j) ? 1u : 0u) << (j - base);
+    if ((unsigned)(self - base) < 32u) m &= ~(1u << (self - base));
+    while (m) {
+      const int jj = __ffs(m) - 1;
+      m &= m - 1;
+      const float2 o = xy_of(partners[base + jj]);
       float gx, gy;
       if (contact_force(sx, sy, o.x, o.y, dist_min, collision_force, k, gx, gy)) {
         fx = __fadd_rn(fx, gx);
         fy = __fadd_rn(fy, gy);
-        if (j < 32) cmask |= (1u << j);
+        if (base + jj < 32) cmask |= (1u << (base + jj));
       }
     }
   }

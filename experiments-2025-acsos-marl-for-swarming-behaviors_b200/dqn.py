@@ -8,7 +8,9 @@ Two drivers:
   * ``DQNTrainer.train_model(config)``  -- the reference loop for ``num_envs = 1`` with the reference's Python
     ``random`` stream for exploration and sampling; reproduces the shipped ``data/stats/*.csv`` rows.
   * ``DQNTrainer.train_model_batched(config)`` -- B envs per tick with the device RNG, fused
-    rollout-tick + replay push, G graphs per update (throughput mode).
+    rollout-tick + replay push, G graphs per update (throughput mode); an episode's ticks replay from a CUDA graph.
+  * ``DQNTrainer.train_model_device(config)`` -- as above with reset, epsilon schedule and episode statistics on
+    the device too: one graph launch per episode, no host synchronisation until the run ends.
 """
 from __future__ import annotations
 
@@ -293,6 +295,69 @@ class DQNTrainer:
         self._loss.copy_(tt.loss)
         self.sync_modules()
         return stats
+
+    def train_model_device(self, config) -> torch.Tensor:
+        """Whole training run on the device: every episode is ONE replay of a CUDA graph holding
+        [swarm_reset_random -> max_steps x (swarm_train_tick_grad, gradient all-reduce, swarm_train_tick_apply) ->
+        swarm_episode_end]; start centres, exploration, replay sampling, the epsilon schedule and the per-episode
+        statistics (train:179-199) all live on the device and the host only reads the statistics at the end.
+        Per-env start centres come from the counter RNG (``shared_center`` reproduces the reference's one draw per
+        reset).  Returns stats f32[episodes, 4] = (mean agent-0 return / N, hits per env, last loss, epsilon)."""
+        env, world = self.env, self.env.world
+        B, n, dev = env.num_envs, env.n_agents, env.device
+        G = int(config.get("graphs_per_update", 32))
+        episodes = int(config["episodes"])
+        ring = self.replay_buffer.ring
+        cfg = ops.clone_config(self.graph_cfg, num_envs=B)
+        rank = torch.distributed.get_rank() if parallel.world_size() > 1 else 0
+        multi = parallel.world_size() > 1
+        tt = ops.TrainTick(cfg, ring, graphs_per_update=G, update_target_every=int(config.get("update_target_every", 200)),
+                           gamma=float(config.get("gamma", 0.99)), loss_scale=parallel.global_loss_scale(G, n),
+                           lr=self.lr, betas=self.betas, eps=self.eps, max_norm=self.max_norm, rng_seed=self.seed,
+                           sample_seed=int(config.get("sample_seed", self.seed)) + 7919 * rank,
+                           env_offset=int(config.get("env_offset", rank * B)))
+        spec = ops.reset_spec(cfg.scenario, random=bool(getattr(env.scenario, "random", True)),
+                              seed=int(config.get("reset_seed", self.seed)), env_offset=tt.hyper.env_offset,
+                              shared_center=bool(config.get("shared_center", False)))
+        parallel.broadcast_weights(self.w)
+        self.w_target.copy_(self.w)
+        tt.load_cursor(int(config.get("start_tick", 0)), self.opt_step, config["epsilon"], 0)
+        returns = torch.zeros(B, n, dtype=torch.float32, device=dev)
+        hits = torch.zeros(B, dtype=torch.int32, device=dev)
+        stats = torch.zeros(episodes, 4, dtype=torch.float32, device=dev)
+
+        def episode():
+            ops.reset_random(cfg, spec, world.state, ctl=tt.ctl)
+            for _ in range(env.max_steps):
+                tt.grad_phase(self.w, self.w_target, world.state, returns, hits)
+                if multi:
+                    torch.distributed.all_reduce(tt.grad_loss)
+                tt.apply_phase(self.w, self.w_target, self.exp_avg, self.exp_avg_sq)
+            tt.episode_end(returns, hits, stats, config["epsilon"], config["epsilon_decay"], config["min_epsilon"])
+
+        done = 0
+        if bool(config.get("cuda_graph", True)) and episodes > 1:
+            episode()                                   # eager once: kernel attributes set, NCCL communicator warm
+            done = 1
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.graph(graph, stream=side):
+                episode()
+            for _ in range(episodes - 1):            # capture records, it does not execute
+                graph.replay()
+            done = episodes
+        for _ in range(episodes - done):
+            episode()
+        cur = tt.read_cursor()
+        self.opt_step = cur["opt_step"]
+        self._grad.copy_(tt.grad)
+        self._loss.copy_(tt.loss)
+        self.sync_modules()
+        out = stats.cpu()
+        self.episode_losses.extend(out[:, 2].tolist())
+        return out
 
     def evaluate_policy(self, eval_episodes):
         """train:206-223 (greedy episodes, mean agent-0 return)."""

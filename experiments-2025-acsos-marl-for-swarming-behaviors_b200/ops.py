@@ -249,13 +249,41 @@ def adam_clip_step(weights: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Ten
                                      ptr(grad_norm), stream_ptr(weights.device)))
 
 
+def reset_spec(scenario: int, random: bool = True, seed: int = 0, env_offset: int = 0,
+               shared_center: bool = False) -> _lib.SwarmResetSpec:
+    """Start-centre distribution of the scenario's reset_world_at (go_to:84-88, oa:100-102)."""
+    sp = _lib.SwarmResetSpec()
+    if scenario == _lib.SCENARIO_GOTO:
+        sp.base_x, sp.base_y, sp.mean_x, sp.mean_y, sp.std_x, sp.std_y = 1.5, -1.5, -0.6, 0.6, 0.4, 0.4
+    else:
+        sp.base_x, sp.base_y, sp.mean_x, sp.mean_y = 0.6, -0.6, 0.0, 0.0
+        sp.std_x = sp.std_y = 0.1 if random else 0.0
+    sp.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    sp.env_offset = int(env_offset)
+    sp.shared_center = 1 if shared_center else 0
+    return sp
+
+
+def reset_random(cfg: SwarmConfig, spec: _lib.SwarmResetSpec, state: torch.Tensor, *, ctl: Optional[torch.Tensor] = None,
+                 episode: int = 0, centers_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Device-side reset_world_at for every env: start centres from the counter RNG (episode number from the device
+    cursor ``ctl`` when given), agents on the grid, velocities zero."""
+    B, N = cfg.num_envs, cfg.n_agents
+    _expect(state, torch.float32, B * N * 4, "state")
+    if centers_out is not None:
+        _expect(centers_out, torch.float32, B * 2, "centers_out")
+    check(lib().swarm_reset_random(C.byref(cfg), C.byref(spec), ptr(ctl), int(episode), ptr(centers_out), ptr(state),
+                                   stream_ptr(state.device)))
+    return state
+
+
 class TrainTick:
     """Device-driven train tick (swarm_train_tick_grad / swarm_train_tick_apply): one iteration of the loop body of
     train_gcn_dqn.py:153-178 for all B envs, with the tick number, replay cursor / fill, optimiser step and epsilon
     held in a 48-byte device struct that the kernels advance themselves.  No launch argument changes from tick to
     tick, so ``grad_phase`` / ``apply_phase`` can be captured in a CUDA graph and replayed (``DQNTrainer``)."""
 
-    CTL_WORDS = 6      # int64 words: tick, ring_cursor, ring_size, opt_step, (epsilon f32 | updating i32), reserved
+    CTL_WORDS = 6      # int64 words: tick, ring_cursor, ring_size, opt_step, (epsilon f32 | updating i32), episode
 
     def __init__(self, cfg: SwarmConfig, ring: ReplayRing, *, graphs_per_update: int = 32, update_target_every: int = 200,
                  gamma: float = 0.99, loss_scale: Optional[float] = None, lr: float = 1e-3, betas=(0.9, 0.999),
@@ -285,9 +313,10 @@ class TrainTick:
         self._rstruct = ring.struct()
 
     # -- cursor <-> host bookkeeping ---------------------------------------------------------------
-    def load_cursor(self, tick: int, opt_step: int, epsilon: float) -> None:
+    def load_cursor(self, tick: int, opt_step: int, epsilon: float, episode: int = 0) -> None:
         """Write the host-side counters (tick, ring position / size, optimiser step, epsilon) into the device cursor."""
-        words = torch.tensor([int(tick), self.ring.position, self.ring.size, int(opt_step), 0, 0], dtype=torch.int64)
+        words = torch.tensor([int(tick), self.ring.position, self.ring.size, int(opt_step), 0, int(episode)],
+                             dtype=torch.int64)
         words.view(torch.float32)[8] = float(epsilon)
         self.ctl.copy_(words)
 
@@ -299,7 +328,16 @@ class TrainTick:
         words = self.ctl.cpu()
         self.ring.position, self.ring.size = int(words[1]), int(words[2])
         return {"tick": int(words[0]), "opt_step": int(words[3]), "epsilon": float(words.view(torch.float32)[8]),
-                "updating": int(words.view(torch.int32)[9])}
+                "updating": int(words.view(torch.int32)[9]), "episode": int(words[5])}
+
+    def episode_end(self, returns: torch.Tensor, hits: Optional[torch.Tensor], stats: Optional[torch.Tensor],
+                    epsilon0: float, epsilon_decay: float, min_epsilon: float) -> None:
+        """End-of-episode bookkeeping on the device (swarm_episode_end): stats row, accumulators zeroed, epsilon
+        schedule (train:179-199), episode counter."""
+        max_ep = 0 if stats is None else stats.shape[0]
+        check(lib().swarm_episode_end(C.byref(self.cfg), ptr(self.ctl), ptr(returns), ptr(hits), ptr(self.loss), ptr(stats),
+                                      max_ep, float(epsilon0), float(epsilon_decay), float(min_epsilon),
+                                      stream_ptr(returns.device)))
 
     # -- the two phases -------------------------------------------------------------------------------
     def grad_phase(self, weights: torch.Tensor, target: torch.Tensor, state: torch.Tensor, returns: torch.Tensor,

@@ -224,7 +224,7 @@ typedef struct SwarmTrainCtl {   /* device memory, 48 bytes, zero-initialised by
   int64_t opt_step;      /* optimiser steps done                                                                    */
   float epsilon;         /* exploration rate of the running episode (the host rewrites it between episodes)         */
   int32_t updating;      /* set by swarm_train_tick_grad: 1 if the ring holds >= graphs_per_update slots (train:113) */
-  int64_t reserved;
+  int64_t episode;       /* episodes completed (advanced by swarm_episode_end)                                      */
 } SwarmTrainCtl;
 
 typedef struct SwarmTrainHyper {
@@ -255,6 +255,33 @@ int swarm_train_tick_grad(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, 
 int swarm_train_tick_apply(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, SwarmTrainCtl* ctl, float* weights,
                            float* target_weights, float* exp_avg, float* exp_avg_sq, const float* grad,
                            int64_t ring_capacity, void* stream);
+
+/* ---- device-side episode boundary -------------------------------------------------------
+ * The reference resets with one CPU torch.normal draw per episode (go_to:84-88, oa:100-102) and does its episode
+ * bookkeeping in Python (train:179-199).  These two calls keep both on the device so that reset + max_steps ticks +
+ * bookkeeping form one replayable CUDA graph and a whole training run needs no host synchronisation. */
+typedef struct SwarmResetSpec {
+  float base_x, base_y;      /* GoTo (1.5, -1.5) = -position_range (go_to:84); OA (0.6, -0.6) (oa:100)                 */
+  float mean_x, mean_y;      /* GoTo (-0.6, 0.6); OA (0, 0)                                                            */
+  float std_x, std_y;        /* GoTo 0.4; OA 0.1 with random=True, else 0                                              */
+  uint64_t seed;             /* counter RNG keyed by (seed, global env index, episode): a documented deviation from    */
+  int64_t env_offset;        /* torch's CPU mt19937 stream; parity tests pass explicit centres to swarm_reset_grid     */
+  int32_t shared_center;     /* 1: every env gets env 0's draw (the reference's `env_index=None` behaviour)            */
+  int32_t pad;
+} SwarmResetSpec;
+
+/* centres c_b = base + mean + std * N(0,1) drawn for episode `ctl->episode` (or `episode` when ctl == NULL), agents on
+ * the start grid around them, velocities zero.  centers_out (optional) float[B][2] receives the drawn centres. */
+int swarm_reset_random(const SwarmConfig* cfg, const SwarmResetSpec* spec, const SwarmTrainCtl* ctl, int64_t episode,
+                       float* centers_out, float* state, void* stream);
+
+/* End-of-episode bookkeeping (train:179-199): row ctl->episode of stats float[max_episodes][4] receives
+ * (mean over envs of agent 0's return / N, mean obstacle hits per env, the last update's loss, the epsilon used);
+ * returns / hits are zeroed for the next episode; epsilon <- max(min_epsilon, epsilon0 * exp(-decay * episode))
+ * (train:180); ctl->episode += 1.  Rows beyond max_episodes are dropped. */
+int swarm_episode_end(const SwarmConfig* cfg, SwarmTrainCtl* ctl, float* returns, int32_t* hits, const float* loss,
+                      float* stats, int64_t max_episodes, double epsilon0, double epsilon_decay, double min_epsilon,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -274,3 +274,63 @@ def test_train_model_batched_graph_equals_eager():
     assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
     assert out[0][2] == out[1][2]
     assert not torch.equal(out[0][0], out[0][1]) or True
+
+
+def test_reset_random_statistics_and_determinism():
+    """Device-side reset: centres follow base + N(mean, std^2) per env and episode, are reproducible, differ between
+    episodes / envs, and the agents sit on the exact start grid around them (bit-equal to swarm_reset_grid)."""
+    import swarm_b200 as sb
+    from swarm_b200 import ops
+    dev = _dev()
+    B, N = 20000, 7
+    for scen, mean, std in ((sb._lib.SCENARIO_GOTO, (0.9, -0.9), 0.4), (sb._lib.SCENARIO_OBSTACLE_AVOIDANCE, (0.6, -0.6), 0.1)):
+        cfg = ops.make_config(scen, B, N)
+        spec = ops.reset_spec(scen, random=True, seed=5, env_offset=100)
+        state = torch.empty(B, N, 4, device=dev)
+        c0 = torch.empty(B, 2, device=dev)
+        ops.reset_random(cfg, spec, state, episode=3, centers_out=c0)
+        assert torch.equal(state, ops.reset_grid(cfg, c0))
+        m, s = c0.mean(0).cpu(), c0.std(0).cpu()
+        assert abs(m[0] - mean[0]) < 4 * std / B ** 0.5 + 1e-3 and abs(m[1] - mean[1]) < 4 * std / B ** 0.5 + 1e-3
+        assert abs(s[0] - std) < 0.03 * std and abs(s[1] - std) < 0.03 * std
+        assert abs(torch.corrcoef(c0.T.cpu())[0, 1]) < 0.03
+        c1 = torch.empty(B, 2, device=dev)
+        ops.reset_random(cfg, spec, state, episode=3, centers_out=c1)
+        assert torch.equal(c0, c1)
+        ops.reset_random(cfg, spec, state, episode=4, centers_out=c1)
+        assert not torch.equal(c0, c1)
+        # env shards: the draw depends on the global env index only
+        half = ops.make_config(scen, B // 2, N)
+        spec2 = ops.reset_spec(scen, random=True, seed=5, env_offset=100 + B // 2)
+        c2 = torch.empty(B // 2, 2, device=dev)
+        ops.reset_random(half, spec2, state[:B // 2].contiguous(), episode=3, centers_out=c2)
+        assert torch.equal(c2, c0[B // 2:])
+        shared = ops.reset_spec(scen, random=True, seed=5, shared_center=True)
+        ops.reset_random(cfg, shared, state, episode=0, centers_out=c1)
+        assert (c1 == c1[0]).all()
+    fixed = ops.reset_spec(sb._lib.SCENARIO_OBSTACLE_AVOIDANCE, random=False)
+    ops.reset_random(cfg, fixed, state, episode=9, centers_out=c1)
+    assert (c1.cpu() == torch.tensor([0.6, -0.6])).all()
+
+
+def test_train_model_device_graph_equals_eager_and_host_loop():
+    """Whole-run-on-device training: graph replays == eager launches (bit-exact weights and statistics), and the
+    statistics rows equal a host-side recomputation (returns mean, epsilon schedule of train:180)."""
+    import swarm_b200 as sb
+    cfgd = {"episodes": 5, "epsilon": 0.9, "epsilon_decay": 0.3, "min_epsilon": 0.05, "graphs_per_update": 64,
+            "update_target_every": 7}
+    out = []
+    for use_graph in (False, True):
+        random.seed(0); torch.manual_seed(0)
+        env = sb.make_env(sb.ObstacleAvoidanceScenario(), num_envs=256, device="cuda", continuous_actions=False,
+                          max_steps=10, dict_spaces=True, seed=0, n_agents=12, random=True)
+        tr = sb.DQNTrainer(env, 0, "/tmp/none", "/tmp/none", "t", replay_capacity=2048)
+        stats = tr.train_model_device(dict(cfgd, cuda_graph=use_graph))
+        torch.cuda.synchronize()
+        out.append((tr.w.clone(), tr.w_target.clone(), stats, tr.opt_step))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
+    assert out[0][3] == 50
+    stats = out[0][2]
+    eps = [0.9] + [max(0.05, 0.9 * float(np.exp(-0.3 * e))) for e in range(4)]
+    assert np.allclose(stats[:, 3].numpy(), np.array(eps, dtype=np.float32), rtol=1e-6)
+    assert (stats[:, 0] < 0).all() and (stats[:, 2] > 0).all() and (stats[:, 1] >= 0).all()
