@@ -50,20 +50,38 @@ __device__ __forceinline__ float gat_logit(float asrc_j, float adst_i) {
 // `alpha * x_j` followed by scatter-add); FUSED = true: one FFMA per channel (half the instructions, one rounding).
 template <bool FUSED = false>
 __device__ __forceinline__ void gat_accumulate(float (&out)[32], float alpha, const float4* __restrict__ hj) {
+  if (FUSED) {
+    // packed FFMA2 (sm_100): two channels per issue slot
+    const float2 a2 = make_float2(alpha, alpha);
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const float4 v = hj[c4];
+      const float2 lo = __ffma2_rn(a2, make_float2(v.x, v.y), make_float2(out[4 * c4 + 0], out[4 * c4 + 1]));
+      const float2 hi = __ffma2_rn(a2, make_float2(v.z, v.w), make_float2(out[4 * c4 + 2], out[4 * c4 + 3]));
+      out[4 * c4 + 0] = lo.x; out[4 * c4 + 1] = lo.y;
+      out[4 * c4 + 2] = hi.x; out[4 * c4 + 3] = hi.y;
+    }
+    return;
+  }
 #pragma unroll
   for (int c4 = 0; c4 < 8; ++c4) {
     const float4 v = hj[c4];
-    if (FUSED) {
-      out[4 * c4 + 0] = fmaf(alpha, v.x, out[4 * c4 + 0]);
-      out[4 * c4 + 1] = fmaf(alpha, v.y, out[4 * c4 + 1]);
-      out[4 * c4 + 2] = fmaf(alpha, v.z, out[4 * c4 + 2]);
-      out[4 * c4 + 3] = fmaf(alpha, v.w, out[4 * c4 + 3]);
-    } else {
-      out[4 * c4 + 0] = __fadd_rn(out[4 * c4 + 0], __fmul_rn(alpha, v.x));
-      out[4 * c4 + 1] = __fadd_rn(out[4 * c4 + 1], __fmul_rn(alpha, v.y));
-      out[4 * c4 + 2] = __fadd_rn(out[4 * c4 + 2], __fmul_rn(alpha, v.z));
-      out[4 * c4 + 3] = __fadd_rn(out[4 * c4 + 3], __fmul_rn(alpha, v.w));
-    }
+    out[4 * c4 + 0] = __fadd_rn(out[4 * c4 + 0], __fmul_rn(alpha, v.x));
+    out[4 * c4 + 1] = __fadd_rn(out[4 * c4 + 1], __fmul_rn(alpha, v.y));
+    out[4 * c4 + 2] = __fadd_rn(out[4 * c4 + 2], __fmul_rn(alpha, v.z));
+    out[4 * c4 + 3] = __fadd_rn(out[4 * c4 + 3], __fmul_rn(alpha, v.w));
+  }
+}
+
+// out += w * row, the row already in registers (packed FFMA2)
+__device__ __forceinline__ void gat_accumulate_regs(float (&out)[32], float w, const float4 (&v)[8]) {
+  const float2 a2 = make_float2(w, w);
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4) {
+    const float2 lo = __ffma2_rn(a2, make_float2(v[c4].x, v[c4].y), make_float2(out[4 * c4 + 0], out[4 * c4 + 1]));
+    const float2 hi = __ffma2_rn(a2, make_float2(v[c4].z, v[c4].w), make_float2(out[4 * c4 + 2], out[4 * c4 + 3]));
+    out[4 * c4 + 0] = lo.x; out[4 * c4 + 1] = lo.y;
+    out[4 * c4 + 2] = hi.x; out[4 * c4 + 3] = hi.y;
   }
 }
 

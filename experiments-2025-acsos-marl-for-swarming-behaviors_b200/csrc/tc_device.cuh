@@ -37,10 +37,11 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+// hi = x rounded to nearest TF32 (ties away from zero, like cvt.rna.tf32.f32), lo = x - hi (exact).  The rounding is
+// done on the bit pattern -- add half a TF32 ulp, clear the 13 low mantissa bits -- in two integer instructions;
+// cvt.rna.tf32.f32 itself compiles to four (it also screens Inf / NaN, which adding 0x1000 maps to themselves anyway).
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));     // round to nearest TF32 (low 13 mantissa bits zero)
-  hi = __uint_as_float(h);
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
   lo = x - hi;
 }
 

@@ -162,7 +162,8 @@ __device__ __forceinline__ void tile_gat_publish(const TileGraphSmem& g, const T
 
 // Edge softmax over the in-edge list of this node in edge-list order (torch_geometric.utils.softmax: max,
 // exp(z - max), sum + 1e-16, divide) followed by the aggregation.  On return agg = sum_e alpha_e h_j (bias not yet
-// added) and the attention coefficients alpha_e are left in g.swt[e][tid].
+// added); the parity path (FUSED = false) also leaves the attention coefficients alpha_e in g.swt[e][tid] (read by
+// the DQN backward pass).
 template <bool FUSED = false>
 __device__ __forceinline__ void tile_gat_attend(const TileGraphSmem& g, const TileThread& t, int deg, float adst,
                                                 float (&agg)[32]) {
@@ -181,24 +182,46 @@ __device__ __forceinline__ void tile_gat_attend(const TileGraphSmem& g, const Ti
       swt[e * T] = z;
       m = fmaxf(m, z);
     }
-    float den = 0.0f;
-#pragma unroll 4
-    for (int e = 0; e < deg; ++e) {
-      const float w = FUSED ? __expf(swt[e * T] - m) : expf(__fsub_rn(swt[e * T], m));
-      swt[e * T] = w;
-      den = __fadd_rn(den, w);
-    }
-    den = __fadd_rn(den, 1e-16f);
     if (FUSED) {
-      // tensor-core path: reciprocal instead of a division per edge, and two edges per iteration with all 16 row
-      // loads issued before the 64 FFMAs so the shared-memory latency of one edge hides behind the other's math
-      const float inv = 1.0f / den;
-      for (int e = 0; e < deg; ++e) {
-        const float alpha = swt[e * T] * inv;
-        swt[e * T] = alpha;
-        gat_accumulate<true>(agg, alpha, reinterpret_cast<const float4*>(shb + sin[e * T] * kHPad));
+      // tensor-core path (activations feed a 3xTF32 contraction anyway): ONE more sweep computes the unnormalised
+      // weights exp(z - max), their sum and the aggregation; the division by the sum is applied once to the 32
+      // channels at the end.  Two edges per iteration, all 16 row loads issued before the 32 packed FFMAs, so the
+      // shared-memory latency of one edge hides behind the other's math.
+      float den = 0.0f;
+      int e = 0;
+      for (; e + 2 <= deg; e += 2) {
+        const float4* __restrict__ r0 = reinterpret_cast<const float4*>(shb + sin[e * T] * kHPad);
+        const float4* __restrict__ r1 = reinterpret_cast<const float4*>(shb + sin[(e + 1) * T] * kHPad);
+        const float w0 = __expf(swt[e * T] - m), w1 = __expf(swt[(e + 1) * T] - m);
+        float4 v0[8], v1[8];
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) { v0[c4] = r0[c4]; v1[c4] = r1[c4]; }
+        den = __fadd_rn(__fadd_rn(den, w0), w1);
+        gat_accumulate_regs(agg, w0, v0);
+        gat_accumulate_regs(agg, w1, v1);
+      }
+      if (e < deg) {
+        const float w0 = __expf(swt[e * T] - m);
+        den = __fadd_rn(den, w0);
+        gat_accumulate<true>(agg, w0, reinterpret_cast<const float4*>(shb + sin[e * T] * kHPad));
+      }
+      const float inv = 1.0f / __fadd_rn(den, 1e-16f);
+      const float2 i2 = make_float2(inv, inv);
+#pragma unroll
+      for (int c2 = 0; c2 < 16; ++c2) {
+        const float2 r = __fmul2_rn(make_float2(agg[2 * c2], agg[2 * c2 + 1]), i2);
+        agg[2 * c2] = r.x;
+        agg[2 * c2 + 1] = r.y;
       }
     } else {
+      float den = 0.0f;
+#pragma unroll 4
+      for (int e = 0; e < deg; ++e) {
+        const float w = expf(__fsub_rn(swt[e * T], m));
+        swt[e * T] = w;
+        den = __fadd_rn(den, w);
+      }
+      den = __fadd_rn(den, 1e-16f);
       for (int e = 0; e < deg; ++e) {
         const int j = sin[e * T];
         const float alpha = __fdiv_rn(swt[e * T], den);
