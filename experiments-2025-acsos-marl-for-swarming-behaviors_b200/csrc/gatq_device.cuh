@@ -92,6 +92,17 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 
+__device__ __forceinline__ float exp2f_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // (aggregate + conv1.bias) -> tanh -> lin1 -> ReLU -> lin2; returns argmax (first maximum wins).
 // On return a1 holds u = tanh(agg + b0) and a2 holds r = relu(W1 u + b1) (kept for the backward pass).
 __device__ __forceinline__ int gat_head_keep(float (&a1)[32], float (&a2)[32], const float* __restrict__ sw, float (&q)[9]) {

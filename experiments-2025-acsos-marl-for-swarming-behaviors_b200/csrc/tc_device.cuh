@@ -46,10 +46,14 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 }
 
 __device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) {
-  split_tf32(v.x, hi.x, lo.x);
-  split_tf32(v.y, hi.y, lo.y);
-  split_tf32(v.z, hi.z, lo.z);
-  split_tf32(v.w, hi.w, lo.w);
+  hi.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
+  hi.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
+  hi.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
+  hi.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
+  // lo = v - hi, two lanes per FADD2
+  const float2 l0 = __fadd2_rn(make_float2(v.x, v.y), make_float2(-hi.x, -hi.y));
+  const float2 l1 = __fadd2_rn(make_float2(v.z, v.w), make_float2(-hi.z, -hi.w));
+  lo = make_float4(l0.x, l0.y, l1.x, l1.y);
 }
 
 // byte offset of (row r, k-chunk c) inside a K-major operand tile with `rows` rows

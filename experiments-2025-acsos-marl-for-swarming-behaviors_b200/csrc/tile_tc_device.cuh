@@ -122,11 +122,23 @@ __device__ __forceinline__ int tile_q_forward_tc(const TileGraphSmem& g, const T
   tc_mma_round(s, tmem, s.x, kTcXBytes / 2, s.w0, kTcW0Bytes / 2, 32, 1, parity);
   float h[32];
   tc::tmem_ld32(lane_addr, h);
-  float asrc = 0.0f, adst = 0.0f;
+  // alpha_src = <h, att_src>, alpha_dst = <h, att_dst>: vector loads of the attention vectors, packed FFMA2 with the
+  // (src, dst) pair as the two lanes
+  float asrc, adst;
+  {
+    float2 acc = make_float2(0.0f, 0.0f);
+    const float4* as4 = reinterpret_cast<const float4*>(s.vec + TV_ATT_S);
+    const float4* ad4 = reinterpret_cast<const float4*>(s.vec + TV_ATT_D);
 #pragma unroll
-  for (int cc = 0; cc < 32; ++cc) {
-    asrc = fmaf(h[cc], s.vec[TV_ATT_S + cc], asrc);
-    adst = fmaf(h[cc], s.vec[TV_ATT_D + cc], adst);
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const float4 a = as4[c4], d = ad4[c4];
+      acc = __ffma2_rn(make_float2(h[4 * c4 + 0], h[4 * c4 + 0]), make_float2(a.x, d.x), acc);
+      acc = __ffma2_rn(make_float2(h[4 * c4 + 1], h[4 * c4 + 1]), make_float2(a.y, d.y), acc);
+      acc = __ffma2_rn(make_float2(h[4 * c4 + 2], h[4 * c4 + 2]), make_float2(a.z, d.z), acc);
+      acc = __ffma2_rn(make_float2(h[4 * c4 + 3], h[4 * c4 + 3]), make_float2(a.w, d.w), acc);
+    }
+    asrc = acc.x;
+    adst = acc.y;
   }
   if (t.active) tile_gat_publish(g, t, h, asrc);
   __syncthreads();
@@ -134,14 +146,41 @@ __device__ __forceinline__ int tile_q_forward_tc(const TileGraphSmem& g, const T
   float a1[32];
   tile_gat_attend<true>(g, t, deg, adst, a1);
   __syncthreads();                 // the h tile aliases the A tiles: everyone is done gathering
+  {
+    // u = tanh(agg + b0) = 1 - 2 / (exp(2 (agg + b0)) + 1), two channels per packed instruction around the SFU ops
+    const float4* b4 = reinterpret_cast<const float4*>(s.vec + TV_B0);
+    const float2 two_log2e = make_float2(2.0f * 1.4426950408889634f, 2.0f * 1.4426950408889634f);
+    const float2 one = make_float2(1.0f, 1.0f), neg2 = make_float2(-2.0f, -2.0f);
 #pragma unroll
-  for (int cc = 0; cc < 32; ++cc) a1[cc] = tanh_fast(a1[cc] + s.vec[TV_B0 + cc]);
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const float4 b = b4[c4];
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int c = 4 * c4 + 2 * h2;
+        const float2 bb = h2 == 0 ? make_float2(b.x, b.y) : make_float2(b.z, b.w);
+        const float2 z = __fmul2_rn(__fadd2_rn(make_float2(a1[c], a1[c + 1]), bb), two_log2e);
+        const float2 e = __fadd2_rn(make_float2(exp2f_approx(z.x), exp2f_approx(z.y)), one);
+        const float2 u = __ffma2_rn(neg2, make_float2(rcp_approx(e.x), rcp_approx(e.y)), one);
+        a1[c] = u.x;
+        a1[c + 1] = u.y;
+      }
+    }
+  }
   tc_store_a_row(s, t.tid, a1);
   // ---- lin1 + ReLU ----
   tc_mma_round(s, tmem + 32, s.a, kTcABytes / 2, s.w1, kTcW1Bytes / 2, 32, 4, parity);
   tc::tmem_ld32(lane_addr + 32, a1);
+  {
+    const float4* b4 = reinterpret_cast<const float4*>(s.vec + TV_B1);
 #pragma unroll
-  for (int cc = 0; cc < 32; ++cc) a1[cc] = fmaxf(__fadd_rn(a1[cc], s.vec[TV_B1 + cc]), 0.0f);
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const float4 b = b4[c4];
+      const float2 lo = __fadd2_rn(make_float2(a1[4 * c4 + 0], a1[4 * c4 + 1]), make_float2(b.x, b.y));
+      const float2 hi = __fadd2_rn(make_float2(a1[4 * c4 + 2], a1[4 * c4 + 3]), make_float2(b.z, b.w));
+      a1[4 * c4 + 0] = fmaxf(lo.x, 0.0f); a1[4 * c4 + 1] = fmaxf(lo.y, 0.0f);
+      a1[4 * c4 + 2] = fmaxf(hi.x, 0.0f); a1[4 * c4 + 3] = fmaxf(hi.y, 0.0f);
+    }
+  }
   tc_store_a_row(s, t.tid, a1);     // lin1 has completed (mbarrier), the A tiles are free again
   // ---- lin2 ----
   tc_mma_round(s, tmem, s.a, kTcABytes / 2, s.w2, kTcW2Bytes / 2, 16, 4, parity);
