@@ -89,7 +89,11 @@ __global__ void __launch_bounds__(kTileThreads, TC ? 3 : 4) tile_kernel(const __
   }
 
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (t.active) s = reinterpret_cast<const float4*>(p.state_in)[t.gidx];
+  float ret0 = 0.0f;                 // running return of this agent, fetched up front (its latency hides behind tick 0)
+  if (t.active) {
+    s = reinterpret_cast<const float4*>(p.state_in)[t.gidx];
+    if (MODE == MODE_ROLLOUT && p.returns) ret0 = p.returns[t.gidx];
+  }
 
   int deg = 0;
   if (kQ && !knn && t.active) deg = tile_in_edges_complete(g, t, N);
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(kTileThreads, TC ? 3 : 4) tile_kernel(const __
   if (MODE == MODE_ROLLOUT) {
     if (t.active) {
       reinterpret_cast<float4*>(p.state_out)[t.gidx] = s;
-      if (p.returns) p.returns[t.gidx] = __fadd_rn(p.returns[t.gidx], ret);
+      if (p.returns) p.returns[t.gidx] = __fadd_rn(ret0, ret);
     }
     if (p.hits) {
       __syncthreads();

@@ -27,41 +27,69 @@ struct TileTcSmem {
 constexpr int kTcABytes = 2 * 128 * 32 * 4, kTcXBytes = 2 * 128 * 8 * 4;
 constexpr int kTcW0Bytes = 2 * 32 * 8 * 4, kTcW1Bytes = 2 * 32 * 32 * 4, kTcW2Bytes = 2 * 16 * 32 * 4;
 
-// global packed weights -> split (hi, lo) UMMA B tiles + bias / attention vectors
+// global packed weights -> split (hi, lo) UMMA B tiles + bias / attention vectors.
+// All global loads of a thread are issued before the first shared-memory store (the destinations are char pointers,
+// which the compiler must assume to alias the source): one exposed memory round trip instead of one per item --
+// this prologue is a fifth of a single-tick launch (train tick).
 __device__ __forceinline__ void stage_weights_tc(const float* __restrict__ gw, const TileTcSmem& s, int tid, int nthreads) {
-  for (int idx = tid; idx < TV_COUNT; idx += nthreads) {
+  constexpr int kVecIters = (TV_COUNT + kTileThreads - 1) / kTileThreads;     // 2
+  constexpr int kItemIters = (448 + kTileThreads - 1) / kTileThreads;         // 4
+  float vv[kVecIters];
+#pragma unroll
+  for (int k = 0; k < kVecIters; ++k) {
+    const int idx = tid + k * nthreads;
     float v = 0.0f;
     if (idx < TV_ATT_D) v = gw[SWARM_W_ATT_SRC + idx];
     else if (idx < TV_B0) v = gw[SWARM_W_ATT_DST + (idx - TV_ATT_D)];
     else if (idx < TV_B1) v = gw[SWARM_W_CONV_BIAS + (idx - TV_B0)];
     else if (idx < TV_B2) v = gw[SWARM_W_LIN1_BIAS + (idx - TV_B1)];
     else if (idx - TV_B2 < 9) v = gw[SWARM_W_LIN2_BIAS + (idx - TV_B2)];
-    s.vec[idx] = v;
+    vv[k] = v;
   }
   // items: (row n, k-chunk c) of W1 (256), W2 (128), W0 (64)
-  for (int it = tid; it < 448; it += nthreads) {
+  float4 item[kItemIters];
+#pragma unroll
+  for (int k = 0; k < kItemIters; ++k) {
+    const int it = tid + k * nthreads;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (it < 256) {
+      const float* r = gw + SWARM_W_LIN1 + (it >> 3) * 32 + 4 * (it & 7);
+      v = make_float4(r[0], r[1], r[2], r[3]);
+    } else if (it < 384) {
+      const int j = it - 256;
+      if ((j >> 3) < 9) {
+        const float* r = gw + SWARM_W_LIN2 + (j >> 3) * 32 + 4 * (j & 7);
+        v = make_float4(r[0], r[1], r[2], r[3]);
+      }
+    } else if (it < 448) {
+      const int j = it - 384;
+      const float* r = gw + SWARM_W_CONV_LIN + (j >> 1) * 7 + 4 * (j & 1);
+      v = (j & 1) == 0 ? make_float4(r[0], r[1], r[2], r[3]) : make_float4(r[0], r[1], r[2], 0.0f);
+    }
+    item[k] = v;
+  }
+#pragma unroll
+  for (int k = 0; k < kVecIters; ++k) {
+    const int idx = tid + k * nthreads;
+    if (idx < TV_COUNT) s.vec[idx] = vv[k];
+  }
+#pragma unroll
+  for (int k = 0; k < kItemIters; ++k) {
+    const int it = tid + k * nthreads;
+    if (it >= 448) break;
     unsigned char* base;
     int rows, n, c, half;
     if (it < 256) {
       n = it >> 3; c = it & 7; rows = 32; base = s.w1; half = kTcW1Bytes / 2;
-      const float* r = gw + SWARM_W_LIN1 + n * 32 + 4 * c;
-      v = make_float4(r[0], r[1], r[2], r[3]);
     } else if (it < 384) {
       const int j = it - 256;
       n = j >> 3; c = j & 7; rows = 16; base = s.w2; half = kTcW2Bytes / 2;
-      if (n < 9) {
-        const float* r = gw + SWARM_W_LIN2 + n * 32 + 4 * c;
-        v = make_float4(r[0], r[1], r[2], r[3]);
-      }
     } else {
       const int j = it - 384;
       n = j >> 1; c = j & 1; rows = 32; base = s.w0; half = kTcW0Bytes / 2;
-      const float* r = gw + SWARM_W_CONV_LIN + n * 7 + 4 * c;
-      v = c == 0 ? make_float4(r[0], r[1], r[2], r[3]) : make_float4(r[0], r[1], r[2], 0.0f);
     }
     float4 hi, lo;
-    tc::split4(v, hi, lo);
+    tc::split4(item[k], hi, lo);
     const int off = tc::tile_off(rows, n, c);
     *reinterpret_cast<float4*>(base + off) = hi;
     *reinterpret_cast<float4*>(base + half + off) = lo;
