@@ -24,32 +24,58 @@ enum {
   TW_COUNT = TW_B2 + kW2Pad
 };
 
-// global packed weights (state-dict order) -> shared, transposed to k-major
+// global packed weights (state-dict order) -> shared, transposed to k-major.
+// The packed array is read in its own order, four floats at a time (every tensor starts at a multiple of four floats),
+// with all of a thread's loads issued before the first store: one coalesced round trip to L2 instead of fourteen
+// dependent scalar ones (this prologue was the largest exposed latency of the small-batch DQN gradient kernel).
+__device__ __forceinline__ void stage_weight_value(float* __restrict__ s, int o, float v) {
+  if (o < SWARM_W_ATT_SRC) {                    // conv1.lin.weight[c][k] -> W0T[k][c]
+    const int c = o / 7, k = o - c * 7;
+    s[TW_W0T + k * 32 + c] = v;
+  } else if (o < SWARM_W_LIN1) {                // att_src, att_dst, conv1.bias keep their order
+    s[TW_ATT_S + (o - SWARM_W_ATT_SRC)] = v;
+  } else if (o < SWARM_W_LIN1_BIAS) {           // lin1.weight[c][k] -> W1T[k][c]
+    const int r = o - SWARM_W_LIN1, c = r >> 5, k = r & 31;
+    s[TW_W1T + k * 32 + c] = v;
+  } else if (o < SWARM_W_LIN2) {
+    s[TW_B1 + (o - SWARM_W_LIN1_BIAS)] = v;
+  } else if (o < SWARM_W_LIN2_BIAS) {           // lin2.weight[a][k] -> W2T[k][a], a padded to 12
+    const int r = o - SWARM_W_LIN2, a = r >> 5, k = r & 31;
+    s[TW_W2T + k * kW2Pad + a] = v;
+  } else if (o < SWARM_W_COUNT) {
+    s[TW_B2 + (o - SWARM_W_LIN2_BIAS)] = v;
+  }
+}
+
 __device__ __forceinline__ void stage_weights(const float* __restrict__ g, float* __restrict__ s, int tid, int nthreads) {
-  for (int idx = tid; idx < TW_COUNT; idx += nthreads) {
-    float v = 0.0f;
-    if (idx < TW_ATT_S) {                       // W0T[k][c] = conv1.lin.weight[c][k]
-      const int k = idx / 32, c = idx % 32;
-      v = g[SWARM_W_CONV_LIN + c * 7 + k];
-    } else if (idx < TW_ATT_D) {
-      v = g[SWARM_W_ATT_SRC + (idx - TW_ATT_S)];
-    } else if (idx < TW_B0) {
-      v = g[SWARM_W_ATT_DST + (idx - TW_ATT_D)];
-    } else if (idx < TW_W1T) {
-      v = g[SWARM_W_CONV_BIAS + (idx - TW_B0)];
-    } else if (idx < TW_B1) {                   // W1T[k][c] = lin1.weight[c][k]
-      const int r = idx - TW_W1T, k = r / 32, c = r % 32;
-      v = g[SWARM_W_LIN1 + c * 32 + k];
-    } else if (idx < TW_W2T) {
-      v = g[SWARM_W_LIN1_BIAS + (idx - TW_B1)];
-    } else if (idx < TW_B2) {                   // W2T[k][a] = lin2.weight[a][k], a padded to 12
-      const int r = idx - TW_W2T, k = r / kW2Pad, a = r % kW2Pad;
-      v = a < 9 ? g[SWARM_W_LIN2 + a * 32 + k] : 0.0f;
-    } else {
-      const int a = idx - TW_B2;
-      v = a < 9 ? g[SWARM_W_LIN2_BIAS + a] : 0.0f;
+  static_assert(TW_ATT_D == TW_ATT_S + 32 && TW_B0 == TW_ATT_D + 32, "attention vectors and conv bias are contiguous");
+  constexpr int kChunks = SWARM_W_COUNT / 4;                 // 418 whole float4 chunks + one scalar tail
+  if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0 && nthreads >= 128) {
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ch = tid + k * nthreads;
+      v[k] = ch < kChunks ? reinterpret_cast<const float4*>(g)[ch] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    s[idx] = v;
+    const float tail = (tid == 0) ? g[SWARM_W_COUNT - 1] : 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ch = tid + k * nthreads;
+      if (ch < kChunks) {
+        stage_weight_value(s, 4 * ch + 0, v[k].x);
+        stage_weight_value(s, 4 * ch + 1, v[k].y);
+        stage_weight_value(s, 4 * ch + 2, v[k].z);
+        stage_weight_value(s, 4 * ch + 3, v[k].w);
+      }
+    }
+    if (tid == 0) stage_weight_value(s, SWARM_W_COUNT - 1, tail);
+  } else {
+    for (int o = tid; o < SWARM_W_COUNT; o += nthreads) stage_weight_value(s, o, g[o]);
+  }
+  // zero padding of the lin2 rows / bias (a = 9 .. 11)
+  for (int idx = tid; idx < 32 * 3 + 3; idx += nthreads) {
+    if (idx < 96) s[TW_W2T + (idx / 3) * kW2Pad + 9 + idx % 3] = 0.0f;
+    else s[TW_B2 + 9 + (idx - 96)] = 0.0f;
   }
 }
 
