@@ -332,10 +332,12 @@ def measure_dqn(sb, ops, dev, cfg, weights, centers, dist, barrier, stream, rank
                            loss_scale=parallel.global_loss_scale(G, N), rng_seed=rank, sample_seed=1000 + rank,
                            env_offset=rank * B)
         tt.load_cursor(0, 0, 0.3)
+        tt.peers = parallel.make_peer_exchange(dev)         # fused NVLink peer-memory all-reduce when available
+        nccl = world > 1 and tt.peers is None
 
         def tick():
             tt.grad_phase(w, w_t, state, returns, hits)
-            if world > 1:
+            if nccl:
                 dist.all_reduce(tt.grad_loss)
             tt.apply_phase(w, w_t, m, v)
 
@@ -370,7 +372,8 @@ def measure_dqn(sb, ops, dev, cfg, weights, centers, dist, barrier, stream, rank
         out[f"G{G}"] = {"graphs_per_update_per_gpu": G, "updates_per_s": ticks / (ms * 1e-3),
                         "train_agent_steps_per_s": world * B * N * ticks / (ms * 1e-3),
                         "transitions_trained_per_s": world * G * ticks / (ms * 1e-3), "ms_per_tick": ms / ticks,
-                        "ms_per_tick_eager": ms_eager / ticks, "kernels_per_tick": 4 + (1 if world > 1 else 0),
+                        "ms_per_tick_eager": ms_eager / ticks, "kernels_per_tick": 4 + (1 if nccl else 0),
+                        "grad_allreduce": ("none" if world == 1 else ("nccl" if nccl else "fused into clip+Adam over NVLink peer memory")),
                         "ticks_done": cur["tick"], "opt_steps_done": cur["opt_step"], "loss": float(tt.loss.item())}
     out["note"] = ("one train tick = rollout tick of all envs (eps 0.3) + replay push + on-device sample + TD target/loss/"
                    "backward + grad all-reduce (N>1) + clip + Adam (+ target sync every 200 ticks); %d ticks captured in "

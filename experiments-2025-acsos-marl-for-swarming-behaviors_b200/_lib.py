@@ -75,6 +75,10 @@ class SwarmResetSpec(C.Structure):
                 ("shared_center", C.c_int32), ("pad", C.c_int32)]
 
 
+class SwarmPeerExchange(C.Structure):
+    _fields_ = [("data", C.c_void_p * 16), ("flags", C.c_void_p * 16), ("world_size", C.c_int32), ("rank", C.c_int32)]
+
+
 class SwarmError(RuntimeError):
     pass
 
@@ -114,7 +118,7 @@ _SIGNATURES = {
     "swarm_episode_end": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 5 + [C.c_int64, C.c_double, C.c_double,
                                                                                  C.c_double, C.c_void_p]),
     "swarm_train_tick_apply": (C.c_int, [C.POINTER(SwarmConfig), C.POINTER(SwarmTrainHyper)] + [C.c_void_p] * 6
-                               + [C.c_int64, C.c_void_p]),
+                               + [C.c_int64, C.POINTER(SwarmPeerExchange), C.c_void_p]),
 }
 
 

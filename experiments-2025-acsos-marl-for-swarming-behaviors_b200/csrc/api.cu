@@ -41,7 +41,8 @@ cudaError_t launch_dqn_grad(const SwarmConfig& c, const float* w_online, const f
 cudaError_t launch_adam_clip(float* w, const float* grad, float* m, float* v, long long step, double lr, double beta1,
                              double beta2, double eps, double max_norm, float* target, float* grad_norm,
                              cudaStream_t stream, SwarmTrainCtl* ctl = nullptr, int num_envs = 0,
-                             long long ring_capacity = 1, int update_target_every = 1);
+                             long long ring_capacity = 1, int update_target_every = 1,
+                             const SwarmPeerExchange* peers = nullptr, float* grad_rw = nullptr);
 
 namespace {
 thread_local std::string g_last_error;
@@ -402,15 +403,21 @@ int swarm_train_tick_grad(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, 
 }
 
 int swarm_train_tick_apply(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, SwarmTrainCtl* ctl, float* weights,
-                           float* target_weights, float* exp_avg, float* exp_avg_sq, const float* grad,
-                           int64_t ring_capacity, void* stream) {
+                           float* target_weights, float* exp_avg, float* exp_avg_sq, float* grad,
+                           int64_t ring_capacity, const SwarmPeerExchange* peers, void* stream) {
   if (!cfg || cfg->num_envs <= 0) return fail(SWARM_ERR_INVALID_ARG, "cfg is NULL or num_envs <= 0");
   if (int rc = validate_hyper(hyper)) return rc;
   if (!ctl || !weights || !target_weights || !exp_avg || !exp_avg_sq || !grad) return fail(SWARM_ERR_INVALID_ARG, "NULL argument");
   if (ring_capacity < cfg->num_envs) return fail(SWARM_ERR_INVALID_ARG, "ring_capacity must be >= num_envs");
+  if (peers) {
+    if (peers->world_size < 1 || peers->world_size > SWARM_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world_size)
+      return fail(SWARM_ERR_INVALID_ARG, "peer exchange: bad world_size / rank");
+    for (int r = 0; r < peers->world_size; ++r)
+      if (!peers->data[r] || !peers->flags[r]) return fail(SWARM_ERR_INVALID_ARG, "peer exchange: NULL peer buffer");
+  }
   return check_cuda(launch_adam_clip(weights, grad, exp_avg, exp_avg_sq, 1, hyper->lr, hyper->beta1, hyper->beta2,
                                      hyper->eps, hyper->max_norm, target_weights, nullptr, (cudaStream_t)stream, ctl,
-                                     cfg->num_envs, ring_capacity, hyper->update_target_every),
+                                     cfg->num_envs, ring_capacity, hyper->update_target_every, peers, grad),
                     "swarm_train_tick_apply");
 }
 

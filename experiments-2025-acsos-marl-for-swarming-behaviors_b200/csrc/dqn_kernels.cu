@@ -530,7 +530,19 @@ struct AdamParams {
   long long ring_capacity;
   int32_t num_envs;
   int32_t update_target_every;
+  // fused one-shot all-reduce over peer memory (ctl mode only); world_size <= 1: off
+  SwarmPeerExchange peers;
+  float* grad_rw;          // same buffer as `grad` (gradient + loss), written back after the exchange
 };
+
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 
 __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
   __shared__ double swarp[8][8];            // [segment][warp] partial sums of squares
@@ -551,16 +563,56 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
   }
   // every thread owns the elements tid, tid + 256, ...: one round trip to memory for grad / m / v / w, everything
   // else from registers
-  constexpr int kPer = (SWARM_W_COUNT + 255) / 256;
+  constexpr int kPer = (SWARM_W_COUNT + 1 + 255) / 256;      // + 1: the loss rides along in the exchange
   float g_[kPer], m_[kPer], v_[kPer], w_[kPer];
 #pragma unroll
   for (int i = 0; i < kPer; ++i) {
     const int o = tid + 256 * i;
     const bool in = o < SWARM_W_COUNT;
-    g_[i] = in ? p.grad[o] : 0.0f;
+    g_[i] = (in || (o == SWARM_W_COUNT && p.peers.world_size > 1)) ? p.grad[o] : 0.0f;
     m_[i] = in ? p.m[o] : 0.0f;
     v_[i] = in ? p.v[o] : 0.0f;
     w_[i] = in ? p.w[o] : 0.0f;
+  }
+  if (p.ctl && p.peers.world_size > 1) {
+    // ---- one-shot all-reduce over NVLink peer memory ------------------------------------------------------
+    // Every rank agrees on `updating` (same ring fill), so either all ranks exchange this tick or none does.
+    const uint64_t epoch = (uint64_t)(p.ctl->tick + 1);
+    const int par = (int)(epoch & 1);
+    const bool upd = p.ctl->updating != 0;
+    if (upd) {
+      float* mine = p.peers.data[p.peers.rank] + par * SWARM_XCHG_STRIDE;
+#pragma unroll
+      for (int i = 0; i < kPer; ++i) {
+        const int o = tid + 256 * i;
+        if (o <= SWARM_W_COUNT) mine[o] = g_[i];
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (tid == 0) st_release_sys(p.peers.flags[p.peers.rank] + par, epoch);
+      if (tid < p.peers.world_size && tid != p.peers.rank) {
+        const uint64_t* f = p.peers.flags[tid] + par;
+        bool ok = false;
+        for (long long it = 0; it < (1ll << 31) && !ok; ++it) ok = ld_acquire_sys(f) >= epoch;
+        if (!ok) __trap();                    // a peer never arrived: fail loudly instead of hanging the GPU
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < kPer; ++i) g_[i] = 0.0f;
+      for (int r = 0; r < p.peers.world_size; ++r) {      // rank order on every rank: bit-identical sums
+        const float* src = p.peers.data[r] + par * SWARM_XCHG_STRIDE;
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+          const int o = tid + 256 * i;
+          if (o <= SWARM_W_COUNT) g_[i] += __ldcv(src + o);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kPer; ++i) {
+        const int o = tid + 256 * i;
+        if (o <= SWARM_W_COUNT) p.grad_rw[o] = g_[i];      // reduced gradient + loss for the host-side statistics
+      }
+    }
   }
   // torch.nn.utils.clip_grad_norm_: norms = [||g_t||_2 for each parameter tensor]; total = ||norms||_2
 #pragma unroll
@@ -696,8 +748,11 @@ cudaError_t launch_dqn_grad(const SwarmConfig& c, const float* w_online, const f
 cudaError_t launch_adam_clip(float* w, const float* grad, float* m, float* v, long long step, double lr, double beta1,
                              double beta2, double eps, double max_norm, float* target, float* grad_norm,
                              cudaStream_t stream, SwarmTrainCtl* ctl, int num_envs, long long ring_capacity,
-                             int update_target_every) {
+                             int update_target_every, const SwarmPeerExchange* peers, float* grad_rw) {
   AdamParams p;
+  if (peers && ctl) p.peers = *peers;
+  else p.peers.world_size = 0;
+  p.grad_rw = grad_rw;
   p.ctl = ctl;
   p.lr = lr;
   p.beta1 = beta1;

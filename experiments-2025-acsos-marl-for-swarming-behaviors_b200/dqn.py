@@ -249,10 +249,14 @@ class DQNTrainer:
         returns = torch.zeros(B, n, dtype=torch.float32, device=dev)
         hits = torch.zeros(B, dtype=torch.int32, device=dev)
         multi = parallel.world_size() > 1
+        # data-parallel: the gradient all-reduce runs inside the clip + Adam kernel over NVLink peer memory when
+        # symmetric memory is available, else as an NCCL all-reduce between the two phases
+        tt.peers = parallel.make_peer_exchange(dev)
+        nccl = multi and tt.peers is None
 
         def tick():
             tt.grad_phase(self.w, self.w_target, world.state, returns, hits)
-            if multi:
+            if nccl:
                 torch.distributed.all_reduce(tt.grad_loss)
             tt.apply_phase(self.w, self.w_target, self.exp_avg, self.exp_avg_sq)
 
@@ -326,11 +330,14 @@ class DQNTrainer:
         hits = torch.zeros(B, dtype=torch.int32, device=dev)
         stats = torch.zeros(episodes, 4, dtype=torch.float32, device=dev)
 
+        tt.peers = parallel.make_peer_exchange(dev)
+        nccl = multi and tt.peers is None
+
         def episode():
             ops.reset_random(cfg, spec, world.state, ctl=tt.ctl)
             for _ in range(env.max_steps):
                 tt.grad_phase(self.w, self.w_target, world.state, returns, hits)
-                if multi:
+                if nccl:
                     torch.distributed.all_reduce(tt.grad_loss)
                 tt.apply_phase(self.w, self.w_target, self.exp_avg, self.exp_avg_sq)
             tt.episode_end(returns, hits, stats, config["epsilon"], config["epsilon_decay"], config["min_epsilon"])

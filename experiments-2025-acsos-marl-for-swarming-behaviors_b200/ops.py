@@ -311,6 +311,7 @@ class TrainTick:
         self._ws_bytes = int(lib().swarm_dqn_workspace_bytes(C.byref(gcfg), G))
         self.workspace = torch.empty(max(self._ws_bytes, 256), dtype=torch.uint8, device=dev)
         self._rstruct = ring.struct()
+        self.peers = None          # parallel.PeerExchange: fuse the gradient all-reduce into apply_phase
 
     # -- cursor <-> host bookkeeping ---------------------------------------------------------------
     def load_cursor(self, tick: int, opt_step: int, epsilon: float, episode: int = 0) -> None:
@@ -350,8 +351,11 @@ class TrainTick:
 
     def apply_phase(self, weights: torch.Tensor, target: torch.Tensor, exp_avg: torch.Tensor,
                     exp_avg_sq: torch.Tensor) -> None:
+        """clip + Adam (+ target sync) and cursor advance.  With ``self.peers`` set (``parallel.PeerExchange``) the
+        gradient + loss are first summed over the ranks inside the same kernel through NVLink peer memory."""
+        peers = C.byref(self.peers.struct) if self.peers is not None else None
         check(lib().swarm_train_tick_apply(C.byref(self.cfg), C.byref(self.hyper), ptr(self.ctl), ptr(weights), ptr(target),
-                                           ptr(exp_avg), ptr(exp_avg_sq), ptr(self.grad), self.ring.capacity,
+                                           ptr(exp_avg), ptr(exp_avg_sq), ptr(self.grad_loss), self.ring.capacity, peers,
                                            stream_ptr(weights.device)))
 
 

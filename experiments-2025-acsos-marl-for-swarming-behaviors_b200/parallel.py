@@ -82,3 +82,46 @@ def allreduce_gradient(grad: torch.Tensor, loss: Optional[torch.Tensor] = None) 
 def global_loss_scale(local_graphs: int, n_agents: int) -> float:
     """1 / (total nodes of the update over all ranks): the mean of train:122 taken over the global batch."""
     return 1.0 / (local_graphs * world_size() * n_agents)
+
+
+class PeerExchange:
+    """Symmetric (peer-mapped) buffers for the fused one-shot gradient all-reduce of ``swarm_train_tick_apply``:
+    every rank allocates float[2][1680] + uint64[2] with ``torch.distributed._symmetric_memory`` and maps all peers'
+    copies over NVLink; the clip + Adam kernel publishes its partial gradient there, flags it, waits for the peers'
+    flags and sums the partials in rank order.  PyTorch only provides the allocation / rendezvous plumbing."""
+
+    DATA_FLOATS = 2 * 1680
+    FLAG_BYTES = 16
+
+    def __init__(self, device, group=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        group = group if group is not None else dist.group.WORLD
+        # one buffer: data floats followed by the two 8-byte flags (offset is a multiple of 16 bytes)
+        self.buf = symm_mem.empty(self.DATA_FLOATS + self.FLAG_BYTES // 4, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        st = _lib.SwarmPeerExchange()
+        st.world_size, st.rank = self.handle.world_size, self.handle.rank
+        if st.world_size > 16:
+            raise ValueError("PeerExchange supports up to 16 ranks")
+        for r, base in enumerate(self.handle.buffer_ptrs):
+            st.data[r] = base
+            st.flags[r] = base + self.DATA_FLOATS * 4
+        self.struct = st
+        torch.cuda.synchronize(device)
+        dist.barrier(group)            # every rank's buffer is zeroed before anybody's kernel can flag it
+
+
+def make_peer_exchange(device) -> Optional["PeerExchange"]:
+    """PeerExchange when data-parallel on GPUs with symmetric memory available, else None (the trainer then keeps the
+    NCCL all-reduce between the two tick phases).  SWARM_PEER_ALLREDUCE=0 forces the NCCL path."""
+    if world_size() <= 1 or os.environ.get("SWARM_PEER_ALLREDUCE", "1") == "0":
+        return None
+    try:
+        return PeerExchange(device)
+    except Exception as exc:           # no NVLink peer mapping / symmetric memory on this box
+        import warnings
+        warnings.warn(f"peer-memory gradient exchange unavailable ({exc!r}); using the NCCL all-reduce")
+        return None

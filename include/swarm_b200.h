@@ -249,12 +249,29 @@ int swarm_train_tick_grad(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, 
                           int32_t* hits, const SwarmReplay* ring, int64_t* indices, float* grad, float* loss,
                           void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Optional peer exchange for swarm_train_tick_apply: a one-shot all-reduce of the gradient over NVLink / NVSwitch peer
+ * memory fused into the clip + Adam kernel (replaces the separate NCCL all-reduce launch of a data-parallel tick).
+ * data[r] / flags[r] are THIS process's mappings of rank r's symmetric buffers (e.g. from
+ * torch.distributed._symmetric_memory): data float[2][SWARM_XCHG_STRIDE] (double-buffered by tick parity), flags
+ * uint64[2], both zero-initialised.  Every rank publishes its partial gradient + loss in its own buffer, releases
+ * flags[rank][parity] = tick + 1 (st.release.sys), acquires the peers' flags and sums the world_size partials in rank
+ * order -- the same order on every rank, so the weights stay bit-identical across ranks without a broadcast. */
+enum { SWARM_MAX_PEERS = 16, SWARM_XCHG_STRIDE = 1680 };
+typedef struct SwarmPeerExchange {
+  float* data[SWARM_MAX_PEERS];
+  uint64_t* flags[SWARM_MAX_PEERS];
+  int32_t world_size;
+  int32_t rank;
+} SwarmPeerExchange;
+
 /* Phase 2: clip_grad_norm_ + Adam on `grad` (bias corrections from ctl->opt_step + 1), target <- online when
  * (ctl->tick + 1) % update_target_every == 0, then ctl advances: tick += 1, ring_cursor / ring_size += B,
- * opt_step += updating. */
+ * opt_step += updating.  `grad` is float[1674] = gradient followed by the loss (the layout swarm_train_tick_grad
+ * writes when grad and loss are adjacent); with `peers` != NULL both are first summed over the ranks (see above) and
+ * the reduced values are written back to `grad`. */
 int swarm_train_tick_apply(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, SwarmTrainCtl* ctl, float* weights,
-                           float* target_weights, float* exp_avg, float* exp_avg_sq, const float* grad,
-                           int64_t ring_capacity, void* stream);
+                           float* target_weights, float* exp_avg, float* exp_avg_sq, float* grad,
+                           int64_t ring_capacity, const SwarmPeerExchange* peers, void* stream);
 
 /* ---- device-side episode boundary -------------------------------------------------------
  * The reference resets with one CPU torch.normal draw per episode (go_to:84-88, oa:100-102) and does its episode
