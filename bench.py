@@ -295,19 +295,95 @@ def run_ours(args):
         "roofline": {"kernel": "tile_kernel<MODE_ROLLOUT>", "bound": "hbm", "achieved": achieved, "peak": peak_gbs,
                      "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
                      "kernel_ms": kernel_ms,
-                     "note": "the fused rollout keeps state on chip for 100 ticks and is FP32-issue bound "
-                             "(SURVEY.md 8d); algorithmic bytes = 40 B/agent-step"},
+                     "note": "the fused rollout keeps the state on chip for 100 ticks, so it is issue / latency bound, not "
+                             "HBM bound (SURVEY.md 8d; see roofline_fp32 and memory_bound_kernels); algorithmic bytes "
+                             "= 40 B/agent-step; traffic = DRAM bytes of one launch from the committed ncu capture"},
         "roofline_fp32": {"achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_achieved / fp32_peak,
                           "flops_per_agent_step": FLOPS_PER_AGENT_STEP,
                           "peak_source": f"148 SMs x 128 FMA lanes x 2 x {sm_mhz:.0f} MHz (sampled under load)"},
         "clocks": clocks,
     }
+    line["roofline"]["traffic"] = ncu_dram_traffic_bytes()
     line["dqn"] = dqn_stats
+    if world == 1:
+        line["memory_bound_kernels"] = measure_streaming_kernels(sb, ops, dev, peak_gbs)
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_single()
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def ncu_dram_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch, from the committed `ncu --set full` summary
+    of this same command (profiles/r1_ncu_rollout_c2.txt); None if the summary is missing."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_rollout_c2.txt")
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        total = 0.0
+        for ln in open(path):
+            if ln.startswith(("dram__bytes_read.sum =", "dram__bytes_write.sum =")):
+                _, rhs = ln.split("=", 1)
+                val, u = rhs.split()[:2]
+                total += float(val) * unit[u]
+        return total
+    except (OSError, KeyError, ValueError):
+        return None
+
+
+def measure_streaming_kernels(sb, ops, dev, peak_gbs, envs=1 << 21):
+    """The stand-alone HBM-bound kernels of the path at a working set far beyond L2 (25 M agents, 400 MB of state):
+    achieved algorithmic GB/s against the measured HBM peak (SURVEY.md 8d bytes per agent-step)."""
+    import ctypes as C
+    L = sb._lib
+    N = N_AGENTS
+    cfg = ops.make_config(L.SCENARIO_OBSTACLE_AVOIDANCE, envs, N)
+    g = torch.Generator().manual_seed(0)
+    centers = (torch.tensor([0.6, -0.6]) + 0.1 * torch.randn(envs, 2, generator=g)).to(dev)
+    state = ops.reset_grid(cfg, centers)
+    out_state = torch.empty_like(state)
+    actions = torch.randint(0, 9, (envs, N), device=dev, dtype=torch.int32)
+    rewards = torch.empty(envs, N, device=dev)
+    flags = torch.empty(envs, N, dtype=torch.uint8, device=dev)
+    obs = torch.empty(envs, N, 6, device=dev)
+    dist_ = torch.empty(envs, N, 2, device=dev)
+    E = ops.edges_per_env(cfg)
+    edges = torch.empty(envs, 2, E, dtype=torch.int32, device=dev)
+    ring = ops.ReplayRing(envs, N, dev)
+    st = L.stream_ptr(dev)
+
+    def step40():
+        L.check(L.lib().swarm_sim_step(C.byref(cfg), L.ptr(state), L.ptr(actions), L.ptr(out_state), L.ptr(rewards), None, None,
+                                       None, None, st))
+
+    def step73():
+        L.check(L.lib().swarm_sim_step(C.byref(cfg), L.ptr(state), L.ptr(actions), L.ptr(out_state), L.ptr(rewards),
+                                       L.ptr(flags), None, L.ptr(obs), L.ptr(dist_), st))
+
+    def complete():
+        L.check(L.lib().swarm_graph_build(C.byref(cfg), L.ptr(state), L.ptr(edges), None, st))
+
+    cases = [("swarm_sim_step (state+action -> state+reward)", step40, envs * N * 40.0),
+             ("swarm_sim_step (+ observations, distances, flags)", step73, envs * N * 73.0),
+             ("swarm_graph_build (complete graph export)", complete, envs * (N * 16.0 + 8.0 * E)),
+             ("swarm_reset_grid", lambda: ops.reset_grid(cfg, centers, out=state), envs * (8.0 + 16.0 * N)),
+             ("swarm_replay_push", lambda: ops.replay_push(cfg, ring, state, actions, rewards, out_state), envs * N * 77.0)]
+    out = []
+    for name, fn, nbytes in cases:
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        ms = a.elapsed_time(b) / 10
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out.append({"kernel": name, "ms": ms, "algorithmic_bytes": nbytes, "achieved": gbs, "unit": "GB/s",
+                    "frac": gbs / peak_gbs})
+    return out
 
 
 def measure_dqn(sb, ops, dev, cfg, weights, centers, dist, barrier, stream, rank, world, ticks=100):

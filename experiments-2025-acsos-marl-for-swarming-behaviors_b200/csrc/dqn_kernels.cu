@@ -587,9 +587,11 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
         const int o = tid + 256 * i;
         if (o <= SWARM_W_COUNT) mine[o] = g_[i];
       }
-      __threadfence_system();
-      __syncthreads();
-      if (tid == 0) st_release_sys(p.peers.flags[p.peers.rank] + par, epoch);
+      __syncthreads();            // the release below is cumulative over the CTA barrier: all rows are published
+      if (tid == 0) {
+        __threadfence_system();
+        st_release_sys(p.peers.flags[p.peers.rank] + par, epoch);
+      }
       if (tid < p.peers.world_size && tid != p.peers.rank) {
         const uint64_t* f = p.peers.flags[tid] + par;
         bool ok = false;

@@ -37,7 +37,7 @@ __device__ __forceinline__ void tile_world_step(const TileParams& p, const TileT
 }
 
 template <int MODE, bool TC>
-__global__ void __launch_bounds__(kTileThreads, TC ? 3 : 4) tile_kernel(const __grid_constant__ TileParams p) {
+__global__ void __launch_bounds__(kTileThreads, TC ? 3 : ((MODE == MODE_GRAPH || MODE == MODE_STEP) ? 8 : 4)) tile_kernel(const __grid_constant__ TileParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr bool kQ = (MODE == MODE_ROLLOUT || MODE == MODE_FORWARD);
   constexpr bool kStep = (MODE == MODE_ROLLOUT || MODE == MODE_STEP);
