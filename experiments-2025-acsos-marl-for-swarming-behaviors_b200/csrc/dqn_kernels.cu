@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(kTileThreads) dqn_grad_kernel(const __grid_con
     __syncthreads();
     if (knn) {
       tile_knn_rows(g, t, sst, sp, N, K);
-      if (t.active) deg = tile_in_edges_knn(g, t, N, K);
+      deg = tile_in_edges_knn(g, t, N, K, reinterpret_cast<uint32_t*>(g.skv));   // distance rows are dead now
     }
     const float x[7] = {sp.x, sp.y, sp.z, sp.w, c.goal_x, c.goal_y, (float)t.i};
     tile_gat_conv(g, t, sw, x, deg, agg, adst);   // alpha_e in g.swt, h rows in g.sh, alpha_src in g.sas

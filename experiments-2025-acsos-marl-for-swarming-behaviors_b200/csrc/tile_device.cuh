@@ -80,29 +80,35 @@ __device__ __forceinline__ void tile_knn_rows(const TileGraphSmem& g, const Tile
       pr.i = j;
       row.set(j, pr);
     }
-    // Fast path: K rounds of "smallest value above the previous pick".  If every pick is unique (no exact distance
-    // tie among the K smallest nor at the K-th / (K+1)-th boundary) the result of *any* correct top-k is this list,
-    // so it equals torch.topk's; the branch-free rounds cost O(K N) uniform instructions.  Any tie (the rule on the
-    // regular start grids) or NaN falls back to the step-for-step libstdc++ emulation, whose tie order is what
-    // torch produces.
-    bool unique = true;
+    // Fast path: K branch-free rounds of "smallest value above the previous pick" give the K smallest DISTINCT values
+    // in ascending order.  If exactly K entries are <= the K-th value (no exact distance tie among the K smallest nor
+    // at the K-th / (K+1)-th boundary) the result of *any* correct top-k is this list, so it equals torch.topk's.
+    // Any tie (the rule on the regular start grids) or NaN falls back to the step-for-step libstdc++ emulation, whose
+    // tie order is what torch produces.
+    const float* __restrict__ kv = g.skv + t.tid;
     float prev = -INFINITY;
-    for (int r = 0; r < K && unique; ++r) {
+    for (int r = 0; r < K; ++r) {
       float best = INFINITY;
-      int bi = 0, cnt = 0;
-      bool nan = false;
+      int bi = 0;
+#pragma unroll 4
       for (int l = 0; l < N; ++l) {
-        const float v = g.skv[l * T + t.tid];
-        nan |= !(v == v);                              // NaN: leave it to the emulation
-        if (v > prev) {
-          if (v < best) { best = v; bi = l; cnt = 1; }
-          else if (v == best) ++cnt;
-        }
+        const float v = kv[l * T];
+        const float c = (v > prev) ? v : INFINITY;
+        const bool lt = c < best;
+        best = lt ? c : best;
+        bi = lt ? l : bi;
       }
-      unique = (cnt == 1) && !nan;
       g.snbr[r * T + t.tid] = (uint8_t)bi;
       prev = best;
     }
+    int below = 0, nans = 0;
+#pragma unroll 4
+    for (int l = 0; l < N; ++l) {
+      const float v = kv[l * T];
+      below += (v <= prev) ? 1 : 0;
+      nans += (v != v) ? 1 : 0;
+    }
+    const bool unique = (below == K) && (nans == 0) && (prev < INFINITY);
     if (!unique) {
       knn_topk_smallest(row, N, K);
       for (int r = 0; r < K; ++r) g.snbr[r * T + t.tid] = g.ski[r * T + t.tid];
@@ -113,17 +119,58 @@ __device__ __forceinline__ void tile_knn_rows(const TileGraphSmem& g, const Tile
 
 // in-edges of node d = i in edge-list order (simulator.py:20-24): for each row ii, slot r with
 // a = topk[ii][r]: edge (ii -> a) then edge (a -> ii); finally (0 -> 0).
-__device__ __forceinline__ int tile_in_edges_knn(const TileGraphSmem& g, const TileThread& t, int N, int K) {
+// The entries of one topk row are distinct, so a row ii != i sends at most ONE edge to i (when i is among its
+// neighbours) while row i itself contributes, per slot, (i -> i) if a == i and then (a -> i).  Membership of i in
+// the other rows is read from per-row bit masks (4 x 32 bits, N <= 128) published to shared memory, which turns the
+// N x K scan per thread into N bit tests.  Contains two block barriers: every thread of the CTA must call it.
+__device__ __forceinline__ int tile_in_edges_knn(const TileGraphSmem& g, const TileThread& t, int N, int K,
+                                                 uint32_t* __restrict__ smask) {
   const int T = kTileThreads;
-  int deg = 0;
-  for (int ii = 0; ii < N; ++ii) {
+  const int words = (N + 31) >> 5;
+  if (t.active) {
+    uint32_t m[4] = {0u, 0u, 0u, 0u};
     for (int r = 0; r < K; ++r) {
-      const int a = g.snbr[r * T + t.envbase + ii];
-      if (a == t.i) g.sin[(deg++) * T + t.tid] = (uint8_t)ii;
-      if (ii == t.i) g.sin[(deg++) * T + t.tid] = (uint8_t)a;
+      const int a = g.snbr[r * T + t.tid];
+      m[0] |= (a < 32) ? (1u << a) : 0u;
+      if (words > 1) {
+        m[1] |= (a >= 32 && a < 64) ? (1u << (a - 32)) : 0u;
+        m[2] |= (a >= 64 && a < 96) ? (1u << (a - 64)) : 0u;
+        m[3] |= (a >= 96) ? (1u << (a - 96)) : 0u;
+      }
     }
+    for (int w = 0; w < words; ++w) smask[w * T + t.tid] = m[w];
   }
-  if (t.i == 0) g.sin[(deg++) * T + t.tid] = 0;
+  __syncthreads();
+  int deg = 0;
+  if (t.active) {
+    // Uniform control flow for the whole warp (every lane's own row sits at a different ii, so branching on
+    // ii == i would make the warp run the K-slot loop in almost every iteration): one predicated pass over the
+    // other rows, whose entries after row i are shifted by the size of the own block, then the own block.
+    const int wi = t.i >> 5;
+    const uint32_t bit = 1u << (t.i & 31);
+    const uint32_t* __restrict__ col = smask + wi * T + t.envbase;
+    uint8_t* __restrict__ sin = g.sin + t.tid;
+    const uint8_t* __restrict__ nbr = g.snbr + t.tid;
+    int own = K;
+    for (int r = 0; r < K; ++r) own += (nbr[r * T] == t.i) ? 1 : 0;     // (i -> i) precedes (a -> i) when a == i
+    int cnt = 0, lo = 0;
+#pragma unroll 4
+    for (int ii = 0; ii < N; ++ii) {
+      const bool has = (ii != t.i) && (col[ii] & bit);
+      lo = (ii == t.i) ? cnt : lo;
+      if (has) sin[(cnt + (ii > t.i ? own : 0)) * T] = (uint8_t)ii;
+      cnt += has ? 1 : 0;
+    }
+    int pos = lo;
+    for (int r = 0; r < K; ++r) {
+      const int a = nbr[r * T];
+      if (a == t.i) sin[(pos++) * T] = (uint8_t)t.i;
+      sin[(pos++) * T] = (uint8_t)a;
+    }
+    deg = cnt + own;
+    if (t.i == 0) sin[(deg++) * T] = 0;
+  }
+  __syncthreads();            // smask may alias a buffer that is rewritten right after
   return deg;
 }
 

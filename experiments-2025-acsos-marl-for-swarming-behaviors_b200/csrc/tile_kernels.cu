@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kTileThreads, TC ? 3 : ((MODE == MODE_GRAPH ||
     // ------------------------------------------------------------------ graph ----------------
     if (knn) {
       tile_knn_rows(g, t, pos, s, N, K);
-      if (kQ && t.active) deg = tile_in_edges_knn(g, t, N, K);
+      if (kQ) deg = tile_in_edges_knn(g, t, N, K, reinterpret_cast<uint32_t*>(g.skv));   // distance rows are dead now
     }
     if (kGraphOut) {
       int32_t* eout = nullptr;
