@@ -4,17 +4,34 @@
 
 namespace swarm {
 
+// The grid offsets (Python doubles cast to float32, go_to:68-76) are the same for every env: each CTA computes the N
+// float2 offsets once in shared memory, so the per-agent work is two float adds and one 16-byte store (the double
+// arithmetic per agent made the first version FP64-bound at 55 % of the HBM peak).
+constexpr int kResetMaxSmemAgents = 4096;
+
+__device__ __forceinline__ void stage_grid_offsets(float2* soff, int n, int cols, int rows, double spacing) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int r = i / cols, q = i % cols;
+    soff[i] = make_float2((float)(((double)q - (double)(cols - 1) / 2.0) * spacing),
+                          (float)(((double)r - (double)(rows - 1) / 2.0) * spacing));
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(256) reset_grid_kernel(SwarmConfig c, int cols, int rows,
                                                          const float2* __restrict__ centers,
                                                          float4* __restrict__ state) {
+  extern __shared__ float2 soff[];
+  stage_grid_offsets(soff, c.n_agents, cols, rows, c.grid_spacing);
   const long long total = (long long)c.num_envs * c.n_agents;
+  const unsigned n = (unsigned)c.n_agents;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
        g += (long long)gridDim.x * blockDim.x) {
-    const long long env = g / c.n_agents;
-    const int i = (int)(g - env * c.n_agents);
+    const long long env = g / n;
+    const int i = (int)(g - env * n);
     const float2 ctr = centers[env];
-    const float2 p = grid_position(ctr.x, ctr.y, i, cols, rows, c.grid_spacing);
-    state[g] = make_float4(p.x, p.y, 0.0f, 0.0f);
+    const float2 o = soff[i];
+    state[g] = make_float4(__fadd_rn(ctr.x, o.x), __fadd_rn(ctr.y, o.y), 0.0f, 0.0f);
   }
 }
 
@@ -23,8 +40,8 @@ cudaError_t launch_reset_grid(const SwarmConfig& c, int cols, int rows, const fl
   const long long total = (long long)c.num_envs * c.n_agents;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  reset_grid_kernel<<<(int)blocks, 256, 0, stream>>>(c, cols, rows, reinterpret_cast<const float2*>(centers),
-                                                     reinterpret_cast<float4*>(state));
+  reset_grid_kernel<<<(int)blocks, 256, c.n_agents * sizeof(float2), stream>>>(
+      c, cols, rows, reinterpret_cast<const float2*>(centers), reinterpret_cast<float4*>(state));
   return cudaGetLastError();
 }
 
@@ -44,6 +61,8 @@ __device__ __forceinline__ float2 draw_center(const SwarmResetSpec& sp, long lon
 __global__ void __launch_bounds__(256) reset_random_kernel(SwarmConfig c, SwarmResetSpec sp, int cols, int rows,
                                                            const SwarmTrainCtl* __restrict__ ctl, long long episode,
                                                            float2* __restrict__ centers_out, float4* __restrict__ state) {
+  extern __shared__ float2 soff[];
+  stage_grid_offsets(soff, c.n_agents, cols, rows, c.grid_spacing);
   if (ctl) episode = ctl->episode;
   const long long total = (long long)c.num_envs * c.n_agents;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
@@ -52,8 +71,8 @@ __global__ void __launch_bounds__(256) reset_random_kernel(SwarmConfig c, SwarmR
     const int i = (int)(g - env * c.n_agents);
     const float2 ctr = draw_center(sp, sp.shared_center ? 0 : sp.env_offset + env, episode);
     if (centers_out && i == 0) centers_out[env] = ctr;
-    const float2 p = grid_position(ctr.x, ctr.y, i, cols, rows, c.grid_spacing);
-    state[g] = make_float4(p.x, p.y, 0.0f, 0.0f);
+    const float2 o = soff[i];
+    state[g] = make_float4(__fadd_rn(ctr.x, o.x), __fadd_rn(ctr.y, o.y), 0.0f, 0.0f);
   }
 }
 
@@ -103,7 +122,7 @@ cudaError_t launch_reset_random(const SwarmConfig& c, const SwarmResetSpec& sp, 
   const long long total = (long long)c.num_envs * c.n_agents;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  reset_random_kernel<<<(int)blocks, 256, 0, stream>>>(c, sp, cols, rows, ctl, episode,
+  reset_random_kernel<<<(int)blocks, 256, c.n_agents * sizeof(float2), stream>>>(c, sp, cols, rows, ctl, episode,
                                                        reinterpret_cast<float2*>(centers_out),
                                                        reinterpret_cast<float4*>(state));
   return cudaGetLastError();
