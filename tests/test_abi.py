@@ -109,3 +109,67 @@ def test_no_cpu_fallback(sb):
     for f in os.listdir(pkg):
         if f.endswith(".py"):
             assert "oracle" not in open(os.path.join(pkg, f)).read(), f"{f} mentions the oracle"
+
+
+def test_training_struct_layouts_match_header(sb, tmp_path):
+    """The device-driven training structs (SwarmTrainCtl is read and written by kernels AND by torch views in
+    ops.TrainTick, so its byte layout is part of the contract)."""
+    fields = [("SwarmTrainCtl", ["tick", "ring_cursor", "ring_size", "opt_step", "epsilon", "updating", "episode"]),
+              ("SwarmTrainHyper", ["lr", "max_norm", "rng_seed", "env_offset", "graphs_per_update", "gamma", "loss_scale"]),
+              ("SwarmResetSpec", ["base_x", "std_y", "seed", "env_offset", "shared_center"]),
+              ("SwarmPeerExchange", ["data", "flags", "world_size", "rank"])]
+    body = "".join(f'printf("%zu ", sizeof({s}));' + "".join(f'printf("%zu ", offsetof({s}, {f}));' for f in fs)
+                   for s, fs in fields)
+    prog = tmp_path / "layout2.c"
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "swarm_b200.h"\nint main(){' + body + 'return 0;}')
+    exe = tmp_path / "layout2"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
+    L = sb._lib
+    exp = []
+    for s, fs in fields:
+        cls = getattr(L, s)
+        exp.append(C.sizeof(cls))
+        exp += [getattr(cls, f).offset for f in fs]
+    assert got == exp
+    assert C.sizeof(L.SwarmTrainCtl) == 48 and L.SwarmTrainCtl.epsilon.offset == 32 and L.SwarmTrainCtl.updating.offset == 36
+    assert sb.ops.TrainTick.CTL_WORDS * 8 == C.sizeof(L.SwarmTrainCtl)
+
+
+def test_training_argument_validation_without_device(sb):
+    lib, L = sb._lib.lib(), sb._lib
+    cfg = sb.ops.make_config(L.SCENARIO_OBSTACLE_AVOIDANCE, 64, 12)
+    h = L.SwarmTrainHyper()
+    h.lr, h.beta1, h.beta2, h.eps, h.max_norm = 1e-3, 0.9, 0.999, 1e-8, 1.0
+    h.graphs_per_update, h.update_target_every, h.gamma, h.loss_scale = 32, 200, 0.99, 1.0
+    ring = L.SwarmReplay(8, 8, 8, 8, 1000)
+    args = lambda: (C.byref(cfg), C.byref(h), 8, 8, 8, 8, None, None, C.byref(ring), None, 8, 8, 8, 1 << 30, None)
+    h.graphs_per_update = 0
+    assert lib.swarm_train_tick_grad(*args()) == -1 and b"graphs_per_update" in lib.swarm_last_error()
+    h.graphs_per_update, h.update_target_every = 32, 0
+    assert lib.swarm_train_tick_grad(*args()) == -1 and b"update_target_every" in lib.swarm_last_error()
+    h.update_target_every, h.beta2 = 200, 1.0
+    assert lib.swarm_train_tick_grad(*args()) == -1 and b"Adam" in lib.swarm_last_error()
+    h.beta2 = 0.999
+    ring.capacity = 10                                                 # smaller than one tick's push
+    assert lib.swarm_train_tick_grad(*args()) == -1 and b"capacity" in lib.swarm_last_error()
+    ring.capacity = 1000
+    assert lib.swarm_train_tick_grad(C.byref(cfg), C.byref(h), 8, 8, 8, 8, None, None, C.byref(ring), None, 8, 8, 8, 16,
+                                     None) == -1 and b"workspace" in lib.swarm_last_error()
+    # apply: ring capacity, peer exchange sanity
+    assert lib.swarm_train_tick_apply(C.byref(cfg), C.byref(h), 8, 8, 8, 8, 8, 8, 10, None, None) == -1
+    px = L.SwarmPeerExchange()
+    px.world_size, px.rank = 2, 5
+    assert lib.swarm_train_tick_apply(C.byref(cfg), C.byref(h), 8, 8, 8, 8, 8, 8, 1000, C.byref(px), None) == -1
+    assert b"peer exchange" in lib.swarm_last_error()
+    px.rank = 1                                                        # NULL peer buffers
+    assert lib.swarm_train_tick_apply(C.byref(cfg), C.byref(h), 8, 8, 8, 8, 8, 8, 1000, C.byref(px), None) == -1
+    # reset / episode end
+    sp = sb.ops.reset_spec(L.SCENARIO_GOTO)
+    assert (sp.base_x, sp.base_y, sp.mean_x, sp.mean_y) == (1.5, -1.5, pytest.approx(-0.6), pytest.approx(0.6))   # go_to:84-88
+    sp.std_x = -1.0
+    assert lib.swarm_reset_random(C.byref(cfg), C.byref(sp), None, 0, None, 8, None) == -1
+    sp.std_x = 0.4
+    assert lib.swarm_reset_random(C.byref(cfg), C.byref(sp), None, -1, None, 8, None) == -1
+    assert lib.swarm_episode_end(C.byref(cfg), None, 8, None, None, None, 0, 0.9, 0.01, 0.05, None) == -1
+    assert lib.swarm_episode_end(C.byref(cfg), 8, 8, None, None, 8, 0, 0.9, 0.01, 0.05, None) == -1     # stats without rows
