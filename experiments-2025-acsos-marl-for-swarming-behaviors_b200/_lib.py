@@ -17,6 +17,7 @@ SCENARIO_GOTO = 0
 SCENARIO_OBSTACLE_AVOIDANCE = 1
 GRAPH_COMPLETE = 0
 GRAPH_KNN = 1
+GRAPH_RADIUS = 2
 FLAG_OBSTACLE_CONTACT = 1
 FLAG_HIT = 2
 FLAG_PENALTY = 4
@@ -37,6 +38,7 @@ class SwarmConfig(C.Structure):
         ("contact_margin", C.c_float), ("agent_radius", C.c_float), ("landmark_radius", C.c_float),
         ("goal_x", C.c_float), ("goal_y", C.c_float), ("obstacle_x", C.c_float), ("obstacle_y", C.c_float),
         ("hit_distance", C.c_float), ("penalty_distance", C.c_float), ("obstacle_weight", C.c_float),
+        ("graph_radius", C.c_float),
     ]
 
 
@@ -93,6 +95,7 @@ _SIGNATURES = {
     "swarm_reset_grid": (C.c_int, [C.POINTER(SwarmConfig), C.c_void_p, C.c_void_p, C.c_void_p]),
     "swarm_sim_step": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 9),
     "swarm_graph_build": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 4),
+    "swarm_graph_build_radius": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 4),
     "swarm_gatq_forward": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 5),
     "swarm_gatq_workspace_bytes": (C.c_int64, [C.c_int32]),
     "swarm_gatq_forward_csr": (C.c_int, [C.c_int32] + [C.c_void_p] * 6 + [C.c_void_p, C.c_int64, C.c_void_p]),

@@ -57,15 +57,6 @@ int check_cuda(cudaError_t e, const char* what) {
   return fail(SWARM_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
-// largest float q with sqrtf(q) <= dmin: makes the squared-distance pre-filter exactly equivalent to
-// the reference's `vector_norm(delta) <= dist_min` test on the rounded norm.
-float sq_threshold(float dmin) {
-  float q = dmin * dmin;
-  while (sqrtf(q) > dmin) q = std::nextafterf(q, 0.0f);
-  while (sqrtf(std::nextafterf(q, INFINITY)) <= dmin) q = std::nextafterf(q, INFINITY);
-  return q;
-}
-
 constexpr int kMaxLargeAgents = 4096;
 
 int validate(const SwarmConfig* cfg, bool need_graph, bool allow_large = false) {
@@ -79,8 +70,14 @@ int validate(const SwarmConfig* cfg, bool need_graph, bool allow_large = false) 
                                        "swarm_graph_build / swarm_gatq_forward_csr for large swarms)");
   if (cfg->n_agents > kMaxLargeAgents) return fail(SWARM_ERR_UNSUPPORTED, "n_agents > 4096");
   if (need_graph) {
-    if (cfg->graph_mode != SWARM_GRAPH_COMPLETE && cfg->graph_mode != SWARM_GRAPH_KNN)
+    if (cfg->graph_mode != SWARM_GRAPH_COMPLETE && cfg->graph_mode != SWARM_GRAPH_KNN &&
+        cfg->graph_mode != SWARM_GRAPH_RADIUS)
       return fail(SWARM_ERR_INVALID_ARG, "unknown graph mode");
+    if (cfg->graph_mode == SWARM_GRAPH_RADIUS) {
+      if (!(cfg->graph_radius >= 0.0f)) return fail(SWARM_ERR_INVALID_ARG, "graph_radius must be >= 0");
+      if (cfg->n_agents > kTileThreads)
+        return fail(SWARM_ERR_UNSUPPORTED, "the radius graph (extension) is implemented for n_agents <= 128");
+    }
     if (cfg->graph_mode == SWARM_GRAPH_KNN) {
       // torch.topk raises "selected index k out of range" for k > n (simulator.py:19 with n_agents < 10)
       if (cfg->knn_k <= 0 || cfg->knn_k > cfg->n_agents)
@@ -104,6 +101,7 @@ int fill_params(TileParams& p, const SwarmConfig* cfg, int mode) {
   p.dmin_ao = cfg->landmark_radius + cfg->agent_radius;
   p.qmax_aa = sq_threshold(p.dmin_aa);
   p.qmax_ao = sq_threshold(p.dmin_ao);
+  p.qmax_r = cfg->graph_mode == SWARM_GRAPH_RADIUS ? sq_threshold(cfg->graph_radius) : 0.0f;
   // dense contractions on the tensor cores (tcgen05 3xTF32) unless SWARM_TC=0 selects the CUDA-core FFMA path
   const char* tc_env = std::getenv("SWARM_TC");
   p.use_tc = (mode == MODE_ROLLOUT || mode == MODE_FORWARD) && !(tc_env && tc_env[0] == '0');
@@ -148,6 +146,7 @@ void swarm_default_config(SwarmConfig* cfg, int32_t scenario, int32_t num_envs, 
   cfg->hit_distance = 0.2f;
   cfg->penalty_distance = 1.0f;
   cfg->obstacle_weight = 2.5f;
+  cfg->graph_radius = 0.35f;       // extension default: <= 20 neighbours on the 0.15-spaced start grid
 }
 
 int64_t swarm_edges_per_env(const SwarmConfig* cfg) {
@@ -192,6 +191,8 @@ int swarm_graph_build(const SwarmConfig* cfg, const float* state, int32_t* edges
   if (int rc = validate(cfg, true, true)) return rc;
   if (!state) return fail(SWARM_ERR_INVALID_ARG, "state is NULL");
   if (!edges && !neighbours) return fail(SWARM_ERR_INVALID_ARG, "no output requested");
+  if (cfg->graph_mode == SWARM_GRAPH_RADIUS)
+    return fail(SWARM_ERR_INVALID_ARG, "radius graphs have a per-env edge count: use swarm_graph_build_radius");
   if (cfg->n_agents > kTileThreads) {
     if (cfg->graph_mode == SWARM_GRAPH_KNN && (int64_t)cfg->knn_k * 64 > cfg->n_agents)
       return fail(SWARM_ERR_UNSUPPORTED,
@@ -206,6 +207,18 @@ int swarm_graph_build(const SwarmConfig* cfg, const float* state, int32_t* edges
   p.edges_out = edges;
   p.nbr_out = neighbours;
   return check_cuda(launch_tile(MODE_GRAPH, p, (cudaStream_t)stream), "swarm_graph_build");
+}
+
+int swarm_graph_build_radius(const SwarmConfig* cfg, const float* state, int32_t* edges, int32_t* counts, void* stream) {
+  if (int rc = validate(cfg, true)) return rc;
+  if (cfg->graph_mode != SWARM_GRAPH_RADIUS) return fail(SWARM_ERR_INVALID_ARG, "cfg->graph_mode must be SWARM_GRAPH_RADIUS");
+  if (!state || !edges) return fail(SWARM_ERR_INVALID_ARG, "state/edges is NULL");
+  TileParams p;
+  if (int rc = fill_params(p, cfg, MODE_GRAPH)) return rc;
+  p.state_in = state;
+  p.edges_out = edges;
+  p.counts_out = counts;
+  return check_cuda(launch_tile(MODE_GRAPH, p, (cudaStream_t)stream), "swarm_graph_build_radius");
 }
 
 int swarm_gatq_forward(const SwarmConfig* cfg, const float* weights, const float* state, float* q, int32_t* actions,
@@ -263,6 +276,8 @@ int swarm_rollout(const SwarmConfig* cfg, const float* weights, float* state, in
   if (ticks == 0) return SWARM_OK;
   if (trace && trace->contact && cfg->n_agents > 32)
     return fail(SWARM_ERR_UNSUPPORTED, "contact masks need n_agents <= 32");
+  if (trace && trace->edges && cfg->graph_mode == SWARM_GRAPH_RADIUS)
+    return fail(SWARM_ERR_UNSUPPORTED, "per-tick edge traces are not available for radius graphs (variable edge count)");
   TileParams p;
   if (int rc = fill_params(p, cfg, MODE_ROLLOUT)) return rc;
   p.weights = weights;

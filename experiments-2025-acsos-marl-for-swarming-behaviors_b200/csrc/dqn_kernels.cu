@@ -27,6 +27,7 @@ struct DqnParams {
   float* partials;
   float* td;
   int32_t epb, maxdeg;
+  float qmax_r;               // radius graph threshold (see TileParams)
   int32_t parallel;           // 1: target pass and online pass of a transition run side by side on two thread groups
   // device-driven tick (swarm_train_tick_grad): slots are drawn here from the ring fill after this tick's push
   const SwarmTrainCtl* ctl;
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(kTileThreads) dqn_grad_kernel(const __grid_con
   const int N = c.n_agents;
   const int K = c.knn_k;
   const bool knn = c.graph_mode == SWARM_GRAPH_KNN;
+  const bool radius = c.graph_mode == SWARM_GRAPH_RADIUS;
   // Thread groups: el in [0, epb) runs the online network on s (and the backward pass); in `parallel` mode
   // el in [epb, 2 epb) runs the target network on s' of transition el - epb at the same time, otherwise the online
   // group runs both passes one after the other.
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(kTileThreads) dqn_grad_kernel(const __grid_con
   }
 
   int deg = 0;
-  if (!knn && t.active) deg = tile_in_edges_complete(g, t, N);
+  if (!knn && !radius && t.active) deg = tile_in_edges_complete(g, t, N);
   float agg[32], r[32];
   float adst = 0.0f, y = 0.0f, delta = 0.0f, dq = 0.0f;
 
@@ -291,6 +293,8 @@ __global__ void __launch_bounds__(kTileThreads) dqn_grad_kernel(const __grid_con
     if (knn) {
       tile_knn_rows(g, t, sst, sp, N, K);
       deg = tile_in_edges_knn(g, t, N, K, reinterpret_cast<uint32_t*>(g.skv));   // distance rows are dead now
+    } else if (radius && t.active) {
+      deg = tile_in_edges_radius(g, t, sst, sp, N, p.qmax_r);
     }
     const float x[7] = {sp.x, sp.y, sp.z, sp.w, c.goal_x, c.goal_y, (float)t.i};
     tile_gat_conv(g, t, sw, x, deg, agg, adst);   // alpha_e in g.swt, h rows in g.sh, alpha_src in g.sas
@@ -748,6 +752,7 @@ cudaError_t launch_dqn_grad(const SwarmConfig& c, const float* w_online, const f
   p.loss_scale = loss_scale;
   p.partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
   p.td = td;
+  p.qmax_r = sq_threshold(c.graph_radius);
   p.epb = dqn_epb(c, n_graphs);
   p.parallel = (2 * p.epb * c.n_agents <= kTileThreads) ? 1 : 0;
   p.maxdeg = dqn_maxdeg(c);

@@ -66,6 +66,67 @@ __device__ __forceinline__ int tile_in_edges_complete(const TileGraphSmem& g, co
   return deg;
 }
 
+// radius graph (EXTENSION, include/swarm_b200.h SWARM_GRAPH_RADIUS): the complete builder filtered by distance, so
+// the in-edges of node i in edge-list order are the sources j != i with ||p_j - p_i|| <= r in ascending j; node 0
+// additionally receives the trailing (0,0).  `pos` is the env-tile state buffer.
+__device__ __forceinline__ bool radius_hit(const float4* pos, int j, const float2& neg, float qmax_r) {
+  const float2 d = __fadd2_rn(xy_of(pos[j]), neg);
+  return __fmaf_rn(d.y, d.y, __fmul_rn(d.x, d.x)) <= qmax_r;
+}
+
+__device__ __forceinline__ int tile_in_edges_radius(const TileGraphSmem& g, const TileThread& t, const float4* pos,
+                                                    const float4& s, int N, float qmax_r) {
+  const int T = kTileThreads;
+  const float2 neg = make_float2(-s.x, -s.y);
+  const float4* env = pos + t.envbase;
+  uint8_t* sin = g.sin + t.tid;
+  int deg = 0;
+#pragma unroll 4
+  for (int j = 0; j < N; ++j) {
+    const bool hit = radius_hit(env, j, neg, qmax_r) && (j != t.i);
+    if (hit) sin[deg * T] = (uint8_t)j;
+    deg += hit ? 1 : 0;
+  }
+  if (t.i == 0) sin[(deg++) * T] = 0;
+  return deg;
+}
+
+// Radius edge list export, compacted per env: every agent counts its partners j > i in range, publishes the count,
+// an exclusive prefix sum over the env's agents gives its first pair slot; columns past the env's edge count are -1.
+// Contains one block barrier: every thread of the CTA must call it.  `scnt` = int[T] scratch.
+__device__ __forceinline__ void tile_write_edges_radius(const TileThread& t, const float4* pos, const float4& s, int N,
+                                                        float qmax_r, int E, int32_t* eout, int32_t* counts, int* scnt) {
+  const float2 neg = make_float2(-s.x, -s.y);
+  const float4* env = pos + t.envbase;
+  int mine = 0;
+  if (t.active)
+    for (int j = t.i + 1; j < N; ++j) mine += radius_hit(env, j, neg, qmax_r) ? 1 : 0;
+  scnt[t.tid] = mine;
+  __syncthreads();
+  if (!t.active) return;
+  int base = 0, total = 0;
+  for (int a = 0; a < N; ++a) {
+    const int c = scnt[t.envbase + a];
+    base += (a < t.i) ? c : 0;
+    total += c;
+  }
+  int32_t* r0 = eout + t.env * 2 * E;
+  int32_t* r1 = r0 + E;
+  for (int e = 2 * total + 1 + t.i; e < E; e += N) { r0[e] = -1; r1[e] = -1; }
+  int slot = base;
+  for (int j = t.i + 1; j < N; ++j) {
+    if (radius_hit(env, j, neg, qmax_r)) {
+      r0[2 * slot] = t.i; r1[2 * slot] = j;
+      r0[2 * slot + 1] = j; r1[2 * slot + 1] = t.i;
+      ++slot;
+    }
+  }
+  if (t.i == 0) {
+    r0[2 * total] = 0; r1[2 * total] = 0;
+    if (counts) counts[t.env] = 2 * total + 1;
+  }
+}
+
 // kNN rows (simulator.py:17-19): distance_to_i = ||x[:, :2] - x[i, :2]||, topk(k, largest=False) with
 // torch's CPU tie order.  `pos` is the env-tile state buffer (float4 per thread).  Ends with a block barrier.
 __device__ __forceinline__ void tile_knn_rows(const TileGraphSmem& g, const TileThread& t, const float4* pos,

@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(kTileThreads, TC ? 3 : ((MODE == MODE_GRAPH ||
   const int N = c.n_agents;
   const int K = c.knn_k;
   const bool knn = (c.graph_mode == SWARM_GRAPH_KNN) && (kQ || MODE == MODE_GRAPH);
+  const bool radius = (c.graph_mode == SWARM_GRAPH_RADIUS) && (kQ || MODE == MODE_GRAPH);
   const TileThread t = tile_thread(N, p.epb, c.num_envs);
   const int tid = t.tid;
   const long long BN = (long long)c.num_envs * N;
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(kTileThreads, TC ? 3 : ((MODE == MODE_GRAPH ||
   }
 
   int deg = 0;
-  if (kQ && !knn && t.active) deg = tile_in_edges_complete(g, t, N);
+  if (kQ && !knn && !radius && t.active) deg = tile_in_edges_complete(g, t, N);
 
   float ret = 0.0f;
   int myhits = 0;
@@ -122,7 +123,10 @@ __global__ void __launch_bounds__(kTileThreads, TC ? 3 : ((MODE == MODE_GRAPH ||
       tile_knn_rows(g, t, pos, s, N, K);
       if (kQ) deg = tile_in_edges_knn(g, t, N, K, reinterpret_cast<uint32_t*>(g.skv));   // distance rows are dead now
     }
-    if (kGraphOut) {
+    if (radius && kQ && t.active) deg = tile_in_edges_radius(g, t, pos, s, N, p.qmax_r);
+    if (MODE == MODE_GRAPH && radius) {
+      tile_write_edges_radius(t, pos, s, N, p.qmax_r, p.edges_per_env, p.edges_out, p.counts_out, reinterpret_cast<int*>(sred));
+    } else if (kGraphOut) {
       int32_t* eout = nullptr;
       if (MODE == MODE_GRAPH) eout = p.edges_out;
       else if (p.trace.edges) eout = p.trace.edges + (long long)tick * c.num_envs * 2 * p.edges_per_env;

@@ -3,6 +3,8 @@
 #ifndef SWARM_TILE_KERNELS_CUH
 #define SWARM_TILE_KERNELS_CUH
 
+#include <math.h>
+
 #include "swarm_device.cuh"
 
 namespace swarm {
@@ -114,7 +116,19 @@ struct TileParams {
   float one_minus_drag;
   float dmin_aa, dmin_ao;        // contact distances agent-agent / agent-obstacle (sum of radii, f32 add)
   float qmax_aa, qmax_ao;        // largest squared distance whose rounded sqrt is <= dmin (exact pre-filter)
+  float qmax_r;                  // same for the radius graph: sqrt(q) <= graph_radius  <=>  q <= qmax_r
+  int32_t* counts_out;           // MODE_GRAPH, radius graph: edges per env
 };
+
+// largest float q with sqrtf(q) <= dmin: makes a squared-distance test exactly equivalent to the reference's
+// `vector_norm(delta) <= dmin` test on the rounded norm (host side)
+inline float sq_threshold(float dmin) {
+  if (!(dmin < 1e18f)) return INFINITY;
+  float q = dmin * dmin;
+  while (sqrtf(q) > dmin) q = nextafterf(q, 0.0f);
+  while (sqrtf(nextafterf(q, INFINITY)) <= dmin) q = nextafterf(q, INFINITY);
+  return q;
+}
 
 // byte offsets of the dynamic shared memory regions
 struct TileLayout {

@@ -16,8 +16,9 @@ from ._lib import SwarmConfig, SwarmReplay, SwarmRolloutOptions, SwarmTrace, che
 
 
 def make_config(scenario: int, num_envs: int, n_agents: int, graph_mode: int = _lib.GRAPH_COMPLETE,
-                knn_k: int = 10) -> SwarmConfig:
+                knn_k: int = 10, graph_radius: float = 0.35) -> SwarmConfig:
     cfg = _lib.default_config(scenario, num_envs, n_agents)
+    cfg.graph_radius = graph_radius
     cfg.graph_mode = graph_mode
     cfg.knn_k = knn_k
     return cfg
@@ -77,11 +78,16 @@ def sim_step(cfg: SwarmConfig, state: torch.Tensor, actions: torch.Tensor, *, st
 
 def graph_build(cfg: SwarmConfig, state: torch.Tensor, want_neighbours: bool = False
                 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """edges int32[B,2,E] (env-local ids) and, for kNN, the topk index table int32[B,N,k]."""
+    """edges int32[B,2,E] (env-local ids) and, for kNN, the topk index table int32[B,N,k].  Radius graphs (extension)
+    return the padded edge block int32[B,2,N(N-1)+1] (-1 past the env's edge count) and the counts int32[B]."""
     B, N = cfg.num_envs, cfg.n_agents
     _expect(state, torch.float32, B * N * 4, "state")
     E = edges_per_env(cfg)
     edges = torch.empty(B, 2, E, dtype=torch.int32, device=state.device)
+    if cfg.graph_mode == _lib.GRAPH_RADIUS:
+        counts = torch.empty(B, dtype=torch.int32, device=state.device)
+        check(lib().swarm_graph_build_radius(C.byref(cfg), ptr(state), ptr(edges), ptr(counts), stream_ptr(state.device)))
+        return edges, counts
     nbr = None
     if want_neighbours and cfg.graph_mode == _lib.GRAPH_KNN:
         nbr = torch.empty(B, N, cfg.knn_k, dtype=torch.int32, device=state.device)

@@ -30,7 +30,11 @@ extern "C" {
 #define SWARM_ABI_VERSION 1
 
 enum { SWARM_SCENARIO_GOTO = 0, SWARM_SCENARIO_OBSTACLE_AVOIDANCE = 1 };
-enum { SWARM_GRAPH_COMPLETE = 0, SWARM_GRAPH_KNN = 1 };
+/* SWARM_GRAPH_RADIUS is an EXTENSION (the reference has no radius graph): the complete-graph
+ * builder of train_gcn_dqn.py:94-110 filtered by distance -- for i < j with ||p_j - p_i|| <= graph_radius (float32
+ * norm as in simulator.py:18) the edges (i -> j), (j -> i), in (i, j) order, then the trailing (0 -> 0).  With an
+ * infinite radius it reproduces the complete graph edge for edge. */
+enum { SWARM_GRAPH_COMPLETE = 0, SWARM_GRAPH_KNN = 1, SWARM_GRAPH_RADIUS = 2 };
 enum {
   SWARM_OK = 0,
   SWARM_ERR_INVALID_ARG = -1,
@@ -81,6 +85,7 @@ typedef struct SwarmConfig {
   float hit_distance;              /* oa:25 */
   float penalty_distance;          /* oa:24 */
   float obstacle_weight;           /* oa:136 */
+  float graph_radius;              /* SWARM_GRAPH_RADIUS only */
 } SwarmConfig;
 
 /* optional per-tick traces of swarm_rollout (any pointer may be NULL); T = ticks */
@@ -98,7 +103,8 @@ typedef struct SwarmTrace {
 int swarm_abi_version(void);
 const char* swarm_last_error(void);
 void swarm_default_config(SwarmConfig* cfg, int32_t scenario, int32_t num_envs, int32_t n_agents);
-/* number of edges per env for cfg->graph_mode: N(N-1)+1 (train_gcn_dqn.py:101-108) or 2kN+1 (simulator.py:15-24) */
+/* number of edges per env for cfg->graph_mode: N(N-1)+1 (train_gcn_dqn.py:101-108) or 2kN+1 (simulator.py:15-24);
+ * for SWARM_GRAPH_RADIUS the CAPACITY N(N-1)+1 of the padded per-env edge block */
 int64_t swarm_edges_per_env(const SwarmConfig* cfg);
 
 /* generate_grid + reset_world_at (go_to:52-106, oa:63-133): agents on the row-major grid around
@@ -121,6 +127,12 @@ int swarm_sim_step(const SwarmConfig* cfg, const float* state_in, const int32_t*
  * topk index row of every agent. */
 int swarm_graph_build(const SwarmConfig* cfg, const float* state, int32_t* edges, int32_t* neighbours,
                       void* stream);
+
+/* Radius graph (extension, see SWARM_GRAPH_RADIUS): edges int32[B][2][N(N-1)+1], the first counts[b] columns of env b
+ * hold its edge list, the rest is -1; counts int32[B] (always odd: pairs come as (i -> j), (j -> i), plus (0 -> 0)).
+ * The per-env list is compacted in shared memory: every agent counts its partners j > i in range, an exclusive
+ * prefix sum over the env's agents gives its write offset.  n_agents <= 128. */
+int swarm_graph_build_radius(const SwarmConfig* cfg, const float* state, int32_t* edges, int32_t* counts, void* stream);
 
 /* GCN.forward (train_gcn_dqn.py:59-70) on the per-env graph named by cfg->graph_mode, node features
  * [pos, vel, goal, agent id] built from state (train:95-99).  q float[B*N][9] and actions int32[B*N]

@@ -105,11 +105,37 @@ def edges_complete(B: int, N: int) -> torch.Tensor:
     return so.graph_complete(N).unsqueeze(0).expand(B, 2, -1).contiguous()
 
 
+def edges_radius(pos: torch.Tensor, radius: float) -> torch.Tensor:
+    """EXTENSION (no reference counterpart): the complete builder of train_gcn_dqn.py:94-110
+    filtered by distance.  For i < j with ||p_j - p_i|| <= radius (float32 norm as in simulator.py:18): (i -> j),
+    (j -> i) in (i, j) order, then (0 -> 0).  Returns the padded block int64[B,2,N(N-1)+1] with -1 past each env's
+    edge count (batch_edge_index drops the padding)."""
+    B, N, _ = pos.shape
+    cap = N * (N - 1) + 1
+    out = torch.full((B, 2, cap), -1, dtype=torch.int64)
+    r = torch.tensor(radius, dtype=torch.float32)
+    for b in range(B):
+        e = []
+        for i in range(N):
+            d = torch.linalg.norm(pos[b] - pos[b, i], dim=1)          # ||p_j - p_i|| for every j
+            for j in range(i + 1, N):
+                if d[j] <= r:
+                    e.append([i, j])
+                    e.append([j, i])
+        e.append([0, 0])
+        ei = torch.tensor(e, dtype=torch.int64).t()
+        out[b, :, :ei.shape[1]] = ei
+    return out
+
+
 def batch_edge_index(edges: torch.Tensor, N: int) -> torch.Tensor:
-    """env-local int64[B,2,E] -> Batch.from_data_list edge_index int64[2,B*E]."""
+    """env-local int64[B,2,E] -> Batch.from_data_list edge_index int64[2,B*E] (columns holding -1 are padding of the
+    variable-length radius lists and are dropped; env order and in-env order are kept)."""
     B = edges.shape[0]
     off = (torch.arange(B) * N).view(B, 1, 1)
-    return (edges + off).permute(1, 0, 2).reshape(2, -1)
+    ei = (edges + off).permute(1, 0, 2).reshape(2, -1)
+    keep = edges.permute(1, 0, 2).reshape(2, -1)[0] >= 0
+    return ei[:, keep] if not bool(keep.all()) else ei
 
 
 def gatq(params: Dict[str, torch.Tensor], pos: torch.Tensor, vel: torch.Tensor, edges: torch.Tensor) -> torch.Tensor:
@@ -119,10 +145,13 @@ def gatq(params: Dict[str, torch.Tensor], pos: torch.Tensor, vel: torch.Tensor, 
     return so.gatq_forward(params, x, batch_edge_index(edges, N)).reshape(B, N, 9)
 
 
-def graph_edges(pos: torch.Tensor, graph_mode: str, k: int) -> torch.Tensor:
+def graph_edges(pos: torch.Tensor, graph_mode: str, k) -> torch.Tensor:
+    """``k`` is the neighbour count for "knn" and the radius for "radius"."""
     B, N, _ = pos.shape
     if graph_mode == "knn":
         return edges_from_knn(knn_table(pos, k))
+    if graph_mode == "radius":
+        return edges_radius(pos, float(k))
     return edges_complete(B, N)
 
 
