@@ -51,11 +51,13 @@ class Environment:
         self.agents = self.world.agents
         self.n_agents = len(self.agents)
         self.steps = torch.zeros(num_envs, device=self.device)
-        obs_spaces = {a.name: Box(-float("inf"), float("inf"), (6,)) for a in self.agents}
         act_spaces = {a.name: Discrete(9) for a in self.agents}
-        self.observation_space = obs_spaces if dict_spaces else list(obs_spaces.values())
         self.action_space = act_spaces if dict_spaces else list(act_spaces.values())
         self.reset(seed=seed)
+        # observation sizes come from the scenario (6 for the reference scenarios: pos, vel, goal; train:79)
+        obs_spaces = {a.name: Box(-float("inf"), float("inf"), (int(scenario.observation(a).shape[-1]),))
+                      for a in self.agents}
+        self.observation_space = obs_spaces if dict_spaces else list(obs_spaces.values())
 
     # -- seeding (vmas Environment.seed) ------------------------------------------------------
     def seed(self, seed: Optional[int] = None) -> List[int]:

@@ -1,89 +1,275 @@
-"""GoTo-position and ObstacleAvoidance scenarios behind the VMAS ``BaseScenario`` surface.
+"""The VMAS scenario seam: ``World`` / ``Agent`` / ``Landmark`` / ``Sphere`` / ``Color`` / ``BaseScenario`` with the
+constructor signatures and attributes of vmas==1.4.0 that scenario files are written against
+(``vmas.simulator.core``, ``vmas.simulator.scenario``, ``vmas.simulator.utils``), plus the two scenarios of the
+hot path, GoTo-position and ObstacleAvoidance.
 
-Mirrors src/scenarios/go_to_position_scenario.py:7-149 and
-src/scenarios/obstacle_avoidance_scenario.py:7-181 (``make_world / reset_world_at / observation /
-reward / done / info`` plus the metric methods the Simulator calls on ``env.scenario``).  The arithmetic
-is not here: ``World.step`` runs ``swarm_sim_step`` and the callbacks return views of what the kernel
-wrote for the agent they are asked about.
+Mirrors src/scenarios/go_to_position_scenario.py:7-149 and src/scenarios/obstacle_avoidance_scenario.py:7-181
+(``make_world / reset_world_at / observation / reward / done / info`` plus the metric methods the Simulator calls on
+``env.scenario``).  The arithmetic is not here: ``World.step`` runs ``swarm_sim_step`` on the world's
+structure-of-arrays state, entities are views into it, and the two built-in scenarios return what the kernel wrote
+for the agent they are asked about.
+
+A scenario written by a user against the vmas API (its own ``make_world`` building ``World(batch_dim, device)``,
+``Landmark(...)``, ``Agent(...)``; rewards / observations computed with torch from ``agent.state.pos``) runs on the
+same CUDA world step as long as it stays inside what the kernels implement: sphere agents of one radius, at most one
+colliding (sphere) landmark at a batch-constant position, vmas' default holonomic dynamics with discrete actions.
+Anything else raises ``NotImplementedError`` at world construction -- there is no CPU fallback.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+import enum
+from typing import Dict, List, Optional, Sequence
 
 import torch
 
 from . import _lib, ops
 
 
+class Color(enum.Enum):
+    """vmas.simulator.utils.Color (rendering only)."""
+    RED = (0.75, 0.25, 0.25)
+    GREEN = (0.25, 0.75, 0.25)
+    BLUE = (0.25, 0.25, 0.75)
+    LIGHT_GREEN = (0.45, 0.95, 0.45)
+    WHITE = (0.75, 0.75, 0.75)
+    GRAY = (0.25, 0.25, 0.25)
+    BLACK = (0.15, 0.15, 0.15)
+
+
+class Shape:
+    pass
+
+
+class Sphere(Shape):
+    """vmas.simulator.core.Sphere; the default entity shape (radius 0.05)."""
+
+    def __init__(self, radius: float = 0.05):
+        if not radius > 0:
+            raise AssertionError(f"Radius must be > 0, got {radius}")
+        self.radius = float(radius)
+
+
+class Box(Shape):
+    def __init__(self, length: float = 0.3, width: float = 0.1, hollow: bool = False):
+        self.length, self.width, self.hollow = length, width, hollow
+
+
+class Line(Shape):
+    def __init__(self, length: float = 0.5):
+        self.length = length
+
+
 class _EntityState:
-    def __init__(self, pos: torch.Tensor, vel: Optional[torch.Tensor]):
+    def __init__(self, pos: Optional[torch.Tensor], vel: Optional[torch.Tensor]):
         self.pos = pos
         self.vel = vel
 
 
-class Landmark:
-    def __init__(self, name: str, collide: bool, pos: torch.Tensor):
+class Entity:
+    """Common part of vmas Agent / Landmark: name, collide / movable flags, shape, colour, batched state."""
+
+    def __init__(self, name: str, movable: bool = False, rotatable: bool = False, collide: bool = True,
+                 density: float = 25.0, mass: float = 1.0, shape: Optional[Shape] = None, v_range: Optional[float] = None,
+                 max_speed: Optional[float] = None, color=Color.GRAY, is_joint: bool = False, drag: Optional[float] = None,
+                 linear_friction: Optional[float] = None, angular_friction: Optional[float] = None, gravity=None,
+                 collision_filter=None, **_ignored):
         self.name = name
+        self.movable = movable
+        self.rotatable = rotatable
         self.collide = collide
-        self.movable = False
-        self.state = _EntityState(pos, None)
+        self.mass = mass
+        self.shape = shape if shape is not None else Sphere()
+        self.color = color
+        self.v_range, self.max_speed = v_range, max_speed
+        if is_joint or drag is not None or linear_friction is not None or angular_friction is not None or gravity is not None:
+            raise NotImplementedError("per-entity drag / friction / gravity / joints are outside the swarm_b200 kernels")
+        self._world: Optional["World"] = None
+        self._index: Optional[int] = None
+        self._pos: Optional[torch.Tensor] = None          # landmarks own their position tensor
+        self._host_pos: Optional[tuple] = None            # batch-constant position mirrored on the host (kernel constants)
+
+    # vmas names
+    @property
+    def batch_dim(self) -> int:
+        return self._world.batch_dim
+
+    @property
+    def device(self):
+        return self._world.device
+
+    def _require_world(self) -> "World":
+        if self._world is None:
+            raise AssertionError(f"{self.name} has not been added to a World")
+        return self._world
+
+    def set_vel(self, vel: torch.Tensor, batch_index: Optional[int] = None) -> None:
+        st = self.state
+        if st.vel is None:
+            return
+        v = torch.as_tensor(vel, dtype=torch.float32).to(st.vel.device)
+        if batch_index is None:
+            st.vel[...] = v
+        else:
+            st.vel[batch_index] = v
 
     def set_pos(self, pos: torch.Tensor, batch_index: Optional[int] = None) -> None:
-        self.state.pos[...] = pos.to(self.state.pos.device)
+        st = self.state
+        p_host = torch.as_tensor(pos, dtype=torch.float32)
+        p = p_host.to(st.pos.device)
+        if batch_index is None:
+            st.pos[...] = p
+            self._host_pos = (float(p_host[0]), float(p_host[1])) if p_host.dim() == 1 and not p_host.is_cuda else None
+        else:
+            st.pos[batch_index] = p
+            if self._world.batch_dim == 1 and p_host.dim() == 1 and not p_host.is_cuda:
+                self._host_pos = (float(p_host[0]), float(p_host[1]))
+            elif self._host_pos is not None and p_host.dim() == 1 and not p_host.is_cuda and \
+                    (float(p_host[0]), float(p_host[1])) != self._host_pos:
+                self._host_pos = None
 
 
-class Agent:
-    """View of one agent column of the world's SoA state."""
+class Landmark(Entity):
+    """vmas.simulator.core.Landmark: static by default; ``collide=True`` makes it the obstacle of the world step."""
 
-    def __init__(self, name: str, index: int, world: "World"):
-        self.name = name
-        self.index = index
-        self.collide = True
-        self.movable = True
-        self._world = world
-        self.goal: Optional[Landmark] = None
-        self.pos_rew = torch.zeros(world.batch_dim, device=world.device)
+    def __init__(self, name: str, shape: Optional[Shape] = None, movable: bool = False, rotatable: bool = False,
+                 collide: bool = True, density: float = 25.0, mass: float = 1.0, v_range=None, max_speed=None,
+                 color=Color.GRAY, **kwargs):
+        super().__init__(name, movable, rotatable, collide, density, mass, shape, v_range, max_speed, color, **kwargs)
 
     @property
     def state(self) -> _EntityState:
-        s = self._world.state
-        return _EntityState(s[:, self.index, 0:2], s[:, self.index, 2:4])
+        self._require_world()
+        return _EntityState(self._pos, None)
+
+
+class Agent(Entity):
+    """vmas.simulator.core.Agent: a view of one agent column of the world's SoA state."""
+
+    def __init__(self, name: str, shape: Optional[Shape] = None, movable: bool = True, rotatable: bool = True,
+                 collide: bool = True, density: float = 25.0, mass: float = 1.0, f_range=None, max_f=None, t_range=None,
+                 max_t=None, v_range=None, max_speed=None, color=Color.BLUE, alpha: float = 0.5, obs_range=None,
+                 obs_noise=None, u_noise=None, u_range: float = 1.0, u_multiplier: float = 1.0, action_script=None,
+                 sensors=None, c_noise: float = 0.0, silent: bool = True, adversary: bool = False,
+                 render_action: bool = False, dynamics=None, action_size=None, discrete_action_nvec=None, **kwargs):
+        super().__init__(name, movable, rotatable, collide, density, mass, shape, v_range, max_speed, color, **kwargs)
+        unsupported = {"f_range": f_range, "max_f": max_f, "obs_noise": obs_noise, "u_noise": u_noise,
+                       "action_script": action_script, "sensors": sensors, "dynamics": dynamics,
+                       "v_range": v_range, "max_speed": max_speed}
+        bad = [k for k, v in unsupported.items() if v]
+        if bad or u_range != 1.0 or u_multiplier != 1.0 or not movable or mass != 1.0:
+            raise NotImplementedError(
+                f"Agent({name}): {bad or 'u_range / u_multiplier / mass / movable'} differ from the vmas defaults the "
+                "swarm_b200 world step implements (holonomic, mass 1, u_range 1, discrete 3 x 3 actions)")
+        self.u_range, self.u_multiplier = u_range, u_multiplier
+        self.render_action = render_action
+        self.goal: Optional[Landmark] = None
 
     @property
-    def distance_to_goal(self) -> torch.Tensor:
-        return self._world.last["dist"][:, self.index, 0]
+    def index(self) -> int:
+        return self._index
+
+    @property
+    def state(self) -> _EntityState:
+        s = self._require_world().state
+        return _EntityState(s[:, self._index, 0:2], s[:, self._index, 2:4])
 
 
 class World:
-    """Batched world: state f32[B,N,4] in HBM, stepped by the CUDA kernel (vmas World.step)."""
+    """vmas.simulator.core.World with the state as one f32[B,N,4] tensor in HBM, stepped by the CUDA kernel."""
 
-    def __init__(self, batch_dim: int, device, scenario_id: int, n_agents: int):
+    def __init__(self, batch_dim: int, device, dt: float = 0.1, substeps: int = 1, drag: float = 0.25,
+                 linear_friction: float = 0.0, angular_friction: float = 0.0, x_semidim: Optional[float] = None,
+                 y_semidim: Optional[float] = None, dim_c: int = 0, collision_force: float = 100.0,
+                 joint_force: float = 130.0, torque_constraint_force: float = 1.0, contact_margin: float = 1e-3,
+                 gravity=(0.0, 0.0)):
         device = torch.device(device)
         if device.type != "cuda":
             raise _lib.SwarmError(f"swarm_b200 worlds live on a CUDA device (got {device}); there is no CPU fallback")
+        if substeps != 1 or linear_friction or angular_friction or x_semidim is not None or y_semidim is not None or \
+                tuple(float(g) for g in gravity) != (0.0, 0.0):
+            raise NotImplementedError("substeps != 1, friction, world bounds and gravity are outside the swarm_b200 "
+                                      "world step (the reference scenarios use the vmas defaults)")
         self.batch_dim = batch_dim
         self.device = device
-        self.cfg = ops.make_config(scenario_id, batch_dim, n_agents)
-        self.state = torch.zeros(batch_dim, n_agents, 4, dtype=torch.float32, device=device)
-        self.agents: List[Agent] = []
-        self.landmarks: List[Landmark] = []
+        self._dt, self._drag, self._collision_force, self._contact_margin = dt, drag, collision_force, contact_margin
+        self._agents: List[Agent] = []
+        self._landmarks: List[Landmark] = []
+        self.state: Optional[torch.Tensor] = None
+        self.cfg: Optional[_lib.SwarmConfig] = None
         self.last: Dict[str, torch.Tensor] = {}
-        self._refresh_outputs()
+        self._obstacle: Optional[Landmark] = None
+        self._goal: Optional[Landmark] = None
 
     # vmas attribute names
     @property
-    def dt(self) -> float:
-        return self.cfg.dt
+    def agents(self) -> List[Agent]:
+        return self._agents
+
+    @property
+    def landmarks(self) -> List[Landmark]:
+        return self._landmarks
 
     @property
     def entities(self):
-        return self.landmarks + self.agents
+        return self._landmarks + self._agents
+
+    @property
+    def dt(self) -> float:
+        return self._dt
 
     def add_agent(self, agent: Agent) -> None:
-        self.agents.append(agent)
+        if self.state is not None:
+            raise AssertionError("agents must be added inside make_world")
+        agent._world, agent._index = self, len(self._agents)
+        self._agents.append(agent)
 
     def add_landmark(self, landmark: Landmark) -> None:
-        self.landmarks.append(landmark)
+        landmark._world, landmark._index = self, len(self._landmarks)
+        landmark._pos = torch.zeros(self.batch_dim, 2, dtype=torch.float32, device=self.device)
+        landmark._host_pos = (0.0, 0.0)
+        self._landmarks.append(landmark)
+
+    def _finalize(self, scenario_id: Optional[int] = None) -> None:
+        """Called once make_world has returned: freeze the entity set, check it against what the kernels implement,
+        allocate the SoA state and derive the kernel configuration."""
+        n = len(self._agents)
+        if n == 0:
+            raise AssertionError("a world needs at least one agent")
+        radii = set()
+        for a in self._agents:
+            if not isinstance(a.shape, Sphere) or not a.collide:
+                raise NotImplementedError("the swarm_b200 world step implements colliding sphere agents")
+            radii.add(a.shape.radius)
+        if len(radii) != 1:
+            raise NotImplementedError("all agents must share one radius")
+        obstacles = [l for l in self._landmarks if l.collide]
+        if len(obstacles) > 1 or any(l.movable for l in self._landmarks):
+            raise NotImplementedError("the swarm_b200 world step implements at most one colliding, static landmark")
+        if obstacles and not isinstance(obstacles[0].shape, Sphere):
+            raise NotImplementedError("the colliding landmark must be a sphere")
+        self._obstacle = obstacles[0] if obstacles else None
+        free = [l for l in self._landmarks if not l.collide]
+        self._goal = free[0] if free else None
+        if scenario_id is None:
+            scenario_id = _lib.SCENARIO_OBSTACLE_AVOIDANCE if self._obstacle is not None else _lib.SCENARIO_GOTO
+        cfg = ops.make_config(scenario_id, self.batch_dim, n)
+        cfg.dt, cfg.drag = self._dt, self._drag
+        cfg.collision_force, cfg.contact_margin = self._collision_force, self._contact_margin
+        cfg.agent_radius = radii.pop()
+        if self._obstacle is not None:
+            cfg.landmark_radius = self._obstacle.shape.radius
+        self.cfg = cfg
+        self.state = torch.zeros(self.batch_dim, n, 4, dtype=torch.float32, device=self.device)
+        self._refresh_outputs()
+
+    def _sync_constants(self) -> None:
+        """Landmark positions are kernel constants (one value for all envs): mirror them into the config."""
+        if self._obstacle is not None:
+            if self._obstacle._host_pos is None:
+                raise NotImplementedError("the obstacle must sit at the same position in every env")
+            self.cfg.obstacle_x, self.cfg.obstacle_y = self._obstacle._host_pos
+        if self._goal is not None and self._goal._host_pos is not None:
+            self.cfg.goal_x, self.cfg.goal_y = self._goal._host_pos
 
     def _refresh_outputs(self) -> None:
         """Observation / distance terms of the current state without stepping (used after reset)."""
@@ -96,9 +282,17 @@ class World:
             "dist": torch.zeros(B, N, 2, dtype=torch.float32, device=self.device),
         }
 
+    def reset(self, env_index: Optional[int] = None) -> None:
+        """vmas World.reset: every entity's state back to zero (the scenario's reset_world_at places them next)."""
+        if env_index is None:
+            self.state.zero_()
+        else:
+            self.state[env_index].zero_()
+
     def reset_to_grid(self, centers: torch.Tensor, env_index: Optional[int] = None) -> None:
         """generate_grid + set_pos for every agent; velocities zero (vmas world.reset)."""
         centers = centers.to(device=self.device, dtype=torch.float32).reshape(-1, 2)
+        self._sync_constants()
         if env_index is None:
             if centers.shape[0] == 1:
                 centers = centers.expand(self.batch_dim, 2)
@@ -110,18 +304,22 @@ class World:
 
     def step(self, actions: torch.Tensor) -> None:
         """actions int32[B,N] -> in-place world step; results kept in ``self.last``."""
+        self._sync_constants()
         self.last = ops.sim_step(self.cfg, self.state, actions, state_out=self.state, want_obs=True)
 
-    def get_distance(self, a, b) -> torch.Tensor:
-        """world.get_distance(agent, obstacle) of the last step (oa:149-150,168,171)."""
-        agent = a if isinstance(a, Agent) else b
-        return self.last["dist"][:, agent.index, 1]
+    def get_distance(self, a: Entity, b: Entity) -> torch.Tensor:
+        """vmas World.get_distance for two spheres: centre distance minus the two radii (oa:149-150,168,171)."""
+        if not isinstance(a.shape, Sphere) or not isinstance(b.shape, Sphere):
+            raise NotImplementedError("get_distance is implemented for spheres")
+        dist = torch.linalg.vector_norm(a.state.pos - b.state.pos, dim=-1)
+        return dist - a.shape.radius - b.shape.radius
 
 
 class BaseScenario:
-    """The slice of vmas.simulator.scenario.BaseScenario the reference scripts rely on."""
+    """vmas.simulator.scenario.BaseScenario: subclasses implement make_world / reset_world_at / observation / reward
+    (and optionally done / info); the environment calls the ``env_*`` wrappers."""
 
-    scenario_id = -1
+    scenario_id: Optional[int] = None        # built-in scenarios name the fused reward kernel they use
 
     def __init__(self):
         self._world: Optional[World] = None
@@ -130,26 +328,64 @@ class BaseScenario:
     def world(self) -> World:
         return self._world
 
+    def to(self, device) -> None:            # vmas API; worlds are created on their device
+        return None
+
     def env_make_world(self, batch_dim: int, device, **kwargs) -> World:
         self._world = self.make_world(batch_dim, device, **kwargs)
+        if not isinstance(self._world, World):
+            raise AssertionError("make_world must return a swarm_b200 World (vmas.simulator.core.World of the shim)")
+        if self._world.state is None:
+            self._world._finalize(self.scenario_id)
         return self._world
 
     def env_reset_world_at(self, env_index: Optional[int]) -> None:
+        self.world.reset(env_index)
         self.reset_world_at(env_index)
+        self.world._sync_constants()
+        self.world._refresh_outputs()
 
-    # -- common to both scenarios ----------------------------------------------------------
+    # -- to be provided by the scenario ---------------------------------------------------------------
+    def make_world(self, batch_dim: int, device, **kwargs) -> World:
+        raise NotImplementedError
+
+    def reset_world_at(self, env_index: Optional[int] = None) -> None:
+        raise NotImplementedError
+
+    def observation(self, agent: Agent) -> torch.Tensor:
+        raise NotImplementedError
+
+    def reward(self, agent: Agent) -> torch.Tensor:
+        raise NotImplementedError
+
+    def done(self) -> torch.Tensor:
+        return torch.zeros(self.world.batch_dim, device=self.world.device, dtype=torch.bool)
+
+    def info(self, agent: Agent) -> Dict[str, torch.Tensor]:
+        return {}
+
+    def extra_render(self, env_index: int = 0):
+        return []
+
+
+class _KernelScenario(BaseScenario):
+    """Shared part of the two hot-path scenarios: rewards, observations and metrics are what the fused world-step
+    kernel wrote (bit-identical to the reference's per-agent torch code, see tests/test_gpu_parity.py)."""
+
     def _build_world(self, batch_dim: int, device, with_obstacle: bool) -> World:
-        world = World(batch_dim, device, self.scenario_id, self.n_agents)
-        B = batch_dim
-        goal = Landmark("goal", collide=False, pos=torch.zeros(B, 2, device=world.device))
+        world = World(batch_dim, device)
+        goal = Landmark(name="goal", collide=False, color=Color.BLACK)
         world.add_landmark(goal)
         if with_obstacle:
-            world.add_landmark(Landmark("obstacle", collide=True, pos=torch.zeros(B, 2, device=world.device)))
+            world.add_landmark(Landmark(name="obstacle", collide=True, color=Color.RED))
         for i in range(self.n_agents):
-            agent = Agent(f"agent{i}", i, world)
+            agent = Agent(name=f"agent{i}", collide=True, color=Color.GREEN, render_action=True)
+            agent.pos_rew = torch.zeros(batch_dim, device=world.device)
+            agent.collision_rew = agent.pos_rew.clone()
             agent.goal = goal
             world.add_agent(agent)
-        self.pos_rew = torch.zeros(B, device=world.device)
+        world._finalize(self.scenario_id)
+        self.pos_rew = torch.zeros(batch_dim, device=world.device)
         self.final_rew = self.pos_rew.clone()
         return world
 
@@ -159,9 +395,6 @@ class BaseScenario:
 
     def reward(self, agent: Agent) -> torch.Tensor:
         return self.world.last["rewards"][:, agent.index]
-
-    def done(self) -> torch.Tensor:
-        return torch.zeros(self.world.batch_dim, device=self.world.device, dtype=torch.bool)
 
     def info(self, agent: Agent) -> Dict[str, torch.Tensor]:
         return {"pos_rew": agent.pos_rew, "final_rew": self.final_rew}
@@ -177,7 +410,7 @@ class BaseScenario:
         self._explicit_centers = centers
 
 
-class GoToPositionScenario(BaseScenario):
+class GoToPositionScenario(_KernelScenario):
     scenario_id = _lib.SCENARIO_GOTO
 
     def make_world(self, batch_dim: int, device, **kwargs) -> World:
@@ -195,7 +428,7 @@ class GoToPositionScenario(BaseScenario):
 
     def reset_world_at(self, env_index: Optional[int] = None) -> None:
         w = self.world
-        w.landmarks[0].set_pos(torch.tensor([w.cfg.goal_x, w.cfg.goal_y]))
+        w.landmarks[0].set_pos(torch.tensor([-0.8, 0.8]), batch_index=env_index)        # go_to:86
         if self._explicit_centers is not None:
             centers = self._explicit_centers if env_index is None else self._explicit_centers[env_index:env_index + 1]
         else:
@@ -215,7 +448,7 @@ class GoToPositionScenario(BaseScenario):
         return torch.tensor(0.0)
 
 
-class ObstacleAvoidanceScenario(BaseScenario):
+class ObstacleAvoidanceScenario(_KernelScenario):
     scenario_id = _lib.SCENARIO_OBSTACLE_AVOIDANCE
 
     def make_world(self, batch_dim: int, device, **kwargs) -> World:
@@ -234,8 +467,8 @@ class ObstacleAvoidanceScenario(BaseScenario):
 
     def reset_world_at(self, env_index: Optional[int] = None) -> None:
         w = self.world
-        w.landmarks[0].set_pos(torch.tensor([w.cfg.goal_x, w.cfg.goal_y]))
-        w.landmarks[1].set_pos(torch.tensor([w.cfg.obstacle_x, w.cfg.obstacle_y]))
+        w.landmarks[0].set_pos(torch.tensor([-0.8, 0.8]), batch_index=env_index)        # oa:97
+        w.landmarks[1].set_pos(torch.tensor([-0.1, 0.1]), batch_index=env_index)        # oa:99
         if self._explicit_centers is not None:
             centers = self._explicit_centers if env_index is None else self._explicit_centers[env_index:env_index + 1]
         else:
