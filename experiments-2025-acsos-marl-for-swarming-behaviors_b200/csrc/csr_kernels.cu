@@ -146,6 +146,12 @@ cudaError_t launch_gatq_csr(int n, const float* weights, const float* x, const i
   return cudaGetLastError();
 }
 
+cudaError_t launch_csr_project(int n, const float* weights, const float* x, float* rows, cudaStream_t stream) {
+  const int blocks = (n + kCsrThreads - 1) / kCsrThreads;
+  csr_project_kernel<<<blocks, kCsrThreads, 0, stream>>>(n, weights, x, rows);
+  return cudaGetLastError();
+}
+
 long long gatq_workspace_bytes(int n) { return (long long)n * kRow * 4 + 256; }
 
 }  // namespace swarm

@@ -708,6 +708,350 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
   }
 }
 
+// ---- GCN backward on an arbitrary graph ------------------------------------------------------------------------
+// The nn.Module seam: loss.backward() through GCN.forward(data) for any Data / Batch graph (train_gcn_dqn.py:116-124
+// when the reference's own train_step_dqn drives the module).  Two gather passes, no atomics:
+//   csr_bwd_target_kernel  thread = target node: recomputes its forward (softmax over the in-edge group in edge-list
+//                          order, head), back-propagates the head, and for every in-edge stores alpha_e and
+//                          d(raw logit)_e in by-target order; per-CTA tile GEMMs give the head's weight gradients
+//   csr_bwd_source_kernel  thread = source node: gathers its out-edges (CSR by source) to form d h_j, then the tile
+//                          GEMMs for conv1.lin.weight / att_src / att_dst
+// followed by the same fixed-order partial reduction as the DQN gradient (bit-reproducible).
+constexpr int kRowB = 36;   // rows workspace of csr_kernels.cu: h[32], alpha_src, alpha_dst, pad
+
+struct CsrBwdParams {
+  int n;
+  const float* weights;
+  const float* x;
+  const int32_t* row_ptr;      // CSR by target (edge-list order inside a group)
+  const int32_t* src;
+  const int32_t* row_ptr_s;    // CSR by source
+  const int32_t* tgt_s;
+  const int32_t* pos_s;        // position in the by-target order of out-edge q
+  const float* grad_q;         // [n][9]
+  const float* rows;           // [n][36] projected features (csr_project_kernel)
+  float* d_out;                // [n][32] d(conv output)
+  float* dd;                   // [n] d(alpha_dst)
+  float* alpha;                // [E] attention coefficients, by-target order
+  float* draw;                 // [E] d(raw logit), by-target order
+  float* partials;             // [ctas][kPartialStride]
+};
+
+__global__ void csr_edge_positions_kernel(long long E, const int32_t* __restrict__ perm_t,
+                                          const int32_t* __restrict__ perm_s, int32_t* __restrict__ inv,
+                                          int32_t* __restrict__ pos_s, int phase) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
+    if (phase == 0) inv[perm_t[e]] = (int32_t)e;          // original edge id -> by-target position
+    else pos_s[e] = inv[perm_s[e]];
+  }
+}
+
+__global__ void __launch_bounds__(kTileThreads) csr_bwd_target_kernel(const __grid_constant__ CsrBwdParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int T = kTileThreads;
+  float* sw = reinterpret_cast<float*>(smem);
+  float* tU = sw + ((TW_COUNT + 3) & ~3);
+  float* tR = tU + T * kHPad;
+  float* tDP = tR + T * kHPad;
+  float* tDO = tDP + T * kHPad;
+  float* tDQ = tDO + T * kHPad;
+  const int tid = threadIdx.x;
+  const int i = blockIdx.x * T + tid;
+  const bool active = i < p.n;
+  stage_weights(p.weights, sw, tid, T);
+  if (!active) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* tiles[4] = {tU, tR, tDP, tDO};
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) {
+      float4* row = reinterpret_cast<float4*>(tiles[b] + tid * kHPad);
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) row[c4] = z;
+    }
+#pragma unroll
+    for (int a = 0; a < kW2Pad; ++a) tDQ[tid * kW2Pad + a] = 0.0f;
+  }
+  __syncthreads();
+  if (active) {
+    const int e0 = p.row_ptr[i], e1 = p.row_ptr[i + 1];
+    const float adst = p.rows[(long long)i * kRowB + 33];
+    // forward, same arithmetic as csr_aggregate_kernel
+    float m = -INFINITY;
+    for (int e = e0; e < e1; ++e) m = fmaxf(m, gat_logit(p.rows[(long long)p.src[e] * kRowB + 32], adst));
+    float den = 0.0f;
+    for (int e = e0; e < e1; ++e)
+      den = __fadd_rn(den, expf(__fsub_rn(gat_logit(p.rows[(long long)p.src[e] * kRowB + 32], adst), m)));
+    den = __fadd_rn(den, 1e-16f);
+    float agg[32], r[32], q[9];
+#pragma unroll
+    for (int cc = 0; cc < 32; ++cc) agg[cc] = 0.0f;
+    for (int e = e0; e < e1; ++e) {
+      const long long j = p.src[e];
+      const float alpha = __fdiv_rn(expf(__fsub_rn(gat_logit(p.rows[j * kRowB + 32], adst), m)), den);
+      p.alpha[e] = alpha;
+      gat_accumulate(agg, alpha, reinterpret_cast<const float4*>(p.rows + j * kRowB));
+    }
+    dqn_head(agg, tU + tid * kHPad, tR + tid * kHPad, sw, r, q);
+    // head backward: dq given
+    float dq[kW2Pad];
+#pragma unroll
+    for (int a = 0; a < kW2Pad; ++a) dq[a] = a < 9 ? p.grad_q[(long long)i * 9 + a] : 0.0f;
+#pragma unroll
+    for (int a = 0; a < kW2Pad; ++a) tDQ[tid * kW2Pad + a] = dq[a];
+    {
+      // dr[k] = sum_a W2[a][k] dq[a]; dp = dr * [r > 0], four k per iteration through the own row
+      const float4* w2 = reinterpret_cast<const float4*>(sw + TW_W2T);
+      const float4* r4 = reinterpret_cast<const float4*>(tR + tid * kHPad);
+      float4* dp4 = reinterpret_cast<float4*>(tDP + tid * kHPad);
+#pragma unroll 1
+      for (int k4 = 0; k4 < 8; ++k4) {
+        const float4 rk = r4[k4];
+        float o[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          float acc = 0.0f;
+#pragma unroll
+          for (int a4 = 0; a4 < 3; ++a4) {
+            const float4 w = w2[(k4 * 4 + kk) * 3 + a4];
+            acc = fmaf(w.x, dq[4 * a4 + 0], acc);
+            acc = fmaf(w.y, dq[4 * a4 + 1], acc);
+            acc = fmaf(w.z, dq[4 * a4 + 2], acc);
+            acc = fmaf(w.w, dq[4 * a4 + 3], acc);
+          }
+          o[kk] = f4c(rk, kk) > 0.0f ? acc : 0.0f;
+        }
+        dp4[k4] = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    float dvec[32];
+    load_row32(tDP, tid, dvec);
+    {
+      // du[k] = sum_c W1[c][k] dp[c] ; do = du * (1 - u^2)
+      const float4* w1 = reinterpret_cast<const float4*>(sw + TW_W1T);
+      const float4* u4 = reinterpret_cast<const float4*>(tU + tid * kHPad);
+      float4* do4 = reinterpret_cast<float4*>(tDO + tid * kHPad);
+#pragma unroll 1
+      for (int k4 = 0; k4 < 8; ++k4) {
+        const float4 uk = u4[k4];
+        float o[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          float acc = 0.0f;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 w = w1[(k4 * 4 + kk) * 8 + c4];
+            acc = fmaf(w.x, dvec[4 * c4 + 0], acc);
+            acc = fmaf(w.y, dvec[4 * c4 + 1], acc);
+            acc = fmaf(w.z, dvec[4 * c4 + 2], acc);
+            acc = fmaf(w.w, dvec[4 * c4 + 3], acc);
+          }
+          const float uu = f4c(uk, kk);
+          o[kk] = acc * (1.0f - uu * uu);
+        }
+        do4[k4] = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    load_row32(tDO, tid, dvec);                       // dvec = d(conv output_i)
+    {
+      float4* g = reinterpret_cast<float4*>(p.d_out + (long long)i * 32);
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) g[c4] = make_float4(dvec[4 * c4], dvec[4 * c4 + 1], dvec[4 * c4 + 2], dvec[4 * c4 + 3]);
+    }
+    // attention backward over the in-edge group
+    float dot_sum = 0.0f;
+    for (int e = e0; e < e1; ++e) {
+      const float4* hj = reinterpret_cast<const float4*>(p.rows + (long long)p.src[e] * kRowB);
+      float da = 0.0f;
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 hv = hj[c4];
+        da = fmaf(dvec[4 * c4 + 0], hv.x, da);
+        da = fmaf(dvec[4 * c4 + 1], hv.y, da);
+        da = fmaf(dvec[4 * c4 + 2], hv.z, da);
+        da = fmaf(dvec[4 * c4 + 3], hv.w, da);
+      }
+      p.draw[e] = da;
+      dot_sum = fmaf(p.alpha[e], da, dot_sum);
+    }
+    float dd_i = 0.0f;
+    for (int e = e0; e < e1; ++e) {
+      const float dz = p.alpha[e] * (p.draw[e] - dot_sum);
+      const float raw = __fadd_rn(p.rows[(long long)p.src[e] * kRowB + 32], adst);
+      const float dzz = raw > 0.0f ? dz : 0.2f * dz;
+      p.draw[e] = dzz;
+      dd_i += dzz;
+    }
+    p.dd[i] = dd_i;
+  }
+  __syncthreads();
+  float* out = p.partials + (long long)blockIdx.x * kPartialStride;
+  constexpr int G_B0 = 8, G_W1 = 256, G_B1 = 8, G_W2 = 72, G_B2 = 3;
+  constexpr int G_TOTAL = G_B0 + G_W1 + G_B1 + G_W2 + G_B2;
+#pragma unroll 1
+  for (int grp = tid; grp < G_TOTAL; grp += T) {
+    int gi = grp;
+    const float* A = nullptr;
+    const float* Bm;
+    int lda = 0, ac = 0, ldb = kHPad, bc, oidx, nout = 4;
+    if (gi < G_B0) {                                   // d conv1.bias[c] = sum_n DO[n][c]
+      Bm = tDO; bc = gi * 4; oidx = SWARM_W_CONV_BIAS + gi * 4;
+    } else if ((gi -= G_B0) < G_W1) {                  // dW1[c][k] = sum_n DP[n][c] U[n][k]
+      A = tDP; lda = kHPad; ac = gi >> 3; Bm = tU; bc = (gi & 7) * 4; oidx = SWARM_W_LIN1 + ac * 32 + bc;
+    } else if ((gi -= G_W1) < G_B1) {                  // d lin1.bias[c] = sum_n DP[n][c]
+      Bm = tDP; bc = gi * 4; oidx = SWARM_W_LIN1_BIAS + gi * 4;
+    } else if ((gi -= G_B1) < G_W2) {                  // dW2[a][k] = sum_n DQ[n][a] R[n][k]
+      A = tDQ; lda = kW2Pad; ac = gi >> 3; Bm = tR; bc = (gi & 7) * 4; oidx = SWARM_W_LIN2 + ac * 32 + bc;
+    } else {                                           // d lin2.bias[a] = sum_n DQ[n][a]
+      gi -= G_W2;
+      Bm = tDQ; ldb = kW2Pad; bc = gi * 4; oidx = SWARM_W_LIN2_BIAS + gi * 4;
+      nout = gi < 2 ? 4 : 1;
+    }
+    const float4 a = tile_gemm4(A, lda, ac, Bm, ldb, bc, T);
+    float* o = out + oidx;
+    o[0] = a.x;
+    if (nout == 4) { o[1] = a.y; o[2] = a.z; o[3] = a.w; }
+  }
+  if (tid == 0) out[SWARM_W_COUNT] = 0.0f;
+}
+
+__global__ void __launch_bounds__(kTileThreads) csr_bwd_source_kernel(const __grid_constant__ CsrBwdParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int T = kTileThreads;
+  float* tDH = reinterpret_cast<float*>(smem);
+  float* tH = tDH + T * kHPad;
+  float* tX = tH + T * kHPad;
+  float* sds = tX + T * kXPad;
+  float* sdd = sds + T;
+  const int tid = threadIdx.x;
+  const int j = blockIdx.x * T + tid;
+  float4* dh_row = reinterpret_cast<float4*>(tDH + tid * kHPad);
+  float4* h_row = reinterpret_cast<float4*>(tH + tid * kHPad);
+  float4* x_row = reinterpret_cast<float4*>(tX + tid * kXPad);
+  float ds_j = 0.0f, dd_j = 0.0f;
+  if (j < p.n) {
+    float dh[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) dh[k] = 0.0f;
+    const int q0 = p.row_ptr_s[j], q1 = p.row_ptr_s[j + 1];
+    for (int q = q0; q < q1; ++q) {
+      const int pp = p.pos_s[q];
+      const float a = p.alpha[pp];
+      ds_j += p.draw[pp];
+      const float4* dr = reinterpret_cast<const float4*>(p.d_out + (long long)p.tgt_s[q] * 32);
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 dv = dr[c4];
+        dh[4 * c4 + 0] = fmaf(a, dv.x, dh[4 * c4 + 0]);
+        dh[4 * c4 + 1] = fmaf(a, dv.y, dh[4 * c4 + 1]);
+        dh[4 * c4 + 2] = fmaf(a, dv.z, dh[4 * c4 + 2]);
+        dh[4 * c4 + 3] = fmaf(a, dv.w, dh[4 * c4 + 3]);
+      }
+    }
+    dd_j = p.dd[j];
+    const float* as = p.weights + SWARM_W_ATT_SRC;
+    const float* ad = p.weights + SWARM_W_ATT_DST;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) dh[k] = fmaf(ds_j, as[k], fmaf(dd_j, ad[k], dh[k]));
+    store_row32(tDH, tid, dh);
+    const float4* hr = reinterpret_cast<const float4*>(p.rows + (long long)j * kRowB);
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) h_row[c4] = hr[c4];
+    const float* xr = p.x + (long long)j * 7;
+    x_row[0] = make_float4(xr[0], xr[1], xr[2], xr[3]);
+    x_row[1] = make_float4(xr[4], xr[5], xr[6], 0.0f);
+  } else {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) { dh_row[c4] = z; h_row[c4] = z; }
+    x_row[0] = z;
+    x_row[1] = z;
+  }
+  sds[tid] = ds_j;
+  sdd[tid] = dd_j;
+  __syncthreads();
+  float* out = p.partials + (long long)blockIdx.x * kPartialStride;
+  constexpr int G_W0 = 64, G_AS = 8, G_AD = 8;
+#pragma unroll 1
+  for (int grp = tid; grp < G_W0 + G_AS + G_AD; grp += T) {
+    if (grp < G_W0) {                                  // dW0[c][k] = sum_n DH[n][c] X[n][k]
+      const int cc = grp >> 1, k4 = (grp & 1) * 4;
+      const float4 a = tile_gemm4(tDH, kHPad, cc, tX, kXPad, k4, T);
+      float* o = out + SWARM_W_CONV_LIN + cc * 7 + k4;
+      o[0] = a.x; o[1] = a.y; o[2] = a.z;
+      if (k4 == 0) o[3] = a.w;
+    } else {
+      const bool is_src = grp < G_W0 + G_AS;           // d att_src[c] = sum_n ds[n] H[n][c]; d att_dst with dd
+      const int gi = is_src ? grp - G_W0 : grp - G_W0 - G_AS;
+      const float4 a = tile_gemm4(is_src ? sds : sdd, 1, 0, tH, kHPad, gi * 4, T);
+      float* o = out + (is_src ? SWARM_W_ATT_SRC : SWARM_W_ATT_DST) + gi * 4;
+      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+    }
+  }
+}
+
+cudaError_t launch_csr_project(int n, const float* weights, const float* x, float* rows, cudaStream_t stream);
+
+static size_t bwd_align(size_t v) { return (v + 255) & ~(size_t)255; }
+
+long long gatq_backward_workspace_bytes(int n, long long E) {
+  const long long ctas = (n + kTileThreads - 1) / kTileThreads;
+  return (long long)(bwd_align((size_t)n * kRowB * 4) + bwd_align((size_t)n * 32 * 4) + bwd_align((size_t)n * 4) +
+                     2 * bwd_align((size_t)E * 4) + 2 * bwd_align((size_t)E * 4) +
+                     bwd_align((size_t)ctas * kPartialStride * 4) + 512);
+}
+
+cudaError_t launch_gatq_backward_csr(int n, long long E, const float* weights, const float* x, const int32_t* row_ptr,
+                                     const int32_t* src, const int32_t* perm, const int32_t* row_ptr_s,
+                                     const int32_t* tgt_s, const int32_t* perm_s, const float* grad_q, float* grad_w,
+                                     void* workspace, cudaStream_t stream) {
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  auto take = [&](size_t bytes) { char* q = base; base += bwd_align(bytes); return q; };
+  float* rows = reinterpret_cast<float*>(take((size_t)n * kRowB * 4));
+  float* d_out = reinterpret_cast<float*>(take((size_t)n * 32 * 4));
+  float* dd = reinterpret_cast<float*>(take((size_t)n * 4));
+  float* alpha = reinterpret_cast<float*>(take((size_t)E * 4));
+  float* draw = reinterpret_cast<float*>(take((size_t)E * 4));
+  int32_t* inv = reinterpret_cast<int32_t*>(take((size_t)E * 4));
+  int32_t* pos_s = reinterpret_cast<int32_t*>(take((size_t)E * 4));
+  const int ctas = (n + kTileThreads - 1) / kTileThreads;
+  float* partials = reinterpret_cast<float*>(take((size_t)ctas * kPartialStride * 4));
+  float* loss_dummy = reinterpret_cast<float*>(take(256));
+
+  cudaError_t err = launch_csr_project(n, weights, x, rows, stream);
+  if (err != cudaSuccess) return err;
+  if (E > 0) {
+    long long blocks = (E + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    csr_edge_positions_kernel<<<(int)blocks, 256, 0, stream>>>(E, perm, perm_s, inv, pos_s, 0);
+    csr_edge_positions_kernel<<<(int)blocks, 256, 0, stream>>>(E, perm, perm_s, inv, pos_s, 1);
+  }
+  CsrBwdParams p;
+  p.n = n;
+  p.weights = weights;
+  p.x = x;
+  p.row_ptr = row_ptr;
+  p.src = src;
+  p.row_ptr_s = row_ptr_s;
+  p.tgt_s = tgt_s;
+  p.pos_s = pos_s;
+  p.grad_q = grad_q;
+  p.rows = rows;
+  p.d_out = d_out;
+  p.dd = dd;
+  p.alpha = alpha;
+  p.draw = draw;
+  p.partials = partials;
+  const int smem_t = (((TW_COUNT + 3) & ~3) + 4 * kTileThreads * kHPad + kTileThreads * kW2Pad) * 4;
+  err = cudaFuncSetAttribute(csr_bwd_target_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_t);
+  if (err != cudaSuccess) return err;
+  csr_bwd_target_kernel<<<ctas, kTileThreads, smem_t, stream>>>(p);
+  const int smem_s = (2 * kTileThreads * kHPad + kTileThreads * kXPad + 2 * kTileThreads) * 4;
+  csr_bwd_source_kernel<<<ctas, kTileThreads, smem_s, stream>>>(p);
+  dqn_reduce_kernel<<<(SWARM_W_COUNT + 1 + 255) / 256, 256, 0, stream>>>(partials, ctas, 1.0f, grad_w, loss_dummy, nullptr, 0,
+                                                                         1, 0);
+  return cudaGetLastError();
+}
+
 // ---- launchers -------------------------------------------------------------------------------
 int dqn_maxdeg(const SwarmConfig& c) {
   return c.graph_mode == SWARM_GRAPH_KNN ? (c.n_agents + c.knn_k + 1) : c.n_agents;

@@ -27,12 +27,6 @@ from .gcn import GCN
 from .graph import Batch, Data, node_features, stack_observations
 
 
-def gatq_backward_csr(packed, x, row_ptr, src, grad_q):
-    raise NotImplementedError(
-        "autograd through GCN.forward on an arbitrary graph is not implemented; DQN gradients come from the fused "
-        "swarm_dqn_grad kernel (swarm_b200.dqn.DQNTrainer / ops.dqn_grad)")
-
-
 class GraphReplayBuffer:
     """train:25-48 on a device ring.  ``push`` takes what the reference pushes (graph, actions, rewards,
     next graph) or raw states; ``sample`` draws with Python's ``random.sample`` exactly like the reference."""

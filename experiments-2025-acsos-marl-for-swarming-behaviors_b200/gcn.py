@@ -4,8 +4,9 @@ Mirrors src/training/train_gcn_dqn.py:50-70 -- ``GCN(input_dim, hidden_dim, outp
 ``conv1 = GATConv(input_dim, hidden_dim, add_self_loops=False, bias=True)``, ``lin1``, ``lin2`` and
 ``forward(data)`` reading ``data.x`` / ``data.edge_index``.  Parameter names, shapes and initialisation
 (including the order and count of RNG draws) match torch_geometric 2.5.3 + torch so that
-the shipped ``data/models/*.pth`` load and seeded runs consume the generator identically.  The forward
-(and backward) arithmetic runs in libswarm_b200.so; there is no PyTorch implementation behind it.
+the shipped ``data/models/*.pth`` load and seeded runs consume the generator identically.  The forward and the
+backward arithmetic (``loss.backward()`` through ``GCN.forward`` for any graph) run in libswarm_b200.so; there is no
+PyTorch implementation behind it.
 """
 from __future__ import annotations
 
@@ -64,20 +65,22 @@ class GATConv(nn.Module):
 
 
 class _GatQFunction(torch.autograd.Function):
-    """packed weights f32[1673], x f32[n,7], CSR-by-target -> Q f32[n,9] through the CUDA kernels."""
+    """packed weights f32[1673], x f32[n,7], graph -> Q f32[n,9]; forward and backward run in the CUDA kernels
+    (swarm_gatq_forward_csr / swarm_gatq_backward_csr).  Gradients flow to the weights only (x is data)."""
 
     @staticmethod
-    def forward(ctx, packed, x, row_ptr, src):
+    def forward(ctx, packed, x, edge_index):
+        packed = packed.detach().contiguous()
+        row_ptr, src, perm = ops.csr_from_edges(edge_index, x.shape[0])
         q = ops.gatq_forward_csr(packed, x, row_ptr, src)
-        ctx.save_for_backward(packed, x, row_ptr, src)
+        ctx.save_for_backward(packed, x, edge_index, row_ptr, src, perm)
         return q
 
     @staticmethod
     def backward(ctx, grad_q):
-        packed, x, row_ptr, src = ctx.saved_tensors
-        from . import dqn
-        grad_w = dqn.gatq_backward_csr(packed, x, row_ptr, src, grad_q.contiguous())
-        return grad_w, None, None, None
+        packed, x, edge_index, row_ptr, src, perm = ctx.saved_tensors
+        grad_w = ops.gatq_backward_csr(packed, x, edge_index, grad_q.contiguous(), by_target=(row_ptr, src, perm))
+        return grad_w, None, None
 
 
 class GCN(nn.Module):
@@ -106,5 +109,6 @@ class GCN(nn.Module):
         if not x.is_cuda:
             raise _lib.SwarmError("GCN.forward runs on CUDA tensors only (swarm_b200 has no CPU fallback); "
                                   "move the model and the graph to a B200")
-        row_ptr, src, _ = ops.csr_from_edges(edge_index, x.shape[0])
-        return _GatQFunction.apply(self.packed_weights(), x.contiguous(), row_ptr, src)
+        if edge_index.dtype != torch.int64:
+            edge_index = edge_index.to(torch.int64)
+        return _GatQFunction.apply(self.packed_weights(), x.contiguous(), edge_index.contiguous())

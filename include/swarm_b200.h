@@ -157,6 +157,18 @@ int swarm_csr_from_edges(int32_t n_nodes, int64_t n_edges, const int64_t* edge_s
                          int32_t* row_ptr, int32_t* src, int32_t* perm, void* workspace, int64_t workspace_bytes,
                          void* stream);
 
+/* Backward pass of GCN.forward on an arbitrary graph (loss.backward() through the nn.Module, train_gcn_dqn.py:116-124
+ * when a script drives the module with torch autograd): grad_q float[n][9] -> grad_weights float[1673] (overwritten).
+ * The graph is given twice, grouped by target (row_ptr / src / perm, as for the forward) and grouped by source
+ * (row_ptr_s / tgt_s / perm_s = swarm_csr_from_edges with the two edge rows swapped); perm arrays map grouped
+ * positions to edge-list positions.  Gathers only, fixed summation order (bit-reproducible).
+ * workspace: swarm_gatq_backward_workspace_bytes(n, E). */
+int64_t swarm_gatq_backward_workspace_bytes(int32_t n_nodes, int64_t n_edges);
+int swarm_gatq_backward_csr(int32_t n_nodes, int64_t n_edges, const float* weights, const float* x,
+                            const int32_t* row_ptr, const int32_t* src, const int32_t* perm, const int32_t* row_ptr_s,
+                            const int32_t* tgt_s, const int32_t* perm_s, const float* grad_q, float* grad_weights,
+                            void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Device replay ring of whole-swarm transitions (GraphReplayBuffer, train_gcn_dqn.py:25-48, capacity 1e6 at
  * train:86).  Only the world state is stored (37 B per agent and transition); node features and graphs are
  * rebuilt from it on the fly. */

@@ -337,3 +337,103 @@ def test_rollout_reproduces_reference_goldens(exp, models, agents):
                 assert np.array_equal(mean_d.numpy(), gold["dist"][e]), "mean goal distance trace differs"
     print(f"{exp}: {exact}/{total} golden episodes reproduced bit-for-bit by the fused CUDA rollout")
     assert exact >= 0.9 * total
+
+
+def _ragged_batch(scenario, seed=0):
+    """Graphs of different sizes and kinds, duplicate edges, self loops and an isolated node."""
+    from oracle import swarm_oracle as so, batched_oracle as bo
+    xs, eis = [], []
+    g = torch.Generator().manual_seed(seed)
+    for n, kind in ((5, "knn"), (12, "complete"), (7, "knn"), (1, "complete"), (9, "complete"), (30, "knn")):
+        pos, vel = _random_states(scenario, 1, n, seed=n + seed)
+        x = bo.node_features(pos, vel)[0]
+        ei = so.graph_knn(x, min(5, n)) if kind == "knn" else so.graph_complete(n)
+        xs.append(x)
+        eis.append(ei)
+    xs.append(torch.randn(4, 7, generator=g))
+    eis.append(torch.tensor([[0, 1, 1, 3, 3], [1, 0, 0, 3, 3]]))     # duplicates, double self loop, node 2 isolated
+    return so.batch_graphs(xs, eis)
+
+
+@pytest.mark.parametrize("exp,scenario", [("GoTo", "go_to"), ("ObstacleAvoidance", "obstacle_avoidance")])
+def test_gcn_module_backward_generic_graph(exp, scenario):
+    """loss.backward() through GCN.forward on an arbitrary Batch: parameter gradients against torch autograd of the
+    oracle network (per tensor, relative to that tensor's largest gradient), bit-reproducible across calls."""
+    from oracle.dqn_oracle import OracleGCN
+    sb = _swarm()
+    params = load_params(exp, 3)
+    x_all, ei_all = _ragged_batch(scenario)
+    cot = torch.randn(x_all.shape[0], 9, generator=torch.Generator().manual_seed(1))
+    ref = OracleGCN(7, 32, 9)
+    ref.load_state_dict(params)
+    (ref(x_all, ei_all) * cot).sum().backward()
+    ref64 = OracleGCN(7, 32, 9).double()
+    ref64.load_state_dict({k: v.double() for k, v in params.items()})
+    (ref64(x_all.double(), ei_all) * cot.double()).sum().backward()
+
+    model = sb.GCN(7, 32, 9)
+    model.load_state_dict(params)
+    model = model.to(_dev())
+    data = sb.Data(x=x_all.to(_dev()), edge_index=ei_all.to(_dev()))
+    grads = []
+    for _ in range(2):
+        model.zero_grad()
+        (model(data) * cot.to(_dev())).sum().backward()
+        grads.append({k: p.grad.detach().clone() for k, p in model.named_parameters()})
+    for k in grads[0]:
+        assert torch.equal(grads[0][k], grads[1][k]), f"{k}: gradient differs between two identical calls"
+    for (name, p32), (_, p64) in zip(ref.named_parameters(), ref64.named_parameters()):
+        g64 = p64.grad.float()
+        got = grads[0][name].cpu().reshape(g64.shape)
+        scale = g64.abs().max().item()
+        err = (got - g64).abs().max().item()
+        err32 = (p32.grad - g64).abs().max().item()
+        assert err <= max(1e-5 * scale, 20 * err32), f"{name}: abs error {err:.3e} (float32 autograd {err32:.3e}, |g|max {scale:.3e})"
+
+
+def test_reference_style_train_step_on_the_module():
+    """The reference's train_step_dqn (train:116-126) written against the nn.Module API -- values.gather, TD target from
+    a target module, MSELoss, backward, clip_grad_norm_, torch.optim.Adam -- runs on swarm_b200.GCN and tracks the same
+    steps on the CPU oracle network."""
+    import torch.nn as nn
+    from oracle.dqn_oracle import OracleGCN
+    sb = _swarm()
+    params = load_params("ObstacleAvoidance", 5)
+    x, ei = _ragged_batch("obstacle_avoidance", seed=2)
+    x2, ei2 = _ragged_batch("obstacle_avoidance", seed=3)
+    n = x.shape[0]
+    g = torch.Generator().manual_seed(0)
+    actions = torch.randint(0, 9, (n,), generator=g)
+    rewards = torch.randn(n, generator=g)
+
+    def make(cls, dev):
+        m, t = cls(7, 32, 9), cls(7, 32, 9)
+        m.load_state_dict(params)
+        t.load_state_dict(load_params("ObstacleAvoidance", 6))
+        return m.to(dev), t.to(dev).eval()
+
+    def run(model, target, fwd, dev):
+        opt = torch.optim.Adam(model.parameters(), lr=0.001)
+        losses = []
+        for _ in range(5):
+            values = fwd(model, x.to(dev), ei.to(dev)).gather(1, actions.to(dev).unsqueeze(1))
+            with torch.no_grad():
+                nxt = fwd(target, x2.to(dev), ei2.to(dev)).max(dim=1)[0]
+            tgt = rewards.to(dev) + 0.99 * nxt
+            loss = nn.MSELoss()(values, tgt.unsqueeze(1))
+            opt.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+            opt.step()
+            losses.append(loss.item())
+        return losses, {k: v.detach().cpu() for k, v in model.state_dict().items()}
+
+    om, ot = make(OracleGCN, "cpu")
+    ref_losses, ref_sd = run(om, ot, lambda m, xx, ee: m(xx, ee), "cpu")
+    gm, gt = make(sb.GCN, _dev())
+    got_losses, got_sd = run(gm, gt, lambda m, xx, ee: m(sb.Data(x=xx, edge_index=ee)), _dev())
+    for a, b in zip(got_losses, ref_losses):
+        assert abs(a - b) <= 1e-4 * abs(b), (got_losses, ref_losses)
+    assert got_losses[-1] < got_losses[0]
+    for k in ref_sd:
+        assert torch.allclose(got_sd[k].reshape(ref_sd[k].shape), ref_sd[k], rtol=2e-4, atol=2e-5), k
