@@ -128,6 +128,51 @@ __device__ __forceinline__ void mma_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint3
   }
 }
 
+// D = A * B^T with A in TENSOR MEMORY (lane = row, one 32-bit column per k) and B in shared memory; 3xTF32 split as
+// above.  a_hi / a_lo are TMEM column addresses of the two halves; a k-step of 8 advances A by 8 columns.
+__device__ __forceinline__ void mma_tf32_tmem_a(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate ? 1u : 0u)
+      : "memory");
+}
+
+__device__ __forceinline__ void mma_3xtf32_tmem_a(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                                  int b_rows, int ksteps, uint32_t idesc) {
+  const uint32_t b_lbo = (uint32_t)b_rows * 16;
+  const uint64_t db_hi = make_desc(b_hi, b_lbo, 128), db_lo = make_desc(b_lo, b_lbo, 128);
+  const uint64_t b_step = (uint64_t)((2 * b_lbo) >> 4);
+  bool acc = false;
+#pragma unroll
+  for (int term = 0; term < 3; ++term) {
+    const uint32_t ta = (term == 0) ? a_lo : a_hi;         // lo*hi, hi*lo, hi*hi (small terms first)
+    const uint64_t db = (term == 1) ? db_lo : db_hi;
+#pragma unroll 4
+    for (int j = 0; j < ksteps; ++j) {
+      mma_tf32_tmem_a(tmem_d, ta + 8u * j, db + j * b_step, idesc, acc);
+      acc = true;
+    }
+  }
+}
+
+// this thread's row (TMEM lane) <- 32 / 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(

@@ -69,8 +69,6 @@ __global__ void __launch_bounds__(kTileThreads, TC ? 3 : ((MODE == MODE_GRAPH ||
   TileTcSmem ts;
   uint32_t tmem = 0, parity = 0;
   if (TC) {
-    ts.a = smem + L.tc_a;
-    ts.x = smem + L.tc_x;
     ts.w0 = smem + L.tc_w0;
     ts.w1 = smem + L.tc_w1;
     ts.w2 = smem + L.tc_w2;

@@ -132,7 +132,7 @@ inline float sq_threshold(float dmin) {
 
 // byte offsets of the dynamic shared memory regions
 struct TileLayout {
-  int w, st, h, asrc, wt, inl, deg, kv, ki, nbr, red, tc_a, tc_x, tc_w0, tc_w1, tc_w2, tc_vec, tc_bar, stage, total;
+  int w, st, h, asrc, wt, inl, deg, kv, ki, nbr, red, tc_w0, tc_w1, tc_w2, tc_vec, tc_bar, stage, total;
 };
 
 __host__ __device__ inline int tile_align16(int x) { return (x + 15) & ~15; }
@@ -145,9 +145,7 @@ __host__ __device__ inline TileLayout tile_layout(int mode, int threads, int n, 
   const bool q = (mode == MODE_ROLLOUT || mode == MODE_FORWARD);
   const bool knn = (graph_mode == SWARM_GRAPH_KNN) && (q || mode == MODE_GRAPH);
   tc = tc && q;
-  // tensor-core operand tiles first (128-byte aligned); the h tile aliases the A tiles in that mode
-  L.tc_a = off;   off = tile_align128(off + (tc ? 2 * 128 * 32 * 4 : 0));
-  L.tc_x = off;   off = tile_align128(off + (tc ? 2 * 128 * 8 * 4 : 0));
+  // tensor-core B operand tiles (weights) first (128-byte aligned); the A operand lives in tensor memory
   L.tc_w0 = off;  off = tile_align128(off + (tc ? 2 * 32 * 8 * 4 : 0));
   L.tc_w1 = off;  off = tile_align128(off + (tc ? 2 * 32 * 32 * 4 : 0));
   L.tc_w2 = off;  off = tile_align128(off + (tc ? 2 * 16 * 32 * 4 : 0));
@@ -155,23 +153,13 @@ __host__ __device__ inline TileLayout tile_layout(int mode, int threads, int n, 
   L.tc_bar = off; off = tile_align16(off + (tc ? 16 : 0));
   L.w = off;    off = tile_align16(off + ((q && !tc) ? TW_COUNT * 4 : 0));
   L.st = off;   off = tile_align16(off + 2 * threads * 16);
-  if (tc) {
-    L.h = L.tc_a;
-  } else {
-    L.h = off;  off = tile_align16(off + (q ? threads * kHPad * 4 : 0));
-  }
+  L.h = off;    off = tile_align16(off + (q ? threads * kHPad * 4 : 0));
   L.asrc = off; off = tile_align16(off + (q ? threads * 4 : 0));
   L.wt = off;   off = tile_align16(off + (q ? maxdeg * threads * 4 : 0));
   L.inl = off;  off = tile_align16(off + (q ? maxdeg * threads : 0));
   L.deg = off;  off = tile_align16(off + (q ? threads : 0));
-  if (tc && knn && n * threads * 5 <= 2 * 128 * 32 * 4) {
-    // the kNN distance / index rows live only inside tile_knn_rows, when the A tiles are idle: alias them
-    L.kv = L.tc_a;
-    L.ki = L.tc_a + n * threads * 4;
-  } else {
-    L.kv = off;   off = tile_align16(off + (knn ? n * threads * 4 : 0));
-    L.ki = off;   off = tile_align16(off + (knn ? n * threads : 0));
-  }
+  L.kv = off;   off = tile_align16(off + (knn ? n * threads * 4 : 0));
+  L.ki = off;   off = tile_align16(off + (knn ? n * threads : 0));
   L.nbr = off;  off = tile_align16(off + (knn ? k * threads : 0));
   L.red = off;  off = tile_align16(off + threads * 4);
   // MODE_GRAPH: the tile's edge lists are staged here and written out with coalesced stores (0 = does not fit)

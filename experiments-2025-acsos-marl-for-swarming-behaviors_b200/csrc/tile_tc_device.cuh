@@ -11,11 +11,12 @@ namespace swarm {
 
 // float offsets inside the small vector block
 enum { TV_ATT_S = 0, TV_ATT_D = 32, TV_B0 = 64, TV_B1 = 96, TV_B2 = 128, TV_COUNT = 144 };
-constexpr int kTmemCols = 64;     // D tiles: [0,32) projection / lin2, [32,64) lin1
+// TMEM columns: D tiles [0,32) projection / lin2 and [32,64) lin1; A operand (this CTA's 128 activation rows, written
+// by their owner threads with tcgen05.st) hi half [64,96), lo half [96,128)
+constexpr int kTmemCols = 128;
+constexpr uint32_t kTmemAHi = 64, kTmemALo = 96;
 
 struct TileTcSmem {
-  unsigned char* a;      // A tiles: hi at +0 (16 KB), lo at +16 KB; the h tile (g.sh) aliases the start
-  unsigned char* x;      // X tiles [128 x 8]: hi at +0 (4 KB), lo at +4 KB
   unsigned char* w0;     // [32 x 8]  hi +0 (1 KB), lo +1 KB
   unsigned char* w1;     // [32 x 32] hi +0 (4 KB), lo +4 KB
   unsigned char* w2;     // [16 x 32] hi +0 (2 KB), lo +2 KB
@@ -24,7 +25,6 @@ struct TileTcSmem {
   uint32_t* tmem_slot;
 };
 
-constexpr int kTcABytes = 2 * 128 * 32 * 4, kTcXBytes = 2 * 128 * 8 * 4;
 constexpr int kTcW0Bytes = 2 * 32 * 8 * 4, kTcW1Bytes = 2 * 32 * 32 * 4, kTcW2Bytes = 2 * 16 * 32 * 4;
 
 // global packed weights -> split (hi, lo) UMMA B tiles + bias / attention vectors.
@@ -96,31 +96,37 @@ __device__ __forceinline__ void stage_weights_tc(const float* __restrict__ gw, c
   }
 }
 
-// writes this thread's 32-vector as row `tid` of the A tiles (hi, lo)
-__device__ __forceinline__ void tc_store_a_row(const TileTcSmem& s, int tid, const float (&v)[32]) {
+// The A operand of the three contractions lives in TENSOR MEMORY: every thread splits its own activation row into
+// (hi, lo) and writes it to its TMEM lane with two tcgen05.st -- no shared-memory stores, no shared-memory operand
+// reads by the MMA (shared-memory bandwidth is the busiest resource of the rollout tick: l1tex 61 %).
+__device__ __forceinline__ void tc_store_a_row(uint32_t lane_addr, const float (&v)[32]) {
+  uint32_t hi[32], lo[32];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    float4 hi, lo;
-    tc::split4(make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]), hi, lo);
-    const int off = tc::tile_off(128, tid, c);
-    *reinterpret_cast<float4*>(s.a + off) = hi;
-    *reinterpret_cast<float4*>(s.a + kTcABytes / 2 + off) = lo;
+    float4 h4, l4;
+    tc::split4(make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]), h4, l4);
+    hi[4 * c + 0] = __float_as_uint(h4.x); hi[4 * c + 1] = __float_as_uint(h4.y);
+    hi[4 * c + 2] = __float_as_uint(h4.z); hi[4 * c + 3] = __float_as_uint(h4.w);
+    lo[4 * c + 0] = __float_as_uint(l4.x); lo[4 * c + 1] = __float_as_uint(l4.y);
+    lo[4 * c + 2] = __float_as_uint(l4.z); lo[4 * c + 3] = __float_as_uint(l4.w);
   }
+  tc::tmem_st32(lane_addr + kTmemAHi, hi);
+  tc::tmem_st32(lane_addr + kTmemALo, lo);
+  tc::tmem_wait_st();
 }
 
-// One UMMA round: every thread has written its operand row; barrier; one elected thread issues the 3xTF32 MMAs
-// and commits to the mbarrier; everybody waits for completion.  `parity` is the per-thread phase bit.
-__device__ __forceinline__ void tc_mma_round(const TileTcSmem& s, uint32_t tmem_d, const unsigned char* a_tile, int a_half,
-                                             const unsigned char* b_tile, int b_half, int b_rows, int ksteps,
-                                             uint32_t& parity) {
-  tc::fence_async_smem();
+// One UMMA round: every thread has written its operand row to TMEM; barrier; one elected thread issues the 3xTF32
+// MMAs and commits to the mbarrier; everybody waits for completion.  `parity` is the per-thread phase bit.
+__device__ __forceinline__ void tc_mma_round(const TileTcSmem& s, uint32_t tmem, uint32_t tmem_d, const unsigned char* b_tile,
+                                             int b_half, int b_rows, int ksteps, uint32_t& parity) {
   tc::fence_before_sync();
   __syncthreads();
   if ((threadIdx.x >> 5) == 0) {
     tc::fence_after_sync();
     if (tc::elect_one()) {
-      const uint32_t a = tc::smem_u32(a_tile), b = tc::smem_u32(b_tile);
-      tc::mma_3xtf32(tmem_d, a, a + a_half, b, b + b_half, b_rows, ksteps, tc::make_idesc_tf32(b_rows));
+      const uint32_t b = tc::smem_u32(b_tile);
+      tc::mma_3xtf32_tmem_a(tmem_d, tmem + kTmemAHi, tmem + kTmemALo, b, b + b_half, b_rows, ksteps,
+                            tc::make_idesc_tf32(b_rows));
       tc::mma_commit(s.bar);
     }
     __syncwarp();
@@ -130,24 +136,25 @@ __device__ __forceinline__ void tc_mma_round(const TileTcSmem& s, uint32_t tmem_
   tc::fence_after_sync();
 }
 
-// Full per-tick Q forward on the tensor cores.  Contains 5 block barriers.  All 128 threads must call it.
+// Full per-tick Q forward on the tensor cores.  Contains 4 block barriers.  All 128 threads must call it.
 __device__ __forceinline__ int tile_q_forward_tc(const TileGraphSmem& g, const TileTcSmem& s, const TileThread& t,
                                                  uint32_t tmem, const float (&x)[7], int deg, uint32_t& parity,
                                                  float (&q)[9]) {
   const uint32_t lane_addr = tmem + ((uint32_t)(t.tid & ~31) << 16);     // this warp's 32 TMEM lanes
   // ---- projection h = x W0^T (K padded 7 -> 8) ----
   {
-    float4 hi, lo;
-    tc::split4(make_float4(x[0], x[1], x[2], x[3]), hi, lo);
-    int off = tc::tile_off(128, t.tid, 0);
-    *reinterpret_cast<float4*>(s.x + off) = hi;
-    *reinterpret_cast<float4*>(s.x + kTcXBytes / 2 + off) = lo;
-    tc::split4(make_float4(x[4], x[5], x[6], 0.0f), hi, lo);
-    off = tc::tile_off(128, t.tid, 1);
-    *reinterpret_cast<float4*>(s.x + off) = hi;
-    *reinterpret_cast<float4*>(s.x + kTcXBytes / 2 + off) = lo;
+    float4 h0, l0, h1, l1;
+    tc::split4(make_float4(x[0], x[1], x[2], x[3]), h0, l0);
+    tc::split4(make_float4(x[4], x[5], x[6], 0.0f), h1, l1);
+    const uint32_t hi[8] = {__float_as_uint(h0.x), __float_as_uint(h0.y), __float_as_uint(h0.z), __float_as_uint(h0.w),
+                            __float_as_uint(h1.x), __float_as_uint(h1.y), __float_as_uint(h1.z), __float_as_uint(h1.w)};
+    const uint32_t lo[8] = {__float_as_uint(l0.x), __float_as_uint(l0.y), __float_as_uint(l0.z), __float_as_uint(l0.w),
+                            __float_as_uint(l1.x), __float_as_uint(l1.y), __float_as_uint(l1.z), __float_as_uint(l1.w)};
+    tc::tmem_st8(lane_addr + kTmemAHi, hi);
+    tc::tmem_st8(lane_addr + kTmemALo, lo);
+    tc::tmem_wait_st();
   }
-  tc_mma_round(s, tmem, s.x, kTcXBytes / 2, s.w0, kTcW0Bytes / 2, 32, 1, parity);
+  tc_mma_round(s, tmem, tmem, s.w0, kTcW0Bytes / 2, 32, 1, parity);
   float h[32];
   tc::tmem_ld32(lane_addr, h);
   // alpha_src = <h, att_src>, alpha_dst = <h, att_dst>: vector loads of the attention vectors, packed FFMA2 with the
@@ -173,7 +180,6 @@ __device__ __forceinline__ int tile_q_forward_tc(const TileGraphSmem& g, const T
   // ---- attention + aggregation (CUDA cores) ----
   float a1[32];
   tile_gat_attend<true>(g, t, deg, adst, a1);
-  __syncthreads();                 // the h tile aliases the A tiles: everyone is done gathering
   {
     // u = tanh(agg + b0) = 1 - 2 / (exp(2 (agg + b0)) + 1), two channels per packed instruction around the SFU ops
     const float4* b4 = reinterpret_cast<const float4*>(s.vec + TV_B0);
@@ -194,9 +200,9 @@ __device__ __forceinline__ int tile_q_forward_tc(const TileGraphSmem& g, const T
       }
     }
   }
-  tc_store_a_row(s, t.tid, a1);
+  tc_store_a_row(lane_addr, a1);
   // ---- lin1 + ReLU ----
-  tc_mma_round(s, tmem + 32, s.a, kTcABytes / 2, s.w1, kTcW1Bytes / 2, 32, 4, parity);
+  tc_mma_round(s, tmem, tmem + 32, s.w1, kTcW1Bytes / 2, 32, 4, parity);
   tc::tmem_ld32(lane_addr + 32, a1);
   {
     const float4* b4 = reinterpret_cast<const float4*>(s.vec + TV_B1);
@@ -209,9 +215,9 @@ __device__ __forceinline__ int tile_q_forward_tc(const TileGraphSmem& g, const T
       a1[4 * c4 + 2] = fmaxf(hi.x, 0.0f); a1[4 * c4 + 3] = fmaxf(hi.y, 0.0f);
     }
   }
-  tc_store_a_row(s, t.tid, a1);     // lin1 has completed (mbarrier), the A tiles are free again
+  tc_store_a_row(lane_addr, a1);    // lin1 has completed (mbarrier), the A columns are free again
   // ---- lin2 ----
-  tc_mma_round(s, tmem, s.a, kTcABytes / 2, s.w2, kTcW2Bytes / 2, 16, 4, parity);
+  tc_mma_round(s, tmem, tmem, s.w2, kTcW2Bytes / 2, 16, 4, parity);
   float qq[16];
   tc::tmem_ld16(lane_addr, qq);
   float best = 0.0f;
