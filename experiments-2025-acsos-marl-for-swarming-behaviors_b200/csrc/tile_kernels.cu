@@ -36,8 +36,12 @@ __device__ __forceinline__ void tile_world_step(const TileParams& p, const TileT
   integrate(s, fx, fy, c.dt, p.one_minus_drag);
 }
 
-template <int MODE, bool TC>
-__global__ void __launch_bounds__(kTileThreads, TC ? 3 : ((MODE == MODE_GRAPH || MODE == MODE_STEP) ? 8 : 4)) tile_kernel(const __grid_constant__ TileParams p) {
+// DENSE: register budget for four resident CTAs per SM (127 registers) instead of three (156).  The tensor-core modes
+// are built both ways: with more CTAs than 3 x 148 the fourth CTA per SM pays (+13 % at 65 536 envs), below that the
+// roomier allocation is the faster one (C2: 410 CTAs).
+template <int MODE, bool TC, bool DENSE>
+__global__ void __launch_bounds__(kTileThreads, (MODE == MODE_GRAPH || MODE == MODE_STEP) ? 8 : ((TC && !DENSE) ? 3 : 4))
+tile_kernel(const __grid_constant__ TileParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr bool kQ = (MODE == MODE_ROLLOUT || MODE == MODE_FORWARD);
   constexpr bool kStep = (MODE == MODE_ROLLOUT || MODE == MODE_STEP);
@@ -336,25 +340,32 @@ cudaError_t launch_replay_gather(const SwarmReplay& r, const int64_t* indices, i
 }
 
 // explicit instantiations + launcher
-template <int MODE, bool TC>
+template <int MODE, bool TC, bool DENSE>
 static cudaError_t launch_tile_impl(const TileParams& p, cudaStream_t stream) {
   const SwarmConfig& c = p.cfg;
   const TileLayout L = tile_layout(MODE, kTileThreads, c.n_agents, c.knn_k, p.maxdeg, c.graph_mode, TC);
   const int grid = (c.num_envs + p.epb - 1) / p.epb;
   if (L.total > 48 * 1024) {
-    cudaError_t err = cudaFuncSetAttribute(tile_kernel<MODE, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+    cudaError_t err = cudaFuncSetAttribute(tile_kernel<MODE, TC, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
     if (err != cudaSuccess) return err;
   }
-  tile_kernel<MODE, TC><<<grid, kTileThreads, L.total, stream>>>(p);
+  tile_kernel<MODE, TC, DENSE><<<grid, kTileThreads, L.total, stream>>>(p);
   return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t launch_tile_q(const TileParams& p, cudaStream_t stream) {
+  if (!p.use_tc) return launch_tile_impl<MODE, false, true>(p, stream);
+  const int grid = (p.cfg.num_envs + p.epb - 1) / p.epb;
+  return grid > 3 * 148 ? launch_tile_impl<MODE, true, true>(p, stream) : launch_tile_impl<MODE, true, false>(p, stream);
 }
 
 cudaError_t launch_tile(int mode, const TileParams& p, cudaStream_t stream) {
   switch (mode) {
-    case MODE_ROLLOUT: return p.use_tc ? launch_tile_impl<MODE_ROLLOUT, true>(p, stream) : launch_tile_impl<MODE_ROLLOUT, false>(p, stream);
-    case MODE_FORWARD: return p.use_tc ? launch_tile_impl<MODE_FORWARD, true>(p, stream) : launch_tile_impl<MODE_FORWARD, false>(p, stream);
-    case MODE_STEP: return launch_tile_impl<MODE_STEP, false>(p, stream);
-    case MODE_GRAPH: return launch_tile_impl<MODE_GRAPH, false>(p, stream);
+    case MODE_ROLLOUT: return launch_tile_q<MODE_ROLLOUT>(p, stream);
+    case MODE_FORWARD: return launch_tile_q<MODE_FORWARD>(p, stream);
+    case MODE_STEP: return launch_tile_impl<MODE_STEP, false, true>(p, stream);
+    case MODE_GRAPH: return launch_tile_impl<MODE_GRAPH, false, true>(p, stream);
     default: return cudaErrorInvalidValue;
   }
 }
