@@ -548,6 +548,9 @@ __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
   return v;
 }
 
+// PEERS: with the fused peer-memory all-reduce (its register arrays and system-scope loads would otherwise slow the
+// single-GPU kernel from 5.4 to 7.6 us)
+template <bool PEERS>
 __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
   __shared__ double swarp[8][8];            // [segment][warp] partial sums of squares
   __shared__ float s_coef, s_neg_step, s_bc2_sqrt;
@@ -573,12 +576,12 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
   for (int i = 0; i < kPer; ++i) {
     const int o = tid + 256 * i;
     const bool in = o < SWARM_W_COUNT;
-    g_[i] = (in || (o == SWARM_W_COUNT && p.peers.world_size > 1)) ? p.grad[o] : 0.0f;
+    g_[i] = (in || (PEERS && o == SWARM_W_COUNT)) ? p.grad[o] : 0.0f;
     m_[i] = in ? p.m[o] : 0.0f;
     v_[i] = in ? p.v[o] : 0.0f;
     w_[i] = in ? p.w[o] : 0.0f;
   }
-  if (p.ctl && p.peers.world_size > 1) {
+  if (PEERS && p.ctl) {
     // ---- one-shot all-reduce over NVLink peer memory ------------------------------------------------------
     // Every rank agrees on `updating` (same ring fill), so either all ranks exchange this tick or none does.
     const uint64_t epoch = (uint64_t)(p.ctl->tick + 1);
@@ -1142,7 +1145,8 @@ cudaError_t launch_adam_clip(float* w, const float* grad, float* m, float* v, lo
   p.bc2_sqrt = (float)sqrt(bc2);
   p.eps = (float)eps;
   p.max_norm = (float)max_norm;
-  adam_clip_kernel<<<1, 256, 0, stream>>>(p);
+  if (p.peers.world_size > 1) adam_clip_kernel<true><<<1, 256, 0, stream>>>(p);
+  else adam_clip_kernel<false><<<1, 256, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
