@@ -1,11 +1,11 @@
 // tc_device.cuh -- tcgen05 (5th-gen tensor core) building blocks for the dense contractions of the Q-network
 // (7->32 projection, 32->32 and 32->9 MLP layers).
 //
-// One CTA of 128 threads = 128 node rows = one UMMA tile: D[128 x N] (TMEM, fp32) = A[128 x K] (smem) * B[N x K]^T
-// (smem), kind::tf32, both operands K-major in the no-swizzle canonical layout (8-row x 16-byte core matrices; LBO =
-// byte stride between the 16-byte K chunks, SBO = byte stride between 8-row groups).  TMEM lane r holds row r, so
-// after tcgen05.ld (32x32b) thread r owns exactly its node's output vector -- the same "thread = agent" ownership as
-// the CUDA-core path.
+// One CTA of 128 threads = 128 node rows = one UMMA tile: D[128 x N] (TMEM, fp32) = A[128 x K] (TMEM, written by the
+// row owners with tcgen05.st) * B[N x K]^T (smem, K-major in the no-swizzle canonical layout: 8-row x 16-byte core
+// matrices; LBO = byte stride between the 16-byte K chunks, SBO = byte stride between 8-row groups), kind::tf32.
+// TMEM lane r holds row r, so after tcgen05.ld (32x32b) thread r owns exactly its node's output vector -- the same
+// "thread = agent" ownership as the CUDA-core path.
 //
 // Precision: float32 operands are split x = hi + lo with hi = round-to-nearest-TF32(x) and lo = x - hi (exact), and
 // the product is accumulated as lo*hi + hi*lo + hi*hi (small terms first).  Measured on B200 (scripts/tc_probe.cu):
@@ -94,42 +94,14 @@ __device__ __forceinline__ bool elect_one() {
   return e != 0;
 }
 
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, bool accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate ? 1u : 0u)
-      : "memory");
-}
-
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// D = A * B^T with the 3xTF32 split: a_hi / a_lo and b_hi / b_lo are the tile base addresses (shared window),
-// `ksteps` = K / 8, a_rows = 128, b_rows = N.  Issued by one elected thread.  The descriptors of one operand
-// differ only in the start-address field, so they are formed by adding to a base descriptor.
-__device__ __forceinline__ void mma_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                           int b_rows, int ksteps, uint32_t idesc) {
-  const uint32_t a_lbo = 128 * 16, b_lbo = (uint32_t)b_rows * 16;
-  const uint64_t da_hi = make_desc(a_hi, a_lbo, 128), da_lo = make_desc(a_lo, a_lbo, 128);
-  const uint64_t db_hi = make_desc(b_hi, b_lbo, 128), db_lo = make_desc(b_lo, b_lbo, 128);
-  const uint64_t a_step = (uint64_t)((2 * a_lbo) >> 4), b_step = (uint64_t)((2 * b_lbo) >> 4);
-  bool acc = false;
-#pragma unroll
-  for (int term = 0; term < 3; ++term) {
-    const uint64_t da = (term == 0) ? da_lo : da_hi;       // lo*hi, hi*lo, hi*hi (small terms first)
-    const uint64_t db = (term == 1) ? db_lo : db_hi;
-#pragma unroll 4
-    for (int j = 0; j < ksteps; ++j) {
-      mma_tf32(tmem_d, da + j * a_step, db + j * b_step, idesc, acc);
-      acc = true;
-    }
-  }
-}
-
-// D = A * B^T with A in TENSOR MEMORY (lane = row, one 32-bit column per k) and B in shared memory; 3xTF32 split as
-// above.  a_hi / a_lo are TMEM column addresses of the two halves; a k-step of 8 advances A by 8 columns.
+// D = A * B^T with A in TENSOR MEMORY (lane = row, one 32-bit column per k) and B in shared memory (b_hi / b_lo = tile
+// base addresses in the shared window, b_rows = N), 3xTF32 split: lo*hi + hi*lo + hi*hi, small terms first.  a_hi / a_lo
+// are TMEM column addresses of the two halves; a k-step of 8 advances A by 8 columns and B by two 16-byte K chunks.
+// Issued by one elected thread.
 __device__ __forceinline__ void mma_tf32_tmem_a(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, bool accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
