@@ -109,3 +109,44 @@ def test_replay_sample_indices_follow_python_random(sb):
     population = [object() for _ in range(57)]
     ref = random.sample(population, 32)
     assert [population.index(o) for o in ref] == ours
+
+
+def test_module_name_shim_exposes_the_vmas_and_pyg_surface():
+    """shim/: `vmas` / `torch_geometric` module names resolve to the swarm_b200 classes with vmas' constructor
+    signatures (no GPU needed to import or to build entities; worlds themselves are CUDA-only)."""
+    import importlib
+    import os
+    import sys
+    import pytest
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (os.path.join(root, "shim"), root):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    vmas = importlib.import_module("vmas")
+    core = importlib.import_module("vmas.simulator.core")
+    scenario = importlib.import_module("vmas.simulator.scenario")
+    utils = importlib.import_module("vmas.simulator.utils")
+    pyg_nn = importlib.import_module("torch_geometric.nn")
+    pyg_data = importlib.import_module("torch_geometric.data")
+    import swarm_b200 as sb
+    assert vmas.make_env is sb.make_env and scenario.BaseScenario is sb.BaseScenario
+    assert core.World is sb.World and core.Agent is sb.Agent and core.Landmark is sb.Landmark and core.Sphere is sb.Sphere
+    assert pyg_nn.GATConv is sb.GATConv and pyg_data.Data is sb.Data and pyg_data.Batch is sb.Batch
+    assert utils.Color.GREEN is sb.Color.GREEN
+    # entity constructors as the reference scenario files call them (oa:29-56)
+    goal = core.Landmark(name="goal", collide=False, color=utils.Color.BLACK)
+    agent = core.Agent(name="agent0", collide=True, color=utils.Color.GREEN, render_action=True)
+    assert goal.shape.radius == 0.05 and agent.shape.radius == 0.05 and agent.movable and not goal.movable
+    agent.pos_rew = torch.zeros(1)                      # scenarios hang their own attributes on entities
+    with pytest.raises(AssertionError):
+        core.Sphere(radius=0.0)
+    with pytest.raises(NotImplementedError):
+        core.Agent(name="a", u_multiplier=2.0)
+    with pytest.raises(sb.SwarmError, match="CUDA"):
+        core.World(1, "cpu")
+    # the built-in scenarios are BaseScenario subclasses with the reference's method set
+    for cls in (sb.GoToPositionScenario, sb.ObstacleAvoidanceScenario):
+        for m in ("make_world", "reset_world_at", "observation", "reward", "done", "info", "average_distance_to_goal",
+                  "average_distance_to_obstacles", "obstacles_hits"):
+            assert callable(getattr(cls, m)), (cls.__name__, m)
