@@ -20,6 +20,9 @@ cudaError_t launch_reset_random(const SwarmConfig& c, const SwarmResetSpec& sp, 
 cudaError_t launch_episode_end(const SwarmConfig& c, SwarmTrainCtl* ctl, float* returns, int32_t* hits, const float* loss,
                                float* stats, long long max_episodes, double eps0, double decay, double min_eps,
                                cudaStream_t stream);
+bool gatq_knn_large_fits(int N, int K);
+cudaError_t launch_gatq_knn_large(const SwarmConfig& c, const float* weights, const float* state, const int32_t* nbr,
+                                  float* q, int32_t* actions, cudaStream_t stream);
 long long csr_workspace_bytes(int n, long long E);
 cudaError_t launch_csr_from_edges(int n, long long E, const int64_t* edge_src, const int64_t* edge_dst, int32_t* row_ptr,
                                   int32_t* src, int32_t* perm, void* workspace, long long workspace_bytes,
@@ -253,6 +256,19 @@ int swarm_gatq_forward_csr(int32_t n_nodes, const float* weights, const float* x
   float* rows = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
   return check_cuda(launch_gatq_csr(n_nodes, weights, x, row_ptr, src, q, actions, rows, (cudaStream_t)stream),
                     "swarm_gatq_forward_csr");
+}
+
+int swarm_gatq_forward_knn_large(const SwarmConfig* cfg, const float* weights, const float* state,
+                                 const int32_t* neighbours, float* q, int32_t* actions, void* stream) {
+  if (int rc = validate(cfg, true, true)) return rc;
+  if (cfg->graph_mode != SWARM_GRAPH_KNN) return fail(SWARM_ERR_INVALID_ARG, "cfg->graph_mode must be SWARM_GRAPH_KNN");
+  if (!weights || !state || !neighbours) return fail(SWARM_ERR_INVALID_ARG, "weights/state/neighbours is NULL");
+  if (!q && !actions) return fail(SWARM_ERR_INVALID_ARG, "no output requested");
+  if (!gatq_knn_large_fits(cfg->n_agents, cfg->knn_k))
+    return fail(SWARM_ERR_UNSUPPORTED, "the env does not fit shared memory: use swarm_graph_build + swarm_csr_from_edges + "
+                                       "swarm_gatq_forward_csr");
+  return check_cuda(launch_gatq_knn_large(*cfg, weights, state, neighbours, q, actions, (cudaStream_t)stream),
+                    "swarm_gatq_forward_knn_large");
 }
 
 int64_t swarm_gatq_backward_workspace_bytes(int32_t n_nodes, int64_t n_edges) {

@@ -13,7 +13,7 @@
 //   complete_edges_kernel   train_gcn_dqn.py:94-110 edge list (closed form)
 // The Q-network then runs through the generic CSR path (csr_kernels.cu).
 #include "knn_select.h"
-#include "tile_kernels.cuh"
+#include "gatq_device.cuh"
 
 namespace swarm {
 
@@ -234,6 +234,174 @@ __global__ void __launch_bounds__(kLargeThreads) complete_edges_kernel(int N, in
     r0[e + 1] = j; r1[e + 1] = i;
   }
   if (i == 0 && threadIdx.x == 0) { r0[E - 1] = 0; r1[E - 1] = 0; }
+}
+
+// ---- fused Q forward for large kNN swarms ---------------------------------------------------------------------
+// GCN.forward (train_gcn_dqn.py:59-70) on the symmetrised kNN graph of simulator.py:9-26 straight from the topk table,
+// one CTA per env, everything of the env in shared memory: the projected features (N x 32 floats), the table and its
+// TRANSPOSE.  The in-edges of node i in edge-list order are: rows ii < i that list i (at most one edge each, topk rows
+// hold distinct indices), then i's own row (per slot (i -> i) if a == i, then (a -> i)), then rows ii > i, and the
+// trailing (0,0) for node 0.  "Rows that list i" is the transposed table: counted and filled with shared-memory
+// atomics, then each (short) list is sorted by row index, which makes the order -- and therefore every sum --
+// deterministic and equal to the generic path's (edge list -> stable sort by target -> CSR kernels), whose per-tick
+// edge export (164 KB per env), int64 glue and radix sort this kernel replaces.
+constexpr int kQLThreads = 512;
+
+struct LargeQParams {
+  SwarmConfig cfg;
+  const float4* state;
+  const int32_t* nbr;        // [B][N][K]
+  const float* weights;
+  float* q_out;              // [B*N][9] or nullptr
+  int32_t* act_out;          // [B*N] or nullptr
+};
+
+__host__ __device__ inline size_t large_q_smem_bytes(int N, int K) {
+  size_t b = (size_t)((TW_COUNT + 3) & ~3) * 4;      // weights
+  b += (size_t)N * 32 * 4;                           // h rows
+  b += (size_t)N * 2 * 4;                            // alpha_src, alpha_dst
+  b += (size_t)(N + 1) * 4 * 2;                      // list offsets, fill cursors
+  b += (size_t)N * K * 2 * 2;                        // table and transposed lists (uint16)
+  return b + 64;
+}
+
+__global__ void __launch_bounds__(kQLThreads, 1) gatq_knn_large_kernel(const __grid_constant__ LargeQParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SwarmConfig& c = p.cfg;
+  const int N = c.n_agents, K = c.knn_k;
+  const int tid = threadIdx.x;
+  const long long env = blockIdx.x;
+  float* sw = reinterpret_cast<float*>(smem_raw);
+  float* sh = sw + ((TW_COUNT + 3) & ~3);
+  float* sas = sh + (size_t)N * 32;
+  float* sad = sas + N;
+  int* roff = reinterpret_cast<int*>(sad + N);           // [N + 1]
+  int* rcur = roff + (N + 1);                            // [N + 1]
+  uint16_t* tab = reinterpret_cast<uint16_t*>(rcur + (N + 1));
+  uint16_t* rev = tab + (size_t)N * K;
+  __shared__ int warp_tot[kQLThreads / 32];
+
+  stage_weights(p.weights, sw, tid, kQLThreads);
+  const int32_t* nbr = p.nbr + env * N * K;
+  for (int e = tid; e < N * K; e += kQLThreads) tab[e] = (uint16_t)nbr[e];
+  for (int i = tid; i <= N; i += kQLThreads) rcur[i] = 0;
+  __syncthreads();
+  // in-degree from other rows
+  for (int e = tid; e < N * K; e += kQLThreads) {
+    const int ii = e / K, a = tab[e];
+    if (a != ii) atomicAdd(&rcur[a], 1);
+  }
+  __syncthreads();
+  // exclusive scan of rcur[0..N) -> roff (every thread owns a contiguous chunk)
+  {
+    const int per = (N + kQLThreads - 1) / kQLThreads;
+    const int b0 = tid * per;
+    int local = 0;
+    for (int k = 0; k < per; ++k) local += (b0 + k < N) ? rcur[b0 + k] : 0;
+    int incl = local;
+#pragma unroll
+    for (int sft = 1; sft < 32; sft <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, sft);
+      if ((tid & 31) >= sft) incl += v;
+    }
+    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < (tid >> 5); ++w) base += warp_tot[w];
+    int run = base + incl - local;
+    for (int k = 0; k < per; ++k) {
+      if (b0 + k < N) {
+        const int cnt = rcur[b0 + k];
+        roff[b0 + k] = run;
+        run += cnt;
+      }
+    }
+    if (tid == kQLThreads - 1) roff[N] = base + incl;
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += kQLThreads) rcur[i] = 0;
+  __syncthreads();
+  for (int e = tid; e < N * K; e += kQLThreads) {
+    const int ii = e / K, a = tab[e];
+    if (a != ii) rev[roff[a] + atomicAdd(&rcur[a], 1)] = (uint16_t)ii;
+  }
+  __syncthreads();
+  // sort every list by row index (insertion sort; the lists hold ~K entries) and project the node features
+  for (int i = tid; i < N; i += kQLThreads) {
+    const int b = roff[i], e = roff[i + 1];
+    for (int x = b + 1; x < e; ++x) {
+      const uint16_t v = rev[x];
+      int y = x - 1;
+      while (y >= b && rev[y] > v) { rev[y + 1] = rev[y]; --y; }
+      rev[y + 1] = v;
+    }
+    const float4 st = p.state[env * N + i];
+    const float xi[7] = {st.x, st.y, st.z, st.w, c.goal_x, c.goal_y, (float)i};
+    float h[32], asrc, adst;
+    gat_project(xi, sw, h, asrc, adst);
+    float4* r = reinterpret_cast<float4*>(sh + (size_t)i * 32);
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) r[c4] = make_float4(h[4 * c4], h[4 * c4 + 1], h[4 * c4 + 2], h[4 * c4 + 3]);
+    sas[i] = asrc;
+    sad[i] = adst;
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += kQLThreads) {
+    const float adst = sad[i];
+    const int b = roff[i], e = roff[i + 1];
+    const uint16_t* own = tab + (size_t)i * K;
+    int split = b;                                    // first list entry with row index > i
+    while (split < e && rev[split] < i) ++split;
+    // the same three sweeps as csr_aggregate_kernel, over the in-edges in edge-list order
+    auto for_each_source = [&](auto&& fn) {
+      for (int x = b; x < split; ++x) fn((int)rev[x]);
+      for (int r = 0; r < K; ++r) {
+        const int a = own[r];
+        if (a == i) fn(i);
+        fn(a);
+      }
+      for (int x = split; x < e; ++x) fn((int)rev[x]);
+      if (i == 0) fn(0);
+    };
+    float m = -INFINITY;
+    for_each_source([&](int j) { m = fmaxf(m, gat_logit(sas[j], adst)); });
+    float den = 0.0f;
+    for_each_source([&](int j) { den = __fadd_rn(den, expf(__fsub_rn(gat_logit(sas[j], adst), m))); });
+    den = __fadd_rn(den, 1e-16f);
+    float a1[32];
+#pragma unroll
+    for (int cc = 0; cc < 32; ++cc) a1[cc] = 0.0f;
+    for_each_source([&](int j) {
+      const float w = expf(__fsub_rn(gat_logit(sas[j], adst), m));
+      gat_accumulate(a1, __fdiv_rn(w, den), reinterpret_cast<const float4*>(sh + (size_t)j * 32));
+    });
+    float q[9];
+    const int action = gat_head(a1, sw, q);
+    const long long g = env * N + i;
+    if (p.q_out) {
+#pragma unroll
+      for (int a = 0; a < 9; ++a) p.q_out[g * 9 + a] = q[a];
+    }
+    if (p.act_out) p.act_out[g] = action;
+  }
+}
+
+bool gatq_knn_large_fits(int N, int K) { return N <= 65535 && large_q_smem_bytes(N, K) <= 227 * 1024; }
+
+cudaError_t launch_gatq_knn_large(const SwarmConfig& c, const float* weights, const float* state, const int32_t* nbr,
+                                  float* q, int32_t* actions, cudaStream_t stream) {
+  LargeQParams p;
+  p.cfg = c;
+  p.state = reinterpret_cast<const float4*>(state);
+  p.nbr = nbr;
+  p.weights = weights;
+  p.q_out = q;
+  p.act_out = actions;
+  const size_t smem = large_q_smem_bytes(c.n_agents, c.knn_k);
+  cudaError_t err = cudaFuncSetAttribute(gatq_knn_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  gatq_knn_large_kernel<<<c.num_envs, kQLThreads, smem, stream>>>(p);
+  return cudaGetLastError();
 }
 
 // ---- launchers ------------------------------------------------------------------------------

@@ -402,6 +402,23 @@ def gatq_forward_csr(weights: torch.Tensor, x: torch.Tensor, row_ptr: torch.Tens
     return q if want_q else act
 
 
+def gatq_forward_knn_large(cfg: SwarmConfig, weights: torch.Tensor, state: torch.Tensor, neighbours: torch.Tensor,
+                           want_q: bool = True, want_actions: bool = False):
+    """GCN.forward on the kNN graph of a large swarm straight from the topk table (one CTA per env, no edge list)."""
+    B, N = cfg.num_envs, cfg.n_agents
+    _expect(state, torch.float32, B * N * 4, "state")
+    _expect(weights, torch.float32, _lib.W_COUNT, "weights")
+    _expect(neighbours, torch.int32, B * N * cfg.knn_k, "neighbours")
+    dev = state.device
+    q = torch.empty(B, N, 9, dtype=torch.float32, device=dev) if want_q else None
+    act = torch.empty(B, N, dtype=torch.int32, device=dev) if want_actions else None
+    check(lib().swarm_gatq_forward_knn_large(C.byref(cfg), ptr(weights), ptr(state), ptr(neighbours), ptr(q), ptr(act),
+                                             stream_ptr(dev)))
+    if want_q and want_actions:
+        return q, act
+    return q if want_q else act
+
+
 def gatq_backward_csr(weights: torch.Tensor, x: torch.Tensor, edge_index: torch.Tensor, grad_q: torch.Tensor,
                       by_target: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
     """Gradient of GCN.forward w.r.t. the packed weights for an arbitrary graph: x f32[n,7], edge_index int64[2,E],
@@ -425,7 +442,7 @@ def gatq_backward_csr(weights: torch.Tensor, x: torch.Tensor, edge_index: torch.
 
 def rollout_large(cfg: SwarmConfig, weights: torch.Tensor, state: torch.Tensor, ticks: int,
                   returns: Optional[torch.Tensor] = None, hits: Optional[torch.Tensor] = None,
-                  trace_state: bool = False) -> Dict[str, torch.Tensor]:
+                  trace_state: bool = False, fused: bool = True) -> Dict[str, torch.Tensor]:
     """Greedy rollout for large swarms (n_agents > 128): per tick graph_build -> CSR grouping -> generic GAT-Q
     forward (argmax) -> world step, all on the device; the per-tick glue (node features, edge offsets, reward
     accumulation) is tensor plumbing.  In place on ``state``."""
@@ -440,7 +457,19 @@ def rollout_large(cfg: SwarmConfig, weights: torch.Tensor, state: torch.Tensor, 
     offs = (torch.arange(B, device=dev, dtype=torch.int64) * N).view(B, 1, 1)
     trace = []
     static_csr = None
+    fused_knn = cfg.graph_mode == _lib.GRAPH_KNN and N * (144 + 4 * cfg.knn_k) + 8192 <= 227 * 1024 and fused
+    nbr = torch.empty(B, N, cfg.knn_k, dtype=torch.int32, device=dev) if fused_knn else None
     for _ in range(ticks):
+        if fused_knn:
+            # topk table only (no edge list), then the per-env fused forward
+            check(lib().swarm_graph_build(C.byref(cfg), ptr(state), None, ptr(nbr), stream_ptr(dev)))
+            act = gatq_forward_knn_large(cfg, weights, state, nbr, want_q=False, want_actions=True)
+            out = sim_step(cfg, state, act, state_out=state, want_obs=False)
+            returns += out["rewards"]
+            hits += ((out["flags"] & _lib.FLAG_HIT) != 0).sum(dim=1, dtype=torch.int32)
+            if trace_state:
+                trace.append(state.clone())
+            continue
         if cfg.graph_mode == _lib.GRAPH_COMPLETE and static_csr is not None:
             row_ptr, src = static_csr
         else:

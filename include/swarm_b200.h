@@ -157,6 +157,14 @@ int swarm_csr_from_edges(int32_t n_nodes, int64_t n_edges, const int64_t* edge_s
                          int32_t* row_ptr, int32_t* src, int32_t* perm, void* workspace, int64_t workspace_bytes,
                          void* stream);
 
+/* GCN.forward on the symmetrised kNN graph of large swarms (n_agents > 128) straight from the topk table that
+ * swarm_graph_build returns in `neighbours` (int32[B][N][k]): one CTA per env builds the in-edge lists in shared memory
+ * (same edge-list order as swarm_graph_build + swarm_csr_from_edges + swarm_gatq_forward_csr, same Q bit for bit) without
+ * materialising the edge list.  Needs N * (144 + 4k) + 7.4 K bytes of shared memory (n_agents <= ~1 200 for k = 10); larger swarms
+ * use the generic CSR path.  q float[B*N][9] and actions int32[B*N] are optional. */
+int swarm_gatq_forward_knn_large(const SwarmConfig* cfg, const float* weights, const float* state,
+                                 const int32_t* neighbours, float* q, int32_t* actions, void* stream);
+
 /* Backward pass of GCN.forward on an arbitrary graph (loss.backward() through the nn.Module, train_gcn_dqn.py:116-124
  * when a script drives the module with torch autograd): grad_q float[n][9] -> grad_weights float[1673] (overwritten).
  * The graph is given twice, grouped by target (row_ptr / src / perm, as for the forward) and grouped by source

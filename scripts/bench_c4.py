@@ -32,11 +32,25 @@ for t in range(5):
     x = timed('node features (torch glue)', lambda: torch.cat([state, goal, ids], dim=2).reshape(B * N, 7))
     act = timed('gatq_forward_csr', lambda: ops.gatq_forward_csr(w, x, row_ptr, src, want_q=False, want_actions=True).view(B, N))
     timed('sim_step', lambda: ops.sim_step(cfg, state, act, state_out=state, want_obs=False))
+# the fused large-swarm path: topk table only + per-env forward from the table
+import ctypes as C
+L = sb._lib
+nbr = torch.empty(B, N, K, dtype=torch.int32, device=dev)
+state = ops.reset_grid(cfg, centers)
+for t in range(5):
+    timed('fused: graph_build (topk table only)', lambda: L.check(L.lib().swarm_graph_build(C.byref(cfg), L.ptr(state), None, L.ptr(nbr), L.stream_ptr(dev))))
+    act = timed('fused: gatq_forward_knn_large', lambda: ops.gatq_forward_knn_large(cfg, w, state, nbr, want_q=False, want_actions=True))
+    timed('fused: sim_step', lambda: ops.sim_step(cfg, state, act, state_out=state, want_obs=False))
 for k_ in stages: stages[k_] /= 5
 state = ops.reset_grid(cfg, centers)
 torch.cuda.synchronize(); a, b = ev(), ev(); a.record()
 ops.rollout_large(cfg, w, state, T)
 b.record(); torch.cuda.synchronize()
 ms = a.elapsed_time(b)
+state = ops.reset_grid(cfg, centers)
+torch.cuda.synchronize(); a2, b2 = ev(), ev(); a2.record()
+ops.rollout_large(cfg, w, state, T, fused=False)
+b2.record(); torch.cuda.synchronize()
+stages['generic path (edge list + CSR), ms per tick'] = a2.elapsed_time(b2) / T
 print(json.dumps({'config': 'C4 OA N=1024 B=1024 kNN k=10 greedy', 'ticks': T, 'ms_per_tick': ms / T,
                   'agent_steps_per_s': B * N * T / (ms * 1e-3), 'stage_ms_per_tick': stages}))

@@ -157,3 +157,40 @@ def test_large_rollout_against_oracle():
         same = (st[..., :2] == p).all(dim=-1)
         assert same.float().mean().item() >= 0.999, f"tick {t}: {int((~same).sum())} agents deviate (argmax flips)"
     assert torch.allclose(out["returns"].cpu(), ret, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("N,k,B,spread", [(1024, 10, 3, 1.0), (640, 10, 3, 0.4), (129, 2, 5, 1.0), (1100, 8, 2, 0.7)])
+def test_large_fused_knn_forward_equals_csr_path(N, k, B, spread):
+    """swarm_gatq_forward_knn_large (per-env in-edge lists from the transposed topk table) gives the same Q, bit for
+    bit, as edge list -> stable sort by target -> CSR kernels, on exact grids (ties), squeezed and jittered swarms."""
+    import swarm_b200 as sb
+    from swarm_b200 import ops
+    dev = _dev()
+    pos, vel = _states("obstacle_avoidance", B, N, seed=N + k, spread=spread)
+    pos[0] = pos[0].round(decimals=2)                               # an env full of exact distance ties
+    state = torch.cat([pos, vel], 2).contiguous().to(dev)
+    w = sb.pack_weights(load_params("ObstacleAvoidance", 1), dev)
+    cfg = ops.make_config(sb._lib.SCENARIO_OBSTACLE_AVOIDANCE, B, N, sb._lib.GRAPH_KNN, k)
+    edges, nbr = ops.graph_build(cfg, state, want_neighbours=True)
+    offs = (torch.arange(B, device=dev, dtype=torch.int64) * N).view(B, 1, 1)
+    ei = (edges.to(torch.int64) + offs).permute(1, 0, 2).reshape(2, -1).contiguous()
+    row_ptr, src, _ = ops.csr_from_edges(ei, B * N)
+    ids = torch.arange(N, device=dev, dtype=torch.float32).view(1, N, 1).expand(B, N, 1)
+    goal = torch.tensor([cfg.goal_x, cfg.goal_y], device=dev).view(1, 1, 2).expand(B, N, 2)
+    x = torch.cat([state, goal, ids], dim=2).reshape(B * N, 7)
+    q_ref, a_ref = ops.gatq_forward_csr(w, x, row_ptr, src, want_q=True, want_actions=True)
+    q, a = ops.gatq_forward_knn_large(cfg, w, state, nbr, want_q=True, want_actions=True)
+    assert torch.equal(q.view(B * N, 9), q_ref) and torch.equal(a.view(-1), a_ref)
+    # and the rollout built on it equals the generic one
+    r1 = ops.rollout_large(cfg, w, state.clone(), 2, fused=True)
+    r2 = ops.rollout_large(cfg, w, state.clone(), 2, fused=False)
+    assert torch.equal(r1["state"], r2["state"]) and torch.equal(r1["returns"], r2["returns"])
+
+
+def test_large_fused_knn_forward_limits():
+    import swarm_b200 as sb
+    from swarm_b200 import ops
+    cfg = ops.make_config(sb._lib.SCENARIO_GOTO, 1, 4096, sb._lib.GRAPH_KNN, 10)
+    with pytest.raises(sb.SwarmError, match="shared memory"):
+        ops.gatq_forward_knn_large(cfg, torch.zeros(1673, device=_dev()), torch.zeros(1, 4096, 4, device=_dev()),
+                                   torch.zeros(1, 4096, 10, dtype=torch.int32, device=_dev()))
