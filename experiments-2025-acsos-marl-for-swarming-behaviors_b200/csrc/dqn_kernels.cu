@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
       if (tid < p.peers.world_size && tid != p.peers.rank) {
         const uint64_t* f = p.peers.flags[tid] + par;
         bool ok = false;
-        for (long long it = 0; it < (1ll << 31) && !ok; ++it) ok = ld_acquire_sys(f) >= epoch;
+        for (long long it = 0; it < (1ll << 25) && !ok; ++it) ok = ld_acquire_sys(f) >= epoch;   // ~1 min of polls
         if (!ok) __trap();                    // a peer never arrived: fail loudly instead of hanging the GPU
       }
       __syncthreads();
