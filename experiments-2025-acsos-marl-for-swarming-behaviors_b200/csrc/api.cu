@@ -28,13 +28,13 @@ cudaError_t launch_csr_from_edges(int n, long long E, const int64_t* edge_src, c
                                   int32_t* src, int32_t* perm, void* workspace, long long workspace_bytes,
                                   cudaStream_t stream);
 cudaError_t launch_gatq_csr(int n, const float* weights, const float* x, const int32_t* row_ptr, const int32_t* src,
-                            float* q, int32_t* actions, float* rows, cudaStream_t stream);
+                            float* q, int32_t* actions, float* rows, cudaStream_t stream, bool conv_only = false);
 long long gatq_workspace_bytes(int n);
 long long gatq_backward_workspace_bytes(int n, long long E);
 cudaError_t launch_gatq_backward_csr(int n, long long E, const float* weights, const float* x, const int32_t* row_ptr,
                                      const int32_t* src, const int32_t* perm, const int32_t* row_ptr_s,
                                      const int32_t* tgt_s, const int32_t* perm_s, const float* grad_q, float* grad_w,
-                                     void* workspace, cudaStream_t stream);
+                                     void* workspace, cudaStream_t stream, bool conv_only = false);
 cudaError_t launch_replay_push(const SwarmReplay& r, long long cursor, int B, int N, const float* state,
                                const int32_t* actions, const float* rewards, const float* next_state,
                                cudaStream_t stream);
@@ -271,6 +271,33 @@ int swarm_gatq_forward_knn_large(const SwarmConfig* cfg, const float* weights, c
                     "swarm_gatq_forward_knn_large");
 }
 
+int swarm_gatconv_forward_csr(int32_t n_nodes, const float* weights, const float* x, const int32_t* row_ptr,
+                              const int32_t* src, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (n_nodes < 0) return fail(SWARM_ERR_INVALID_ARG, "n_nodes must be >= 0");
+  if (n_nodes == 0) return SWARM_OK;
+  if (!weights || !x || !row_ptr || !out || !workspace) return fail(SWARM_ERR_INVALID_ARG, "NULL argument");
+  if (workspace_bytes < gatq_workspace_bytes(n_nodes)) return fail(SWARM_ERR_INVALID_ARG, "workspace too small");
+  float* rows = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  return check_cuda(launch_gatq_csr(n_nodes, weights, x, row_ptr, src, out, nullptr, rows, (cudaStream_t)stream, true),
+                    "swarm_gatconv_forward_csr");
+}
+
+int swarm_gatconv_backward_csr(int32_t n_nodes, int64_t n_edges, const float* weights, const float* x,
+                               const int32_t* row_ptr, const int32_t* src, const int32_t* perm, const int32_t* row_ptr_s,
+                               const int32_t* tgt_s, const int32_t* perm_s, const float* grad_out, float* grad_weights,
+                               void* workspace, int64_t workspace_bytes, void* stream) {
+  if (n_nodes <= 0 || n_edges < 0) return fail(SWARM_ERR_INVALID_ARG, "n_nodes must be > 0 and n_edges >= 0");
+  if (n_edges >= (1LL << 31)) return fail(SWARM_ERR_UNSUPPORTED, "more than 2^31 - 1 edges");
+  if (!weights || !x || !row_ptr || !row_ptr_s || !grad_out || !grad_weights || !workspace)
+    return fail(SWARM_ERR_INVALID_ARG, "NULL argument");
+  if (n_edges > 0 && (!src || !perm || !tgt_s || !perm_s)) return fail(SWARM_ERR_INVALID_ARG, "NULL edge array");
+  if (workspace_bytes < gatq_backward_workspace_bytes(n_nodes, n_edges))
+    return fail(SWARM_ERR_INVALID_ARG, "workspace too small");
+  return check_cuda(launch_gatq_backward_csr(n_nodes, n_edges, weights, x, row_ptr, src, perm, row_ptr_s, tgt_s, perm_s,
+                                             grad_out, grad_weights, workspace, (cudaStream_t)stream, true),
+                    "swarm_gatconv_backward_csr");
+}
+
 int64_t swarm_gatq_backward_workspace_bytes(int32_t n_nodes, int64_t n_edges) {
   if (n_nodes <= 0 || n_edges < 0) return 0;
   return gatq_backward_workspace_bytes(n_nodes, n_edges);
@@ -302,8 +329,8 @@ int swarm_csr_from_edges(int32_t n_nodes, int64_t n_edges, const int64_t* edge_s
                          void* stream) {
   if (n_nodes <= 0 || n_edges < 0) return fail(SWARM_ERR_INVALID_ARG, "n_nodes must be > 0 and n_edges >= 0");
   if (n_edges >= (1LL << 31)) return fail(SWARM_ERR_UNSUPPORTED, "more than 2^31 - 1 edges");
-  if (!edge_src || !edge_dst || !row_ptr || !src || !perm || !workspace)
-    return fail(SWARM_ERR_INVALID_ARG, "NULL argument");
+  if (!row_ptr || !workspace) return fail(SWARM_ERR_INVALID_ARG, "NULL argument");
+  if (n_edges > 0 && (!edge_src || !edge_dst || !src || !perm)) return fail(SWARM_ERR_INVALID_ARG, "NULL edge array");
   if (workspace_bytes < csr_workspace_bytes(n_nodes, n_edges)) return fail(SWARM_ERR_INVALID_ARG, "workspace too small");
   return check_cuda(launch_csr_from_edges(n_nodes, n_edges, edge_src, edge_dst, row_ptr, src, perm, workspace,
                                           workspace_bytes, (cudaStream_t)stream),

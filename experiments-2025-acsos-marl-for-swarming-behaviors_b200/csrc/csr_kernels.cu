@@ -31,6 +31,9 @@ __global__ void __launch_bounds__(kCsrThreads) csr_project_kernel(int n, const f
   r[8] = make_float4(asrc, adst, 0.0f, 0.0f);
 }
 
+// HEAD = true: the whole Q-network (aggregate + bias -> tanh -> lin1 -> ReLU -> lin2); HEAD = false: the GATConv layer
+// alone, q_out = float[n][32] = aggregate + conv1.bias (torch_geometric GATConv.forward)
+template <bool HEAD>
 __global__ void __launch_bounds__(kCsrThreads) csr_aggregate_kernel(int n, const float* __restrict__ weights,
                                                                     const float* __restrict__ rows,
                                                                     const int32_t* __restrict__ row_ptr,
@@ -57,6 +60,15 @@ __global__ void __launch_bounds__(kCsrThreads) csr_aggregate_kernel(int n, const
     const long long j = src[e];
     const float w = expf(__fsub_rn(gat_logit(rows[j * kRow + 32], adst), m));
     gat_accumulate(a1, __fdiv_rn(w, den), reinterpret_cast<const float4*>(rows + j * kRow));
+  }
+  if (!HEAD) {
+    float4* o = reinterpret_cast<float4*>(q_out + (long long)i * 32);
+    const float* b0 = sw + TW_B0;
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4)
+      o[c4] = make_float4(__fadd_rn(a1[4 * c4], b0[4 * c4]), __fadd_rn(a1[4 * c4 + 1], b0[4 * c4 + 1]),
+                          __fadd_rn(a1[4 * c4 + 2], b0[4 * c4 + 2]), __fadd_rn(a1[4 * c4 + 3], b0[4 * c4 + 3]));
+    return;
   }
   float q[9];
   const int action = gat_head(a1, sw, q);
@@ -127,10 +139,12 @@ cudaError_t launch_csr_from_edges(int n, long long E, const int64_t* edge_src, c
   long long blocks = (E + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  csr_prepare_kernel<<<(int)blocks, 256, 0, stream>>>(E, edge_dst, keys_in, vals_in);
-  cudaError_t err = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, perm, (int)E, 0,
-                                                    key_bits(n), stream);
-  if (err != cudaSuccess) return err;
+  if (E > 0) {                                       // an edgeless graph: row_ptr = 0 everywhere, nothing to sort
+    csr_prepare_kernel<<<(int)blocks, 256, 0, stream>>>(E, edge_dst, keys_in, vals_in);
+    cudaError_t err = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, perm, (int)E, 0,
+                                                      key_bits(n), stream);
+    if (err != cudaSuccess) return err;
+  }
   long long work = E > n + 1 ? E : n + 1;
   blocks = (work + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -139,10 +153,11 @@ cudaError_t launch_csr_from_edges(int n, long long E, const int64_t* edge_src, c
 }
 
 cudaError_t launch_gatq_csr(int n, const float* weights, const float* x, const int32_t* row_ptr, const int32_t* src,
-                            float* q, int32_t* actions, float* rows, cudaStream_t stream) {
+                            float* q, int32_t* actions, float* rows, cudaStream_t stream, bool conv_only) {
   const int blocks = (n + kCsrThreads - 1) / kCsrThreads;
   csr_project_kernel<<<blocks, kCsrThreads, 0, stream>>>(n, weights, x, rows);
-  csr_aggregate_kernel<<<blocks, kCsrThreads, 0, stream>>>(n, weights, rows, row_ptr, src, q, actions);
+  if (conv_only) csr_aggregate_kernel<false><<<blocks, kCsrThreads, 0, stream>>>(n, weights, rows, row_ptr, src, q, nullptr);
+  else csr_aggregate_kernel<true><<<blocks, kCsrThreads, 0, stream>>>(n, weights, rows, row_ptr, src, q, actions);
   return cudaGetLastError();
 }
 

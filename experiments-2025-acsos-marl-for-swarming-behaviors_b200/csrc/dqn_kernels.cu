@@ -731,7 +731,8 @@ struct CsrBwdParams {
   const int32_t* row_ptr_s;    // CSR by source
   const int32_t* tgt_s;
   const int32_t* pos_s;        // position in the by-target order of out-edge q
-  const float* grad_q;         // [n][9]
+  const float* grad_q;         // [n][9]; conv_only: d(conv output) [n][32]
+  int conv_only;               // 1: the GATConv layer alone (no head): gradients of conv1.* only
   const float* rows;           // [n][36] projected features (csr_project_kernel)
   float* d_out;                // [n][32] d(conv output)
   float* dd;                   // [n] d(alpha_dst)
@@ -794,6 +795,17 @@ __global__ void __launch_bounds__(kTileThreads) csr_bwd_target_kernel(const __gr
       p.alpha[e] = alpha;
       gat_accumulate(agg, alpha, reinterpret_cast<const float4*>(p.rows + j * kRowB));
     }
+    float dvec[32];
+    if (p.conv_only) {
+      // stand-alone GATConv: the upstream gradient IS d(conv output)
+      const float4* gin = reinterpret_cast<const float4*>(p.grad_q + (long long)i * 32);
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 v = gin[c4];
+        dvec[4 * c4] = v.x; dvec[4 * c4 + 1] = v.y; dvec[4 * c4 + 2] = v.z; dvec[4 * c4 + 3] = v.w;
+      }
+      store_row32(tDO, tid, dvec);
+    } else {
     dqn_head(agg, tU + tid * kHPad, tR + tid * kHPad, sw, r, q);
     // head backward: dq given
     float dq[kW2Pad];
@@ -826,7 +838,6 @@ __global__ void __launch_bounds__(kTileThreads) csr_bwd_target_kernel(const __gr
         dp4[k4] = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
-    float dvec[32];
     load_row32(tDP, tid, dvec);
     {
       // du[k] = sum_c W1[c][k] dp[c] ; do = du * (1 - u^2)
@@ -855,6 +866,7 @@ __global__ void __launch_bounds__(kTileThreads) csr_bwd_target_kernel(const __gr
       }
     }
     load_row32(tDO, tid, dvec);                       // dvec = d(conv output_i)
+    }
     {
       float4* g = reinterpret_cast<float4*>(p.d_out + (long long)i * 32);
 #pragma unroll
@@ -890,8 +902,9 @@ __global__ void __launch_bounds__(kTileThreads) csr_bwd_target_kernel(const __gr
   float* out = p.partials + (long long)blockIdx.x * kPartialStride;
   constexpr int G_B0 = 8, G_W1 = 256, G_B1 = 8, G_W2 = 72, G_B2 = 3;
   constexpr int G_TOTAL = G_B0 + G_W1 + G_B1 + G_W2 + G_B2;
+  const int n_groups = p.conv_only ? G_B0 : G_TOTAL;      // conv-only: the partial row was zeroed by the launcher
 #pragma unroll 1
-  for (int grp = tid; grp < G_TOTAL; grp += T) {
+  for (int grp = tid; grp < n_groups; grp += T) {
     int gi = grp;
     const float* A = nullptr;
     const float* Bm;
@@ -1006,7 +1019,7 @@ long long gatq_backward_workspace_bytes(int n, long long E) {
 cudaError_t launch_gatq_backward_csr(int n, long long E, const float* weights, const float* x, const int32_t* row_ptr,
                                      const int32_t* src, const int32_t* perm, const int32_t* row_ptr_s,
                                      const int32_t* tgt_s, const int32_t* perm_s, const float* grad_q, float* grad_w,
-                                     void* workspace, cudaStream_t stream) {
+                                     void* workspace, cudaStream_t stream, bool conv_only) {
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
   auto take = [&](size_t bytes) { char* q = base; base += bwd_align(bytes); return q; };
   float* rows = reinterpret_cast<float*>(take((size_t)n * kRowB * 4));
@@ -1028,7 +1041,12 @@ cudaError_t launch_gatq_backward_csr(int n, long long E, const float* weights, c
     csr_edge_positions_kernel<<<(int)blocks, 256, 0, stream>>>(E, perm, perm_s, inv, pos_s, 0);
     csr_edge_positions_kernel<<<(int)blocks, 256, 0, stream>>>(E, perm, perm_s, inv, pos_s, 1);
   }
+  if (conv_only) {
+    err = cudaMemsetAsync(partials, 0, (size_t)ctas * kPartialStride * 4, stream);
+    if (err != cudaSuccess) return err;
+  }
   CsrBwdParams p;
+  p.conv_only = conv_only ? 1 : 0;
   p.n = n;
   p.weights = weights;
   p.x = x;

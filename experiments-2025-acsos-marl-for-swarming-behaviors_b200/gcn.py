@@ -39,11 +39,32 @@ class _Projection(nn.Module):
         _glorot(self.weight)
 
 
+class _GatConvFunction(torch.autograd.Function):
+    """Stand-alone GATConv layer through swarm_gatconv_forward_csr / swarm_gatconv_backward_csr (weights only)."""
+
+    @staticmethod
+    def forward(ctx, packed, x, edge_index):
+        packed = packed.detach().contiguous()
+        row_ptr, src, perm = ops.csr_from_edges(edge_index, x.shape[0])
+        out = ops.gatconv_forward_csr(packed, x, row_ptr, src)
+        ctx.save_for_backward(packed, x, edge_index, row_ptr, src, perm)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        packed, x, edge_index, row_ptr, src, perm = ctx.saved_tensors
+        grad_w = ops.gatq_backward_csr(packed, x, edge_index, grad_out.contiguous(), by_target=(row_ptr, src, perm),
+                                       conv_only=True)
+        return grad_w, None, None
+
+
 class GATConv(nn.Module):
-    """Parameter container for GATConv(in, out, heads=1, add_self_loops=False, bias=True)
-    (train:53).  Keys: ``att_src`` [1,1,out], ``att_dst`` [1,1,out], ``bias`` [out], ``lin.weight``
-    [out,in].  The projection is initialised twice, like torch_geometric (Linear.__init__ followed by
-    GATConv.reset_parameters)."""
+    """GATConv(in, out, heads=1, add_self_loops=False, bias=True) (train:53).  Keys: ``att_src`` [1,1,out],
+    ``att_dst`` [1,1,out], ``bias`` [out], ``lin.weight`` [out,in].  The projection is initialised twice, like
+    torch_geometric (Linear.__init__ followed by GATConv.reset_parameters).  Inside ``swarm_b200.GCN`` it is a parameter
+    container (the whole network is one fused call); called on its own -- ``conv(x, edge_index)`` as the reference's
+    ``GCN.forward`` does (train:61) -- it runs the layer alone in the CUDA kernels, differentiable w.r.t. its
+    parameters (the node features are data: no gradient flows into ``x``)."""
 
     def __init__(self, in_channels: int, out_channels: int, heads: int = 1, add_self_loops: bool = False,
                  bias: bool = True):
@@ -62,6 +83,18 @@ class GATConv(nn.Module):
         _glorot(self.att_src)
         _glorot(self.att_dst)
         self.bias.data.zero_()
+
+    def forward(self, x: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
+        if (self.in_channels, self.out_channels) != (_FEAT, _HIDDEN):
+            raise NotImplementedError(f"the swarm_b200 kernels implement GATConv({_FEAT}, {_HIDDEN})")
+        if not x.is_cuda:
+            raise _lib.SwarmError("GATConv.forward runs on CUDA tensors only (swarm_b200 has no CPU fallback)")
+        if x.requires_grad:
+            raise NotImplementedError("gradients w.r.t. the node features are not implemented (first layer only)")
+        head = torch.zeros(_lib.W_COUNT - 320, dtype=torch.float32, device=x.device)
+        packed = torch.cat([self.lin.weight.reshape(-1), self.att_src.reshape(-1), self.att_dst.reshape(-1),
+                            self.bias.reshape(-1), head])
+        return _GatConvFunction.apply(packed, x.contiguous(), edge_index.to(torch.int64).contiguous())
 
 
 class _GatQFunction(torch.autograd.Function):

@@ -419,24 +419,39 @@ def gatq_forward_knn_large(cfg: SwarmConfig, weights: torch.Tensor, state: torch
     return q if want_q else act
 
 
+def gatconv_forward_csr(weights: torch.Tensor, x: torch.Tensor, row_ptr: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    """The GATConv layer alone: x f32[n,7] + CSR-by-target -> f32[n,32] (aggregate + bias)."""
+    n = x.shape[0]
+    _expect(x, torch.float32, n * 7, "x")
+    _expect(weights, torch.float32, _lib.W_COUNT, "weights")
+    out = torch.empty(n, 32, dtype=torch.float32, device=x.device)
+    wb = int(lib().swarm_gatq_workspace_bytes(n))
+    ws = torch.empty(max(wb, 1), dtype=torch.uint8, device=x.device)
+    check(lib().swarm_gatconv_forward_csr(n, ptr(weights), ptr(x.contiguous()), ptr(row_ptr), ptr(src), ptr(out), ptr(ws), wb,
+                                          stream_ptr(x.device)))
+    return out
+
+
 def gatq_backward_csr(weights: torch.Tensor, x: torch.Tensor, edge_index: torch.Tensor, grad_q: torch.Tensor,
-                      by_target: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
+                      by_target: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None,
+                      conv_only: bool = False) -> torch.Tensor:
     """Gradient of GCN.forward w.r.t. the packed weights for an arbitrary graph: x f32[n,7], edge_index int64[2,E],
-    grad_q f32[n,9] -> f32[1673].  ``by_target`` = (row_ptr, src, perm) of the forward's grouping, if already built."""
+    grad_q f32[n,9] -> f32[1673].  ``by_target`` = (row_ptr, src, perm) of the forward's grouping, if already built.
+    ``conv_only``: the GATConv layer alone, grad_q = d(conv output) f32[n,32]."""
     n = x.shape[0]
     E = edge_index.shape[1]
     _expect(x, torch.float32, n * 7, "x")
     _expect(weights, torch.float32, _lib.W_COUNT, "weights")
-    _expect(grad_q, torch.float32, n * 9, "grad_q")
+    _expect(grad_q, torch.float32, n * (32 if conv_only else 9), "grad_q")
     dev = x.device
     row_ptr, src, perm = by_target if by_target is not None else csr_from_edges(edge_index, n)
     row_ptr_s, tgt_s, perm_s = csr_from_edges(edge_index.flip(0).contiguous(), n)
     grad = torch.empty(_lib.W_COUNT, dtype=torch.float32, device=dev)
     wb = int(lib().swarm_gatq_backward_workspace_bytes(n, E))
     ws = torch.empty(max(wb, 1), dtype=torch.uint8, device=dev)
-    check(lib().swarm_gatq_backward_csr(n, E, ptr(weights), ptr(x.contiguous()), ptr(row_ptr), ptr(src), ptr(perm),
-                                        ptr(row_ptr_s), ptr(tgt_s), ptr(perm_s), ptr(grad_q.contiguous()), ptr(grad),
-                                        ptr(ws), wb, stream_ptr(dev)))
+    fn = lib().swarm_gatconv_backward_csr if conv_only else lib().swarm_gatq_backward_csr
+    check(fn(n, E, ptr(weights), ptr(x.contiguous()), ptr(row_ptr), ptr(src), ptr(perm), ptr(row_ptr_s), ptr(tgt_s),
+             ptr(perm_s), ptr(grad_q.contiguous()), ptr(grad), ptr(ws), wb, stream_ptr(dev)))
     return grad
 
 

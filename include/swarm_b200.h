@@ -151,7 +151,8 @@ int swarm_gatq_forward_csr(int32_t n_nodes, const float* weights, const float* x
 
 /* Stable grouping of an edge list by target (the order scatter-add sees): edge_src/edge_dst int64[E]
  * (torch_geometric edge_index rows) -> row_ptr int32[n+1], src int32[E], perm int32[E] (perm[p] = position
- * in the input list of grouped edge p).  workspace: swarm_csr_workspace_bytes(n, E) bytes. */
+ * in the input list of grouped edge p).  workspace: swarm_csr_workspace_bytes(n, E) bytes.  An edgeless graph
+ * (E = 0, e.g. a single agent) is valid: the edge arrays may then be NULL and row_ptr is all zeros. */
 int64_t swarm_csr_workspace_bytes(int32_t n_nodes, int64_t n_edges);
 int swarm_csr_from_edges(int32_t n_nodes, int64_t n_edges, const int64_t* edge_src, const int64_t* edge_dst,
                          int32_t* row_ptr, int32_t* src, int32_t* perm, void* workspace, int64_t workspace_bytes,
@@ -176,6 +177,18 @@ int swarm_gatq_backward_csr(int32_t n_nodes, int64_t n_edges, const float* weigh
                             const int32_t* row_ptr, const int32_t* src, const int32_t* perm, const int32_t* row_ptr_s,
                             const int32_t* tgt_s, const int32_t* perm_s, const float* grad_q, float* grad_weights,
                             void* workspace, int64_t workspace_bytes, void* stream);
+
+/* The GATConv layer alone (torch_geometric.nn.GATConv(7, 32, heads=1, add_self_loops=False) as the reference's GCN
+ * class calls it, train_gcn_dqn.py:53,61): out float[n][32] = softmax-weighted aggregate + bias, and its backward pass
+ * (grad_out float[n][32] -> the conv1.* segments of grad_weights float[1673]; the other segments are zero).  Same
+ * graph arguments, workspaces (swarm_gatq_workspace_bytes / swarm_gatq_backward_workspace_bytes) and determinism as
+ * the whole-network calls above; only the conv1.* entries of `weights` are read. */
+int swarm_gatconv_forward_csr(int32_t n_nodes, const float* weights, const float* x, const int32_t* row_ptr,
+                              const int32_t* src, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+int swarm_gatconv_backward_csr(int32_t n_nodes, int64_t n_edges, const float* weights, const float* x,
+                               const int32_t* row_ptr, const int32_t* src, const int32_t* perm, const int32_t* row_ptr_s,
+                               const int32_t* tgt_s, const int32_t* perm_s, const float* grad_out, float* grad_weights,
+                               void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Device replay ring of whole-swarm transitions (GraphReplayBuffer, train_gcn_dqn.py:25-48, capacity 1e6 at
  * train:86).  Only the world state is stored (37 B per agent and transition); node features and graphs are

@@ -437,3 +437,89 @@ def test_reference_style_train_step_on_the_module():
     assert got_losses[-1] < got_losses[0]
     for k in ref_sd:
         assert torch.allclose(got_sd[k].reshape(ref_sd[k].shape), ref_sd[k], rtol=2e-4, atol=2e-5), k
+
+
+@pytest.mark.parametrize("exp,scenario", [("GoTo", "go_to"), ("ObstacleAvoidance", "obstacle_avoidance")])
+def test_gatconv_layer_alone_forward_backward(exp, scenario):
+    """The network class as the reference DEFINES it (train:50-70): its own ``forward`` composed of
+    ``GATConv(x, edge_index)`` + torch tanh / Linear / relu, with only the GATConv layer from this package.  Loads the
+    shipped state dict (same key set), matches the fused swarm_b200.GCN and the oracle network in value and in every
+    parameter gradient, and is bit-reproducible across calls."""
+    import torch.nn as nn
+    from oracle.dqn_oracle import OracleGCN
+    sb = _swarm()
+
+    def nerr(a, b):                        # max error relative to the largest reference magnitude
+        return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+
+    class ReferenceStyleGCN(nn.Module):
+        def __init__(self, input_dim, hidden_dim, output_dim):
+            super().__init__()
+            self.conv1 = sb.GATConv(input_dim, hidden_dim, add_self_loops=False, bias=True)
+            self.lin1 = nn.Linear(hidden_dim, hidden_dim)
+            self.lin2 = nn.Linear(hidden_dim, output_dim)
+
+        def forward(self, data):
+            x, edge_index = data.x, data.edge_index
+            x = torch.tanh(self.conv1(x, edge_index))
+            x = torch.relu(self.lin1(x))
+            return self.lin2(x)
+
+    params = load_params(exp, 4)
+    x_all, ei_all = _ragged_batch(scenario, seed=5)
+    cot = torch.randn(x_all.shape[0], 9, generator=torch.Generator().manual_seed(2))
+    ref64 = OracleGCN(7, 32, 9).double()
+    ref64.load_state_dict({k: v.double() for k, v in params.items()})
+    q64 = ref64(x_all.double(), ei_all)
+    (q64 * cot.double()).sum().backward()
+    ref32 = OracleGCN(7, 32, 9)
+    ref32.load_state_dict(params)
+    (ref32(x_all, ei_all) * cot).sum().backward()
+
+    model = ReferenceStyleGCN(7, 32, 9)
+    model.load_state_dict(params)
+    model = model.to(_dev())
+    fused = sb.GCN(7, 32, 9)
+    fused.load_state_dict(params)
+    fused = fused.to(_dev())
+    data = sb.Data(x=x_all.to(_dev()), edge_index=ei_all.to(_dev()))
+
+    # the layer's own output against the oracle's conv stage
+    with torch.no_grad():
+        conv = model.conv1(data.x, data.edge_index).cpu()
+        want = ref64.conv1(x_all.double(), ei_all)
+    assert nerr(conv, want) < 2e-6
+    q = model(data)
+    assert nerr(q.detach().cpu(), q64.detach()) < 5e-6
+    assert nerr(q.detach().cpu(), fused(data).detach().cpu()) < 5e-6
+
+    grads = []
+    for _ in range(2):
+        model.zero_grad()
+        (model(data) * cot.to(_dev())).sum().backward()
+        grads.append({k: p.grad.detach().clone() for k, p in model.named_parameters()})
+    for k in grads[0]:
+        if k.startswith("conv1."):
+            assert torch.equal(grads[0][k], grads[1][k]), f"{k}: gradient differs between two identical calls"
+    for (name, p32), (_, p64) in zip(ref32.named_parameters(), ref64.named_parameters()):
+        g64 = p64.grad.float()
+        got = grads[0][name].cpu().reshape(g64.shape)
+        scale = g64.abs().max().item()
+        err = (got - g64).abs().max().item()
+        err32 = (p32.grad - g64).abs().max().item()
+        assert err <= max(1e-5 * scale, 20 * err32), f"{name}: abs error {err:.3e} (float32 autograd {err32:.3e}, |g|max {scale:.3e})"
+
+    # empty graph and isolated nodes: the layer returns the bias for nodes without in-edges
+    xe = x_all[:5].to(_dev())
+    out = model.conv1(xe, torch.zeros(2, 0, dtype=torch.int64, device=_dev()))
+    assert torch.equal(out, model.conv1.bias.detach().expand(5, 32))
+    empty = sb.Data(x=xe, edge_index=torch.zeros(2, 0, dtype=torch.int64, device=_dev()))
+    q_empty = fused(empty)
+    want_empty = ref32(x_all[:5], torch.zeros(2, 0, dtype=torch.int64))
+    assert nerr(q_empty.detach().cpu(), want_empty.detach()) < 5e-6
+    fused.zero_grad()
+    q_empty.sum().backward()                 # edgeless graph: only the bias / head gradients are non-zero
+    assert float(fused.conv1.lin.weight.grad.abs().max()) == 0.0
+    assert torch.allclose(fused.lin2.bias.grad.cpu(), torch.full((9,), 5.0))
+    with pytest.raises(NotImplementedError):
+        sb.GATConv(7, 16)(xe, torch.zeros(2, 0, dtype=torch.int64, device=_dev()))
