@@ -77,6 +77,17 @@ class SwarmResetSpec(C.Structure):
                 ("shared_center", C.c_int32), ("pad", C.c_int32)]
 
 
+class SwarmRewardSpec(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("num_envs", C.c_int32), ("n_agents", C.c_int32), ("reset", C.c_int32),
+                ("env_index", C.c_int64), ("goal_x", C.c_float), ("goal_y", C.c_float), ("goal_radius", C.c_float),
+                ("agent_radius", C.c_float), ("pos_shaping", C.c_float), ("dist_shaping", C.c_float),
+                ("desired_distance", C.c_float), ("min_collision_distance", C.c_float), ("collision_reward", C.c_float),
+                ("on_goal_bonus", C.c_float), ("sigma", C.c_float), ("pad", C.c_float)]
+
+
+REWARD_FLOCKING, REWARD_COHESION = 0, 1
+
+
 class SwarmPeerExchange(C.Structure):
     _fields_ = [("data", C.c_void_p * 16), ("flags", C.c_void_p * 16), ("world_size", C.c_int32), ("rank", C.c_int32)]
 
@@ -121,6 +132,8 @@ _SIGNATURES = {
                                        C.c_void_p]),
     "swarm_train_tick_grad": (C.c_int, [C.POINTER(SwarmConfig), C.POINTER(SwarmTrainHyper)] + [C.c_void_p] * 6
                               + [C.POINTER(SwarmReplay)] + [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]),
+    "swarm_default_reward_spec": (None, [C.POINTER(SwarmRewardSpec), C.c_int32, C.c_int32, C.c_int32]),
+    "swarm_scenario_reward": (C.c_int, [C.POINTER(SwarmRewardSpec)] + [C.c_void_p] * 5),
     "swarm_reset_random": (C.c_int, [C.POINTER(SwarmConfig), C.POINTER(SwarmResetSpec), C.c_void_p, C.c_int64,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "swarm_episode_end": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 5 + [C.c_int64, C.c_double, C.c_double,

@@ -15,6 +15,8 @@ cudaError_t launch_graph_large(const SwarmConfig& c, const float* state, int32_t
                                cudaStream_t stream);
 cudaError_t launch_reset_grid(const SwarmConfig& c, int cols, int rows, const float* centers, float* state,
                               cudaStream_t stream);
+cudaError_t launch_scenario_reward(const SwarmRewardSpec& sp, const float* state, float* shaping, float* reward,
+                                   float* terms, cudaStream_t stream);
 cudaError_t launch_reset_random(const SwarmConfig& c, const SwarmResetSpec& sp, int cols, int rows, const SwarmTrainCtl* ctl,
                                 long long episode, float* centers_out, float* state, cudaStream_t stream);
 cudaError_t launch_episode_end(const SwarmConfig& c, SwarmTrainCtl* ctl, float* returns, int32_t* hits, const float* loss,
@@ -516,6 +518,51 @@ int swarm_reset_random(const SwarmConfig* cfg, const SwarmResetSpec* spec, const
   const int rows = (int)std::ceil((double)n / (double)cols);
   return check_cuda(launch_reset_random(*cfg, *spec, cols, rows, ctl, episode, centers_out, state, (cudaStream_t)stream),
                     "swarm_reset_random");
+}
+
+void swarm_default_reward_spec(SwarmRewardSpec* spec, int32_t kind, int32_t num_envs, int32_t n_agents) {
+  if (!spec) return;
+  *spec = SwarmRewardSpec{};
+  spec->kind = kind;
+  spec->num_envs = num_envs;
+  spec->n_agents = n_agents;
+  spec->reset = 0;
+  spec->env_index = -1;
+  spec->goal_x = -0.8f;
+  spec->goal_y = 0.8f;
+  spec->goal_radius = 0.05f;
+  spec->agent_radius = 0.05f;
+  spec->pos_shaping = 10.0f;
+  spec->dist_shaping = 10.0f;
+  spec->desired_distance = 0.15f;
+  spec->min_collision_distance = 0.005f;
+  spec->collision_reward = -1.0f;
+  spec->on_goal_bonus = 50.0f;
+  spec->sigma = 0.15f;
+}
+
+int swarm_scenario_reward(const SwarmRewardSpec* spec, const float* state, float* shaping, float* reward, float* terms,
+                          void* stream) {
+  if (!spec) return fail(SWARM_ERR_INVALID_ARG, "spec is NULL");
+  if (spec->kind != SWARM_REWARD_FLOCKING && spec->kind != SWARM_REWARD_COHESION)
+    return fail(SWARM_ERR_INVALID_ARG, "unknown reward kind");
+  if (spec->num_envs < 0) return fail(SWARM_ERR_INVALID_ARG, "num_envs must be >= 0");
+  if (spec->n_agents < 2) return fail(SWARM_ERR_INVALID_ARG, "the scenario rewards need at least two agents");
+  if (spec->n_agents > 128) return fail(SWARM_ERR_UNSUPPORTED, "scenario rewards are implemented for n_agents <= 128");
+  if (spec->env_index < -1 || spec->env_index >= spec->num_envs)
+    return fail(SWARM_ERR_INVALID_ARG, "env_index out of range");
+  if (spec->num_envs == 0) return SWARM_OK;
+  if (!state) return fail(SWARM_ERR_INVALID_ARG, "state is NULL");
+  if (spec->kind == SWARM_REWARD_FLOCKING) {
+    if (!shaping) return fail(SWARM_ERR_INVALID_ARG, "Flocking needs the shaping buffer");
+    if (!spec->reset && !reward) return fail(SWARM_ERR_INVALID_ARG, "reward is NULL");
+  } else {
+    if (spec->reset) return fail(SWARM_ERR_INVALID_ARG, "Cohesion keeps no shaping memory (reset must be 0)");
+    if (!reward) return fail(SWARM_ERR_INVALID_ARG, "reward is NULL");
+    if (!(spec->sigma > 0.0f)) return fail(SWARM_ERR_INVALID_ARG, "sigma must be > 0");
+  }
+  return check_cuda(launch_scenario_reward(*spec, state, shaping, reward, terms, (cudaStream_t)stream),
+                    "swarm_scenario_reward");
 }
 
 int swarm_episode_end(const SwarmConfig* cfg, SwarmTrainCtl* ctl, float* returns, int32_t* hits, const float* loss,

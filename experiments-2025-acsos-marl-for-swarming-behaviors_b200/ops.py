@@ -270,6 +270,42 @@ def reset_spec(scenario: int, random: bool = True, seed: int = 0, env_offset: in
     return sp
 
 
+def reward_spec(kind: int, num_envs: int, n_agents: int, **overrides) -> _lib.SwarmRewardSpec:
+    """Reference constants of the Flocking / Cohesion reward (flocking:10-21, cohesion:10-23); keyword overrides."""
+    sp = _lib.SwarmRewardSpec()
+    lib().swarm_default_reward_spec(C.byref(sp), kind, num_envs, n_agents)
+    for k, v in overrides.items():
+        if not hasattr(sp, k):
+            raise TypeError(f"SwarmRewardSpec has no field {k!r}")
+        setattr(sp, k, v)
+    return sp
+
+
+def scenario_reward(spec: _lib.SwarmRewardSpec, state: torch.Tensor, shaping: Optional[torch.Tensor] = None, *,
+                    reset: bool = False, env_index: Optional[int] = None, want_terms: bool = False):
+    """swarm_scenario_reward on state f32[B,N,4].  Flocking: shaping f32[B,N,2] is updated in place; returns the
+    collective reward f32[B] (None for a reset call).  Cohesion: returns f32[B,N].  ``want_terms`` adds f32[B,N,4]."""
+    B, N = spec.num_envs, spec.n_agents
+    _expect(state, torch.float32, B * N * 4, "state")
+    dev = state.device
+    flocking = spec.kind == _lib.REWARD_FLOCKING
+    if flocking:
+        if shaping is None:
+            raise ValueError("Flocking needs the shaping buffer f32[B,N,2]")
+        _expect(shaping, torch.float32, B * N * 2, "shaping")
+    call = _lib.SwarmRewardSpec.from_buffer_copy(spec)
+    call.reset = 1 if reset else 0
+    call.env_index = -1 if env_index is None else int(env_index)
+    reward = None
+    if not reset:
+        reward = torch.zeros(B, dtype=torch.float32, device=dev) if flocking else \
+            torch.zeros(B, N, dtype=torch.float32, device=dev)
+    terms = torch.zeros(B, N, 4, dtype=torch.float32, device=dev) if (want_terms and not reset) else None
+    check(lib().swarm_scenario_reward(C.byref(call), ptr(state), ptr(shaping) if flocking else None, ptr(reward),
+                                      ptr(terms), stream_ptr(dev)))
+    return (reward, terms) if want_terms else reward
+
+
 def reset_random(cfg: SwarmConfig, spec: _lib.SwarmResetSpec, state: torch.Tensor, *, ctl: Optional[torch.Tensor] = None,
                  episode: int = 0, centers_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Device-side reset_world_at for every env: start centres from the counter RNG (episode number from the device

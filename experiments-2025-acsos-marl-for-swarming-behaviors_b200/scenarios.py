@@ -114,6 +114,7 @@ class Entity:
 
     def set_pos(self, pos: torch.Tensor, batch_index: Optional[int] = None) -> None:
         st = self.state
+        self._require_world().version += 1
         p_host = torch.as_tensor(pos, dtype=torch.float32)
         p = p_host.to(st.pos.device)
         if batch_index is None:
@@ -199,6 +200,7 @@ class World:
         self.last: Dict[str, torch.Tensor] = {}
         self._obstacle: Optional[Landmark] = None
         self._goal: Optional[Landmark] = None
+        self.version = 0                       # bumped whenever the state may have changed (step / reset / set_pos)
 
     # vmas attribute names
     @property
@@ -284,6 +286,7 @@ class World:
 
     def reset(self, env_index: Optional[int] = None) -> None:
         """vmas World.reset: every entity's state back to zero (the scenario's reset_world_at places them next)."""
+        self.version += 1
         if env_index is None:
             self.state.zero_()
         else:
@@ -292,6 +295,7 @@ class World:
     def reset_to_grid(self, centers: torch.Tensor, env_index: Optional[int] = None) -> None:
         """generate_grid + set_pos for every agent; velocities zero (vmas world.reset)."""
         centers = centers.to(device=self.device, dtype=torch.float32).reshape(-1, 2)
+        self.version += 1
         self._sync_constants()
         if env_index is None:
             if centers.shape[0] == 1:
@@ -305,6 +309,7 @@ class World:
     def step(self, actions: torch.Tensor) -> None:
         """actions int32[B,N] -> in-place world step; results kept in ``self.last``."""
         self._sync_constants()
+        self.version += 1
         self.last = ops.sim_step(self.cfg, self.state, actions, state_out=self.state, want_obs=True)
 
     def get_distance(self, a: Entity, b: Entity) -> torch.Tensor:
@@ -488,3 +493,175 @@ class ObstacleAvoidanceScenario(_KernelScenario):
     def obstacles_hits(self) -> torch.Tensor:
         hits = (self.world.last["flags"] & _lib.FLAG_HIT) != 0       # oa:170-173
         return torch.sum(hits)
+
+
+class FlockingScenario(BaseScenario):
+    """src/scenarios/flocking_scenario.py:7-205.  The world is GoTo's (goal landmark that does not collide, colliding
+    sphere agents) and is stepped by ``swarm_sim_step``; the collective reward -- shaped goal progress, +50 on the goal,
+    -1 per near-contact, shaped spacing progress, with the two ``previous_*`` memories per agent -- is one
+    ``swarm_scenario_reward`` launch per tick over all envs.  The reference branches on tensors in Python
+    (flocking:141,169) and so only runs with ``num_envs = 1``; here every env is its own copy of that computation."""
+
+    scenario_id = _lib.SCENARIO_GOTO
+
+    def make_world(self, batch_dim: int, device, **kwargs) -> World:
+        self.pos_shaping_factor = kwargs.get("pos_shaping_factor", 10.0)
+        self.dist_shaping_factor = kwargs.get("dist_shaping_factor", 10.0)
+        self.agent_radius = kwargs.get("agent_radius", 0.1)       # unused by the physics, as in the reference
+        self.n_agents = kwargs.get("n_agents", 1)
+        self.per_env_centers = kwargs.get("per_env_centers", False)
+        self._explicit_centers = None
+        self.min_distance_between_entities = self.agent_radius * 2 + 0.05
+        self.world_semidim = 1
+        self.collective_reward = 0
+        self.agent_collision_reward = -1
+        self.desired_distance = 0.15
+        self.min_collision_distance = 0.005
+
+        world = World(batch_dim, device)
+        goal = Landmark(name="goal", collide=False, color=Color.BLACK)
+        world.add_landmark(goal)
+        for i in range(self.n_agents):
+            agent = Agent(name=f"agent{i}", collide=True, color=Color.GREEN, render_action=True)
+            agent.pos_rew = torch.zeros(batch_dim, device=world.device)
+            agent.collision_rew = agent.pos_rew.clone()
+            agent.goal = goal
+            world.add_agent(agent)
+        world._finalize(self.scenario_id)
+        self.pos_rew = torch.zeros(batch_dim, device=world.device)
+        self.final_rew = self.pos_rew.clone()
+        # (previous_distance_to_goal, previous_distance_to_agents) of every agent: f32[B, N, 2] in HBM
+        self.shaping = torch.zeros(batch_dim, self.n_agents, 2, dtype=torch.float32, device=world.device)
+        return world
+
+    def _spec(self) -> "_lib.SwarmRewardSpec":
+        w = self.world
+        w._sync_constants()
+        return ops.reward_spec(_lib.REWARD_FLOCKING, w.batch_dim, self.n_agents, goal_x=w.cfg.goal_x, goal_y=w.cfg.goal_y,
+                               goal_radius=w.landmarks[0].shape.radius, agent_radius=w.cfg.agent_radius,
+                               pos_shaping=self.pos_shaping_factor, dist_shaping=self.dist_shaping_factor,
+                               desired_distance=self.desired_distance,
+                               min_collision_distance=self.min_collision_distance,
+                               collision_reward=float(self.agent_collision_reward))
+
+    def set_start_centers(self, centers: Optional[torch.Tensor]) -> None:
+        """Batched extension: explicit per-env start centres f32[B,2] for the next resets."""
+        self._explicit_centers = centers
+
+    def reset_world_at(self, env_index: Optional[int] = None) -> None:
+        w = self.world
+        w.landmarks[0].set_pos(torch.tensor([-0.8, 0.8]), None)                              # flocking:96
+        if self._explicit_centers is not None:
+            centers = self._explicit_centers if env_index is None else self._explicit_centers[env_index:env_index + 1]
+        else:
+            n = w.batch_dim if (self.per_env_centers and env_index is None) else 1
+            position_range = torch.tensor([-1, 1])                                           # flocking:94
+            if n == 1:
+                centers = position_range + torch.normal(mean=torch.tensor([-0.6, 0.6]), std=torch.tensor([0.4, 0.4]))
+            else:
+                centers = position_range + torch.normal(mean=torch.tensor([-0.6, 0.6]).expand(n, 2),
+                                                        std=torch.tensor([0.4, 0.4]).expand(n, 2))
+            # generate_grid draws two unused deviates per grid point (flocking:70-71); draw them too so that seeded
+            # runs leave the global generator where the reference leaves it
+            for _ in range(2 * self.n_agents):
+                torch.normal(mean=torch.tensor([0.0]), std=torch.tensor([0.1]))
+        w.reset_to_grid(centers, env_index)
+        # previous_distance_to_goal / previous_distance_to_agents as reset_world_at leaves them (flocking:101-121)
+        ops.scenario_reward(self._spec(), w.state, self.shaping, reset=True, env_index=env_index)
+
+    def reward(self, agent: Agent) -> torch.Tensor:
+        if agent is self.world.agents[0]:                                                    # flocking:125
+            w = self.world
+            self.collective_reward, terms = ops.scenario_reward(self._spec(), w.state, self.shaping, want_terms=True)
+            radius = w.landmarks[0].shape.radius
+            for a in w.agents:
+                a.pos_rew = terms[:, a.index, 0]
+                a.collision_rew = terms[:, a.index, 1]
+                a.dist_rew = terms[:, a.index, 2]
+                a.distance_to_goal = terms[:, a.index, 3]
+                a.on_goal = a.distance_to_goal < radius
+        return self.collective_reward
+
+    @property
+    def previous_distance_to_goal(self) -> torch.Tensor:
+        return self.shaping[:, :, 0]
+
+    @property
+    def previous_distance_to_agents(self) -> torch.Tensor:
+        return self.shaping[:, :, 1]
+
+    def observation(self, agent: Agent) -> torch.Tensor:
+        """cat[pos, vel, goal] f32[B,6] (flocking:173-182)."""
+        return self.world.last["obs"][:, agent.index]
+
+    def distance_to_goal_all(self) -> torch.Tensor:
+        """f32[B,N] (flocking:184-191)."""
+        w = self.world
+        goal = w.landmarks[0].state.pos.unsqueeze(1)
+        return torch.linalg.vector_norm(w.state[:, :, 0:2] - goal, dim=-1)
+
+    def info(self, agent: Agent) -> Dict[str, torch.Tensor]:
+        return {"pos_rew": agent.pos_rew, "final_rew": self.final_rew}
+
+
+class CohesionScenario(BaseScenario):
+    """src/scenarios/cohesion_scenario.py:7-101: no landmark, up to nine agents on a fixed start table, observation
+    cat[pos, vel] (4 floats), per-agent reward from the smallest / largest surface distance to the other agents
+    (``swarm_scenario_reward``, one launch per tick for all agents and envs).  Stepped by ``swarm_sim_step`` like GoTo.
+    The reference takes the min / max over everything ``torch.cat`` returns, i.e. it assumes one env; here the min / max
+    are per env.  The Q-network kernels are specialised for 6-float observations, so this scenario is served at the
+    environment level (world step + reward), not by the fused rollout."""
+
+    scenario_id = _lib.SCENARIO_GOTO
+    _START = [[-1.0, -1.0], [0.0, -1.0], [0.0, 1.0], [0.0, 0.0], [1.0, 1.0], [1.0, -1.0], [-1.0, 1.0], [1.0, 0.0],
+              [-1.0, 0.0]]                                                                   # cohesion:46-56
+
+    def make_world(self, batch_dim: int, device, **kwargs) -> World:
+        self.pos_shaping_factor = kwargs.get("pos_shaping_factor", 10.0)
+        self.dist_shaping_factor = kwargs.get("dist_shaping_factor", 10.0)
+        self.agent_radius = kwargs.get("agent_radius", 0.1)
+        self.n_agents = kwargs.get("n_agents", 1)
+        self.min_distance_between_entities = self.agent_radius * 2 + 0.05
+        self.world_semidim = 1
+        self.agent_collision_reward = -1
+        self.desired_distance = 0.15
+        self.min_collision_distance = 0.005
+        self.collective_reward = 0
+        self.sigma = 0.15
+        world = World(batch_dim, device)
+        for i in range(self.n_agents):
+            agent = Agent(name=f"agent{i}", collide=True, color=Color.GREEN, render_action=True)
+            agent.pos_rew = torch.zeros(batch_dim, device=world.device)
+            agent.collision_rew = agent.pos_rew.clone()
+            world.add_agent(agent)
+        world._finalize(self.scenario_id)
+        self.pos_rew = torch.zeros(batch_dim, device=world.device)
+        self.final_rew = self.pos_rew.clone()
+        self._rewards: Optional[torch.Tensor] = None
+        self._rewards_version = -1
+        return world
+
+    def reset_world_at(self, env_index: Optional[int] = None) -> None:
+        table = torch.tensor(self._START, dtype=torch.float32)
+        for i, agent in enumerate(self.world.agents):
+            agent.set_pos(table[i], batch_index=env_index)       # IndexError beyond nine agents, as in the reference
+
+    def all_rewards(self) -> torch.Tensor:
+        """f32[B,N] for the current state (cached until the world steps or resets)."""
+        w = self.world
+        if self._rewards is None or self._rewards_version != w.version:
+            spec = ops.reward_spec(_lib.REWARD_COHESION, w.batch_dim, self.n_agents, agent_radius=w.cfg.agent_radius,
+                                   sigma=self.sigma)
+            self._rewards = ops.scenario_reward(spec, w.state)
+            self._rewards_version = w.version
+        return self._rewards
+
+    def reward(self, agent: Agent) -> torch.Tensor:
+        return self.all_rewards()[:, agent.index]
+
+    def observation(self, agent: Agent) -> torch.Tensor:
+        """cat[pos, vel] f32[B,4] (cohesion:87-94)."""
+        return self.world.state[:, agent.index].clone()
+
+    def info(self, agent: Agent) -> Dict[str, torch.Tensor]:
+        return {"pos_rew": agent.pos_rew, "final_rew": self.final_rew}

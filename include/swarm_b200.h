@@ -345,6 +345,43 @@ int swarm_episode_end(const SwarmConfig* cfg, SwarmTrainCtl* ctl, float* returns
                       float* stats, int64_t max_episodes, double epsilon0, double epsilon_decay, double min_epsilon,
                       void* stream);
 
+/* ---- rewards of the remaining reference scenarios -----------------------------------------
+ * FlockingScenario (flocking_scenario.py:93-176) and CohesionScenario (cohesion_scenario.py:66-85) step the same world
+ * as GoTo (colliding sphere agents, no colliding landmark: swarm_sim_step with SWARM_SCENARIO_GOTO); only their reward
+ * differs.  swarm_scenario_reward evaluates it on the stepped state, one env = one copy of the reference's one-env
+ * computation (the reference branches on tensors in Python and cannot run batched).
+ *   Flocking: reward float[B] = the collective reward every agent receives (flocking:124-131); shaping float[B][N][2]
+ *     carries (previous_distance_to_goal, previous_distance_to_agents) between ticks and is REQUIRED; a call with
+ *     reset = 1 initialises it the way reset_world_at does (agent i sees the agents after it at the origin, where
+ *     world.reset left them, flocking:93-121) and writes no reward; env_index >= 0 restricts either call to one env
+ *     (reset_world_at(env_index)).  terms (optional) float[B][N][4] = (pos_rew, avoidance, dist_rew, distance_to_goal).
+ *   Cohesion: reward float[B][N] per agent; shaping unused (NULL); terms (optional) float[B][N][4] =
+ *     (collision_factor, cohesion_factor, min_distance, max_distance).
+ * 2 <= n_agents <= 128 (with one agent the reference's torch.stack / torch.cat of an empty list raises). */
+#define SWARM_REWARD_FLOCKING 0
+#define SWARM_REWARD_COHESION 1
+typedef struct SwarmRewardSpec {
+  int32_t kind;                  /* SWARM_REWARD_*                                                                      */
+  int32_t num_envs, n_agents;
+  int32_t reset;                 /* Flocking: 1 = initialise the shaping memory, no reward                              */
+  int64_t env_index;             /* -1 = every env                                                                      */
+  float goal_x, goal_y;          /* (-0.8, 0.8) flocking:96                                                             */
+  float goal_radius;             /* 0.05: on_goal = distance_to_goal < goal.shape.radius (flocking:134)                 */
+  float agent_radius;            /* 0.05: world.get_distance subtracts both radii                                       */
+  float pos_shaping;             /* pos_shaping_factor 10 (flocking:10)                                                 */
+  float dist_shaping;            /* dist_shaping_factor 10 (flocking:11)                                                */
+  float desired_distance;        /* 0.15 (flocking:20)                                                                  */
+  float min_collision_distance;  /* 0.005 (flocking:21)                                                                 */
+  float collision_reward;        /* -1 (flocking:19)                                                                    */
+  float on_goal_bonus;           /* 50 (flocking:142)                                                                   */
+  float sigma;                   /* Cohesion 0.15 (cohesion:23)                                                         */
+  float pad;
+} SwarmRewardSpec;
+
+void swarm_default_reward_spec(SwarmRewardSpec* spec, int32_t kind, int32_t num_envs, int32_t n_agents);
+int swarm_scenario_reward(const SwarmRewardSpec* spec, const float* state, float* shaping, float* reward, float* terms,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,218 @@
+"""FlockingScenario / CohesionScenario (flocking_scenario.py, cohesion_scenario.py) through the
+environment seam: world step in swarm_sim_step (GoTo physics, covered bit-exactly by test_gpu_parity.py), rewards in
+swarm_scenario_reward.  Every env is compared with its own single-env oracle (oracle/scenario_rewards_oracle.py) on the
+SAME device states, tick by tick, so the reward arithmetic and the shaping memory are what is being checked.
+
+Tolerance: rewards are chains of separately rounded float32 ops in the reference's order; the only op whose rounding
+the kernel does not reproduce by construction is torch's ``mean`` (and ``exp`` for Cohesion).  torch sums a contiguous
+row with SIMD partial sums whose width depends on the host CPU (8 or 16 lanes), so for more than 8 partners the
+reference's own last bit is machine dependent; the kernel adds in partner order, which is what torch does below the SIMD
+width.  Results must agree to 2e-5 absolute + 1e-5 relative everywhere, and up to 5 agents at least 90 % of the
+collective rewards must be bit-identical."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ATOL, RTOL = 2e-5, 1e-5
+
+
+def _swarm():
+    import swarm_b200 as sb
+    return sb
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _close(got, want):
+    return torch.allclose(got, want, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("n", [2, 5, 12])
+def test_flocking_env_matches_oracle(n):
+    from oracle import scenario_rewards_oracle as sro
+    sb = _swarm()
+    B, T = 6, 25
+    g = torch.Generator().manual_seed(n)
+    centers = torch.tensor([-1.0, 1.0]) + torch.tensor([-0.6, 0.6]) + 0.4 * torch.randn(B, 2, generator=g)
+    scenario = sb.FlockingScenario()
+    env = sb.Environment(scenario, num_envs=B, device=_dev(), max_steps=T, continuous_actions=False, seed=0,
+                         dict_spaces=True, n_agents=n)
+    scenario.set_start_centers(centers)
+    obs = env.reset()
+    assert obs["agent0"].shape == (B, 6)
+    oracles = [sro.FlockingOracle(n) for _ in range(B)]
+    for b, orc in enumerate(oracles):
+        orc.reset(centers[b])
+        pos, _ = orc.world.state()
+        assert torch.equal(env.world.state[b, :, 0:2].cpu(), pos), "start grid"
+        assert _close(scenario.previous_distance_to_goal[b].cpu(), torch.cat(orc.previous_distance_to_goal))
+        assert _close(scenario.previous_distance_to_agents[b].cpu(), torch.cat(orc.previous_distance_to_agents))
+    exact = total = 0
+    for t in range(T):
+        # head for the goal most of the time so that agents bunch up, touch and reach the goal
+        act = torch.randint(0, 9, (B, n), generator=g)
+        act = torch.where(torch.rand(B, n, generator=g) < 0.7, torch.full_like(act, 5), act)     # 5 = (-1, +1)
+        obs, rews, dones, infos = env.step({f"agent{i}": act[:, i] for i in range(n)})
+        state = env.world.state.cpu()
+        for b, orc in enumerate(oracles):
+            orc.world.set_state(state[b, :, 0:2], state[b, :, 2:4])
+            want = orc.reward()
+            got = rews["agent0"][b].cpu()
+            assert _close(got, want[0]), (t, b, float(got), float(want))
+            exact += int(got == want[0])
+            total += 1
+            assert _close(infos["agent0"]["pos_rew"][b].cpu(), orc.pos_rew[0][0])
+        for i in range(1, n):
+            assert torch.equal(rews[f"agent{i}"], rews["agent0"])         # one collective reward for everybody
+        assert obs["agent0"].shape == (B, 6) and torch.equal(obs["agent0"][:, 4:6].cpu(), torch.tensor([[-0.8, 0.8]] * B))
+    if n <= 5:
+        assert exact >= 0.9 * total, f"only {exact} / {total} collective rewards bit-identical"
+
+
+def test_flocking_contacts_goal_bonus_and_reset_at():
+    """Hand-placed states on the decision boundaries: surface gap just inside / outside 0.005, an agent just inside /
+    outside the goal radius; then reset_at(1) re-initialises the memory of that env only."""
+    from oracle import scenario_rewards_oracle as sro
+    sb = _swarm()
+    n, B = 4, 3
+    scenario = sb.FlockingScenario()
+    env = sb.Environment(scenario, num_envs=B, device=_dev(), max_steps=10, continuous_actions=False, seed=3,
+                         dict_spaces=True, n_agents=n)
+    centers = torch.tensor([[0.1, 0.1], [-0.3, 0.4], [0.5, -0.2]])
+    scenario.set_start_centers(centers)
+    env.reset()
+    oracles = [sro.FlockingOracle(n) for _ in range(B)]
+    for b, orc in enumerate(oracles):
+        orc.reset(centers[b])
+    placed = torch.tensor([
+        [[-0.8, 0.8 + 0.0499], [0.0, 0.0], [0.1049, 0.0], [0.5, 0.5]],          # on goal; pair gap 0.0049
+        [[-0.8, 0.8 + 0.0501], [0.0, 0.0], [0.1051, 0.0], [0.5, 0.5]],          # just off goal; pair gap 0.0051
+        [[-0.8, 0.8], [0.3, 0.3], [0.3, 0.3], [0.3, 0.4]],                      # coincident pair + a touching third
+    ])
+    env.world.state[:, :, 0:2] = placed.to(_dev())
+    got, terms = sb.ops.scenario_reward(scenario._spec(), env.world.state, scenario.shaping, want_terms=True)
+    for b, orc in enumerate(oracles):
+        orc.world.set_state(placed[b], torch.zeros(n, 2))
+        want = orc.reward()
+        assert _close(got[b].cpu(), want[0]), (b, float(got[b]), float(want))
+    terms = terms.cpu()
+    assert terms[0, 0, 3] < 0.05 <= terms[1, 0, 3]                               # distance_to_goal either side of the radius
+    assert terms[0, 1, 1] == -1.0 and terms[0, 2, 1] == -1.0 and terms[0, 3, 1] == 0.0
+    assert (terms[1, :, 1] == 0.0).all()
+    # env 2: agents 1 and 2 coincide and agent 3 touches both (centre distance 0.1 -> gap 0): two penalties each
+    assert terms[2, 0, 1] == 0.0 and (terms[2, 1:, 1] == -2.0).all()
+    # reset_at(1): env 1 back on its grid with fresh memory, envs 0 and 2 untouched
+    before = scenario.shaping.clone()
+    env.reset_at(1)
+    oracles[1].reset(centers[1])
+    assert torch.equal(scenario.shaping[0], before[0]) and torch.equal(scenario.shaping[2], before[2])
+    assert _close(scenario.previous_distance_to_goal[1].cpu(), torch.cat(oracles[1].previous_distance_to_goal))
+    assert _close(scenario.previous_distance_to_agents[1].cpu(), torch.cat(oracles[1].previous_distance_to_agents))
+    assert torch.equal(env.world.state[1, :, 0:2].cpu(), oracles[1].world.state()[0])
+
+
+def test_flocking_seeded_reset_follows_the_reference_generator_stream():
+    """Without explicit centres the reset draws what flocking:94-98 and :70-71 draw, in that order."""
+    from oracle import scenario_rewards_oracle as sro
+    sb = _swarm()
+    n = 5
+    env = sb.make_env(scenario=sb.FlockingScenario(), num_envs=1, device=_dev(), continuous_actions=False,
+                      max_steps=5, dict_spaces=True, seed=42, n_agents=n)
+    after = torch.rand(1)
+    torch.manual_seed(42)
+    orc = sro.FlockingOracle(n)
+    orc.reset()
+    assert torch.equal(after, torch.rand(1))
+    assert torch.equal(env.world.state[0, :, 0:2].cpu(), orc.world.state()[0])
+
+
+@pytest.mark.parametrize("n", [2, 9])
+def test_cohesion_env_matches_oracle(n):
+    from oracle import scenario_rewards_oracle as sro
+    sb = _swarm()
+    B, T = 5, 20
+    g = torch.Generator().manual_seed(7 + n)
+    scenario = sb.CohesionScenario()
+    env = sb.Environment(scenario, num_envs=B, device=_dev(), max_steps=T, continuous_actions=False, seed=0,
+                         dict_spaces=True, n_agents=n)
+    assert env.observation_space["agent0"].shape == (4,)
+    obs = env.reset()
+    assert obs["agent0"].shape == (B, 4)
+    oracles = [sro.CohesionOracle(n) for _ in range(B)]
+    for b, orc in enumerate(oracles):
+        orc.reset()
+        assert torch.equal(env.world.state[b].cpu(), torch.cat(orc.world.state(), dim=1))
+    start = scenario.all_rewards().cpu()
+    for b, orc in enumerate(oracles):
+        assert _close(start[b], orc.reward())
+    for t in range(T):
+        act = torch.randint(0, 9, (B, n), generator=g)
+        obs, rews, dones, infos = env.step({f"agent{i}": act[:, i] for i in range(n)})
+        state = env.world.state.cpu()
+        got = torch.stack([rews[f"agent{i}"] for i in range(n)], dim=1).cpu()
+        for b, orc in enumerate(oracles):
+            orc.world.set_state(state[b, :, 0:2], state[b, :, 2:4])
+            assert _close(got[b], orc.reward()), (t, b)
+        assert torch.equal(obs["agent1"].cpu(), state[:, 1])
+    # both branches of cohesion:80,83 at sigma, and agents closer than sigma
+    placed = torch.zeros(B, n, 2)
+    placed[:, 1, 0] = torch.tensor([0.2, 0.25, 0.2500001, 0.3, 1.0])             # gaps 0.1, 0.15, ~0.15, 0.2, 0.9
+    if n > 2:
+        placed[:, 2:, 1] = 2.0 + torch.arange(n - 2).float().view(1, -1)
+    env.world.state.zero_()
+    env.world.state[:, :, 0:2] = placed.to(_dev())
+    env.world.version += 1
+    got = scenario.all_rewards().cpu()
+    for b, orc in enumerate(oracles):
+        orc.world.set_state(placed[b], torch.zeros(n, 2))
+        assert _close(got[b], orc.reward()), b
+    assert got[0, 0] > 0.5                                                       # exp(-(0.1 / 0.15)): the reference's sign
+
+
+def test_scenario_reward_argument_errors():
+    sb = _swarm()
+    ops = sb.ops
+    state = torch.zeros(4, 1, 4, device=_dev())
+    with pytest.raises(ValueError):
+        ops.scenario_reward(ops.reward_spec(sb._lib.REWARD_COHESION, 4, 1), state)          # one agent
+    state = torch.zeros(4, 3, 4, device=_dev())
+    with pytest.raises(ValueError):
+        ops.scenario_reward(ops.reward_spec(sb._lib.REWARD_FLOCKING, 4, 3), state)          # no shaping buffer
+    with pytest.raises(RuntimeError):                                                       # index errors, like torch
+        ops.scenario_reward(ops.reward_spec(sb._lib.REWARD_COHESION, 4, 3), state, env_index=4)
+    with pytest.raises(IndexError):
+        sb.Environment(sb.CohesionScenario(), num_envs=2, device=_dev(), continuous_actions=False, n_agents=10)
+    # zero envs is a no-op
+    empty = torch.zeros(0, 3, 4, device=_dev())
+    assert ops.scenario_reward(ops.reward_spec(sb._lib.REWARD_COHESION, 0, 3), empty).shape == (0, 3)
+
+
+def test_scenario_reward_full_size_properties():
+    """C2-sized batch (4096 envs x 12 agents): replicated envs give replicated rewards, a second call on an unchanged
+    state returns only bonuses / penalties (the shaping memory moved), permutation of envs permutes the rewards."""
+    sb = _swarm()
+    ops = sb.ops
+    B, n = 4096, 12
+    g = torch.Generator().manual_seed(0)
+    base = torch.randn(64, n, 4, generator=g) * 0.3
+    state = base.repeat(B // 64, 1, 1).contiguous().to(_dev())
+    spec = ops.reward_spec(sb._lib.REWARD_FLOCKING, B, n)
+    shaping = torch.zeros(B, n, 2, device=_dev())
+    ops.scenario_reward(spec, state, shaping, reset=True)
+    moved = (state + 0.01).contiguous()
+    r1, t1 = ops.scenario_reward(spec, moved, shaping, want_terms=True)
+    assert torch.equal(r1.view(-1, 64), r1[:64].view(1, 64).expand(B // 64, 64))
+    r2, t2 = ops.scenario_reward(spec, moved, shaping, want_terms=True)
+    assert (t2[:, :, 0] == 0).all() and (t2[:, :, 2] == 0).all()                 # no progress on an unchanged state
+    assert torch.equal(t2[:, :, 1], t1[:, :, 1])
+    perm = torch.randperm(B, generator=g).to(_dev())
+    shaping_p = torch.zeros(B, n, 2, device=_dev())
+    ops.scenario_reward(spec, state[perm].contiguous(), shaping_p, reset=True)
+    rp = ops.scenario_reward(spec, moved[perm].contiguous(), shaping_p)
+    assert torch.equal(rp, r1[perm])
+    cspec = ops.reward_spec(sb._lib.REWARD_COHESION, B, n)
+    rc = ops.scenario_reward(cspec, state)
+    assert torch.equal(rc[perm], ops.scenario_reward(cspec, state[perm].contiguous()))
+    assert torch.isfinite(rc).all()
