@@ -551,6 +551,8 @@ int swarm_scenario_reward(const SwarmRewardSpec* spec, const float* state, float
   if (spec->n_agents > 128) return fail(SWARM_ERR_UNSUPPORTED, "scenario rewards are implemented for n_agents <= 128");
   if (spec->env_index < -1 || spec->env_index >= spec->num_envs)
     return fail(SWARM_ERR_INVALID_ARG, "env_index out of range");
+  if ((int64_t)spec->num_envs * spec->n_agents + 128 * 148 * 16 >= (1LL << 31))
+    return fail(SWARM_ERR_UNSUPPORTED, "num_envs * n_agents must stay below 2^31");
   if (spec->num_envs == 0) return SWARM_OK;
   if (!state) return fail(SWARM_ERR_INVALID_ARG, "state is NULL");
   if (spec->kind == SWARM_REWARD_FLOCKING) {
