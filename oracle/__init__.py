@@ -14,4 +14,7 @@ Parity status: **pinned**.  ``tests/test_oracle_golden.py`` checks this oracle a
 own shipped artefacts (per-tick positions / distances / hits / result.csv of ``data/test_stats`` and
 the ``Episode,Reward,Loss`` rows of ``data/stats``; committed in compact form under ``tests/golden``
 by ``tests/golden/make_golden.py``).
+
+Exception: ``scenario_rewards_oracle.py`` (Flocking / Cohesion) is **parity unpinned** -- the reference ships no
+outputs for those scenarios; see that file's header.
 """
