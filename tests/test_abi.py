@@ -173,3 +173,50 @@ def test_training_argument_validation_without_device(sb):
     assert lib.swarm_reset_random(C.byref(cfg), C.byref(sp), None, -1, None, 8, None) == -1
     assert lib.swarm_episode_end(C.byref(cfg), None, 8, None, None, None, 0, 0.9, 0.01, 0.05, None) == -1
     assert lib.swarm_episode_end(C.byref(cfg), 8, 8, None, None, 8, 0, 0.9, 0.01, 0.05, None) == -1     # stats without rows
+
+
+def test_reward_spec_layout_defaults_and_validation(sb, tmp_path):
+    """SwarmRewardSpec (Flocking / Cohesion rewards): byte layout against the header, reference constants as defaults
+    (flocking:10-21,96,142; cohesion:23) and argument checks that need no device."""
+    fs = ["kind", "num_envs", "n_agents", "reset", "env_index", "goal_x", "goal_radius", "agent_radius", "pos_shaping",
+          "dist_shaping", "desired_distance", "min_collision_distance", "collision_reward", "on_goal_bonus", "sigma"]
+    body = 'printf("%zu ", sizeof(SwarmRewardSpec));' + "".join(f'printf("%zu ", offsetof(SwarmRewardSpec, {f}));' for f in fs)
+    prog = tmp_path / "layout3.c"
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "swarm_b200.h"\nint main(){' + body + 'return 0;}')
+    exe = tmp_path / "layout3"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
+    L, lib = sb._lib, sb._lib.lib()
+    assert got == [C.sizeof(L.SwarmRewardSpec)] + [getattr(L.SwarmRewardSpec, f).offset for f in fs]
+
+    sp = sb.ops.reward_spec(L.REWARD_FLOCKING, 16, 5)
+    assert (sp.kind, sp.num_envs, sp.n_agents, sp.reset, sp.env_index) == (0, 16, 5, 0, -1)
+    assert (sp.goal_x, sp.goal_y) == (pytest.approx(-0.8), pytest.approx(0.8))
+    assert (sp.pos_shaping, sp.dist_shaping, sp.on_goal_bonus, sp.collision_reward) == (10.0, 10.0, 50.0, -1.0)
+    assert sp.desired_distance == pytest.approx(0.15) and sp.min_collision_distance == pytest.approx(0.005)
+    assert sp.goal_radius == pytest.approx(0.05) and sp.agent_radius == pytest.approx(0.05) and sp.sigma == pytest.approx(0.15)
+    with pytest.raises(TypeError):
+        sb.ops.reward_spec(L.REWARD_FLOCKING, 16, 5, no_such_field=1.0)
+
+    call = lambda s, shaping=8, reward=8: lib.swarm_scenario_reward(C.byref(s), 8, shaping, reward, None, None)
+    assert lib.swarm_scenario_reward(None, 8, 8, 8, None, None) == -1
+    assert call(sp, shaping=None) == -1 and b"shaping" in lib.swarm_last_error()
+    assert call(sp, reward=None) == -1
+    sp.reset = 1
+    sp.n_agents = 1
+    assert call(sp) == -1 and b"two agents" in lib.swarm_last_error()
+    sp.n_agents = 129
+    assert call(sp) == -2                                             # SWARM_ERR_UNSUPPORTED
+    sp.n_agents, sp.env_index = 5, 16
+    assert call(sp) == -1 and b"env_index" in lib.swarm_last_error()
+    sp.env_index, sp.kind = -1, 7
+    assert call(sp) == -1
+    co = sb.ops.reward_spec(L.REWARD_COHESION, 16, 9)
+    co.reset = 1
+    assert call(co, shaping=None) == -1 and b"Cohesion" in lib.swarm_last_error()
+    co.reset, co.sigma = 0, 0.0
+    assert call(co, shaping=None) == -1 and b"sigma" in lib.swarm_last_error()
+    co.sigma, co.num_envs, co.n_agents = 0.15, 1 << 28, 12
+    assert call(co, shaping=None) == -2                               # beyond the kernel's 32-bit row index
+    co.num_envs = 0
+    assert call(co, shaping=None, reward=None) == 0                   # nothing to do
