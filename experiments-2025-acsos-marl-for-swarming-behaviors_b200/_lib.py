@@ -113,6 +113,10 @@ _SIGNATURES = {
     "swarm_gatq_forward_knn_large": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 6),
     "swarm_gatconv_forward_csr": (C.c_int, [C.c_int32] + [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]),
     "swarm_gatconv_backward_csr": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 11 + [C.c_int64, C.c_void_p]),
+    "swarm_gat_layer_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
+    "swarm_gat_layer_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 9 + [C.c_int64, C.c_void_p]),
+    "swarm_gat_layer_backward": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 17 +
+                                 [C.c_int64, C.c_void_p]),
     "swarm_gatq_backward_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64]),
     "swarm_gatq_backward_csr": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 11 + [C.c_int64, C.c_void_p]),
     "swarm_csr_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64]),

@@ -15,6 +15,15 @@ cudaError_t launch_graph_large(const SwarmConfig& c, const float* state, int32_t
                                cudaStream_t stream);
 cudaError_t launch_reset_grid(const SwarmConfig& c, int cols, int rows, const float* centers, float* state,
                               cudaStream_t stream);
+long long gat_layer_workspace_bytes(int n, long long E, int ci, int co, bool backward);
+cudaError_t launch_gat_layer_forward(int n, int ci, int co, const float* W, const float* a_src, const float* a_dst,
+                                     const float* bias, const float* x, const int32_t* row_ptr, const int32_t* src,
+                                     float* out, void* workspace, cudaStream_t stream);
+cudaError_t launch_gat_layer_backward(int n, long long E, int ci, int co, const float* W, const float* a_src,
+                                      const float* a_dst, const float* x, const int32_t* row_ptr, const int32_t* src,
+                                      const int32_t* perm, const int32_t* row_ptr_s, const int32_t* tgt_s,
+                                      const int32_t* perm_s, const float* grad_out, float* gW, float* gas, float* gad,
+                                      float* gb, float* grad_x, void* workspace, cudaStream_t stream);
 cudaError_t launch_scenario_reward(const SwarmRewardSpec& sp, const float* state, float* shaping, float* reward,
                                    float* terms, cudaStream_t stream);
 cudaError_t launch_reset_random(const SwarmConfig& c, const SwarmResetSpec& sp, int cols, int rows, const SwarmTrainCtl* ctl,
@@ -298,6 +307,57 @@ int swarm_gatconv_backward_csr(int32_t n_nodes, int64_t n_edges, const float* we
   return check_cuda(launch_gatq_backward_csr(n_nodes, n_edges, weights, x, row_ptr, src, perm, row_ptr_s, tgt_s, perm_s,
                                              grad_out, grad_weights, workspace, (cudaStream_t)stream, true),
                     "swarm_gatconv_backward_csr");
+}
+
+static int gat_layer_check_dims(int32_t n_nodes, int64_t n_edges, int32_t ci, int32_t co) {
+  if (n_nodes < 0 || n_edges < 0) return fail(SWARM_ERR_INVALID_ARG, "n_nodes and n_edges must be >= 0");
+  if (n_edges >= (1LL << 31)) return fail(SWARM_ERR_UNSUPPORTED, "more than 2^31 - 1 edges");
+  if (ci < 1 || co < 1) return fail(SWARM_ERR_INVALID_ARG, "in_channels and out_channels must be >= 1");
+  if (ci > 64 || co > 64) return fail(SWARM_ERR_UNSUPPORTED, "the GAT layer kernels cover in_channels, out_channels <= 64");
+  if ((int64_t)n_nodes * 68 >= (1LL << 31)) return fail(SWARM_ERR_UNSUPPORTED, "too many nodes for one call");
+  return SWARM_OK;
+}
+
+int64_t swarm_gat_layer_workspace_bytes(int32_t n_nodes, int64_t n_edges, int32_t in_channels, int32_t out_channels,
+                                        int32_t backward) {
+  if (gat_layer_check_dims(n_nodes, n_edges, in_channels, out_channels)) return -1;
+  return gat_layer_workspace_bytes(n_nodes, n_edges, in_channels, out_channels, backward != 0);
+}
+
+int swarm_gat_layer_forward(int32_t n_nodes, int32_t in_channels, int32_t out_channels, const float* lin_weight,
+                            const float* att_src, const float* att_dst, const float* bias, const float* x,
+                            const int32_t* row_ptr, const int32_t* src, float* out, void* workspace,
+                            int64_t workspace_bytes, void* stream) {
+  if (int rc = gat_layer_check_dims(n_nodes, 0, in_channels, out_channels)) return rc;
+  if (n_nodes == 0) return SWARM_OK;
+  if (!lin_weight || !att_src || !att_dst || !bias || !x || !row_ptr || !out || !workspace)
+    return fail(SWARM_ERR_INVALID_ARG, "NULL argument");
+  if (workspace_bytes < gat_layer_workspace_bytes(n_nodes, 0, in_channels, out_channels, false))
+    return fail(SWARM_ERR_INVALID_ARG, "workspace too small");
+  return check_cuda(launch_gat_layer_forward(n_nodes, in_channels, out_channels, lin_weight, att_src, att_dst, bias, x,
+                                             row_ptr, src, out, workspace, (cudaStream_t)stream),
+                    "swarm_gat_layer_forward");
+}
+
+int swarm_gat_layer_backward(int32_t n_nodes, int64_t n_edges, int32_t in_channels, int32_t out_channels,
+                             const float* lin_weight, const float* att_src, const float* att_dst, const float* x,
+                             const int32_t* row_ptr, const int32_t* src, const int32_t* perm, const int32_t* row_ptr_s,
+                             const int32_t* tgt_s, const int32_t* perm_s, const float* grad_out, float* grad_lin_weight,
+                             float* grad_att_src, float* grad_att_dst, float* grad_bias, float* grad_x, void* workspace,
+                             int64_t workspace_bytes, void* stream) {
+  if (int rc = gat_layer_check_dims(n_nodes, n_edges, in_channels, out_channels)) return rc;
+  if (n_nodes == 0) return fail(SWARM_ERR_INVALID_ARG, "n_nodes must be > 0");
+  if (!lin_weight || !att_src || !att_dst || !x || !row_ptr || !row_ptr_s || !grad_out || !grad_lin_weight ||
+      !grad_att_src || !grad_att_dst || !grad_bias || !workspace)
+    return fail(SWARM_ERR_INVALID_ARG, "NULL argument");
+  if (n_edges > 0 && (!src || !perm || !tgt_s || !perm_s)) return fail(SWARM_ERR_INVALID_ARG, "NULL edge array");
+  if (workspace_bytes < gat_layer_workspace_bytes(n_nodes, n_edges, in_channels, out_channels, true))
+    return fail(SWARM_ERR_INVALID_ARG, "workspace too small");
+  return check_cuda(launch_gat_layer_backward(n_nodes, n_edges, in_channels, out_channels, lin_weight, att_src, att_dst, x,
+                                              row_ptr, src, perm, row_ptr_s, tgt_s, perm_s, grad_out, grad_lin_weight,
+                                              grad_att_src, grad_att_dst, grad_bias, grad_x, workspace,
+                                              (cudaStream_t)stream),
+                    "swarm_gat_layer_backward");
 }
 
 int64_t swarm_gatq_backward_workspace_bytes(int32_t n_nodes, int64_t n_edges) {

@@ -58,13 +58,35 @@ class _GatConvFunction(torch.autograd.Function):
         return grad_w, None, None
 
 
+class _GatLayerFunction(torch.autograd.Function):
+    """One GATConv layer of any width <= 64 (swarm_gat_layer_forward / swarm_gat_layer_backward): differentiable w.r.t.
+    its four parameters and the node features, so layers stack under autograd."""
+
+    @staticmethod
+    def forward(ctx, x, lin_weight, att_src, att_dst, bias, edge_index):
+        x, lin_weight = x.detach().contiguous(), lin_weight.detach().contiguous()
+        att_src, att_dst, bias = (t.detach().reshape(-1).contiguous() for t in (att_src, att_dst, bias))
+        row_ptr, src, perm = ops.csr_from_edges(edge_index, x.shape[0])
+        out = ops.gat_layer_forward(lin_weight, att_src, att_dst, bias, x, row_ptr, src)
+        ctx.save_for_backward(x, lin_weight, att_src, att_dst, edge_index, row_ptr, src, perm)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, lin_weight, att_src, att_dst, edge_index, row_ptr, src, perm = ctx.saved_tensors
+        gw, gas, gad, gb, gx = ops.gat_layer_backward(lin_weight, att_src, att_dst, x, edge_index, grad_out.contiguous(),
+                                                      want_grad_x=ctx.needs_input_grad[0], by_target=(row_ptr, src, perm))
+        return gx, gw, gas.view(1, 1, -1), gad.view(1, 1, -1), gb, None
+
+
 class GATConv(nn.Module):
     """GATConv(in, out, heads=1, add_self_loops=False, bias=True) (train:53).  Keys: ``att_src`` [1,1,out],
     ``att_dst`` [1,1,out], ``bias`` [out], ``lin.weight`` [out,in].  The projection is initialised twice, like
     torch_geometric (Linear.__init__ followed by GATConv.reset_parameters).  Inside ``swarm_b200.GCN`` it is a parameter
     container (the whole network is one fused call); called on its own -- ``conv(x, edge_index)`` as the reference's
-    ``GCN.forward`` does (train:61) -- it runs the layer alone in the CUDA kernels, differentiable w.r.t. its
-    parameters (the node features are data: no gradient flows into ``x``)."""
+    ``GCN.forward`` does (train:61) -- it runs the layer alone in the CUDA kernels: the (7 -> 32) first layer on data
+    through the kernels of the fused network, any other width up to 64 (or an input that needs a gradient, i.e. a
+    stacked layer) through the generic layer kernels, differentiable w.r.t. parameters and node features."""
 
     def __init__(self, in_channels: int, out_channels: int, heads: int = 1, add_self_loops: bool = False,
                  bias: bool = True):
@@ -85,16 +107,17 @@ class GATConv(nn.Module):
         self.bias.data.zero_()
 
     def forward(self, x: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
-        if (self.in_channels, self.out_channels) != (_FEAT, _HIDDEN):
-            raise NotImplementedError(f"the swarm_b200 kernels implement GATConv({_FEAT}, {_HIDDEN})")
         if not x.is_cuda:
             raise _lib.SwarmError("GATConv.forward runs on CUDA tensors only (swarm_b200 has no CPU fallback)")
-        if x.requires_grad:
-            raise NotImplementedError("gradients w.r.t. the node features are not implemented (first layer only)")
+        edge_index = edge_index.to(torch.int64).contiguous()
+        if (self.in_channels, self.out_channels) != (_FEAT, _HIDDEN) or x.requires_grad:
+            if self.in_channels > 64 or self.out_channels > 64:
+                raise NotImplementedError("the swarm_b200 GAT layer kernels cover in_channels, out_channels <= 64")
+            return _GatLayerFunction.apply(x, self.lin.weight, self.att_src, self.att_dst, self.bias, edge_index)
         head = torch.zeros(_lib.W_COUNT - 320, dtype=torch.float32, device=x.device)
         packed = torch.cat([self.lin.weight.reshape(-1), self.att_src.reshape(-1), self.att_dst.reshape(-1),
                             self.bias.reshape(-1), head])
-        return _GatConvFunction.apply(packed, x.contiguous(), edge_index.to(torch.int64).contiguous())
+        return _GatConvFunction.apply(packed, x.contiguous(), edge_index)
 
 
 class _GatQFunction(torch.autograd.Function):

@@ -491,6 +491,53 @@ def gatq_backward_csr(weights: torch.Tensor, x: torch.Tensor, edge_index: torch.
     return grad
 
 
+def gat_layer_forward(lin_weight: torch.Tensor, att_src: torch.Tensor, att_dst: torch.Tensor, bias: torch.Tensor,
+                      x: torch.Tensor, row_ptr: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    """One GATConv(in, out, heads=1) layer of any width <= 64: x f32[n,in] + CSR-by-target -> f32[n,out]."""
+    n, ci = x.shape
+    co = lin_weight.shape[0]
+    _expect(lin_weight, torch.float32, co * ci, "lin_weight")
+    for name, t in (("att_src", att_src), ("att_dst", att_dst), ("bias", bias)):
+        _expect(t, torch.float32, co, name)
+    _expect(row_ptr, torch.int32, n + 1, "row_ptr")
+    dev = x.device
+    out = torch.empty(n, co, dtype=torch.float32, device=dev)
+    wb = int(lib().swarm_gat_layer_workspace_bytes(n, 0, ci, co, 0))
+    if wb < 0:
+        check(-1 if "must be" in lib().swarm_last_error().decode() else -2)
+    ws = torch.empty(max(wb, 1), dtype=torch.uint8, device=dev)
+    check(lib().swarm_gat_layer_forward(n, ci, co, ptr(lin_weight.contiguous()), ptr(att_src.contiguous()),
+                                        ptr(att_dst.contiguous()), ptr(bias.contiguous()), ptr(x.contiguous()), ptr(row_ptr),
+                                        ptr(src), ptr(out), ptr(ws), wb, stream_ptr(dev)))
+    return out
+
+
+def gat_layer_backward(lin_weight: torch.Tensor, att_src: torch.Tensor, att_dst: torch.Tensor, x: torch.Tensor,
+                       edge_index: torch.Tensor, grad_out: torch.Tensor, want_grad_x: bool = True,
+                       by_target: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None):
+    """Backward of gat_layer_forward: -> (grad_lin_weight f32[out,in], grad_att_src f32[out], grad_att_dst f32[out],
+    grad_bias f32[out], grad_x f32[n,in] or None)."""
+    n, ci = x.shape
+    co = lin_weight.shape[0]
+    E = edge_index.shape[1]
+    _expect(grad_out, torch.float32, n * co, "grad_out")
+    dev = x.device
+    row_ptr, src, perm = by_target if by_target is not None else csr_from_edges(edge_index, n)
+    row_ptr_s, tgt_s, perm_s = csr_from_edges(edge_index.flip(0).contiguous(), n)
+    gw = torch.empty(co, ci, dtype=torch.float32, device=dev)
+    gas, gad, gb = (torch.empty(co, dtype=torch.float32, device=dev) for _ in range(3))
+    gx = torch.empty(n, ci, dtype=torch.float32, device=dev) if want_grad_x else None
+    wb = int(lib().swarm_gat_layer_workspace_bytes(n, E, ci, co, 1))
+    if wb < 0:
+        check(-2)
+    ws = torch.empty(max(wb, 1), dtype=torch.uint8, device=dev)
+    check(lib().swarm_gat_layer_backward(n, E, ci, co, ptr(lin_weight.contiguous()), ptr(att_src.contiguous()),
+                                         ptr(att_dst.contiguous()), ptr(x.contiguous()), ptr(row_ptr), ptr(src), ptr(perm),
+                                         ptr(row_ptr_s), ptr(tgt_s), ptr(perm_s), ptr(grad_out.contiguous()), ptr(gw),
+                                         ptr(gas), ptr(gad), ptr(gb), ptr(gx), ptr(ws), wb, stream_ptr(dev)))
+    return gw, gas, gad, gb, gx
+
+
 def rollout_large(cfg: SwarmConfig, weights: torch.Tensor, state: torch.Tensor, ticks: int,
                   returns: Optional[torch.Tensor] = None, hits: Optional[torch.Tensor] = None,
                   trace_state: bool = False, fused: bool = True) -> Dict[str, torch.Tensor]:

@@ -190,6 +190,28 @@ int swarm_gatconv_backward_csr(int32_t n_nodes, int64_t n_edges, const float* we
                                const int32_t* tgt_s, const int32_t* perm_s, const float* grad_out, float* grad_weights,
                                void* workspace, int64_t workspace_bytes, void* stream);
 
+/* One single-head GATConv layer of any small width (EXTENSION towards SURVEY.md 8f rank 4, multi-layer attention
+ * networks such as the three 8-wide layers of the reference's data/models/experiment_Flocking-seed_*.pth):
+ * torch_geometric.nn.GATConv(in_channels, out_channels, heads=1, add_self_loops=False, bias=True), 1 <= in_channels,
+ * out_channels <= 64, on an arbitrary graph given as for swarm_gatq_forward_csr / swarm_gatq_backward_csr.
+ *   forward : lin_weight float[out][in], att_src / att_dst / bias float[out], x float[n][in] -> out float[n][out]
+ *   backward: grad_out float[n][out] -> grad_lin_weight, grad_att_src, grad_att_dst, grad_bias (overwritten) and,
+ *             when grad_x != NULL, grad_x float[n][in] -- so layers can be stacked under torch autograd.
+ * Gather-only with fixed reduction orders: results are bit-reproducible.  Workspace in bytes from
+ * swarm_gat_layer_workspace_bytes(n, E, in, out, backward != 0). */
+int64_t swarm_gat_layer_workspace_bytes(int32_t n_nodes, int64_t n_edges, int32_t in_channels, int32_t out_channels,
+                                        int32_t backward);
+int swarm_gat_layer_forward(int32_t n_nodes, int32_t in_channels, int32_t out_channels, const float* lin_weight,
+                            const float* att_src, const float* att_dst, const float* bias, const float* x,
+                            const int32_t* row_ptr, const int32_t* src, float* out, void* workspace,
+                            int64_t workspace_bytes, void* stream);
+int swarm_gat_layer_backward(int32_t n_nodes, int64_t n_edges, int32_t in_channels, int32_t out_channels,
+                             const float* lin_weight, const float* att_src, const float* att_dst, const float* x,
+                             const int32_t* row_ptr, const int32_t* src, const int32_t* perm, const int32_t* row_ptr_s,
+                             const int32_t* tgt_s, const int32_t* perm_s, const float* grad_out, float* grad_lin_weight,
+                             float* grad_att_src, float* grad_att_dst, float* grad_bias, float* grad_x, void* workspace,
+                             int64_t workspace_bytes, void* stream);
+
 /* Device replay ring of whole-swarm transitions (GraphReplayBuffer, train_gcn_dqn.py:25-48, capacity 1e6 at
  * train:86).  Only the world state is stored (37 B per agent and transition); node features and graphs are
  * rebuilt from it on the fly. */

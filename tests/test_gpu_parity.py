@@ -521,5 +521,5 @@ def test_gatconv_layer_alone_forward_backward(exp, scenario):
     q_empty.sum().backward()                 # edgeless graph: only the bias / head gradients are non-zero
     assert float(fused.conv1.lin.weight.grad.abs().max()) == 0.0
     assert torch.allclose(fused.lin2.bias.grad.cpu(), torch.full((9,), 5.0))
-    with pytest.raises(NotImplementedError):
-        sb.GATConv(7, 16)(xe, torch.zeros(2, 0, dtype=torch.int64, device=_dev()))
+    with pytest.raises(NotImplementedError):              # widths beyond the generic layer kernels (tests/test_gpu_gat_layer.py)
+        sb.GATConv(7, 65).to(_dev())(xe, torch.zeros(2, 0, dtype=torch.int64, device=_dev()))
