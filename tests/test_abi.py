@@ -220,3 +220,23 @@ def test_reward_spec_layout_defaults_and_validation(sb, tmp_path):
     assert call(co, shaping=None) == -2                               # beyond the kernel's 32-bit row index
     co.num_envs = 0
     assert call(co, shaping=None, reward=None) == 0                   # nothing to do
+
+
+def test_gat_layer_argument_validation_without_device(sb):
+    lib = sb._lib.lib()
+    assert lib.swarm_gat_layer_workspace_bytes(100, 1000, 7, 8, 0) > 0
+    assert lib.swarm_gat_layer_workspace_bytes(100, 1000, 7, 8, 1) > lib.swarm_gat_layer_workspace_bytes(100, 1000, 7, 8, 0)
+    assert lib.swarm_gat_layer_workspace_bytes(100, 1000, 65, 8, 0) == -1 and b"<= 64" in lib.swarm_last_error()
+    assert lib.swarm_gat_layer_workspace_bytes(100, 1000, 7, 0, 0) == -1
+    fwd = lambda n, ci, co, w=8, ws=8, wb=1 << 30: lib.swarm_gat_layer_forward(n, ci, co, w, 8, 8, 8, 8, 8, 8, 8, ws, wb, None)
+    assert fwd(10, 7, 65) == -2
+    assert fwd(10, 0, 8) == -1
+    assert fwd(10, 7, 8, w=None) == -1 and b"NULL" in lib.swarm_last_error()
+    assert fwd(10, 7, 8, wb=16) == -1 and b"workspace" in lib.swarm_last_error()
+    assert fwd(0, 7, 8, w=None) == 0                                   # nothing to do
+    bwd = lambda n, E, src=8, gx=None, wb=1 << 30: lib.swarm_gat_layer_backward(
+        n, E, 7, 8, 8, 8, 8, 8, 8, src, 8, 8, 8, 8, 8, 8, 8, 8, 8, gx, 8, wb, None)
+    assert bwd(0, 0) == -1
+    assert bwd(10, 5, src=None) == -1 and b"edge" in lib.swarm_last_error()
+    assert bwd(10, 5, wb=64) == -1 and b"workspace" in lib.swarm_last_error()
+    assert bwd(10, 1 << 31) == -2
