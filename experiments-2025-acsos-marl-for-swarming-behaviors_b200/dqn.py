@@ -25,6 +25,7 @@ import torch
 from . import _lib, ops, parallel
 from .gcn import GCN
 from .graph import Batch, Data, node_features, stack_observations
+from .scenarios import _KernelScenario
 
 
 class GraphReplayBuffer:
@@ -189,7 +190,12 @@ class DQNTrainer:
                 else:
                     actions = self._policy_actions()
                 _, rewards, done, _ = self.env.step(actions)
-                rewards_dev = world.last["rewards"]
+                if isinstance(self.env.scenario, _KernelScenario):
+                    rewards_dev = world.last["rewards"]
+                else:
+                    # any other scenario (Flocking, a user's own): the rewards its reward() returned, f32[1, n]
+                    cols = [rewards[a.name] for a in self.env.agents] if isinstance(rewards, dict) else list(rewards)
+                    rewards_dev = torch.stack([c.reshape(-1).to(torch.float32) for c in cols], dim=1).contiguous()
                 ring = self.replay_buffer.ring
                 ops.replay_push(world.cfg, ring, state, actions.contiguous(), rewards_dev, world.state)
                 loss = self.train_step_dqn(32, self.model, self.target_model, ticks, update_target_every=200)
@@ -221,6 +227,9 @@ class DQNTrainer:
         all-reduce in between when data-parallel.  The tick counters live on the device, so with
         ``config["cuda_graph"]`` (default on) the ticks of one episode are captured once in a CUDA graph and each
         episode is a single graph launch."""
+        if not isinstance(self.env.scenario, _KernelScenario):
+            raise NotImplementedError("the fused train tick computes the GoTo / ObstacleAvoidance rewards in the kernel; "
+                                      "train other scenarios (Flocking, user-written) with train_model")
         env, world = self.env, self.env.world
         B, n, dev = env.num_envs, env.n_agents, env.device
         G = int(config.get("graphs_per_update", 32))
@@ -301,6 +310,9 @@ class DQNTrainer:
         statistics (train:179-199) all live on the device and the host only reads the statistics at the end.
         Per-env start centres come from the counter RNG (``shared_center`` reproduces the reference's one draw per
         reset).  Returns stats f32[episodes, 4] = (mean agent-0 return / N, hits per env, last loss, epsilon)."""
+        if not isinstance(self.env.scenario, _KernelScenario):
+            raise NotImplementedError("the fused train tick computes the GoTo / ObstacleAvoidance rewards in the kernel; "
+                                      "train other scenarios (Flocking, user-written) with train_model")
         env, world = self.env, self.env.world
         B, n, dev = env.num_envs, env.n_agents, env.device
         G = int(config.get("graphs_per_update", 32))

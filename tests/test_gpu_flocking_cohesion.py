@@ -216,3 +216,40 @@ def test_scenario_reward_full_size_properties():
     rc = ops.scenario_reward(cspec, state)
     assert torch.equal(rc[perm], ops.scenario_reward(cspec, state[perm].contiguous()))
     assert torch.isfinite(rc).all()
+
+
+def test_reference_training_loop_runs_on_flocking():
+    """DQNTrainer.train_model (the reference's num_envs = 1 loop, train:139-204) on a Flocking env: the transitions it
+    stores carry the Flocking collective reward (not the world-step kernel's GoTo reward), the update changes the
+    weights, losses are finite; the fused trainers refuse scenarios whose reward the tick kernel does not compute."""
+    sb = _swarm()
+    sb.set_seed(1)
+    n, T = 5, 40
+    env = sb.make_env(scenario=sb.FlockingScenario(), num_envs=1, device=_dev(), continuous_actions=False, wrapper=None,
+                      max_steps=T, dict_spaces=True, n_agents=n, seed=1)
+    trainer = sb.DQNTrainer(env, 1, "/tmp/swarm_models", "/tmp/swarm_stats", "Flocking", replay_capacity=512)
+    w0 = trainer.w.clone()
+    seen = []
+    step = env.step
+
+    def recording_step(actions):
+        out = step(actions)
+        seen.append(out[1]["agent0"].clone())
+        return out
+
+    env.step = recording_step
+    trainer.train_model({"epsilon": 0.99, "epsilon_decay": 0.01, "min_epsilon": 0.05, "episodes": 2, "verbose": False,
+                         "save": False})
+    assert len(seen) == 2 * T and len(trainer.episode_losses) == 2
+    assert all(torch.isfinite(torch.as_tensor(l)) for l in trainer.episode_losses) and trainer.episode_losses[1] > 0
+    assert not torch.equal(trainer.w, w0)
+    ring = trainer.replay_buffer.ring
+    stored = sb.ops.replay_gather(ring, torch.arange(2 * T, device=_dev(), dtype=torch.int64))["rewards"]
+    want = torch.stack(seen).reshape(2 * T, 1).expand(2 * T, n)
+    assert torch.equal(stored.reshape(2 * T, n), want), "the replay ring holds the Flocking collective reward"
+    goto_like = -torch.linalg.vector_norm(env.world.state[0, :, 0:2] - torch.tensor([-0.8, 0.8], device=_dev()), dim=-1).sum()
+    assert abs(float(seen[-1]) - float(goto_like)) > 1e-3, "and it is not the GoTo reward of the world-step kernel"
+    with pytest.raises(NotImplementedError):
+        trainer.train_model_batched({"epsilon": 0.5, "episodes": 1})
+    with pytest.raises(NotImplementedError):
+        trainer.train_model_device({"epsilon": 0.5, "episodes": 1})
