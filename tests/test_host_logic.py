@@ -150,3 +150,15 @@ def test_module_name_shim_exposes_the_vmas_and_pyg_surface():
         for m in ("make_world", "reset_world_at", "observation", "reward", "done", "info", "average_distance_to_goal",
                   "average_distance_to_obstacles", "obstacles_hits"):
             assert callable(getattr(cls, m)), (cls.__name__, m)
+
+
+def test_flocking_and_cohesion_scenarios_have_no_cpu_fallback():
+    """The two remaining reference scenarios are exported with the reference's kwargs; their worlds live on a CUDA
+    device like every other world of this package."""
+    import swarm_b200 as sb
+    for cls in (sb.FlockingScenario, sb.CohesionScenario):
+        sc = cls()
+        with pytest.raises(sb.SwarmError):
+            sc.env_make_world(2, "cpu", n_agents=3)
+        assert sc.n_agents == 3 and sc.desired_distance == 0.15 and sc.min_collision_distance == 0.005
+    assert len(sb.CohesionScenario._START) == 9                      # cohesion:46-56
