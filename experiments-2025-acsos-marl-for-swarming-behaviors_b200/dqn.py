@@ -165,6 +165,14 @@ class DQNTrainer:
         _, act = ops.gatq_forward(cfg, self.w, self.env.world.state, want_q=False)
         return act
 
+    def _rewards_tensor(self, rewards) -> torch.Tensor:
+        """The rewards of the tick just stepped as f32[B, n]: what the world-step kernel wrote for the two fused
+        scenarios, else what the scenario's reward() returned (Flocking, Cohesion, a user's own)."""
+        if isinstance(self.env.scenario, _KernelScenario):
+            return self.env.world.last["rewards"]
+        cols = [rewards[a.name] for a in self.env.agents] if isinstance(rewards, dict) else list(rewards)
+        return torch.stack([c.reshape(-1).to(torch.float32) for c in cols], dim=1).contiguous()
+
     def train_model(self, config):
         """train:139-204 for num_envs = 1, Python ``random`` exploration/sampling like the reference."""
         if self.env.num_envs != 1:
@@ -190,12 +198,7 @@ class DQNTrainer:
                 else:
                     actions = self._policy_actions()
                 _, rewards, done, _ = self.env.step(actions)
-                if isinstance(self.env.scenario, _KernelScenario):
-                    rewards_dev = world.last["rewards"]
-                else:
-                    # any other scenario (Flocking, a user's own): the rewards its reward() returned, f32[1, n]
-                    cols = [rewards[a.name] for a in self.env.agents] if isinstance(rewards, dict) else list(rewards)
-                    rewards_dev = torch.stack([c.reshape(-1).to(torch.float32) for c in cols], dim=1).contiguous()
+                rewards_dev = self._rewards_tensor(rewards)
                 ring = self.replay_buffer.ring
                 ops.replay_push(world.cfg, ring, state, actions.contiguous(), rewards_dev, world.state)
                 loss = self.train_step_dqn(32, self.model, self.target_model, ticks, update_target_every=200)
@@ -229,7 +232,7 @@ class DQNTrainer:
         episode is a single graph launch."""
         if not isinstance(self.env.scenario, _KernelScenario):
             raise NotImplementedError("the fused train tick computes the GoTo / ObstacleAvoidance rewards in the kernel; "
-                                      "train other scenarios (Flocking, user-written) with train_model")
+                                      "train other scenarios (Flocking, user-written) with train_model / train_model_stepwise")
         env, world = self.env, self.env.world
         B, n, dev = env.num_envs, env.n_agents, env.device
         G = int(config.get("graphs_per_update", 32))
@@ -303,6 +306,66 @@ class DQNTrainer:
         self.sync_modules()
         return stats
 
+    def train_model_stepwise(self, config) -> Dict[str, float]:
+        """B envs per tick for ANY scenario (Flocking, user-written): the reference's loop body (train:153-178) batched
+        over the envs with the scenario's own ``reward()``.  Per tick: greedy Q forward -> one exploration draw per env
+        (train:164) -> ``env.step`` -> replay push of the B transitions -> G slot indices -> ``swarm_dqn_grad`` ->
+        ``swarm_adam_clip_step`` (hard target sync every ``update_target_every`` ticks).  Exploration and sampling use a
+        torch device generator.  This is the general path (about ten launches per tick, no CUDA graph);
+        ``train_model_batched`` is the fused one for GoTo / ObstacleAvoidance."""
+        env, world = self.env, self.env.world
+        B, n, dev = env.num_envs, env.n_agents, env.device
+        G = int(config.get("graphs_per_update", 32))
+        every = int(config.get("update_target_every", 200))
+        gamma = float(config.get("gamma", 0.99))
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(int(config.get("sample_seed", self.seed)))
+        ring = self.replay_buffer.ring
+        cfg = ops.clone_config(self.graph_cfg, num_envs=B)
+        gcfg = ops.clone_config(self.graph_cfg, num_envs=G)
+        if ring.capacity < B:
+            raise ValueError("the replay ring must hold at least one tick of transitions")
+        epsilon = config["epsilon"]
+        ticks = int(config.get("start_tick", 0))
+        stats: Dict[str, float] = {}
+        for episode in range(config["episodes"]):
+            env.reset()
+            returns = torch.zeros(B, n, dtype=torch.float32, device=dev)
+            loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+            updates = 0
+            for _ in range(env.max_steps):
+                ticks += 1
+                state = world.state.clone()
+                _, greedy = ops.gatq_forward(cfg, self.w, world.state, want_q=False)
+                explore = torch.rand(B, 1, device=dev, generator=gen) < epsilon
+                rnd = torch.randint(0, 9, (B, n), device=dev, generator=gen, dtype=torch.int32)
+                actions = torch.where(explore, rnd, greedy.view(B, n).to(torch.int32)).contiguous()
+                _, rewards, _, _ = env.step(actions)
+                rewards_dev = self._rewards_tensor(rewards)
+                ops.replay_push(cfg, ring, state, actions, rewards_dev, world.state)
+                returns += rewards_dev
+                if len(ring) >= G:
+                    idx = torch.randint(0, len(ring), (G,), device=dev, generator=gen, dtype=torch.int64)
+                    ops.dqn_grad(gcfg, self.w, self.w_target, ring, idx, G, gamma=gamma, grad=self._grad, loss=self._loss)
+                    self.opt_step += 1
+                    ops.adam_clip_step(self.w, self._grad, self.exp_avg, self.exp_avg_sq, self.opt_step, self.lr,
+                                       self.betas, self.eps, self.max_norm,
+                                       target=self.w_target if ticks % every == 0 else None)
+                    loss_sum += self._loss
+                    updates += 1
+            epsilon = max(config["min_epsilon"], config["epsilon"] * np.exp(-config["epsilon_decay"] * episode))
+            stats = {"episode": episode, "mean_return_agent0": float(returns[:, 0].mean() / n),
+                     "loss": float(loss_sum.item()) / max(updates, 1), "ticks": ticks, "opt_steps": self.opt_step}
+            self.episode_losses.append(stats["loss"])
+            self.rewards_buffer.append(torch.tensor(stats["mean_return_agent0"]))
+            if (episode + 1) % 10 == 0:
+                self.episode_rewards.append(sum(self.rewards_buffer) / 10)
+                self.rewards_buffer = []
+            if config.get("verbose", False):
+                print(stats)
+        self.sync_modules()
+        return stats
+
     def train_model_device(self, config) -> torch.Tensor:
         """Whole training run on the device: every episode is ONE replay of a CUDA graph holding
         [swarm_reset_random -> max_steps x (swarm_train_tick_grad, gradient all-reduce, swarm_train_tick_apply) ->
@@ -312,7 +375,7 @@ class DQNTrainer:
         reset).  Returns stats f32[episodes, 4] = (mean agent-0 return / N, hits per env, last loss, epsilon)."""
         if not isinstance(self.env.scenario, _KernelScenario):
             raise NotImplementedError("the fused train tick computes the GoTo / ObstacleAvoidance rewards in the kernel; "
-                                      "train other scenarios (Flocking, user-written) with train_model")
+                                      "train other scenarios (Flocking, user-written) with train_model / train_model_stepwise")
         env, world = self.env, self.env.world
         B, n, dev = env.num_envs, env.n_agents, env.device
         G = int(config.get("graphs_per_update", 32))

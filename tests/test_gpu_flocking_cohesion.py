@@ -9,6 +9,7 @@ row with SIMD partial sums whose width depends on the host CPU (8 or 16 lanes), 
 reference's own last bit is machine dependent; the kernel adds in partner order, which is what torch does below the SIMD
 width.  Results must agree to 2e-5 absolute + 1e-5 relative everywhere, and up to 5 agents at least 90 % of the
 collective rewards must be bit-identical."""
+import numpy as np
 import pytest
 import torch
 
@@ -253,3 +254,49 @@ def test_reference_training_loop_runs_on_flocking():
         trainer.train_model_batched({"epsilon": 0.5, "episodes": 1})
     with pytest.raises(NotImplementedError):
         trainer.train_model_device({"epsilon": 0.5, "episodes": 1})
+
+
+@pytest.mark.parametrize("which", ["flocking", "obstacle_avoidance"])
+def test_stepwise_batched_training_any_scenario(which):
+    """DQNTrainer.train_model_stepwise: B envs per tick through env.step and the scenario's own reward().  The ring
+    receives B transitions per tick carrying that reward, updates start once G transitions exist, weights move, the
+    target network is synchronised on schedule, and a second run with the same seeds is bit-identical."""
+    sb = _swarm()
+    B, n, T, G = 48, 5, 12, 32
+
+    def run():
+        sb.set_seed(2)
+        scenario = sb.FlockingScenario() if which == "flocking" else sb.ObstacleAvoidanceScenario()
+        env = sb.make_env(scenario=scenario, num_envs=B, device=_dev(), continuous_actions=False, wrapper=None,
+                          max_steps=T, dict_spaces=True, n_agents=n, seed=2, per_env_centers=True)
+        trainer = sb.DQNTrainer(env, 2, "/tmp/swarm_models", "/tmp/swarm_stats", which, replay_capacity=B * T * 2 + 7)
+        last = {}
+        step = env.step
+
+        def recording_step(actions):
+            out = step(actions)
+            last["rewards"] = torch.stack([out[1][f"agent{i}"] for i in range(n)], dim=1).clone()
+            last["actions"] = actions.clone()
+            return out
+
+        env.step = recording_step
+        w0 = trainer.w.clone()
+        stats = trainer.train_model_stepwise({"epsilon": 0.5, "epsilon_decay": 0.01, "min_epsilon": 0.05, "episodes": 2,
+                                              "graphs_per_update": G, "update_target_every": 10})
+        return trainer, stats, w0, last
+
+    trainer, stats, w0, last = run()
+    ring = trainer.replay_buffer.ring
+    assert len(ring) == 2 * T * B and ring.position == 2 * T * B
+    assert stats["ticks"] == 2 * T and stats["opt_steps"] == 2 * T          # B >= G: an update on every tick
+    assert np.isfinite(stats["loss"]) and stats["loss"] > 0 and not torch.equal(trainer.w, w0)
+    tail = torch.arange(2 * T * B - B, 2 * T * B, device=_dev(), dtype=torch.int64)
+    got = sb.ops.replay_gather(ring, tail)
+    assert torch.equal(got["rewards"], last["rewards"]) and torch.equal(got["actions"], last["actions"].to(torch.int32))
+    assert torch.equal(got["next_state"], trainer.env.world.state)
+    if which == "flocking":
+        assert torch.equal(got["rewards"][:, 0], got["rewards"][:, n - 1])     # one collective reward per env
+    # tick 20 was the last target sync (every 10 ticks); four more updates moved the online weights since
+    assert not torch.equal(trainer.w, trainer.w_target)
+    again, stats2, _, _ = run()
+    assert torch.equal(again.w, trainer.w) and stats2["loss"] == stats["loss"]
