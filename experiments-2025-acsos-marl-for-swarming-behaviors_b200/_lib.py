@@ -55,7 +55,7 @@ class SwarmReplay(C.Structure):
 class SwarmRolloutOptions(C.Structure):
     _fields_ = [("forced_actions", C.c_void_p), ("epsilon", C.c_float), ("rng_seed", C.c_uint64),
                 ("rng_tick0", C.c_int64), ("replay", C.POINTER(SwarmReplay)), ("replay_cursor", C.c_int64),
-                ("env_offset", C.c_int64)]
+                ("env_offset", C.c_int64), ("flocking", C.c_void_p), ("flocking_shaping", C.c_void_p)]
 
 
 class SwarmTrainCtl(C.Structure):
@@ -68,7 +68,7 @@ class SwarmTrainHyper(C.Structure):
     _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
                 ("max_norm", C.c_double), ("rng_seed", C.c_uint64), ("sample_seed", C.c_uint64),
                 ("env_offset", C.c_int64), ("graphs_per_update", C.c_int32), ("update_target_every", C.c_int32),
-                ("gamma", C.c_float), ("loss_scale", C.c_float)]
+                ("gamma", C.c_float), ("loss_scale", C.c_float), ("flocking", C.c_void_p), ("flocking_shaping", C.c_void_p)]
 
 
 class SwarmResetSpec(C.Structure):

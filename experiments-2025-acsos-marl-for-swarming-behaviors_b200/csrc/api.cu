@@ -399,6 +399,20 @@ int swarm_csr_from_edges(int32_t n_nodes, int64_t n_edges, const int64_t* edge_s
                     "swarm_csr_from_edges");
 }
 
+// SwarmRolloutOptions / SwarmTrainHyper: the optional Flocking reward of the fused tick
+static int attach_flocking(TileParams& p, const SwarmConfig* cfg, const SwarmRewardSpec* fs, float* shaping) {
+  if (!fs) return SWARM_OK;
+  if (fs->kind != SWARM_REWARD_FLOCKING) return fail(SWARM_ERR_INVALID_ARG, "`flocking` must be a Flocking reward spec");
+  if (cfg->scenario != SWARM_SCENARIO_GOTO)
+    return fail(SWARM_ERR_INVALID_ARG, "the Flocking reward runs on the GoTo world (cfg->scenario = SWARM_SCENARIO_GOTO)");
+  if (cfg->n_agents < 2) return fail(SWARM_ERR_INVALID_ARG, "the scenario rewards need at least two agents");
+  if (!shaping) return fail(SWARM_ERR_INVALID_ARG, "Flocking needs the shaping buffer");
+  p.flock = *fs;
+  p.shaping = reinterpret_cast<float2*>(shaping);
+  p.use_flock = 1;
+  return SWARM_OK;
+}
+
 int swarm_rollout(const SwarmConfig* cfg, const float* weights, float* state, int32_t ticks,
                   const SwarmRolloutOptions* opts, float* returns, int32_t* hits, const SwarmTrace* trace, void* stream) {
   if (int rc = validate(cfg, true)) return rc;
@@ -433,6 +447,7 @@ int swarm_rollout(const SwarmConfig* cfg, const float* weights, float* state, in
       p.replay = r;
       p.replay_cursor = opts->replay_cursor % r.capacity;
     }
+    if (int rc = attach_flocking(p, cfg, opts->flocking, opts->flocking_shaping)) return rc;
   }
   if (trace) p.trace = *trace;
   return check_cuda(launch_tile(MODE_ROLLOUT, p, (cudaStream_t)stream), "swarm_rollout");
@@ -540,6 +555,7 @@ int swarm_train_tick_grad(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, 
   p.env_offset = hyper->env_offset;
   p.replay = *ring;
   p.ctl = ctl;
+  if (int rc = attach_flocking(p, cfg, hyper->flocking, hyper->flocking_shaping)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = check_cuda(launch_tile(MODE_ROLLOUT, p, st), "swarm_train_tick_grad(rollout)")) return rc;
   return check_cuda(launch_dqn_grad(*cfg, weights, target_weights, *ring, nullptr, hyper->graphs_per_update, hyper->gamma,

@@ -39,7 +39,11 @@ __device__ __forceinline__ void tile_world_step(const TileParams& p, const TileT
 // DENSE: register budget for four resident CTAs per SM (127 registers) instead of three (156).  The tensor-core modes
 // are built both ways: with more CTAs than 3 x 148 the fourth CTA per SM pays (+13 % at 65 536 envs), below that the
 // roomier allocation is the faster one (C2: 410 CTAs).
-template <int MODE, bool TC, bool DENSE>
+// FLOCK (MODE_ROLLOUT only): the world is GoTo's, the reward is FlockingScenario's collective reward, evaluated with the
+// op sequence of reward_kernels.cu on the post-step positions; the two shaping terms of the agent live in registers
+// across the ticks like its state.  A separate template value so that the GoTo / ObstacleAvoidance instantiations keep
+// their code byte for byte.
+template <int MODE, bool TC, bool DENSE, bool FLOCK = false>
 __global__ void __launch_bounds__(kTileThreads, (MODE == MODE_GRAPH || MODE == MODE_STEP) ? 8 : ((TC && !DENSE) ? 3 : 4))
 tile_kernel(const __grid_constant__ TileParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -97,6 +101,8 @@ tile_kernel(const __grid_constant__ TileParams p) {
     s = reinterpret_cast<const float4*>(p.state_in)[t.gidx];
     if (MODE == MODE_ROLLOUT && p.returns) ret0 = p.returns[t.gidx];
   }
+  float2 shp = make_float2(0.0f, 0.0f);      // FLOCK: (previous_distance_to_goal, previous_distance_to_agents)
+  if (FLOCK && t.active) shp = p.shaping[t.gidx];
 
   int deg = 0;
   if (kQ && !knn && !radius && t.active) deg = tile_in_edges_complete(g, t, N);
@@ -211,7 +217,7 @@ tile_kernel(const __grid_constant__ TileParams p) {
           dobs = obstacle_distance(s.x, s.y, c);
           reward = oa_reward(dgoal, dobs, c, flags);
           myhits += (flags & SWARM_FLAG_HIT) ? 1 : 0;
-        } else {
+        } else if (!FLOCK) {
           sred[tid] = dgoal;     // GoTo's collective reward needs every agent's distance: finished below
         }
         if (MODE == MODE_STEP) {
@@ -240,7 +246,47 @@ tile_kernel(const __grid_constant__ TileParams p) {
           }
         }
       }
-      if (c.scenario == SWARM_SCENARIO_GOTO) {
+      if (FLOCK) {
+        // Flocking (flocking:124-171): every agent's term from the POST-step positions of its env, then the collective
+        // sum in agent order.  The post-step states go into the state buffer the next tick will fill anyway.
+        const SwarmRewardSpec& fs = p.flock;
+        float4* post = sst + ((tick + 1) & 1) * T;
+        post[tid] = s;
+        __syncthreads();
+        float term = 0.0f;
+        if (t.active) {
+          const float d_goal = norm2(__fsub_rn(s.x, fs.goal_x), __fsub_rn(s.y, fs.goal_y));
+          const float shaped_goal = __fmul_rn(d_goal, fs.pos_shaping);
+          const float4* others = post + t.envbase;
+          float sum = 0.0f;
+          int close = 0;
+#pragma unroll 2
+          for (int j = 0; j < N; ++j) {
+            const float4 q = others[j];
+            const float dx = __fsub_rn(s.x, q.x), dy = __fsub_rn(s.y, q.y);
+            float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+            const bool self = j == t.i;
+            d2 = self ? 1.0f : d2;
+            const float d = __fsqrt_rn(d2);
+            const float e = __fsub_rn(d, fs.desired_distance);
+            sum = __fadd_rn(sum, self ? 0.0f : __fmul_rn(e, e));
+            const float gap = __fsub_rn(__fsub_rn(d, fs.agent_radius), fs.agent_radius);
+            close += (!self && gap <= fs.min_collision_distance) ? 1 : 0;
+          }
+          const float spacing = __fmul_rn(__fdiv_rn(sum, (float)(N - 1)), fs.dist_shaping);
+          const float pos_rew = __fsub_rn(shp.x, shaped_goal);
+          float r = pos_rew;
+          if (d_goal < fs.goal_radius) r = __fadd_rn(r, fs.on_goal_bonus);
+          const float avoid = close ? __fmul_rn((float)close, fs.collision_reward) : 0.0f;
+          const float dist_rew = __fsub_rn(shp.y, spacing);
+          shp = make_float2(shaped_goal, spacing);
+          term = __fadd_rn(__fadd_rn(r, avoid), dist_rew);
+        }
+        sred[tid] = term;
+        __syncthreads();
+        if (t.active)
+          for (int a = 0; a < N; ++a) reward = __fadd_rn(reward, sred[t.envbase + a]);
+      } else if (c.scenario == SWARM_SCENARIO_GOTO) {
         // collective reward (go_to:108-115): 0 + (-d_0) + (-d_1) + ... in agent order, same for all agents
         __syncthreads();
         if (t.active)
@@ -265,6 +311,7 @@ tile_kernel(const __grid_constant__ TileParams p) {
     if (t.active) {
       reinterpret_cast<float4*>(p.state_out)[t.gidx] = s;
       if (p.returns) p.returns[t.gidx] = __fadd_rn(ret0, ret);
+      if (FLOCK) p.shaping[t.gidx] = shp;
     }
     if (p.hits) {
       __syncthreads();
@@ -340,16 +387,17 @@ cudaError_t launch_replay_gather(const SwarmReplay& r, const int64_t* indices, i
 }
 
 // explicit instantiations + launcher
-template <int MODE, bool TC, bool DENSE>
+template <int MODE, bool TC, bool DENSE, bool FLOCK = false>
 static cudaError_t launch_tile_impl(const TileParams& p, cudaStream_t stream) {
   const SwarmConfig& c = p.cfg;
   const TileLayout L = tile_layout(MODE, kTileThreads, c.n_agents, c.knn_k, p.maxdeg, c.graph_mode, TC);
   const int grid = (c.num_envs + p.epb - 1) / p.epb;
   if (L.total > 48 * 1024) {
-    cudaError_t err = cudaFuncSetAttribute(tile_kernel<MODE, TC, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+    cudaError_t err =
+        cudaFuncSetAttribute(tile_kernel<MODE, TC, DENSE, FLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
     if (err != cudaSuccess) return err;
   }
-  tile_kernel<MODE, TC, DENSE><<<grid, kTileThreads, L.total, stream>>>(p);
+  tile_kernel<MODE, TC, DENSE, FLOCK><<<grid, kTileThreads, L.total, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -360,9 +408,17 @@ static cudaError_t launch_tile_q(const TileParams& p, cudaStream_t stream) {
   return grid > 3 * 148 ? launch_tile_impl<MODE, true, true>(p, stream) : launch_tile_impl<MODE, true, false>(p, stream);
 }
 
+// the Flocking-reward rollout: same selection of the tensor-core / register-budget variants
+static cudaError_t launch_tile_flock(const TileParams& p, cudaStream_t stream) {
+  if (!p.use_tc) return launch_tile_impl<MODE_ROLLOUT, false, true, true>(p, stream);
+  const int grid = (p.cfg.num_envs + p.epb - 1) / p.epb;
+  return grid > 3 * 148 ? launch_tile_impl<MODE_ROLLOUT, true, true, true>(p, stream)
+                        : launch_tile_impl<MODE_ROLLOUT, true, false, true>(p, stream);
+}
+
 cudaError_t launch_tile(int mode, const TileParams& p, cudaStream_t stream) {
   switch (mode) {
-    case MODE_ROLLOUT: return launch_tile_q<MODE_ROLLOUT>(p, stream);
+    case MODE_ROLLOUT: return p.use_flock ? launch_tile_flock(p, stream) : launch_tile_q<MODE_ROLLOUT>(p, stream);
     case MODE_FORWARD: return launch_tile_q<MODE_FORWARD>(p, stream);
     case MODE_STEP: return launch_tile_impl<MODE_STEP, false, true>(p, stream);
     case MODE_GRAPH: return launch_tile_impl<MODE_GRAPH, false, true>(p, stream);

@@ -118,6 +118,10 @@ struct TileParams {
   float qmax_aa, qmax_ao;        // largest squared distance whose rounded sqrt is <= dmin (exact pre-filter)
   float qmax_r;                  // same for the radius graph: sqrt(q) <= graph_radius  <=>  q <= qmax_r
   int32_t* counts_out;           // MODE_GRAPH, radius graph: edges per env
+  // MODE_ROLLOUT, FLOCK variant: the Flocking reward (flocking_scenario.py:124-171) instead of GoTo's on the GoTo world
+  SwarmRewardSpec flock;         // its constants
+  float2* shaping;               // [B*N] (previous_distance_to_goal, previous_distance_to_agents), read at launch, written back
+  int32_t use_flock;
 };
 
 // largest float q with sqrtf(q) <= dmin: makes a squared-distance test exactly equivalent to the reference's

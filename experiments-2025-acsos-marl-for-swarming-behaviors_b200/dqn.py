@@ -25,7 +25,7 @@ import torch
 from . import _lib, ops, parallel
 from .gcn import GCN
 from .graph import Batch, Data, node_features, stack_observations
-from .scenarios import _KernelScenario
+from .scenarios import FlockingScenario, _KernelScenario
 
 
 class GraphReplayBuffer:
@@ -229,10 +229,12 @@ class DQNTrainer:
         TD target / loss / backward) + ``swarm_train_tick_apply`` (clip + Adam + target sync), with one gradient
         all-reduce in between when data-parallel.  The tick counters live on the device, so with
         ``config["cuda_graph"]`` (default on) the ticks of one episode are captured once in a CUDA graph and each
-        episode is a single graph launch."""
-        if not isinstance(self.env.scenario, _KernelScenario):
-            raise NotImplementedError("the fused train tick computes the GoTo / ObstacleAvoidance rewards in the kernel; "
-                                      "train other scenarios (Flocking, user-written) with train_model / train_model_stepwise")
+        episode is a single graph launch.  A ``FlockingScenario`` env trains on its collective reward: the tick kernel
+        then evaluates the Flocking reward on the GoTo world and keeps the scenario's shaping memory up to date."""
+        flock = isinstance(self.env.scenario, FlockingScenario)
+        if not flock and not isinstance(self.env.scenario, _KernelScenario):
+            raise NotImplementedError("the fused train tick computes the GoTo / ObstacleAvoidance / Flocking rewards in the "
+                                      "kernel; train other scenarios with train_model / train_model_stepwise")
         env, world = self.env, self.env.world
         B, n, dev = env.num_envs, env.n_agents, env.device
         G = int(config.get("graphs_per_update", 32))
@@ -248,7 +250,9 @@ class DQNTrainer:
                            gamma=float(config.get("gamma", 0.99)), loss_scale=parallel.global_loss_scale(G, n),
                            lr=self.lr, betas=self.betas, eps=self.eps, max_norm=self.max_norm, rng_seed=self.seed,
                            sample_seed=int(config.get("sample_seed", self.seed)) + 7919 * rank,
-                           env_offset=int(config.get("env_offset", rank * B)))
+                           env_offset=int(config.get("env_offset", rank * B)),
+                           flocking=env.scenario._spec() if flock else None,
+                           shaping=env.scenario.shaping if flock else None)
         parallel.broadcast_weights(self.w)
         self.w_target.copy_(self.w)
         tt.load_cursor(int(config.get("start_tick", 0)), self.opt_step, epsilon)
@@ -374,8 +378,8 @@ class DQNTrainer:
         Per-env start centres come from the counter RNG (``shared_center`` reproduces the reference's one draw per
         reset).  Returns stats f32[episodes, 4] = (mean agent-0 return / N, hits per env, last loss, epsilon)."""
         if not isinstance(self.env.scenario, _KernelScenario):
-            raise NotImplementedError("the fused train tick computes the GoTo / ObstacleAvoidance rewards in the kernel; "
-                                      "train other scenarios (Flocking, user-written) with train_model / train_model_stepwise")
+            raise NotImplementedError("the whole-run device loop resets GoTo / ObstacleAvoidance worlds on the device; train "
+                                      "Flocking with train_model_batched, other scenarios with train_model_stepwise")
         env, world = self.env, self.env.world
         B, n, dev = env.num_envs, env.n_agents, env.device
         G = int(config.get("graphs_per_update", 32))

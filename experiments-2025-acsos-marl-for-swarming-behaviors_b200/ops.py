@@ -135,10 +135,13 @@ def rollout(cfg: SwarmConfig, weights: torch.Tensor, state: torch.Tensor, ticks:
             forced_actions: Optional[torch.Tensor] = None, returns: Optional[torch.Tensor] = None,
             hits: Optional[torch.Tensor] = None, trace: Optional[Dict[str, bool]] = None,
             epsilon: float = 0.0, rng_seed: int = 0, rng_tick0: int = 0, env_offset: int = 0,
-            replay: Optional[ReplayRing] = None) -> Dict[str, torch.Tensor]:
+            replay: Optional[ReplayRing] = None, flocking: Optional["_lib.SwarmRewardSpec"] = None,
+            shaping: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """Fused (epsilon-)greedy rollout, in place on ``state``.  ``trace`` names the per-tick records to keep
     (any of state, actions, q, rewards, flags, contact, edges, dist).  With ``replay`` every tick's B
-    transitions are pushed into the ring (and its cursor advanced)."""
+    transitions are pushed into the ring (and its cursor advanced).  With ``flocking`` (a Flocking reward spec, cfg =
+    the GoTo world) the reward of every tick is the Flocking collective reward and ``shaping`` f32[B,N,2] carries the
+    ``previous_*`` memory in and out."""
     B, N = cfg.num_envs, cfg.n_agents
     _expect(state, torch.float32, B * N * 4, "state")
     _expect(weights, torch.float32, _lib.W_COUNT, "weights")
@@ -173,6 +176,13 @@ def rollout(cfg: SwarmConfig, weights: torch.Tensor, state: torch.Tensor, ticks:
     opts.rng_seed = int(rng_seed) & 0xFFFFFFFFFFFFFFFF
     opts.rng_tick0 = int(rng_tick0)
     opts.env_offset = int(env_offset)
+    if flocking is not None:
+        if shaping is None:
+            raise ValueError("Flocking needs the shaping buffer f32[B,N,2]")
+        _expect(shaping, torch.float32, B * N * 2, "shaping")
+        opts.flocking = C.addressof(flocking)
+        opts.flocking_shaping = ptr(shaping)
+        out["shaping"] = shaping
     rstruct = None
     if replay is not None:
         if replay.n_agents != N:
@@ -329,7 +339,8 @@ class TrainTick:
 
     def __init__(self, cfg: SwarmConfig, ring: ReplayRing, *, graphs_per_update: int = 32, update_target_every: int = 200,
                  gamma: float = 0.99, loss_scale: Optional[float] = None, lr: float = 1e-3, betas=(0.9, 0.999),
-                 eps: float = 1e-8, max_norm: float = 1.0, rng_seed: int = 0, sample_seed: int = 0, env_offset: int = 0):
+                 eps: float = 1e-8, max_norm: float = 1.0, rng_seed: int = 0, sample_seed: int = 0, env_offset: int = 0,
+                 flocking: Optional["_lib.SwarmRewardSpec"] = None, shaping: Optional[torch.Tensor] = None):
         dev = ring.state.device
         self.cfg, self.ring = cfg, ring
         G = int(graphs_per_update)
@@ -341,6 +352,14 @@ class TrainTick:
         h.graphs_per_update, h.update_target_every = G, int(update_target_every)
         h.gamma = float(gamma)
         h.loss_scale = float(loss_scale) if loss_scale is not None else 1.0 / (G * cfg.n_agents)
+        if flocking is not None:
+            # the tick's reward is the Flocking collective reward; `shaping` f32[B,N,2] is its memory (in / out)
+            if shaping is None:
+                raise ValueError("Flocking needs the shaping buffer f32[B,N,2]")
+            _expect(shaping, torch.float32, cfg.num_envs * cfg.n_agents * 2, "shaping")
+            self._flocking, self._shaping = _lib.SwarmRewardSpec.from_buffer_copy(flocking), shaping   # kept alive
+            h.flocking = C.addressof(self._flocking)
+            h.flocking_shaping = ptr(shaping)
         self.hyper = h
         assert C.sizeof(_lib.SwarmTrainCtl) == 8 * self.CTL_WORDS
         self.ctl = torch.zeros(self.CTL_WORDS, dtype=torch.int64, device=dev)

@@ -223,6 +223,8 @@ typedef struct SwarmReplay {
   int64_t capacity;      /* slots (one slot = one env transition)   */
 } SwarmReplay;
 
+struct SwarmRewardSpec;          /* defined with swarm_scenario_reward below */
+
 typedef struct SwarmRolloutOptions {
   const int32_t* forced_actions; /* optional [ticks][B*N]; entries >= 0 override the policy's action        */
   float epsilon;                 /* epsilon-greedy (train:164-167): one coin per env and tick; 0 = greedy   */
@@ -231,6 +233,13 @@ typedef struct SwarmRolloutOptions {
   const SwarmReplay* replay;     /* optional: push (s, a, r, s') of every env and tick (train:171-172) ...  */
   int64_t replay_cursor;         /* ... at slot (cursor + tick*B + env) mod capacity                        */
   int64_t env_offset;            /* global index of env 0 (RNG streams of an env shard)                     */
+  /* Flocking (flocking_scenario.py:124-171) on the fused path: with `flocking` set (kind SWARM_REWARD_FLOCKING,
+   * cfg->scenario SWARM_SCENARIO_GOTO, whose world Flocking shares) every tick's reward -- returns, reward trace,
+   * replay push -- is the Flocking collective reward, evaluated exactly like swarm_scenario_reward after each world
+   * step; flocking_shaping float[B*N][2] is read at the start and written back at the end (initialise it with a
+   * swarm_scenario_reward reset call after placing the agents). */
+  const struct SwarmRewardSpec* flocking;
+  float* flocking_shaping;
 } SwarmRolloutOptions;
 
 /* Fused rollout: `ticks` iterations of [graph build -> GCN forward -> (epsilon-)greedy argmax -> env step]
@@ -303,6 +312,9 @@ typedef struct SwarmTrainHyper {
   int32_t update_target_every;  /* hard target sync period in ticks (reference: 200, train:175)                     */
   float gamma;                  /* 0.99                                                                             */
   float loss_scale;             /* 1 / (global number of nodes in the update batch)                                 */
+  /* optional, as in SwarmRolloutOptions: the tick's reward is the Flocking collective reward (cfg = the GoTo world) */
+  const struct SwarmRewardSpec* flocking;
+  float* flocking_shaping;
 } SwarmTrainHyper;
 
 /* Phase 1: rollout tick of all cfg->num_envs envs with the online weights (pushes B transitions at ctl->ring_cursor),

@@ -222,7 +222,7 @@ def test_scenario_reward_full_size_properties():
 def test_reference_training_loop_runs_on_flocking():
     """DQNTrainer.train_model (the reference's num_envs = 1 loop, train:139-204) on a Flocking env: the transitions it
     stores carry the Flocking collective reward (not the world-step kernel's GoTo reward), the update changes the
-    weights, losses are finite; the fused trainers refuse scenarios whose reward the tick kernel does not compute."""
+    weights, losses are finite; the whole-run device loop refuses scenarios it cannot reset on the device."""
     sb = _swarm()
     sb.set_seed(1)
     n, T = 5, 40
@@ -250,8 +250,6 @@ def test_reference_training_loop_runs_on_flocking():
     assert torch.equal(stored.reshape(2 * T, n), want), "the replay ring holds the Flocking collective reward"
     goto_like = -torch.linalg.vector_norm(env.world.state[0, :, 0:2] - torch.tensor([-0.8, 0.8], device=_dev()), dim=-1).sum()
     assert abs(float(seen[-1]) - float(goto_like)) > 1e-3, "and it is not the GoTo reward of the world-step kernel"
-    with pytest.raises(NotImplementedError):
-        trainer.train_model_batched({"epsilon": 0.5, "episodes": 1})
     with pytest.raises(NotImplementedError):
         trainer.train_model_device({"epsilon": 0.5, "episodes": 1})
 
@@ -300,3 +298,84 @@ def test_stepwise_batched_training_any_scenario(which):
     assert not torch.equal(trainer.w, trainer.w_target)
     again, stats2, _, _ = run()
     assert torch.equal(again.w, trainer.w) and stats2["loss"] == stats["loss"]
+
+
+def _flocking_pair(B, n, T, seed):
+    """Two identical Flocking envs (explicit per-env start centres) + GoTo weights."""
+    from helpers import load_params
+    sb = _swarm()
+    g = torch.Generator().manual_seed(seed)
+    centers = torch.tensor([-1.0, 1.0]) + torch.tensor([-0.6, 0.6]) + 0.4 * torch.randn(B, 2, generator=g)
+    envs = []
+    for _ in range(2):
+        sc = sb.FlockingScenario()
+        env = sb.Environment(sc, num_envs=B, device=_dev(), max_steps=T, continuous_actions=False, seed=0, dict_spaces=True,
+                             n_agents=n)
+        sc.set_start_centers(centers)
+        env.reset()
+        envs.append(env)
+    w = sb.pack_weights(load_params("GoTo", 0), _dev())
+    return sb, envs[0], envs[1], w
+
+
+@pytest.mark.parametrize("graph,n", [("complete", 7), ("knn", 12), ("complete", 2)])
+def test_fused_flocking_rollout_matches_env_stepping(graph, n):
+    """swarm_rollout with the Flocking option (graph -> GAT-Q -> epsilon-greedy -> world step -> Flocking reward, T ticks in
+    one launch) against Environment.step on a second FlockingScenario env driven with the traced actions: states, rewards,
+    returns, replay pushes and the shaping memory agree bit for bit."""
+    B, T = 37, 20
+    sb, env_a, env_b, w = _flocking_pair(B, n, T, seed=n)
+    ops, L = sb.ops, sb._lib
+    sc_a, sc_b = env_a.scenario, env_b.scenario
+    cfg = ops.clone_config(env_a.world.cfg, graph_mode=L.GRAPH_KNN if graph == "knn" else L.GRAPH_COMPLETE, knn_k=min(5, n))
+    ring = ops.ReplayRing(B * T, n, _dev())
+    out = ops.rollout(cfg, w, env_a.world.state, T, trace=dict(actions=True, rewards=True, state=True), epsilon=0.3,
+                      rng_seed=11, replay=ring, flocking=sc_a._spec(), shaping=sc_a.shaping)
+    ret = torch.zeros(B, device=_dev())
+    for t in range(T):
+        _, rews, _, _ = env_b.step(out["trace_actions"][t])
+        assert torch.equal(env_b.world.state, out["trace_state"][t]), f"state after tick {t}"
+        r = rews["agent0"]
+        assert torch.equal(out["trace_rewards"][t], r[:, None].expand(B, n)), f"reward of tick {t}"
+        ret = ret + r
+    assert torch.equal(sc_b.shaping, sc_a.shaping)
+    assert torch.equal(out["returns"], ret[:, None].expand(B, n))
+    got = ops.replay_gather(ring, torch.arange(B * T, device=_dev(), dtype=torch.int64))
+    assert torch.equal(got["rewards"].view(T, B, n), out["trace_rewards"])
+    assert torch.equal(got["next_state"].view(T, B, n, 4), out["trace_state"])
+    # the option is validated: wrong scenario / missing shaping
+    with pytest.raises(ValueError):
+        ops.rollout(cfg, w, env_a.world.state, 1, flocking=sc_a._spec())
+    oa = ops.clone_config(cfg, scenario=L.SCENARIO_OBSTACLE_AVOIDANCE)
+    with pytest.raises(ValueError):
+        ops.rollout(oa, w, env_a.world.state, 1, flocking=sc_a._spec(), shaping=sc_a.shaping)
+
+
+def test_fused_batched_training_on_flocking():
+    """DQNTrainer.train_model_batched on a Flocking env: the fused train tick pushes the Flocking reward (re-derived
+    here by stepping a second env with the stored actions), and the CUDA-graph run equals the eager run bit for bit."""
+    B, n, T, G = 64, 5, 15, 32
+
+    def run(use_graph, episodes):
+        sb, env, env_ref, _ = _flocking_pair(B, n, T, seed=9)
+        sb.set_seed(3)
+        trainer = sb.DQNTrainer(env, 3, "/tmp/swarm_models", "/tmp/swarm_stats", "Flocking", replay_capacity=B * T * 4)
+        stats = trainer.train_model_batched({"epsilon": 0.4, "epsilon_decay": 0.01, "min_epsilon": 0.05, "episodes": episodes,
+                                             "graphs_per_update": G, "update_target_every": 7, "cuda_graph": use_graph})
+        return sb, trainer, env_ref, stats
+
+    sb, trainer, env_ref, stats = run(False, 3)
+    ring = trainer.replay_buffer.ring
+    assert len(ring) == 3 * T * B and stats["opt_steps"] == 3 * T and np.isfinite(stats["loss"])
+    first = sb.ops.replay_gather(ring, torch.arange(T * B, device=_dev(), dtype=torch.int64))     # episode 0
+    for t in range(T):
+        sl = slice(t * B, (t + 1) * B)
+        assert torch.equal(first["state"][sl], env_ref.world.state), f"pre-step state of tick {t}"
+        _, rews, _, _ = env_ref.step(first["actions"][sl])
+        assert torch.equal(first["next_state"][sl], env_ref.world.state)
+        assert torch.equal(first["rewards"][sl], rews["agent0"][:, None].expand(B, n)), f"reward of tick {t}"
+    _, graphed, _, stats_g = run(True, 3)
+    assert torch.equal(graphed.w, trainer.w) and torch.equal(graphed.w_target, trainer.w_target)
+    assert stats_g["loss"] == stats["loss"]
+    with pytest.raises(NotImplementedError):
+        trainer.train_model_device({"epsilon": 0.5, "episodes": 1})
