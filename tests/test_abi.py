@@ -240,3 +240,23 @@ def test_gat_layer_argument_validation_without_device(sb):
     assert bwd(10, 5, src=None) == -1 and b"edge" in lib.swarm_last_error()
     assert bwd(10, 5, wb=64) == -1 and b"workspace" in lib.swarm_last_error()
     assert bwd(10, 1 << 31) == -2
+
+
+def test_flocking_option_of_the_fused_tick_is_validated(sb):
+    """SwarmRolloutOptions.flocking / SwarmTrainHyper.flocking: argument errors are reported before any launch."""
+    lib, L = sb._lib.lib(), sb._lib
+    cfg = sb.ops.make_config(L.SCENARIO_GOTO, 16, 5)
+    spec = sb.ops.reward_spec(L.REWARD_FLOCKING, 16, 5)
+    opts = L.SwarmRolloutOptions()
+    opts.flocking = C.addressof(spec)
+    roll = lambda c: lib.swarm_rollout(C.byref(c), 8, 8, 1, C.byref(opts), None, None, None, None)
+    assert roll(cfg) == -1 and b"shaping" in lib.swarm_last_error()
+    opts.flocking_shaping = 8
+    oa = sb.ops.clone_config(cfg, scenario=L.SCENARIO_OBSTACLE_AVOIDANCE)
+    assert roll(oa) == -1 and b"GoTo world" in lib.swarm_last_error()
+    one = sb.ops.clone_config(cfg, n_agents=1)
+    assert roll(one) == -1 and b"two agents" in lib.swarm_last_error()
+    spec.kind = L.REWARD_COHESION
+    assert roll(cfg) == -1 and b"Flocking reward spec" in lib.swarm_last_error()
+    assert L.SwarmRolloutOptions.flocking.offset + 16 == C.sizeof(L.SwarmRolloutOptions)
+    assert L.SwarmTrainHyper.flocking.offset + 16 == C.sizeof(L.SwarmTrainHyper)
