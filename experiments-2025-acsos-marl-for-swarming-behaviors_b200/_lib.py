@@ -22,6 +22,8 @@ FLAG_OBSTACLE_CONTACT = 1
 FLAG_HIT = 2
 FLAG_PENALTY = 4
 W_COUNT = 1673
+ABI_VERSION = 2
+XCHG_STRIDE = 1680
 
 # state-dict tensors in packed order (include/swarm_b200.h SWARM_W_*)
 WEIGHT_KEYS = ("conv1.lin.weight", "conv1.att_src", "conv1.att_dst", "conv1.bias",
@@ -89,7 +91,7 @@ REWARD_FLOCKING, REWARD_COHESION = 0, 1
 
 
 class SwarmPeerExchange(C.Structure):
-    _fields_ = [("data", C.c_void_p * 16), ("flags", C.c_void_p * 16), ("world_size", C.c_int32), ("rank", C.c_int32)]
+    _fields_ = [("data", C.c_void_p * 16), ("world_size", C.c_int32), ("rank", C.c_int32)]
 
 
 class SwarmError(RuntimeError):
@@ -161,7 +163,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)      # AttributeError if the ABI is incomplete
             fn.restype = res
             fn.argtypes = args
-        if handle.swarm_abi_version() != 1:
+        if handle.swarm_abi_version() != ABI_VERSION:
             raise SwarmError("libswarm_b200.so ABI version mismatch; rebuild")
         _LIB = handle
     return _LIB

@@ -575,7 +575,7 @@ int swarm_train_tick_apply(const SwarmConfig* cfg, const SwarmTrainHyper* hyper,
     if (peers->world_size < 1 || peers->world_size > SWARM_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world_size)
       return fail(SWARM_ERR_INVALID_ARG, "peer exchange: bad world_size / rank");
     for (int r = 0; r < peers->world_size; ++r)
-      if (!peers->data[r] || !peers->flags[r]) return fail(SWARM_ERR_INVALID_ARG, "peer exchange: NULL peer buffer");
+      if (!peers->data[r]) return fail(SWARM_ERR_INVALID_ARG, "peer exchange: NULL peer buffer");
   }
   return check_cuda(launch_adam_clip(weights, grad, exp_avg, exp_avg_sq, 1, hyper->lr, hyper->beta1, hyper->beta2,
                                      hyper->eps, hyper->max_norm, target_weights, nullptr, (cudaStream_t)stream, ctl,

@@ -249,12 +249,13 @@ __global__ void __launch_bounds__(kTileThreads) dqn_grad_kernel(const __grid_con
       slot = (long long)__umul64hi(rnd, (uint64_t)ring_size);
       if (p.indices_out && t.i == 0 && !tgt_group) p.indices_out[t.env] = slot;
     } else if (p.indices) {
-      slot = p.indices[t.env];
+      slot = p.indices[t.env];                            // caller-supplied: clamped into the ring, never out of bounds
+      slot = slot < 0 ? 0 : (slot >= p.batch.capacity ? p.batch.capacity - 1 : slot);
     }
     const long long ri = slot * N + t.i;
     s = reinterpret_cast<const float4*>(p.batch.state)[ri];
     s2 = reinterpret_cast<const float4*>(p.batch.next_state)[ri];
-    act = p.batch.actions[ri];
+    act = sanitize_action(p.batch.actions[ri]);
     rew = p.batch.rewards[ri];
   } else if (tid < rows) {
     // rows of idle threads inside the row range take part in the tile GEMMs below: exact zeros
@@ -539,12 +540,13 @@ struct AdamParams {
   float* grad_rw;          // same buffer as `grad` (gradient + loss), written back after the exchange
 };
 
-__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+// one naturally aligned 64-bit word = (epoch << 32 | float bits): single-copy atomic, so the word itself is the flag
+__device__ __forceinline__ void st_relaxed_sys_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+__device__ __forceinline__ uint64_t ld_relaxed_sys_u64(const uint64_t* p) {
   uint64_t v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 
@@ -582,53 +584,52 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
     w_[i] = in ? p.w[o] : 0.0f;
   }
   if (PEERS && p.ctl) {
-    // ---- one-shot all-reduce over NVLink peer memory ------------------------------------------------------
-    // Every rank agrees on `updating` (same ring fill), so either all ranks exchange this tick or none does.
-    const uint64_t epoch = (uint64_t)(p.ctl->tick + 1);
-    const int par = (int)(epoch & 1);
+    // ---- one-shot PUSH all-reduce over NVLink peer memory ("low-latency" protocol) ---------------------------
+    // Every rank agrees on `updating` (the trainer checks that all shards have the same env count and ring fill), so
+    // either all ranks exchange this tick or none does.  Each rank WRITES its partial gradient + loss into its own
+    // slot of every peer's receive buffer; each 8-byte word carries the value and the epoch (tick + 1), so a word is
+    // its own arrival flag: no fence, no separate flag, and the waits poll LOCAL memory.  The critical path is one
+    // one-way NVLink store latency (the pull version paid a remote flag poll plus two remote read round trips).
+    // Slots are double-buffered by epoch parity: a rank can only be one exchange ahead of a peer, because its next
+    // push needs the peer's words of the current one.
+    const uint32_t epoch = (uint32_t)(p.ctl->tick + 1);
+    const int par = (int)(epoch & 1u);
+    const int W = p.peers.world_size;
     const bool upd = p.ctl->updating != 0;
     if (upd) {
-      float* mine = p.peers.data[p.peers.rank] + par * SWARM_XCHG_STRIDE;
+      uint64_t word[kPer];
 #pragma unroll
-      for (int i = 0; i < kPer; ++i) {
-        const int o = tid + 256 * i;
-        if (o <= SWARM_W_COUNT) mine[o] = g_[i];
+      for (int i = 0; i < kPer; ++i) word[i] = ((uint64_t)epoch << 32) | (uint64_t)__float_as_uint(g_[i]);
+      const size_t my_slot = ((size_t)par * W + p.peers.rank) * SWARM_XCHG_STRIDE;
+      for (int q = 0; q < W; ++q) {
+        const int peer = (p.peers.rank + q) % W;            // own buffer first, then ring order: spreads the links
+        uint64_t* dst = p.peers.data[peer] + my_slot;
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+          const int o = tid + 256 * i;
+          if (o <= SWARM_W_COUNT) st_relaxed_sys_u64(dst + o, word[i]);
+        }
       }
-      __syncthreads();            // the release below is cumulative over the CTA barrier: all rows are published
-      if (tid == 0) {
-        __threadfence_system();
-        st_release_sys(p.peers.flags[p.peers.rank] + par, epoch);
-      }
-      if (tid < p.peers.world_size && tid != p.peers.rank) {
-        const uint64_t* f = p.peers.flags[tid] + par;
-        bool ok = false;
-        for (long long it = 0; it < (1ll << 25) && !ok; ++it) ok = ld_acquire_sys(f) >= epoch;   // ~1 min of polls
-        if (!ok) __trap();                    // a peer never arrived: fail loudly instead of hanging the GPU
-      }
-      __syncthreads();
+      // rank order on every rank: bit-identical sums
 #pragma unroll
       for (int i = 0; i < kPer; ++i) g_[i] = 0.0f;
-      // rank order on every rank: bit-identical sums.  Four peers' rows are fetched per round trip over NVLink (all
-      // 28 loads of a thread in flight) before they are added, so 8 ranks cost two P2P latencies instead of eight.
-      for (int r0 = 0; r0 < p.peers.world_size; r0 += 4) {
-        float tq[4][kPer];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const bool have = r0 + q < p.peers.world_size;
-          const float* src = p.peers.data[have ? r0 + q : p.peers.rank] + par * SWARM_XCHG_STRIDE;
+      const uint64_t* mine = p.peers.data[p.peers.rank] + (size_t)par * W * SWARM_XCHG_STRIDE;
+      for (int r = 0; r < W; ++r) {
+        const uint64_t* src = mine + (size_t)r * SWARM_XCHG_STRIDE;
+        uint64_t got[kPer];
+        bool ok = false;
+        for (long long it = 0; it < (1ll << 26) && !ok; ++it) {     // bounded: a lost peer traps instead of hanging
+          ok = true;
 #pragma unroll
           for (int i = 0; i < kPer; ++i) {
             const int o = tid + 256 * i;
-            tq[q][i] = (have && o <= SWARM_W_COUNT) ? __ldcv(src + o) : 0.0f;
+            got[i] = (o <= SWARM_W_COUNT) ? ld_relaxed_sys_u64(src + o) : ((uint64_t)epoch << 32);
+            ok = ok && ((uint32_t)(got[i] >> 32) == epoch);
           }
         }
+        if (!ok) __trap();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (r0 + q < p.peers.world_size) {
-#pragma unroll
-            for (int i = 0; i < kPer; ++i) g_[i] += tq[q][i];
-          }
-        }
+        for (int i = 0; i < kPer; ++i) g_[i] += __uint_as_float((uint32_t)got[i]);
       }
 #pragma unroll
       for (int i = 0; i < kPer; ++i) {

@@ -31,22 +31,23 @@ struct LargeStepParams {
   float one_minus_drag, dmin_aa, dmin_ao, qmax_aa, qmax_ao;
 };
 
-// grid = (chunks of 256 agents, envs)
+// grid = envs: ONE CTA owns a whole env.  It stages every pre-step position of the env in shared memory before any
+// thread writes a post-step state, so state_out may alias state_in (the in-place use of World.step / rollout_large);
+// a (chunk, env) grid would let a later-scheduled chunk read partner positions that an earlier chunk already stepped.
 __global__ void __launch_bounds__(kLargeThreads) sim_step_large_kernel(const __grid_constant__ LargeStepParams p) {
   extern __shared__ float2 spos[];
   const SwarmConfig& c = p.cfg;
   const int N = c.n_agents;
-  const long long env = blockIdx.y;
+  const long long env = blockIdx.x;
   const float4* env_state = p.state_in + env * N;
   for (int j = threadIdx.x; j < N; j += kLargeThreads) {
     const float4 s = env_state[j];
     spos[j] = make_float2(s.x, s.y);
   }
   __syncthreads();
-  const int i = blockIdx.x * kLargeThreads + threadIdx.x;
-  if (i >= N) return;
+  for (int i = threadIdx.x; i < N; i += kLargeThreads) {
   const long long gidx = env * N + i;
-  float4 s = env_state[i];
+  float4 s = env_state[i];               // only this thread ever writes index i: no hazard with the in-place store below
   float fx, fy, gx, gy;
   decode_action(p.actions[gidx], fx, fy);
   uint8_t flags = 0;
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(kLargeThreads) sim_step_large_kernel(const __g
     o[2] = make_float2(c.goal_x, c.goal_y);
   }
   if (p.dist) p.dist[gidx] = make_float2(dgoal, dobs);
+  }
 }
 
 // GoTo (go_to:108-115): reward = 0 + (-d_0) + (-d_1) + ... summed in agent order, the same value for every agent.
@@ -143,7 +145,7 @@ struct LargeKnnParams {
   int32_t edges_per_env;
 };
 
-// grid = (chunks of 256 agents, envs); dynamic smem: positions float2[N], heap values float[K][256], indices int[K][256]
+// grid = (envs, chunks of 256 agents); dynamic smem: positions float2[N], heap values float[K][256], indices int[K][256]
 __global__ void __launch_bounds__(kLargeThreads) knn_large_kernel(const __grid_constant__ LargeKnnParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SwarmConfig& c = p.cfg;
@@ -151,13 +153,13 @@ __global__ void __launch_bounds__(kLargeThreads) knn_large_kernel(const __grid_c
   float2* spos = reinterpret_cast<float2*>(smem_raw);
   float* hv = reinterpret_cast<float*>(spos + N);
   int* hi = reinterpret_cast<int*>(hv + K * kLargeThreads);
-  const long long env = blockIdx.y;
+  const long long env = blockIdx.x;          // envs on grid.x (no 65 535 cap), agent chunks on grid.y
   for (int j = threadIdx.x; j < N; j += kLargeThreads) {
     const float4 s = p.state[env * N + j];
     spos[j] = make_float2(s.x, s.y);
   }
   __syncthreads();
-  const int i = blockIdx.x * kLargeThreads + threadIdx.x;
+  const int i = blockIdx.y * kLargeThreads + threadIdx.x;
   if (i >= N) return;
   VirtualRow row{hv + threadIdx.x, hi + threadIdx.x, spos, spos[i].x, spos[i].y, K};
   for (int j = 0; j < K; ++j) {
@@ -223,10 +225,10 @@ __global__ void __launch_bounds__(kLargeThreads) knn_large_kernel(const __grid_c
 
 // complete graph, closed form: pair (i, j), i < j at edges 2p, 2p+1 with p = i N - i(i+1)/2 + (j - i - 1)
 __global__ void __launch_bounds__(kLargeThreads) complete_edges_kernel(int N, int E, int32_t* __restrict__ edges) {
-  const long long env = blockIdx.y;
+  const long long env = blockIdx.x;
   int32_t* r0 = edges + env * 2 * E;
   int32_t* r1 = r0 + E;
-  const int i = blockIdx.x;
+  const int i = blockIdx.y;
   const long long base = (long long)i * N - ((long long)i * (i + 1)) / 2;
   for (int j = i + 1 + threadIdx.x; j < N; j += kLargeThreads) {
     const long long e = 2 * (base + (j - i - 1));
@@ -421,8 +423,7 @@ cudaError_t launch_sim_step_large(const TileParams& tp, cudaStream_t stream) {
   p.dmin_ao = tp.dmin_ao;
   p.qmax_aa = tp.qmax_aa;
   p.qmax_ao = tp.qmax_ao;
-  const dim3 grid((c.n_agents + kLargeThreads - 1) / kLargeThreads, c.num_envs);
-  sim_step_large_kernel<<<grid, kLargeThreads, c.n_agents * sizeof(float2), stream>>>(p);
+  sim_step_large_kernel<<<c.num_envs, kLargeThreads, c.n_agents * sizeof(float2), stream>>>(p);
   if (c.scenario == SWARM_SCENARIO_GOTO && tp.rewards_out)
     goto_reward_large_kernel<<<c.num_envs, kLargeThreads, c.n_agents * sizeof(float), stream>>>(
         c, reinterpret_cast<const float4*>(tp.state_out), tp.rewards_out);
@@ -438,13 +439,13 @@ cudaError_t launch_graph_large(const SwarmConfig& c, const float* state, int32_t
     p.edges = edges;
     p.nbr = nbr;
     p.edges_per_env = edges_per_env;
-    const dim3 grid((c.n_agents + kLargeThreads - 1) / kLargeThreads, c.num_envs);
+    const dim3 grid(c.num_envs, (c.n_agents + kLargeThreads - 1) / kLargeThreads);
     const size_t smem = c.n_agents * sizeof(float2) + (size_t)c.knn_k * kLargeThreads * 8;
     cudaError_t err = cudaFuncSetAttribute(knn_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     knn_large_kernel<<<grid, kLargeThreads, smem, stream>>>(p);
   } else if (edges) {
-    const dim3 grid(c.n_agents, c.num_envs);
+    const dim3 grid(c.num_envs, c.n_agents);
     complete_edges_kernel<<<grid, kLargeThreads, 0, stream>>>(c.n_agents, edges_per_env, edges);
   }
   return cudaGetLastError();

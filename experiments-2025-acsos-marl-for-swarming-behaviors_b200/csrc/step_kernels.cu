@@ -131,7 +131,7 @@ struct StepStreamSmem {
   float rout[kStepOutBufs][kStepThreads];
   float sdg[kStepThreads];
   uint64_t full[kStepStages];
-  float2 force_of_action[16];     // decode table: flat action -> (ux, uy); entries >= 9 unused
+  float2 force_of_action[16];     // decode table: flat action -> (ux, uy); entries >= 9 are zero (invalid actions)
 };
 
 // `ntiles` full tiles of p.epb envs each (the ragged tail goes to sim_step_kernel); p.epb * N is a multiple of 4 so
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) sim_step_stream_kernel(const 
       float4 s = sm.sin[stage][tid];
       const int action = sm.ain[stage][tid];
       float gx, gy;
-      const float2 u = sm.force_of_action[action & 15];      // vmas _set_action (a // 3, a % 3) -> (0, -1, +1)
+      const float2 u = sm.force_of_action[min((unsigned)action, 9u)];      // vmas _set_action (a // 3, a % 3) -> (0, -1, +1)
       float fx = u.x, fy = u.y;
       uint8_t flags = 0;
       uint32_t cmask = 0;

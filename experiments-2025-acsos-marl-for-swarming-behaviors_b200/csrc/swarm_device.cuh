@@ -26,7 +26,11 @@ __device__ __forceinline__ float norm2(float x, float y) {
 __device__ __forceinline__ float action_component(int idx) {
   return idx == 0 ? 0.0f : (idx == 1 ? -1.0f : 1.0f);
 }
+// Flat actions outside [0, 8] are a caller error (vmas raises; the Python seam asserts on them): every kernel treats
+// them as action 0 (no force) and the replay ring stores 0, so no table or weight row is ever indexed out of range.
+__device__ __forceinline__ int sanitize_action(int a) { return (unsigned)a > 8u ? 0 : a; }
 __device__ __forceinline__ void decode_action(int a, float& ux, float& uy) {
+  a = sanitize_action(a);
   ux = action_component(a / 3);
   uy = action_component(a % 3);
 }

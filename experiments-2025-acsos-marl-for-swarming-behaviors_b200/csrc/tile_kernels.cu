@@ -242,7 +242,7 @@ tile_kernel(const __grid_constant__ TileParams p) {
             const long long ri = slot * N + t.i;
             reinterpret_cast<float4*>(p.replay.state)[ri] = s_prev;
             reinterpret_cast<float4*>(p.replay.next_state)[ri] = s;
-            p.replay.actions[ri] = (uint8_t)action;
+            p.replay.actions[ri] = (uint8_t)sanitize_action(action);
           }
         }
       }
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(256) replay_push_kernel(SwarmReplay r, long lo
     const long long ri = ((cursor + b) % r.capacity) * N + i;
     reinterpret_cast<float4*>(r.state)[ri] = state[gI];
     reinterpret_cast<float4*>(r.next_state)[ri] = next_state[gI];
-    r.actions[ri] = (uint8_t)actions[gI];
+    r.actions[ri] = (uint8_t)sanitize_action(actions[gI]);
     r.rewards[ri] = rewards[gI];
   }
 }
@@ -357,7 +357,9 @@ __global__ void __launch_bounds__(256) replay_gather_kernel(SwarmReplay r, const
   for (long long gI = (long long)blockIdx.x * blockDim.x + threadIdx.x; gI < total; gI += (long long)gridDim.x * blockDim.x) {
     const long long b = gI / N;
     const int i = (int)(gI - b * N);
-    const long long ri = indices[b] * N + i;
+    long long slot = indices[b];                          // caller-supplied: clamped into the ring, never out of bounds
+    slot = slot < 0 ? 0 : (slot >= r.capacity ? r.capacity - 1 : slot);
+    const long long ri = slot * N + i;
     state[gI] = reinterpret_cast<const float4*>(r.state)[ri];
     next_state[gI] = reinterpret_cast<const float4*>(r.next_state)[ri];
     actions[gI] = r.actions[ri];

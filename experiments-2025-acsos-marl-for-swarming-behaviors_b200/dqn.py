@@ -253,6 +253,7 @@ class DQNTrainer:
                            env_offset=int(config.get("env_offset", rank * B)),
                            flocking=env.scenario._spec() if flock else None,
                            shaping=env.scenario.shaping if flock else None)
+        parallel.require_equal_shards(B, ring.size, ring.position, ring.capacity, G)
         parallel.broadcast_weights(self.w)
         self.w_target.copy_(self.w)
         tt.load_cursor(int(config.get("start_tick", 0)), self.opt_step, epsilon)
@@ -396,6 +397,7 @@ class DQNTrainer:
         spec = ops.reset_spec(cfg.scenario, random=bool(getattr(env.scenario, "random", True)),
                               seed=int(config.get("reset_seed", self.seed)), env_offset=tt.hyper.env_offset,
                               shared_center=bool(config.get("shared_center", False)))
+        parallel.require_equal_shards(B, ring.size, ring.position, ring.capacity, G)
         parallel.broadcast_weights(self.w)
         self.w_target.copy_(self.w)
         tt.load_cursor(int(config.get("start_tick", 0)), self.opt_step, config["epsilon"], 0)
@@ -446,7 +448,13 @@ class DQNTrainer:
         cfg = ops.clone_config(self.graph_cfg, num_envs=self.env.num_envs)
         for _ in range(eval_episodes):
             self.env.reset()
-            out = ops.rollout(cfg, self.w, self.env.world.state, self.env.max_steps)
+            flock = isinstance(self.env.scenario, FlockingScenario)
+            out = ops.rollout(cfg, self.w, self.env.world.state, self.env.max_steps,
+                              trace=dict(rewards=True, flags=True, dist=True),
+                              flocking=self.env.scenario._spec() if flock else None,
+                              shaping=self.env.scenario.shaping if flock else None)
+            self.env.steps += self.env.max_steps
+            self.env.world.adopt_rollout(out)
             total += out["returns"][0, 0].item()
         return total / eval_episodes
 

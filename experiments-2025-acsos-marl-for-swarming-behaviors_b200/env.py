@@ -106,6 +106,8 @@ class Environment:
         if isinstance(actions, torch.Tensor):
             if actions.shape != (B, N):
                 raise AssertionError(f"action tensor must be [{B}, {N}], got {list(actions.shape)}")
+            if actions.is_cuda:
+                torch._assert_async(((actions >= 0) & (actions <= 8)).all(), "Discrete actions must be in [0, 8]")
             return actions.to(device=self.device, dtype=torch.int32).contiguous()
         if isinstance(actions, dict):
             if len(actions) != N or any(a.name not in actions for a in self.agents):
@@ -124,6 +126,10 @@ class Environment:
             lo, hi = int(out.min()), int(out.max())
             if lo < 0 or hi > 8:
                 raise AssertionError(f"Discrete actions must be in [0, 8], got [{lo}, {hi}]")
+        else:
+            # device tensors: asserted on the device without a host sync (vmas raises here); the kernels themselves
+            # map an out-of-range action to "no force" so nothing is indexed out of bounds either way
+            torch._assert_async(((out >= 0) & (out <= 8)).all(), "Discrete actions must be in [0, 8]")
         return out.to(device=self.device, dtype=torch.int32).contiguous()
 
     def step(self, actions):

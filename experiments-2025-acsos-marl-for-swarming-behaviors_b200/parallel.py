@@ -84,34 +84,47 @@ def global_loss_scale(local_graphs: int, n_agents: int) -> float:
     return 1.0 / (local_graphs * world_size() * n_agents)
 
 
-class PeerExchange:
-    """Symmetric (peer-mapped) buffers for the fused one-shot gradient all-reduce of ``swarm_train_tick_apply``:
-    every rank allocates float[2][1680] + uint64[2] with ``torch.distributed._symmetric_memory`` and maps all peers'
-    copies over NVLink; the clip + Adam kernel publishes its partial gradient there, flags it, waits for the peers'
-    flags and sums the partials in rank order.  PyTorch only provides the allocation / rendezvous plumbing."""
+def require_equal_shards(num_envs: int, ring_size: int, ring_position: int, ring_capacity: int,
+                         graphs_per_update: int) -> None:
+    """The data-parallel tick decides on the device whether a tick updates (ring fill >= G, train:113-115) and every
+    rank must take the same decision: a rank that exchanges gradients while a peer skips would wait for words that
+    never arrive (fused peer exchange) or apply Adam alone (NCCL path).  So all ranks must run the same number of
+    envs per tick and start from the same ring state.  Raises ValueError otherwise (``shard_envs`` with a remainder
+    gives unequal counts: pad or trim the env total to a multiple of the world size)."""
+    if world_size() <= 1:
+        return
+    mine = [int(num_envs), int(ring_size), int(ring_position), int(ring_capacity), int(graphs_per_update)]
+    gathered = [None] * world_size()
+    dist.all_gather_object(gathered, mine)
+    if any(g != gathered[0] for g in gathered):
+        raise ValueError("data-parallel DQN needs the same (num_envs, replay fill, cursor, capacity, graphs_per_update) on "
+                         f"every rank; got {gathered}")
 
-    DATA_FLOATS = 2 * 1680
-    FLAG_BYTES = 16
+
+class PeerExchange:
+    """Symmetric (peer-mapped) receive buffers for the fused one-shot PUSH all-reduce of ``swarm_train_tick_apply``:
+    every rank allocates uint64[2][world][1680] with ``torch.distributed._symmetric_memory`` and maps all peers' copies
+    over NVLink; the clip + Adam kernel writes its partial gradient (value + epoch per 8-byte word) into its slot of
+    every peer's buffer, polls its own local buffer for the peers' words and sums the partials in rank order.  PyTorch
+    only provides the allocation / rendezvous plumbing."""
 
     def __init__(self, device, group=None):
-        import ctypes as C
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
         group = group if group is not None else dist.group.WORLD
-        # one buffer: data floats followed by the two 8-byte flags (offset is a multiple of 16 bytes)
-        self.buf = symm_mem.empty(self.DATA_FLOATS + self.FLAG_BYTES // 4, dtype=torch.float32, device=device)
+        world = dist.get_world_size(group)
+        if world > 16:
+            raise ValueError("PeerExchange supports up to 16 ranks")
+        self.buf = symm_mem.empty(2 * world * _lib.XCHG_STRIDE, dtype=torch.int64, device=device)
         self.buf.zero_()
         self.handle = symm_mem.rendezvous(self.buf, group)
         st = _lib.SwarmPeerExchange()
         st.world_size, st.rank = self.handle.world_size, self.handle.rank
-        if st.world_size > 16:
-            raise ValueError("PeerExchange supports up to 16 ranks")
         for r, base in enumerate(self.handle.buffer_ptrs):
             st.data[r] = base
-            st.flags[r] = base + self.DATA_FLOATS * 4
         self.struct = st
         torch.cuda.synchronize(device)
-        dist.barrier(group)            # every rank's buffer is zeroed before anybody's kernel can flag it
+        dist.barrier(group)            # every rank's buffer is zeroed before anybody's kernel can write into it
 
 
 def make_peer_exchange(device) -> Optional["PeerExchange"]:

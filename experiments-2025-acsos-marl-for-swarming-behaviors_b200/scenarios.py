@@ -117,15 +117,17 @@ class Entity:
         self._require_world().version += 1
         p_host = torch.as_tensor(pos, dtype=torch.float32)
         p = p_host.to(st.pos.device)
+        # a 1-D position is one value for every env it is written to: mirrored on the host (kernel constant); a device
+        # tensor costs one tiny D2H copy here, at reset time
+        vec = tuple(float(v) for v in p_host.detach().cpu()[:2]) if p_host.dim() == 1 else None
         if batch_index is None:
             st.pos[...] = p
-            self._host_pos = (float(p_host[0]), float(p_host[1])) if p_host.dim() == 1 and not p_host.is_cuda else None
+            self._host_pos = vec
         else:
             st.pos[batch_index] = p
-            if self._world.batch_dim == 1 and p_host.dim() == 1 and not p_host.is_cuda:
-                self._host_pos = (float(p_host[0]), float(p_host[1]))
-            elif self._host_pos is not None and p_host.dim() == 1 and not p_host.is_cuda and \
-                    (float(p_host[0]), float(p_host[1])) != self._host_pos:
+            if self._world.batch_dim == 1 and vec is not None:
+                self._host_pos = vec
+            elif self._host_pos is not None and vec != self._host_pos:
                 self._host_pos = None
 
 
@@ -270,7 +272,9 @@ class World:
             if self._obstacle._host_pos is None:
                 raise NotImplementedError("the obstacle must sit at the same position in every env")
             self.cfg.obstacle_x, self.cfg.obstacle_y = self._obstacle._host_pos
-        if self._goal is not None and self._goal._host_pos is not None:
+        if self._goal is not None:
+            if self._goal._host_pos is None:
+                raise NotImplementedError("the goal must sit at the same position in every env")
             self.cfg.goal_x, self.cfg.goal_y = self._goal._host_pos
 
     def _refresh_outputs(self) -> None:
@@ -311,6 +315,23 @@ class World:
         self._sync_constants()
         self.version += 1
         self.last = ops.sim_step(self.cfg, self.state, actions, state_out=self.state, want_obs=True)
+
+    def adopt_rollout(self, out: Dict[str, torch.Tensor]) -> None:
+        """A fused rollout (``ops.rollout``) advanced ``self.state`` in place: make the world look as it does after the
+        last ``Environment.step`` of that rollout -- version bumped (version-keyed reward caches drop their entry) and
+        ``self.last`` rebuilt from the last tick's traces, so that ``observation()`` / ``reward()`` /
+        ``average_distance_to_goal()`` / ``obstacles_hits()`` report the final tick instead of the post-reset zeros.
+        ``out`` must carry the ``rewards``, ``flags`` and ``dist`` traces."""
+        B, N = self.cfg.num_envs, self.cfg.n_agents
+        self.version += 1
+        goal = torch.tensor([self.cfg.goal_x, self.cfg.goal_y], dtype=torch.float32, device=self.device)
+        self.last = {
+            "state": self.state,
+            "obs": torch.cat([self.state, goal.view(1, 1, 2).expand(B, N, 2)], dim=2),
+            "rewards": out["trace_rewards"][-1].clone(),
+            "flags": out["trace_flags"][-1].clone(),
+            "dist": out["trace_dist"][-1].clone(),
+        }
 
     def get_distance(self, a: Entity, b: Entity) -> torch.Tensor:
         """vmas World.get_distance for two spheres: centre distance minus the two radii (oa:149-150,168,171)."""

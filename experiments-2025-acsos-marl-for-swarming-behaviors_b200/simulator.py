@@ -21,6 +21,7 @@ import torch
 
 from . import _lib, ops
 from .graph import Data, create_graph_from_observations as _create_graph
+from .scenarios import FlockingScenario
 
 
 def create_graph_from_observations(self, observations: Dict[str, torch.Tensor], num_agents: int, k: int = 10) -> Data:
@@ -65,8 +66,12 @@ class Simulator:
         for episode in range(self.episodes):
             env.reset()
             init_time = time.time()
-            out = ops.rollout(cfg, weights, world.state, T, trace=dict(state=True, rewards=True, flags=True, dist=True))
+            flock = isinstance(env.scenario, FlockingScenario)      # its collective reward replaces GoTo's on the fused path
+            out = ops.rollout(cfg, weights, world.state, T, trace=dict(state=True, rewards=True, flags=True, dist=True),
+                              flocking=env.scenario._spec() if flock else None,
+                              shaping=env.scenario.shaping if flock else None)
             env.steps += T
+            world.adopt_rollout(out)         # scenario metrics / observation() / reward() now describe the final tick
             st = out["trace_state"][:, 0].cpu()                   # [T, n, 4]
             rew = out["trace_rewards"][:, 0].cpu()                # [T, n]
             hit = ((out["trace_flags"][:, 0].cpu() & _lib.FLAG_HIT) != 0)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SWARM_ABI_VERSION 1
+#define SWARM_ABI_VERSION 2
 
 enum { SWARM_SCENARIO_GOTO = 0, SWARM_SCENARIO_OBSTACLE_AVOIDANCE = 1 };
 /* SWARM_GRAPH_RADIUS is an EXTENSION (the reference has no radius graph): the complete-graph
@@ -328,17 +328,18 @@ int swarm_train_tick_grad(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, 
                           int32_t* hits, const SwarmReplay* ring, int64_t* indices, float* grad, float* loss,
                           void* workspace, int64_t workspace_bytes, void* stream);
 
-/* Optional peer exchange for swarm_train_tick_apply: a one-shot all-reduce of the gradient over NVLink / NVSwitch peer
- * memory fused into the clip + Adam kernel (replaces the separate NCCL all-reduce launch of a data-parallel tick).
- * data[r] / flags[r] are THIS process's mappings of rank r's symmetric buffers (e.g. from
- * torch.distributed._symmetric_memory): data float[2][SWARM_XCHG_STRIDE] (double-buffered by tick parity), flags
- * uint64[2], both zero-initialised.  Every rank publishes its partial gradient + loss in its own buffer, releases
- * flags[rank][parity] = tick + 1 (st.release.sys), acquires the peers' flags and sums the world_size partials in rank
- * order -- the same order on every rank, so the weights stay bit-identical across ranks without a broadcast. */
+/* Optional peer exchange for swarm_train_tick_apply: a one-shot PUSH all-reduce of the gradient over NVLink / NVSwitch
+ * peer memory fused into the clip + Adam kernel (replaces the separate NCCL all-reduce launch of a data-parallel tick).
+ * data[r] is THIS process's mapping of rank r's symmetric receive buffer (e.g. from
+ * torch.distributed._symmetric_memory): uint64[2][world_size][SWARM_XCHG_STRIDE], zero-initialised -- slot
+ * [parity of tick + 1][source rank].  Every rank writes its partial gradient + loss into its slot of EVERY rank's buffer
+ * as 8-byte words (epoch = tick + 1 in the high half, the float in the low half: the word is its own arrival flag), then
+ * waits on its own (local) buffer and sums the world_size partials in rank order -- the same order on every rank, so the
+ * weights stay bit-identical across ranks without a broadcast.  All ranks must run the same number of envs and start
+ * from the same ring fill (they must agree on which ticks update). */
 enum { SWARM_MAX_PEERS = 16, SWARM_XCHG_STRIDE = 1680 };
 typedef struct SwarmPeerExchange {
-  float* data[SWARM_MAX_PEERS];
-  uint64_t* flags[SWARM_MAX_PEERS];
+  uint64_t* data[SWARM_MAX_PEERS];
   int32_t world_size;
   int32_t rank;
 } SwarmPeerExchange;

@@ -117,7 +117,7 @@ def test_training_struct_layouts_match_header(sb, tmp_path):
     fields = [("SwarmTrainCtl", ["tick", "ring_cursor", "ring_size", "opt_step", "epsilon", "updating", "episode"]),
               ("SwarmTrainHyper", ["lr", "max_norm", "rng_seed", "env_offset", "graphs_per_update", "gamma", "loss_scale"]),
               ("SwarmResetSpec", ["base_x", "std_y", "seed", "env_offset", "shared_center"]),
-              ("SwarmPeerExchange", ["data", "flags", "world_size", "rank"])]
+              ("SwarmPeerExchange", ["data", "world_size", "rank"])]
     body = "".join(f'printf("%zu ", sizeof({s}));' + "".join(f'printf("%zu ", offsetof({s}, {f}));' for f in fs)
                    for s, fs in fields)
     prog = tmp_path / "layout2.c"

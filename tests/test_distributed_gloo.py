@@ -68,7 +68,15 @@ def _worker(rank, world, port, ret):
         off += p.numel()
     grad, loss = _partial_grad(model, target, _batch(7 + shard.rank, G, N), parallel.global_loss_scale(G, N))
     parallel.allreduce_gradient(grad, loss)
-    ret[rank] = (flat.clone(), tflat.clone(), grad.clone(), loss.clone(), shard)
+    # every rank must take the same "does this tick update?" decision: equal shards pass, unequal ones are refused on
+    # EVERY rank (a one-sided error would leave the peers waiting in the exchange)
+    parallel.require_equal_shards(64, 0, 0, 4096, 32)
+    try:
+        parallel.require_equal_shards(64 + rank, 0, 0, 4096, 32)
+        refused = False
+    except ValueError:
+        refused = True
+    ret[rank] = (flat.clone(), tflat.clone(), grad.clone(), loss.clone(), shard, refused)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -79,7 +87,8 @@ def test_sharded_update_equals_full_batch_update():
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
-    (w0, t0, g0, l0, s0), (w1, t1, g1, l1, s1) = ret[0], ret[1]
+    (w0, t0, g0, l0, s0, r0), (w1, t1, g1, l1, s1, r1) = ret[0], ret[1]
+    assert r0 and r1, "unequal env shards must be refused on every rank"
     assert torch.equal(w0, w1) and torch.equal(t0, t1), "weights must be replicated after the broadcast"
     assert torch.equal(g0, g1) and torch.equal(l0, l1), "all ranks hold the same reduced gradient"
     assert (s0.offset, s0.count, s1.offset, s1.count) == (0, 6, 6, 6)

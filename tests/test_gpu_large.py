@@ -54,6 +54,33 @@ def test_large_sim_step_parity(scenario, N, B):
         assert torch.allclose(out["rewards"].cpu(), ref["rewards"], rtol=1e-6)
 
 
+def test_large_sim_step_in_place_with_contacts():
+    """state_out == state_in (what World.step and rollout_large do) with contacts at N = 1024 and more CTAs than one
+    wave: every env's partner positions must be the PRE-step ones, so the in-place result equals the out-of-place one
+    bit for bit and the call is repeatable (a (chunk, env) grid used to race here)."""
+    import swarm_b200 as sb
+    N, B = 1024, 640                                      # 640 envs > 148 SMs x resident CTAs of this kernel
+    pos, vel = _states("obstacle_avoidance", 4, N, seed=11, spread=0.55)
+    reps = B // 4
+    pos, vel = pos.repeat(reps, 1, 1), vel.repeat(reps, 1, 1)
+    actions = torch.randint(0, 9, (B, N), generator=torch.Generator().manual_seed(5)).to(torch.int32).to(_dev())
+    state = torch.cat([pos, vel], 2).contiguous().to(_dev())
+    cfg = sb.ops.make_config(sb._lib.SCENARIO_OBSTACLE_AVOIDANCE, B, N)
+    ref = sb.ops.sim_step(cfg, state, actions, want_obs=False)
+    d = torch.cdist(pos[:4], pos[:4]) + 10 * torch.eye(N)
+    assert (d <= 0.1).any(), "the fixture must contain agent-agent contacts"
+    for _ in range(3):
+        work = state.clone()
+        out = sb.ops.sim_step(cfg, work, actions, state_out=work, want_obs=False)
+        assert torch.equal(out["state"], ref["state"]) and torch.equal(out["rewards"], ref["rewards"])
+        assert torch.equal(out["flags"], ref["flags"])
+    # and envs with identical inputs give identical outputs, whichever CTA / wave ran them
+    st = ref["state"].view(reps, 4, N, 4)
+    a4 = actions.view(reps, 4, N)
+    same = (a4 == a4[:1]).all(dim=2)                      # [reps, 4]: envs whose actions equal replica 0's
+    assert same[0].all()
+
+
 def _vector_step(scenario, pos, vel, actions):
     """oracle/batched_oracle.step with the agent-pair loop vectorised over j (same separately rounded torch ops and
     the same ascending-partner accumulation order); cross-checked against the oracle itself in test below."""

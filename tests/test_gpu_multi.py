@@ -1,6 +1,8 @@
-"""Two-GPU checks of the data-parallel train tick (skipped on single-GPU boxes): the gradient all-reduce fused into the
-clip + Adam kernel over NVLink peer memory gives the same weights as the NCCL all-reduce between the two phases, the
-ranks stay bit-identical, and the ticks replay from a CUDA graph.  Run with `gpurun --gpus 2`."""
+"""Multi-GPU checks of the data-parallel train tick (skipped on single-GPU boxes; uses every visible GPU, 2 ... 8): the
+gradient all-reduce fused into the clip + Adam kernel (one-shot push over NVLink peer memory) gives the same weights as
+the NCCL all-reduce between the two phases -- bit for bit at 2 ranks, where any summation order is the same sum, within
+float32 rounding above -- the ranks stay bit-identical, and the ticks replay from a CUDA graph.
+Run with `gpurun --gpus 2` (or 4 / 8).  `bench.py --gpus N` repeats the bit-identity check on its DQN ticks."""
 import os
 import socket
 import sys
@@ -78,9 +80,14 @@ def _worker(rank, world, port, out):
         gathered = [torch.empty_like(w) for _ in range(world)]
         dist.all_gather(gathered, w)
         assert all(torch.equal(gathered[0], x) for x in gathered), f"{mode}: ranks diverged"
-    for a, b in (("nccl", "peer"), ("peer", "peer_graph")):
-        for x, y in zip(res[a], res[b]):
-            assert torch.equal(x, y), f"{a} vs {b} differ: {(x - y).abs().max().item():.3e}"
+    for x, y in zip(res["peer"], res["peer_graph"]):
+        assert torch.equal(x, y), f"peer vs peer_graph differ: {(x - y).abs().max().item():.3e}"
+    for x, y in zip(res["nccl"], res["peer"]):
+        if world == 2:
+            assert torch.equal(x, y), f"nccl vs peer differ: {(x - y).abs().max().item():.3e}"
+        else:       # NCCL's reduction order is its own; Adam's normalisation (an early step moves a weight by +-lr whatever
+            #         the gradient's size) amplifies last-bit gradient differences, so this is a sanity bound only
+            assert torch.allclose(x, y, rtol=1e-2, atol=5e-3), f"nccl vs peer differ: {(x - y).abs().max().item():.3e}"
     assert not torch.equal(res["nccl"][0], w0)
     dist.barrier()
     dist.destroy_process_group()
@@ -88,9 +95,10 @@ def _worker(rank, world, port, out):
         open(out, "w").write("ok")
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least two GPUs")
 def test_peer_allreduce_matches_nccl(tmp_path):
     import torch.multiprocessing as mp
     out = str(tmp_path / "done")
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    world = min(torch.cuda.device_count(), 8)
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert open(out).read() == "ok"
