@@ -266,6 +266,26 @@ def run_ours(args):
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
     ms_e2e = timed(step_e2e, args.steps)
     dqn_stats = measure_dqn(sb, ops, dev, cfg, weights, centers, dist, barrier, stream, rank, world)
+    strong = None
+    if world > 1:
+        # strong-scaling point: the SAME 4 096 envs in total, split over the ranks
+        Bs = ENVS_PER_GPU // world
+        scfg = ops.make_config(sb._lib.SCENARIO_OBSTACLE_AVOIDANCE, Bs, N, sb._lib.GRAPH_COMPLETE)
+        sc = draw_centers(0, ENVS_PER_GPU)[rank * Bs:(rank + 1) * Bs].contiguous().to(dev)
+        sstate = torch.empty(Bs, N, 4, device=dev)
+        sret = torch.zeros(Bs, N, device=dev)
+        shits = torch.zeros(Bs, dtype=torch.int32, device=dev)
+
+        def step_strong():
+            ops.reset_grid(scfg, sc, out=sstate)
+            ops.rollout(scfg, weights, sstate, T, returns=sret, hits=shits)
+
+        for _ in range(3):
+            step_strong()
+        ms_strong = timed(step_strong, args.steps)
+        strong = {"scaling": "strong", "total_envs": Bs * world, "envs_per_gpu": Bs,
+                  "value": Bs * world * N * T * args.steps / (ms_strong * 1e-3), "unit": "agent-steps/s",
+                  "ms_per_step": ms_strong / args.steps}
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -305,6 +325,8 @@ def run_ours(args):
     }
     line["roofline"]["traffic"] = ncu_dram_traffic_bytes()
     line["dqn"] = dqn_stats
+    if strong is not None:
+        line["strong_scaling_point"] = strong
     if world == 1:
         line["memory_bound_kernels"] = measure_streaming_kernels(sb, ops, dev, peak_gbs)
     if world == 1 and not args.no_cpu:
@@ -445,7 +467,20 @@ def measure_dqn(sb, ops, dev, cfg, weights, centers, dist, barrier, stream, rank
         graph.replay()                      # warm replay
         ms = timed(graph.replay)
         cur = tt.read_cursor()
-        out[f"G{G}"] = {"graphs_per_update_per_gpu": G, "updates_per_s": ticks / (ms * 1e-3),
+        # replicas must stay bit-identical (train:131-133 semantics: one model): all-gather the packed weights after
+        # the 10 + 2 * ticks + ticks data-parallel updates and compare them on every rank
+        identical, digest = True, None
+        if dist is not None:
+            gathered = [torch.empty_like(w) for _ in range(world)]
+            dist.all_gather(gathered, w)
+            identical = all(torch.equal(gathered[0], x) for x in gathered)
+            flag = torch.tensor([1 if identical else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            identical = bool(flag.item())
+        import hashlib
+        digest = hashlib.sha1(w.cpu().numpy().tobytes()).hexdigest()[:16]
+        out[f"G{G}"] = {"weights_bit_identical_across_ranks": identical, "weights_sha1_16": digest, "ranks_compared": world,
+"graphs_per_update_per_gpu": G, "updates_per_s": ticks / (ms * 1e-3),
                         "train_agent_steps_per_s": world * B * N * ticks / (ms * 1e-3),
                         "transitions_trained_per_s": world * G * ticks / (ms * 1e-3), "ms_per_tick": ms / ticks,
                         "ms_per_tick_eager": ms_eager / ticks, "kernels_per_tick": 4 + (1 if nccl else 0),

@@ -15,6 +15,7 @@ own shipped artefacts (per-tick positions / distances / hits / result.csv of ``d
 the ``Episode,Reward,Loss`` rows of ``data/stats``; committed in compact form under ``tests/golden``
 by ``tests/golden/make_golden.py``).
 
-Exception: ``scenario_rewards_oracle.py`` (Flocking / Cohesion) is **parity unpinned** -- the reference ships no
-outputs for those scenarios; see that file's header.
+``scenario_rewards_oracle.py`` (Flocking / Cohesion) is pinned against the reference's own scenario source executed
+unmodified on ``oracle/refstub`` (CPU stand-ins of vmas / torch_geometric backed by this oracle; see that directory's
+README and ``tests/golden/make_reference_runs.py``).
 """

@@ -11,17 +11,22 @@ reference runs them,
 on the vmas world the GoTo oracle already restates (``swarm_oracle.OracleWorld``: colliding sphere agents, no
 colliding landmark).
 
-Parity status of THIS file: **parity unpinned**.  The reference ships no golden vectors, result files or tests for
-these two scenarios (``data/`` only holds GoTo / ObstacleAvoidance statistics; the ``experiment_Flocking-*.pth`` files
-are weights of an older network, not trajectories) and vmas cannot be imported here, so the restatement below is
-anchored on the scenario source alone.  The physics, ``vector_norm`` and ``get_distance`` pieces it shares with the GoTo /
-ObstacleAvoidance oracle ARE pinned by the golden trajectories (tests/test_oracle_golden.py).
+Parity status of THIS file: **pinned** (since round 2) against the reference's own source.  The reference ships no
+golden vectors for these two scenarios and vmas cannot be imported here, so the reference's ``flocking_scenario.py`` /
+``cohesion_scenario.py`` are executed UNMODIFIED on a CPU stand-in of the vmas API (``oracle/refstub``, whose world step
+is the restatement that reproduces the reference's shipped GoTo / ObstacleAvoidance trajectories bit for bit --
+``tests/test_refstub.py`` proves that with the reference's own Simulator file).  ``tests/golden/make_reference_runs.py``
+records what their ``reset_world_at`` / ``reward()`` code produces over 60-tick runs with contacts, collision terms,
+on-goal bonuses and both sigma branches (``tests/golden/reference_runs.npz``), and ``tests/test_oracle_scenarios.py``
+checks this restatement against it bit for bit -- including cohesion:80's ``np.exp`` on a tensor (numpy's float32 exp,
+not torch's: 216 of 960 rewards differ in the last bit if ``torch.exp`` is used instead).
 """
 from __future__ import annotations
 
 import math
 from typing import List, Optional
 
+import numpy as np
 import torch
 
 from . import swarm_oracle as so
@@ -156,7 +161,7 @@ class CohesionOracle:
         for i in range(self.n):
             distances = torch.cat([so.get_distance(w.pos[i], w.pos[j]) for j in range(self.n) if j != i])
             mn, mx = torch.min(distances), torch.max(distances)
-            collision = 0 if mn > SIGMA else torch.exp(-(mn / SIGMA))
+            collision = 0 if mn > SIGMA else np.exp(-(mn / SIGMA))     # cohesion:80: numpy's float32 exp on a tensor
             cohesion = 0 if mn < SIGMA else -(mx - SIGMA)
             out.append(torch.as_tensor(collision + cohesion, dtype=torch.float32).reshape(1))
         return torch.cat(out)

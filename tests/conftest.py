@@ -8,6 +8,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+collect_ignore_glob = ["_refsrc/*"]          # the staged reference files are inputs of the tests, not tests
+
+
 def pytest_configure(config):
     # the oracle must be deterministic: multi-threaded torch CPU reductions / scatters change the
     # summation order from run to run (the reference itself runs tiny B = 1 tensors, never parallelised)

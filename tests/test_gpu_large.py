@@ -74,11 +74,6 @@ def test_large_sim_step_in_place_with_contacts():
         out = sb.ops.sim_step(cfg, work, actions, state_out=work, want_obs=False)
         assert torch.equal(out["state"], ref["state"]) and torch.equal(out["rewards"], ref["rewards"])
         assert torch.equal(out["flags"], ref["flags"])
-    # and envs with identical inputs give identical outputs, whichever CTA / wave ran them
-    st = ref["state"].view(reps, 4, N, 4)
-    a4 = actions.view(reps, 4, N)
-    same = (a4 == a4[:1]).all(dim=2)                      # [reps, 4]: envs whose actions equal replica 0's
-    assert same[0].all()
 
 
 def _vector_step(scenario, pos, vel, actions):

@@ -1,10 +1,13 @@
 """Known-answer checks of the Flocking / Cohesion oracle (oracle/scenario_rewards_oracle.py) against values worked out
 independently in float64 from the scenario source (flocking_scenario.py:93-171, cohesion_scenario.py:44-85).  The
-reference ships no golden vectors for these two scenarios -- the oracle says "parity unpinned" -- so these tests pin the
-restatement to the formulas, not to reference outputs."""
+reference ships no golden vectors for these two scenarios, so the restatement is pinned twice: to the formulas (the
+hand computations below) and -- at the end of this file -- to the outputs of the reference's own scenario files,
+executed unmodified on the CPU stand-in of vmas (tests/golden/reference_runs.npz, made by
+tests/golden/make_reference_runs.py)."""
 import math
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import scenario_rewards_oracle as sro
@@ -94,3 +97,57 @@ def test_cohesion_more_than_nine_agents_raises():
     import pytest
     with pytest.raises(IndexError):
         sro.CohesionOracle(10)
+
+
+# ---- the pin: the reference's own reward() source (tests/golden/reference_runs.npz) ---------------------------------
+@pytest.mark.parametrize("n", [2, 5, 9, 12])
+def test_flocking_oracle_equals_the_reference_source(n):
+    """FlockingScenario (flocking_scenario.py, executed unmodified on oracle/refstub by
+    tests/golden/make_reference_runs.py) vs the restatement: shaping memory after reset, 60 ticks of positions and
+    collective rewards incl. contacts, the -1 collision terms and the +50 on-goal bonus -- bit for bit."""
+    import numpy as np
+    from helpers import npz
+    g, pre = npz("reference_runs.npz"), f"flocking/n{n}/"
+    o = sro.FlockingOracle(n)
+    w = o.world
+    w.goal = torch.tensor(list(sro.GOAL_POS)).unsqueeze(0)
+    pos0 = torch.from_numpy(g[pre + "pos0"])
+    for i in range(n):
+        w.pos[i], w.vel[i] = torch.zeros(1, 2), torch.zeros(1, 2)
+    for i in range(n):                                  # reset_world_at's placement loop (flocking:93-121)
+        w.pos[i] = pos0[i:i + 1].clone()
+        o.previous_distance_to_goal[i] = torch.linalg.vector_norm(w.pos[i] - w.goal, dim=1) * o.pos_shaping_factor
+        o.previous_distance_to_agents[i] = o._spacing(i)
+    shaping = lambda: np.stack([[float(o.previous_distance_to_goal[i]), float(o.previous_distance_to_agents[i])]
+                                for i in range(n)]).astype(np.float32)
+    assert np.array_equal(shaping(), g[pre + "shaping0"])
+    contact = False
+    for t in range(g[pre + "actions"].shape[0]):
+        r = o.step(torch.from_numpy(g[pre + "actions"][t].astype(np.int64)))
+        pos = torch.cat(w.pos).numpy()
+        assert np.array_equal(pos, g[pre + "pos"][t]) and np.array_equal(torch.cat(w.vel).numpy(), g[pre + "vel"][t])
+        assert np.all(np.float32(r.item()) == g[pre + "rewards"][t]), f"tick {t}"
+        assert np.array_equal(shaping(), g[pre + "shaping"][t])
+        d = np.linalg.norm(pos[:, None] - pos[None], axis=-1) + 9 * np.eye(n)
+        contact |= bool(d.min() <= 0.1)
+    assert contact, "the fixture is meant to exercise contacts"
+
+
+@pytest.mark.parametrize("n", [2, 5, 9])
+def test_cohesion_oracle_equals_the_reference_source(n):
+    """CohesionScenario (cohesion_scenario.py incl. its np.exp on a tensor, cohesion:80): fixed start table, 60 ticks of
+    positions and per-agent rewards -- bit for bit; observations are 4 floats."""
+    import numpy as np
+    from helpers import npz
+    g, pre = npz("reference_runs.npz"), f"cohesion/n{n}/"
+    o = sro.CohesionOracle(n)
+    o.reset()
+    assert np.array_equal(torch.cat(o.world.pos).numpy(), g[pre + "pos0"])
+    assert o.observations().shape[-1] == int(g[pre + "obs_dim"]) == 4
+    branches = set()
+    for t in range(g[pre + "actions"].shape[0]):
+        r = o.step(torch.from_numpy(g[pre + "actions"][t].astype(np.int64)))
+        assert np.array_equal(torch.cat(o.world.pos).numpy(), g[pre + "pos"][t])
+        assert np.array_equal(r.numpy(), g[pre + "rewards"][t]), f"tick {t}"
+        branches |= {"near" if v > 0 else "far" for v in r.tolist()}
+    assert branches == {"near", "far"}, "both sigma branches must occur"
