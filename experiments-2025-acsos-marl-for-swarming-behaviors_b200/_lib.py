@@ -169,6 +169,25 @@ def lib() -> C.CDLL:
     return _LIB
 
 
+def offload_device() -> Optional[torch.device]:
+    """``SWARM_DEVICE`` (e.g. ``cuda`` or ``cuda:0``): the B200 that serves scripts which ask for ``device="cpu"``.
+
+    The reference scripts hard-code ``device = 'cpu'`` (train_gcn_dqn.py:262, tests/test_*.py:33).  With SWARM_DEVICE set
+    such a script runs UNMODIFIED: tensors at its seams (observations, rewards, ``agent.state.pos``, ``Data.x``,
+    model parameters) stay host tensors as it asked, while ``env.step`` and ``GATConv`` / ``GCN`` execute in
+    libswarm_b200.so on this device (host<->device copies at the seam).  Without it, a CPU device raises: there is no
+    CPU implementation to fall back to."""
+    name = os.environ.get("SWARM_DEVICE", "").strip()
+    if not name:
+        return None
+    dev = torch.device(name)
+    if dev.type != "cuda":
+        raise SwarmError(f"SWARM_DEVICE must name a CUDA device, got {name!r}")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
 def check(rc: int) -> None:
     if rc != 0:
         msg = lib().swarm_last_error().decode()

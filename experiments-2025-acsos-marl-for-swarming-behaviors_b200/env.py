@@ -89,12 +89,16 @@ class Environment:
         return self._collect(self.scenario.observation) if return_observations else None
 
     def _collect(self, fn):
+        # tensors cross the seam on the device the script asked for (host-seam mode: a D2H copy of what a kernel-backed
+        # scenario returned; a no-op otherwise)
+        def home(v):
+            return v.to(self.device) if isinstance(v, torch.Tensor) and v.device != self.device else v
         if self.dict_spaces:
-            return {a.name: fn(a) for a in self.agents}
-        return [fn(a) for a in self.agents]
+            return {a.name: home(fn(a)) for a in self.agents}
+        return [home(fn(a)) for a in self.agents]
 
     def done(self) -> torch.Tensor:
-        dones = self.scenario.done().clone()
+        dones = self.scenario.done().clone().to(self.device)
         if self.max_steps is not None:
             dones = dones | (self.steps >= self.max_steps)
         return dones
@@ -108,7 +112,7 @@ class Environment:
                 raise AssertionError(f"action tensor must be [{B}, {N}], got {list(actions.shape)}")
             if actions.is_cuda:
                 torch._assert_async(((actions >= 0) & (actions <= 8)).all(), "Discrete actions must be in [0, 8]")
-            return actions.to(device=self.device, dtype=torch.int32).contiguous()
+            return actions.to(device=self.world.compute_device, dtype=torch.int32).contiguous()
         if isinstance(actions, dict):
             if len(actions) != N or any(a.name not in actions for a in self.agents):
                 raise AssertionError("Expecting actions for all agents")     # vmas Environment.step assertion
@@ -130,7 +134,7 @@ class Environment:
             # device tensors: asserted on the device without a host sync (vmas raises here); the kernels themselves
             # map an out-of-range action to "no force" so nothing is indexed out of bounds either way
             torch._assert_async(((out >= 0) & (out <= 8)).all(), "Discrete actions must be in [0, 8]")
-        return out.to(device=self.device, dtype=torch.int32).contiguous()
+        return out.to(device=self.world.compute_device, dtype=torch.int32).contiguous()
 
     def step(self, actions):
         self.world.step(self._gather_actions(actions))

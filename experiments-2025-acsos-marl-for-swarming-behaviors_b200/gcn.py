@@ -39,23 +39,38 @@ class _Projection(nn.Module):
         _glorot(self.weight)
 
 
+def _compute_device(x: torch.Tensor) -> torch.device:
+    """The CUDA device a layer call runs on: the tensor's own, or -- for host tensors of a script that hard-codes
+    device='cpu' -- the B200 named by SWARM_DEVICE (``_lib.offload_device``; results return to the host)."""
+    if x.is_cuda:
+        return x.device
+    off = _lib.offload_device()
+    if off is None:
+        raise _lib.SwarmError("GATConv / GCN run on CUDA tensors only (swarm_b200 has no CPU fallback); move the model "
+                              "and the graph to a B200, or set SWARM_DEVICE=cuda to serve host tensors from one")
+    return off
+
+
 class _GatConvFunction(torch.autograd.Function):
     """Stand-alone GATConv layer through swarm_gatconv_forward_csr / swarm_gatconv_backward_csr (weights only)."""
 
     @staticmethod
     def forward(ctx, packed, x, edge_index):
-        packed = packed.detach().contiguous()
+        dev = _compute_device(x)
+        ctx.homes = (packed.device, x.device)
+        packed = packed.detach().to(dev).contiguous()
+        x, edge_index = x.detach().to(dev).contiguous(), edge_index.to(dev).contiguous()
         row_ptr, src, perm = ops.csr_from_edges(edge_index, x.shape[0])
         out = ops.gatconv_forward_csr(packed, x, row_ptr, src)
         ctx.save_for_backward(packed, x, edge_index, row_ptr, src, perm)
-        return out
+        return out.to(ctx.homes[1])
 
     @staticmethod
     def backward(ctx, grad_out):
         packed, x, edge_index, row_ptr, src, perm = ctx.saved_tensors
-        grad_w = ops.gatq_backward_csr(packed, x, edge_index, grad_out.contiguous(), by_target=(row_ptr, src, perm),
-                                       conv_only=True)
-        return grad_w, None, None
+        grad_w = ops.gatq_backward_csr(packed, x, edge_index, grad_out.to(x.device).contiguous(),
+                                       by_target=(row_ptr, src, perm), conv_only=True)
+        return grad_w.to(ctx.homes[0]), None, None
 
 
 class _GatLayerFunction(torch.autograd.Function):
@@ -64,19 +79,25 @@ class _GatLayerFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, lin_weight, att_src, att_dst, bias, edge_index):
-        x, lin_weight = x.detach().contiguous(), lin_weight.detach().contiguous()
-        att_src, att_dst, bias = (t.detach().reshape(-1).contiguous() for t in (att_src, att_dst, bias))
+        dev = _compute_device(x)
+        ctx.homes = (x.device, lin_weight.device)
+        x, lin_weight = x.detach().to(dev).contiguous(), lin_weight.detach().to(dev).contiguous()
+        att_src, att_dst, bias = (t.detach().to(dev).reshape(-1).contiguous() for t in (att_src, att_dst, bias))
+        edge_index = edge_index.to(dev).contiguous()
         row_ptr, src, perm = ops.csr_from_edges(edge_index, x.shape[0])
         out = ops.gat_layer_forward(lin_weight, att_src, att_dst, bias, x, row_ptr, src)
         ctx.save_for_backward(x, lin_weight, att_src, att_dst, edge_index, row_ptr, src, perm)
-        return out
+        return out.to(ctx.homes[0])
 
     @staticmethod
     def backward(ctx, grad_out):
         x, lin_weight, att_src, att_dst, edge_index, row_ptr, src, perm = ctx.saved_tensors
-        gw, gas, gad, gb, gx = ops.gat_layer_backward(lin_weight, att_src, att_dst, x, edge_index, grad_out.contiguous(),
+        gw, gas, gad, gb, gx = ops.gat_layer_backward(lin_weight, att_src, att_dst, x, edge_index,
+                                                      grad_out.to(x.device).contiguous(),
                                                       want_grad_x=ctx.needs_input_grad[0], by_target=(row_ptr, src, perm))
-        return gx, gw, gas.view(1, 1, -1), gad.view(1, 1, -1), gb, None
+        hx, hw = ctx.homes
+        return (gx.to(hx) if gx is not None else None), gw.to(hw), gas.view(1, 1, -1).to(hw), gad.view(1, 1, -1).to(hw), \
+            gb.to(hw), None
 
 
 class GATConv(nn.Module):
@@ -107,8 +128,7 @@ class GATConv(nn.Module):
         self.bias.data.zero_()
 
     def forward(self, x: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
-        if not x.is_cuda:
-            raise _lib.SwarmError("GATConv.forward runs on CUDA tensors only (swarm_b200 has no CPU fallback)")
+        _compute_device(x)                      # raises for host tensors unless SWARM_DEVICE names the serving B200
         edge_index = edge_index.to(torch.int64).contiguous()
         if (self.in_channels, self.out_channels) != (_FEAT, _HIDDEN) or x.requires_grad:
             if self.in_channels > 64 or self.out_channels > 64:
@@ -126,17 +146,21 @@ class _GatQFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, packed, x, edge_index):
-        packed = packed.detach().contiguous()
+        dev = _compute_device(x)
+        ctx.homes = (packed.device, x.device)
+        packed = packed.detach().to(dev).contiguous()
+        x, edge_index = x.detach().to(dev).contiguous(), edge_index.to(dev).contiguous()
         row_ptr, src, perm = ops.csr_from_edges(edge_index, x.shape[0])
         q = ops.gatq_forward_csr(packed, x, row_ptr, src)
         ctx.save_for_backward(packed, x, edge_index, row_ptr, src, perm)
-        return q
+        return q.to(ctx.homes[1])
 
     @staticmethod
     def backward(ctx, grad_q):
         packed, x, edge_index, row_ptr, src, perm = ctx.saved_tensors
-        grad_w = ops.gatq_backward_csr(packed, x, edge_index, grad_q.contiguous(), by_target=(row_ptr, src, perm))
-        return grad_w, None, None
+        grad_w = ops.gatq_backward_csr(packed, x, edge_index, grad_q.to(x.device).contiguous(),
+                                       by_target=(row_ptr, src, perm))
+        return grad_w.to(ctx.homes[0]), None, None
 
 
 class GCN(nn.Module):
@@ -162,9 +186,7 @@ class GCN(nn.Module):
 
     def forward(self, data) -> torch.Tensor:
         x, edge_index = data.x, data.edge_index
-        if not x.is_cuda:
-            raise _lib.SwarmError("GCN.forward runs on CUDA tensors only (swarm_b200 has no CPU fallback); "
-                                  "move the model and the graph to a B200")
+        _compute_device(x)                      # raises for host tensors unless SWARM_DEVICE names the serving B200
         if edge_index.dtype != torch.int64:
             edge_index = edge_index.to(torch.int64)
         return _GatQFunction.apply(self.packed_weights(), x.contiguous(), edge_index.contiguous())

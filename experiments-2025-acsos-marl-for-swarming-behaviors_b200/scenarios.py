@@ -102,6 +102,9 @@ class Entity:
             raise AssertionError(f"{self.name} has not been added to a World")
         return self._world
 
+    def _mirror(self) -> None:
+        """Host-seam worlds (see World): what was just written into the host copy of this entity also goes to HBM."""
+
     def set_vel(self, vel: torch.Tensor, batch_index: Optional[int] = None) -> None:
         st = self.state
         if st.vel is None:
@@ -111,6 +114,7 @@ class Entity:
             st.vel[...] = v
         else:
             st.vel[batch_index] = v
+        self._mirror()
 
     def set_pos(self, pos: torch.Tensor, batch_index: Optional[int] = None) -> None:
         st = self.state
@@ -129,6 +133,7 @@ class Entity:
                 self._host_pos = vec
             elif self._host_pos is not None and vec != self._host_pos:
                 self._host_pos = None
+        self._mirror()
 
 
 class Landmark(Entity):
@@ -173,8 +178,14 @@ class Agent(Entity):
 
     @property
     def state(self) -> _EntityState:
-        s = self._require_world().state
+        w = self._require_world()
+        s = w.host_state if w.host_state is not None else w.state
         return _EntityState(s[:, self._index, 0:2], s[:, self._index, 2:4])
+
+    def _mirror(self) -> None:
+        w = self._world
+        if w is not None and w.host_state is not None:
+            w.state[:, self._index].copy_(w.host_state[:, self._index])
 
 
 class World:
@@ -186,14 +197,23 @@ class World:
                  joint_force: float = 130.0, torque_constraint_force: float = 1.0, contact_margin: float = 1e-3,
                  gravity=(0.0, 0.0)):
         device = torch.device(device)
+        compute = device
         if device.type != "cuda":
-            raise _lib.SwarmError(f"swarm_b200 worlds live on a CUDA device (got {device}); there is no CPU fallback")
+            # host-seam mode: the script asked for host tensors (the reference hard-codes device='cpu'); the world still
+            # lives in HBM and is stepped by the CUDA kernel, entity states are read through a host copy refreshed
+            # after every kernel (_lib.offload_device)
+            compute = _lib.offload_device()
+            if compute is None:
+                raise _lib.SwarmError(f"swarm_b200 worlds live on a CUDA device (got {device}); there is no CPU fallback "
+                                      "(set SWARM_DEVICE=cuda to serve a script that hard-codes device='cpu' from a B200)")
         if substeps != 1 or linear_friction or angular_friction or x_semidim is not None or y_semidim is not None or \
                 tuple(float(g) for g in gravity) != (0.0, 0.0):
             raise NotImplementedError("substeps != 1, friction, world bounds and gravity are outside the swarm_b200 "
                                       "world step (the reference scenarios use the vmas defaults)")
         self.batch_dim = batch_dim
-        self.device = device
+        self.device = device                   # where the script's tensors live (vmas World.device)
+        self.compute_device = compute          # where the state lives and the kernels run
+        self.host_state: Optional[torch.Tensor] = None
         self._dt, self._drag, self._collision_force, self._contact_margin = dt, drag, collision_force, contact_margin
         self._agents: List[Agent] = []
         self._landmarks: List[Landmark] = []
@@ -263,7 +283,9 @@ class World:
         if self._obstacle is not None:
             cfg.landmark_radius = self._obstacle.shape.radius
         self.cfg = cfg
-        self.state = torch.zeros(self.batch_dim, n, 4, dtype=torch.float32, device=self.device)
+        self.state = torch.zeros(self.batch_dim, n, 4, dtype=torch.float32, device=self.compute_device)
+        if self.compute_device != self.device:
+            self.host_state = torch.zeros(self.batch_dim, n, 4, dtype=torch.float32).pin_memory()
         self._refresh_outputs()
 
     def _sync_constants(self) -> None:
@@ -280,13 +302,19 @@ class World:
     def _refresh_outputs(self) -> None:
         """Observation / distance terms of the current state without stepping (used after reset)."""
         B, N = self.cfg.num_envs, self.cfg.n_agents
-        goal = torch.tensor([self.cfg.goal_x, self.cfg.goal_y], dtype=torch.float32, device=self.device)
+        dev = self.compute_device
+        goal = torch.tensor([self.cfg.goal_x, self.cfg.goal_y], dtype=torch.float32, device=dev)
         self.last = {
             "obs": torch.cat([self.state, goal.view(1, 1, 2).expand(B, N, 2)], dim=2),
-            "rewards": torch.zeros(B, N, dtype=torch.float32, device=self.device),
-            "flags": torch.zeros(B, N, dtype=torch.uint8, device=self.device),
-            "dist": torch.zeros(B, N, 2, dtype=torch.float32, device=self.device),
+            "rewards": torch.zeros(B, N, dtype=torch.float32, device=dev),
+            "flags": torch.zeros(B, N, dtype=torch.uint8, device=dev),
+            "dist": torch.zeros(B, N, 2, dtype=torch.float32, device=dev),
         }
+
+    def _download(self) -> None:
+        """Host-seam mode: refresh the host copy of the state after a kernel wrote it."""
+        if self.host_state is not None:
+            self.host_state.copy_(self.state)
 
     def reset(self, env_index: Optional[int] = None) -> None:
         """vmas World.reset: every entity's state back to zero (the scenario's reset_world_at places them next)."""
@@ -295,10 +323,11 @@ class World:
             self.state.zero_()
         else:
             self.state[env_index].zero_()
+        self._download()
 
     def reset_to_grid(self, centers: torch.Tensor, env_index: Optional[int] = None) -> None:
         """generate_grid + set_pos for every agent; velocities zero (vmas world.reset)."""
-        centers = centers.to(device=self.device, dtype=torch.float32).reshape(-1, 2)
+        centers = centers.to(device=self.compute_device, dtype=torch.float32).reshape(-1, 2)
         self.version += 1
         self._sync_constants()
         if env_index is None:
@@ -308,6 +337,7 @@ class World:
         else:
             one = ops.clone_config(self.cfg, num_envs=1)
             ops.reset_grid(one, centers[:1].contiguous(), out=self.state[env_index])
+        self._download()
         self._refresh_outputs()
 
     def step(self, actions: torch.Tensor) -> None:
@@ -315,6 +345,7 @@ class World:
         self._sync_constants()
         self.version += 1
         self.last = ops.sim_step(self.cfg, self.state, actions, state_out=self.state, want_obs=True)
+        self._download()
 
     def adopt_rollout(self, out: Dict[str, torch.Tensor]) -> None:
         """A fused rollout (``ops.rollout``) advanced ``self.state`` in place: make the world look as it does after the
@@ -324,7 +355,8 @@ class World:
         ``out`` must carry the ``rewards``, ``flags`` and ``dist`` traces."""
         B, N = self.cfg.num_envs, self.cfg.n_agents
         self.version += 1
-        goal = torch.tensor([self.cfg.goal_x, self.cfg.goal_y], dtype=torch.float32, device=self.device)
+        goal = torch.tensor([self.cfg.goal_x, self.cfg.goal_y], dtype=torch.float32, device=self.compute_device)
+        self._download()
         self.last = {
             "state": self.state,
             "obs": torch.cat([self.state, goal.view(1, 1, 2).expand(B, N, 2)], dim=2),
@@ -552,7 +584,7 @@ class FlockingScenario(BaseScenario):
         self.pos_rew = torch.zeros(batch_dim, device=world.device)
         self.final_rew = self.pos_rew.clone()
         # (previous_distance_to_goal, previous_distance_to_agents) of every agent: f32[B, N, 2] in HBM
-        self.shaping = torch.zeros(batch_dim, self.n_agents, 2, dtype=torch.float32, device=world.device)
+        self.shaping = torch.zeros(batch_dim, self.n_agents, 2, dtype=torch.float32, device=world.compute_device)
         return world
 
     def _spec(self) -> "_lib.SwarmRewardSpec":
