@@ -21,9 +21,9 @@ constexpr int kRewardThreads = 128;
 // computed, and the shared-memory arrays are double-buffered, so an iteration costs one barrier (Cohesion) or two
 // (Flocking) and no load latency sits on the critical path (the first version -- load, barrier, compute, load shaping,
 // barrier, sum, barrier -- spent two thirds of its time waiting on those two loads, profiles/r1_ncu_scenario_reward.txt).
-// The partner sweeps are branch-free: the own slot is neutralised with selects (adding +0 to a non-negative sum and
-// skipping the penalty count leave the results unchanged), which keeps the warp converged and the exact square root off
-// its zero-input slow path.
+// The partner sweeps are branch-free.  Flocking's walks the OTHER agents (compressed index k -> partner k + (k >= i)) in
+// the order torch's CPU row sum adds them (swarm_device.cuh torch_row_sum: eight lanes, so eight independent exact
+// square roots are in flight); Cohesion's neutralises the own slot with selects.
 template <int KIND>
 __global__ void __launch_bounds__(kRewardThreads, KIND == SWARM_REWARD_FLOCKING ? 12 : 16) scenario_reward_kernel(SwarmRewardSpec sp,
                                                                              const float4* __restrict__ state,
@@ -77,23 +77,11 @@ __global__ void __launch_bounds__(kRewardThreads, KIND == SWARM_REWARD_FLOCKING 
         // spacing term ((|p_i - p_j| - desired)^2 over j != i).mean() * dist_shaping (flocking:109-121,148-160); at a
         // reset the agents after i have not been placed yet and still sit at the origin world.reset put them at
         const int placed = sp.reset ? i : N;              // partners j > placed are still at the origin
-        float sum = 0.0f;
-        int close = 0;
-#pragma unroll 4
-        for (int j = 0; j < N; ++j) {
-          float2 q = others[j];
-          if (j > placed) q = make_float2(0.0f, 0.0f);
-          const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y);
-          float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
-          const bool self = j == i;
-          d2 = self ? 1.0f : d2;
-          const float d = __fsqrt_rn(d2);
-          const float e = __fsub_rn(d, sp.desired_distance);
-          sum = __fadd_rn(sum, self ? 0.0f : __fmul_rn(e, e));
-          // world.get_distance: centre distance minus both radii (flocking:166)
-          const float gap = __fsub_rn(__fsub_rn(d, sp.agent_radius), sp.agent_radius);
-          close += (!self && gap <= sp.min_collision_distance) ? 1 : 0;
-        }
+        float sum;
+        int close;
+        flocking_partner_sweep(p.x, p.y, i, N,
+                               [&](int j) { return j > placed ? make_float2(0.0f, 0.0f) : others[j]; },
+                               sp.desired_distance, sp.agent_radius, sp.min_collision_distance, sum, close);
         const float spacing = __fmul_rn(__fdiv_rn(sum, (float)(N - 1)), sp.dist_shaping);
         shaping[g] = make_float2(shaped_goal, spacing);                         // flocking:101-121,138,159
         if (!sp.reset) {

@@ -21,6 +21,88 @@ __device__ __forceinline__ float norm2(float x, float y) {
   return __fsqrt_rn(__fmaf_rn(y, y, __fmul_rn(x, x)));
 }
 
+// ---- torch CPU sum over a contiguous float row --------------------------------------------------------------------
+// `x.mean(-1)` / `x.sum(-1)` over a contiguous row of m floats is NOT a left-to-right sum on the CPU: ATen's
+// SumKernel.cpp (vectorized_inner_sum -> row_sum -> multi_row_sum) adds the row as 8-lane vectors, four vector
+// accumulators interleaved over groups of four chunks, the chunks left over into accumulator 0, the accumulators into
+// accumulator 0, and finally  0 + tail elements (k >= 8 * (m / 8)) + lane 0 + ... + lane 7; rows shorter than a vector
+// use four interleaved scalar accumulators instead.  Only for m <= 4 and m = 8 is that a left-to-right sum; otherwise
+// it differs in the last bit (observed on flocking_scenario.py:109-121 with 12 agents: 2 of 12
+// shaping terms).  elem(k) yields element k; it is called exactly once per k.  (m < 16 * 32: no cascade levels.)
+template <typename F>
+__device__ __forceinline__ float torch_row_sum(int m, F elem) {
+  if (m < 8) {
+    // rows shorter than one vector take ATen's scalar path (scalar_inner_sum -> row_sum with four interleaved scalar
+    // accumulators): p[k] = e[k] (k < 4), the rest into p[0], then p[0] + p[1] + p[2] + p[3]
+    float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+    int k = 0;
+    if (m >= 4) {
+      p0 = elem(0); p1 = elem(1); p2 = elem(2); p3 = elem(3);
+      k = 4;
+    }
+    for (; k < m; ++k) p0 = __fadd_rn(p0, elem(k));
+    return __fadd_rn(__fadd_rn(__fadd_rn(p0, p1), p2), p3);
+  }
+  const int chunks = m >> 3, groups = chunks >> 2;
+  float a0[8];
+#pragma unroll
+  for (int l = 0; l < 8; ++l) a0[l] = 0.0f;
+  int c = 0;
+  if (groups > 0) {
+    float a1[8], a2[8], a3[8];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) a1[l] = a2[l] = a3[l] = 0.0f;
+    for (int gI = 0; gI < groups; ++gI, c += 4) {
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        a0[l] = __fadd_rn(a0[l], elem((c + 0) * 8 + l));
+        a1[l] = __fadd_rn(a1[l], elem((c + 1) * 8 + l));
+        a2[l] = __fadd_rn(a2[l], elem((c + 2) * 8 + l));
+        a3[l] = __fadd_rn(a3[l], elem((c + 3) * 8 + l));
+      }
+    }
+    for (; c < chunks; ++c) {
+#pragma unroll
+      for (int l = 0; l < 8; ++l) a0[l] = __fadd_rn(a0[l], elem(c * 8 + l));
+    }
+#pragma unroll
+    for (int l = 0; l < 8; ++l) a0[l] = __fadd_rn(__fadd_rn(__fadd_rn(a0[l], a1[l]), a2[l]), a3[l]);
+  } else {
+    for (; c < chunks; ++c) {
+#pragma unroll
+      for (int l = 0; l < 8; ++l) a0[l] = __fadd_rn(a0[l], elem(c * 8 + l));
+    }
+  }
+  float fin = 0.0f;
+  for (int k = chunks * 8; k < m; ++k) fin = __fadd_rn(fin, elem(k));
+#pragma unroll
+  for (int l = 0; l < 8; ++l) fin = __fadd_rn(fin, a0[l]);
+  return fin;
+}
+
+// Flocking's partner sweep of agent i at (px, py) (flocking_scenario.py:109-121,148-168): element k of the stacked
+// distance list is partner j = k + (k >= i) -- the list comprehension skips the agent itself --
+//   sum   = torch sum of (|p_i - p_j| - desired)^2 in torch's CPU row order (see torch_row_sum)
+//   close = number of partners with world.get_distance <= min_collision_distance (centre distance minus both radii)
+// pos(j) yields partner j's position.
+template <typename P>
+__device__ __forceinline__ void flocking_partner_sweep(float px, float py, int i, int N, P pos, float desired,
+                                                       float radius, float min_collision_distance, float& sum,
+                                                       int& close) {
+  int cnt = 0;
+  sum = torch_row_sum(N - 1, [&](int k) -> float {
+    const int j = k + (k >= i ? 1 : 0);
+    const float2 q = pos(j);
+    const float dx = __fsub_rn(px, q.x), dy = __fsub_rn(py, q.y);
+    const float d = __fsqrt_rn(__fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    const float e = __fsub_rn(d, desired);
+    const float gap = __fsub_rn(__fsub_rn(d, radius), radius);
+    cnt += (gap <= min_collision_distance) ? 1 : 0;
+    return __fmul_rn(e, e);
+  });
+  close = cnt;
+}
+
 // ---- vmas Environment._set_action for discrete_action_nvec = [3, 3] -----------------------------
 // flat a -> (a / 3, a % 3); index 0 -> 0, 1 -> -1, 2 -> +1
 __device__ __forceinline__ float action_component(int idx) {

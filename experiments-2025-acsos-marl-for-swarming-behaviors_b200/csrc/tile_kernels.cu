@@ -258,21 +258,10 @@ tile_kernel(const __grid_constant__ TileParams p) {
           const float d_goal = norm2(__fsub_rn(s.x, fs.goal_x), __fsub_rn(s.y, fs.goal_y));
           const float shaped_goal = __fmul_rn(d_goal, fs.pos_shaping);
           const float4* others = post + t.envbase;
-          float sum = 0.0f;
-          int close = 0;
-#pragma unroll 2
-          for (int j = 0; j < N; ++j) {
-            const float4 q = others[j];
-            const float dx = __fsub_rn(s.x, q.x), dy = __fsub_rn(s.y, q.y);
-            float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
-            const bool self = j == t.i;
-            d2 = self ? 1.0f : d2;
-            const float d = __fsqrt_rn(d2);
-            const float e = __fsub_rn(d, fs.desired_distance);
-            sum = __fadd_rn(sum, self ? 0.0f : __fmul_rn(e, e));
-            const float gap = __fsub_rn(__fsub_rn(d, fs.agent_radius), fs.agent_radius);
-            close += (!self && gap <= fs.min_collision_distance) ? 1 : 0;
-          }
+          float sum;
+          int close;
+          flocking_partner_sweep(s.x, s.y, t.i, N, [&](int j) { return xy_of(others[j]); }, fs.desired_distance,
+                                 fs.agent_radius, fs.min_collision_distance, sum, close);
           const float spacing = __fmul_rn(__fdiv_rn(sum, (float)(N - 1)), fs.dist_shaping);
           const float pos_rew = __fsub_rn(shp.x, shaped_goal);
           float r = pos_rew;

@@ -84,9 +84,9 @@ def main():
     out = {}
     with refsrc.reference_modules("refstub") as ref:
         import vmas
-        for kind, sizes in (("flocking", (2, 5, 9, 12)), ("cohesion", (2, 5, 9))):
+        for kind, sizes in (("flocking", (2, 5, 7, 8, 9, 12, 40)), ("cohesion", (2, 5, 9))):
             for n in sizes:
-                run = scenario_run(ref, vmas, kind, n, T=60, seed=100 + n)
+                run = scenario_run(ref, vmas, kind, n, T=60 if n <= 12 else 30, seed=100 + n)
                 for k, v in run.items():
                     out[f"{kind}/n{n}/{k}"] = v
                 r = run["rewards"]

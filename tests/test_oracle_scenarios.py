@@ -100,7 +100,7 @@ def test_cohesion_more_than_nine_agents_raises():
 
 
 # ---- the pin: the reference's own reward() source (tests/golden/reference_runs.npz) ---------------------------------
-@pytest.mark.parametrize("n", [2, 5, 9, 12])
+@pytest.mark.parametrize("n", [2, 5, 7, 8, 9, 12, 40])
 def test_flocking_oracle_equals_the_reference_source(n):
     """FlockingScenario (flocking_scenario.py, executed unmodified on oracle/refstub by
     tests/golden/make_reference_runs.py) vs the restatement: shaping memory after reset, 60 ticks of positions and
