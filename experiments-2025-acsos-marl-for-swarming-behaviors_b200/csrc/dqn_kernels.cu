@@ -291,7 +291,11 @@ __global__ void __launch_bounds__(kTileThreads) dqn_grad_kernel(const __grid_con
     __syncthreads();                              // weights staged / previous pass done with sst and the h tile
     sst[tid] = sp;
     __syncthreads();
-    if (knn) {
+    if (knn && N <= kKnnSmallMax) {
+      uint64_t cache_rank = ~0ull, cache_nbr = 0;
+      const uint64_t nbr_word = tile_knn_small(t, sst, sp, N, K, cache_rank, cache_nbr);
+      deg = tile_in_edges_knn_small(g, t, N, K, nbr_word, reinterpret_cast<uint32_t*>(g.skv));
+    } else if (knn) {
       tile_knn_rows(g, t, sst, sp, N, K);
       deg = tile_in_edges_knn(g, t, N, K, reinterpret_cast<uint32_t*>(g.skv));   // distance rows are dead now
     } else if (radius && t.active) {

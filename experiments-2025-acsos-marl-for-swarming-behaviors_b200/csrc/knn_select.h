@@ -30,17 +30,18 @@ SWARM_HD bool knn_less(const KnnPair& a, const KnnPair& b) {
   return ((a.v == a.v) && (b.v != b.v)) || (a.v < b.v);
 }
 
-// Arr must provide:  KnnPair get(int) const;  void set(int, const KnnPair&);
+// Arr must provide:  Pair get(int) const;  void set(int, const Pair&);  with knn_less(Pair, Pair) defined -- KnnPair
+// (float value, index) for rows in memory, KnnRankPair (knn_small.h) for the register-resident rows of small swarms.
 template <class Arr>
 SWARM_HD void knn_swap(Arr& a, int p, int q) {
-  KnnPair t = a.get(p);
+  auto t = a.get(p);
   a.set(p, a.get(q));
   a.set(q, t);
 }
 
 template <class Arr>
 SWARM_HD void knn_move_median_to_first(Arr& a, int result, int ia, int ib, int ic) {
-  KnnPair A = a.get(ia), B = a.get(ib), C = a.get(ic);
+  auto A = a.get(ia), B = a.get(ib), C = a.get(ic);
   if (knn_less(A, B)) {
     if (knn_less(B, C)) knn_swap(a, result, ib);
     else if (knn_less(A, C)) knn_swap(a, result, ic);
@@ -71,7 +72,7 @@ SWARM_HD int knn_partition_pivot(Arr& a, int first, int last) {
 
 template <class Arr>
 SWARM_HD void knn_unguarded_linear_insert(Arr& a, int last) {
-  KnnPair val = a.get(last);
+  auto val = a.get(last);
   int next = last - 1;
   while (knn_less(val, a.get(next))) {
     a.set(last, a.get(next));
@@ -86,7 +87,7 @@ SWARM_HD void knn_insertion_sort(Arr& a, int first, int last) {
   if (first == last) return;
   for (int i = first + 1; i != last; ++i) {
     if (knn_less(a.get(i), a.get(first))) {
-      KnnPair val = a.get(i);
+      auto val = a.get(i);
       for (int j = i; j > first; --j) a.set(j, a.get(j - 1));
       a.set(first, val);
     } else {
@@ -96,8 +97,8 @@ SWARM_HD void knn_insertion_sort(Arr& a, int first, int last) {
 }
 
 // ---- heap helpers (bits/stl_heap.h); indices are relative to `first` ----
-template <class Arr>
-SWARM_HD void knn_push_heap(Arr& a, int first, int hole, int top, const KnnPair& value) {
+template <class Arr, class Pair>
+SWARM_HD void knn_push_heap(Arr& a, int first, int hole, int top, const Pair& value) {
   int parent = (hole - 1) / 2;
   while (hole > top && knn_less(a.get(first + parent), value)) {
     a.set(first + hole, a.get(first + parent));
@@ -107,8 +108,8 @@ SWARM_HD void knn_push_heap(Arr& a, int first, int hole, int top, const KnnPair&
   a.set(first + hole, value);
 }
 
-template <class Arr>
-SWARM_HD void knn_adjust_heap(Arr& a, int first, int hole, int len, const KnnPair& value) {
+template <class Arr, class Pair>
+SWARM_HD void knn_adjust_heap(Arr& a, int first, int hole, int len, const Pair& value) {
   const int top = hole;
   int child = hole;
   while (child < (len - 1) / 2) {
@@ -127,7 +128,7 @@ SWARM_HD void knn_adjust_heap(Arr& a, int first, int hole, int len, const KnnPai
 
 template <class Arr>
 SWARM_HD void knn_pop_heap(Arr& a, int first, int last, int result) {
-  KnnPair value = a.get(result);
+  auto value = a.get(result);
   a.set(result, a.get(first));
   knn_adjust_heap(a, first, 0, last - first, value);
 }
@@ -138,7 +139,7 @@ SWARM_HD void knn_make_heap(Arr& a, int first, int last) {
   const int len = last - first;
   int parent = (len - 2) / 2;
   while (true) {
-    KnnPair value = a.get(first + parent);
+    auto value = a.get(first + parent);
     knn_adjust_heap(a, first, parent, len, value);
     if (parent == 0) return;
     parent--;

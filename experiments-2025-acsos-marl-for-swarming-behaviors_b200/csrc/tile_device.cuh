@@ -6,6 +6,7 @@
 
 #include "gatq_device.cuh"
 #include "knn_select.h"
+#include "knn_small.h"
 
 namespace swarm {
 
@@ -235,16 +236,95 @@ __device__ __forceinline__ int tile_in_edges_knn(const TileGraphSmem& g, const T
   return deg;
 }
 
+// ---- small swarms (N <= 16): the kNN row lives in registers (knn_small.h) ------------------------------------------
+constexpr int kKnnSmallMax = 16;
+
+__device__ __forceinline__ int knn_nib(uint64_t w, int r) { return (int)((w >> (4 * r)) & 15u); }
+
+// Row of this agent -> nibble word of its K neighbours in torch.topk's output order.  No shared-memory writes, no
+// barrier.  (cache_rank, cache_nbr): the order pattern and answer of this thread's previous tie row -- on the start
+// lattices the same pattern comes back tick after tick while the swarm moves in formation.
+template <int NP>
+__device__ __forceinline__ uint64_t tile_knn_small_np(const TileThread& t, const float4* pos, const float4& s, int N, int K,
+                                                     uint64_t& cache_rank, uint64_t& cache_nbr) {
+  uint32_t u[NP];
+  const float4* env = pos + t.envbase;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    uint32_t key = kKnnPadKey;
+    if (j < N) {
+      const float2 o = xy_of(env[j]);
+      key = knn_key_nonneg(norm2(__fsub_rn(o.x, s.x), __fsub_rn(o.y, s.y)));
+    }
+    u[j] = key;
+  }
+  int r[NP];
+  uint32_t present;
+  const uint64_t rank = knn_small_ranks<NP>(u, r, present);
+  if (knn_small_tie_free(present, N, K)) return knn_small_by_rank<NP>(r, K);
+  if (rank != cache_rank) {
+    cache_nbr = knn_small_topk(rank, N, K);
+    cache_rank = rank;
+  }
+  return cache_nbr;
+}
+
+__device__ __forceinline__ uint64_t tile_knn_small(const TileThread& t, const float4* pos, const float4& s, int N, int K,
+                                                  uint64_t& cache_rank, uint64_t& cache_nbr) {
+  if (!t.active) return 0;
+  if (N <= 8) return tile_knn_small_np<8>(t, pos, s, N, K, cache_rank, cache_nbr);
+  if (N <= 12) return tile_knn_small_np<12>(t, pos, s, N, K, cache_rank, cache_nbr);
+  return tile_knn_small_np<16>(t, pos, s, N, K, cache_rank, cache_nbr);
+}
+
+// in-edges of node i from the neighbour words (same list, same order as tile_in_edges_knn): every thread publishes the
+// 16-bit set of its row, one barrier, then N bit tests.  `smask` = uint32[T]; it is rewritten only after the barriers
+// of the Q forward that follows, so no trailing barrier is needed.  Every thread of the CTA must call it.
+__device__ __forceinline__ int tile_in_edges_knn_small(const TileGraphSmem& g, const TileThread& t, int N, int K, uint64_t nbr,
+                                                       uint32_t* __restrict__ smask) {
+  const int T = kTileThreads;
+  uint32_t mine = 0;
+  if (t.active)
+    for (int r = 0; r < K; ++r) mine |= 1u << knn_nib(nbr, r);
+  smask[t.tid] = mine;
+  __syncthreads();
+  int deg = 0;
+  if (t.active) {
+    const uint32_t* __restrict__ col = smask + t.envbase;
+    uint8_t* __restrict__ sin = g.sin + t.tid;
+    const int own = K + (int)((mine >> t.i) & 1u);      // (i -> i) precedes (a -> i) when a == i
+    int cnt = 0, lo = 0;
+#pragma unroll 4
+    for (int ii = 0; ii < N; ++ii) {
+      const bool has = (ii != t.i) && ((col[ii] >> t.i) & 1u);
+      lo = (ii == t.i) ? cnt : lo;
+      if (has) sin[(cnt + (ii > t.i ? own : 0)) * T] = (uint8_t)ii;
+      cnt += has ? 1 : 0;
+    }
+    int pos = lo;
+    for (int r = 0; r < K; ++r) {
+      const int a = knn_nib(nbr, r);
+      if (a == t.i) sin[(pos++) * T] = (uint8_t)t.i;
+      sin[(pos++) * T] = (uint8_t)a;
+    }
+    deg = cnt + own;
+    if (t.i == 0) sin[(deg++) * T] = 0;
+  }
+  return deg;
+}
+
 // edge list export (env-local ids) in the reference's order
+// (small swarms: `nbr_word` holds the neighbours, `use_word` = true)
 __device__ __forceinline__ void tile_write_edges(const TileGraphSmem& g, const TileThread& t, int N, int K, bool knn,
-                                                 int E, int32_t* eout, long long env_index) {
+                                                 int E, int32_t* eout, long long env_index, bool use_word = false,
+                                                 uint64_t nbr_word = 0) {
   const int T = kTileThreads;
   int32_t* r0 = eout + env_index * 2 * E;
   int32_t* r1 = r0 + E;
   const int i = t.i;
   if (knn) {
     for (int r = 0; r < K; ++r) {
-      const int a = g.snbr[r * T + t.tid];
+      const int a = use_word ? knn_nib(nbr_word, r) : (int)g.snbr[r * T + t.tid];
       const int e = (i * K + r) * 2;
       r0[e] = i; r1[e] = a;
       r0[e + 1] = a; r1[e + 1] = i;

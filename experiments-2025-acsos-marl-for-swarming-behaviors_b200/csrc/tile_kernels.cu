@@ -106,6 +106,8 @@ tile_kernel(const __grid_constant__ TileParams p) {
 
   int deg = 0;
   if (kQ && !knn && !radius && t.active) deg = tile_in_edges_complete(g, t, N);
+  const bool knn_small = knn && N <= kKnnSmallMax;          // register-resident rows (knn_small.h)
+  uint64_t nbr_word = 0, knn_cache_rank = ~0ull, knn_cache_nbr = 0;
 
   float ret = 0.0f;
   int myhits = 0;
@@ -127,7 +129,10 @@ tile_kernel(const __grid_constant__ TileParams p) {
     int action = 0;
 
     // ------------------------------------------------------------------ graph ----------------
-    if (knn) {
+    if (knn_small) {
+      nbr_word = tile_knn_small(t, pos, s, N, K, knn_cache_rank, knn_cache_nbr);
+      if (kQ) deg = tile_in_edges_knn_small(g, t, N, K, nbr_word, reinterpret_cast<uint32_t*>(g.skv));
+    } else if (knn) {
       tile_knn_rows(g, t, pos, s, N, K);
       if (kQ) deg = tile_in_edges_knn(g, t, N, K, reinterpret_cast<uint32_t*>(g.skv));   // distance rows are dead now
     }
@@ -142,7 +147,7 @@ tile_kernel(const __grid_constant__ TileParams p) {
         // stage the tile's edge lists in shared memory, then stream the contiguous [envs][2][E] block out with
         // coalesced 8-byte stores (E is odd, so the block is only 8-byte aligned)
         int32_t* stage = reinterpret_cast<int32_t*>(smem + L.stage);
-        if (t.active) tile_write_edges(g, t, N, K, knn, p.edges_per_env, stage, t.el);
+        if (t.active) tile_write_edges(g, t, N, K, knn, p.edges_per_env, stage, t.el, knn_small, nbr_word);
         __syncthreads();
         const long long env0 = (long long)blockIdx.x * p.epb;
         const long long envs_here = (c.num_envs - env0 < p.epb) ? (c.num_envs - env0) : p.epb;
@@ -152,10 +157,10 @@ tile_kernel(const __grid_constant__ TileParams p) {
         for (long long w = tid; w < pairs; w += T) reinterpret_cast<int2*>(dst)[w] = reinterpret_cast<const int2*>(stage)[w];
         if ((words & 1) && tid == 0) dst[words - 1] = stage[words - 1];
       } else if (eout && t.active) {
-        tile_write_edges(g, t, N, K, knn, p.edges_per_env, eout, t.env);
+        tile_write_edges(g, t, N, K, knn, p.edges_per_env, eout, t.env, knn_small, nbr_word);
       }
       if (MODE == MODE_GRAPH && knn && p.nbr_out && t.active)
-        for (int r = 0; r < K; ++r) p.nbr_out[t.gidx * K + r] = g.snbr[r * T + tid];
+        for (int r = 0; r < K; ++r) p.nbr_out[t.gidx * K + r] = knn_small ? knn_nib(nbr_word, r) : (int)g.snbr[r * T + tid];
     }
 
     // ------------------------------------------------------------------ GAT-Q forward --------

@@ -162,9 +162,11 @@ __host__ __device__ inline TileLayout tile_layout(int mode, int threads, int n, 
   L.wt = off;   off = tile_align16(off + (q ? maxdeg * threads * 4 : 0));
   L.inl = off;  off = tile_align16(off + (q ? maxdeg * threads : 0));
   L.deg = off;  off = tile_align16(off + (q ? threads : 0));
-  L.kv = off;   off = tile_align16(off + (knn ? n * threads * 4 : 0));
-  L.ki = off;   off = tile_align16(off + (knn ? n * threads : 0));
-  L.nbr = off;  off = tile_align16(off + (knn ? k * threads : 0));
+  // kNN rows: swarms of n <= 16 keep them in registers (knn_small.h) and only publish one membership word per thread
+  const bool knn_rows = knn && n > 16;
+  L.kv = off;   off = tile_align16(off + (knn ? (knn_rows ? n : 1) * threads * 4 : 0));
+  L.ki = off;   off = tile_align16(off + (knn_rows ? n * threads : 0));
+  L.nbr = off;  off = tile_align16(off + (knn_rows ? k * threads : 0));
   L.red = off;  off = tile_align16(off + threads * 4);
   // MODE_GRAPH: the tile's edge lists are staged here and written out with coalesced stores (0 = does not fit)
   {

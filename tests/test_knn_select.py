@@ -20,6 +20,9 @@ def shim(tmp_path_factory):
     subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", inc, src, "-o", str(out)], check=True)
     lib = ctypes.CDLL(str(out))
     lib.swarm_host_topk_smallest.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.swarm_host_topk_small.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_void_p]
+    lib.swarm_host_topk_small.restype = ctypes.c_int
     return lib
 
 
@@ -66,3 +69,44 @@ def test_nan_ordering_matches_torch(shim):
     for k in (1, 3, 6, 8):
         ref = torch.topk(rows, k, dim=-1, largest=False).indices
         assert torch.equal(_ours(shim, rows, k), ref)
+
+
+def _small(lib, values: torch.Tensor, k: int, mode: int):
+    rows, n = values.shape
+    v = values.contiguous()
+    out = torch.empty(rows, k, dtype=torch.int32)
+    emulated = lib.swarm_host_topk_small(v.data_ptr(), rows, n, k, mode, out.data_ptr())
+    return out.long(), emulated
+
+
+@pytest.mark.parametrize("n", list(range(1, 17)))
+def test_small_register_path_matches_torch_topk(shim, n):
+    """csrc/knn_small.h: ranks from pairwise comparisons, the tie-free shortcut, and the libstdc++ emulation on the
+    nibble-packed rank pattern (what the env-tile kernels run for n <= 16)."""
+    g = torch.Generator().manual_seed(77 + n)
+    rows = torch.cat([_grid_distance_rows(n, g, j) for j in (0.0, 0.0, 0.0, 0.0, 1e-7, 1e-3, 0.05)] +
+                     [torch.randint(0, 5, (300, n), generator=g).float() * 0.25, torch.rand(200, n, generator=g),
+                      torch.randint(0, 2, (100, n), generator=g).float()])
+    rows[-1, n // 2] = float("nan")
+    rows[-2, :] = float("nan")
+    rows[-3, 0] = float("inf")
+    took_shortcut = False
+    for k in range(1, n + 1):
+        ref = torch.topk(rows, k, dim=-1, largest=False).indices
+        got, emulated = _small(shim, rows, k, 0)
+        assert torch.equal(got, ref), f"n={n} k={k} (kernel path)"
+        took_shortcut |= emulated < rows.shape[0]
+        got, emulated = _small(shim, rows, k, 1)
+        assert emulated == rows.shape[0] and torch.equal(got, ref), f"n={n} k={k} (emulation on every row)"
+    assert took_shortcut
+
+
+@pytest.mark.parametrize("n,k", [(4, 2), (5, 3), (6, 3), (6, 5), (7, 4)])
+def test_small_register_path_exhaustive_patterns(shim, n, k):
+    """every order pattern with ties of n values drawn from n levels (n^n rows)"""
+    grids = torch.cartesian_prod(*[torch.arange(n, dtype=torch.float32)] * n)
+    ref = torch.topk(grids, k, dim=-1, largest=False).indices
+    got, _ = _small(shim, grids, k, 0)
+    assert torch.equal(got, ref)
+    got, _ = _small(shim, grids, k, 1)
+    assert torch.equal(got, ref)
