@@ -33,12 +33,18 @@ struct TileThread {
   bool active;
 };
 
-__device__ __forceinline__ TileThread tile_thread(int n_agents, int epb, long long num_envs) {
+__device__ __forceinline__ TileThread tile_thread(int n_agents, int epb, long long num_envs, int bal_q = 0, int bal_r = 0) {
   TileThread t;
   t.tid = threadIdx.x;
   t.el = t.tid / n_agents;
   t.i = t.tid - t.el * n_agents;
-  t.env = (long long)blockIdx.x * epb + t.el;
+  const int b = blockIdx.x;
+  if (bal_q > 0) {
+    t.env = (long long)b * bal_q + (b < bal_r ? b : bal_r) + t.el;
+    epb = bal_q + (b < bal_r ? 1 : 0);
+  } else {
+    t.env = (long long)b * epb + t.el;
+  }
   t.active = (t.el < epb) && (t.env < num_envs);
   t.envbase = t.el * n_agents;
   t.gidx = t.env * n_agents + t.i;

@@ -10,6 +10,8 @@
 //   MODE_STEP     one world step with given actions                       (vmas Environment.step)
 //   MODE_GRAPH    edge list / neighbour table export                      (train:94-110, simulator:9-26)
 // so the stand-alone kernels and the fused rollout are consistent by construction.
+#include <cstdlib>
+
 #include "tile_tc_device.cuh"
 
 namespace swarm {
@@ -57,7 +59,7 @@ tile_kernel(const __grid_constant__ TileParams p) {
   const int K = c.knn_k;
   const bool knn = (c.graph_mode == SWARM_GRAPH_KNN) && (kQ || MODE == MODE_GRAPH);
   const bool radius = (c.graph_mode == SWARM_GRAPH_RADIUS) && (kQ || MODE == MODE_GRAPH);
-  const TileThread t = tile_thread(N, p.epb, c.num_envs);
+  const TileThread t = tile_thread(N, p.epb, c.num_envs, p.bal_q, p.bal_r);
   const int tid = t.tid;
   const long long BN = (long long)c.num_envs * N;
 
@@ -105,7 +107,8 @@ tile_kernel(const __grid_constant__ TileParams p) {
   if (FLOCK && t.active) shp = p.shaping[t.gidx];
 
   int deg = 0;
-  if (kQ && !knn && !radius && t.active) deg = tile_in_edges_complete(g, t, N);
+  const bool complete = !knn && !radius;
+  if (kQ && !TC && complete && t.active) deg = tile_in_edges_complete(g, t, N);   // the TC path needs no edge list for it
   const bool knn_small = knn && N <= kKnnSmallMax;          // register-resident rows (knn_small.h)
   uint64_t nbr_word = 0, knn_cache_rank = ~0ull, knn_cache_nbr = 0;
 
@@ -124,6 +127,14 @@ tile_kernel(const __grid_constant__ TileParams p) {
   for (int tick = 0; tick < p.ticks; ++tick) {
     const float4* pos = sst + (tick & 1) * T;
     sst[(tick & 1) * T + tid] = s;
+    float adst_tc = 0.0f;
+    if (TC && kQ) {
+      // attention terms straight from the input features (tile_tc_device.cuh): published with the state
+      const float x[7] = {s.x, s.y, s.z, s.w, c.goal_x, c.goal_y, (float)t.i};
+      float asrc;
+      tc_alpha_terms(ts, x, asrc, adst_tc);
+      g.sas[tid] = asrc;
+    }
     __syncthreads();
 
     int action = 0;
@@ -166,11 +177,12 @@ tile_kernel(const __grid_constant__ TileParams p) {
     // ------------------------------------------------------------------ GAT-Q forward --------
     if (kQ) {
       // node features (train:95-99): [pos, vel, goal, agent id]
-      const float x[7] = {s.x, s.y, s.z, s.w, c.goal_x, c.goal_y, (float)t.i};
       float q[9];
       if (TC) {
-        action = tile_q_forward_tc(g, ts, t, tmem, x, deg, parity, q);
+        action = complete ? tile_q_forward_tc<true>(g, ts, t, tmem, pos, N, deg, adst_tc, c.goal_x, c.goal_y, parity, q)
+                          : tile_q_forward_tc<false>(g, ts, t, tmem, pos, N, deg, adst_tc, c.goal_x, c.goal_y, parity, q);
       } else {
+        const float x[7] = {s.x, s.y, s.z, s.w, c.goal_x, c.goal_y, (float)t.i};
         float a1[32];
         float adst;
         tile_gat_conv(g, t, sw, x, deg, a1, adst);
@@ -387,7 +399,7 @@ template <int MODE, bool TC, bool DENSE, bool FLOCK = false>
 static cudaError_t launch_tile_impl(const TileParams& p, cudaStream_t stream) {
   const SwarmConfig& c = p.cfg;
   const TileLayout L = tile_layout(MODE, kTileThreads, c.n_agents, c.knn_k, p.maxdeg, c.graph_mode, TC);
-  const int grid = (c.num_envs + p.epb - 1) / p.epb;
+  const int grid = p.bal_q > 0 ? (int)((c.num_envs - p.bal_r) / p.bal_q) : (c.num_envs + p.epb - 1) / p.epb;
   if (L.total > 48 * 1024) {
     cudaError_t err =
         cudaFuncSetAttribute(tile_kernel<MODE, TC, DENSE, FLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
@@ -397,19 +409,42 @@ static cudaError_t launch_tile_impl(const TileParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// Grid shape of the Q modes.  A batch that fits one wave of CTA slots is spread EVENLY over all of them (a tick of a
+// CTA costs about the same for 7 envs as for 10 -- it is latency bound -- so what counts is that every SM carries the
+// same number of resident CTAs: C2's 4 096 envs are 410 full CTAs on 444 slots, 34 SMs with one CTA less);
+// SWARM_TILE_DENSE = 0 / 1 forces the 3- / 4-CTAs-per-SM register budget, SWARM_TILE_GRID the number of CTAs.
+static bool tile_grid_plan(TileParams& p) {
+  static const char* dense_env = std::getenv("SWARM_TILE_DENSE");
+  static const char* grid_env = std::getenv("SWARM_TILE_GRID");
+  const long long B = p.cfg.num_envs;
+  const long long uniform = (B + p.epb - 1) / p.epb;
+  bool dense = uniform > 3 * 148;
+  if (dense_env) dense = dense_env[0] == '1';
+  const long long slots = (dense ? 4 : 3) * 148;
+  long long G = 0;
+  if (grid_env) G = std::atoll(grid_env);
+  else if (uniform <= slots) G = B < slots ? B : slots;
+  p.bal_q = p.bal_r = 0;
+  if (G >= uniform && G <= B && G > 0) {
+    p.bal_q = (int)(B / G);
+    p.bal_r = (int)(B - (long long)p.bal_q * G);
+  }
+  return dense;
+}
+
 template <int MODE>
-static cudaError_t launch_tile_q(const TileParams& p, cudaStream_t stream) {
-  if (!p.use_tc) return launch_tile_impl<MODE, false, true>(p, stream);
-  const int grid = (p.cfg.num_envs + p.epb - 1) / p.epb;
-  return grid > 3 * 148 ? launch_tile_impl<MODE, true, true>(p, stream) : launch_tile_impl<MODE, true, false>(p, stream);
+static cudaError_t launch_tile_q(const TileParams& p0, cudaStream_t stream) {
+  if (!p0.use_tc) return launch_tile_impl<MODE, false, true>(p0, stream);
+  TileParams p = p0;
+  return tile_grid_plan(p) ? launch_tile_impl<MODE, true, true>(p, stream) : launch_tile_impl<MODE, true, false>(p, stream);
 }
 
 // the Flocking-reward rollout: same selection of the tensor-core / register-budget variants
-static cudaError_t launch_tile_flock(const TileParams& p, cudaStream_t stream) {
-  if (!p.use_tc) return launch_tile_impl<MODE_ROLLOUT, false, true, true>(p, stream);
-  const int grid = (p.cfg.num_envs + p.epb - 1) / p.epb;
-  return grid > 3 * 148 ? launch_tile_impl<MODE_ROLLOUT, true, true, true>(p, stream)
-                        : launch_tile_impl<MODE_ROLLOUT, true, false, true>(p, stream);
+static cudaError_t launch_tile_flock(const TileParams& p0, cudaStream_t stream) {
+  if (!p0.use_tc) return launch_tile_impl<MODE_ROLLOUT, false, true, true>(p0, stream);
+  TileParams p = p0;
+  return tile_grid_plan(p) ? launch_tile_impl<MODE_ROLLOUT, true, true, true>(p, stream)
+                           : launch_tile_impl<MODE_ROLLOUT, true, false, true>(p, stream);
 }
 
 cudaError_t launch_tile(int mode, const TileParams& p, cudaStream_t stream) {

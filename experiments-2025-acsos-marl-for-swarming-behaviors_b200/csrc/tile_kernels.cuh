@@ -110,7 +110,9 @@ struct TileParams {
   float epsilon;
   int32_t use_tc;                // 1: dense contractions on the tensor cores (tcgen05, 3xTF32)
   int32_t ticks;
-  int32_t epb;                   // envs per block
+  int32_t epb;                   // envs per block (capacity of a CTA)
+  int32_t bal_q, bal_r;          // balanced assignment (bal_q > 0): CTA b owns bal_q + (b < bal_r) envs from
+                                 // b * bal_q + min(b, bal_r) on -- a single-wave grid spread evenly over every CTA slot
   int32_t maxdeg;                // max in-degree of the graph (rows of the per-thread edge scratch)
   int32_t edges_per_env;
   float one_minus_drag;
@@ -153,14 +155,17 @@ __host__ __device__ inline TileLayout tile_layout(int mode, int threads, int n, 
   L.tc_w0 = off;  off = tile_align128(off + (tc ? 2 * 32 * 8 * 4 : 0));
   L.tc_w1 = off;  off = tile_align128(off + (tc ? 2 * 32 * 32 * 4 : 0));
   L.tc_w2 = off;  off = tile_align128(off + (tc ? 2 * 16 * 32 * 4 : 0));
-  L.tc_vec = off; off = tile_align16(off + (tc ? 144 * 4 : 0));
+  L.tc_vec = off; off = tile_align16(off + (tc ? 96 * 4 : 0));
   L.tc_bar = off; off = tile_align16(off + (tc ? 16 : 0));
   L.w = off;    off = tile_align16(off + ((q && !tc) ? TW_COUNT * 4 : 0));
   L.st = off;   off = tile_align16(off + 2 * threads * 16);
-  L.h = off;    off = tile_align16(off + (q ? threads * kHPad * 4 : 0));
+  // the tensor-core path attends in input space (tile_tc_device.cuh): no tile of projected features, no per-edge
+  // scratch, and no edge list for the complete graph
+  const bool tc_complete = tc && graph_mode == SWARM_GRAPH_COMPLETE;
+  L.h = off;    off = tile_align16(off + ((q && !tc) ? threads * kHPad * 4 : 0));
   L.asrc = off; off = tile_align16(off + (q ? threads * 4 : 0));
-  L.wt = off;   off = tile_align16(off + (q ? maxdeg * threads * 4 : 0));
-  L.inl = off;  off = tile_align16(off + (q ? maxdeg * threads : 0));
+  L.wt = off;   off = tile_align16(off + ((q && !tc) ? maxdeg * threads * 4 : 0));
+  L.inl = off;  off = tile_align16(off + ((q && !tc_complete) ? maxdeg * threads : 0));
   L.deg = off;  off = tile_align16(off + (q ? threads : 0));
   // kNN rows: swarms of n <= 16 keep them in registers (knn_small.h) and only publish one membership word per thread
   const bool knn_rows = knn && n > 16;

@@ -1,6 +1,17 @@
 // tile_tc_device.cuh -- the tensor-core (tcgen05, 3xTF32) variant of the per-tick Q-network forward of the
 // env-tile kernels.  The three dense contractions run as UMMA tiles over the CTA's 128 node rows; attention
 // softmax / aggregation, biases, tanh / ReLU and the argmax stay on the CUDA cores.
+//
+// Attention in INPUT space.  GATConv's projection is linear and has no bias (train:50-58: h_j = W0 x_j), so
+//     sum_e alpha_e h_src(e) = W0 (sum_e alpha_e x_src(e))      and      <h_j, att> = <x_j, W0^T att>.
+// The tick therefore never forms h: every node takes two 7-term dot products with the pre-multiplied attention
+// vectors (v_s = W0^T att_src, v_d = W0^T att_dst, computed once per launch), the softmax-weighted mean is taken over
+// the 7 input features of the neighbours -- of which four are the state already staged for the world step, two are
+// the constant goal and one is the agent id -- and ONE projection MMA (K = 8) maps the mean to the 32 channels.  Per
+// edge that is one 16-byte shared-memory load and three FMAs instead of eight loads and sixteen packed FMAs, the
+// 18 KB tile of projected features, its publication and one block barrier per tick disappear.  Same mathematics as
+// the reference's order of operations, different rounding (float32 level both ways); the bit-faithful order lives on
+// in the SWARM_TC=0 path.
 #ifndef SWARM_TILE_TC_DEVICE_CUH
 #define SWARM_TILE_TC_DEVICE_CUH
 
@@ -10,7 +21,8 @@
 namespace swarm {
 
 // float offsets inside the small vector block
-enum { TV_ATT_S = 0, TV_ATT_D = 32, TV_B0 = 64, TV_B1 = 96, TV_B2 = 128, TV_COUNT = 144 };
+// (v_s, v_d: W0^T att_src / W0^T att_dst, 7 entries + one zero each)
+enum { TV_VS = 0, TV_VD = 8, TV_B0 = 16, TV_B1 = 48, TV_B2 = 80, TV_COUNT = 96 };
 // TMEM columns: D tiles [0,32) projection / lin2 and [32,64) lin1; A operand (this CTA's 128 activation rows, written
 // by their owner threads with tcgen05.st) hi half [64,96), lo half [96,128)
 constexpr int kTmemCols = 128;
@@ -32,20 +44,26 @@ constexpr int kTcW0Bytes = 2 * 32 * 8 * 4, kTcW1Bytes = 2 * 32 * 32 * 4, kTcW2By
 // which the compiler must assume to alias the source): one exposed memory round trip instead of one per item --
 // this prologue is a fifth of a single-tick launch (train tick).
 __device__ __forceinline__ void stage_weights_tc(const float* __restrict__ gw, const TileTcSmem& s, int tid, int nthreads) {
-  constexpr int kVecIters = (TV_COUNT + kTileThreads - 1) / kTileThreads;     // 2
-  constexpr int kItemIters = (448 + kTileThreads - 1) / kTileThreads;         // 4
-  float vv[kVecIters];
+  // bias vectors, and the attention vectors pulled through the projection: v[k] = sum_c att[c] W0[c][k], c ascending
+  // (threads 0 .. 13; every load is issued before the FMA chain starts)
+  float vv = 0.0f;
+  {
+    const int idx = tid;
+    if (idx < TV_B0) {
+      const int k = idx & 7;
+      if (k < 7) {
+        const float* att = gw + ((idx < TV_VD) ? SWARM_W_ATT_SRC : SWARM_W_ATT_DST);
+        float a[32], w[32];
 #pragma unroll
-  for (int k = 0; k < kVecIters; ++k) {
-    const int idx = tid + k * nthreads;
-    float v = 0.0f;
-    if (idx < TV_ATT_D) v = gw[SWARM_W_ATT_SRC + idx];
-    else if (idx < TV_B0) v = gw[SWARM_W_ATT_DST + (idx - TV_ATT_D)];
-    else if (idx < TV_B1) v = gw[SWARM_W_CONV_BIAS + (idx - TV_B0)];
-    else if (idx < TV_B2) v = gw[SWARM_W_LIN1_BIAS + (idx - TV_B1)];
-    else if (idx - TV_B2 < 9) v = gw[SWARM_W_LIN2_BIAS + (idx - TV_B2)];
-    vv[k] = v;
+        for (int c = 0; c < 32; ++c) { a[c] = att[c]; w[c] = gw[SWARM_W_CONV_LIN + c * 7 + k]; }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) vv = fmaf(a[c], w[c], vv);
+      }
+    } else if (idx < TV_B1) vv = gw[SWARM_W_CONV_BIAS + (idx - TV_B0)];
+    else if (idx < TV_B2) vv = gw[SWARM_W_LIN1_BIAS + (idx - TV_B1)];
+    else if (idx - TV_B2 < 9) vv = gw[SWARM_W_LIN2_BIAS + (idx - TV_B2)];
   }
+  constexpr int kItemIters = (448 + kTileThreads - 1) / kTileThreads;         // 4
   // items: (row n, k-chunk c) of W1 (256), W2 (128), W0 (64)
   float4 item[kItemIters];
 #pragma unroll
@@ -68,11 +86,7 @@ __device__ __forceinline__ void stage_weights_tc(const float* __restrict__ gw, c
     }
     item[k] = v;
   }
-#pragma unroll
-  for (int k = 0; k < kVecIters; ++k) {
-    const int idx = tid + k * nthreads;
-    if (idx < TV_COUNT) s.vec[idx] = vv[k];
-  }
+  if (tid < TV_COUNT) s.vec[tid] = vv;
 #pragma unroll
   for (int k = 0; k < kItemIters; ++k) {
     const int it = tid + k * nthreads;
@@ -136,16 +150,79 @@ __device__ __forceinline__ void tc_mma_round(const TileTcSmem& s, uint32_t tmem,
   tc::fence_after_sync();
 }
 
-// Full per-tick Q forward on the tensor cores.  Contains 4 block barriers.  All 128 threads must call it.
+// alpha_src / alpha_dst of the node with input features x (attention vectors pulled through the projection)
+__device__ __forceinline__ void tc_alpha_terms(const TileTcSmem& s, const float (&x)[7], float& asrc, float& adst) {
+  const float4* v4 = reinterpret_cast<const float4*>(s.vec + TV_VS);
+  const float4 s0 = v4[0], s1 = v4[1], d0 = v4[2], d1 = v4[3];
+  float2 acc = make_float2(0.0f, 0.0f);
+  acc = __ffma2_rn(make_float2(x[0], x[0]), make_float2(s0.x, d0.x), acc);
+  acc = __ffma2_rn(make_float2(x[1], x[1]), make_float2(s0.y, d0.y), acc);
+  acc = __ffma2_rn(make_float2(x[2], x[2]), make_float2(s0.z, d0.z), acc);
+  acc = __ffma2_rn(make_float2(x[3], x[3]), make_float2(s0.w, d0.w), acc);
+  acc = __ffma2_rn(make_float2(x[4], x[4]), make_float2(s1.x, d1.x), acc);
+  acc = __ffma2_rn(make_float2(x[5], x[5]), make_float2(s1.y, d1.y), acc);
+  acc = __ffma2_rn(make_float2(x[6], x[6]), make_float2(s1.z, d1.z), acc);
+  asrc = acc.x;
+  adst = acc.y;
+}
+
+// Softmax-weighted mean of the neighbours' input features (see the header).  `pos` = the tile's states, g.sas = the
+// published alpha_src terms.  COMPLETE: the reference's complete graph (train:101-108) -- sources of node i are all
+// j != i in ascending order, node 0 additionally ends with its (0,0) self loop -- without an edge list in memory;
+// otherwise the in-edge list g.sin / deg.
+template <bool COMPLETE>
+__device__ __forceinline__ void tile_attend_inputs(const TileGraphSmem& g, const TileThread& t, const float4* __restrict__ pos,
+                                                   int N, int deg, float adst, float goal_x, float goal_y, float (&xm)[8]) {
+  const int T = kTileThreads;
+  const float* __restrict__ sas = g.sas + t.envbase;
+  const float4* __restrict__ env = pos + t.envbase;
+  const uint8_t* __restrict__ sin = g.sin + t.tid;
+  const bool node0 = (t.i == 0);
+  const int n_edges = COMPLETE ? (t.active ? (node0 ? N : N - 1) : 0) : deg;
+  auto source = [&](int e) -> int {
+    if (COMPLETE) return node0 ? ((e + 1 == N) ? 0 : e + 1) : (e + (e >= t.i ? 1 : 0));
+    return sin[e * T];
+  };
+  // LeakyReLU and the rounded add are monotone: max_e leaky(a_e + d) = leaky(max_e a_e + d)
+  float amax = -INFINITY;
+#pragma unroll 4
+  for (int e = 0; e < n_edges; ++e) amax = fmaxf(amax, sas[source(e)]);
+  const float zt = __fadd_rn(amax, adst);
+  const float m = fmaxf(zt, __fmul_rn(zt, 0.2f));
+  float den = 0.0f, acc_id = 0.0f;
+  float2 acc_p = make_float2(0.0f, 0.0f), acc_v = make_float2(0.0f, 0.0f);
+#pragma unroll 2
+  for (int e = 0; e < n_edges; ++e) {
+    const int j = source(e);
+    const float4 sj = env[j];
+    const float zz = __fadd_rn(sas[j], adst);
+    const float w = __expf(fmaxf(zz, __fmul_rn(zz, 0.2f)) - m);
+    const float2 w2 = make_float2(w, w);
+    den = __fadd_rn(den, w);
+    acc_p = __ffma2_rn(w2, make_float2(sj.x, sj.y), acc_p);
+    acc_v = __ffma2_rn(w2, make_float2(sj.z, sj.w), acc_v);
+    acc_id = fmaf(w, (float)j, acc_id);
+  }
+  const float inv = 1.0f / __fadd_rn(den, 1e-16f);
+  const float wsum = den * inv;                  // sum of the attention coefficients (the goal features are constant)
+  xm[0] = acc_p.x * inv; xm[1] = acc_p.y * inv; xm[2] = acc_v.x * inv; xm[3] = acc_v.y * inv;
+  xm[4] = goal_x * wsum; xm[5] = goal_y * wsum; xm[6] = acc_id * inv; xm[7] = 0.0f;
+}
+
+// Full per-tick Q forward on the tensor cores.  The caller has published g.sas[tid] = alpha_src of every node and
+// passed a block barrier since (the tick's state barrier).  Contains 3 block barriers.  All 128 threads must call it.
+template <bool COMPLETE>
 __device__ __forceinline__ int tile_q_forward_tc(const TileGraphSmem& g, const TileTcSmem& s, const TileThread& t,
-                                                 uint32_t tmem, const float (&x)[7], int deg, uint32_t& parity,
-                                                 float (&q)[9]) {
+                                                 uint32_t tmem, const float4* __restrict__ pos, int N, int deg, float adst,
+                                                 float goal_x, float goal_y, uint32_t& parity, float (&q)[9]) {
   const uint32_t lane_addr = tmem + ((uint32_t)(t.tid & ~31) << 16);     // this warp's 32 TMEM lanes
-  // ---- projection h = x W0^T (K padded 7 -> 8) ----
+  // ---- attention in input space, then agg = mean W0^T (K padded 7 -> 8) ----
   {
+    float xm[8];
+    tile_attend_inputs<COMPLETE>(g, t, pos, N, deg, adst, goal_x, goal_y, xm);
     float4 h0, l0, h1, l1;
-    tc::split4(make_float4(x[0], x[1], x[2], x[3]), h0, l0);
-    tc::split4(make_float4(x[4], x[5], x[6], 0.0f), h1, l1);
+    tc::split4(make_float4(xm[0], xm[1], xm[2], xm[3]), h0, l0);
+    tc::split4(make_float4(xm[4], xm[5], xm[6], 0.0f), h1, l1);
     const uint32_t hi[8] = {__float_as_uint(h0.x), __float_as_uint(h0.y), __float_as_uint(h0.z), __float_as_uint(h0.w),
                             __float_as_uint(h1.x), __float_as_uint(h1.y), __float_as_uint(h1.z), __float_as_uint(h1.w)};
     const uint32_t lo[8] = {__float_as_uint(l0.x), __float_as_uint(l0.y), __float_as_uint(l0.z), __float_as_uint(l0.w),
@@ -155,31 +232,8 @@ __device__ __forceinline__ int tile_q_forward_tc(const TileGraphSmem& g, const T
     tc::tmem_wait_st();
   }
   tc_mma_round(s, tmem, tmem, s.w0, kTcW0Bytes / 2, 32, 1, parity);
-  float h[32];
-  tc::tmem_ld32(lane_addr, h);
-  // alpha_src = <h, att_src>, alpha_dst = <h, att_dst>: vector loads of the attention vectors, packed FFMA2 with the
-  // (src, dst) pair as the two lanes
-  float asrc, adst;
-  {
-    float2 acc = make_float2(0.0f, 0.0f);
-    const float4* as4 = reinterpret_cast<const float4*>(s.vec + TV_ATT_S);
-    const float4* ad4 = reinterpret_cast<const float4*>(s.vec + TV_ATT_D);
-#pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) {
-      const float4 a = as4[c4], d = ad4[c4];
-      acc = __ffma2_rn(make_float2(h[4 * c4 + 0], h[4 * c4 + 0]), make_float2(a.x, d.x), acc);
-      acc = __ffma2_rn(make_float2(h[4 * c4 + 1], h[4 * c4 + 1]), make_float2(a.y, d.y), acc);
-      acc = __ffma2_rn(make_float2(h[4 * c4 + 2], h[4 * c4 + 2]), make_float2(a.z, d.z), acc);
-      acc = __ffma2_rn(make_float2(h[4 * c4 + 3], h[4 * c4 + 3]), make_float2(a.w, d.w), acc);
-    }
-    asrc = acc.x;
-    adst = acc.y;
-  }
-  if (t.active) tile_gat_publish(g, t, h, asrc);
-  __syncthreads();
-  // ---- attention + aggregation (CUDA cores) ----
   float a1[32];
-  tile_gat_attend<true>(g, t, deg, adst, a1);
+  tc::tmem_ld32(lane_addr, a1);
   {
     // u = tanh(agg + b0) = 1 - 2 / (exp(2 (agg + b0)) + 1), two channels per packed instruction around the SFU ops
     const float4* b4 = reinterpret_cast<const float4*>(s.vec + TV_B0);
