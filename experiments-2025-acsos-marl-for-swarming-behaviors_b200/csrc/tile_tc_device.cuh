@@ -176,32 +176,53 @@ __device__ __forceinline__ void tile_attend_inputs(const TileGraphSmem& g, const
   const int T = kTileThreads;
   const float* __restrict__ sas = g.sas + t.envbase;
   const float4* __restrict__ env = pos + t.envbase;
-  const uint8_t* __restrict__ sin = g.sin + t.tid;
-  const bool node0 = (t.i == 0);
-  const int n_edges = COMPLETE ? (t.active ? (node0 ? N : N - 1) : 0) : deg;
-  auto source = [&](int e) -> int {
-    if (COMPLETE) return node0 ? ((e + 1 == N) ? 0 : e + 1) : (e + (e >= t.i ? 1 : 0));
-    return sin[e * T];
-  };
-  // LeakyReLU and the rounded add are monotone: max_e leaky(a_e + d) = leaky(max_e a_e + d)
-  float amax = -INFINITY;
-#pragma unroll 4
-  for (int e = 0; e < n_edges; ++e) amax = fmaxf(amax, sas[source(e)]);
-  const float zt = __fadd_rn(amax, adst);
-  const float m = fmaxf(zt, __fmul_rn(zt, 0.2f));
   float den = 0.0f, acc_id = 0.0f;
   float2 acc_p = make_float2(0.0f, 0.0f), acc_v = make_float2(0.0f, 0.0f);
+  // LeakyReLU and the rounded add are monotone: max_e leaky(a_e + d) = leaky(max_e a_e + d)
+  if (COMPLETE) {
+    // Sources of node i: every j != i, and j = 0 for node 0 itself (its self loop).  The sums run over j = 0 .. N - 1
+    // with the own slot weighted zero -- for node 0 the self loop is summed first instead of last, a different
+    // rounding of the same sum -- so the loop needs no index arithmetic at all.
+    const int self = (t.i == 0) ? -1 : t.i;
+    const int n = t.active ? N : 0;
+    float amax = -INFINITY;
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) amax = fmaxf(amax, j == self ? -INFINITY : sas[j]);
+    const float zt = __fadd_rn(amax, adst);
+    const float m = fmaxf(zt, __fmul_rn(zt, 0.2f));
+    float fj = 0.0f;
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) {
+      const float4 sj = env[j];
+      const float zz = __fadd_rn(sas[j], adst);
+      const float ex = __expf(fmaxf(zz, __fmul_rn(zz, 0.2f)) - m);
+      const float w = (j == self) ? 0.0f : ex;
+      const float2 w2 = make_float2(w, w);
+      den = __fadd_rn(den, w);
+      acc_p = __ffma2_rn(w2, make_float2(sj.x, sj.y), acc_p);
+      acc_v = __ffma2_rn(w2, make_float2(sj.z, sj.w), acc_v);
+      acc_id = fmaf(w, fj, acc_id);
+      fj += 1.0f;
+    }
+  } else {
+    const uint8_t* __restrict__ sin = g.sin + t.tid;
+    float amax = -INFINITY;
+#pragma unroll 4
+    for (int e = 0; e < deg; ++e) amax = fmaxf(amax, sas[sin[e * T]]);
+    const float zt = __fadd_rn(amax, adst);
+    const float m = fmaxf(zt, __fmul_rn(zt, 0.2f));
 #pragma unroll 2
-  for (int e = 0; e < n_edges; ++e) {
-    const int j = source(e);
-    const float4 sj = env[j];
-    const float zz = __fadd_rn(sas[j], adst);
-    const float w = __expf(fmaxf(zz, __fmul_rn(zz, 0.2f)) - m);
-    const float2 w2 = make_float2(w, w);
-    den = __fadd_rn(den, w);
-    acc_p = __ffma2_rn(w2, make_float2(sj.x, sj.y), acc_p);
-    acc_v = __ffma2_rn(w2, make_float2(sj.z, sj.w), acc_v);
-    acc_id = fmaf(w, (float)j, acc_id);
+    for (int e = 0; e < deg; ++e) {
+      const int j = sin[e * T];
+      const float4 sj = env[j];
+      const float zz = __fadd_rn(sas[j], adst);
+      const float w = __expf(fmaxf(zz, __fmul_rn(zz, 0.2f)) - m);
+      const float2 w2 = make_float2(w, w);
+      den = __fadd_rn(den, w);
+      acc_p = __ffma2_rn(w2, make_float2(sj.x, sj.y), acc_p);
+      acc_v = __ffma2_rn(w2, make_float2(sj.z, sj.w), acc_v);
+      acc_id = fmaf(w, (float)j, acc_id);
+    }
   }
   const float inv = 1.0f / __fadd_rn(den, 1e-16f);
   const float wsum = den * inv;                  // sum of the attention coefficients (the goal features are constant)
