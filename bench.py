@@ -156,7 +156,10 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.gpus),
+            "config": dict(workload_config(args.gpus), reference_arm_runs=(
+                f"{cores} single-env CPU processes (num_envs = 1 each, as the reference runs), {ticks} greedy ticks per "
+                "process per step from a fresh contact-free reset; same scenario / swarm size / graph / weights, not the "
+                "4096-env batch (the reference cannot batch)")),
             "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": "port",
                              "sample": f"per step: {cores} processes x {ticks} ticks of one 12-agent env each "
                                        "(reference-structured per-tick loop, oracle/swarm_oracle.py)"},
@@ -202,6 +205,7 @@ def run_ours(args):
     hits = torch.zeros(B, dtype=torch.int32, device=dev)
     returns_host = torch.empty(B, N).pin_memory()
     hits_host = torch.empty(B, dtype=torch.int32).pin_memory()
+    state_host = torch.empty(B, N, 4).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
 
@@ -217,6 +221,7 @@ def run_ours(args):
         ops.rollout(cfg, weights, state, T, returns=returns, hits=hits)
         returns_host.copy_(returns, non_blocking=True)
         hits_host.copy_(hits, non_blocking=True)
+        state_host.copy_(state, non_blocking=True)            # what a caller of rollout() gets back: final states too
         stream.synchronize()
         return float(returns_host[0, 0])
 
@@ -310,17 +315,23 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": B * 2 * 4,
-                "d2h_bytes_per_step": B * N * 4 + B * 4, "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": B * N * 4 + B * 4 + B * N * 16, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": 2 * args.steps,
-        "roofline": {"kernel": "tile_kernel<MODE_ROLLOUT>", "bound": "hbm", "achieved": achieved, "peak": peak_gbs,
-                     "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
-                     "kernel_ms": kernel_ms,
-                     "note": "the fused rollout keeps the state on chip for 100 ticks, so it is issue / latency bound, not "
-                             "HBM bound (SURVEY.md 8d; see roofline_fp32 and memory_bound_kernels); algorithmic bytes "
-                             "= 40 B/agent-step; traffic = DRAM bytes of one launch from the committed ncu capture"},
-        "roofline_fp32": {"achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_achieved / fp32_peak,
-                          "flops_per_agent_step": FLOPS_PER_AGENT_STEP,
-                          "peak_source": f"148 SMs x 128 FMA lanes x 2 x {sm_mhz:.0f} MHz (sampled under load)"},
+        # the dominant kernel keeps the state on chip for 100 ticks: it is bound by instruction issue on the CUDA cores,
+        # not by HBM and not by the tensor pipe -- `roofline` states that bound (algorithmic FLOPs of the reference
+        # computation, SURVEY.md 8d, against the FP32 FMA issue peak at the sampled clock); the HBM view of the same
+        # launch is kept beside it
+        "roofline": {"kernel": "tile_kernel<MODE_ROLLOUT>", "bound": "issue (fp32 CUDA cores)", "achieved": fp32_achieved,
+                     "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_achieved / fp32_peak,
+                     "traffic": None, "kernel_ms": kernel_ms, "flops_per_agent_step": FLOPS_PER_AGENT_STEP,
+                     "peak_source": f"148 SMs x 128 FMA lanes x 2 x {sm_mhz:.0f} MHz (sampled under load; not in "
+                                    "MEASURED_PEAKS.json, which holds HBM and bf16 tensor peaks)",
+                     "note": "algorithmic FLOPs = 4 200 per agent-step (reference op count, N = 12, complete graph); the "
+                             "kernel itself executes fewer (attention in input space); traffic = DRAM bytes of one launch "
+                             "from the committed ncu capture"},
+        "roofline_hbm": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                         "peak_source": peak_src, "bytes_per_agent_step": BYTES_PER_AGENT_STEP,
+                         "note": "40 B/agent-step algorithmic; only 36 B/agent/launch actually move (state in registers)"},
         "clocks": clocks,
     }
     line["roofline"]["traffic"] = ncu_dram_traffic_bytes()
@@ -329,6 +340,7 @@ def run_ours(args):
         line["strong_scaling_point"] = strong
     if world == 1:
         line["memory_bound_kernels"] = measure_streaming_kernels(sb, ops, dev, peak_gbs)
+        line["extra"] = measure_extra(sb, ops, dev)
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_single()
     emit(line)
@@ -336,10 +348,65 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def measure_extra(sb, ops, dev):
+    """The other BASELINE.json configurations, driver-run: the kNN (evaluation-graph) variant of C2, the
+    C3 sweep (65 536 envs, GoTo, N = 5 / 8 / 12, complete and kNN k = 5) and C4 (1 024 agents x 1 024 envs, kNN k = 10).
+    Device-resident, CUDA events, greedy policy of the shipped seed-0 weights."""
+    L = sb._lib
+    models = np.load(os.path.join(ROOT, "tests", "golden", "models.npz"))
+
+    def weights(pre):
+        return sb.pack_weights({k[len(pre):]: torch.from_numpy(models[k]) for k in models.files if k.startswith(pre)}, dev)
+
+    w_oa, w_goto = weights("ObstacleAvoidance/0/"), weights("GoTo/0/")
+
+    def rollout_rate(scen, B, N, graph, k, ticks, reps=3):
+        cfg = ops.make_config(scen, B, N, graph, k)
+        centers = draw_centers(7, B).to(dev)
+        state = ops.reset_grid(cfg, centers)
+        ret = torch.zeros(B, N, device=dev)
+        hits = torch.zeros(B, dtype=torch.int32, device=dev)
+        w = w_oa if scen == L.SCENARIO_OBSTACLE_AVOIDANCE else w_goto
+        ops.rollout(cfg, w, state, ticks, returns=ret, hits=hits)
+        ms = 0.0
+        for _ in range(reps):
+            ops.reset_grid(cfg, centers, out=state)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ops.rollout(cfg, w, state, ticks, returns=ret, hits=hits)
+            b.record()
+            torch.cuda.synchronize(dev)
+            ms += a.elapsed_time(b)
+        return B * N * ticks * reps / (ms * 1e-3)
+
+    out = {"unit": "agent-steps/s"}
+    out["c2_knn_k5"] = rollout_rate(L.SCENARIO_OBSTACLE_AVOIDANCE, ENVS_PER_GPU, N_AGENTS, L.GRAPH_KNN, 5, TICKS)
+    sweep = {}
+    for n in (5, 8, 12):
+        sweep[f"N{n}_complete"] = rollout_rate(L.SCENARIO_GOTO, 65536, n, L.GRAPH_COMPLETE, 5, 50)
+        sweep[f"N{n}_knn_k5"] = rollout_rate(L.SCENARIO_GOTO, 65536, n, L.GRAPH_KNN, 5, 50)
+    out["c3_goto_65536_envs"] = sweep
+    # C4: large swarm, per-tick launches (topk table -> per-env Q -> world step)
+    B4, N4, K4, T4 = 1024, 1024, 10, 10
+    cfg4 = ops.make_config(L.SCENARIO_OBSTACLE_AVOIDANCE, B4, N4, L.GRAPH_KNN, K4)
+    st4 = ops.reset_grid(cfg4, draw_centers(9, B4).to(dev))
+    ops.rollout_large(cfg4, w_oa, st4, 2)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    ops.rollout_large(cfg4, w_oa, st4, T4)
+    b.record()
+    torch.cuda.synchronize(dev)
+    out["c4_oa_1024x1024_knn_k10"] = {"agent_steps_per_s": B4 * N4 * T4 / (a.elapsed_time(b) * 1e-3),
+                                      "ms_per_tick": a.elapsed_time(b) / T4}
+    return out
+
+
 def ncu_dram_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch, from the committed `ncu --set full` summary
-    of this same command (profiles/r1_ncu_rollout_c2.txt); None if the summary is missing."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_rollout_c2.txt")
+    of this same command (profiles/r2_ncu_rollout_c2.txt, else round 1's); None if the summary is missing."""
+    path = os.path.join(ROOT, "profiles", "r2_ncu_rollout_c2.txt")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r1_ncu_rollout_c2.txt")
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     try:
         total = 0.0
