@@ -8,39 +8,9 @@
 // (target, source) pair), and all weight gradients are tile GEMMs  dW = L^T R  over the CTA's 128 node
 // rows; per-CTA partials are then summed in CTA order by dqn_reduce_kernel.  No atomics anywhere, so the
 // gradient is bit-reproducible from run to run.
-#include "tile_device.cuh"
+#include "dqn_common.cuh"
 
 namespace swarm {
-
-constexpr int kPartialStride = 1680;   // 1673 gradients + [1673] = sum of squared TD errors, padded
-constexpr int kXPad = 8;
-
-struct DqnParams {
-  SwarmConfig cfg;
-  const float* w_online;
-  const float* w_target;
-  SwarmReplay batch;
-  const int64_t* indices;
-  int32_t n_graphs;
-  float gamma;
-  float loss_scale;
-  float* partials;
-  float* td;
-  int32_t epb, maxdeg;
-  float qmax_r;               // radius graph threshold (see TileParams)
-  int32_t parallel;           // 1: target pass and online pass of a transition run side by side on two thread groups
-  // device-driven tick (swarm_train_tick_grad): slots are drawn here from the ring fill after this tick's push
-  const SwarmTrainCtl* ctl;
-  int64_t* indices_out;       // [n_graphs] the drawn slots (exported for tests / logging)
-  unsigned long long sample_seed;
-  int32_t pushed_envs;        // transitions pushed by this tick's rollout
-};
-
-// ring fill after this tick's push, and whether it allows an update (train:113-115)
-__device__ __forceinline__ long long train_ring_size(const SwarmTrainCtl* ctl, int pushed, long long capacity) {
-  const long long size = ctl->ring_size + pushed;
-  return size < capacity ? size : capacity;
-}
 
 struct DqnLayout {
   int w_on, w_tg, st, h, asrc, wt, wd, inl, kv, ki, nbr, u, r, dp, dob, dh, x, dq, ds, dt, ma, mz, red, total;
@@ -1098,7 +1068,15 @@ long long dqn_workspace_bytes(const SwarmConfig& c, int n_graphs) {
   return ctas * kPartialStride * 4 + 256;
 }
 
+bool dqn_tc_enabled();
+int dqn_tc_smem_bytes(const SwarmConfig& c);
+cudaError_t launch_dqn_grad_tc(DqnParams& p, cudaStream_t stream);
+
+// the tensor-core kernel (dqn_tc_kernels.cu) unless SWARM_TC=0 or its tile does not fit shared memory
+static bool dqn_use_tc(const SwarmConfig& c) { return dqn_tc_enabled() && dqn_tc_smem_bytes(c) <= 227 * 1024; }
+
 int dqn_smem_bytes(const SwarmConfig& c) {
+  if (dqn_use_tc(c)) return dqn_tc_smem_bytes(c);
   const int epb = kTileThreads / c.n_agents;
   return dqn_layout(c.n_agents, c.knn_k, dqn_maxdeg(c), epb, c.graph_mode).total;
 }
@@ -1126,11 +1104,17 @@ cudaError_t launch_dqn_grad(const SwarmConfig& c, const float* w_online, const f
   p.epb = dqn_epb(c, n_graphs);
   p.parallel = (2 * p.epb * c.n_agents <= kTileThreads) ? 1 : 0;
   p.maxdeg = dqn_maxdeg(c);
-  const int smem = dqn_layout(c.n_agents, c.knn_k, p.maxdeg, p.epb, c.graph_mode).total;
-  cudaError_t err = cudaFuncSetAttribute(dqn_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (err != cudaSuccess) return err;
   const int ctas = (n_graphs + p.epb - 1) / p.epb;
-  dqn_grad_kernel<<<ctas, kTileThreads, smem, stream>>>(p);
+  cudaError_t err;
+  if (dqn_use_tc(c)) {
+    err = launch_dqn_grad_tc(p, stream);
+    if (err != cudaSuccess) return err;
+  } else {
+    const int smem = dqn_layout(c.n_agents, c.knn_k, p.maxdeg, p.epb, c.graph_mode).total;
+    err = cudaFuncSetAttribute(dqn_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return err;
+    dqn_grad_kernel<<<ctas, kTileThreads, smem, stream>>>(p);
+  }
   dqn_reduce_kernel<<<(SWARM_W_COUNT + 1 + 255) / 256, 256, 0, stream>>>(p.partials, ctas, loss_scale, grad, loss, ctl,
                                                                          pushed_envs, batch.capacity, n_graphs);
   return cudaGetLastError();

@@ -1,0 +1,628 @@
+// dqn_tc_kernels.cu -- the DQN gradient (train_gcn_dqn.py:112-137: target net on s', online net on s, TD error, backward
+// pass) on the tensor cores.
+//
+// Same env-tile scheme as the rollout (thread = node, CTA = floor(128 / N) sampled transitions, per-CTA partial
+// gradients reduced in CTA order by dqn_reduce_kernel -- no atomics, bit-reproducible), but every dense contraction
+// runs on the tensor pipe and the attention layer is differentiated in INPUT space (tile_tc_device.cuh):
+//
+//   forward     xm_i = sum_e alpha_e x_src(e)           softmax-weighted mean of the 7 input features, CUDA cores
+//               o_i = W0 xm_i + b0, u = tanh(o), p = W1 u + b1, r = relu(p), q = W2 r + b2
+//                                                        three tcgen05 3xTF32 UMMA rounds, A rows in tensor memory
+//   backward    dp = (W2[a]^T dq) * [r > 0];  du = W1^T dp (UMMA, B = W1^T tile);  do = du * (1 - u^2)
+//               dxm = W0^T do (UMMA, B = W0^T tile);  d alpha_e = <dxm_i, x_src(e)>   -- a 7-term dot product; no
+//               32-channel gather over the neighbours, no tile of projected features
+//               softmax / LeakyReLU backward per in-edge;  d alpha_src_j gathered through a per-env dense matrix
+//   weights     dW1 = sum_n dp_n (x) u_n,  dW2 = sum_n dq_n e_a (x) r_n,  dW0 = sum_n do_n (x) xm_n  contract over NODES:
+//               every warp contracts its own 32 nodes with mma.sync m16n8k8 TF32 (3x split) from two warp-private
+//               staging tiles (__syncwarp only), column sums give the bias gradients, and the attention vectors get
+//               theirs through v = W0^T att:  d att = W0 dv,  dW0 += att (x) dv  with  dv_s = sum_j d alpha_src_j x_j.
+//               The four warp partials are added in warp order.
+// One transition set costs ~3 k instructions per warp instead of ~19 k on the CUDA-core kernel (dqn_kernels.cu, which
+// stays as the SWARM_TC=0 parity path), and the CTA needs 2 x 5 KB of staging per warp instead of six 18 KB tiles.
+#include <cstdlib>
+
+#include "dqn_common.cuh"
+#include "tile_tc_device.cuh"
+
+namespace swarm {
+
+constexpr int kStageLd = 40;                    // floats per staged row: conflict-free mma fragment loads
+constexpr int kStageBuf = 32 * kStageLd;        // one warp-private tile (32 nodes)
+// slots of a partial beyond the packed gradient: [1673] sum of squared TD errors, then dv_s[8], dv_d[8]
+constexpr int kPartSse = SWARM_W_COUNT, kPartDvS = SWARM_W_COUNT + 1, kPartDvD = SWARM_W_COUNT + 9;
+constexpr int kPartCount = SWARM_W_COUNT + 17;
+static_assert(kPartCount <= 2 * kStageBuf, "a warp partial must fit the warp's two staging tiles");
+constexpr int kTcW1tBytes = 2 * 32 * 32 * 4, kTcW0tBytes = 2 * 16 * 32 * 4;
+
+struct DqnTcLayout {
+  int tg_w0, tg_w1, tg_w2, tg_vec, on_w0, on_w1, on_w2, on_vec, w1t, w0t, plain, bar, st, asrc, wt, inl, kv, ki, nbr, mz,
+      sdq, sact, sdasrc, sdadst, sx, xbar, stage, red, total;
+};
+// plain float32 copies of online tensors read by the CUDA-core parts: W2 [9][32], att_src [32], att_dst [32], W0 [32][7]
+enum { PL_W2 = 0, PL_ATT_S = 288, PL_ATT_D = 320, PL_W0 = 352, PL_DV = 576, PL_COUNT = 592 };
+
+__host__ __device__ inline DqnTcLayout dqn_tc_layout(int n, int k, int maxdeg, int epb, int graph_mode) {
+  const int T = kTileThreads;
+  DqnTcLayout L;
+  int off = 0;
+  auto take = [&](int bytes, int align) { off = (off + align - 1) & ~(align - 1); const int o = off; off += bytes; return o; };
+  const bool knn = graph_mode == SWARM_GRAPH_KNN;
+  const bool knn_rows = knn && n > 16;
+  const bool complete = graph_mode == SWARM_GRAPH_COMPLETE;
+  L.tg_w0 = take(kTcW0Bytes, 128); L.tg_w1 = take(kTcW1Bytes, 128); L.tg_w2 = take(kTcW2Bytes, 128);
+  L.on_w0 = take(kTcW0Bytes, 128); L.on_w1 = take(kTcW1Bytes, 128); L.on_w2 = take(kTcW2Bytes, 128);
+  L.w1t = take(kTcW1tBytes, 128); L.w0t = take(kTcW0tBytes, 128);
+  L.tg_vec = take(TV_COUNT * 4, 16); L.on_vec = take(TV_COUNT * 4, 16);
+  L.plain = take(PL_COUNT * 4, 16);
+  L.bar = take(16, 16);
+  L.st = take(T * 16, 16);
+  L.asrc = take(T * 4, 16);
+  L.wt = take(maxdeg * T * 4, 16);
+  L.inl = take(complete ? 0 : maxdeg * T, 16);
+  L.kv = take(knn ? (knn_rows ? n : 1) * T * 4 : 0, 16);
+  L.ki = take(knn_rows ? n * T : 0, 16);
+  L.nbr = take(knn_rows ? k * T : 0, 16);
+  L.mz = take(epb * n * n * 4, 16);
+  L.sdq = take(T * 4, 16); L.sact = take(T * 4, 16); L.sdasrc = take(T * 4, 16); L.sdadst = take(T * 4, 16);
+  L.sx = take(T * 8 * 4, 16);
+  L.xbar = take(T * 8 * 4, 16);
+  L.stage = take(4 * 2 * kStageBuf * 4, 16);
+  L.red = take(T * 4, 16);
+  L.total = off;
+  return L;
+}
+
+// ---- extra B tiles of the backward pass --------------------------------------------------------------------------
+// w1t: B[n = k][K = c] = W1[c][k]  (du = W1^T dp);  w0t: B[n = k < 7, padded to 16][K = c] = W0[c][k]  (dxm = W0^T do)
+__device__ __forceinline__ void stage_backward_tiles(const float* __restrict__ gw, unsigned char* w1t, unsigned char* w0t,
+                                                     float* plain, int tid, int nthreads) {
+  for (int it = tid; it < 256 + 128; it += nthreads) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned char* base;
+    int rows, n, c, half;
+    if (it < 256) {
+      n = it >> 3; c = it & 7; rows = 32; base = w1t; half = kTcW1tBytes / 2;
+      const float* col = gw + SWARM_W_LIN1 + n;                 // W1[4c + j][n]
+      v = make_float4(col[(4 * c + 0) * 32], col[(4 * c + 1) * 32], col[(4 * c + 2) * 32], col[(4 * c + 3) * 32]);
+    } else {
+      const int j = it - 256;
+      n = j >> 3; c = j & 7; rows = 16; base = w0t; half = kTcW0tBytes / 2;
+      if (n < 7) {
+        const float* col = gw + SWARM_W_CONV_LIN + n;           // W0[4c + j][n]
+        v = make_float4(col[(4 * c + 0) * 7], col[(4 * c + 1) * 7], col[(4 * c + 2) * 7], col[(4 * c + 3) * 7]);
+      }
+    }
+    float4 hi, lo;
+    tc::split4(v, hi, lo);
+    const int off = tc::tile_off(rows, n, c);
+    *reinterpret_cast<float4*>(base + off) = hi;
+    *reinterpret_cast<float4*>(base + half + off) = lo;
+  }
+  for (int o = tid; o < PL_DV; o += nthreads) {
+    float v;
+    if (o < PL_ATT_S) v = gw[SWARM_W_LIN2 + o];
+    else if (o < PL_ATT_D) v = gw[SWARM_W_ATT_SRC + (o - PL_ATT_S)];
+    else if (o < PL_W0) v = gw[SWARM_W_ATT_DST + (o - PL_ATT_D)];
+    else v = gw[SWARM_W_CONV_LIN + (o - PL_W0)];
+    plain[o] = v;
+  }
+}
+
+// ---- warp-level node contraction on mma.sync (m16n8k8, TF32, 3x split) --------------------------------------------
+__device__ __forceinline__ void split_frag(float x, uint32_t& hi, uint32_t& lo) {
+  float h, l;
+  tc::split_tf32(x, h, l);
+  hi = __float_as_uint(h);
+  lo = __float_as_uint(l);
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// acc[mt][nt] += sum over this warp's 32 nodes of left(node, m) * right(node, n); m = mt * 16 + row, n = nt * 8 + col.
+// Fragment ownership (g = lane / 4, tg = lane % 4): A (g | g + 8, tg | tg + 4), B (k = tg | tg + 4, n = g),
+// C (g | g + 8, 2 tg | 2 tg + 1).  Small terms first, like the UMMA path.
+template <int MT, int NT, typename FL, typename FR>
+__device__ __forceinline__ void warp_node_gemm(float (&acc)[MT][NT][4], int lane, FL left, FR right) {
+  const int g = lane >> 2, tg = lane & 3;
+#pragma unroll 1
+  for (int ks = 0; ks < 4; ++ks) {
+    const int n0 = ks * 8 + tg, n1 = n0 + 4;
+    uint32_t ah[MT][4], al[MT][4], bh[NT][2], bl[NT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      split_frag(left(n0, mt * 16 + g), ah[mt][0], al[mt][0]);
+      split_frag(left(n0, mt * 16 + g + 8), ah[mt][1], al[mt][1]);
+      split_frag(left(n1, mt * 16 + g), ah[mt][2], al[mt][2]);
+      split_frag(left(n1, mt * 16 + g + 8), ah[mt][3], al[mt][3]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      split_frag(right(n0, nt * 8 + g), bh[nt][0], bl[nt][0]);
+      split_frag(right(n1, nt * 8 + g), bh[nt][1], bl[nt][1]);
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        mma_tf32(acc[mt][nt], al[mt], bh[nt]);
+        mma_tf32(acc[mt][nt], ah[mt], bl[nt]);
+        mma_tf32(acc[mt][nt], ah[mt], bh[nt]);
+      }
+  }
+}
+
+__device__ __forceinline__ void stage_row(float* buf, int lane, const float (&v)[32]) {
+  float4* r = reinterpret_cast<float4*>(buf + lane * kStageLd);
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4) r[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+}
+
+// softmax weights and weighted mean of the neighbours' input features, keeping what the backward pass needs:
+// the unnormalised weights w_e in swt[e][tid] and 1 / (sum + 1e-16).  Exact expf / division here -- the TD error is a
+// small difference of large Q values, so the forward pass of the update keeps float32-level accuracy throughout.
+template <bool COMPLETE>
+__device__ __forceinline__ float dqn_attend(const TileGraphSmem& g, const TileThread& t, const float4* __restrict__ pos,
+                                            int N, int deg, float adst, float goal_x, float goal_y, float (&xm)[8]) {
+  const int T = kTileThreads;
+  const float* __restrict__ sas = g.sas + t.envbase;
+  const float4* __restrict__ env = pos + t.envbase;
+  float* __restrict__ swt = g.swt + t.tid;
+  const uint8_t* __restrict__ sin = g.sin + t.tid;
+  const int self = (t.i == 0) ? -1 : t.i;                      // complete graph: node 0 keeps its (0,0) self loop
+  const int n_edges = COMPLETE ? (t.active ? N : 0) : deg;
+  float amax = -INFINITY;
+#pragma unroll 4
+  for (int e = 0; e < n_edges; ++e) {
+    const int j = COMPLETE ? e : (int)sin[e * T];
+    amax = fmaxf(amax, (COMPLETE && j == self) ? -INFINITY : sas[j]);
+  }
+  const float zt = __fadd_rn(amax, adst);
+  const float m = fmaxf(zt, __fmul_rn(zt, 0.2f));
+  float den = 0.0f, acc_id = 0.0f;
+  float2 acc_p = make_float2(0.0f, 0.0f), acc_v = make_float2(0.0f, 0.0f);
+#pragma unroll 2
+  for (int e = 0; e < n_edges; ++e) {
+    const int j = COMPLETE ? e : (int)sin[e * T];
+    const float4 sj = env[j];
+    const float zz = __fadd_rn(sas[j], adst);
+    float w = expf(__fsub_rn(fmaxf(zz, __fmul_rn(zz, 0.2f)), m));
+    if (COMPLETE && j == self) w = 0.0f;
+    swt[e * T] = w;
+    const float2 w2 = make_float2(w, w);
+    den = __fadd_rn(den, w);
+    acc_p = __ffma2_rn(w2, make_float2(sj.x, sj.y), acc_p);
+    acc_v = __ffma2_rn(w2, make_float2(sj.z, sj.w), acc_v);
+    acc_id = fmaf(w, (float)j, acc_id);
+  }
+  const float inv = __fdiv_rn(1.0f, __fadd_rn(den, 1e-16f));
+  const float wsum = den * inv;
+  xm[0] = acc_p.x * inv; xm[1] = acc_p.y * inv; xm[2] = acc_v.x * inv; xm[3] = acc_v.y * inv;
+  xm[4] = goal_x * wsum; xm[5] = goal_y * wsum; xm[6] = acc_id * inv; xm[7] = 0.0f;
+  return inv;
+}
+
+__device__ __forceinline__ void tc_store_a8(uint32_t lane_addr, const float (&v)[8]) {
+  float4 h0, l0, h1, l1;
+  tc::split4(make_float4(v[0], v[1], v[2], v[3]), h0, l0);
+  tc::split4(make_float4(v[4], v[5], v[6], v[7]), h1, l1);
+  const uint32_t hi[8] = {__float_as_uint(h0.x), __float_as_uint(h0.y), __float_as_uint(h0.z), __float_as_uint(h0.w),
+                          __float_as_uint(h1.x), __float_as_uint(h1.y), __float_as_uint(h1.z), __float_as_uint(h1.w)};
+  const uint32_t lo[8] = {__float_as_uint(l0.x), __float_as_uint(l0.y), __float_as_uint(l0.z), __float_as_uint(l0.w),
+                          __float_as_uint(l1.x), __float_as_uint(l1.y), __float_as_uint(l1.z), __float_as_uint(l1.w)};
+  tc::tmem_st8(lane_addr + kTmemAHi, hi);
+  tc::tmem_st8(lane_addr + kTmemALo, lo);
+  tc::tmem_wait_st();
+}
+
+template <bool COMPLETE>
+__global__ void __launch_bounds__(kTileThreads, 2) dqn_grad_tc_kernel(const __grid_constant__ DqnParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SwarmConfig& c = p.cfg;
+  const int T = kTileThreads;
+  const int N = c.n_agents;
+  const int K = c.knn_k;
+  const bool knn = c.graph_mode == SWARM_GRAPH_KNN;
+  const bool radius = c.graph_mode == SWARM_GRAPH_RADIUS;
+  TileThread t = tile_thread(N, p.epb, p.n_graphs);
+  const int tid = t.tid, lane = tid & 31, warp = tid >> 5;
+
+  long long ring_size = 0;
+  if (p.ctl) {
+    ring_size = train_ring_size(p.ctl, p.pushed_envs, p.batch.capacity);
+    if (ring_size < p.n_graphs) return;        // replay ring not filled yet (train:113-115)
+  }
+
+  const DqnTcLayout L = dqn_tc_layout(N, K, p.maxdeg, p.epb, c.graph_mode);
+  TileTcSmem ts_tg, ts_on;
+  ts_tg.w0 = smem + L.tg_w0; ts_tg.w1 = smem + L.tg_w1; ts_tg.w2 = smem + L.tg_w2;
+  ts_tg.vec = reinterpret_cast<float*>(smem + L.tg_vec);
+  ts_on.w0 = smem + L.on_w0; ts_on.w1 = smem + L.on_w1; ts_on.w2 = smem + L.on_w2;
+  ts_on.vec = reinterpret_cast<float*>(smem + L.on_vec);
+  ts_tg.bar = ts_on.bar = reinterpret_cast<uint64_t*>(smem + L.bar);
+  ts_tg.tmem_slot = ts_on.tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar + 8);
+  unsigned char* w1t = smem + L.w1t;
+  unsigned char* w0t = smem + L.w0t;
+  float* plain = reinterpret_cast<float*>(smem + L.plain);
+  float4* sst = reinterpret_cast<float4*>(smem + L.st);
+  TileGraphSmem g;
+  g.sh = nullptr;
+  g.sas = reinterpret_cast<float*>(smem + L.asrc);
+  g.swt = reinterpret_cast<float*>(smem + L.wt);
+  g.sin = smem + L.inl;
+  g.skv = reinterpret_cast<float*>(smem + L.kv);
+  g.ski = smem + L.ki;
+  g.snbr = smem + L.nbr;
+  float* mZ = reinterpret_cast<float*>(smem + L.mz);
+  float* sdq = reinterpret_cast<float*>(smem + L.sdq);
+  int* sact = reinterpret_cast<int*>(smem + L.sact);
+  float* sdasrc = reinterpret_cast<float*>(smem + L.sdasrc);
+  float* sdadst = reinterpret_cast<float*>(smem + L.sdadst);
+  float* sx = reinterpret_cast<float*>(smem + L.sx);
+  float* sxbar = reinterpret_cast<float*>(smem + L.xbar);
+  float* stage_all = reinterpret_cast<float*>(smem + L.stage);
+  float* buf0 = stage_all + (warp * 2 + 0) * kStageBuf;         // U, then (with buf1) this warp's partial
+  float* buf1 = stage_all + (warp * 2 + 1) * kStageBuf;         // R, then DP, then DO
+  float* sred = reinterpret_cast<float*>(smem + L.red);
+
+  // ---- the sampled transition of this node (loads in flight while the weights are staged) -------------------------
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s;
+  int act = 0;
+  float rew = 0.0f;
+  if (t.active) {
+    long long slot = t.env;
+    if (p.ctl) {
+      const uint64_t rnd = rng_draw(p.sample_seed, (uint64_t)t.env, (uint64_t)(p.ctl->tick + 1), 0x5A17u);
+      slot = (long long)__umul64hi(rnd, (uint64_t)ring_size);
+      if (p.indices_out && t.i == 0) p.indices_out[t.env] = slot;
+    } else if (p.indices) {
+      slot = p.indices[t.env];
+      slot = slot < 0 ? 0 : (slot >= p.batch.capacity ? p.batch.capacity - 1 : slot);
+    }
+    const long long ri = slot * N + t.i;
+    s = reinterpret_cast<const float4*>(p.batch.state)[ri];
+    s2 = reinterpret_cast<const float4*>(p.batch.next_state)[ri];
+    act = sanitize_action(p.batch.actions[ri]);
+    rew = p.batch.rewards[ri];
+  }
+
+  stage_weights_tc(p.w_target, ts_tg, tid, T);
+  stage_weights_tc(p.w_online, ts_on, tid, T);
+  stage_backward_tiles(p.w_online, w1t, w0t, plain, tid, T);
+  if (tid == 0) tc::mbar_init(ts_on.bar, 1);
+  if (warp == 0) tc::tmem_alloc(ts_on.tmem_slot, kTmemCols);
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *ts_on.tmem_slot;
+  const uint32_t lane_addr = tmem + ((uint32_t)(tid & ~31) << 16);
+  uint32_t parity = 0;
+
+  float u[32], r[32], xm[8];
+  float adst = 0.0f, inv = 0.0f, y = 0.0f, v_taken = 0.0f;
+  int deg = 0;
+
+  // target network on s' -> y = r + gamma * max_a Q_target(s')  (train:120-121); online network on s (train:119)
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const bool target_role = (pass == 0);
+    const float4 sp = target_role ? s2 : s;
+    const TileTcSmem& ts = target_role ? ts_tg : ts_on;
+    const float x[7] = {sp.x, sp.y, sp.z, sp.w, c.goal_x, c.goal_y, (float)t.i};
+    float asrc;
+    tc_alpha_terms(ts, x, asrc, adst);
+    // (the previous pass finished its reads of sst / sas before the barriers of its UMMA rounds)
+    sst[tid] = sp;
+    g.sas[tid] = asrc;
+    if (!target_role) {
+      float4* xr = reinterpret_cast<float4*>(sx + tid * 8);
+      xr[0] = make_float4(x[0], x[1], x[2], x[3]);
+      xr[1] = make_float4(x[4], x[5], x[6], 0.f);
+    }
+    __syncthreads();
+    if (!COMPLETE) {
+      if (knn && N <= kKnnSmallMax) {
+        uint64_t cache_rank = ~0ull, cache_nbr = 0;
+        const uint64_t nbr_word = tile_knn_small(t, sst, sp, N, K, cache_rank, cache_nbr);
+        deg = tile_in_edges_knn_small(g, t, N, K, nbr_word, reinterpret_cast<uint32_t*>(g.skv));
+      } else if (knn) {
+        tile_knn_rows(g, t, sst, sp, N, K);
+        deg = tile_in_edges_knn(g, t, N, K, reinterpret_cast<uint32_t*>(g.skv));
+      } else if (radius) {
+        deg = t.active ? tile_in_edges_radius(g, t, sst, sp, N, p.qmax_r) : 0;
+      }
+    }
+    inv = dqn_attend<COMPLETE>(g, t, sst, N, deg, adst, c.goal_x, c.goal_y, xm);
+    tc_store_a8(lane_addr, xm);
+    tc_mma_round(ts, tmem, tmem, ts.w0, kTcW0Bytes / 2, 32, 1, parity);
+    tc::tmem_ld32(lane_addr, u);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) u[k] = tanhf(__fadd_rn(u[k], ts.vec[TV_B0 + k]));
+    tc_store_a_row(lane_addr, u);
+    tc_mma_round(ts, tmem, tmem + 32, ts.w1, kTcW1Bytes / 2, 32, 4, parity);
+    tc::tmem_ld32(lane_addr + 32, r);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) r[k] = fmaxf(__fadd_rn(r[k], ts.vec[TV_B1 + k]), 0.0f);
+    tc_store_a_row(lane_addr, r);
+    tc_mma_round(ts, tmem, tmem, ts.w2, kTcW2Bytes / 2, 16, 4, parity);
+    float qq[16];
+    tc::tmem_ld16(lane_addr, qq);
+    if (target_role) {
+      float qmax = __fadd_rn(qq[0], ts.vec[TV_B2]);
+#pragma unroll
+      for (int a = 1; a < 9; ++a) qmax = fmaxf(qmax, __fadd_rn(qq[a], ts.vec[TV_B2 + a]));
+      y = __fadd_rn(rew, __fmul_rn(p.gamma, qmax));
+    } else {
+      v_taken = __fadd_rn(qq[0], ts.vec[TV_B2]);
+#pragma unroll
+      for (int a = 1; a < 9; ++a) v_taken = (act == a) ? __fadd_rn(qq[a], ts.vec[TV_B2 + a]) : v_taken;   // Q(s).gather(1, a)
+    }
+  }
+
+  // ---- TD error --------------------------------------------------------------------------------------------------
+  float delta = 0.0f, dq = 0.0f;
+  if (t.active) {
+    delta = __fsub_rn(v_taken, y);
+    dq = 2.0f * delta * p.loss_scale;             // d mean((v - y)^2) / dv
+    if (p.td) p.td[t.gidx] = delta;
+  }
+  sdq[tid] = dq;
+  sact[tid] = act;
+  stage_row(buf0, lane, u);
+  stage_row(buf1, lane, r);
+  {
+    float4* xb = reinterpret_cast<float4*>(sxbar + tid * 8);
+    xb[0] = make_float4(xm[0], xm[1], xm[2], xm[3]);
+    xb[1] = make_float4(xm[4], xm[5], xm[6], 0.f);
+  }
+  __syncwarp();
+
+  // ---- dW2 = sum_n dq_n e_{a_n} (x) r_n ;  d lin2.bias ---------------------------------------------------------------
+  float acc2[1][4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) acc2[0][nt][q4] = 0.0f;
+  {
+    const float* wdq = sdq + warp * 32;
+    const int* wact = sact + warp * 32;
+    warp_node_gemm<1, 4>(acc2, lane, [&](int n, int m) { return wact[n] == m ? wdq[n] : 0.0f; },
+                         [&](int n, int col) { return buf1[n * kStageLd + col]; });
+  }
+  float db2 = 0.0f;
+  if (lane < 9) {
+    for (int n = 0; n < 32; ++n) db2 += (sact[warp * 32 + n] == lane) ? sdq[warp * 32 + n] : 0.0f;
+  }
+
+  // ---- backward through lin2 / ReLU:  dp = (W2[a]^T dq) * [r > 0] --------------------------------------------------
+  float dvec[32];
+  {
+    const float4* w2a = reinterpret_cast<const float4*>(plain + PL_W2 + act * 32);
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+      const float4 w = w2a[k4];
+      dvec[4 * k4 + 0] = r[4 * k4 + 0] > 0.0f ? w.x * dq : 0.0f;
+      dvec[4 * k4 + 1] = r[4 * k4 + 1] > 0.0f ? w.y * dq : 0.0f;
+      dvec[4 * k4 + 2] = r[4 * k4 + 2] > 0.0f ? w.z * dq : 0.0f;
+      dvec[4 * k4 + 3] = r[4 * k4 + 3] > 0.0f ? w.w * dq : 0.0f;
+    }
+  }
+  __syncwarp();                                    // every lane is done with the R tile
+  stage_row(buf1, lane, dvec);
+  tc_store_a_row(lane_addr, dvec);
+  __syncwarp();
+
+  // ---- dW1 = sum_n dp_n (x) u_n ;  d lin1.bias ----------------------------------------------------------------------
+  float acc1[2][4][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) acc1[mt][nt][q4] = 0.0f;
+  warp_node_gemm<2, 4>(acc1, lane, [&](int n, int m) { return buf1[n * kStageLd + m]; },
+                       [&](int n, int col) { return buf0[n * kStageLd + col]; });
+  float db1 = 0.0f;
+  for (int n = 0; n < 32; ++n) db1 += buf1[n * kStageLd + lane];
+
+  // ---- du = W1^T dp (UMMA);  do = du * (1 - u^2) ---------------------------------------------------------------------
+  tc_mma_round(ts_on, tmem, tmem + 32, w1t, kTcW1tBytes / 2, 32, 4, parity);
+  tc::tmem_ld32(lane_addr + 32, dvec);
+#pragma unroll
+  for (int k = 0; k < 32; ++k) dvec[k] = dvec[k] * (1.0f - u[k] * u[k]);     // dvec = d(o_i) from here on
+  __syncwarp();                                    // every lane is done with the DP tile
+  stage_row(buf1, lane, dvec);
+  tc_store_a_row(lane_addr, dvec);
+  __syncwarp();
+
+  // ---- dW0 = sum_n do_n (x) xm_n ;  d conv1.bias --------------------------------------------------------------------
+  float acc0[2][1][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) acc0[mt][0][q4] = 0.0f;
+  {
+    const float* wxb = sxbar + warp * 32 * 8;
+    warp_node_gemm<2, 1>(acc0, lane, [&](int n, int m) { return buf1[n * kStageLd + m]; },
+                         [&](int n, int col) { return wxb[n * 8 + col]; });
+  }
+  float db0 = 0.0f;
+  for (int n = 0; n < 32; ++n) db0 += buf1[n * kStageLd + lane];
+
+  // ---- dxm = W0^T do (UMMA);  attention backward in input space ---------------------------------------------------------
+  tc_mma_round(ts_on, tmem, tmem, w0t, kTcW0tBytes / 2, 16, 4, parity);
+  float dxm[16];
+  tc::tmem_ld16(lane_addr, dxm);
+  float dadst = 0.0f;
+  {
+    const int T_ = T;
+    const float* __restrict__ sas = g.sas + t.envbase;
+    const float4* __restrict__ env = sst + t.envbase;
+    const float* __restrict__ swt = g.swt + tid;
+    const uint8_t* __restrict__ sin = g.sin + tid;
+    float* rz = mZ + (t.el * N + t.i) * N;
+    const int n_edges = COMPLETE ? (t.active ? N : 0) : deg;
+    if (!COMPLETE && t.active)
+      for (int j = 0; j < N; ++j) rz[j] = 0.0f;
+    const float cg = fmaf(dxm[4], c.goal_x, dxm[5] * c.goal_y);
+    auto dalpha = [&](int j) {
+      const float4 sj = env[j];
+      return fmaf(dxm[0], sj.x, fmaf(dxm[1], sj.y, fmaf(dxm[2], sj.z, fmaf(dxm[3], sj.w, fmaf(dxm[6], (float)j, cg)))));
+    };
+    // softmax backward: d z_e = alpha_e (d alpha_e - sum_e' alpha_e' d alpha_e')
+    float dot_sum = 0.0f;
+#pragma unroll 2
+    for (int e = 0; e < n_edges; ++e) {
+      const int j = COMPLETE ? e : (int)sin[e * T_];
+      dot_sum = fmaf(swt[e * T_] * inv, dalpha(j), dot_sum);
+    }
+#pragma unroll 2
+    for (int e = 0; e < n_edges; ++e) {
+      const int j = COMPLETE ? e : (int)sin[e * T_];
+      const float alpha = swt[e * T_] * inv;
+      const float dz = alpha * (dalpha(j) - dot_sum);
+      const float raw = __fadd_rn(sas[j], adst);
+      const float dzz = raw > 0.0f ? dz : 0.2f * dz;
+      if (COMPLETE) rz[j] = dzz;
+      else rz[j] += dzz;                          // parallel edges (duplicates, double self loops) accumulate
+      dadst += dzz;
+    }
+  }
+  sdadst[tid] = dadst;
+  __syncthreads();            // mZ complete (an env may straddle two warps)
+  {
+    float ds = 0.0f;
+    if (t.active)
+      for (int ii = 0; ii < N; ++ii) ds += mZ[(t.el * N + ii) * N + t.i];
+    sdasrc[tid] = ds;
+  }
+  __syncwarp();
+
+  // ---- dv_s = sum_j d alpha_src_j x_j,  dv_d = sum_i d alpha_dst_i x_i over this warp's nodes; squared TD errors -----
+  float dv = 0.0f;
+  if (lane < 16) {
+    const float* coef = (lane < 8 ? sdasrc : sdadst) + warp * 32;
+    const float* xr = sx + warp * 32 * 8 + (lane & 7);
+    for (int n = 0; n < 32; ++n) dv = fmaf(coef[n], xr[n * 8], dv);
+  }
+  float sse = delta * delta;
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) sse += __shfl_xor_sync(0xffffffffu, sse, sh);
+
+  // ---- this warp's partial into its own staging tiles (every lane is done reading them) ---------------------------
+  __syncwarp();
+  float* part = buf0;                              // buf0 and buf1 are contiguous
+  for (int o = lane; o < kPartCount; o += 32) part[o] = 0.0f;
+  __syncwarp();
+  {
+    const int gq = lane >> 2, tg = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int k0 = nt * 8 + 2 * tg;
+      if (gq < 9) {
+        part[SWARM_W_LIN2 + gq * 32 + k0] = acc2[0][nt][0];
+        part[SWARM_W_LIN2 + gq * 32 + k0 + 1] = acc2[0][nt][1];
+      }
+      if (gq + 8 < 9) {
+        part[SWARM_W_LIN2 + (gq + 8) * 32 + k0] = acc2[0][nt][2];
+        part[SWARM_W_LIN2 + (gq + 8) * 32 + k0 + 1] = acc2[0][nt][3];
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int c0 = mt * 16 + gq;
+        part[SWARM_W_LIN1 + c0 * 32 + k0] = acc1[mt][nt][0];
+        part[SWARM_W_LIN1 + c0 * 32 + k0 + 1] = acc1[mt][nt][1];
+        part[SWARM_W_LIN1 + (c0 + 8) * 32 + k0] = acc1[mt][nt][2];
+        part[SWARM_W_LIN1 + (c0 + 8) * 32 + k0 + 1] = acc1[mt][nt][3];
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int c0 = mt * 16 + gq, k0 = 2 * tg;
+      if (k0 < 7) {
+        part[SWARM_W_CONV_LIN + c0 * 7 + k0] = acc0[mt][0][0];
+        part[SWARM_W_CONV_LIN + (c0 + 8) * 7 + k0] = acc0[mt][0][2];
+      }
+      if (k0 + 1 < 7) {
+        part[SWARM_W_CONV_LIN + c0 * 7 + k0 + 1] = acc0[mt][0][1];
+        part[SWARM_W_CONV_LIN + (c0 + 8) * 7 + k0 + 1] = acc0[mt][0][3];
+      }
+    }
+    part[SWARM_W_LIN1_BIAS + lane] = db1;
+    part[SWARM_W_CONV_BIAS + lane] = db0;
+    if (lane < 9) part[SWARM_W_LIN2_BIAS + lane] = db2;
+    if (lane < 8) part[kPartDvS + lane] = dv;
+    else if (lane < 16) part[kPartDvD + (lane - 8)] = dv;
+    if (lane == 0) part[kPartSse] = sse;
+  }
+  __syncthreads();
+
+  // ---- warp partials added in warp order; the attention vectors' gradients through v = W0^T att ------------------------
+  auto warp_sum = [&](int o) {
+    float a = stage_all[0 * 2 * kStageBuf + o];
+    a += stage_all[1 * 2 * kStageBuf + o];
+    a += stage_all[2 * 2 * kStageBuf + o];
+    a += stage_all[3 * 2 * kStageBuf + o];
+    return a;
+  };
+  if (tid < 16) plain[PL_DV + tid] = warp_sum(kPartDvS + tid);         // dv_s[8] and dv_d[8] are contiguous
+  __syncthreads();
+  const float* dvs = plain + PL_DV;
+  const float* dvd = plain + PL_DV + 8;
+  float* out = p.partials + (long long)blockIdx.x * kPartialStride;
+  for (int o = tid; o <= SWARM_W_COUNT; o += T) {
+    float val;
+    if (o < SWARM_W_ATT_SRC) {                                  // conv1.lin.weight[c][k] += att_s[c] dv_s[k] + att_d[c] dv_d[k]
+      const int cc = o / 7, k = o - cc * 7;
+      val = warp_sum(o) + plain[PL_ATT_S + cc] * dvs[k] + plain[PL_ATT_D + cc] * dvd[k];
+    } else if (o < SWARM_W_CONV_BIAS) {                         // d att_src[c] = sum_k W0[c][k] dv_s[k]  (att_dst alike)
+      const bool src = o < SWARM_W_ATT_DST;
+      const int cc = o - (src ? SWARM_W_ATT_SRC : SWARM_W_ATT_DST);
+      const float* dvv = src ? dvs : dvd;
+      val = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) val = fmaf(plain[PL_W0 + cc * 7 + k], dvv[k], val);
+    } else {
+      val = warp_sum(o);                                        // o == SWARM_W_COUNT: sum of squared TD errors
+    }
+    out[o] = val;
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, kTmemCols);
+}
+
+int dqn_maxdeg(const SwarmConfig& c);
+int dqn_epb(const SwarmConfig& c, int n_graphs);
+
+bool dqn_tc_enabled() {
+  static const char* tc_env = std::getenv("SWARM_TC");
+  return !(tc_env && tc_env[0] == '0');
+}
+
+int dqn_tc_smem_bytes(const SwarmConfig& c) {
+  return dqn_tc_layout(c.n_agents, c.knn_k, dqn_maxdeg(c), kTileThreads / c.n_agents, c.graph_mode).total;
+}
+
+cudaError_t launch_dqn_grad_tc(DqnParams& p, cudaStream_t stream) {
+  const SwarmConfig& c = p.cfg;
+  p.parallel = 0;
+  const int smem = dqn_tc_layout(c.n_agents, c.knn_k, p.maxdeg, p.epb, c.graph_mode).total;
+  const int ctas = (p.n_graphs + p.epb - 1) / p.epb;
+  cudaError_t err;
+  if (c.graph_mode == SWARM_GRAPH_COMPLETE) {
+    err = cudaFuncSetAttribute(dqn_grad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return err;
+    dqn_grad_tc_kernel<true><<<ctas, kTileThreads, smem, stream>>>(p);
+  } else {
+    err = cudaFuncSetAttribute(dqn_grad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return err;
+    dqn_grad_tc_kernel<false><<<ctas, kTileThreads, smem, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace swarm
