@@ -76,35 +76,61 @@ __host__ __device__ inline DqnTcLayout dqn_tc_layout(int n, int k, int maxdeg, i
 // w1t: B[n = k][K = c] = W1[c][k]  (du = W1^T dp);  w0t: B[n = k < 7, padded to 16][K = c] = W0[c][k]  (dxm = W0^T do)
 __device__ __forceinline__ void stage_backward_tiles(const float* __restrict__ gw, unsigned char* w1t, unsigned char* w0t,
                                                      float* plain, int tid, int nthreads) {
-  for (int it = tid; it < 256 + 128; it += nthreads) {
+  // every global load of the thread is issued before its first shared-memory store (one exposed round trip to L2
+  // instead of eight: the destinations are char / float pointers the compiler must assume to alias the source)
+  constexpr int kItems = (256 + 128) / kTileThreads;                    // 3
+  constexpr int kPlain = (PL_DV + kTileThreads - 1) / kTileThreads;     // 5
+  float4 item[kItems];
+  float pv[kPlain];
+#pragma unroll
+  for (int q = 0; q < kItems; ++q) {
+    const int it = tid + q * nthreads;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    unsigned char* base;
-    int rows, n, c, half;
     if (it < 256) {
-      n = it >> 3; c = it & 7; rows = 32; base = w1t; half = kTcW1tBytes / 2;
+      const int n = it >> 3, c = it & 7;
       const float* col = gw + SWARM_W_LIN1 + n;                 // W1[4c + j][n]
       v = make_float4(col[(4 * c + 0) * 32], col[(4 * c + 1) * 32], col[(4 * c + 2) * 32], col[(4 * c + 3) * 32]);
-    } else {
-      const int j = it - 256;
-      n = j >> 3; c = j & 7; rows = 16; base = w0t; half = kTcW0tBytes / 2;
+    } else if (it < 384) {
+      const int j = it - 256, n = j >> 3, c = j & 7;
       if (n < 7) {
         const float* col = gw + SWARM_W_CONV_LIN + n;           // W0[4c + j][n]
         v = make_float4(col[(4 * c + 0) * 7], col[(4 * c + 1) * 7], col[(4 * c + 2) * 7], col[(4 * c + 3) * 7]);
       }
     }
+    item[q] = v;
+  }
+#pragma unroll
+  for (int q = 0; q < kPlain; ++q) {
+    const int o = tid + q * nthreads;
+    float v = 0.0f;
+    if (o < PL_ATT_S) v = gw[SWARM_W_LIN2 + o];
+    else if (o < PL_ATT_D) v = gw[SWARM_W_ATT_SRC + (o - PL_ATT_S)];
+    else if (o < PL_W0) v = gw[SWARM_W_ATT_DST + (o - PL_ATT_D)];
+    else if (o < PL_DV) v = gw[SWARM_W_CONV_LIN + (o - PL_W0)];
+    pv[q] = v;
+  }
+#pragma unroll
+  for (int q = 0; q < kItems; ++q) {
+    const int it = tid + q * nthreads;
+    if (it >= 384) break;
+    unsigned char* base;
+    int rows, n, c, half;
+    if (it < 256) {
+      n = it >> 3; c = it & 7; rows = 32; base = w1t; half = kTcW1tBytes / 2;
+    } else {
+      const int j = it - 256;
+      n = j >> 3; c = j & 7; rows = 16; base = w0t; half = kTcW0tBytes / 2;
+    }
     float4 hi, lo;
-    tc::split4(v, hi, lo);
+    tc::split4(item[q], hi, lo);
     const int off = tc::tile_off(rows, n, c);
     *reinterpret_cast<float4*>(base + off) = hi;
     *reinterpret_cast<float4*>(base + half + off) = lo;
   }
-  for (int o = tid; o < PL_DV; o += nthreads) {
-    float v;
-    if (o < PL_ATT_S) v = gw[SWARM_W_LIN2 + o];
-    else if (o < PL_ATT_D) v = gw[SWARM_W_ATT_SRC + (o - PL_ATT_S)];
-    else if (o < PL_W0) v = gw[SWARM_W_ATT_DST + (o - PL_ATT_D)];
-    else v = gw[SWARM_W_CONV_LIN + (o - PL_W0)];
-    plain[o] = v;
+#pragma unroll
+  for (int q = 0; q < kPlain; ++q) {
+    const int o = tid + q * nthreads;
+    if (o < PL_DV) plain[o] = pv[q];
   }
 }
 
@@ -338,8 +364,27 @@ __global__ void __launch_bounds__(kTileThreads, 2) dqn_grad_tc_kernel(const __gr
     tc_store_a8(lane_addr, xm);
     tc_mma_round(ts, tmem, tmem, ts.w0, kTcW0Bytes / 2, 32, 1, parity);
     tc::tmem_ld32(lane_addr, u);
+    {
+      // u = tanh(o) = 1 - 2 / (exp(2 o) + 1) on the SFU like the rollout's forward (absolute error ~1e-7; tanhf costs
+      // 17 instructions per channel and was a sixth of this kernel)
+      const float4* b4 = reinterpret_cast<const float4*>(ts.vec + TV_B0);
+      const float2 two_log2e = make_float2(2.0f * 1.4426950408889634f, 2.0f * 1.4426950408889634f);
+      const float2 one = make_float2(1.0f, 1.0f), neg2 = make_float2(-2.0f, -2.0f);
 #pragma unroll
-    for (int k = 0; k < 32; ++k) u[k] = tanhf(__fadd_rn(u[k], ts.vec[TV_B0 + k]));
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 b = b4[c4];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int k = 4 * c4 + 2 * h2;
+          const float2 bb = h2 == 0 ? make_float2(b.x, b.y) : make_float2(b.z, b.w);
+          const float2 z = __fmul2_rn(__fadd2_rn(make_float2(u[k], u[k + 1]), bb), two_log2e);
+          const float2 e = __fadd2_rn(make_float2(exp2f_approx(z.x), exp2f_approx(z.y)), one);
+          const float2 uu = __ffma2_rn(neg2, make_float2(rcp_approx(e.x), rcp_approx(e.y)), one);
+          u[k] = uu.x;
+          u[k + 1] = uu.y;
+        }
+      }
+    }
     tc_store_a_row(lane_addr, u);
     tc_mma_round(ts, tmem, tmem + 32, ts.w1, kTcW1Bytes / 2, 32, 4, parity);
     tc::tmem_ld32(lane_addr + 32, r);
