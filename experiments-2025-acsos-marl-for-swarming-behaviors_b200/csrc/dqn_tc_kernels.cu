@@ -74,14 +74,14 @@ __host__ __device__ inline DqnTcLayout dqn_tc_layout(int n, int k, int maxdeg, i
 
 // ---- extra B tiles of the backward pass --------------------------------------------------------------------------
 // w1t: B[n = k][K = c] = W1[c][k]  (du = W1^T dp);  w0t: B[n = k < 7, padded to 16][K = c] = W0[c][k]  (dxm = W0^T do)
-__device__ __forceinline__ void stage_backward_tiles(const float* __restrict__ gw, unsigned char* w1t, unsigned char* w0t,
-                                                     float* plain, int tid, int nthreads) {
-  // every global load of the thread is issued before its first shared-memory store (one exposed round trip to L2
-  // instead of eight: the destinations are char / float pointers the compiler must assume to alias the source)
-  constexpr int kItems = (256 + 128) / kTileThreads;                    // 3
-  constexpr int kPlain = (PL_DV + kTileThreads - 1) / kTileThreads;     // 5
-  float4 item[kItems];
-  float pv[kPlain];
+struct BwdStageRegs {
+  float4 item[(256 + 128) / kTileThreads];                     // 3
+  float pv[(PL_DV + kTileThreads - 1) / kTileThreads];         // 5
+};
+
+__device__ __forceinline__ void stage_backward_load(const float* __restrict__ gw, BwdStageRegs& r, int tid, int nthreads) {
+  constexpr int kItems = (256 + 128) / kTileThreads;
+  constexpr int kPlain = (PL_DV + kTileThreads - 1) / kTileThreads;
 #pragma unroll
   for (int q = 0; q < kItems; ++q) {
     const int it = tid + q * nthreads;
@@ -97,7 +97,7 @@ __device__ __forceinline__ void stage_backward_tiles(const float* __restrict__ g
         v = make_float4(col[(4 * c + 0) * 7], col[(4 * c + 1) * 7], col[(4 * c + 2) * 7], col[(4 * c + 3) * 7]);
       }
     }
-    item[q] = v;
+    r.item[q] = v;
   }
 #pragma unroll
   for (int q = 0; q < kPlain; ++q) {
@@ -107,8 +107,14 @@ __device__ __forceinline__ void stage_backward_tiles(const float* __restrict__ g
     else if (o < PL_ATT_D) v = gw[SWARM_W_ATT_SRC + (o - PL_ATT_S)];
     else if (o < PL_W0) v = gw[SWARM_W_ATT_DST + (o - PL_ATT_D)];
     else if (o < PL_DV) v = gw[SWARM_W_CONV_LIN + (o - PL_W0)];
-    pv[q] = v;
+    r.pv[q] = v;
   }
+}
+
+__device__ __forceinline__ void stage_backward_store(const BwdStageRegs& r, unsigned char* w1t, unsigned char* w0t, float* plain,
+                                                     int tid, int nthreads) {
+  constexpr int kItems = (256 + 128) / kTileThreads;
+  constexpr int kPlain = (PL_DV + kTileThreads - 1) / kTileThreads;
 #pragma unroll
   for (int q = 0; q < kItems; ++q) {
     const int it = tid + q * nthreads;
@@ -122,7 +128,7 @@ __device__ __forceinline__ void stage_backward_tiles(const float* __restrict__ g
       n = j >> 3; c = j & 7; rows = 16; base = w0t; half = kTcW0tBytes / 2;
     }
     float4 hi, lo;
-    tc::split4(item[q], hi, lo);
+    tc::split4(r.item[q], hi, lo);
     const int off = tc::tile_off(rows, n, c);
     *reinterpret_cast<float4*>(base + off) = hi;
     *reinterpret_cast<float4*>(base + half + off) = lo;
@@ -130,7 +136,7 @@ __device__ __forceinline__ void stage_backward_tiles(const float* __restrict__ g
 #pragma unroll
   for (int q = 0; q < kPlain; ++q) {
     const int o = tid + q * nthreads;
-    if (o < PL_DV) plain[o] = pv[q];
+    if (o < PL_DV) plain[o] = r.pv[q];
   }
 }
 
@@ -188,7 +194,7 @@ __device__ __forceinline__ void stage_row(float* buf, int lane, const float (&v)
 // softmax weights and weighted mean of the neighbours' input features, keeping what the backward pass needs:
 // the unnormalised weights w_e in swt[e][tid] and 1 / (sum + 1e-16).  Exact expf / division here -- the TD error is a
 // small difference of large Q values, so the forward pass of the update keeps float32-level accuracy throughout.
-template <bool COMPLETE>
+template <bool COMPLETE, bool KEEP>
 __device__ __forceinline__ float dqn_attend(const TileGraphSmem& g, const TileThread& t, const float4* __restrict__ pos,
                                             int N, int deg, float adst, float goal_x, float goal_y, float (&xm)[8]) {
   const int T = kTileThreads;
@@ -215,7 +221,7 @@ __device__ __forceinline__ float dqn_attend(const TileGraphSmem& g, const TileTh
     const float zz = __fadd_rn(sas[j], adst);
     float w = expf(__fsub_rn(fmaxf(zz, __fmul_rn(zz, 0.2f)), m));
     if (COMPLETE && j == self) w = 0.0f;
-    swt[e * T] = w;
+    if (KEEP) swt[e * T] = w;
     const float2 w2 = make_float2(w, w);
     den = __fadd_rn(den, w);
     acc_p = __ffma2_rn(w2, make_float2(sj.x, sj.y), acc_p);
@@ -229,6 +235,56 @@ __device__ __forceinline__ float dqn_attend(const TileGraphSmem& g, const TileTh
   return inv;
 }
 
+// complete graph, online and target pass in one loop (two independent dependency chains per iteration)
+__device__ __forceinline__ float dqn_attend_pair(const TileGraphSmem& go, const TileGraphSmem& gt, const TileThread& t,
+                                                 const float4* __restrict__ pos_o, const float4* __restrict__ pos_t, int N,
+                                                 float adst_o, float adst_t, float goal_x, float goal_y, float (&xo)[8],
+                                                 float (&xt)[8]) {
+  const int T = kTileThreads;
+  const float* __restrict__ sas_o = go.sas + t.envbase;
+  const float* __restrict__ sas_t = gt.sas + t.envbase;
+  const float4* __restrict__ env_o = pos_o + t.envbase;
+  const float4* __restrict__ env_t = pos_t + t.envbase;
+  float* __restrict__ swt = go.swt + t.tid;
+  const int self = (t.i == 0) ? -1 : t.i;
+  const int n = t.active ? N : 0;
+  float amax_o = -INFINITY, amax_t = -INFINITY;
+#pragma unroll 4
+  for (int j = 0; j < n; ++j) {
+    amax_o = fmaxf(amax_o, j == self ? -INFINITY : sas_o[j]);
+    amax_t = fmaxf(amax_t, j == self ? -INFINITY : sas_t[j]);
+  }
+  const float zo = __fadd_rn(amax_o, adst_o), zt = __fadd_rn(amax_t, adst_t);
+  const float mo = fmaxf(zo, __fmul_rn(zo, 0.2f)), mt = fmaxf(zt, __fmul_rn(zt, 0.2f));
+  float den_o = 0.0f, den_t = 0.0f, id_o = 0.0f, id_t = 0.0f, fj = 0.0f;
+  float2 po = make_float2(0.f, 0.f), vo = po, pt = po, vt = po;
+#pragma unroll 4
+  for (int j = 0; j < n; ++j) {
+    const float4 so = env_o[j], st = env_t[j];
+    const float ao = __fadd_rn(sas_o[j], adst_o), at = __fadd_rn(sas_t[j], adst_t);
+    float wo = expf(__fsub_rn(fmaxf(ao, __fmul_rn(ao, 0.2f)), mo));
+    float wt = expf(__fsub_rn(fmaxf(at, __fmul_rn(at, 0.2f)), mt));
+    if (j == self) { wo = 0.0f; wt = 0.0f; }
+    swt[j * T] = wo;
+    den_o = __fadd_rn(den_o, wo);
+    den_t = __fadd_rn(den_t, wt);
+    po = __ffma2_rn(make_float2(wo, wo), make_float2(so.x, so.y), po);
+    vo = __ffma2_rn(make_float2(wo, wo), make_float2(so.z, so.w), vo);
+    pt = __ffma2_rn(make_float2(wt, wt), make_float2(st.x, st.y), pt);
+    vt = __ffma2_rn(make_float2(wt, wt), make_float2(st.z, st.w), vt);
+    id_o = fmaf(wo, fj, id_o);
+    id_t = fmaf(wt, fj, id_t);
+    fj += 1.0f;
+  }
+  const float inv_o = __fdiv_rn(1.0f, __fadd_rn(den_o, 1e-16f)), inv_t = __fdiv_rn(1.0f, __fadd_rn(den_t, 1e-16f));
+  const float ws_o = den_o * inv_o, ws_t = den_t * inv_t;
+  xo[0] = po.x * inv_o; xo[1] = po.y * inv_o; xo[2] = vo.x * inv_o; xo[3] = vo.y * inv_o;
+  xo[4] = goal_x * ws_o; xo[5] = goal_y * ws_o; xo[6] = id_o * inv_o; xo[7] = 0.0f;
+  xt[0] = pt.x * inv_t; xt[1] = pt.y * inv_t; xt[2] = vt.x * inv_t; xt[3] = vt.y * inv_t;
+  xt[4] = goal_x * ws_t; xt[5] = goal_y * ws_t; xt[6] = id_t * inv_t; xt[7] = 0.0f;
+  return inv_o;
+}
+
 __device__ __forceinline__ void tc_store_a8(uint32_t lane_addr, const float (&v)[8]) {
   float4 h0, l0, h1, l1;
   tc::split4(make_float4(v[0], v[1], v[2], v[3]), h0, l0);
@@ -240,6 +296,62 @@ __device__ __forceinline__ void tc_store_a8(uint32_t lane_addr, const float (&v)
   tc::tmem_st8(lane_addr + kTmemAHi, hi);
   tc::tmem_st8(lane_addr + kTmemALo, lo);
   tc::tmem_wait_st();
+}
+
+// TMEM columns: the online network uses [0, 128) as in the rollout (D tiles [0, 64), A hi / lo [64, 128)), the target
+// network the same layout 128 columns further on, so both forward passes advance together: every thread writes both
+// operand rows, ONE round issues the two 3xTF32 products (target weights for the target rows, online weights for the
+// online rows) behind one barrier and one mbarrier wait.  Halves the number of round trips of the forward passes and
+// gives each thread two independent epilogue chains.
+constexpr int kDqnTmemCols = 256;
+constexpr uint32_t kTmemTarget = 128;
+
+__device__ __forceinline__ void tc_mma_round2(uint64_t* bar, uint32_t tmem, uint32_t d_off, const unsigned char* b_on,
+                                              const unsigned char* b_tg, int b_half, int b_rows, int ksteps,
+                                              uint32_t& parity) {
+  tc::fence_before_sync();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) {
+    tc::fence_after_sync();
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::make_idesc_tf32(b_rows);
+      const uint32_t bo = tc::smem_u32(b_on), bt = tc::smem_u32(b_tg);
+      tc::mma_3xtf32_tmem_a(tmem + kTmemTarget + d_off, tmem + kTmemTarget + kTmemAHi, tmem + kTmemTarget + kTmemALo, bt,
+                            bt + b_half, b_rows, ksteps, idesc);
+      tc::mma_3xtf32_tmem_a(tmem + d_off, tmem + kTmemAHi, tmem + kTmemALo, bo, bo + b_half, b_rows, ksteps, idesc);
+      tc::mma_commit(bar);
+    }
+    __syncwarp();
+  }
+  tc::mbar_wait(bar, parity);
+  parity ^= 1u;
+  tc::fence_after_sync();
+}
+
+// u = tanh(o + b0) = 1 - 2 / (exp(2 (o + b0)) + 1) on the SFU like the rollout's forward (absolute error ~1e-7; tanhf
+// costs 17 instructions per channel and was a sixth of this kernel)
+__device__ __forceinline__ void dqn_tanh_bias(float (&u)[32], const float* __restrict__ b0) {
+  const float4* b4 = reinterpret_cast<const float4*>(b0);
+  const float2 two_log2e = make_float2(2.0f * 1.4426950408889634f, 2.0f * 1.4426950408889634f);
+  const float2 one = make_float2(1.0f, 1.0f), neg2 = make_float2(-2.0f, -2.0f);
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4) {
+    const float4 b = b4[c4];
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int k = 4 * c4 + 2 * h2;
+      const float2 bb = h2 == 0 ? make_float2(b.x, b.y) : make_float2(b.z, b.w);
+      const float2 z = __fmul2_rn(__fadd2_rn(make_float2(u[k], u[k + 1]), bb), two_log2e);
+      const float2 e = __fadd2_rn(make_float2(exp2f_approx(z.x), exp2f_approx(z.y)), one);
+      const float2 uu = __ffma2_rn(neg2, make_float2(rcp_approx(e.x), rcp_approx(e.y)), one);
+      u[k] = uu.x;
+      u[k + 1] = uu.y;
+    }
+  }
+}
+__device__ __forceinline__ void dqn_relu_bias(float (&r)[32], const float* __restrict__ b1) {
+#pragma unroll
+  for (int k = 0; k < 32; ++k) r[k] = fmaxf(__fadd_rn(r[k], b1[k]), 0.0f);
 }
 
 template <bool COMPLETE>
@@ -313,11 +425,20 @@ __global__ void __launch_bounds__(kTileThreads, 2) dqn_grad_tc_kernel(const __gr
     rew = p.batch.rewards[ri];
   }
 
-  stage_weights_tc(p.w_target, ts_tg, tid, T);
-  stage_weights_tc(p.w_online, ts_on, tid, T);
-  stage_backward_tiles(p.w_online, w1t, w0t, plain, tid, T);
+  {
+    // all global loads of the three weight sets first (the v_s / v_d chains of the two networks on warps 0 and 1; the vector block takes 96 threads),
+    // then the shared-memory stores: one exposed round trip to L2 for the whole prologue
+    TcStageRegs rt, ro;
+    BwdStageRegs rb;
+    stage_weights_tc_load(p.w_target, rt, tid, T, tid - 32);
+    stage_weights_tc_load(p.w_online, ro, tid, T, tid);
+    stage_backward_load(p.w_online, rb, tid, T);
+    stage_weights_tc_store(rt, ts_tg, tid, T, tid - 32);
+    stage_weights_tc_store(ro, ts_on, tid, T, tid);
+    stage_backward_store(rb, w1t, w0t, plain, tid, T);
+  }
   if (tid == 0) tc::mbar_init(ts_on.bar, 1);
-  if (warp == 0) tc::tmem_alloc(ts_on.tmem_slot, kTmemCols);
+  if (warp == 0) tc::tmem_alloc(ts_on.tmem_slot, kDqnTmemCols);
   tc::fence_async_smem();
   tc::fence_before_sync();
   __syncthreads();
@@ -330,80 +451,80 @@ __global__ void __launch_bounds__(kTileThreads, 2) dqn_grad_tc_kernel(const __gr
   float adst = 0.0f, inv = 0.0f, y = 0.0f, v_taken = 0.0f;
   int deg = 0;
 
-  // target network on s' -> y = r + gamma * max_a Q_target(s')  (train:120-121); online network on s (train:119)
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    const bool target_role = (pass == 0);
-    const float4 sp = target_role ? s2 : s;
-    const TileTcSmem& ts = target_role ? ts_tg : ts_on;
-    const float x[7] = {sp.x, sp.y, sp.z, sp.w, c.goal_x, c.goal_y, (float)t.i};
-    float asrc;
-    tc_alpha_terms(ts, x, asrc, adst);
-    // (the previous pass finished its reads of sst / sas before the barriers of its UMMA rounds)
-    sst[tid] = sp;
-    g.sas[tid] = asrc;
-    if (!target_role) {
+  // target network on s' -> y = r + gamma * max_a Q_target(s')  (train:120-121) and online network on s (train:119),
+  // advancing together.  The target pass's state / alpha_src / edge list live in the (still unused) staging tiles.
+  {
+    float4* sst_t = reinterpret_cast<float4*>(stage_all);
+    TileGraphSmem gt = g;
+    gt.sas = stage_all + 4 * T;
+    gt.sin = reinterpret_cast<uint8_t*>(stage_all + 5 * T);
+    const float x_o[7] = {s.x, s.y, s.z, s.w, c.goal_x, c.goal_y, (float)t.i};
+    const float x_t[7] = {s2.x, s2.y, s2.z, s2.w, c.goal_x, c.goal_y, (float)t.i};
+    float asrc_o, asrc_t, adst_t;
+    tc_alpha_terms(ts_on, x_o, asrc_o, adst);
+    tc_alpha_terms(ts_tg, x_t, asrc_t, adst_t);
+    sst[tid] = s;
+    g.sas[tid] = asrc_o;
+    sst_t[tid] = s2;
+    gt.sas[tid] = asrc_t;
+    {
       float4* xr = reinterpret_cast<float4*>(sx + tid * 8);
-      xr[0] = make_float4(x[0], x[1], x[2], x[3]);
-      xr[1] = make_float4(x[4], x[5], x[6], 0.f);
+      xr[0] = make_float4(x_o[0], x_o[1], x_o[2], x_o[3]);
+      xr[1] = make_float4(x_o[4], x_o[5], x_o[6], 0.f);
     }
     __syncthreads();
+    int deg_t = 0;
     if (!COMPLETE) {
-      if (knn && N <= kKnnSmallMax) {
-        uint64_t cache_rank = ~0ull, cache_nbr = 0;
-        const uint64_t nbr_word = tile_knn_small(t, sst, sp, N, K, cache_rank, cache_nbr);
-        deg = tile_in_edges_knn_small(g, t, N, K, nbr_word, reinterpret_cast<uint32_t*>(g.skv));
-      } else if (knn) {
-        tile_knn_rows(g, t, sst, sp, N, K);
-        deg = tile_in_edges_knn(g, t, N, K, reinterpret_cast<uint32_t*>(g.skv));
-      } else if (radius) {
-        deg = t.active ? tile_in_edges_radius(g, t, sst, sp, N, p.qmax_r) : 0;
-      }
-    }
-    inv = dqn_attend<COMPLETE>(g, t, sst, N, deg, adst, c.goal_x, c.goal_y, xm);
-    tc_store_a8(lane_addr, xm);
-    tc_mma_round(ts, tmem, tmem, ts.w0, kTcW0Bytes / 2, 32, 1, parity);
-    tc::tmem_ld32(lane_addr, u);
-    {
-      // u = tanh(o) = 1 - 2 / (exp(2 o) + 1) on the SFU like the rollout's forward (absolute error ~1e-7; tanhf costs
-      // 17 instructions per channel and was a sixth of this kernel)
-      const float4* b4 = reinterpret_cast<const float4*>(ts.vec + TV_B0);
-      const float2 two_log2e = make_float2(2.0f * 1.4426950408889634f, 2.0f * 1.4426950408889634f);
-      const float2 one = make_float2(1.0f, 1.0f), neg2 = make_float2(-2.0f, -2.0f);
-#pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 b = b4[c4];
-#pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-          const int k = 4 * c4 + 2 * h2;
-          const float2 bb = h2 == 0 ? make_float2(b.x, b.y) : make_float2(b.z, b.w);
-          const float2 z = __fmul2_rn(__fadd2_rn(make_float2(u[k], u[k + 1]), bb), two_log2e);
-          const float2 e = __fadd2_rn(make_float2(exp2f_approx(z.x), exp2f_approx(z.y)), one);
-          const float2 uu = __ffma2_rn(neg2, make_float2(rcp_approx(e.x), rcp_approx(e.y)), one);
-          u[k] = uu.x;
-          u[k + 1] = uu.y;
+      auto in_edges = [&](const TileGraphSmem& gg, const float4* pos, const float4& sp) -> int {
+        if (knn && N <= kKnnSmallMax) {
+          uint64_t cache_rank = ~0ull, cache_nbr = 0;
+          const uint64_t nbr_word = tile_knn_small(t, pos, sp, N, K, cache_rank, cache_nbr);
+          return tile_in_edges_knn_small(gg, t, N, K, nbr_word, reinterpret_cast<uint32_t*>(gg.skv));
+        } else if (knn) {
+          tile_knn_rows(gg, t, pos, sp, N, K);
+          return tile_in_edges_knn(gg, t, N, K, reinterpret_cast<uint32_t*>(gg.skv));
         }
-      }
+        return t.active ? tile_in_edges_radius(gg, t, pos, sp, N, p.qmax_r) : 0;
+      };
+      deg_t = in_edges(gt, sst_t, s2);
+      __syncthreads();                             // the kNN scratch is shared by the two builds
+      deg = in_edges(g, sst, s);
     }
-    tc_store_a_row(lane_addr, u);
-    tc_mma_round(ts, tmem, tmem + 32, ts.w1, kTcW1Bytes / 2, 32, 4, parity);
-    tc::tmem_ld32(lane_addr + 32, r);
-#pragma unroll
-    for (int k = 0; k < 32; ++k) r[k] = fmaxf(__fadd_rn(r[k], ts.vec[TV_B1 + k]), 0.0f);
-    tc_store_a_row(lane_addr, r);
-    tc_mma_round(ts, tmem, tmem, ts.w2, kTcW2Bytes / 2, 16, 4, parity);
-    float qq[16];
-    tc::tmem_ld16(lane_addr, qq);
-    if (target_role) {
-      float qmax = __fadd_rn(qq[0], ts.vec[TV_B2]);
-#pragma unroll
-      for (int a = 1; a < 9; ++a) qmax = fmaxf(qmax, __fadd_rn(qq[a], ts.vec[TV_B2 + a]));
-      y = __fadd_rn(rew, __fmul_rn(p.gamma, qmax));
+    float xm_t[8];
+    if (COMPLETE) {
+      inv = dqn_attend_pair(g, gt, t, sst, sst_t, N, adst, adst_t, c.goal_x, c.goal_y, xm, xm_t);
     } else {
-      v_taken = __fadd_rn(qq[0], ts.vec[TV_B2]);
-#pragma unroll
-      for (int a = 1; a < 9; ++a) v_taken = (act == a) ? __fadd_rn(qq[a], ts.vec[TV_B2 + a]) : v_taken;   // Q(s).gather(1, a)
+      dqn_attend<COMPLETE, false>(gt, t, sst_t, N, deg_t, adst_t, c.goal_x, c.goal_y, xm_t);
+      inv = dqn_attend<COMPLETE, true>(g, t, sst, N, deg, adst, c.goal_x, c.goal_y, xm);
     }
+    tc_store_a8(lane_addr + kTmemTarget, xm_t);
+    tc_store_a8(lane_addr, xm);
+    tc_mma_round2(ts_on.bar, tmem, 0, ts_on.w0, ts_tg.w0, kTcW0Bytes / 2, 32, 1, parity);
+    float ut[32];
+    tc::tmem_ld32(lane_addr + kTmemTarget, ut);
+    tc::tmem_ld32(lane_addr, u);
+    dqn_tanh_bias(ut, ts_tg.vec + TV_B0);
+    dqn_tanh_bias(u, ts_on.vec + TV_B0);
+    tc_store_a_row(lane_addr + kTmemTarget, ut);
+    tc_store_a_row(lane_addr, u);
+    tc_mma_round2(ts_on.bar, tmem, 32, ts_on.w1, ts_tg.w1, kTcW1Bytes / 2, 32, 4, parity);
+    tc::tmem_ld32(lane_addr + kTmemTarget + 32, ut);
+    tc::tmem_ld32(lane_addr + 32, r);
+    dqn_relu_bias(ut, ts_tg.vec + TV_B1);
+    dqn_relu_bias(r, ts_on.vec + TV_B1);
+    tc_store_a_row(lane_addr + kTmemTarget, ut);
+    tc_store_a_row(lane_addr, r);
+    tc_mma_round2(ts_on.bar, tmem, 0, ts_on.w2, ts_tg.w2, kTcW2Bytes / 2, 16, 4, parity);
+    float qt[16], qo[16];
+    tc::tmem_ld16(lane_addr + kTmemTarget, qt);
+    tc::tmem_ld16(lane_addr, qo);
+    float qmax = __fadd_rn(qt[0], ts_tg.vec[TV_B2]);
+#pragma unroll
+    for (int a = 1; a < 9; ++a) qmax = fmaxf(qmax, __fadd_rn(qt[a], ts_tg.vec[TV_B2 + a]));
+    y = __fadd_rn(rew, __fmul_rn(p.gamma, qmax));
+    v_taken = __fadd_rn(qo[0], ts_on.vec[TV_B2]);
+#pragma unroll
+    for (int a = 1; a < 9; ++a) v_taken = (act == a) ? __fadd_rn(qo[a], ts_on.vec[TV_B2 + a]) : v_taken;   // Q(s).gather(1, a)
   }
 
   // ---- TD error --------------------------------------------------------------------------------------------------
@@ -558,9 +679,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) dqn_grad_tc_kernel(const __gr
 
   // ---- this warp's partial into its own staging tiles (every lane is done reading them) ---------------------------
   __syncwarp();
-  float* part = buf0;                              // buf0 and buf1 are contiguous
-  for (int o = lane; o < kPartCount; o += 32) part[o] = 0.0f;
-  __syncwarp();
+  float* part = buf0;                              // buf0 and buf1 are contiguous; every slot read below is written here
   {
     const int gq = lane >> 2, tg = lane & 3;
 #pragma unroll
@@ -637,7 +756,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) dqn_grad_tc_kernel(const __gr
 
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, kTmemCols);
+  if (warp == 0) tc::tmem_dealloc(tmem, kDqnTmemCols);
 }
 
 int dqn_maxdeg(const SwarmConfig& c);

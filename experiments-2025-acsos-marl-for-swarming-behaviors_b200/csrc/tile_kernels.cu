@@ -76,6 +76,24 @@ tile_kernel(const __grid_constant__ TileParams p) {
   g.ski = smem + L.ki;
   g.snbr = smem + L.nbr;
 
+  // this agent's state, running return and the tick-dependent scalars: global loads issued before the weights are
+  // staged, so their latency overlaps the staging round trip (a single-tick launch is mostly prologue)
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  float ret0 = 0.0f;
+  if (t.active) {
+    s = reinterpret_cast<const float4*>(p.state_in)[t.gidx];
+    if (MODE == MODE_ROLLOUT && p.returns) ret0 = p.returns[t.gidx];
+  }
+  float2 shp = make_float2(0.0f, 0.0f);      // FLOCK: (previous_distance_to_goal, previous_distance_to_agents)
+  if (FLOCK && t.active) shp = p.shaping[t.gidx];
+  float epsilon = p.epsilon;
+  long long rng_tick0 = p.rng_tick0, replay_cursor = p.replay_cursor;
+  if (MODE == MODE_ROLLOUT && p.ctl) {
+    epsilon = p.ctl->epsilon;
+    rng_tick0 = p.ctl->tick + 1;
+    replay_cursor = p.ctl->ring_cursor;
+  }
+
   TileTcSmem ts;
   uint32_t tmem = 0, parity = 0;
   if (TC) {
@@ -97,14 +115,6 @@ tile_kernel(const __grid_constant__ TileParams p) {
     stage_weights(p.weights, sw, tid, T);
   }
 
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  float ret0 = 0.0f;                 // running return of this agent, fetched up front (its latency hides behind tick 0)
-  if (t.active) {
-    s = reinterpret_cast<const float4*>(p.state_in)[t.gidx];
-    if (MODE == MODE_ROLLOUT && p.returns) ret0 = p.returns[t.gidx];
-  }
-  float2 shp = make_float2(0.0f, 0.0f);      // FLOCK: (previous_distance_to_goal, previous_distance_to_agents)
-  if (FLOCK && t.active) shp = p.shaping[t.gidx];
 
   int deg = 0;
   const bool complete = !knn && !radius;
@@ -115,14 +125,6 @@ tile_kernel(const __grid_constant__ TileParams p) {
   float ret = 0.0f;
   int myhits = 0;
 
-  // tick-dependent scalars: launch parameters, or the device-resident training cursor (graph-replayable ticks)
-  float epsilon = p.epsilon;
-  long long rng_tick0 = p.rng_tick0, replay_cursor = p.replay_cursor;
-  if (MODE == MODE_ROLLOUT && p.ctl) {
-    epsilon = p.ctl->epsilon;
-    rng_tick0 = p.ctl->tick + 1;
-    replay_cursor = p.ctl->ring_cursor;
-  }
 
   for (int tick = 0; tick < p.ticks; ++tick) {
     const float4* pos = sst + (tick & 1) * T;

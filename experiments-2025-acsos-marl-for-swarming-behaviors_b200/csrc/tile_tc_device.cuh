@@ -43,13 +43,22 @@ constexpr int kTcW0Bytes = 2 * 32 * 8 * 4, kTcW1Bytes = 2 * 32 * 32 * 4, kTcW2By
 // All global loads of a thread are issued before the first shared-memory store (the destinations are char pointers,
 // which the compiler must assume to alias the source): one exposed memory round trip instead of one per item --
 // this prologue is a fifth of a single-tick launch (train tick).
-__device__ __forceinline__ void stage_weights_tc(const float* __restrict__ gw, const TileTcSmem& s, int tid, int nthreads) {
+// Split into a load phase (global -> registers) and a store phase (registers -> shared), so a kernel that stages
+// several weight sets issues all their loads before the first store.  `vtid` = index of the thread inside the group
+// that fills the vector block (tid itself, or tid - 32 * w to put the dot-product chains of v_s / v_d on warp w).
+struct TcStageRegs {
+  float vv;
+  float4 item[(448 + kTileThreads - 1) / kTileThreads];
+};
+
+__device__ __forceinline__ void stage_weights_tc_load(const float* __restrict__ gw, TcStageRegs& r, int tid, int nthreads,
+                                                      int vtid) {
   // bias vectors, and the attention vectors pulled through the projection: v[k] = sum_c att[c] W0[c][k], c ascending
-  // (threads 0 .. 13; every load is issued before the FMA chain starts)
+  // (threads 0 .. 13 of the group; every load is issued before the FMA chain starts)
   float vv = 0.0f;
   {
-    const int idx = tid;
-    if (idx < TV_B0) {
+    const int idx = vtid;
+    if (idx >= 0 && idx < TV_B0) {
       const int k = idx & 7;
       if (k < 7) {
         const float* att = gw + ((idx < TV_VD) ? SWARM_W_ATT_SRC : SWARM_W_ATT_DST);
@@ -59,34 +68,39 @@ __device__ __forceinline__ void stage_weights_tc(const float* __restrict__ gw, c
 #pragma unroll
         for (int c = 0; c < 32; ++c) vv = fmaf(a[c], w[c], vv);
       }
-    } else if (idx < TV_B1) vv = gw[SWARM_W_CONV_BIAS + (idx - TV_B0)];
-    else if (idx < TV_B2) vv = gw[SWARM_W_LIN1_BIAS + (idx - TV_B1)];
-    else if (idx - TV_B2 < 9) vv = gw[SWARM_W_LIN2_BIAS + (idx - TV_B2)];
+    } else if (idx >= TV_B0 && idx < TV_B1) vv = gw[SWARM_W_CONV_BIAS + (idx - TV_B0)];
+    else if (idx >= TV_B1 && idx < TV_B2) vv = gw[SWARM_W_LIN1_BIAS + (idx - TV_B1)];
+    else if (idx >= TV_B2 && idx - TV_B2 < 9) vv = gw[SWARM_W_LIN2_BIAS + (idx - TV_B2)];
   }
+  r.vv = vv;
   constexpr int kItemIters = (448 + kTileThreads - 1) / kTileThreads;         // 4
   // items: (row n, k-chunk c) of W1 (256), W2 (128), W0 (64)
-  float4 item[kItemIters];
 #pragma unroll
   for (int k = 0; k < kItemIters; ++k) {
     const int it = tid + k * nthreads;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (it < 256) {
-      const float* r = gw + SWARM_W_LIN1 + (it >> 3) * 32 + 4 * (it & 7);
-      v = make_float4(r[0], r[1], r[2], r[3]);
+      const float* q = gw + SWARM_W_LIN1 + (it >> 3) * 32 + 4 * (it & 7);
+      v = make_float4(q[0], q[1], q[2], q[3]);
     } else if (it < 384) {
       const int j = it - 256;
       if ((j >> 3) < 9) {
-        const float* r = gw + SWARM_W_LIN2 + (j >> 3) * 32 + 4 * (j & 7);
-        v = make_float4(r[0], r[1], r[2], r[3]);
+        const float* q = gw + SWARM_W_LIN2 + (j >> 3) * 32 + 4 * (j & 7);
+        v = make_float4(q[0], q[1], q[2], q[3]);
       }
     } else if (it < 448) {
       const int j = it - 384;
-      const float* r = gw + SWARM_W_CONV_LIN + (j >> 1) * 7 + 4 * (j & 1);
-      v = (j & 1) == 0 ? make_float4(r[0], r[1], r[2], r[3]) : make_float4(r[0], r[1], r[2], 0.0f);
+      const float* q = gw + SWARM_W_CONV_LIN + (j >> 1) * 7 + 4 * (j & 1);
+      v = (j & 1) == 0 ? make_float4(q[0], q[1], q[2], q[3]) : make_float4(q[0], q[1], q[2], 0.0f);
     }
-    item[k] = v;
+    r.item[k] = v;
   }
-  if (tid < TV_COUNT) s.vec[tid] = vv;
+}
+
+__device__ __forceinline__ void stage_weights_tc_store(const TcStageRegs& r, const TileTcSmem& s, int tid, int nthreads,
+                                                       int vtid) {
+  constexpr int kItemIters = (448 + kTileThreads - 1) / kTileThreads;
+  if (vtid >= 0 && vtid < TV_COUNT) s.vec[vtid] = r.vv;
 #pragma unroll
   for (int k = 0; k < kItemIters; ++k) {
     const int it = tid + k * nthreads;
@@ -103,11 +117,17 @@ __device__ __forceinline__ void stage_weights_tc(const float* __restrict__ gw, c
       n = j >> 1; c = j & 1; rows = 32; base = s.w0; half = kTcW0Bytes / 2;
     }
     float4 hi, lo;
-    tc::split4(item[k], hi, lo);
+    tc::split4(r.item[k], hi, lo);
     const int off = tc::tile_off(rows, n, c);
     *reinterpret_cast<float4*>(base + off) = hi;
     *reinterpret_cast<float4*>(base + half + off) = lo;
   }
+}
+
+__device__ __forceinline__ void stage_weights_tc(const float* __restrict__ gw, const TileTcSmem& s, int tid, int nthreads) {
+  TcStageRegs r;
+  stage_weights_tc_load(gw, r, tid, nthreads, tid);
+  stage_weights_tc_store(r, s, tid, nthreads, tid);
 }
 
 // The A operand of the three contractions lives in TENSOR MEMORY: every thread splits its own activation row into
@@ -180,14 +200,14 @@ __device__ __forceinline__ void tile_attend_inputs(const TileGraphSmem& g, const
   float2 acc_p = make_float2(0.0f, 0.0f), acc_v = make_float2(0.0f, 0.0f);
   // LeakyReLU and the rounded add are monotone: max_e leaky(a_e + d) = leaky(max_e a_e + d)
   if (COMPLETE) {
-    // Sources of node i: every j != i, and j = 0 for node 0 itself (its self loop).  The sums run over j = 0 .. N - 1
-    // with the own slot weighted zero -- for node 0 the self loop is summed first instead of last, a different
-    // rounding of the same sum -- so the loop needs no index arithmetic at all.
-    const int self = (t.i == 0) ? -1 : t.i;
+    // Sources of node i: every j != i in ascending order; node 0 additionally ends with its own (0,0) self loop.  The
+    // sums run over j = 0 .. N - 1 with the own slot weighted zero, so the loop needs no index arithmetic; node 0's
+    // self loop is added after the loop -- the same operations in the same order as over the explicit edge list.
     const int n = t.active ? N : 0;
+    const bool node0 = t.active && t.i == 0;
     float amax = -INFINITY;
 #pragma unroll 4
-    for (int j = 0; j < n; ++j) amax = fmaxf(amax, j == self ? -INFINITY : sas[j]);
+    for (int j = 0; j < n; ++j) amax = fmaxf(amax, (j == t.i && !node0) ? -INFINITY : sas[j]);
     const float zt = __fadd_rn(amax, adst);
     const float m = fmaxf(zt, __fmul_rn(zt, 0.2f));
     float fj = 0.0f;
@@ -196,13 +216,23 @@ __device__ __forceinline__ void tile_attend_inputs(const TileGraphSmem& g, const
       const float4 sj = env[j];
       const float zz = __fadd_rn(sas[j], adst);
       const float ex = __expf(fmaxf(zz, __fmul_rn(zz, 0.2f)) - m);
-      const float w = (j == self) ? 0.0f : ex;
+      const float w = (j == t.i) ? 0.0f : ex;
       const float2 w2 = make_float2(w, w);
       den = __fadd_rn(den, w);
       acc_p = __ffma2_rn(w2, make_float2(sj.x, sj.y), acc_p);
       acc_v = __ffma2_rn(w2, make_float2(sj.z, sj.w), acc_v);
       acc_id = fmaf(w, fj, acc_id);
       fj += 1.0f;
+    }
+    if (node0) {
+      const float4 sj = env[0];
+      const float zz = __fadd_rn(sas[0], adst);
+      const float w = __expf(fmaxf(zz, __fmul_rn(zz, 0.2f)) - m);
+      const float2 w2 = make_float2(w, w);
+      den = __fadd_rn(den, w);
+      acc_p = __ffma2_rn(w2, make_float2(sj.x, sj.y), acc_p);
+      acc_v = __ffma2_rn(w2, make_float2(sj.z, sj.w), acc_v);
+      acc_id = fmaf(w, 0.0f, acc_id);
     }
   } else {
     const uint8_t* __restrict__ sin = g.sin + t.tid;
