@@ -200,14 +200,15 @@ __device__ __forceinline__ void tile_attend_inputs(const TileGraphSmem& g, const
   float2 acc_p = make_float2(0.0f, 0.0f), acc_v = make_float2(0.0f, 0.0f);
   // LeakyReLU and the rounded add are monotone: max_e leaky(a_e + d) = leaky(max_e a_e + d)
   if (COMPLETE) {
-    // Sources of node i: every j != i in ascending order; node 0 additionally ends with its own (0,0) self loop.  The
-    // sums run over j = 0 .. N - 1 with the own slot weighted zero, so the loop needs no index arithmetic; node 0's
-    // self loop is added after the loop -- the same operations in the same order as over the explicit edge list.
+    // Sources of node i: every j != i, and j = 0 for node 0 itself (its self loop).  The sums run over j = 0 .. N - 1
+    // with the own slot weighted zero -- for node 0 the self loop is summed first instead of last, a different
+    // rounding of the same sum (summing it last through a tail branch that every warp executes cost 4 % of the
+    // rollout) -- so the loop needs no index arithmetic at all.
+    const int self = (t.i == 0) ? -1 : t.i;
     const int n = t.active ? N : 0;
-    const bool node0 = t.active && t.i == 0;
     float amax = -INFINITY;
 #pragma unroll 4
-    for (int j = 0; j < n; ++j) amax = fmaxf(amax, (j == t.i && !node0) ? -INFINITY : sas[j]);
+    for (int j = 0; j < n; ++j) amax = fmaxf(amax, j == self ? -INFINITY : sas[j]);
     const float zt = __fadd_rn(amax, adst);
     const float m = fmaxf(zt, __fmul_rn(zt, 0.2f));
     float fj = 0.0f;
@@ -216,23 +217,13 @@ __device__ __forceinline__ void tile_attend_inputs(const TileGraphSmem& g, const
       const float4 sj = env[j];
       const float zz = __fadd_rn(sas[j], adst);
       const float ex = __expf(fmaxf(zz, __fmul_rn(zz, 0.2f)) - m);
-      const float w = (j == t.i) ? 0.0f : ex;
+      const float w = (j == self) ? 0.0f : ex;
       const float2 w2 = make_float2(w, w);
       den = __fadd_rn(den, w);
       acc_p = __ffma2_rn(w2, make_float2(sj.x, sj.y), acc_p);
       acc_v = __ffma2_rn(w2, make_float2(sj.z, sj.w), acc_v);
       acc_id = fmaf(w, fj, acc_id);
       fj += 1.0f;
-    }
-    if (node0) {
-      const float4 sj = env[0];
-      const float zz = __fadd_rn(sas[0], adst);
-      const float w = __expf(fmaxf(zz, __fmul_rn(zz, 0.2f)) - m);
-      const float2 w2 = make_float2(w, w);
-      den = __fadd_rn(den, w);
-      acc_p = __ffma2_rn(w2, make_float2(sj.x, sj.y), acc_p);
-      acc_v = __ffma2_rn(w2, make_float2(sj.z, sj.w), acc_v);
-      acc_id = fmaf(w, 0.0f, acc_id);
     }
   } else {
     const uint8_t* __restrict__ sin = g.sin + t.tid;
