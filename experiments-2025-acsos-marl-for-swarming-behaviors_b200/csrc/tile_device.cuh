@@ -319,6 +319,35 @@ __device__ __forceinline__ int tile_in_edges_knn_small(const TileGraphSmem& g, c
   return deg;
 }
 
+// Multiplicities of the in-edges of node i in the symmetrised kNN list (simulator.py:20-24), 2 bits per source j:
+//   j != i:  [i in topk(j)] + [j in topk(i)]          (edge (j -> i) of row j, edge (j -> i) mirrored from row i)
+//   j == i:  2 [i in topk(i)]                         (row i lists itself: (i -> i) and its mirror)   + 1 for node 0
+// Every thread publishes the 16-bit set of its row, one barrier, then N bit tests.  Every thread of the CTA must call
+// it; `smask` is rewritten only after the barriers of the Q forward that follows.
+__device__ __forceinline__ uint32_t spread_bits16(uint32_t x) {       // bit j -> bit 2 j
+  x = (x | (x << 8)) & 0x00FF00FFu;
+  x = (x | (x << 4)) & 0x0F0F0F0Fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
+__device__ __forceinline__ uint32_t tile_knn_counts_small(const TileThread& t, int N, int K, uint64_t nbr,
+                                                         uint32_t* __restrict__ smask) {
+  uint32_t mine = 0;
+  if (t.active)
+    for (int r = 0; r < K; ++r) mine |= 1u << knn_nib(nbr, r);
+  smask[t.tid] = mine;
+  __syncthreads();
+  if (!t.active) return 0;
+  const uint32_t* __restrict__ col = smask + t.envbase;
+  uint32_t in = 0;
+#pragma unroll 4
+  for (int ii = 0; ii < N; ++ii) in |= ((col[ii] >> t.i) & 1u) << ii;
+  in &= ~(1u << t.i);
+  const uint32_t self2 = ((mine >> t.i) & 1u) << (2 * t.i);
+  return spread_bits16(in) + spread_bits16(mine) + self2 + (t.i == 0 ? 1u : 0u);
+}
+
 // edge list export (env-local ids) in the reference's order
 // (small swarms: `nbr_word` holds the neighbours, `use_word` = true)
 __device__ __forceinline__ void tile_write_edges(const TileGraphSmem& g, const TileThread& t, int N, int K, bool knn,

@@ -142,9 +142,11 @@ tile_kernel(const __grid_constant__ TileParams p) {
     int action = 0;
 
     // ------------------------------------------------------------------ graph ----------------
+    uint32_t knn_counts = 0;
     if (knn_small) {
       nbr_word = tile_knn_small(t, pos, s, N, K, knn_cache_rank, knn_cache_nbr);
-      if (kQ) deg = tile_in_edges_knn_small(g, t, N, K, nbr_word, reinterpret_cast<uint32_t*>(g.skv));
+      if (kQ && TC) knn_counts = tile_knn_counts_small(t, N, K, nbr_word, reinterpret_cast<uint32_t*>(g.skv));
+      else if (kQ) deg = tile_in_edges_knn_small(g, t, N, K, nbr_word, reinterpret_cast<uint32_t*>(g.skv));
     } else if (knn) {
       tile_knn_rows(g, t, pos, s, N, K);
       if (kQ) deg = tile_in_edges_knn(g, t, N, K, reinterpret_cast<uint32_t*>(g.skv));   // distance rows are dead now
@@ -181,8 +183,12 @@ tile_kernel(const __grid_constant__ TileParams p) {
       // node features (train:95-99): [pos, vel, goal, agent id]
       float q[9];
       if (TC) {
-        action = complete ? tile_q_forward_tc<true>(g, ts, t, tmem, pos, N, deg, adst_tc, c.goal_x, c.goal_y, parity, q)
-                          : tile_q_forward_tc<false>(g, ts, t, tmem, pos, N, deg, adst_tc, c.goal_x, c.goal_y, parity, q);
+        if (complete)
+          action = tile_q_forward_tc<ATT_COMPLETE>(g, ts, t, tmem, pos, N, deg, 0u, adst_tc, c.goal_x, c.goal_y, parity, q);
+        else if (knn_small)
+          action = tile_q_forward_tc<ATT_COUNTS>(g, ts, t, tmem, pos, N, deg, knn_counts, adst_tc, c.goal_x, c.goal_y, parity, q);
+        else
+          action = tile_q_forward_tc<ATT_LIST>(g, ts, t, tmem, pos, N, deg, 0u, adst_tc, c.goal_x, c.goal_y, parity, q);
       } else {
         const float x[7] = {s.x, s.y, s.z, s.w, c.goal_x, c.goal_y, (float)t.i};
         float a1[32];

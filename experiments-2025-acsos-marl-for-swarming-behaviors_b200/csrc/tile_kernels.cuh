@@ -161,7 +161,8 @@ __host__ __device__ inline TileLayout tile_layout(int mode, int threads, int n, 
   L.st = off;   off = tile_align16(off + 2 * threads * 16);
   // the tensor-core path attends in input space (tile_tc_device.cuh): no tile of projected features, no per-edge
   // scratch, and no edge list for the complete graph
-  const bool tc_complete = tc && graph_mode == SWARM_GRAPH_COMPLETE;
+  // (nor for kNN swarms of n <= 16, whose in-edges are multiplicity words in registers)
+  const bool tc_complete = tc && (graph_mode == SWARM_GRAPH_COMPLETE || (graph_mode == SWARM_GRAPH_KNN && n <= 16));
   L.h = off;    off = tile_align16(off + ((q && !tc) ? threads * kHPad * 4 : 0));
   L.asrc = off; off = tile_align16(off + (q ? threads * 4 : 0));
   L.wt = off;   off = tile_align16(off + ((q && !tc) ? maxdeg * threads * 4 : 0));

@@ -187,19 +187,50 @@ __device__ __forceinline__ void tc_alpha_terms(const TileTcSmem& s, const float 
 }
 
 // Softmax-weighted mean of the neighbours' input features (see the header).  `pos` = the tile's states, g.sas = the
-// published alpha_src terms.  COMPLETE: the reference's complete graph (train:101-108) -- sources of node i are all
-// j != i in ascending order, node 0 additionally ends with its (0,0) self loop -- without an edge list in memory;
-// otherwise the in-edge list g.sin / deg.
-template <bool COMPLETE>
+// published alpha_src terms.  Three ways to name the in-edges of node i:
+//   ATT_LIST      the in-edge list g.sin / deg in edge-list order (radius graph, large kNN swarms)
+//   ATT_COMPLETE  the reference's complete graph (train:101-108): every j != i, node 0 additionally its (0,0) self loop
+//   ATT_COUNTS    `counts` = 2 bits per source j: how many parallel edges j -> i the symmetrised kNN list of
+//                 simulator.py:20-24 holds (0 .. 3); the sums run over j = 0 .. N - 1 with the term weighted by its
+//                 multiplicity -- the same sum as over the list, term order and one rounding apart -- so the per-tick
+//                 in-edge LIST (strided byte stores, two barriers) is never built
+enum { ATT_LIST = 0, ATT_COMPLETE = 1, ATT_COUNTS = 2 };
+
+template <int ATT>
 __device__ __forceinline__ void tile_attend_inputs(const TileGraphSmem& g, const TileThread& t, const float4* __restrict__ pos,
-                                                   int N, int deg, float adst, float goal_x, float goal_y, float (&xm)[8]) {
+                                                   int N, int deg, uint32_t counts, float adst, float goal_x, float goal_y,
+                                                   float (&xm)[8]) {
+  constexpr bool COMPLETE = (ATT == ATT_COMPLETE);
   const int T = kTileThreads;
   const float* __restrict__ sas = g.sas + t.envbase;
   const float4* __restrict__ env = pos + t.envbase;
   float den = 0.0f, acc_id = 0.0f;
   float2 acc_p = make_float2(0.0f, 0.0f), acc_v = make_float2(0.0f, 0.0f);
   // LeakyReLU and the rounded add are monotone: max_e leaky(a_e + d) = leaky(max_e a_e + d)
-  if (COMPLETE) {
+  if (ATT == ATT_COUNTS) {
+    const int n = t.active ? N : 0;
+    float amax = -INFINITY;
+    uint32_t cw = counts;
+#pragma unroll 4
+    for (int j = 0; j < n; ++j, cw >>= 2) amax = fmaxf(amax, (cw & 3u) ? sas[j] : -INFINITY);
+    const float zt = __fadd_rn(amax, adst);
+    const float m = fmaxf(zt, __fmul_rn(zt, 0.2f));
+    float fj = 0.0f;
+    cw = counts;
+#pragma unroll 4
+    for (int j = 0; j < n; ++j, cw >>= 2) {
+      const float4 sj = env[j];
+      const float zz = __fadd_rn(sas[j], adst);
+      const float ex = __expf(fmaxf(zz, __fmul_rn(zz, 0.2f)) - m);
+      const float w = ex * (float)(cw & 3u);
+      const float2 w2 = make_float2(w, w);
+      den = __fadd_rn(den, w);
+      acc_p = __ffma2_rn(w2, make_float2(sj.x, sj.y), acc_p);
+      acc_v = __ffma2_rn(w2, make_float2(sj.z, sj.w), acc_v);
+      acc_id = fmaf(w, fj, acc_id);
+      fj += 1.0f;
+    }
+  } else if (COMPLETE) {
     // Sources of node i: every j != i, and j = 0 for node 0 itself (its self loop).  The sums run over j = 0 .. N - 1
     // with the own slot weighted zero -- for node 0 the self loop is summed first instead of last, a different
     // rounding of the same sum (summing it last through a tail branch that every warp executes cost 4 % of the
@@ -253,15 +284,16 @@ __device__ __forceinline__ void tile_attend_inputs(const TileGraphSmem& g, const
 
 // Full per-tick Q forward on the tensor cores.  The caller has published g.sas[tid] = alpha_src of every node and
 // passed a block barrier since (the tick's state barrier).  Contains 3 block barriers.  All 128 threads must call it.
-template <bool COMPLETE>
+template <int ATT>
 __device__ __forceinline__ int tile_q_forward_tc(const TileGraphSmem& g, const TileTcSmem& s, const TileThread& t,
-                                                 uint32_t tmem, const float4* __restrict__ pos, int N, int deg, float adst,
-                                                 float goal_x, float goal_y, uint32_t& parity, float (&q)[9]) {
+                                                 uint32_t tmem, const float4* __restrict__ pos, int N, int deg,
+                                                 uint32_t counts, float adst, float goal_x, float goal_y, uint32_t& parity,
+                                                 float (&q)[9]) {
   const uint32_t lane_addr = tmem + ((uint32_t)(t.tid & ~31) << 16);     // this warp's 32 TMEM lanes
   // ---- attention in input space, then agg = mean W0^T (K padded 7 -> 8) ----
   {
     float xm[8];
-    tile_attend_inputs<COMPLETE>(g, t, pos, N, deg, adst, goal_x, goal_y, xm);
+    tile_attend_inputs<ATT>(g, t, pos, N, deg, counts, adst, goal_x, goal_y, xm);
     float4 h0, l0, h1, l1;
     tc::split4(make_float4(xm[0], xm[1], xm[2], xm[3]), h0, l0);
     tc::split4(make_float4(xm[4], xm[5], xm[6], 0.0f), h1, l1);
