@@ -378,9 +378,10 @@ class DQNTrainer:
         statistics (train:179-199) all live on the device and the host only reads the statistics at the end.
         Per-env start centres come from the counter RNG (``shared_center`` reproduces the reference's one draw per
         reset).  Returns stats f32[episodes, 4] = (mean agent-0 return / N, hits per env, last loss, epsilon)."""
-        if not isinstance(self.env.scenario, _KernelScenario):
-            raise NotImplementedError("the whole-run device loop resets GoTo / ObstacleAvoidance worlds on the device; train "
-                                      "Flocking with train_model_batched, other scenarios with train_model_stepwise")
+        flock = isinstance(self.env.scenario, FlockingScenario)
+        if not (flock or isinstance(self.env.scenario, _KernelScenario)):
+            raise NotImplementedError("the whole-run device loop resets GoTo / ObstacleAvoidance / Flocking worlds on the "
+                                      "device; train other scenarios with train_model_stepwise")
         env, world = self.env, self.env.world
         B, n, dev = env.num_envs, env.n_agents, env.device
         G = int(config.get("graphs_per_update", 32))
@@ -393,10 +394,13 @@ class DQNTrainer:
                            gamma=float(config.get("gamma", 0.99)), loss_scale=parallel.global_loss_scale(G, n),
                            lr=self.lr, betas=self.betas, eps=self.eps, max_norm=self.max_norm, rng_seed=self.seed,
                            sample_seed=int(config.get("sample_seed", self.seed)) + 7919 * rank,
-                           env_offset=int(config.get("env_offset", rank * B)))
+                           env_offset=int(config.get("env_offset", rank * B)),
+                           flocking=env.scenario._spec() if flock else None,
+                           shaping=env.scenario.shaping if flock else None)
         spec = ops.reset_spec(cfg.scenario, random=bool(getattr(env.scenario, "random", True)),
                               seed=int(config.get("reset_seed", self.seed)), env_offset=tt.hyper.env_offset,
-                              shared_center=bool(config.get("shared_center", False)))
+                              shared_center=bool(config.get("shared_center", False)), flocking=flock)
+        flock_spec = env.scenario._spec() if flock else None
         parallel.require_equal_shards(B, ring.size, ring.position, ring.capacity, G)
         parallel.broadcast_weights(self.w)
         self.w_target.copy_(self.w)
@@ -410,6 +414,10 @@ class DQNTrainer:
 
         def episode():
             ops.reset_random(cfg, spec, world.state, ctl=tt.ctl)
+            if flock:
+                # previous_distance_to_goal / previous_distance_to_agents as reset_world_at leaves them
+                # (flocking:101-121), on the device: the same reset launch the host-side reset_world_at issues
+                ops.scenario_reward(flock_spec, world.state, env.scenario.shaping, reset=True)
             for _ in range(env.max_steps):
                 tt.grad_phase(self.w, self.w_target, world.state, returns, hits)
                 if nccl:

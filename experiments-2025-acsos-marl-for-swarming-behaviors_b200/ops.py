@@ -266,10 +266,13 @@ def adam_clip_step(weights: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Ten
 
 
 def reset_spec(scenario: int, random: bool = True, seed: int = 0, env_offset: int = 0,
-               shared_center: bool = False) -> _lib.SwarmResetSpec:
-    """Start-centre distribution of the scenario's reset_world_at (go_to:84-88, oa:100-102)."""
+               shared_center: bool = False, flocking: bool = False) -> _lib.SwarmResetSpec:
+    """Start-centre distribution of the scenario's reset_world_at (go_to:84-88, oa:100-102; ``flocking``:
+    flocking_scenario.py:94-98, position_range (-1, 1) + N((-0.6, 0.6), 0.4))."""
     sp = _lib.SwarmResetSpec()
-    if scenario == _lib.SCENARIO_GOTO:
+    if flocking:
+        sp.base_x, sp.base_y, sp.mean_x, sp.mean_y, sp.std_x, sp.std_y = -1.0, 1.0, -0.6, 0.6, 0.4, 0.4
+    elif scenario == _lib.SCENARIO_GOTO:
         sp.base_x, sp.base_y, sp.mean_x, sp.mean_y, sp.std_x, sp.std_y = 1.5, -1.5, -0.6, 0.6, 0.4, 0.4
     else:
         sp.base_x, sp.base_y, sp.mean_x, sp.mean_y = 0.6, -0.6, 0.0, 0.0

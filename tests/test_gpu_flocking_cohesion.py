@@ -250,8 +250,49 @@ def test_reference_training_loop_runs_on_flocking():
     assert torch.equal(stored.reshape(2 * T, n), want), "the replay ring holds the Flocking collective reward"
     goto_like = -torch.linalg.vector_norm(env.world.state[0, :, 0:2] - torch.tensor([-0.8, 0.8], device=_dev()), dim=-1).sum()
     assert abs(float(seen[-1]) - float(goto_like)) > 1e-3, "and it is not the GoTo reward of the world-step kernel"
-    with pytest.raises(NotImplementedError):
-        trainer.train_model_device({"epsilon": 0.5, "episodes": 1})
+
+
+def test_device_loop_training_on_flocking():
+    """DQNTrainer.train_model_device on a Flocking env: the reset of flocking:93-121 (start centre from the counter RNG,
+    grid at the desired distance, the two shaping memories) happens on the device inside the episode graph.  The
+    pushed transitions of episode 0 are re-derived by stepping a second env from the same start states, and the
+    CUDA-graph run equals the eager run bit for bit."""
+    B, n, T, G = 64, 5, 12, 32
+    cfgd = {"epsilon": 0.4, "epsilon_decay": 0.05, "min_epsilon": 0.05, "episodes": 3, "graphs_per_update": G,
+            "update_target_every": 5}
+
+    def run(use_graph):
+        sb, env, env_ref, _ = _flocking_pair(B, n, T, seed=11)
+        sb.set_seed(5)
+        trainer = sb.DQNTrainer(env, 5, "/tmp/swarm_models", "/tmp/swarm_stats", "Flocking", replay_capacity=B * T * 4)
+        stats = trainer.train_model_device(dict(cfgd, cuda_graph=use_graph))
+        torch.cuda.synchronize()
+        return sb, trainer, env_ref, stats
+
+    sb, trainer, env_ref, stats = run(False)
+    ring = trainer.replay_buffer.ring
+    assert len(ring) == 3 * T * B and trainer.opt_step == 3 * T and torch.isfinite(stats).all()
+    first = sb.ops.replay_gather(ring, torch.arange(T * B, device=_dev(), dtype=torch.int64))     # episode 0
+    start = first["state"][:B]
+    # the device reset: zero velocities, agents on the 0.15-spaced grid around a centre drawn from (-1, 1) + N((-0.6, 0.6), 0.4)
+    assert (start[..., 2:] == 0).all()
+    centres = start[..., :2].mean(dim=1).cpu()
+    assert abs(centres[:, 0].mean().item() + 1.6) < 0.3 and abs(centres[:, 1].mean().item() - 1.6) < 0.3
+    assert 0.2 < centres[:, 0].std().item() < 0.6
+    dx = (start[:, 1, 0] - start[:, 0, 0]).cpu()
+    assert torch.allclose(dx, torch.full_like(dx, 0.15), atol=1e-6)
+    # rewards: the second env starts from the same states with the reset shaping memory and replays the stored actions
+    env_ref.world.state.copy_(start)
+    sb.ops.scenario_reward(env_ref.scenario._spec(), env_ref.world.state, env_ref.scenario.shaping, reset=True)
+    for t in range(T):
+        sl = slice(t * B, (t + 1) * B)
+        assert torch.equal(first["state"][sl], env_ref.world.state), f"pre-step state of tick {t}"
+        _, rews, _, _ = env_ref.step(first["actions"][sl])
+        assert torch.equal(first["next_state"][sl], env_ref.world.state)
+        assert torch.equal(first["rewards"][sl], rews["agent0"][:, None].expand(B, n)), f"reward of tick {t}"
+    _, graphed, _, stats_g = run(True)
+    assert torch.equal(graphed.w, trainer.w) and torch.equal(graphed.w_target, trainer.w_target)
+    assert torch.equal(stats_g, stats)
 
 
 @pytest.mark.parametrize("which", ["flocking", "obstacle_avoidance"])
@@ -377,5 +418,46 @@ def test_fused_batched_training_on_flocking():
     _, graphed, _, stats_g = run(True, 3)
     assert torch.equal(graphed.w, trainer.w) and torch.equal(graphed.w_target, trainer.w_target)
     assert stats_g["loss"] == stats["loss"]
-    with pytest.raises(NotImplementedError):
-        trainer.train_model_device({"epsilon": 0.5, "episodes": 1})
+
+
+def test_device_loop_training_on_flocking():
+    """DQNTrainer.train_model_device on a Flocking env: the reset of flocking:93-121 (start centre from the counter RNG,
+    grid at the desired distance, the two shaping memories) happens on the device inside the episode graph.  The
+    pushed transitions of episode 0 are re-derived by stepping a second env from the same start states, and the
+    CUDA-graph run equals the eager run bit for bit."""
+    B, n, T, G = 64, 5, 12, 32
+    cfgd = {"epsilon": 0.4, "epsilon_decay": 0.05, "min_epsilon": 0.05, "episodes": 3, "graphs_per_update": G,
+            "update_target_every": 5}
+
+    def run(use_graph):
+        sb, env, env_ref, _ = _flocking_pair(B, n, T, seed=11)
+        sb.set_seed(5)
+        trainer = sb.DQNTrainer(env, 5, "/tmp/swarm_models", "/tmp/swarm_stats", "Flocking", replay_capacity=B * T * 4)
+        stats = trainer.train_model_device(dict(cfgd, cuda_graph=use_graph))
+        torch.cuda.synchronize()
+        return sb, trainer, env_ref, stats
+
+    sb, trainer, env_ref, stats = run(False)
+    ring = trainer.replay_buffer.ring
+    assert len(ring) == 3 * T * B and trainer.opt_step == 3 * T and torch.isfinite(stats).all()
+    first = sb.ops.replay_gather(ring, torch.arange(T * B, device=_dev(), dtype=torch.int64))     # episode 0
+    start = first["state"][:B]
+    # the device reset: zero velocities, agents on the 0.15-spaced grid around a centre drawn from (-1, 1) + N((-0.6, 0.6), 0.4)
+    assert (start[..., 2:] == 0).all()
+    centres = start[..., :2].mean(dim=1).cpu()
+    assert abs(centres[:, 0].mean().item() + 1.6) < 0.3 and abs(centres[:, 1].mean().item() - 1.6) < 0.3
+    assert 0.2 < centres[:, 0].std().item() < 0.6
+    dx = (start[:, 1, 0] - start[:, 0, 0]).cpu()
+    assert torch.allclose(dx, torch.full_like(dx, 0.15), atol=1e-6)
+    # rewards: the second env starts from the same states with the reset shaping memory and replays the stored actions
+    env_ref.world.state.copy_(start)
+    sb.ops.scenario_reward(env_ref.scenario._spec(), env_ref.world.state, env_ref.scenario.shaping, reset=True)
+    for t in range(T):
+        sl = slice(t * B, (t + 1) * B)
+        assert torch.equal(first["state"][sl], env_ref.world.state), f"pre-step state of tick {t}"
+        _, rews, _, _ = env_ref.step(first["actions"][sl])
+        assert torch.equal(first["next_state"][sl], env_ref.world.state)
+        assert torch.equal(first["rewards"][sl], rews["agent0"][:, None].expand(B, n)), f"reward of tick {t}"
+    _, graphed, _, stats_g = run(True)
+    assert torch.equal(graphed.w, trainer.w) and torch.equal(graphed.w_target, trainer.w_target)
+    assert torch.equal(stats_g, stats)
