@@ -113,6 +113,9 @@ _SIGNATURES = {
     "swarm_gatq_workspace_bytes": (C.c_int64, [C.c_int32]),
     "swarm_gatq_forward_csr": (C.c_int, [C.c_int32] + [C.c_void_p] * 6 + [C.c_void_p, C.c_int64, C.c_void_p]),
     "swarm_gatq_forward_knn_large": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 6),
+    "swarm_rollout_large_workspace_bytes": (C.c_int64, [C.POINTER(SwarmConfig)]),
+    "swarm_rollout_large": (C.c_int, [C.POINTER(SwarmConfig), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int64, C.c_void_p]),
     "swarm_gatconv_forward_csr": (C.c_int, [C.c_int32] + [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]),
     "swarm_gatconv_backward_csr": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 11 + [C.c_int64, C.c_void_p]),
     "swarm_gat_layer_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32]),

@@ -282,6 +282,49 @@ int swarm_gatq_forward_knn_large(const SwarmConfig* cfg, const float* weights, c
                     "swarm_gatq_forward_knn_large");
 }
 
+int64_t swarm_rollout_large_workspace_bytes(const SwarmConfig* cfg) {
+  if (!cfg || cfg->num_envs <= 0 || cfg->n_agents <= 0 || cfg->knn_k <= 0) return 0;
+  const int64_t bn = (int64_t)cfg->num_envs * cfg->n_agents;
+  return bn * cfg->knn_k * 4 + bn * 4 + 512;
+}
+
+int swarm_rollout_large(const SwarmConfig* cfg, const float* weights, float* state, int32_t ticks, float* returns,
+                        int32_t* hits, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (int rc = validate(cfg, true, true)) return rc;
+  if (cfg->graph_mode != SWARM_GRAPH_KNN) return fail(SWARM_ERR_INVALID_ARG, "cfg->graph_mode must be SWARM_GRAPH_KNN");
+  if (cfg->n_agents <= kTileThreads) return fail(SWARM_ERR_INVALID_ARG, "n_agents <= 128: use swarm_rollout");
+  if (!weights || !state || !workspace) return fail(SWARM_ERR_INVALID_ARG, "weights/state/workspace is NULL");
+  if (ticks < 0) return fail(SWARM_ERR_INVALID_ARG, "ticks must be >= 0");
+  if ((int64_t)cfg->knn_k * 64 > cfg->n_agents)
+    return fail(SWARM_ERR_UNSUPPORTED, "large-swarm kNN implements torch.topk's partial_sort branch (64 k <= n)");
+  if (!gatq_knn_large_fits(cfg->n_agents, cfg->knn_k))
+    return fail(SWARM_ERR_UNSUPPORTED, "the env does not fit shared memory: step it with swarm_graph_build + "
+                                       "swarm_csr_from_edges + swarm_gatq_forward_csr + swarm_sim_step");
+  if (workspace_bytes < swarm_rollout_large_workspace_bytes(cfg)) return fail(SWARM_ERR_INVALID_ARG, "workspace too small");
+  TileParams p;
+  if (int rc = fill_params(p, cfg, MODE_STEP)) return rc;
+  const int64_t bn = (int64_t)cfg->num_envs * cfg->n_agents;
+  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
+  int32_t* nbr = reinterpret_cast<int32_t*>(base);
+  int32_t* actions = nbr + bn * cfg->knn_k;
+  p.state_in = state;
+  p.state_out = state;           // in place: one CTA owns a whole env and stages its positions first
+  p.actions_in = actions;
+  p.returns = returns;
+  p.hits = hits;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int t = 0; t < ticks; ++t) {
+    // simulator.py:59-68 per tick: topk table -> GCN forward + argmax straight from the table -> Environment.step,
+    // returns / hits accumulated by the step kernel: three launches, nothing but the state leaves the device
+    if (cudaError_t e = launch_graph_large(*cfg, state, nullptr, nbr, p.edges_per_env, st); e != cudaSuccess)
+      return check_cuda(e, "swarm_rollout_large (graph)");
+    if (cudaError_t e = launch_gatq_knn_large(*cfg, weights, state, nbr, nullptr, actions, st); e != cudaSuccess)
+      return check_cuda(e, "swarm_rollout_large (forward)");
+    if (cudaError_t e = launch_sim_step_large(p, st); e != cudaSuccess) return check_cuda(e, "swarm_rollout_large (step)");
+  }
+  return SWARM_OK;
+}
+
 int swarm_gatconv_forward_csr(int32_t n_nodes, const float* weights, const float* x, const int32_t* row_ptr,
                               const int32_t* src, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
   if (n_nodes < 0) return fail(SWARM_ERR_INVALID_ARG, "n_nodes must be >= 0");

@@ -29,6 +29,8 @@ struct LargeStepParams {
   float* obs;
   float2* dist;
   float one_minus_drag, dmin_aa, dmin_ao, qmax_aa, qmax_ao;
+  float* returns;          // optional: per-agent running return += reward (swarm_rollout_large)
+  int32_t* hits;           // optional: per-env obstacle hits += number of agents inside hit_distance this tick
 };
 
 // grid = envs: ONE CTA owns a whole env.  It stages every pre-step position of the env in shared memory before any
@@ -36,10 +38,13 @@ struct LargeStepParams {
 // a (chunk, env) grid would let a later-scheduled chunk read partner positions that an earlier chunk already stepped.
 __global__ void __launch_bounds__(kLargeThreads) sim_step_large_kernel(const __grid_constant__ LargeStepParams p) {
   extern __shared__ float2 spos[];
+  __shared__ int s_hits;
   const SwarmConfig& c = p.cfg;
   const int N = c.n_agents;
   const long long env = blockIdx.x;
   const float4* env_state = p.state_in + env * N;
+  if (threadIdx.x == 0) s_hits = 0;
+  int my_hits = 0;
   for (int j = threadIdx.x; j < N; j += kLargeThreads) {
     const float4 s = env_state[j];
     spos[j] = make_float2(s.x, s.y);
@@ -70,6 +75,8 @@ __global__ void __launch_bounds__(kLargeThreads) sim_step_large_kernel(const __g
     dobs = obstacle_distance(s.x, s.y, c);
     const float reward = oa_reward(dgoal, dobs, c, flags);
     if (p.rewards) p.rewards[gidx] = reward;
+    if (p.returns) p.returns[gidx] = __fadd_rn(p.returns[gidx], reward);
+    my_hits += (flags & SWARM_FLAG_HIT) ? 1 : 0;
   }
   p.state_out[gidx] = s;
   if (p.flags) p.flags[gidx] = flags;
@@ -81,11 +88,17 @@ __global__ void __launch_bounds__(kLargeThreads) sim_step_large_kernel(const __g
   }
   if (p.dist) p.dist[gidx] = make_float2(dgoal, dobs);
   }
+  if (p.hits) {
+    if (my_hits) atomicAdd(&s_hits, my_hits);          // integer: order-independent
+    __syncthreads();
+    if (threadIdx.x == 0) p.hits[env] += s_hits;
+  }
 }
 
 // GoTo (go_to:108-115): reward = 0 + (-d_0) + (-d_1) + ... summed in agent order, the same value for every agent.
 __global__ void __launch_bounds__(kLargeThreads) goto_reward_large_kernel(SwarmConfig c, const float4* __restrict__ state,
-                                                                          float* __restrict__ rewards) {
+                                                                          float* __restrict__ rewards,
+                                                                          float* __restrict__ returns) {
   extern __shared__ float sdg[];
   __shared__ float total;
   const int N = c.n_agents;
@@ -102,7 +115,10 @@ __global__ void __launch_bounds__(kLargeThreads) goto_reward_large_kernel(SwarmC
   }
   __syncthreads();
   const float r = total;
-  for (int j = threadIdx.x; j < N; j += kLargeThreads) rewards[env * N + j] = r;
+  for (int j = threadIdx.x; j < N; j += kLargeThreads) {
+    if (rewards) rewards[env * N + j] = r;
+    if (returns) returns[env * N + j] = __fadd_rn(returns[env * N + j], r);
+  }
 }
 
 // ---- kNN, partial_sort branch ------------------------------------------------------------------
@@ -423,10 +439,12 @@ cudaError_t launch_sim_step_large(const TileParams& tp, cudaStream_t stream) {
   p.dmin_ao = tp.dmin_ao;
   p.qmax_aa = tp.qmax_aa;
   p.qmax_ao = tp.qmax_ao;
+  p.returns = tp.returns;
+  p.hits = tp.hits;
   sim_step_large_kernel<<<c.num_envs, kLargeThreads, c.n_agents * sizeof(float2), stream>>>(p);
-  if (c.scenario == SWARM_SCENARIO_GOTO && tp.rewards_out)
+  if (c.scenario == SWARM_SCENARIO_GOTO && (tp.rewards_out || tp.returns))
     goto_reward_large_kernel<<<c.num_envs, kLargeThreads, c.n_agents * sizeof(float), stream>>>(
-        c, reinterpret_cast<const float4*>(tp.state_out), tp.rewards_out);
+        c, reinterpret_cast<const float4*>(tp.state_out), tp.rewards_out, tp.returns);
   return cudaGetLastError();
 }
 

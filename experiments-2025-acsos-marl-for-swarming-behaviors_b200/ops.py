@@ -578,6 +578,14 @@ def rollout_large(cfg: SwarmConfig, weights: torch.Tensor, state: torch.Tensor, 
     trace = []
     static_csr = None
     fused_knn = cfg.graph_mode == _lib.GRAPH_KNN and N * (144 + 4 * cfg.knn_k) + 8192 <= 227 * 1024 and fused
+    if fused_knn and not trace_state and N > 128:
+        # the whole tick sequence from the library (swarm_rollout_large): topk table -> per-env Q + argmax -> world step
+        # with returns / hits accumulated by the step kernel; no tensor op between the launches
+        wb = int(lib().swarm_rollout_large_workspace_bytes(C.byref(cfg)))
+        ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+        check(lib().swarm_rollout_large(C.byref(cfg), ptr(weights), ptr(state), int(ticks), ptr(returns), ptr(hits), ptr(ws),
+                                        wb, stream_ptr(dev)))
+        return {"state": state, "returns": returns, "hits": hits}
     nbr = torch.empty(B, N, cfg.knn_k, dtype=torch.int32, device=dev) if fused_knn else None
     for _ in range(ticks):
         if fused_knn:

@@ -166,6 +166,16 @@ int swarm_csr_from_edges(int32_t n_nodes, int64_t n_edges, const int64_t* edge_s
 int swarm_gatq_forward_knn_large(const SwarmConfig* cfg, const float* weights, const float* state,
                                  const int32_t* neighbours, float* q, int32_t* actions, void* stream);
 
+/* `ticks` greedy evaluation ticks of a LARGE kNN swarm (n_agents > 128; simulator.py:59-93 with the shipped kNN graph)
+ * launched back to back from the library: per tick the topk table (swarm_graph_build), the Q forward + argmax straight
+ * from the table (swarm_gatq_forward_knn_large) and the world step, whose kernel also accumulates returns float[B*N] (+=)
+ * and hits int32[B] (+=), both optional.  state float[B][N][4] is advanced in place.  No host work, no allocation and
+ * no tensor-library op between the launches (the loop is CUDA-graph capturable).  Same restrictions as the two
+ * building blocks: 64 k <= n_agents and the env must fit shared memory (see swarm_gatq_forward_knn_large). */
+int64_t swarm_rollout_large_workspace_bytes(const SwarmConfig* cfg);
+int swarm_rollout_large(const SwarmConfig* cfg, const float* weights, float* state, int32_t ticks, float* returns,
+                        int32_t* hits, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Backward pass of GCN.forward on an arbitrary graph (loss.backward() through the nn.Module, train_gcn_dqn.py:116-124
  * when a script drives the module with torch autograd): grad_q float[n][9] -> grad_weights float[1673] (overwritten).
  * The graph is given twice, grouped by target (row_ptr / src / perm, as for the forward) and grouped by source

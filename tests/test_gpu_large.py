@@ -204,9 +204,17 @@ def test_large_fused_knn_forward_equals_csr_path(N, k, B, spread):
     q, a = ops.gatq_forward_knn_large(cfg, w, state, nbr, want_q=True, want_actions=True)
     assert torch.equal(q.view(B * N, 9), q_ref) and torch.equal(a.view(-1), a_ref)
     # and the rollout built on it equals the generic one
-    r1 = ops.rollout_large(cfg, w, state.clone(), 2, fused=True)
-    r2 = ops.rollout_large(cfg, w, state.clone(), 2, fused=False)
+    # (fused = swarm_rollout_large: the tick sequence launched from the library, returns / hits accumulated on the device)
+    r1 = ops.rollout_large(cfg, w, state.clone(), 3, fused=True)
+    r2 = ops.rollout_large(cfg, w, state.clone(), 3, fused=False)
     assert torch.equal(r1["state"], r2["state"]) and torch.equal(r1["returns"], r2["returns"])
+    assert torch.equal(r1["hits"], r2["hits"])
+    # GoTo's collective reward through the same path, continuing running totals
+    cg = ops.make_config(sb._lib.SCENARIO_GOTO, B, N, sb._lib.GRAPH_KNN, k)
+    g1 = ops.rollout_large(cg, w, state.clone(), 2, fused=True, returns=r1["returns"].clone(), hits=r1["hits"].clone())
+    g2 = ops.rollout_large(cg, w, state.clone(), 2, fused=False, returns=r2["returns"].clone(), hits=r2["hits"].clone())
+    assert torch.equal(g1["state"], g2["state"]) and torch.equal(g1["returns"], g2["returns"])
+    assert torch.equal(g1["hits"], g2["hits"])
 
 
 def test_large_fused_knn_forward_limits():
