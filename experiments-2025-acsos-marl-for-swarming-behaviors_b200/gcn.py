@@ -78,13 +78,14 @@ class _GatLayerFunction(torch.autograd.Function):
     its four parameters and the node features, so layers stack under autograd."""
 
     @staticmethod
-    def forward(ctx, x, lin_weight, att_src, att_dst, bias, edge_index):
+    def forward(ctx, x, lin_weight, att_src, att_dst, bias, edge_index, csr=None):
         dev = _compute_device(x)
         ctx.homes = (x.device, lin_weight.device)
+        ctx.att_shape = att_src.shape
         x, lin_weight = x.detach().to(dev).contiguous(), lin_weight.detach().to(dev).contiguous()
         att_src, att_dst, bias = (t.detach().to(dev).reshape(-1).contiguous() for t in (att_src, att_dst, bias))
         edge_index = edge_index.to(dev).contiguous()
-        row_ptr, src, perm = ops.csr_from_edges(edge_index, x.shape[0])
+        row_ptr, src, perm = csr if csr is not None else ops.csr_from_edges(edge_index, x.shape[0])
         out = ops.gat_layer_forward(lin_weight, att_src, att_dst, bias, x, row_ptr, src)
         ctx.save_for_backward(x, lin_weight, att_src, att_dst, edge_index, row_ptr, src, perm)
         return out.to(ctx.homes[0])
@@ -96,29 +97,33 @@ class _GatLayerFunction(torch.autograd.Function):
                                                       grad_out.to(x.device).contiguous(),
                                                       want_grad_x=ctx.needs_input_grad[0], by_target=(row_ptr, src, perm))
         hx, hw = ctx.homes
-        return (gx.to(hx) if gx is not None else None), gw.to(hw), gas.view(1, 1, -1).to(hw), gad.view(1, 1, -1).to(hw), \
-            gb.to(hw), None
+        return (gx.to(hx) if gx is not None else None), gw.to(hw), gas.view(ctx.att_shape).to(hw), \
+            gad.view(ctx.att_shape).to(hw), gb.to(hw), None, None
 
 
 class GATConv(nn.Module):
-    """GATConv(in, out, heads=1, add_self_loops=False, bias=True) (train:53).  Keys: ``att_src`` [1,1,out],
-    ``att_dst`` [1,1,out], ``bias`` [out], ``lin.weight`` [out,in].  The projection is initialised twice, like
-    torch_geometric (Linear.__init__ followed by GATConv.reset_parameters).  Inside ``swarm_b200.GCN`` it is a parameter
-    container (the whole network is one fused call); called on its own -- ``conv(x, edge_index)`` as the reference's
-    ``GCN.forward`` does (train:61) -- it runs the layer alone in the CUDA kernels: the (7 -> 32) first layer on data
-    through the kernels of the fused network, any other width up to 64 (or an input that needs a gradient, i.e. a
-    stacked layer) through the generic layer kernels, differentiable w.r.t. parameters and node features."""
+    """GATConv(in, out, heads=H, concat=True, add_self_loops=False, bias=True) (train:53 uses heads = 1).  Keys as in
+    torch_geometric 2.5.3: ``att_src`` [1,H,out], ``att_dst`` [1,H,out], ``lin.weight`` [H*out,in], ``bias`` [H*out]
+    (``concat=True``) or [out] (``concat=False``: mean over the heads, then the bias).  The projection is initialised
+    twice, like torch_geometric (Linear.__init__ followed by GATConv.reset_parameters).  Inside ``swarm_b200.GCN`` it is a
+    parameter container (the whole network is one fused call); called on its own -- ``conv(x, edge_index)`` as the
+    reference's ``GCN.forward`` does (train:61) -- it runs the layer alone in the CUDA kernels: the (7 -> 32) first
+    layer on data through the kernels of the fused network, any other width up to 64 (or an input that needs a
+    gradient, i.e. a stacked layer) through the generic layer kernels, differentiable w.r.t. parameters and node
+    features.  Heads are independent attention layers over slices of the projection, so a multi-head layer is H
+    launches of the single-head layer kernels on one shared CSR grouping (forward and backward), concatenated or
+    averaged as torch_geometric does."""
 
-    def __init__(self, in_channels: int, out_channels: int, heads: int = 1, add_self_loops: bool = False,
-                 bias: bool = True):
+    def __init__(self, in_channels: int, out_channels: int, heads: int = 1, concat: bool = True,
+                 add_self_loops: bool = False, bias: bool = True):
         super().__init__()
-        if heads != 1 or add_self_loops or not bias:
-            raise NotImplementedError("the swarm_b200 kernels implement GATConv(heads=1, add_self_loops=False, bias=True)")
-        self.in_channels, self.out_channels = in_channels, out_channels
-        self.lin = _Projection(in_channels, out_channels)
-        self.att_src = nn.Parameter(torch.empty(1, 1, out_channels))
-        self.att_dst = nn.Parameter(torch.empty(1, 1, out_channels))
-        self.bias = nn.Parameter(torch.empty(out_channels))
+        if add_self_loops or not bias or heads < 1:
+            raise NotImplementedError("the swarm_b200 kernels implement GATConv(add_self_loops=False, bias=True)")
+        self.in_channels, self.out_channels, self.heads, self.concat = in_channels, out_channels, heads, concat
+        self.lin = _Projection(in_channels, heads * out_channels)
+        self.att_src = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.bias = nn.Parameter(torch.empty(heads * out_channels if concat else out_channels))
         self.reset_parameters()
 
     def reset_parameters(self) -> None:
@@ -128,8 +133,22 @@ class GATConv(nn.Module):
         self.bias.data.zero_()
 
     def forward(self, x: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
-        _compute_device(x)                      # raises for host tensors unless SWARM_DEVICE names the serving B200
+        dev = _compute_device(x)                # raises for host tensors unless SWARM_DEVICE names the serving B200
         edge_index = edge_index.to(torch.int64).contiguous()
+        if self.heads > 1:
+            if self.in_channels > 64 or self.out_channels > 64:
+                raise NotImplementedError("the swarm_b200 GAT layer kernels cover in_channels, out_channels <= 64")
+            C_ = self.out_channels
+            csr = ops.csr_from_edges(edge_index.to(dev), x.shape[0])          # one grouping for all heads
+            zero = torch.zeros(C_, dtype=torch.float32, device=self.bias.device)
+            outs = []
+            for h in range(self.heads):
+                b = self.bias[h * C_:(h + 1) * C_] if self.concat else zero
+                outs.append(_GatLayerFunction.apply(x, self.lin.weight[h * C_:(h + 1) * C_], self.att_src[:, h:h + 1],
+                                                    self.att_dst[:, h:h + 1], b, edge_index, csr))
+            if self.concat:
+                return torch.cat(outs, dim=1)
+            return torch.stack(outs, dim=0).mean(dim=0) + self.bias.to(outs[0].device)
         if (self.in_channels, self.out_channels) != (_FEAT, _HIDDEN) or x.requires_grad:
             if self.in_channels > 64 or self.out_channels > 64:
                 raise NotImplementedError("the swarm_b200 GAT layer kernels cover in_channels, out_channels <= 64")

@@ -154,6 +154,53 @@ def test_gat_layer_argument_errors_and_empty_graph():
     with pytest.raises(NotImplementedError):
         sb.GATConv(65, 8).to(_dev())(torch.randn(3, 65, device=_dev()), torch.zeros(2, 0, dtype=torch.int64, device=_dev()))
     with pytest.raises(NotImplementedError):
-        sb.GATConv(8, 8, heads=2)
+        sb.GATConv(8, 8, add_self_loops=True)
     with pytest.raises(sb.SwarmError):
         sb.GATConv(4, 6)(torch.randn(5, 4), torch.zeros(2, 0, dtype=torch.int64))          # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("heads,concat,ci,co,n", [(3, True, 7, 8, 60), (2, False, 5, 16, 41), (4, True, 12, 4, 90)])
+def test_multi_head_layer_matches_per_head_oracle(heads, concat, ci, co, n):
+    """GATConv(heads = H): torch_geometric projects to H * C channels, runs one attention per head on its slice and
+    concatenates (``concat=True``) or averages (``concat=False``) the heads before the bias.  Reference = the oracle's
+    single-head layer applied per head under float64 autograd; ours = swarm_b200.GATConv (H launches of the layer kernels
+    on one CSR grouping) with gradients for every parameter and the node features."""
+    sb = _swarm()
+    g = torch.Generator().manual_seed(heads * 1000 + ci * 10 + co)
+    ei = _graph(n, seed=n + heads)
+    x = torch.randn(n, ci, generator=g)
+    conv = sb.GATConv(ci, co, heads=heads, concat=concat)
+    assert conv.lin.weight.shape == (heads * co, ci) and conv.att_src.shape == (1, heads, co)
+    assert conv.bias.shape == ((heads * co,) if concat else (co,))
+    with torch.no_grad():
+        conv.lin.weight.copy_(torch.randn(heads * co, ci, generator=g) * 0.5)
+        conv.att_src.copy_(torch.randn(1, heads, co, generator=g) * 0.5)
+        conv.att_dst.copy_(torch.randn(1, heads, co, generator=g) * 0.5)
+        conv.bias.copy_(torch.randn(conv.bias.shape, generator=g) * 0.1)
+    cot = torch.randn(n, heads * co if concat else co, generator=g)
+
+    def run_oracle(dtype):
+        xx = x.detach().clone().to(dtype).requires_grad_(True)
+        ps = [p.detach().clone().to(dtype).requires_grad_(True) for p in (conv.lin.weight, conv.att_src, conv.att_dst, conv.bias)]
+        w, a_s, a_d, b = ps
+        outs = []
+        for h in range(heads):
+            bh = b[h * co:(h + 1) * co] if concat else torch.zeros(co, dtype=dtype)
+            outs.append(_oracle_layer(xx, ei, w[h * co:(h + 1) * co], a_s[:, h:h + 1], a_d[:, h:h + 1], bh))
+        out = torch.cat(outs, dim=1) if concat else torch.stack(outs).mean(dim=0) + b
+        (out * cot.to(dtype)).sum().backward()
+        return out.detach(), [xx.grad] + [p.grad for p in ps]
+
+    ref64, g64 = run_oracle(torch.float64)
+    _, g32 = run_oracle(torch.float32)
+    conv = conv.to(_dev())
+    xg = x.detach().clone().to(_dev()).requires_grad_(True)
+    out = conv(xg, ei.to(_dev()))
+    assert out.shape == ref64.shape
+    assert (out.detach().cpu().double() - ref64).abs().max().item() <= 5e-6 * max(ref64.abs().max().item(), 1.0)
+    (out * cot.to(_dev())).sum().backward()
+    got = [xg.grad, conv.lin.weight.grad, conv.att_src.grad, conv.att_dst.grad, conv.bias.grad]
+    for name, a, r32, r64 in zip(["x", "lin.weight", "att_src", "att_dst", "bias"], got, g32, g64):
+        assert a is not None and r64 is not None, f"{name}: missing gradient (ours {a is not None}, oracle {r64 is not None})"
+        assert a.shape == r64.shape
+        _grad_check(a.cpu(), r32, r64, name)
