@@ -328,8 +328,9 @@ typedef struct SwarmTrainHyper {
 } SwarmTrainHyper;
 
 /* Phase 1: rollout tick of all cfg->num_envs envs with the online weights (pushes B transitions at ctl->ring_cursor),
- * draws graphs_per_update slot indices uniformly from the filled part of the ring (counter RNG keyed by
- * (sample_seed, tick, g); exported to indices int64[G] when indices != NULL), then gradient + loss of the update
+ * draws graphs_per_update slot indices uniformly and independently (i.e. with replacement; the reference's
+ * random.sample draws without) from the filled part of the ring (counter RNG keyed by (sample_seed, tick, g);
+ * exported to indices int64[G] when indices != NULL), then gradient + loss of the update
  * batch as swarm_dqn_grad.
  * workspace: swarm_dqn_workspace_bytes(cfg, G).  If the ring holds fewer than G slots, grad / loss are left
  * untouched and ctl->updating = 0 (the reference prints "Not enough samples" and skips, train:113-115). */
