@@ -130,5 +130,111 @@ SWARM_HD uint64_t knn_small_topk(uint64_t rank, int n, int k) {
   return row.perm;
 }
 
+// ---- the same algorithms, written for latency ----------------------------------------------------------------------
+// knn_small_topk walks the generic templates of knn_select.h element by element: every get() is two dependent 64-bit
+// variable shifts, every comparison a branch, and a warp executes the union of its lanes' paths -- measured 3-4 us per
+// tick on the critical path of a CTA.  knn_small_topk_fast produces the same permutation with word-level operations:
+//   * the row is (perm, rk): nibble p of `perm` = index at position p, nibble p of `rk` = its rank (kept in step);
+//   * std::__unguarded_partition: the comparisons of all 16 positions against the pivot are two 16-bit masks (SWAR
+//     byte compares on the rank word), the two scans become count-trailing / count-leading-zeros on them, and a swap
+//     exchanges the two mask bits too (the element that arrives at `first` was not greater, the one at `last` not less);
+//   * std::__insertion_sort is a STABLE sort (it only moves an element past strictly greater ones): short leftward scan
+//     on the rank word, then one masked shift of the nibble field instead of an element-by-element move;
+//   * the heap-select fallback of introselect (depth limit hit: rare) restarts with knn_small_topk.
+// tests/test_knn_select.py checks it against torch.topk and against knn_small_topk (every n^n pattern for n <= 7).
+SWARM_HD int knn_ctz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)x) - 1;
+#else
+  return __builtin_ctz(x);
+#endif
+}
+SWARM_HD int knn_fls32(uint32_t x) {     // index of the highest set bit
+#if defined(__CUDA_ARCH__)
+  return 31 - __clz((int)x);
+#else
+  return 31 - __builtin_clz(x);
+#endif
+}
+SWARM_HD int knn_nibble(uint64_t w, int p) { return (int)((w >> (4 * p)) & 15u); }
+SWARM_HD void knn_swap_nibbles(uint64_t& w, int p, int q) {
+  const uint64_t x = ((w >> (4 * p)) ^ (w >> (4 * q))) & 15u;
+  w ^= (x << (4 * p)) | (x << (4 * q));
+}
+// bit7 of each byte of x (x & 0x8080...) -> 8 consecutive bits
+SWARM_HD uint32_t knn_gather_msb(uint64_t x) { return (uint32_t)(((x >> 7) * 0x0102040810204080ull) >> 56); }
+SWARM_HD uint32_t knn_spread8(uint32_t x) {     // bit b -> bit 2 b
+  x = (x | (x << 4)) & 0x0F0Fu;
+  x = (x | (x << 2)) & 0x3333u;
+  x = (x | (x << 1)) & 0x5555u;
+  return x;
+}
+// 16-bit mask of the positions whose rank is >= v (v in 0 .. 16)
+SWARM_HD uint32_t knn_mask_ge(uint64_t rk, int v) {
+  const uint64_t lo = 0x0F0F0F0F0F0F0F0Full, hi = 0x8080808080808080ull;
+  const uint64_t vb = (uint64_t)(uint32_t)v * 0x0101010101010101ull;
+  const uint64_t even = (((rk & lo) | hi) - vb) & hi;            // byte b: position 2 b
+  const uint64_t odd = ((((rk >> 4) & lo) | hi) - vb) & hi;      // byte b: position 2 b + 1
+  return knn_spread8(knn_gather_msb(even)) | (knn_spread8(knn_gather_msb(odd)) << 1);
+}
+
+// stable sort by rank of positions [a, b): std::__insertion_sort
+SWARM_HD void knn_fast_insertion_sort(uint64_t& perm, uint64_t& rk, int a, int b) {
+  for (int i = a + 1; i < b; ++i) {
+    const int rv = knn_nibble(rk, i);
+    int pos = i;
+    while (pos > a && rv < knn_nibble(rk, pos - 1)) --pos;
+    if (pos != i) {
+      // nibbles [pos, i) move up by one, the element of position i lands at pos
+      const uint64_t field = (~0ull >> (64 - 4 * (i - pos))) << (4 * pos);          // nibbles pos .. i - 1
+      const uint64_t whole = field | (field << 4);                                   // nibbles pos .. i
+      const uint64_t iv = (uint64_t)(uint32_t)knn_nibble(perm, i);
+      perm = (perm & ~whole) | ((perm & field) << 4) | (iv << (4 * pos));
+      rk = (rk & ~whole) | ((rk & field) << 4) | ((uint64_t)(uint32_t)rv << (4 * pos));
+    }
+  }
+}
+
+SWARM_HD uint64_t knn_small_topk_fast(uint64_t rank, int n, int k) {
+  uint64_t perm = 0xFEDCBA9876543210ull, rk = rank;
+  if (k <= 0) return perm;
+  const int nth = k - 1;
+  int first = 0, last = n, depth = knn_lg(n) * 2;
+  while (last - first > 3) {
+    if (depth == 0) return knn_small_topk(rank, n, k);            // heap-select branch: the step-by-step emulation
+    --depth;
+    const int mid = first + (last - first) / 2;
+    // std::__move_median_to_first(first, first + 1, mid, last - 1)
+    const int ra = knn_nibble(rk, first + 1), rb = knn_nibble(rk, mid), rc = knn_nibble(rk, last - 1);
+    int m;
+    if (ra < rb) m = (rb < rc) ? mid : ((ra < rc) ? last - 1 : first + 1);
+    else m = (ra < rc) ? first + 1 : ((rb < rc) ? last - 1 : mid);
+    knn_swap_nibbles(perm, first, m);
+    knn_swap_nibbles(rk, first, m);
+    // std::__unguarded_partition(first + 1, last, pivot = *first)
+    const int pv = knn_nibble(rk, first);
+    uint32_t not_lt = knn_mask_ge(rk, pv);                       // positions with rank >= pivot
+    uint32_t not_gt = ~knn_mask_ge(rk, pv + 1) & 0xFFFFu;        // positions with rank <= pivot
+    int f = first + 1, l = last, cut;
+    while (true) {
+      f += knn_ctz32(not_lt >> f);                               // while (*f < pivot) ++f
+      l = knn_fls32(not_gt & ((1u << l) - 1u));                  // --l; while (pivot < *l) --l
+      if (!(f < l)) { cut = f; break; }
+      knn_swap_nibbles(perm, f, l);
+      knn_swap_nibbles(rk, f, l);
+      const uint32_t x1 = ((not_lt >> f) ^ (not_lt >> l)) & 1u;
+      not_lt ^= (x1 << f) | (x1 << l);
+      const uint32_t x2 = ((not_gt >> f) ^ (not_gt >> l)) & 1u;
+      not_gt ^= (x2 << f) | (x2 << l);
+      ++f;
+    }
+    if (cut <= nth) first = cut;
+    else last = cut;
+  }
+  knn_fast_insertion_sort(perm, rk, first, last);
+  knn_fast_insertion_sort(perm, rk, 0, k - 1);
+  return perm;
+}
+
 }  // namespace swarm
 #endif  // SWARM_KNN_SMALL_H

@@ -269,7 +269,7 @@ __device__ __forceinline__ uint64_t tile_knn_small_np(const TileThread& t, const
   const uint64_t rank = knn_small_ranks<NP>(u, r, present);
   if (knn_small_tie_free(present, N, K)) return knn_small_by_rank<NP>(r, K);
   if (rank != cache_rank) {
-    cache_nbr = knn_small_topk(rank, N, K);
+    cache_nbr = knn_small_topk_fast(rank, N, K);
     cache_rank = rank;
   }
   return cache_nbr;

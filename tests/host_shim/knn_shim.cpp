@@ -31,7 +31,8 @@ extern "C" void swarm_host_topk_smallest(const float* values, int rows, int n, i
 
 // The register-resident path of small swarms (csrc/knn_small.h), n <= 16, non-negative values or NaN.
 // mode 0: as the kernel runs it (rank answer when no tie can matter, emulation on the rank pattern otherwise);
-// mode 1: the emulation on the rank pattern for every row.  Returns the number of rows that took the emulation.
+// mode 1: the step-by-step emulation on the rank pattern for every row; mode 2: the word-level emulation
+// (knn_small_topk_fast) for every row.  Returns the number of rows that took the emulation.
 extern "C" int swarm_host_topk_small(const float* values, int rows, int n, int k, int mode, int32_t* out_idx) {
   int emulated = 0;
   for (int r = 0; r < rows; ++r) {
@@ -44,7 +45,7 @@ extern "C" int swarm_host_topk_small(const float* values, int rows, int n, int k
     if (mode == 0 && swarm::knn_small_tie_free(present, n, k)) {
       w = swarm::knn_small_by_rank<16>(rk, k);
     } else {
-      w = swarm::knn_small_topk(rank, n, k);
+      w = (mode == 2) ? swarm::knn_small_topk_fast(rank, n, k) : swarm::knn_small_topk(rank, n, k);
       ++emulated;
     }
     for (int j = 0; j < k; ++j) out_idx[(long long)r * k + j] = (int32_t)((w >> (4 * j)) & 15u);

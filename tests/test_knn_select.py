@@ -98,6 +98,8 @@ def test_small_register_path_matches_torch_topk(shim, n):
         took_shortcut |= emulated < rows.shape[0]
         got, emulated = _small(shim, rows, k, 1)
         assert emulated == rows.shape[0] and torch.equal(got, ref), f"n={n} k={k} (emulation on every row)"
+        got, emulated = _small(shim, rows, k, 2)
+        assert emulated == rows.shape[0] and torch.equal(got, ref), f"n={n} k={k} (word-level emulation on every row)"
     assert took_shortcut
 
 
@@ -110,3 +112,23 @@ def test_small_register_path_exhaustive_patterns(shim, n, k):
     assert torch.equal(got, ref)
     got, _ = _small(shim, grids, k, 1)
     assert torch.equal(got, ref)
+    got, _ = _small(shim, grids, k, 2)
+    assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("n", [8, 12, 16])
+def test_word_level_emulation_equals_the_stepwise_one_on_adversarial_patterns(shim, n):
+    """knn_small_topk_fast against knn_small_topk (and torch.topk) on patterns chosen to stress introselect: few
+    distinct values, sorted / reversed / organ-pipe rows (bad median-of-three pivots, depth limit), all k."""
+    g = torch.Generator().manual_seed(n)
+    rows = [torch.randint(0, m, (400, n), generator=g).float() for m in (2, 3, 4, n)]
+    base = torch.arange(n, dtype=torch.float32)
+    organ = torch.cat([base[::2], base[1::2].flip(0)])
+    rows += [base[None], base.flip(0)[None], organ[None], organ.flip(0)[None], (base // 2)[None], (base // 3).flip(0)[None]]
+    rows += [torch.stack([torch.roll(organ, s) for s in range(n)]), torch.stack([torch.roll(base // 2, s) for s in range(n)])]
+    rows = torch.cat(rows)
+    for k in range(1, n + 1):
+        ref = torch.topk(rows, k, dim=-1, largest=False).indices
+        slow, _ = _small(shim, rows, k, 1)
+        fast, _ = _small(shim, rows, k, 2)
+        assert torch.equal(slow, ref) and torch.equal(fast, ref), f"n={n} k={k}"
