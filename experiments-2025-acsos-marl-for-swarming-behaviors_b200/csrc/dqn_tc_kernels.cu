@@ -155,11 +155,12 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 // acc[mt][nt] += sum over this warp's 32 nodes of left(node, m) * right(node, n); m = mt * 16 + row, n = nt * 8 + col.
 // Fragment ownership (g = lane / 4, tg = lane % 4): A (g | g + 8, tg | tg + 4), B (k = tg | tg + 4, n = g),
 // C (g | g + 8, 2 tg | 2 tg + 1).  Small terms first, like the UMMA path.
+// `ksteps` = groups of 8 nodes that can be non-zero (a CTA with one 12-node graph contracts 2 groups in warp 0, none elsewhere)
 template <int MT, int NT, typename FL, typename FR>
-__device__ __forceinline__ void warp_node_gemm(float (&acc)[MT][NT][4], int lane, FL left, FR right) {
+__device__ __forceinline__ void warp_node_gemm(float (&acc)[MT][NT][4], int lane, int ksteps, FL left, FR right) {
   const int g = lane >> 2, tg = lane & 3;
 #pragma unroll 1
-  for (int ks = 0; ks < 4; ++ks) {
+  for (int ks = 0; ks < ksteps; ++ks) {
     const int n0 = ks * 8 + tg, n1 = n0 + 4;
     uint32_t ah[MT][4], al[MT][4], bh[NT][2], bl[NT][2];
 #pragma unroll
@@ -403,6 +404,9 @@ __global__ void __launch_bounds__(kTileThreads, 2) dqn_grad_tc_kernel(const __gr
   float* buf0 = stage_all + (warp * 2 + 0) * kStageBuf;         // U, then (with buf1) this warp's partial
   float* buf1 = stage_all + (warp * 2 + 1) * kStageBuf;         // R, then DP, then DO
   float* sred = reinterpret_cast<float*>(smem + L.red);
+  // node rows of this warp that belong to a graph (the rest contribute exact zeros: dq = 0)
+  const int wnodes = min(32, max(0, min(p.epb, p.n_graphs - (int)blockIdx.x * p.epb) * N - warp * 32));
+  const int wsteps = (wnodes + 7) >> 3;
 
   // ---- the sampled transition of this node (loads in flight while the weights are staged) -------------------------
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s;
@@ -554,7 +558,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) dqn_grad_tc_kernel(const __gr
   {
     const float* wdq = sdq + warp * 32;
     const int* wact = sact + warp * 32;
-    warp_node_gemm<1, 4>(acc2, lane, [&](int n, int m) { return wact[n] == m ? wdq[n] : 0.0f; },
+    warp_node_gemm<1, 4>(acc2, lane, wsteps, [&](int n, int m) { return wact[n] == m ? wdq[n] : 0.0f; },
                          [&](int n, int col) { return buf1[n * kStageLd + col]; });
   }
   float db2 = 0.0f;
@@ -588,7 +592,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) dqn_grad_tc_kernel(const __gr
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) acc1[mt][nt][q4] = 0.0f;
-  warp_node_gemm<2, 4>(acc1, lane, [&](int n, int m) { return buf1[n * kStageLd + m]; },
+  warp_node_gemm<2, 4>(acc1, lane, wsteps, [&](int n, int m) { return buf1[n * kStageLd + m]; },
                        [&](int n, int col) { return buf0[n * kStageLd + col]; });
   float db1 = 0.0f;
   for (int n = 0; n < 32; ++n) db1 += buf1[n * kStageLd + lane];
@@ -611,7 +615,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) dqn_grad_tc_kernel(const __gr
     for (int q4 = 0; q4 < 4; ++q4) acc0[mt][0][q4] = 0.0f;
   {
     const float* wxb = sxbar + warp * 32 * 8;
-    warp_node_gemm<2, 1>(acc0, lane, [&](int n, int m) { return buf1[n * kStageLd + m]; },
+    warp_node_gemm<2, 1>(acc0, lane, wsteps, [&](int n, int m) { return buf1[n * kStageLd + m]; },
                          [&](int n, int col) { return wxb[n * 8 + col]; });
   }
   float db0 = 0.0f;
