@@ -68,7 +68,15 @@ def test_full_size_rollout_is_batch_invariant_and_matches_oracle(scen, B, N, mod
     o = ops.rollout(cfg, w, state, T0, trace=dict(actions=True))
     got_actions = o["trace_actions"][:, idx.to(dev)].cpu().long()
     same = (got_actions == ref["actions"]).all(dim=0).all(dim=1)                    # per sampled env
-    assert same.float().mean() >= 0.9, "greedy action streams differ from the oracle on more than 10% of the sample"
+    # an env may only leave the oracle's action stream at a tick where the oracle itself has a float32 near-tie between
+    # its two best actions (top-2 Q gap <= 2e-5 of max |Q|) -- the criterion of tests/test_gpu_golden_sweep.py
+    for e in torch.nonzero(~same).flatten().tolist():
+        diff = got_actions[:, e] != ref["actions"][:, e]                            # [T0, N]
+        t0 = int(torch.nonzero(diff.any(dim=1))[0])
+        q = ref["q"][t0, e]                                                         # [N, 9]
+        top2 = q.topk(2, dim=-1).values
+        gap = (top2[:, 0] - top2[:, 1]) / q.abs().amax(dim=-1)
+        assert (gap[diff[t0]] <= 2e-5).all(), f"env {int(idx[e])}: action differs from the oracle at tick {t0} outside a near-tie"
     got_pos = o["state"][idx.to(dev)][..., :2].cpu()
     assert torch.allclose(got_pos[same], ref["pos"][-1][same], rtol=0, atol=1e-5)
 
