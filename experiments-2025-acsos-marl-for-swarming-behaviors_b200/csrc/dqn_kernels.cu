@@ -588,22 +588,34 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
 #pragma unroll
       for (int i = 0; i < kPer; ++i) g_[i] = 0.0f;
       const uint64_t* mine = p.peers.data[p.peers.rank] + (size_t)par * W * SWARM_XCHG_STRIDE;
-      for (int r = 0; r < W; ++r) {
-        const uint64_t* src = mine + (size_t)r * SWARM_XCHG_STRIDE;
-        uint64_t got[kPer];
+      // the slots of four ranks are polled together (28 loads in flight per thread): a poll is a round trip to memory, and
+      // waiting rank by rank made the exchange cost grow with the world size (8 ranks: eight round trips)
+      constexpr int kGroup = 4;
+      for (int r0 = 0; r0 < W; r0 += kGroup) {
+        uint64_t got[kGroup][kPer];
         bool ok = false;
         for (long long it = 0; it < (1ll << 26) && !ok; ++it) {     // bounded: a lost peer traps instead of hanging
           ok = true;
 #pragma unroll
-          for (int i = 0; i < kPer; ++i) {
-            const int o = tid + 256 * i;
-            got[i] = (o <= SWARM_W_COUNT) ? ld_relaxed_sys_u64(src + o) : ((uint64_t)epoch << 32);
-            ok = ok && ((uint32_t)(got[i] >> 32) == epoch);
+          for (int q = 0; q < kGroup; ++q) {
+            const uint64_t* src = mine + (size_t)(r0 + q) * SWARM_XCHG_STRIDE;
+            const bool live = r0 + q < W;
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) {
+              const int o = tid + 256 * i;
+              got[q][i] = (live && o <= SWARM_W_COUNT) ? ld_relaxed_sys_u64(src + o) : ((uint64_t)epoch << 32);
+            }
           }
+#pragma unroll
+          for (int q = 0; q < kGroup; ++q)
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) ok = ok && ((uint32_t)(got[q][i] >> 32) == epoch);
         }
         if (!ok) __trap();
 #pragma unroll
-        for (int i = 0; i < kPer; ++i) g_[i] += __uint_as_float((uint32_t)got[i]);
+        for (int q = 0; q < kGroup; ++q)
+#pragma unroll
+          for (int i = 0; i < kPer; ++i) g_[i] += __uint_as_float((uint32_t)got[q][i]);       // rank order; absent ranks add +0
       }
 #pragma unroll
       for (int i = 0; i < kPer; ++i) {
