@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kStepThreads) sim_step_kernel(const __grid_con
 
 // ---- persistent TMA-pipelined variant --------------------------------------------------------------------------
 constexpr int kStepStages = 4;     // input ring depth
-constexpr int kStepOutBufs = 3;    // output staging ring depth
+constexpr int kStepOutBufs = 4;    // output staging ring depth (two tiles per loop iteration)
 
 __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -129,7 +129,7 @@ struct StepStreamSmem {
   float4 sout[kStepOutBufs][kStepThreads];
   int32_t ain[kStepStages][kStepThreads];
   float rout[kStepOutBufs][kStepThreads];
-  float sdg[kStepThreads];
+  float sdg[2][kStepThreads];
   uint64_t full[kStepStages];
   float2 force_of_action[16];     // decode table: flat action -> (ux, uy); entries >= 9 are zero (invalid actions)
 };
@@ -173,82 +173,107 @@ __global__ void __launch_bounds__(kStepThreads, 4) sim_step_stream_kernel(const 
   }
   __syncthreads();
 
+  // Two tiles per loop iteration: the mbarrier waits, the proxy fence, the block barrier and thread 0's copy
+  // bookkeeping are paid once per PAIR of tiles (the kernel is issue bound at ~290 instructions per agent, ~25 of them
+  // this per-tile overhead), and the two agents of a thread are independent instruction streams.
+  auto step_agent = [&](int stage, int ob, long long gidx, int which) -> float {
+    float reward = 0.0f;
+    float4 s = sm.sin[stage][tid];
+    const int action = sm.ain[stage][tid];
+    float gx, gy;
+    const float2 u = sm.force_of_action[min((unsigned)action, 9u)];      // vmas _set_action (a // 3, a % 3) -> (0, -1, +1)
+    float fx = u.x, fy = u.y;
+    uint8_t flags = 0;
+    uint32_t cmask = 0;
+    if (OA) {
+      const float dx = __fsub_rn(s.x, c.obstacle_x), dy = __fsub_rn(s.y, c.obstacle_y);
+      if (__fmaf_rn(dy, dy, __fmul_rn(dx, dx)) <= p.qmax_ao) {
+        if (contact_force(s.x, s.y, c.obstacle_x, c.obstacle_y, p.dmin_ao, c.collision_force, c.contact_margin, gx, gy)) {
+          fx = __fadd_rn(fx, gx);
+          fy = __fadd_rn(fy, gy);
+          flags |= SWARM_FLAG_OBSTACLE_CONTACT;
+        }
+      }
+    }
+    agent_contacts(&sm.sin[stage][envbase], N, i, s.x, s.y, p.qmax_aa, p.dmin_aa, c.collision_force, c.contact_margin, fx,
+                   fy, cmask);
+    integrate(s, fx, fy, c.dt, p.one_minus_drag);
+
+    const float dgoal = goal_distance(s.x, s.y, c);
+    float dobs = 0.0f;
+    if (OA) {
+      dobs = obstacle_distance(s.x, s.y, c);
+      reward = oa_reward(dgoal, dobs, c, flags);
+    } else {
+      sm.sdg[which][tid] = dgoal;
+    }
+    sm.sout[ob][tid] = s;
+    if (EXTRAS) {
+      if (p.flags) p.flags[gidx] = flags;
+      if (p.contact) p.contact[gidx] = cmask;
+      if (p.obs) {
+        float2* o = reinterpret_cast<float2*>(p.obs + gidx * 6);
+        o[0] = make_float2(s.x, s.y);
+        o[1] = make_float2(s.z, s.w);
+        o[2] = make_float2(c.goal_x, c.goal_y);
+      }
+      if (p.dist) p.dist[gidx] = make_float2(dgoal, dobs);
+    }
+    return reward;
+  };
+
   int stage = 0, ob = 0;
   uint32_t parity = 0;
   long long a0 = first * tile_agents;
   const long long a_stride = stride * tile_agents;
-  for (long long it = 0; it < n_my; ++it, a0 += a_stride) {
-    const long long gidx = a0 + tid;
+  for (long long it = 0; it < n_my; it += 2, a0 += 2 * a_stride) {
+    const bool two = it + 1 < n_my;
+    float reward0 = 0.0f, reward1 = 0.0f;
     tc::mbar_wait(&sm.full[stage], parity);
-
-    float reward = 0.0f;
-    if (active) {
-      float4 s = sm.sin[stage][tid];
-      const int action = sm.ain[stage][tid];
-      float gx, gy;
-      const float2 u = sm.force_of_action[min((unsigned)action, 9u)];      // vmas _set_action (a // 3, a % 3) -> (0, -1, +1)
-      float fx = u.x, fy = u.y;
-      uint8_t flags = 0;
-      uint32_t cmask = 0;
-      if (OA) {
-        const float dx = __fsub_rn(s.x, c.obstacle_x), dy = __fsub_rn(s.y, c.obstacle_y);
-        if (__fmaf_rn(dy, dy, __fmul_rn(dx, dx)) <= p.qmax_ao) {
-          if (contact_force(s.x, s.y, c.obstacle_x, c.obstacle_y, p.dmin_ao, c.collision_force, c.contact_margin, gx, gy)) {
-            fx = __fadd_rn(fx, gx);
-            fy = __fadd_rn(fy, gy);
-            flags |= SWARM_FLAG_OBSTACLE_CONTACT;
-          }
-        }
-      }
-      agent_contacts(&sm.sin[stage][envbase], N, i, s.x, s.y, p.qmax_aa, p.dmin_aa, c.collision_force, c.contact_margin, fx,
-                     fy, cmask);
-      integrate(s, fx, fy, c.dt, p.one_minus_drag);
-
-      const float dgoal = goal_distance(s.x, s.y, c);
-      float dobs = 0.0f;
-      if (OA) {
-        dobs = obstacle_distance(s.x, s.y, c);
-        reward = oa_reward(dgoal, dobs, c, flags);
-      } else {
-        sm.sdg[tid] = dgoal;
-      }
-      sm.sout[ob][tid] = s;
-      if (EXTRAS) {
-        if (p.flags) p.flags[gidx] = flags;
-        if (p.contact) p.contact[gidx] = cmask;
-        if (p.obs) {
-          float2* o = reinterpret_cast<float2*>(p.obs + gidx * 6);
-          o[0] = make_float2(s.x, s.y);
-          o[1] = make_float2(s.z, s.w);
-          o[2] = make_float2(c.goal_x, c.goal_y);
-        }
-        if (p.dist) p.dist[gidx] = make_float2(dgoal, dobs);
-      }
+    if (active) reward0 = step_agent(stage, ob, a0 + tid, 0);
+    if (two) {
+      tc::mbar_wait(&sm.full[stage + 1], parity);
+      if (active) reward1 = step_agent(stage + 1, ob + 1, a0 + a_stride + tid, 1);
     }
     if (!OA) {
+      // GoTo's collective reward (go_to:108-115): 0 + (-d_0) + (-d_1) + ... in agent order
       __syncthreads();
-      if (active)
-        for (int a = 0; a < N; ++a) reward = __fadd_rn(reward, -sm.sdg[envbase + a]);
+      if (active) {
+        for (int a = 0; a < N; ++a) reward0 = __fadd_rn(reward0, -sm.sdg[0][envbase + a]);
+        if (two)
+          for (int a = 0; a < N; ++a) reward1 = __fadd_rn(reward1, -sm.sdg[1][envbase + a]);
+      }
     }
-    if (active) sm.rout[ob][tid] = reward;
+    if (active) {
+      sm.rout[ob][tid] = reward0;
+      if (two) sm.rout[ob + 1][tid] = reward1;
+    }
 
     tc::fence_async_smem();          // generic-proxy writes of sout / rout -> visible to the bulk-copy engine
-    __syncthreads();                 // ... and every thread is done reading sin[stage]
+    __syncthreads();                 // ... and every thread is done reading sin[stage], sin[stage + 1] (and sdg)
     if (tid == 0) {
       bulk_store(p.state_out + a0, sm.sout[ob], sbytes);
       if (p.rewards) bulk_store(p.rewards + a0, sm.rout[ob], abytes);
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      if (it + kStepStages < n_my) {
-        const long long n0 = a0 + kStepStages * a_stride;
-        mbar_expect_tx(&sm.full[stage], sbytes + abytes);
-        bulk_load(sm.sin[stage], p.state_in + n0, sbytes, &sm.full[stage]);
-        bulk_load(sm.ain[stage], p.actions + n0, abytes, &sm.full[stage]);
+      if (two) {
+        bulk_store(p.state_out + a0 + a_stride, sm.sout[ob + 1], sbytes);
+        if (p.rewards) bulk_store(p.rewards + a0 + a_stride, sm.rout[ob + 1], abytes);
       }
-      // the staging buffer written two iterations from now was last read by the store issued one iteration ago
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      for (int q = 0; q < 2; ++q) {
+        if (it + q + kStepStages < n_my) {
+          const long long n0 = a0 + (kStepStages + q) * a_stride;
+          mbar_expect_tx(&sm.full[stage + q], sbytes + abytes);
+          bulk_load(sm.sin[stage + q], p.state_in + n0, sbytes, &sm.full[stage + q]);
+          bulk_load(sm.ain[stage + q], p.actions + n0, abytes, &sm.full[stage + q]);
+        }
+      }
+      // the staging buffers written in the next iteration were last read by the stores issued one iteration ago
       asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
     }
-    if (++stage == kStepStages) { stage = 0; parity ^= 1u; }
-    if (++ob == kStepOutBufs) ob = 0;
+    stage += 2;
+    if (stage == kStepStages) { stage = 0; parity ^= 1u; }
+    ob += 2;
+    if (ob == kStepOutBufs) ob = 0;
   }
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
