@@ -13,6 +13,7 @@
 //   complete_edges_kernel   train_gcn_dqn.py:94-110 edge list (closed form)
 // The Q-network then runs through the generic CSR path (csr_kernels.cu).
 #include "knn_select.h"
+#include "knn_small.h"
 #include "gatq_device.cuh"
 
 namespace swarm {
@@ -122,35 +123,27 @@ __global__ void __launch_bounds__(kLargeThreads) goto_reward_large_kernel(SwarmC
 }
 
 // ---- kNN, partial_sort branch ------------------------------------------------------------------
-// Virtual (value, index) row of agent `self`: entries [0, K) are the heap in shared memory, entries >= K are
-// computed on demand and never written back (heap_select only ever reads position i once, before overwriting it).
-struct VirtualRow {
-  float* hv;            // heap values  [K][threads]
-  int* hi;              // heap indices [K][threads]
-  const float2* pos;
-  float sx, sy;
-  int K;
-  __device__ __forceinline__ float dist(int j) const {
-    const float2 o = pos[j];
-    return norm2(__fsub_rn(o.x, sx), __fsub_rn(o.y, sy));
-  }
-  __device__ __forceinline__ KnnPair get(int j) const {
-    KnnPair p;
-    if (j < K) {
-      p.v = hv[j * kLargeThreads];
-      p.i = hi[j * kLargeThreads];
-    } else {
-      p.v = dist(j);
-      p.i = j;
-    }
+// The K-entry heap of std::partial_sort lives in shared memory as ONE 8-byte word per entry: (key, index) with
+// key = the distance's bit pattern (monotone for the non-negative 2-norm; every NaN maps to one key above +inf, like
+// torch's comparator -- knn_small.h), so a heap access is a single 64-bit load / store and a comparison a single integer
+// compare.  The algorithms are the generic ones of knn_select.h (make_heap, __adjust_heap for the replace-top of
+// heap_select, sort_heap); only indices leave the kernel.
+struct KnnKeyPair {
+  uint32_t v;
+  int i;
+};
+__device__ __forceinline__ bool knn_less(const KnnKeyPair& a, const KnnKeyPair& b) { return a.v < b.v; }
+
+struct HeapRow {
+  uint2* h;             // [K][threads]
+  __device__ __forceinline__ KnnKeyPair get(int j) const {
+    const uint2 w = h[j * kLargeThreads];
+    KnnKeyPair p;
+    p.v = w.x;
+    p.i = (int)w.y;
     return p;
   }
-  __device__ __forceinline__ void set(int j, const KnnPair& p) {
-    if (j < K) {
-      hv[j * kLargeThreads] = p.v;
-      hi[j * kLargeThreads] = p.i;
-    }
-  }
+  __device__ __forceinline__ void set(int j, const KnnKeyPair& p) { h[j * kLargeThreads] = make_uint2(p.v, (uint32_t)p.i); }
 };
 
 struct LargeKnnParams {
@@ -161,14 +154,13 @@ struct LargeKnnParams {
   int32_t edges_per_env;
 };
 
-// grid = (envs, chunks of 256 agents); dynamic smem: positions float2[N], heap values float[K][256], indices int[K][256]
+// grid = (envs, chunks of 256 agents); dynamic smem: positions float2[N], heap uint2[K][256]
 __global__ void __launch_bounds__(kLargeThreads) knn_large_kernel(const __grid_constant__ LargeKnnParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SwarmConfig& c = p.cfg;
   const int N = c.n_agents, K = c.knn_k;
   float2* spos = reinterpret_cast<float2*>(smem_raw);
-  float* hv = reinterpret_cast<float*>(spos + N);
-  int* hi = reinterpret_cast<int*>(hv + K * kLargeThreads);
+  uint2* hw = reinterpret_cast<uint2*>(spos + N);
   const long long env = blockIdx.x;          // envs on grid.x (no 65 535 cap), agent chunks on grid.y
   for (int j = threadIdx.x; j < N; j += kLargeThreads) {
     const float4 s = p.state[env * N + j];
@@ -177,60 +169,66 @@ __global__ void __launch_bounds__(kLargeThreads) knn_large_kernel(const __grid_c
   __syncthreads();
   const int i = blockIdx.y * kLargeThreads + threadIdx.x;
   if (i >= N) return;
-  VirtualRow row{hv + threadIdx.x, hi + threadIdx.x, spos, spos[i].x, spos[i].y, K};
+  const float sx = spos[i].x, sy = spos[i].y;
+  HeapRow heap{hw + threadIdx.x};
   for (int j = 0; j < K; ++j) {
-    KnnPair pr;
-    pr.v = row.dist(j);
+    const float2 o = spos[j];
+    KnnKeyPair pr;
+    pr.v = knn_key_nonneg(norm2(__fsub_rn(o.x, sx), __fsub_rn(o.y, sy)));
     pr.i = j;
-    row.set(j, pr);
+    heap.set(j, pr);
   }
   // std::partial_sort(b, b + k, e) = __heap_select + __sort_heap; the select loop is open-coded to skip the sqrt of
   // candidates whose squared distance already rules them out (q_j >= q_top  =>  d_j >= d_top  =>  !comp)
-  knn_make_heap(row, 0, K);
+  knn_make_heap(heap, 0, K);
   // The candidates K .. N-1 are visited in index order, kChunk at a time.  A branch-free sweep (packed subtract, one
   // compare per candidate) marks those whose squared distance is below the heap top's at the START of the chunk --
   // the top only ever decreases, so this is a superset of the candidates heap_select would accept -- and only the
-  // marked ones go through the (divergent, ~100-instruction) replace-top path, re-tested against the current top.
+  // marked ones go through the (divergent) replace-top path, re-tested against the current top.
   // A warp therefore pays for max-over-lanes(inserts per chunk) heap updates instead of one per candidate at which
   // ANY of its 32 lanes inserts.  (Measured on C4: 16 per chunk 3.8 ms, 32: 2.9 ms, 64: 3.5 ms, unchunked: 5.7 ms.)
   constexpr int kChunk = 32;
-  const float2 neg = make_float2(-row.sx, -row.sy);
+  const float2 neg = make_float2(-sx, -sy);
+  // squared-distance threshold for "could be below the top" (conservative: never drops a candidate with d_j < top);
+  // a NaN top is above every real distance
+  auto threshold = [](uint32_t top_key) {
+    const float top = __uint_as_float(top_key);
+    return (top != top) ? INFINITY : __fmul_rn(top, top) * 1.0000005f + 1e-37f;
+  };
   for (int base = K; base < N; base += kChunk) {
     const int cnt = (N - base < kChunk) ? (N - base) : kChunk;
-    const float top0 = hv[threadIdx.x];
-    const float thr0 = __fmul_rn(top0, top0) * 1.0000005f + 1e-37f;     // conservative: never drops a candidate with d_j < top
+    const float thr0 = threshold(hw[threadIdx.x].x);
     uint32_t m = 0;
 #pragma unroll 8
     for (int u = 0; u < cnt; ++u) {
       const float2 d = __fadd2_rn(spos[base + u], neg);
       const float q = __fmaf_rn(d.y, d.y, __fmul_rn(d.x, d.x));
-      m |= (q < thr0) ? (1u << u) : 0u;
+      m |= (q < thr0 || q != q) ? (1u << u) : 0u;
     }
     while (m) {
       const int j = base + __ffs(m) - 1;
       m &= m - 1;
       const float2 o = spos[j];
-      const float dx = __fsub_rn(o.x, row.sx), dy = __fsub_rn(o.y, row.sy);
+      const float dx = __fsub_rn(o.x, sx), dy = __fsub_rn(o.y, sy);
       const float q = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
-      const float top = hv[threadIdx.x];
-      if (q < __fmul_rn(top, top) * 1.0000005f + 1e-37f) {
-        KnnPair cand;
-        cand.v = __fsqrt_rn(q);
+      const uint32_t top_key = hw[threadIdx.x].x;
+      if (q < threshold(top_key) || q != q) {
+        KnnKeyPair cand;
+        cand.v = knn_key_nonneg(__fsqrt_rn(q));
         cand.i = j;
-        KnnPair first = row.get(0);
-        if (knn_less(cand, first)) knn_adjust_heap(row, 0, 0, K, cand);     // __pop_heap(first, middle, j)
+        if (cand.v < top_key) knn_adjust_heap(heap, 0, 0, K, cand);       // __pop_heap(first, middle, j)
       }
     }
   }
-  knn_sort_heap(row, 0, K);
+  knn_sort_heap(heap, 0, K);
   if (p.nbr)
-    for (int r = 0; r < K; ++r) p.nbr[(env * N + i) * K + r] = hi[r * kLargeThreads + threadIdx.x];
+    for (int r = 0; r < K; ++r) p.nbr[(env * N + i) * K + r] = (int)hw[r * kLargeThreads + threadIdx.x].y;
   if (p.edges) {
     const int E = p.edges_per_env;
     int32_t* r0 = p.edges + env * 2 * E;
     int32_t* r1 = r0 + E;
     for (int r = 0; r < K; ++r) {
-      const int a = hi[r * kLargeThreads + threadIdx.x];
+      const int a = (int)hw[r * kLargeThreads + threadIdx.x].y;
       const int e = (i * K + r) * 2;
       r0[e] = i; r1[e] = a;
       r0[e + 1] = a; r1[e + 1] = i;
