@@ -32,6 +32,9 @@ cudaError_t launch_episode_end(const SwarmConfig& c, SwarmTrainCtl* ctl, float* 
                                float* stats, long long max_episodes, double eps0, double decay, double min_eps,
                                cudaStream_t stream);
 bool gatq_knn_large_fits(int N, int K);
+bool gatq_knn_large_x_fits(int N, int K);
+cudaError_t launch_gatq_knn_large_x(const SwarmConfig& c, const float* weights, const float* state, const int32_t* nbr,
+                                    float* q, int32_t* actions, cudaStream_t stream);
 cudaError_t launch_gatq_knn_large(const SwarmConfig& c, const float* weights, const float* state, const int32_t* nbr,
                                   float* q, int32_t* actions, cudaStream_t stream);
 long long csr_workspace_bytes(int n, long long E);
@@ -297,7 +300,11 @@ int swarm_rollout_large(const SwarmConfig* cfg, const float* weights, float* sta
   if (ticks < 0) return fail(SWARM_ERR_INVALID_ARG, "ticks must be >= 0");
   if ((int64_t)cfg->knn_k * 64 > cfg->n_agents)
     return fail(SWARM_ERR_UNSUPPORTED, "large-swarm kNN implements torch.topk's partial_sort branch (64 k <= n)");
-  if (!gatq_knn_large_fits(cfg->n_agents, cfg->knn_k))
+  // attention in input space (no projected-feature tile: envs up to 4 096 agents fit) unless SWARM_TC=0 asks for the
+  // bit-faithful forward of swarm_gatq_forward_knn_large
+  const char* tc_env = std::getenv("SWARM_TC");
+  const bool xspace = !(tc_env && tc_env[0] == '0');
+  if (!(xspace ? gatq_knn_large_x_fits(cfg->n_agents, cfg->knn_k) : gatq_knn_large_fits(cfg->n_agents, cfg->knn_k)))
     return fail(SWARM_ERR_UNSUPPORTED, "the env does not fit shared memory: step it with swarm_graph_build + "
                                        "swarm_csr_from_edges + swarm_gatq_forward_csr + swarm_sim_step");
   if (workspace_bytes < swarm_rollout_large_workspace_bytes(cfg)) return fail(SWARM_ERR_INVALID_ARG, "workspace too small");
@@ -318,7 +325,9 @@ int swarm_rollout_large(const SwarmConfig* cfg, const float* weights, float* sta
     // returns / hits accumulated by the step kernel: three launches, nothing but the state leaves the device
     if (cudaError_t e = launch_graph_large(*cfg, state, nullptr, nbr, p.edges_per_env, st); e != cudaSuccess)
       return check_cuda(e, "swarm_rollout_large (graph)");
-    if (cudaError_t e = launch_gatq_knn_large(*cfg, weights, state, nbr, nullptr, actions, st); e != cudaSuccess)
+    if (cudaError_t e = xspace ? launch_gatq_knn_large_x(*cfg, weights, state, nbr, nullptr, actions, st)
+                               : launch_gatq_knn_large(*cfg, weights, state, nbr, nullptr, actions, st);
+        e != cudaSuccess)
       return check_cuda(e, "swarm_rollout_large (forward)");
     if (cudaError_t e = launch_sim_step_large(p, st); e != cudaSuccess) return check_cuda(e, "swarm_rollout_large (step)");
   }

@@ -402,6 +402,188 @@ __global__ void __launch_bounds__(kQLThreads, 1) gatq_knn_large_kernel(const __g
   }
 }
 
+// ---- the same forward with the attention in input space (tile_tc_device.cuh) -------------------------------------
+// sum_e alpha_e h_src(e) = W0 (sum_e alpha_e x_src(e)) and <h_j, att> = <x_j, W0^T att>: no tile of projected features
+// (N x 128 B -- what limited the kernel above to one CTA per SM and ~1 200 agents), the gather per in-edge is one 16-byte
+// state instead of a 128-byte feature row, and the topk table is read from global memory.  Shared memory: 20 B per
+// agent + 2 K B of reversed lists + 8 B of list offsets -> 76 KB at N = 1 024, k = 10 (two to three CTAs per SM), 202 KB
+// at N = 4 096.  Same mathematics, float32-level different rounding than the bit-faithful kernel above; used where only
+// the greedy actions are consumed (swarm_rollout_large), SWARM_TC=0 keeps the bit-faithful one.
+__host__ __device__ inline size_t large_qx_smem_bytes(int N, int K) {
+  size_t b = (size_t)((TW_COUNT + 3) & ~3) * 4 + 64;  // weights, v_s / v_d
+  b += (size_t)N * 16;                                // states
+  b += (size_t)N * 4;                                 // alpha_src
+  b += (size_t)(N + 1) * 4 * 2;                       // list offsets, fill cursors
+  b += (size_t)N * K * 2;                             // reversed lists (uint16)
+  return b + 64;
+}
+
+__global__ void __launch_bounds__(kQLThreads) gatq_knn_large_x_kernel(const __grid_constant__ LargeQParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SwarmConfig& c = p.cfg;
+  const int N = c.n_agents, K = c.knn_k;
+  const int tid = threadIdx.x;
+  const long long env = blockIdx.x;
+  float* sw = reinterpret_cast<float*>(smem_raw);
+  float* sv = sw + ((TW_COUNT + 3) & ~3);                 // v_s[8], v_d[8]
+  float4* sst = reinterpret_cast<float4*>(sv + 16);
+  float* sas = reinterpret_cast<float*>(sst + N);
+  int* roff = reinterpret_cast<int*>(sas + N);           // [N + 1]
+  int* rcur = roff + (N + 1);                            // [N + 1]
+  uint16_t* rev = reinterpret_cast<uint16_t*>(rcur + (N + 1));
+  __shared__ int warp_tot[kQLThreads / 32];
+
+  stage_weights(p.weights, sw, tid, kQLThreads);
+  const int32_t* nbr = p.nbr + env * N * K;
+  for (int i = tid; i < N; i += kQLThreads) sst[i] = p.state[env * N + i];
+  for (int i = tid; i <= N; i += kQLThreads) rcur[i] = 0;
+  __syncthreads();
+  if (tid < 16) {
+    // attention vectors pulled through the projection: v[k] = sum_c att[c] W0[c][k]
+    const int k = tid & 7;
+    const float* att = sw + (tid < 8 ? TW_ATT_S : TW_ATT_D);
+    float v = 0.0f;
+    if (k < 7)
+      for (int cc = 0; cc < 32; ++cc) v = fmaf(att[cc], sw[TW_W0T + k * 32 + cc], v);
+    sv[tid] = v;
+  }
+  // in-degree from other rows
+  for (int e = tid; e < N * K; e += kQLThreads) {
+    const int ii = e / K, a = nbr[e];
+    if (a != ii) atomicAdd(&rcur[a], 1);
+  }
+  __syncthreads();
+  // exclusive scan of rcur[0..N) -> roff (every thread owns a contiguous chunk)
+  {
+    const int per = (N + kQLThreads - 1) / kQLThreads;
+    const int b0 = tid * per;
+    int local = 0;
+    for (int k = 0; k < per; ++k) local += (b0 + k < N) ? rcur[b0 + k] : 0;
+    int incl = local;
+#pragma unroll
+    for (int sft = 1; sft < 32; sft <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, sft);
+      if ((tid & 31) >= sft) incl += v;
+    }
+    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < (tid >> 5); ++w) base += warp_tot[w];
+    int run = base + incl - local;
+    for (int k = 0; k < per; ++k) {
+      if (b0 + k < N) {
+        const int cnt = rcur[b0 + k];
+        roff[b0 + k] = run;
+        run += cnt;
+      }
+    }
+    if (tid == kQLThreads - 1) roff[N] = base + incl;
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += kQLThreads) rcur[i] = 0;
+  __syncthreads();
+  for (int e = tid; e < N * K; e += kQLThreads) {
+    const int ii = e / K, a = nbr[e];
+    if (a != ii) rev[roff[a] + atomicAdd(&rcur[a], 1)] = (uint16_t)ii;
+  }
+  __syncthreads();
+  // sort every list by row index (the fill order of the atomics is not deterministic; sums must be) and publish the
+  // alpha_src term of every node
+  for (int i = tid; i < N; i += kQLThreads) {
+    const int b = roff[i], e = roff[i + 1];
+    for (int x = b + 1; x < e; ++x) {
+      const uint16_t v = rev[x];
+      int y = x - 1;
+      while (y >= b && rev[y] > v) { rev[y + 1] = rev[y]; --y; }
+      rev[y + 1] = v;
+    }
+    const float4 st = sst[i];
+    sas[i] = fmaf(st.x, sv[0], fmaf(st.y, sv[1], fmaf(st.z, sv[2], fmaf(st.w, sv[3],
+             fmaf(c.goal_x, sv[4], fmaf(c.goal_y, sv[5], (float)i * sv[6]))))));
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += kQLThreads) {
+    const float4 st = sst[i];
+    const float adst = fmaf(st.x, sv[8], fmaf(st.y, sv[9], fmaf(st.z, sv[10], fmaf(st.w, sv[11],
+                       fmaf(c.goal_x, sv[12], fmaf(c.goal_y, sv[13], (float)i * sv[14]))))));
+    const int b = roff[i], e = roff[i + 1];
+    const int32_t* own = nbr + (size_t)i * K;
+    int split = b;                                    // first list entry with row index > i
+    while (split < e && rev[split] < i) ++split;
+    // in-edges in edge-list order (simulator.py:20-24): rows < i that list i, the own row (self twice), rows > i,
+    // the trailing (0,0) of node 0
+    auto for_each_source = [&](auto&& fn) {
+      for (int x = b; x < split; ++x) fn((int)rev[x]);
+      for (int r = 0; r < K; ++r) {
+        const int a = own[r];
+        if (a == i) fn(i);
+        fn(a);
+      }
+      for (int x = split; x < e; ++x) fn((int)rev[x]);
+      if (i == 0) fn(0);
+    };
+    float amax = -INFINITY;
+    for_each_source([&](int j) { amax = fmaxf(amax, sas[j]); });
+    const float m = gat_logit(amax, adst);             // LeakyReLU and the rounded add are monotone
+    float den = 0.0f, acc_id = 0.0f;
+    float2 acc_p = make_float2(0.f, 0.f), acc_v = make_float2(0.f, 0.f);
+    for_each_source([&](int j) {
+      const float4 sj = sst[j];
+      const float w = __expf(gat_logit(sas[j], adst) - m);
+      den = __fadd_rn(den, w);
+      acc_p = __ffma2_rn(make_float2(w, w), make_float2(sj.x, sj.y), acc_p);
+      acc_v = __ffma2_rn(make_float2(w, w), make_float2(sj.z, sj.w), acc_v);
+      acc_id = fmaf(w, (float)j, acc_id);
+    });
+    const float inv = 1.0f / __fadd_rn(den, 1e-16f);
+    const float wsum = den * inv;
+    const float xm[7] = {acc_p.x * inv, acc_p.y * inv, acc_v.x * inv, acc_v.y * inv, c.goal_x * wsum, c.goal_y * wsum,
+                         acc_id * inv};
+    // agg = W0 xm (the projection of gat_project without its attention terms), then the head
+    float a1[32];
+#pragma unroll
+    for (int cc = 0; cc < 32; ++cc) a1[cc] = 0.0f;
+    const float4* w0 = reinterpret_cast<const float4*>(sw + TW_W0T);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 w = w0[k * 8 + c4];
+        a1[4 * c4 + 0] = fmaf(xm[k], w.x, a1[4 * c4 + 0]);
+        a1[4 * c4 + 1] = fmaf(xm[k], w.y, a1[4 * c4 + 1]);
+        a1[4 * c4 + 2] = fmaf(xm[k], w.z, a1[4 * c4 + 2]);
+        a1[4 * c4 + 3] = fmaf(xm[k], w.w, a1[4 * c4 + 3]);
+      }
+    }
+    float q[9];
+    const int action = gat_head(a1, sw, q);
+    const long long g = env * N + i;
+    if (p.q_out) {
+#pragma unroll
+      for (int a = 0; a < 9; ++a) p.q_out[g * 9 + a] = q[a];
+    }
+    if (p.act_out) p.act_out[g] = action;
+  }
+}
+
+bool gatq_knn_large_x_fits(int N, int K) { return N <= 65535 && large_qx_smem_bytes(N, K) <= 227 * 1024; }
+
+cudaError_t launch_gatq_knn_large_x(const SwarmConfig& c, const float* weights, const float* state, const int32_t* nbr,
+                                    float* q, int32_t* actions, cudaStream_t stream) {
+  LargeQParams p;
+  p.cfg = c;
+  p.state = reinterpret_cast<const float4*>(state);
+  p.nbr = nbr;
+  p.weights = weights;
+  p.q_out = q;
+  p.act_out = actions;
+  const size_t smem = large_qx_smem_bytes(c.n_agents, c.knn_k);
+  cudaError_t err = cudaFuncSetAttribute(gatq_knn_large_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  gatq_knn_large_x_kernel<<<c.num_envs, kQLThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
 bool gatq_knn_large_fits(int N, int K) { return N <= 65535 && large_q_smem_bytes(N, K) <= 227 * 1024; }
 
 cudaError_t launch_gatq_knn_large(const SwarmConfig& c, const float* weights, const float* state, const int32_t* nbr,

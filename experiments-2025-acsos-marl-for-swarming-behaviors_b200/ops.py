@@ -7,6 +7,7 @@ is computed in PyTorch.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -578,7 +579,11 @@ def rollout_large(cfg: SwarmConfig, weights: torch.Tensor, state: torch.Tensor, 
     trace = []
     static_csr = None
     fused_knn = cfg.graph_mode == _lib.GRAPH_KNN and N * (144 + 4 * cfg.knn_k) + 8192 <= 227 * 1024 and fused
-    if fused_knn and not trace_state and N > 128:
+    # swarm_rollout_large attends in input space unless SWARM_TC=0 (no projected-feature tile: envs up to 4 096 agents)
+    xspace = os.environ.get("SWARM_TC", "1")[:1] != "0"
+    lib_loop = fused and cfg.graph_mode == _lib.GRAPH_KNN and N > 128 and 64 * cfg.knn_k <= N and not trace_state and \
+        (N * (28 + 2 * cfg.knn_k) + 8400 <= 227 * 1024 if xspace else fused_knn)
+    if lib_loop:
         # the whole tick sequence from the library (swarm_rollout_large): topk table -> per-env Q + argmax -> world step
         # with returns / hits accumulated by the step kernel; no tensor op between the launches
         wb = int(lib().swarm_rollout_large_workspace_bytes(C.byref(cfg)))
