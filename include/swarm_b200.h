@@ -170,8 +170,11 @@ int swarm_gatq_forward_knn_large(const SwarmConfig* cfg, const float* weights, c
  * launched back to back from the library: per tick the topk table (swarm_graph_build), the Q forward + argmax straight
  * from the table (swarm_gatq_forward_knn_large) and the world step, whose kernel also accumulates returns float[B*N] (+=)
  * and hits int32[B] (+=), both optional.  state float[B][N][4] is advanced in place.  No host work, no allocation and
- * no tensor-library op between the launches (the loop is CUDA-graph capturable).  Same restrictions as the two
- * building blocks: 64 k <= n_agents and the env must fit shared memory (see swarm_gatq_forward_knn_large). */
+ * no tensor-library op between the launches (the loop is CUDA-graph capturable).  The Q forward attends in input space
+ * (GATConv's projection is linear: weighted mean of the neighbours' 7 input features, then one projection), which needs
+ * 28 + 2k bytes of shared memory per agent, so envs up to 4 096 agents fit; its greedy actions equal those of
+ * swarm_gatq_forward_knn_large except at float32 near-ties, and SWARM_TC=0 selects that bit-faithful forward (then the
+ * env must fit its 144 + 4k bytes per agent).  64 k <= n_agents as for swarm_graph_build. */
 int64_t swarm_rollout_large_workspace_bytes(const SwarmConfig* cfg);
 int swarm_rollout_large(const SwarmConfig* cfg, const float* weights, float* state, int32_t ticks, float* returns,
                         int32_t* hits, void* workspace, int64_t workspace_bytes, void* stream);
