@@ -161,10 +161,33 @@ __global__ void __launch_bounds__(kLargeThreads) knn_large_kernel(const __grid_c
   const int N = c.n_agents, K = c.knn_k;
   float2* spos = reinterpret_cast<float2*>(smem_raw);
   uint2* hw = reinterpret_cast<uint2*>(spos + N);
+  float4* sbox = reinterpret_cast<float4*>(                                       // [chunks] (xmin, xmax, ymin, ymax)
+      (reinterpret_cast<uintptr_t>(hw + (size_t)K * kLargeThreads) + 15) & ~(uintptr_t)15);
   const long long env = blockIdx.x;          // envs on grid.x (no 65 535 cap), agent chunks on grid.y
   for (int j = threadIdx.x; j < N; j += kLargeThreads) {
     const float4 s = p.state[env * N + j];
     spos[j] = make_float2(s.x, s.y);
+  }
+  __syncthreads();
+  // bounding box of every candidate chunk (K + 32 c .. K + 32 c + 31): a chunk whose box lies beyond the heap top holds
+  // no candidate and is skipped without looking at its members
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nchunks = (N - K + 31) / 32;
+    for (int ch = warp; ch < nchunks; ch += kLargeThreads / 32) {
+      const int j = K + ch * 32 + lane;
+      const bool in = j < N;
+      const float2 q = in ? spos[j] : make_float2(0.f, 0.f);
+      float xmin = in ? q.x : INFINITY, xmax = in ? q.x : -INFINITY, ymin = in ? q.y : INFINITY, ymax = in ? q.y : -INFINITY;
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) {
+        xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, sh));
+        xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, sh));
+        ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, sh));
+        ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, sh));
+      }
+      if (lane == 0) sbox[ch] = make_float4(xmin, xmax, ymin, ymax);
+    }
   }
   __syncthreads();
   const int i = blockIdx.y * kLargeThreads + threadIdx.x;
@@ -198,6 +221,13 @@ __global__ void __launch_bounds__(kLargeThreads) knn_large_kernel(const __grid_c
   for (int base = K; base < N; base += kChunk) {
     const int cnt = (N - base < kChunk) ? (N - base) : kChunk;
     const float thr0 = threshold(hw[threadIdx.x].x);
+    {
+      // squared distance to the chunk's bounding box, with a margin for its own rounding: beyond the threshold, no
+      // member can be (a NaN threshold or box compares false and the chunk is swept)
+      const float4 bb = sbox[(base - K) / kChunk];
+      const float ex = fmaxf(fmaxf(bb.x - sx, sx - bb.y), 0.0f), ey = fmaxf(fmaxf(bb.z - sy, sy - bb.w), 0.0f);
+      if (fmaf(ey, ey, ex * ex) * 0.999999f >= thr0) continue;
+    }
     uint32_t m = 0;
 #pragma unroll 8
     for (int u = 0; u < cnt; ++u) {
@@ -638,7 +668,8 @@ cudaError_t launch_graph_large(const SwarmConfig& c, const float* state, int32_t
     p.nbr = nbr;
     p.edges_per_env = edges_per_env;
     const dim3 grid(c.num_envs, (c.n_agents + kLargeThreads - 1) / kLargeThreads);
-    const size_t smem = c.n_agents * sizeof(float2) + (size_t)c.knn_k * kLargeThreads * 8;
+    const size_t smem = c.n_agents * sizeof(float2) + (size_t)c.knn_k * kLargeThreads * 8 +
+                        (size_t)((c.n_agents - c.knn_k + 31) / 32) * sizeof(float4) + 16;
     cudaError_t err = cudaFuncSetAttribute(knn_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     knn_large_kernel<<<grid, kLargeThreads, smem, stream>>>(p);
