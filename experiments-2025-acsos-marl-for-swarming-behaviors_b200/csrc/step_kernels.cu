@@ -139,12 +139,14 @@ struct StepStreamSmem {
 // EXTRAS: any of the optional outputs (flags / contact masks / observations / distances) is requested; OA: scenario
 // known at compile time.  The minimal variant is issue bound (ncu: 81 % issue utilisation), so the four null checks
 // and the scenario branches per agent are worth a template.
-template <bool EXTRAS, bool OA>
+// NT: swarm size known at compile time (0 = run-time value): the index arithmetic and the partner sweep of the
+// benchmark shape (12 agents) unroll completely.
+template <bool EXTRAS, bool OA, int NT>
 __global__ void __launch_bounds__(kStepThreads, 4) sim_step_stream_kernel(const __grid_constant__ StepParams p,
                                                                           const long long ntiles) {
   __shared__ __align__(128) StepStreamSmem sm;
   const SwarmConfig& c = p.cfg;
-  const int N = c.n_agents;
+  const int N = NT > 0 ? NT : c.n_agents;
   const int tid = threadIdx.x;
   const int el = tid / N;
   const int i = tid - el * N;
@@ -310,10 +312,27 @@ cudaError_t launch_sim_step(const TileParams& tp, cudaStream_t stream) {
     const long long grid = ntiles < 148 * 4 ? ntiles : 148 * 4;
     const bool extras = p.flags || p.contact || p.obs || p.dist;
     const bool oa = p.cfg.scenario == SWARM_SCENARIO_OBSTACLE_AVOIDANCE;
-    if (extras && oa) sim_step_stream_kernel<true, true><<<(unsigned)grid, kStepThreads, 0, stream>>>(p, ntiles);
-    else if (extras) sim_step_stream_kernel<true, false><<<(unsigned)grid, kStepThreads, 0, stream>>>(p, ntiles);
-    else if (oa) sim_step_stream_kernel<false, true><<<(unsigned)grid, kStepThreads, 0, stream>>>(p, ntiles);
-    else sim_step_stream_kernel<false, false><<<(unsigned)grid, kStepThreads, 0, stream>>>(p, ntiles);
+#define SWARM_STEP_LAUNCH(NT)                                                                                           \
+  do {                                                                                                                  \
+    if (extras && oa) sim_step_stream_kernel<true, true, NT><<<(unsigned)grid, kStepThreads, 0, stream>>>(p, ntiles);   \
+    else if (extras) sim_step_stream_kernel<true, false, NT><<<(unsigned)grid, kStepThreads, 0, stream>>>(p, ntiles);   \
+    else if (oa) sim_step_stream_kernel<false, true, NT><<<(unsigned)grid, kStepThreads, 0, stream>>>(p, ntiles);       \
+    else sim_step_stream_kernel<false, false, NT><<<(unsigned)grid, kStepThreads, 0, stream>>>(p, ntiles);              \
+  } while (0)
+    // the swarm sizes of the reference's experiments (5 .. 12 agents) with the size as a compile-time
+    // constant; any other size through the run-time variant
+    switch (N) {
+      case 5: SWARM_STEP_LAUNCH(5); break;
+      case 6: SWARM_STEP_LAUNCH(6); break;
+      case 7: SWARM_STEP_LAUNCH(7); break;
+      case 8: SWARM_STEP_LAUNCH(8); break;
+      case 9: SWARM_STEP_LAUNCH(9); break;
+      case 10: SWARM_STEP_LAUNCH(10); break;
+      case 11: SWARM_STEP_LAUNCH(11); break;
+      case 12: SWARM_STEP_LAUNCH(12); break;
+      default: SWARM_STEP_LAUNCH(0); break;
+    }
+#undef SWARM_STEP_LAUNCH
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     env0 = ntiles * epb_s;
