@@ -36,7 +36,7 @@ constexpr int kTcW1tBytes = 2 * 32 * 32 * 4, kTcW0tBytes = 2 * 16 * 32 * 4;
 
 struct DqnTcLayout {
   int tg_w0, tg_w1, tg_w2, tg_vec, on_w0, on_w1, on_w2, on_vec, w1t, w0t, plain, bar, st, asrc, wt, inl, kv, ki, nbr, mz,
-      sdq, sact, sdasrc, sdadst, sx, xbar, stage, red, total;
+      sdq, sact, sdasrc, sdadst, sx, xbar, stage, total;
 };
 // plain float32 copies of online tensors read by the CUDA-core parts: W2 [9][32], att_src [32], att_dst [32], W0 [32][7]
 enum { PL_W2 = 0, PL_ATT_S = 288, PL_ATT_D = 320, PL_W0 = 352, PL_DV = 576, PL_COUNT = 592 };
@@ -67,7 +67,6 @@ __host__ __device__ inline DqnTcLayout dqn_tc_layout(int n, int k, int maxdeg, i
   L.sx = take(T * 8 * 4, 16);
   L.xbar = take(T * 8 * 4, 16);
   L.stage = take(4 * 2 * kStageBuf * 4, 16);
-  L.red = take(T * 4, 16);
   L.total = off;
   return L;
 }
@@ -403,7 +402,6 @@ __global__ void __launch_bounds__(kTileThreads, 2) dqn_grad_tc_kernel(const __gr
   float* stage_all = reinterpret_cast<float*>(smem + L.stage);
   float* buf0 = stage_all + (warp * 2 + 0) * kStageBuf;         // U, then (with buf1) this warp's partial
   float* buf1 = stage_all + (warp * 2 + 1) * kStageBuf;         // R, then DP, then DO
-  float* sred = reinterpret_cast<float*>(smem + L.red);
   // node rows of this warp that belong to a graph (the rest contribute exact zeros: dq = 0)
   const int wnodes = min(32, max(0, min(p.epb, p.n_graphs - (int)blockIdx.x * p.epb) * N - warp * 32));
   const int wsteps = (wnodes + 7) >> 3;

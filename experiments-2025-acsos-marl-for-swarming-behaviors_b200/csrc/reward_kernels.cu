@@ -24,7 +24,9 @@ constexpr int kRewardThreads = 128;
 // The partner sweeps are branch-free.  Flocking's walks the OTHER agents (compressed index k -> partner k + (k >= i)) in
 // the order torch's CPU row sum adds them (swarm_device.cuh torch_row_sum: eight lanes, so eight independent exact
 // square roots are in flight); Cohesion's neutralises the own slot with selects.
-template <int KIND>
+// NT: swarm size as a compile-time constant (0 = run-time value) for the sizes of the reference's experiments: the
+// partner sweeps and the index arithmetic unroll completely (the same specialisation as the streaming world step).
+template <int KIND, int NT>
 __global__ void __launch_bounds__(kRewardThreads, KIND == SWARM_REWARD_FLOCKING ? 12 : 16) scenario_reward_kernel(SwarmRewardSpec sp,
                                                                              const float4* __restrict__ state,
                                                                              float2* __restrict__ shaping,
@@ -32,7 +34,7 @@ __global__ void __launch_bounds__(kRewardThreads, KIND == SWARM_REWARD_FLOCKING 
                                                                              float4* __restrict__ terms) {
   __shared__ float2 spos[2][kRewardThreads];
   __shared__ float sterm[2][kRewardThreads];
-  const int N = sp.n_agents;
+  const int N = NT > 0 ? NT : sp.n_agents;
   const int epb = kRewardThreads / N;
   const int tid = threadIdx.x;
   const int le = tid / N;                       // env within the CTA
@@ -135,10 +137,21 @@ cudaError_t launch_scenario_reward(const SwarmRewardSpec& sp, const float* state
   const float4* s = reinterpret_cast<const float4*>(state);
   float2* sh = reinterpret_cast<float2*>(shaping);
   float4* t = reinterpret_cast<float4*>(terms);
-  if (sp.kind == SWARM_REWARD_FLOCKING)
-    scenario_reward_kernel<SWARM_REWARD_FLOCKING><<<(int)tiles, kRewardThreads, 0, stream>>>(sp, s, sh, reward, t);
-  else
-    scenario_reward_kernel<SWARM_REWARD_COHESION><<<(int)tiles, kRewardThreads, 0, stream>>>(sp, s, sh, reward, t);
+#define SWARM_REWARD_LAUNCH(NT)                                                                                         \
+  do {                                                                                                                  \
+    if (sp.kind == SWARM_REWARD_FLOCKING)                                                                               \
+      scenario_reward_kernel<SWARM_REWARD_FLOCKING, NT><<<(int)tiles, kRewardThreads, 0, stream>>>(sp, s, sh, reward, t); \
+    else                                                                                                                \
+      scenario_reward_kernel<SWARM_REWARD_COHESION, NT><<<(int)tiles, kRewardThreads, 0, stream>>>(sp, s, sh, reward, t); \
+  } while (0)
+  switch (sp.n_agents) {
+    case 5: SWARM_REWARD_LAUNCH(5); break;
+    case 8: SWARM_REWARD_LAUNCH(8); break;
+    case 10: SWARM_REWARD_LAUNCH(10); break;
+    case 12: SWARM_REWARD_LAUNCH(12); break;
+    default: SWARM_REWARD_LAUNCH(0); break;
+  }
+#undef SWARM_REWARD_LAUNCH
   return cudaGetLastError();
 }
 
