@@ -458,8 +458,12 @@ static cudaError_t launch_tile_q(const TileParams& p0, cudaStream_t stream) {
 static cudaError_t launch_tile_flock(const TileParams& p0, cudaStream_t stream) {
   if (!p0.use_tc) return launch_tile_impl<MODE_ROLLOUT, false, true, true>(p0, stream);
   TileParams p = p0;
-  return tile_grid_plan(p) ? launch_tile_impl<MODE_ROLLOUT, true, true, true>(p, stream)
-                           : launch_tile_impl<MODE_ROLLOUT, true, false, true>(p, stream);
+  const bool dense = tile_grid_plan(p);
+  if (p.cfg.n_agents == 12)
+    return dense ? launch_tile_impl<MODE_ROLLOUT, true, true, true, 12>(p, stream)
+                 : launch_tile_impl<MODE_ROLLOUT, true, false, true, 12>(p, stream);
+  return dense ? launch_tile_impl<MODE_ROLLOUT, true, true, true>(p, stream)
+               : launch_tile_impl<MODE_ROLLOUT, true, false, true>(p, stream);
 }
 
 cudaError_t launch_tile(int mode, const TileParams& p, cudaStream_t stream) {
