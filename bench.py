@@ -350,7 +350,8 @@ def run_ours(args):
 
 def measure_extra(sb, ops, dev):
     """The other BASELINE.json configurations, driver-run: the kNN (evaluation-graph) variant of C2, the
-    C3 sweep (65 536 envs, GoTo, N = 5 / 8 / 12, complete and kNN k = 5) and C4 (1 024 agents x 1 024 envs, kNN k = 10).
+    C3 sweep (65 536 envs, GoTo, N = 5 / 8 / 12, complete and kNN k = 5) and C4 (1 024 agents x 1 024 envs; kNN k = 10,
+    radius 0.35, complete).
     Device-resident, CUDA events, greedy policy of the shipped seed-0 weights."""
     L = sb._lib
     models = np.load(os.path.join(ROOT, "tests", "golden", "models.npz"))
@@ -398,6 +399,19 @@ def measure_extra(sb, ops, dev):
     torch.cuda.synchronize(dev)
     out["c4_oa_1024x1024_knn_k10"] = {"agent_steps_per_s": B4 * N4 * T4 / (a.elapsed_time(b) * 1e-3),
                                       "ms_per_tick": a.elapsed_time(b) / T4}
+    # C4 with the other two graphs SURVEY 8d names: radius r = 0.35 (uniform-grid broad phase) and the complete graph
+    # (1.07e9 edges per tick if it were materialised); two launches per tick, no edge list
+    for name, gm in (("radius_r0.35", L.GRAPH_RADIUS), ("complete", L.GRAPH_COMPLETE)):
+        cfg = ops.make_config(L.SCENARIO_OBSTACLE_AVOIDANCE, B4, N4, gm, K4, graph_radius=0.35)
+        st = ops.reset_grid(cfg, draw_centers(9, B4).to(dev))
+        ops.rollout_large(cfg, w_oa, st, 2)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ops.rollout_large(cfg, w_oa, st, T4)
+        b.record()
+        torch.cuda.synchronize(dev)
+        out[f"c4_oa_1024x1024_{name}"] = {"agent_steps_per_s": B4 * N4 * T4 / (a.elapsed_time(b) * 1e-3),
+                                          "ms_per_tick": a.elapsed_time(b) / T4}
     return out
 
 

@@ -109,6 +109,8 @@ _SIGNATURES = {
     "swarm_sim_step": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 9),
     "swarm_graph_build": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 4),
     "swarm_graph_build_radius": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 4),
+    "swarm_graph_build_radius_csr": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 5),
+    "swarm_gatq_forward_large": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 5),
     "swarm_gatq_forward": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 5),
     "swarm_gatq_workspace_bytes": (C.c_int64, [C.c_int32]),
     "swarm_gatq_forward_csr": (C.c_int, [C.c_int32] + [C.c_void_p] * 6 + [C.c_void_p, C.c_int64, C.c_void_p]),

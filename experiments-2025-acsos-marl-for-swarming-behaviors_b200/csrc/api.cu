@@ -32,6 +32,11 @@ cudaError_t launch_episode_end(const SwarmConfig& c, SwarmTrainCtl* ctl, float* 
                                float* stats, long long max_episodes, double eps0, double decay, double min_eps,
                                cudaStream_t stream);
 bool gatq_knn_large_fits(int N, int K);
+bool gatq_large_x_fits(int N, bool radius);
+cudaError_t launch_gatq_large_x(const SwarmConfig& c, const float* weights, const float* state, float* q, int32_t* actions,
+                                cudaStream_t stream);
+cudaError_t launch_radius_csr(const SwarmConfig& c, const float* state, int32_t* degree, const int32_t* row_ptr,
+                              int32_t* src, cudaStream_t stream);
 bool gatq_knn_large_x_fits(int N, int K);
 cudaError_t launch_gatq_knn_large_x(const SwarmConfig& c, const float* weights, const float* state, const int32_t* nbr,
                                     float* q, int32_t* actions, cudaStream_t stream);
@@ -97,8 +102,9 @@ int validate(const SwarmConfig* cfg, bool need_graph, bool allow_large = false) 
       return fail(SWARM_ERR_INVALID_ARG, "unknown graph mode");
     if (cfg->graph_mode == SWARM_GRAPH_RADIUS) {
       if (!(cfg->graph_radius >= 0.0f)) return fail(SWARM_ERR_INVALID_ARG, "graph_radius must be >= 0");
-      if (cfg->n_agents > kTileThreads)
-        return fail(SWARM_ERR_UNSUPPORTED, "the radius graph (extension) is implemented for n_agents <= 128");
+      if (cfg->n_agents > kTileThreads && !allow_large)
+        return fail(SWARM_ERR_UNSUPPORTED, "the padded radius edge block is implemented for n_agents <= 128 (large swarms: "
+                                           "swarm_graph_build_radius_csr / swarm_gatq_forward_large / swarm_rollout_large)");
     }
     if (cfg->graph_mode == SWARM_GRAPH_KNN) {
       // torch.topk raises "selected index k out of range" for k > n (simulator.py:19 with n_agents < 10)
@@ -285,26 +291,56 @@ int swarm_gatq_forward_knn_large(const SwarmConfig* cfg, const float* weights, c
                     "swarm_gatq_forward_knn_large");
 }
 
+int swarm_graph_build_radius_csr(const SwarmConfig* cfg, const float* state, int32_t* degree, const int32_t* row_ptr,
+                                 int32_t* src, void* stream) {
+  if (int rc = validate(cfg, true, true)) return rc;
+  if (cfg->graph_mode != SWARM_GRAPH_RADIUS) return fail(SWARM_ERR_INVALID_ARG, "cfg->graph_mode must be SWARM_GRAPH_RADIUS");
+  if (!state) return fail(SWARM_ERR_INVALID_ARG, "state is NULL");
+  if ((src == nullptr) == (degree == nullptr))
+    return fail(SWARM_ERR_INVALID_ARG, "pass degree (count pass) or row_ptr + src (fill pass), not both");
+  if (src && !row_ptr) return fail(SWARM_ERR_INVALID_ARG, "the fill pass needs row_ptr");
+  if ((int64_t)cfg->num_envs * cfg->n_agents > 0x7fffffffLL) return fail(SWARM_ERR_UNSUPPORTED, "more than 2^31 - 1 nodes");
+  return check_cuda(launch_radius_csr(*cfg, state, degree, row_ptr, src, (cudaStream_t)stream), "swarm_graph_build_radius_csr");
+}
+
+int swarm_gatq_forward_large(const SwarmConfig* cfg, const float* weights, const float* state, float* q, int32_t* actions,
+                             void* stream) {
+  if (int rc = validate(cfg, true, true)) return rc;
+  if (cfg->graph_mode != SWARM_GRAPH_RADIUS && cfg->graph_mode != SWARM_GRAPH_COMPLETE)
+    return fail(SWARM_ERR_INVALID_ARG, "cfg->graph_mode must be SWARM_GRAPH_RADIUS or SWARM_GRAPH_COMPLETE "
+                                       "(kNN: swarm_gatq_forward_knn_large)");
+  if (!weights || !state) return fail(SWARM_ERR_INVALID_ARG, "weights/state is NULL");
+  if (!q && !actions) return fail(SWARM_ERR_INVALID_ARG, "no output requested");
+  if (!gatq_large_x_fits(cfg->n_agents, cfg->graph_mode == SWARM_GRAPH_RADIUS))
+    return fail(SWARM_ERR_UNSUPPORTED, "the env does not fit shared memory");
+  return check_cuda(launch_gatq_large_x(*cfg, weights, state, q, actions, (cudaStream_t)stream), "swarm_gatq_forward_large");
+}
+
 int64_t swarm_rollout_large_workspace_bytes(const SwarmConfig* cfg) {
-  if (!cfg || cfg->num_envs <= 0 || cfg->n_agents <= 0 || cfg->knn_k <= 0) return 0;
+  if (!cfg || cfg->num_envs <= 0 || cfg->n_agents <= 0) return 0;
   const int64_t bn = (int64_t)cfg->num_envs * cfg->n_agents;
-  return bn * cfg->knn_k * 4 + bn * 4 + 512;
+  const int64_t k = cfg->graph_mode == SWARM_GRAPH_KNN ? (cfg->knn_k > 0 ? cfg->knn_k : 0) : 0;
+  return bn * k * 4 + bn * 4 + 512;
 }
 
 int swarm_rollout_large(const SwarmConfig* cfg, const float* weights, float* state, int32_t ticks, float* returns,
                         int32_t* hits, void* workspace, int64_t workspace_bytes, void* stream) {
   if (int rc = validate(cfg, true, true)) return rc;
-  if (cfg->graph_mode != SWARM_GRAPH_KNN) return fail(SWARM_ERR_INVALID_ARG, "cfg->graph_mode must be SWARM_GRAPH_KNN");
   if (cfg->n_agents <= kTileThreads) return fail(SWARM_ERR_INVALID_ARG, "n_agents <= 128: use swarm_rollout");
   if (!weights || !state || !workspace) return fail(SWARM_ERR_INVALID_ARG, "weights/state/workspace is NULL");
   if (ticks < 0) return fail(SWARM_ERR_INVALID_ARG, "ticks must be >= 0");
-  if ((int64_t)cfg->knn_k * 64 > cfg->n_agents)
+  const bool knn = cfg->graph_mode == SWARM_GRAPH_KNN;
+  if (knn && (int64_t)cfg->knn_k * 64 > cfg->n_agents)
     return fail(SWARM_ERR_UNSUPPORTED, "large-swarm kNN implements torch.topk's partial_sort branch (64 k <= n)");
   // attention in input space (no projected-feature tile: envs up to 4 096 agents fit) unless SWARM_TC=0 asks for the
-  // bit-faithful forward of swarm_gatq_forward_knn_large
+  // bit-faithful forward of swarm_gatq_forward_knn_large (kNN only; the radius / complete graph of a large swarm has
+  // the input-space forward alone -- their bit-faithful path is the CSR one)
   const char* tc_env = std::getenv("SWARM_TC");
-  const bool xspace = !(tc_env && tc_env[0] == '0');
-  if (!(xspace ? gatq_knn_large_x_fits(cfg->n_agents, cfg->knn_k) : gatq_knn_large_fits(cfg->n_agents, cfg->knn_k)))
+  const bool xspace = !knn || !(tc_env && tc_env[0] == '0');
+  const bool fits = !knn ? gatq_large_x_fits(cfg->n_agents, cfg->graph_mode == SWARM_GRAPH_RADIUS)
+                         : (xspace ? gatq_knn_large_x_fits(cfg->n_agents, cfg->knn_k)
+                                   : gatq_knn_large_fits(cfg->n_agents, cfg->knn_k));
+  if (!fits)
     return fail(SWARM_ERR_UNSUPPORTED, "the env does not fit shared memory: step it with swarm_graph_build + "
                                        "swarm_csr_from_edges + swarm_gatq_forward_csr + swarm_sim_step");
   if (workspace_bytes < swarm_rollout_large_workspace_bytes(cfg)) return fail(SWARM_ERR_INVALID_ARG, "workspace too small");
@@ -313,7 +349,7 @@ int swarm_rollout_large(const SwarmConfig* cfg, const float* weights, float* sta
   const int64_t bn = (int64_t)cfg->num_envs * cfg->n_agents;
   uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
   int32_t* nbr = reinterpret_cast<int32_t*>(base);
-  int32_t* actions = nbr + bn * cfg->knn_k;
+  int32_t* actions = nbr + (knn ? bn * cfg->knn_k : 0);
   p.state_in = state;
   p.state_out = state;           // in place: one CTA owns a whole env and stages its positions first
   p.actions_in = actions;
@@ -323,12 +359,18 @@ int swarm_rollout_large(const SwarmConfig* cfg, const float* weights, float* sta
   for (int t = 0; t < ticks; ++t) {
     // simulator.py:59-68 per tick: topk table -> GCN forward + argmax straight from the table -> Environment.step,
     // returns / hits accumulated by the step kernel: three launches, nothing but the state leaves the device
-    if (cudaError_t e = launch_graph_large(*cfg, state, nullptr, nbr, p.edges_per_env, st); e != cudaSuccess)
-      return check_cuda(e, "swarm_rollout_large (graph)");
-    if (cudaError_t e = xspace ? launch_gatq_knn_large_x(*cfg, weights, state, nbr, nullptr, actions, st)
-                               : launch_gatq_knn_large(*cfg, weights, state, nbr, nullptr, actions, st);
-        e != cudaSuccess)
+    // (radius / complete graph: the forward finds its own sources -- uniform-grid broad phase / every other agent --
+    // so a tick is two launches)
+    if (knn) {
+      if (cudaError_t e = launch_graph_large(*cfg, state, nullptr, nbr, p.edges_per_env, st); e != cudaSuccess)
+        return check_cuda(e, "swarm_rollout_large (graph)");
+      if (cudaError_t e = xspace ? launch_gatq_knn_large_x(*cfg, weights, state, nbr, nullptr, actions, st)
+                                 : launch_gatq_knn_large(*cfg, weights, state, nbr, nullptr, actions, st);
+          e != cudaSuccess)
+        return check_cuda(e, "swarm_rollout_large (forward)");
+    } else if (cudaError_t e = launch_gatq_large_x(*cfg, weights, state, nullptr, actions, st); e != cudaSuccess) {
       return check_cuda(e, "swarm_rollout_large (forward)");
+    }
     if (cudaError_t e = launch_sim_step_large(p, st); e != cudaSuccess) return check_cuda(e, "swarm_rollout_large (step)");
   }
   return SWARM_OK;

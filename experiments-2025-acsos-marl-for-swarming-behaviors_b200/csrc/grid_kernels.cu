@@ -1,0 +1,426 @@
+// grid_kernels.cu -- uniform-grid broad phase for large swarms (n_agents <= 4096; SURVEY 8(f) rank 4, BASELINE config
+// "1024 agents x 1024 envs" with the radius / complete graph).
+//
+// One CTA owns one env.  Its agents are binned into square cells at least one graph radius wide (at most 64 x 64 cells
+// over the env's bounding box), the (cell, agent) keys are sorted by a bitonic network in shared memory -- agents of a
+// cell end up contiguous AND in ascending agent order, so every walk over the grid is deterministic -- and a node only
+// ever looks at the 3 x 3 cells around its own.  Membership is decided by the exact test of the small-swarm radius
+// graph (tile_device.cuh radius_hit: squared distance against the largest q whose rounded sqrt is <= r), the grid only
+// prunes candidates.  On top of it:
+//   radius_csr_kernel     the radius graph (batched_oracle.edges_radius: the complete builder of train_gcn_dqn.py:94-110
+//                         filtered by distance) as a compact CSR grouped by target -- in-degrees, then sources in
+//                         ascending order through a 9-way merge of the cell lists, which is exactly the order the edge
+//                         list -> stable sort by target gives; feeds swarm_gatq_forward_csr (bit-faithful forward)
+//   gatq_large_x_kernel   GCN.forward (train_gcn_dqn.py:59-70) + argmax for a large env on the radius or the complete
+//                         graph with the attention in input space (see large_kernels.cu gatq_knn_large_x_kernel): no
+//                         edge list at all -- the complete graph of 1 024 agents would be 1.07e9 edges per tick at C4.
+#include "gatq_device.cuh"
+
+namespace swarm {
+
+constexpr int kGridThreads = 512;
+constexpr int kGridMax = 64;            // cells per axis
+constexpr int kGridCells = kGridMax * kGridMax;
+constexpr int kIdxBits = 12;            // n_agents <= 4096
+constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1u;
+
+struct CellGrid {
+  float x0, y0, inv;
+  int nx, ny;
+  __device__ __forceinline__ int cx(float x) const {
+    const int c = (int)fminf(__fmul_rn(__fsub_rn(x, x0), inv), (float)(kGridMax - 1));
+    return c < 0 ? 0 : (c >= nx ? nx - 1 : c);
+  }
+  __device__ __forceinline__ int cy(float y) const {
+    const int c = (int)fminf(__fmul_rn(__fsub_rn(y, y0), inv), (float)(kGridMax - 1));
+    return c < 0 ? 0 : (c >= ny ? ny - 1 : c);
+  }
+};
+
+__host__ __device__ inline int grid_pow2(int n) {
+  int p = 64;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+// Bins and sorts the env's agents.  Every thread of the CTA calls it (block barriers inside).
+//   keys  uint32[P]  (cell << 12 | agent), ascending; P = grid_pow2(N), padded with 0xFFFFFFFF
+//   cbeg / cend uint16[kGridCells]: the key range of every cell (empty: 0, 0)
+//   sred  float[64] scratch
+// Two agents within `radius` of each other (rounded 2-norm) land in the same or in adjacent cells: the cell is 0.1 %
+// wider than the radius, the float error of a cell coordinate is below 64 * 2e-7.
+template <typename Pos>
+__device__ __forceinline__ CellGrid grid_build(Pos pos, int N, int P, float radius, uint32_t* keys, uint16_t* cbeg,
+                                               uint16_t* cend, float* sred) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+  for (int j = tid; j < N; j += kGridThreads) {
+    const float2 q = pos(j);
+    xmin = fminf(xmin, q.x); xmax = fmaxf(xmax, q.x);
+    ymin = fminf(ymin, q.y); ymax = fmaxf(ymax, q.y);
+  }
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) {
+    xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, sh));
+    xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, sh));
+    ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, sh));
+    ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, sh));
+  }
+  if (lane == 0) {
+    sred[warp * 4 + 0] = xmin; sred[warp * 4 + 1] = xmax;
+    sred[warp * 4 + 2] = ymin; sred[warp * 4 + 3] = ymax;
+  }
+  for (int c = tid; c < kGridCells; c += kGridThreads) { cbeg[c] = 0; cend[c] = 0; }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < kGridThreads / 32; ++w) {
+    xmin = fminf(xmin, sred[w * 4 + 0]); xmax = fmaxf(xmax, sred[w * 4 + 1]);
+    ymin = fminf(ymin, sred[w * 4 + 2]); ymax = fmaxf(ymax, sred[w * 4 + 3]);
+  }
+  CellGrid g;
+  const float ex = xmax - xmin, ey = ymax - ymin;            // NaN / inf extents collapse the grid to few cells: still exact
+  float cell = fmaxf(radius * 1.001f, fmaxf(ex, ey) * (1.0f / kGridMax));
+  cell = fmaxf(cell, 1e-20f);
+  g.x0 = xmin;
+  g.y0 = ymin;
+  g.inv = 1.0f / cell;
+  g.nx = (int)fminf(ex * g.inv, (float)(kGridMax - 1)) + 1;
+  g.ny = (int)fminf(ey * g.inv, (float)(kGridMax - 1)) + 1;
+  g.nx = g.nx < 1 ? 1 : g.nx;
+  g.ny = g.ny < 1 ? 1 : g.ny;
+  for (int j = tid; j < P; j += kGridThreads) {
+    uint32_t key = 0xFFFFFFFFu;
+    if (j < N) {
+      const float2 q = pos(j);
+      key = ((uint32_t)(g.cy(q.y) * g.nx + g.cx(q.x)) << kIdxBits) | (uint32_t)j;
+    }
+    keys[j] = key;
+  }
+  __syncthreads();
+  // bitonic network; a warp's 32 pairs of a stage with distance <= 32 stay inside its own 64-key window, so those
+  // stages only need a warp barrier
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (P >> 1); t += kGridThreads) {
+        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int hi = lo | j;
+        const bool up = (lo & k) == 0;
+        const uint32_t a = keys[lo], b = keys[hi];
+        if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+      }
+      const int jn = (j > 1) ? (j >> 1) : k;              // distance of the next stage
+      if (j > 32 || jn > 32) __syncthreads(); else __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int p = tid; p < N; p += kGridThreads) {
+    const uint32_t c = keys[p] >> kIdxBits;
+    if (p == 0 || (keys[p - 1] >> kIdxBits) != c) cbeg[c] = (uint16_t)p;
+    if (p == N - 1 || (keys[p + 1] >> kIdxBits) != c) cend[c] = (uint16_t)(p + 1);
+  }
+  __syncthreads();
+  return g;
+}
+
+__device__ __forceinline__ bool grid_hit(const float2& pj, const float2& neg, float qmax_r) {
+  const float2 d = __fadd2_rn(pj, neg);
+  return __fmaf_rn(d.y, d.y, __fmul_rn(d.x, d.x)) <= qmax_r;
+}
+
+// ---- radius graph as CSR ----------------------------------------------------------------------------------------
+struct RadiusCsrParams {
+  SwarmConfig cfg;
+  const float4* state;
+  int32_t* degree;            // [B*N]   (count pass)
+  const int32_t* row_ptr;     // [B*N+1] (fill pass)
+  int32_t* src;               // [E]     (fill pass): global node ids b*N + j
+  float qmax_r;
+};
+
+__host__ __device__ inline size_t radius_csr_smem_bytes(int N) {
+  return (size_t)N * 8 + (size_t)grid_pow2(N) * 4 + (size_t)kGridCells * 4 + 64 * 4 + 64;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(kGridThreads) radius_csr_kernel(const __grid_constant__ RadiusCsrParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = p.cfg.n_agents, P = grid_pow2(N);
+  float2* spos = reinterpret_cast<float2*>(smem_raw);
+  uint32_t* keys = reinterpret_cast<uint32_t*>(spos + N);
+  uint16_t* cbeg = reinterpret_cast<uint16_t*>(keys + P);
+  uint16_t* cend = cbeg + kGridCells;
+  float* sred = reinterpret_cast<float*>(cend + kGridCells);
+  const long long env = blockIdx.x;
+  for (int j = threadIdx.x; j < N; j += kGridThreads) {
+    const float4 s = p.state[env * N + j];
+    spos[j] = make_float2(s.x, s.y);
+  }
+  __syncthreads();
+  const CellGrid g = grid_build([&](int j) { return spos[j]; }, N, P, p.cfg.graph_radius, keys, cbeg, cend, sred);
+  const long long base = env * N;
+  for (int i = threadIdx.x; i < N; i += kGridThreads) {
+    const float2 pi = spos[i];
+    const float2 neg = make_float2(-pi.x, -pi.y);
+    const int cx = g.cx(pi.x), cy = g.cy(pi.y);
+    if (!FILL) {
+      int deg = (i == 0) ? 1 : 0;                           // the trailing (0 -> 0)
+      for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.ny - 1); ++yy)
+        for (int xx = max(cx - 1, 0); xx <= min(cx + 1, g.nx - 1); ++xx) {
+          const int c = yy * g.nx + xx;
+          for (int q = cbeg[c], e = cend[c]; q < e; ++q) {
+            const int j = (int)(keys[q] & kIdxMask);
+            deg += (j != i && grid_hit(spos[j], neg, p.qmax_r)) ? 1 : 0;
+          }
+        }
+      p.degree[base + i] = deg;
+    } else {
+      // sources in ascending order: 9-way merge of the (ascending) cell lists
+      int h[9], e[9];
+      uint32_t v[9];
+#pragma unroll
+      for (int c9 = 0; c9 < 9; ++c9) {
+        const int yy = cy - 1 + c9 / 3, xx = cx - 1 + c9 % 3;
+        const bool ok = yy >= 0 && yy < g.ny && xx >= 0 && xx < g.nx;
+        const int c = ok ? yy * g.nx + xx : 0;
+        h[c9] = ok ? (int)cbeg[c] : 0;
+        e[c9] = ok ? (int)cend[c] : 0;
+        v[c9] = h[c9] < e[c9] ? (keys[h[c9]] & kIdxMask) : 0xFFFFu;
+      }
+      int32_t* out = p.src + p.row_ptr[base + i];
+      int n = 0;
+      while (true) {
+        uint32_t m = v[0];
+#pragma unroll
+        for (int c9 = 1; c9 < 9; ++c9) m = min(m, v[c9]);
+        if (m == 0xFFFFu) break;
+#pragma unroll
+        for (int c9 = 0; c9 < 9; ++c9) {
+          if (v[c9] == m) {
+            ++h[c9];
+            v[c9] = h[c9] < e[c9] ? (keys[h[c9]] & kIdxMask) : 0xFFFFu;
+          }
+        }
+        if ((int)m != i && grid_hit(spos[m], neg, p.qmax_r)) out[n++] = (int32_t)(base + m);
+      }
+      if (i == 0) out[n++] = (int32_t)base;
+    }
+  }
+}
+
+cudaError_t launch_radius_csr(const SwarmConfig& c, const float* state, int32_t* degree, const int32_t* row_ptr,
+                              int32_t* src, cudaStream_t stream) {
+  RadiusCsrParams p;
+  p.cfg = c;
+  p.state = reinterpret_cast<const float4*>(state);
+  p.degree = degree;
+  p.row_ptr = row_ptr;
+  p.src = src;
+  p.qmax_r = sq_threshold(c.graph_radius);
+  const size_t smem = radius_csr_smem_bytes(c.n_agents);
+  if (src) {
+    cudaError_t err = cudaFuncSetAttribute(radius_csr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    radius_csr_kernel<true><<<c.num_envs, kGridThreads, smem, stream>>>(p);
+  } else {
+    cudaError_t err = cudaFuncSetAttribute(radius_csr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    radius_csr_kernel<false><<<c.num_envs, kGridThreads, smem, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+// ---- Q forward with the attention in input space, radius / complete graph -----------------------------------------
+struct LargeXParams {
+  SwarmConfig cfg;
+  const float4* state;
+  const float* weights;
+  float* q_out;              // [B*N][9] or nullptr
+  int32_t* act_out;          // [B*N] or nullptr
+  float qmax_r;
+};
+
+__host__ __device__ inline size_t large_x_smem_bytes(int N, bool radius) {
+  size_t b = (size_t)((TW_COUNT + 3) & ~3) * 4 + 64;        // weights, v_s / v_d
+  b += (size_t)N * 16 + (size_t)N * 4;                       // states, alpha_src
+  b += 64 * 4;                                               // reduction scratch
+  if (radius) b += (size_t)grid_pow2(N) * 4 + (size_t)kGridCells * 4;
+  return b + 64;
+}
+
+template <bool RADIUS>
+__global__ void __launch_bounds__(kGridThreads) gatq_large_x_kernel(const __grid_constant__ LargeXParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SwarmConfig& c = p.cfg;
+  const int N = c.n_agents, P = grid_pow2(N);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long env = blockIdx.x;
+  float* sw = reinterpret_cast<float*>(smem_raw);
+  float* sv = sw + ((TW_COUNT + 3) & ~3);                 // v_s[8], v_d[8]
+  float4* sst = reinterpret_cast<float4*>(sv + 16);
+  float* sas = reinterpret_cast<float*>(sst + N);
+  float* sred = sas + N;                                  // [64]
+  uint32_t* keys = reinterpret_cast<uint32_t*>(sred + 64);
+  uint16_t* cbeg = reinterpret_cast<uint16_t*>(keys + P);
+  uint16_t* cend = cbeg + kGridCells;
+
+  stage_weights(p.weights, sw, tid, kGridThreads);
+  for (int i = tid; i < N; i += kGridThreads) sst[i] = p.state[env * N + i];
+  __syncthreads();
+  if (tid < 16) {
+    // attention vectors pulled through the projection: v[k] = sum_c att[c] W0[c][k]
+    const int k = tid & 7;
+    const float* att = sw + (tid < 8 ? TW_ATT_S : TW_ATT_D);
+    float v = 0.0f;
+    if (k < 7)
+      for (int cc = 0; cc < 32; ++cc) v = fmaf(att[cc], sw[TW_W0T + k * 32 + cc], v);
+    sv[tid] = v;
+  }
+  CellGrid g;
+  if (RADIUS)
+    g = grid_build([&](int j) { const float4 s = sst[j]; return make_float2(s.x, s.y); }, N, P, c.graph_radius, keys, cbeg,
+                   cend, sred);
+  __syncthreads();
+  // alpha_src of every node; for the complete graph also the two largest of the env (the softmax shift of node i is the
+  // largest alpha_src among its sources: everybody but itself)
+  float t1 = -INFINITY, t2 = -INFINITY;
+  int t1i = -1;
+  for (int i = tid; i < N; i += kGridThreads) {
+    const float4 st = sst[i];
+    const float a = fmaf(st.x, sv[0], fmaf(st.y, sv[1], fmaf(st.z, sv[2], fmaf(st.w, sv[3],
+                    fmaf(c.goal_x, sv[4], fmaf(c.goal_y, sv[5], (float)i * sv[6]))))));
+    sas[i] = a;
+    if (a > t1) { t2 = t1; t1 = a; t1i = i; }
+    else if (a > t2) t2 = a;
+  }
+  if (!RADIUS) {
+    auto merge = [&](float o1, int oi, float o2) {
+      if (o1 > t1) { t2 = fmaxf(t1, o2); t1 = o1; t1i = oi; }
+      else t2 = fmaxf(t2, o1);
+    };
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) {
+      const float o1 = __shfl_xor_sync(0xffffffffu, t1, sh), o2 = __shfl_xor_sync(0xffffffffu, t2, sh);
+      const int oi = __shfl_xor_sync(0xffffffffu, t1i, sh);
+      merge(o1, oi, o2);
+    }
+    __syncthreads();                                        // sred was grid_build's scratch
+    if (lane == 0) {
+      sred[warp * 3 + 0] = t1;
+      sred[warp * 3 + 1] = __int_as_float(t1i);
+      sred[warp * 3 + 2] = t2;
+    }
+    __syncthreads();
+    t1 = -INFINITY; t2 = -INFINITY; t1i = -1;
+    for (int w = 0; w < kGridThreads / 32; ++w) merge(sred[w * 3 + 0], __float_as_int(sred[w * 3 + 1]), sred[w * 3 + 2]);
+  } else {
+    __syncthreads();
+  }
+
+  for (int i = tid; i < N; i += kGridThreads) {
+    const float4 st = sst[i];
+    const float adst = fmaf(st.x, sv[8], fmaf(st.y, sv[9], fmaf(st.z, sv[10], fmaf(st.w, sv[11],
+                       fmaf(c.goal_x, sv[12], fmaf(c.goal_y, sv[13], (float)i * sv[14]))))));
+    float den = 0.0f, acc_id = 0.0f;
+    float2 acc_p = make_float2(0.f, 0.f), acc_v = make_float2(0.f, 0.f);
+    float m;
+    auto add = [&](int j) {
+      const float4 sj = sst[j];
+      const float w = __expf(gat_logit(sas[j], adst) - m);
+      den = __fadd_rn(den, w);
+      acc_p = __ffma2_rn(make_float2(w, w), make_float2(sj.x, sj.y), acc_p);
+      acc_v = __ffma2_rn(make_float2(w, w), make_float2(sj.z, sj.w), acc_v);
+      acc_id = fmaf(w, (float)j, acc_id);
+    };
+    if (RADIUS) {
+      // in-edges: agents j != i within the radius (train:94-110 filtered by distance) + the trailing (0,0) of node 0
+      const float2 neg = make_float2(-st.x, -st.y);
+      const int cx = g.cx(st.x), cy = g.cy(st.y);
+      const int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.ny - 1), x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+      float amax = (i == 0) ? sas[0] : -INFINITY;
+      for (int yy = y0; yy <= y1; ++yy)
+        for (int xx = x0; xx <= x1; ++xx) {
+          const int cc = yy * g.nx + xx;
+          for (int q = cbeg[cc], e = cend[cc]; q < e; ++q) {
+            const int j = (int)(keys[q] & kIdxMask);
+            const float4 sj = sst[j];
+            if (j != i && grid_hit(make_float2(sj.x, sj.y), neg, p.qmax_r)) amax = fmaxf(amax, sas[j]);
+          }
+        }
+      m = gat_logit(amax, adst);                          // LeakyReLU and the rounded add are monotone
+      for (int yy = y0; yy <= y1; ++yy)
+        for (int xx = x0; xx <= x1; ++xx) {
+          const int cc = yy * g.nx + xx;
+          for (int q = cbeg[cc], e = cend[cc]; q < e; ++q) {
+            const int j = (int)(keys[q] & kIdxMask);
+            const float4 sj = sst[j];
+            if (j != i && grid_hit(make_float2(sj.x, sj.y), neg, p.qmax_r)) add(j);
+          }
+        }
+      if (i == 0) add(0);
+    } else {
+      // complete graph (train:94-110): every j != i, node 0 additionally its (0,0)
+      const float amax = (i == 0 || t1i != i) ? t1 : t2;
+      m = gat_logit(amax, adst);
+#pragma unroll 4
+      for (int j = 0; j < i; ++j) add(j);
+#pragma unroll 4
+      for (int j = i + 1; j < N; ++j) add(j);
+      if (i == 0) add(0);
+    }
+    const float inv = 1.0f / __fadd_rn(den, 1e-16f);
+    const float wsum = den * inv;
+    const float xm[7] = {acc_p.x * inv, acc_p.y * inv, acc_v.x * inv, acc_v.y * inv, c.goal_x * wsum, c.goal_y * wsum,
+                         acc_id * inv};
+    // agg = W0 xm (the projection of gat_project without its attention terms), then the head
+    float a1[32];
+#pragma unroll
+    for (int cc = 0; cc < 32; ++cc) a1[cc] = 0.0f;
+    const float4* w0 = reinterpret_cast<const float4*>(sw + TW_W0T);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 w = w0[k * 8 + c4];
+        a1[4 * c4 + 0] = fmaf(xm[k], w.x, a1[4 * c4 + 0]);
+        a1[4 * c4 + 1] = fmaf(xm[k], w.y, a1[4 * c4 + 1]);
+        a1[4 * c4 + 2] = fmaf(xm[k], w.z, a1[4 * c4 + 2]);
+        a1[4 * c4 + 3] = fmaf(xm[k], w.w, a1[4 * c4 + 3]);
+      }
+    }
+    float q[9];
+    const int action = gat_head(a1, sw, q);
+    const long long gi = env * N + i;
+    if (p.q_out) {
+#pragma unroll
+      for (int a = 0; a < 9; ++a) p.q_out[gi * 9 + a] = q[a];
+    }
+    if (p.act_out) p.act_out[gi] = action;
+  }
+}
+
+bool gatq_large_x_fits(int N, bool radius) { return N <= (1 << kIdxBits) && large_x_smem_bytes(N, radius) <= 227 * 1024; }
+
+cudaError_t launch_gatq_large_x(const SwarmConfig& c, const float* weights, const float* state, float* q, int32_t* actions,
+                                cudaStream_t stream) {
+  LargeXParams p;
+  p.cfg = c;
+  p.state = reinterpret_cast<const float4*>(state);
+  p.weights = weights;
+  p.q_out = q;
+  p.act_out = actions;
+  const bool radius = c.graph_mode == SWARM_GRAPH_RADIUS;
+  p.qmax_r = radius ? sq_threshold(c.graph_radius) : 0.0f;
+  const size_t smem = large_x_smem_bytes(c.n_agents, radius);
+  if (radius) {
+    cudaError_t err = cudaFuncSetAttribute(gatq_large_x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    gatq_large_x_kernel<true><<<c.num_envs, kGridThreads, smem, stream>>>(p);
+  } else {
+    cudaError_t err = cudaFuncSetAttribute(gatq_large_x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    gatq_large_x_kernel<false><<<c.num_envs, kGridThreads, smem, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace swarm

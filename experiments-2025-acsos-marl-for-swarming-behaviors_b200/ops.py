@@ -478,6 +478,41 @@ def gatq_forward_knn_large(cfg: SwarmConfig, weights: torch.Tensor, state: torch
     return q if want_q else act
 
 
+def gatq_forward_large(cfg: SwarmConfig, weights: torch.Tensor, state: torch.Tensor, want_q: bool = True,
+                       want_actions: bool = False):
+    """GCN.forward on the radius / complete graph of a swarm of any size without an edge list (one CTA per env,
+    uniform-grid broad phase for the radius graph, attention in input space)."""
+    B, N = cfg.num_envs, cfg.n_agents
+    _expect(state, torch.float32, B * N * 4, "state")
+    _expect(weights, torch.float32, _lib.W_COUNT, "weights")
+    dev = state.device
+    q = torch.empty(B, N, 9, dtype=torch.float32, device=dev) if want_q else None
+    act = torch.empty(B, N, dtype=torch.int32, device=dev) if want_actions else None
+    check(lib().swarm_gatq_forward_large(C.byref(cfg), ptr(weights), ptr(state), ptr(q), ptr(act), stream_ptr(dev)))
+    if want_q and want_actions:
+        return q, act
+    return q if want_q else act
+
+
+def graph_build_radius_csr(cfg: SwarmConfig, state: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Radius graph of swarms of any size as a CSR grouped by target: (row_ptr int32[B*N+1], src int32[E]) with global
+    node ids, sources ascending per target, node 0's (0, 0) last -- what csr_from_edges makes of the edge list.  Two
+    library passes (count, fill) with the prefix sum in between as tensor plumbing."""
+    B, N = cfg.num_envs, cfg.n_agents
+    _expect(state, torch.float32, B * N * 4, "state")
+    dev = state.device
+    deg = torch.empty(B * N, dtype=torch.int32, device=dev)
+    check(lib().swarm_graph_build_radius_csr(C.byref(cfg), ptr(state), ptr(deg), None, None, stream_ptr(dev)))
+    row_ptr = torch.zeros(B * N + 1, dtype=torch.int32, device=dev)
+    total = torch.cumsum(deg, 0, dtype=torch.int64)
+    if int(total[-1]) > 2 ** 31 - 1:
+        raise _lib.SwarmError("the radius graph has more than 2^31 - 1 edges")
+    row_ptr[1:] = total.to(torch.int32)
+    src = torch.empty(max(int(total[-1]), 1), dtype=torch.int32, device=dev)
+    check(lib().swarm_graph_build_radius_csr(C.byref(cfg), ptr(state), None, ptr(row_ptr), ptr(src), stream_ptr(dev)))
+    return row_ptr, src[:int(total[-1])]
+
+
 def gatconv_forward_csr(weights: torch.Tensor, x: torch.Tensor, row_ptr: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
     """The GATConv layer alone: x f32[n,7] + CSR-by-target -> f32[n,32] (aggregate + bias)."""
     n = x.shape[0]
@@ -583,6 +618,8 @@ def rollout_large(cfg: SwarmConfig, weights: torch.Tensor, state: torch.Tensor, 
     xspace = os.environ.get("SWARM_TC", "1")[:1] != "0"
     lib_loop = fused and cfg.graph_mode == _lib.GRAPH_KNN and N > 128 and 64 * cfg.knn_k <= N and not trace_state and \
         (N * (28 + 2 * cfg.knn_k) + 8400 <= 227 * 1024 if xspace else fused_knn)
+    # radius / complete graph: the library forward finds its own sources (uniform grid / every other agent), no edge list
+    lib_loop = lib_loop or (fused and cfg.graph_mode != _lib.GRAPH_KNN and 128 < N <= 4096 and not trace_state)
     if lib_loop:
         # the whole tick sequence from the library (swarm_rollout_large): topk table -> per-env Q + argmax -> world step
         # with returns / hits accumulated by the step kernel; no tensor op between the launches
@@ -605,6 +642,8 @@ def rollout_large(cfg: SwarmConfig, weights: torch.Tensor, state: torch.Tensor, 
             continue
         if cfg.graph_mode == _lib.GRAPH_COMPLETE and static_csr is not None:
             row_ptr, src = static_csr
+        elif cfg.graph_mode == _lib.GRAPH_RADIUS:
+            row_ptr, src = graph_build_radius_csr(cfg, state)         # bit-faithful generic path: CSR straight from the grid
         else:
             edges, _ = graph_build(cfg, state)
             ei = (edges.to(torch.int64) + offs).permute(1, 0, 2).reshape(2, -1).contiguous()

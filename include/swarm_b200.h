@@ -134,6 +134,30 @@ int swarm_graph_build(const SwarmConfig* cfg, const float* state, int32_t* edges
  * prefix sum over the env's agents gives its write offset.  n_agents <= 128. */
 int swarm_graph_build_radius(const SwarmConfig* cfg, const float* state, int32_t* edges, int32_t* counts, void* stream);
 
+/* Radius graph of a swarm of ANY size (n_agents <= 4096) in compact CSR form, grouped by target -- the large-swarm
+ * counterpart of swarm_graph_build_radius, whose padded N(N-1)+1 block would be 8 MB per env at N = 1024.  Same edge set
+ * and order as the edge list (i -> j), (j -> i) for i < j within cfg->graph_radius (rounded float32 2-norm, inclusive),
+ * then (0 -> 0), after a stable sort by target: the sources of a node ascend, node 0's self loop comes last.
+ * Candidates come from a uniform grid (cells one radius wide, at most 64 x 64 over the env's bounding box, agents sorted
+ * by (cell, index) in shared memory; a node looks at its 3 x 3 cells), membership from the exact distance test.
+ * Two passes on the same state:
+ *   count: degree int32[B*N] != NULL, row_ptr = src = NULL   -> in-degree of every node
+ *   fill:  degree = NULL, row_ptr int32[B*N+1] = exclusive prefix sum of the degrees (the caller's scan), src int32[E]
+ *          -> GLOBAL source ids b*N + j.  (row_ptr, src) feed swarm_gatq_forward_csr / swarm_gatq_backward_csr with
+ *          n_nodes = B*N directly. */
+int swarm_graph_build_radius_csr(const SwarmConfig* cfg, const float* state, int32_t* degree, const int32_t* row_ptr,
+                                 int32_t* src, void* stream);
+
+/* GCN.forward (train_gcn_dqn.py:59-70) + argmax for LARGE swarms on the radius graph (sources from the uniform grid
+ * above) or the complete graph (train:94-110: every other agent, node 0 also itself) without materialising an edge
+ * list -- the complete graph of 1 024 agents is 1 047 553 edges per env.  One CTA per env, attention in input space
+ * (GATConv's projection is linear and bias-free: softmax-weighted mean of the sources' 7 input features, then one
+ * projection), 20 B of shared memory per agent (+ 4 B + 16 KB for the grid): n_agents <= 4096.  Same mathematics as
+ * swarm_gatq_forward_csr on the same graph with float32-level different rounding (no fixed edge order); any n_agents
+ * >= 1 is accepted.  q float[B*N][9] and actions int32[B*N] are optional. */
+int swarm_gatq_forward_large(const SwarmConfig* cfg, const float* weights, const float* state, float* q,
+                             int32_t* actions, void* stream);
+
 /* GCN.forward (train_gcn_dqn.py:59-70) on the per-env graph named by cfg->graph_mode, node features
  * [pos, vel, goal, agent id] built from state (train:95-99).  q float[B*N][9] and actions int32[B*N]
  * (argmax, first maximum wins; train:167, simulator:64) are optional. */
@@ -166,6 +190,8 @@ int swarm_csr_from_edges(int32_t n_nodes, int64_t n_edges, const int64_t* edge_s
 int swarm_gatq_forward_knn_large(const SwarmConfig* cfg, const float* weights, const float* state,
                                  const int32_t* neighbours, float* q, int32_t* actions, void* stream);
 
+/* (graph_mode RADIUS / COMPLETE: the per-tick sequence is swarm_gatq_forward_large + the world step -- two launches --
+ * and SWARM_TC has no effect; everything else below applies.) */
 /* `ticks` greedy evaluation ticks of a LARGE kNN swarm (n_agents > 128; simulator.py:59-93 with the shipped kNN graph)
  * launched back to back from the library: per tick the topk table (swarm_graph_build), the Q forward + argmax straight
  * from the table (swarm_gatq_forward_knn_large) and the world step, whose kernel also accumulates returns float[B*N] (+=)
