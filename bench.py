@@ -362,6 +362,8 @@ def measure_extra(sb, ops, dev):
     w_oa, w_goto = weights("ObstacleAvoidance/0/"), weights("GoTo/0/")
 
     def rollout_rate(scen, B, N, graph, k, ticks, reps=3):
+        # kNN rows: the memo table of boundary-tie patterns (ops.knn_memo_table) is cleared before every timed launch, so
+        # the figure is that of a first encounter with these states, not of a replay of a remembered episode
         cfg = ops.make_config(scen, B, N, graph, k)
         centers = draw_centers(7, B).to(dev)
         state = ops.reset_grid(cfg, centers)
@@ -372,6 +374,8 @@ def measure_extra(sb, ops, dev):
         ms = 0.0
         for _ in range(reps):
             ops.reset_grid(cfg, centers, out=state)
+            if graph == L.GRAPH_KNN and N <= 12:
+                ops.knn_memo_table(dev, N, k, fresh=True)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             ops.rollout(cfg, w, state, ticks, returns=ret, hits=hits)

@@ -57,7 +57,8 @@ class SwarmReplay(C.Structure):
 class SwarmRolloutOptions(C.Structure):
     _fields_ = [("forced_actions", C.c_void_p), ("epsilon", C.c_float), ("rng_seed", C.c_uint64),
                 ("rng_tick0", C.c_int64), ("replay", C.POINTER(SwarmReplay)), ("replay_cursor", C.c_int64),
-                ("env_offset", C.c_int64), ("flocking", C.c_void_p), ("flocking_shaping", C.c_void_p)]
+                ("env_offset", C.c_int64), ("flocking", C.c_void_p), ("flocking_shaping", C.c_void_p),
+                ("knn_memo", C.c_void_p), ("knn_memo_entries", C.c_int64)]
 
 
 class SwarmTrainCtl(C.Structure):

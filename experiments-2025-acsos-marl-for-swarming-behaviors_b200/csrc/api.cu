@@ -133,6 +133,8 @@ int fill_params(TileParams& p, const SwarmConfig* cfg, int mode) {
   // dense contractions on the tensor cores (tcgen05 3xTF32) unless SWARM_TC=0 selects the CUDA-core FFMA path
   const char* tc_env = std::getenv("SWARM_TC");
   p.use_tc = (mode == MODE_ROLLOUT || mode == MODE_FORWARD) && !(tc_env && tc_env[0] == '0');
+  const char* ord_env = std::getenv("SWARM_KNN_ORDERED");
+  p.knn_ordered = (ord_env && ord_env[0] == '1') ? 1 : 0;
   TileLayout L = tile_layout(mode, kTileThreads, n, cfg->knn_k, p.maxdeg, cfg->graph_mode, p.use_tc != 0);
   if (L.total > 227 * 1024 && p.use_tc) {
     p.use_tc = 0;
@@ -542,6 +544,13 @@ int swarm_rollout(const SwarmConfig* cfg, const float* weights, float* state, in
       p.replay_cursor = opts->replay_cursor % r.capacity;
     }
     if (int rc = attach_flocking(p, cfg, opts->flocking, opts->flocking_shaping)) return rc;
+    if (opts->knn_memo) {
+      const int64_t n = opts->knn_memo_entries;
+      if (n <= 0 || (n & (n - 1)) != 0 || n > (1LL << 32))
+        return fail(SWARM_ERR_INVALID_ARG, "knn_memo_entries must be a power of two (<= 2^32)");
+      p.knn_memo = reinterpret_cast<unsigned long long*>(opts->knn_memo);
+      p.knn_memo_mask = (uint32_t)(n - 1);
+    }
   }
   if (trace) p.trace = *trace;
   return check_cuda(launch_tile(MODE_ROLLOUT, p, (cudaStream_t)stream), "swarm_rollout");

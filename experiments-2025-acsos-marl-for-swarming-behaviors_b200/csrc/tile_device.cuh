@@ -283,6 +283,77 @@ __device__ __forceinline__ uint64_t tile_knn_small(const TileThread& t, const fl
   return tile_knn_small_np<16>(t, pos, s, N, K, cache_rank, cache_nbr);
 }
 
+// ---- the SET of the K neighbours -----------------------------------------------------------------------------------
+// The tensor-core Q forward consumes the kNN graph as in-edge multiplicities (tile_knn_counts_small): it needs WHICH K
+// agents torch.topk returns, not in which order.  The set is unique unless a tie straddles the K boundary:
+// S = {j : rank_j < K} always contains the K smallest, so |S| = K decides it without running any algorithm (ties inside
+// the top K or beyond it -- the four equidistant lattice neighbours of an interior agent -- no longer matter; on C2
+// rollouts 4.5 % of the rows are left instead of 10 %).  The remaining rows go through
+//   1. the thread's previous boundary-tie row (cache_rank / cache_set: formation flight repeats its pattern),
+//   2. a memo table in global memory shared by every CTA and launch (optional, caller-owned, swarms of <= 12 agents:
+//      one 64-bit word per entry = 48-bit order pattern | 16-bit set, so a racing reader sees an old or a new entry,
+//      never a torn one; direct-mapped, lossy; 95 % of the boundary-tie rows of a C2 rollout carry a pattern some env
+//      has met before), and only then
+//   3. the libstdc++ emulation (knn_small_topk_fast), whose answer is published to the table.
+// The table belongs to ONE (n_agents, knn_k) pair: the order pattern does not encode them.
+struct KnnMemo {
+  unsigned long long* table;     // nullptr: no table
+  uint32_t mask;                 // entries - 1 (power of two)
+};
+
+template <int NP>
+__device__ __forceinline__ uint32_t tile_knn_small_set_np(const TileThread& t, const float4* pos, const float4& s, int N, int K,
+                                                         uint64_t& cache_rank, uint64_t& cache_set, const KnnMemo& memo) {
+  uint32_t u[NP];
+  const float4* env = pos + t.envbase;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    uint32_t key = kKnnPadKey;
+    if (j < N) {
+      const float2 o = xy_of(env[j]);
+      key = knn_key_nonneg(norm2(__fsub_rn(o.x, s.x), __fsub_rn(o.y, s.y)));
+    }
+    u[j] = key;
+  }
+  int r[NP];
+  uint32_t present;
+  const uint64_t rank = knn_small_ranks<NP>(u, r, present);
+  uint32_t lt = 0;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) lt |= (r[j] < K ? 1u : 0u) << j;     // padding ranks N >= K
+  if (__popc(lt) == K) return lt;
+  if (rank == cache_rank) return (uint32_t)cache_set;
+  uint32_t set = 0;
+  bool found = false;
+  const bool use_table = NP <= 12 && memo.table != nullptr;
+  unsigned long long* slot = nullptr;
+  if (use_table) {
+    slot = memo.table + ((uint32_t)((rank * 0x9E3779B97F4A7C15ull) >> 40) & memo.mask);
+    const unsigned long long e = __ldcg(slot);
+    if ((e >> 16) == rank && __popc((uint32_t)(e & 0xFFFFu)) == K) {
+      set = (uint32_t)(e & 0xFFFFu);
+      found = true;
+    }
+  }
+  if (!found) {
+    const uint64_t nbr = knn_small_topk_fast(rank, N, K);
+    for (int q = 0; q < K; ++q) set |= 1u << knn_nib(nbr, q);
+    if (use_table) __stcg(slot, (unsigned long long)((rank << 16) | set));
+  }
+  cache_rank = rank;
+  cache_set = set;
+  return set;
+}
+
+__device__ __forceinline__ uint32_t tile_knn_small_set(const TileThread& t, const float4* pos, const float4& s, int N, int K,
+                                                      uint64_t& cache_rank, uint64_t& cache_set, const KnnMemo& memo) {
+  if (!t.active) return 0;
+  if (K >= N) return (1u << N) - 1u;                  // k = n (simulator.py:19 with 5 agents and k = 5): everybody
+  if (N <= 8) return tile_knn_small_set_np<8>(t, pos, s, N, K, cache_rank, cache_set, memo);
+  if (N <= 12) return tile_knn_small_set_np<12>(t, pos, s, N, K, cache_rank, cache_set, memo);
+  return tile_knn_small_set_np<16>(t, pos, s, N, K, cache_rank, cache_set, memo);
+}
+
 // in-edges of node i from the neighbour words (same list, same order as tile_in_edges_knn): every thread publishes the
 // 16-bit set of its row, one barrier, then N bit tests.  `smask` = uint32[T]; it is rewritten only after the barriers
 // of the Q forward that follows, so no trailing barrier is needed.  Every thread of the CTA must call it.
@@ -331,11 +402,18 @@ __device__ __forceinline__ uint32_t spread_bits16(uint32_t x) {       // bit j -
   x = (x | (x << 1)) & 0x55555555u;
   return x;
 }
+// (`mine` = the 16-bit set of this thread's row)
+__device__ __forceinline__ uint32_t tile_knn_counts_small_set(const TileThread& t, int N, uint32_t mine,
+                                                             uint32_t* __restrict__ smask);
 __device__ __forceinline__ uint32_t tile_knn_counts_small(const TileThread& t, int N, int K, uint64_t nbr,
                                                          uint32_t* __restrict__ smask) {
   uint32_t mine = 0;
   if (t.active)
     for (int r = 0; r < K; ++r) mine |= 1u << knn_nib(nbr, r);
+  return tile_knn_counts_small_set(t, N, mine, smask);
+}
+__device__ __forceinline__ uint32_t tile_knn_counts_small_set(const TileThread& t, int N, uint32_t mine,
+                                                             uint32_t* __restrict__ smask) {
   smask[t.tid] = mine;
   __syncthreads();
   if (!t.active) return 0;

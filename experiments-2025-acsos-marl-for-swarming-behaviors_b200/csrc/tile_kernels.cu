@@ -124,6 +124,9 @@ tile_kernel(const __grid_constant__ TileParams p) {
   if (kQ && !TC && complete && t.active) deg = tile_in_edges_complete(g, t, N);   // the TC path needs no edge list for it
   const bool knn_small = knn && N <= kKnnSmallMax;          // register-resident rows (knn_small.h)
   uint64_t nbr_word = 0, knn_cache_rank = ~0ull, knn_cache_nbr = 0;
+  // order-free kNN: nobody reads the neighbours' ORDER (no edge export) and the forward takes multiplicities
+  const bool knn_set = knn_small && TC && kQ && !(MODE == MODE_ROLLOUT && p.trace.edges) && !p.knn_ordered;
+  const KnnMemo knn_memo{p.knn_memo, p.knn_memo_mask};
 
   float ret = 0.0f;
   int myhits = 0;
@@ -146,7 +149,11 @@ tile_kernel(const __grid_constant__ TileParams p) {
 
     // ------------------------------------------------------------------ graph ----------------
     uint32_t knn_counts = 0;
-    if (knn_small) {
+    if (knn_small && knn_set) {
+      // the tensor-core forward needs the SET of the K neighbours only (tile_device.cuh)
+      const uint32_t mine = tile_knn_small_set(t, pos, s, N, K, knn_cache_rank, knn_cache_nbr, knn_memo);
+      knn_counts = tile_knn_counts_small_set(t, N, mine, reinterpret_cast<uint32_t*>(g.skv));
+    } else if (knn_small) {
       nbr_word = tile_knn_small(t, pos, s, N, K, knn_cache_rank, knn_cache_nbr);
       if (kQ && TC) knn_counts = tile_knn_counts_small(t, N, K, nbr_word, reinterpret_cast<uint32_t*>(g.skv));
       else if (kQ) deg = tile_in_edges_knn_small(g, t, N, K, nbr_word, reinterpret_cast<uint32_t*>(g.skv));

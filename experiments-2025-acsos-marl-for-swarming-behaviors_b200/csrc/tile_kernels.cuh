@@ -124,6 +124,10 @@ struct TileParams {
   SwarmRewardSpec flock;         // its constants
   float2* shaping;               // [B*N] (previous_distance_to_goal, previous_distance_to_agents), read at launch, written back
   int32_t use_flock;
+  // kNN rows of small swarms on the tensor-core path (tile_device.cuh): optional memo table of boundary-tie patterns
+  unsigned long long* knn_memo;
+  uint32_t knn_memo_mask;        // entries - 1
+  int32_t knn_ordered;           // 1: always run the ordered (torch.topk output order) row code (SWARM_KNN_ORDERED=1)
 };
 
 // largest float q with sqrtf(q) <= dmin: makes a squared-distance test exactly equivalent to the reference's

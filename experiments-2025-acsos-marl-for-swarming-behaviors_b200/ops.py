@@ -132,21 +132,42 @@ class ReplayRing:
         return self.size
 
 
+_KNN_MEMO: Dict[Tuple[str, int, int], torch.Tensor] = {}
+KNN_MEMO_ENTRIES = 1 << 17          # 1 MB: stays L2 resident
+
+
+def knn_memo_table(device, n_agents: int, knn_k: int, fresh: bool = False) -> torch.Tensor:
+    """The cached memo table of kNN boundary-tie patterns for (device, n_agents, knn_k) (SwarmRolloutOptions.knn_memo);
+    ``fresh`` clears it."""
+    key = (str(torch.device(device)), int(n_agents), int(knn_k))
+    t = _KNN_MEMO.get(key)
+    if t is None:
+        t = torch.zeros(KNN_MEMO_ENTRIES, dtype=torch.int64, device=device)
+        _KNN_MEMO[key] = t
+    elif fresh:
+        t.zero_()
+    return t
+
+
 def rollout(cfg: SwarmConfig, weights: torch.Tensor, state: torch.Tensor, ticks: int, *,
             forced_actions: Optional[torch.Tensor] = None, returns: Optional[torch.Tensor] = None,
             hits: Optional[torch.Tensor] = None, trace: Optional[Dict[str, bool]] = None,
             epsilon: float = 0.0, rng_seed: int = 0, rng_tick0: int = 0, env_offset: int = 0,
             replay: Optional[ReplayRing] = None, flocking: Optional["_lib.SwarmRewardSpec"] = None,
-            shaping: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+            shaping: Optional[torch.Tensor] = None, knn_memo="auto") -> Dict[str, torch.Tensor]:
     """Fused (epsilon-)greedy rollout, in place on ``state``.  ``trace`` names the per-tick records to keep
     (any of state, actions, q, rewards, flags, contact, edges, dist).  With ``replay`` every tick's B
     transitions are pushed into the ring (and its cursor advanced).  With ``flocking`` (a Flocking reward spec, cfg =
     the GoTo world) the reward of every tick is the Flocking collective reward and ``shaping`` f32[B,N,2] carries the
-    ``previous_*`` memory in and out."""
+    ``previous_*`` memory in and out.  ``knn_memo``: the memo table of kNN boundary-tie patterns (``"auto"`` = one
+    cached int64 table per (device, n_agents, knn_k), ``None`` = no table, or a caller-owned zero-initialised int64
+    tensor with a power-of-two length); it only saves time, results never depend on it."""
     B, N = cfg.num_envs, cfg.n_agents
     _expect(state, torch.float32, B * N * 4, "state")
     _expect(weights, torch.float32, _lib.W_COUNT, "weights")
     dev = state.device
+    if isinstance(knn_memo, str):
+        knn_memo = knn_memo_table(dev, N, cfg.knn_k) if (cfg.graph_mode == _lib.GRAPH_KNN and N <= 12) else None
     if forced_actions is not None:
         _expect(forced_actions, torch.int32, ticks * B * N, "forced_actions")
     if returns is None:
@@ -184,6 +205,10 @@ def rollout(cfg: SwarmConfig, weights: torch.Tensor, state: torch.Tensor, ticks:
         opts.flocking = C.addressof(flocking)
         opts.flocking_shaping = ptr(shaping)
         out["shaping"] = shaping
+    if knn_memo is not None:
+        _expect(knn_memo, torch.int64, knn_memo.numel(), "knn_memo")
+        opts.knn_memo = ptr(knn_memo)
+        opts.knn_memo_entries = knn_memo.numel()
     rstruct = None
     if replay is not None:
         if replay.n_agents != N:

@@ -279,6 +279,15 @@ typedef struct SwarmRolloutOptions {
    * swarm_scenario_reward reset call after placing the agents). */
   const struct SwarmRewardSpec* flocking;
   float* flocking_shaping;
+  /* kNN graph, n_agents <= 12, tensor-core path without an edge trace: the Q forward consumes the kNN graph as in-edge
+   * multiplicities, so only the SET of each row's k neighbours is needed; it is unique unless a tie straddles the k
+   * boundary, and only those rows need torch.topk's algorithm (libstdc++ introselect, emulated step for step).  Its
+   * answer is a function of the row's order pattern alone, so it can be memoised: knn_memo uint64[knn_memo_entries]
+   * (optional; entries a power of two; zero-initialised by the caller, then owned by the library's kernels: a lossy
+   * direct-mapped table, one word per entry = 48-bit order pattern | 16-bit neighbour set) is shared by every CTA and
+   * may be kept across launches.  ONE table per (n_agents, knn_k) pair.  Results do not depend on its contents. */
+  uint64_t* knn_memo;
+  int64_t knn_memo_entries;
 } SwarmRolloutOptions;
 
 /* Fused rollout: `ticks` iterations of [graph build -> GCN forward -> (epsilon-)greedy argmax -> env step]

@@ -258,5 +258,10 @@ def test_flocking_option_of_the_fused_tick_is_validated(sb):
     assert roll(one) == -1 and b"two agents" in lib.swarm_last_error()
     spec.kind = L.REWARD_COHESION
     assert roll(cfg) == -1 and b"Flocking reward spec" in lib.swarm_last_error()
-    assert L.SwarmRolloutOptions.flocking.offset + 16 == C.sizeof(L.SwarmRolloutOptions)
+    assert L.SwarmRolloutOptions.flocking.offset + 32 == C.sizeof(L.SwarmRolloutOptions)     # + knn_memo, knn_memo_entries
+    opts2 = L.SwarmRolloutOptions()
+    opts2.knn_memo, opts2.knn_memo_entries = 8, 1000                                        # not a power of two
+    knn = sb.ops.make_config(L.SCENARIO_GOTO, 16, 5, L.GRAPH_KNN, 3)
+    assert lib.swarm_rollout(C.byref(knn), 8, 8, 1, C.byref(opts2), None, None, None, None) == -1
+    assert b"power of two" in lib.swarm_last_error()
     assert L.SwarmTrainHyper.flocking.offset + 16 == C.sizeof(L.SwarmTrainHyper)

@@ -132,3 +132,27 @@ def test_word_level_emulation_equals_the_stepwise_one_on_adversarial_patterns(sh
         slow, _ = _small(shim, rows, k, 1)
         fast, _ = _small(shim, rows, k, 2)
         assert torch.equal(slow, ref) and torch.equal(fast, ref), f"n={n} k={k}"
+
+
+@pytest.mark.parametrize("n,k", [(5, 5), (6, 3), (8, 3), (9, 5), (12, 5), (12, 10), (16, 6), (16, 15)])
+def test_rank_below_k_decides_the_neighbour_set(n, k):
+    """The order-free shortcut of the tensor-core rollout (csrc/tile_device.cuh tile_knn_small_set_np): with
+    rank_j = #{l : d_l < d_j}, S = {j : rank_j < k} always contains torch.topk's k indices, so |S| = k means the SET is
+    S whatever order the algorithm returns it in -- checked against torch.topk on tie-heavy rows (lattice distances)."""
+    g = torch.Generator().manual_seed(n * 31 + k)
+    decided = undecided = 0
+    for trial in range(400):
+        rows = _grid_distance_rows(n, g, jitter=0.0 if trial % 2 == 0 else 1e-3)
+        for row in rows:
+            rank = (row[None, :] < row[:, None]).sum(1)
+            s = set(torch.nonzero(rank < k).flatten().tolist())
+            top = set(torch.topk(row, k, largest=False).indices.tolist())
+            assert top <= s
+            if len(s) == k:
+                assert top == s
+                decided += 1
+            else:
+                undecided += 1
+    assert decided > 0
+    if (n, k) == (12, 5):
+        assert undecided > 0, "the lattice rows must contain boundary ties"
