@@ -61,6 +61,15 @@ class SwarmRolloutOptions(C.Structure):
                 ("knn_memo", C.c_void_p), ("knn_memo_entries", C.c_int64)]
 
 
+class SwarmStackSpec(C.Structure):
+    """Multi-layer GAT Q-network (include/swarm_b200.h SwarmStackSpec)."""
+    _fields_ = [("n_layers", C.c_int32), ("hidden", C.c_int32), ("in_features", C.c_int32),
+                ("activation", C.c_int32 * 4), ("pad", C.c_int32)]
+
+
+ACT_TANH, ACT_RELU = 0, 1
+
+
 class SwarmTrainCtl(C.Structure):
     """Host mirror of the 48-byte device struct (only used to document / check the layout)."""
     _fields_ = [("tick", C.c_int64), ("ring_cursor", C.c_int64), ("ring_size", C.c_int64), ("opt_step", C.c_int64),
@@ -110,6 +119,11 @@ _SIGNATURES = {
     "swarm_sim_step": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 9),
     "swarm_graph_build": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 4),
     "swarm_graph_build_radius": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 4),
+    "swarm_stack_weight_count": (C.c_int64, [C.POINTER(SwarmStackSpec)]),
+    "swarm_gatstack_forward": (C.c_int, [C.POINTER(SwarmConfig), C.POINTER(SwarmStackSpec)] + [C.c_void_p] * 5),
+    "swarm_rollout_stack_workspace_bytes": (C.c_int64, [C.POINTER(SwarmConfig)]),
+    "swarm_rollout_stack": (C.c_int, [C.POINTER(SwarmConfig), C.POINTER(SwarmStackSpec), C.c_void_p, C.c_void_p, C.c_int32,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "swarm_graph_build_radius_csr": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 5),
     "swarm_gatq_forward_large": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 5),
     "swarm_gatq_forward": (C.c_int, [C.POINTER(SwarmConfig)] + [C.c_void_p] * 5),

@@ -31,6 +31,11 @@ cudaError_t launch_reset_random(const SwarmConfig& c, const SwarmResetSpec& sp, 
 cudaError_t launch_episode_end(const SwarmConfig& c, SwarmTrainCtl* ctl, float* returns, int32_t* hits, const float* loss,
                                float* stats, long long max_episodes, double eps0, double decay, double min_eps,
                                cudaStream_t stream);
+int stack_weight_count_host(const SwarmStackSpec& s);
+cudaError_t launch_gatstack_forward(const SwarmConfig& c, const SwarmStackSpec& spec, const float* weights, const float* state,
+                                    float* q, int32_t* actions, cudaStream_t stream);
+cudaError_t launch_stack_accumulate(long long total, int N, const float* rewards, int per_env, const uint8_t* flags,
+                                    float* returns, int32_t* hits, cudaStream_t stream);
 bool gatq_knn_large_fits(int N, int K);
 bool gatq_large_x_fits(int N, bool radius);
 cudaError_t launch_gatq_large_x(const SwarmConfig& c, const float* weights, const float* state, float* q, int32_t* actions,
@@ -744,6 +749,96 @@ int swarm_scenario_reward(const SwarmRewardSpec* spec, const float* state, float
   }
   return check_cuda(launch_scenario_reward(*spec, state, shaping, reward, terms, (cudaStream_t)stream),
                     "swarm_scenario_reward");
+}
+
+namespace {
+int validate_stack(const SwarmConfig* cfg, const SwarmStackSpec* spec) {
+  if (int rc = validate(cfg, true)) return rc;
+  if (!spec) return fail(SWARM_ERR_INVALID_ARG, "spec is NULL");
+  if (spec->n_layers < 1 || spec->n_layers > 4) return fail(SWARM_ERR_INVALID_ARG, "n_layers must be 1 .. 4");
+  if (spec->hidden < 1 || spec->hidden > 32) return fail(SWARM_ERR_UNSUPPORTED, "hidden must be 1 .. 32");
+  if (spec->in_features != 7 && spec->in_features != 5) return fail(SWARM_ERR_INVALID_ARG, "in_features must be 7 or 5");
+  for (int l = 0; l < spec->n_layers; ++l)
+    if (spec->activation[l] != SWARM_ACT_TANH && spec->activation[l] != SWARM_ACT_RELU)
+      return fail(SWARM_ERR_INVALID_ARG, "unknown activation");
+  if (cfg->graph_mode == SWARM_GRAPH_KNN && cfg->n_agents > 16)
+    return fail(SWARM_ERR_UNSUPPORTED, "stacked networks on the kNN graph are implemented for n_agents <= 16");
+  return SWARM_OK;
+}
+}  // namespace
+
+int64_t swarm_stack_weight_count(const SwarmStackSpec* spec) {
+  if (!spec || spec->n_layers < 1 || spec->n_layers > 4 || spec->hidden < 1 || spec->hidden > 32) return 0;
+  return stack_weight_count_host(*spec);
+}
+
+int swarm_gatstack_forward(const SwarmConfig* cfg, const SwarmStackSpec* spec, const float* weights, const float* state,
+                           float* q, int32_t* actions, void* stream) {
+  if (int rc = validate_stack(cfg, spec)) return rc;
+  if (!weights || !state) return fail(SWARM_ERR_INVALID_ARG, "weights/state is NULL");
+  if (!q && !actions) return fail(SWARM_ERR_INVALID_ARG, "no output requested");
+  return check_cuda(launch_gatstack_forward(*cfg, *spec, weights, state, q, actions, (cudaStream_t)stream),
+                    "swarm_gatstack_forward");
+}
+
+int64_t swarm_rollout_stack_workspace_bytes(const SwarmConfig* cfg) {
+  if (!cfg || cfg->num_envs <= 0 || cfg->n_agents <= 0) return 0;
+  const int64_t bn = (int64_t)cfg->num_envs * cfg->n_agents;
+  return bn * 4 + bn * 4 + bn + 1024;             // actions, rewards, flags
+}
+
+int swarm_rollout_stack(const SwarmConfig* cfg, const SwarmStackSpec* spec, const float* weights, float* state,
+                        int32_t ticks, const SwarmRewardSpec* reward, float* shaping, float* returns, int32_t* hits,
+                        void* workspace, int64_t workspace_bytes, void* stream) {
+  if (int rc = validate_stack(cfg, spec)) return rc;
+  if (!weights || !state || !workspace) return fail(SWARM_ERR_INVALID_ARG, "weights/state/workspace is NULL");
+  if (ticks < 0) return fail(SWARM_ERR_INVALID_ARG, "ticks must be >= 0");
+  if (workspace_bytes < swarm_rollout_stack_workspace_bytes(cfg)) return fail(SWARM_ERR_INVALID_ARG, "workspace too small");
+  SwarmRewardSpec rs;
+  if (reward) {
+    rs = *reward;
+    if (rs.kind != SWARM_REWARD_FLOCKING && rs.kind != SWARM_REWARD_COHESION)
+      return fail(SWARM_ERR_INVALID_ARG, "unknown reward kind");
+    if (cfg->scenario != SWARM_SCENARIO_GOTO)
+      return fail(SWARM_ERR_INVALID_ARG, "the Flocking / Cohesion rewards run on the GoTo world (cfg->scenario)");
+    if (rs.num_envs != cfg->num_envs || rs.n_agents != cfg->n_agents)
+      return fail(SWARM_ERR_INVALID_ARG, "reward spec and cfg disagree on num_envs / n_agents");
+    if (rs.n_agents < 2) return fail(SWARM_ERR_INVALID_ARG, "the scenario rewards need at least two agents");
+    if (rs.kind == SWARM_REWARD_FLOCKING && !shaping) return fail(SWARM_ERR_INVALID_ARG, "Flocking needs the shaping buffer");
+    if (rs.kind == SWARM_REWARD_COHESION && !(rs.sigma > 0.0f)) return fail(SWARM_ERR_INVALID_ARG, "sigma must be > 0");
+    rs.reset = 0;
+    rs.env_index = -1;
+  }
+  TileParams p;
+  if (int rc = fill_params(p, cfg, MODE_STEP)) return rc;
+  const int64_t bn = (int64_t)cfg->num_envs * cfg->n_agents;
+  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
+  int32_t* actions = reinterpret_cast<int32_t*>(base);
+  float* rewards = reinterpret_cast<float*>(actions + bn);
+  uint8_t* flags = reinterpret_cast<uint8_t*>(rewards + bn);
+  p.state_in = state;
+  p.state_out = state;
+  p.actions_in = actions;
+  p.rewards_out = rewards;
+  p.flags_out = flags;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int t = 0; t < ticks; ++t) {
+    if (cudaError_t e = launch_gatstack_forward(*cfg, *spec, weights, state, nullptr, actions, st); e != cudaSuccess)
+      return check_cuda(e, "swarm_rollout_stack (forward)");
+    cudaError_t e = cfg->n_agents <= 64 ? launch_sim_step(p, st) : launch_tile(MODE_STEP, p, st);
+    if (e != cudaSuccess) return check_cuda(e, "swarm_rollout_stack (step)");
+    int per_env = 0;
+    if (reward) {
+      per_env = rs.kind == SWARM_REWARD_FLOCKING ? 1 : 0;
+      if (cudaError_t e2 = launch_scenario_reward(rs, state, shaping, rewards, nullptr, st); e2 != cudaSuccess)
+        return check_cuda(e2, "swarm_rollout_stack (reward)");
+    }
+    if (returns || hits)
+      if (cudaError_t e3 = launch_stack_accumulate(bn, cfg->n_agents, rewards, per_env, flags, returns, hits, st);
+          e3 != cudaSuccess)
+        return check_cuda(e3, "swarm_rollout_stack (accumulate)");
+  }
+  return SWARM_OK;
 }
 
 int swarm_episode_end(const SwarmConfig* cfg, SwarmTrainCtl* ctl, float* returns, int32_t* hits, const float* loss,

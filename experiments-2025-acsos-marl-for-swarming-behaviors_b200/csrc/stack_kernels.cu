@@ -1,0 +1,310 @@
+// stack_kernels.cu -- multi-layer GAT Q-networks in ONE launch.
+//
+// The reference's GCN class carries two more GATConv layers in comments (train_gcn_dqn.py:54-55, 64-67) and ships ten
+// checkpoints of that three-layer form (data/models/experiment_Flocking-seed_*.pth: conv1 7 -> 8, conv2 / conv3 8 -> 8,
+// lin1 8 -> 8, lin2 8 -> 9).  Stacking the generic layer kernels (gatlayer_kernels.cu) costs one launch set per layer
+// plus the edge-list / CSR glue; here a whole forward
+//     node features -> per-env graph -> L x [GATConv -> activation] -> lin1 -> ReLU -> lin2 (-> argmax)
+// is one env-tile kernel (thread = agent, CTA = floor(128 / N) envs, tile_device.cuh): the in-edge lists are built once
+// in shared memory and reused by every layer, the layer outputs never leave the chip.  The input features are the
+// reference's [pos, vel, goal, agent id] (train:95-99) or [pos, vel, agent id] for scenarios whose observation() is
+// cat[pos, vel] (cohesion_scenario.py:87-94).  Per layer the arithmetic follows torch_geometric's GATConv like the
+// one-layer kernels: h = x W^T, alpha = <h, att>, LeakyReLU(0.2) logits, max-subtracted softmax with the 1e-16
+// denominator, messages alpha * h_src summed in edge-list order, + bias.
+#include "tile_device.cuh"
+
+namespace swarm {
+
+struct StackParams {
+  SwarmConfig cfg;
+  SwarmStackSpec spec;
+  const float* weights;
+  const float4* state;
+  float* q_out;              // [B*N][9] or nullptr
+  int32_t* act_out;          // [B*N] or nullptr
+  int32_t epb, maxdeg;
+  float qmax_r;
+};
+
+constexpr int kStackMaxLayers = 4;
+
+// shared-memory weight block, everything padded to HP channels / 8 input features with zeros
+template <int HP>
+struct StackLayout {
+  static constexpr int kIn0 = 8;                                        // padded input features
+  static constexpr int kLayer0 = kIn0 * HP + 3 * HP;                    // WT[8][HP], att_s, att_d, bias
+  static constexpr int kLayer = HP * HP + 3 * HP;                       // WT[HP][HP], att_s, att_d, bias
+  static constexpr int kW2Cols = 12;
+  __host__ __device__ static int layer_off(int l) { return l == 0 ? 0 : kLayer0 + (l - 1) * kLayer; }
+  __host__ __device__ static int lin1_off(int L) { return layer_off(L); }
+  __host__ __device__ static int lin2_off(int L) { return lin1_off(L) + HP * HP + HP; }
+  __host__ __device__ static int total(int L) { return lin2_off(L) + HP * kW2Cols + kW2Cols; }
+};
+
+__host__ __device__ inline int stack_weight_count(const SwarmStackSpec& s) {
+  const int H = s.hidden;
+  int n = 0;
+  for (int l = 0; l < s.n_layers; ++l) n += 3 * H + H * (l == 0 ? s.in_features : H);
+  return n + H * H + H + 9 * H + 9;
+}
+
+// packed weights (state-dict order: per layer att_src, att_dst, bias, lin.weight[H][Cin]; lin1.weight[H][H], lin1.bias,
+// lin2.weight[9][H], lin2.bias) -> padded k-major shared layout
+template <int HP>
+__device__ __forceinline__ void stack_stage_weights(const SwarmStackSpec& s, const float* __restrict__ g, float* __restrict__ sw,
+                                                    int tid, int nthreads) {
+  using SL = StackLayout<HP>;
+  const int H = s.hidden, L = s.n_layers;
+  for (int o = tid; o < SL::total(L); o += nthreads) sw[o] = 0.0f;
+  __syncthreads();
+  int goff = 0;
+  for (int l = 0; l < L; ++l) {
+    const int cin = l == 0 ? s.in_features : H;
+    const int cinp = l == 0 ? SL::kIn0 : HP;
+    float* base = sw + SL::layer_off(l);
+    float* vec = base + cinp * HP;
+    for (int o = tid; o < 3 * H; o += nthreads) vec[(o / H) * HP + (o % H)] = g[goff + o];
+    goff += 3 * H;
+    for (int o = tid; o < H * cin; o += nthreads) {
+      const int c = o / cin, k = o - c * cin;
+      base[k * HP + c] = g[goff + o];
+    }
+    goff += H * cin;
+  }
+  float* l1 = sw + SL::lin1_off(L);
+  for (int o = tid; o < H * H; o += nthreads) {
+    const int c = o / H, k = o - c * H;
+    l1[k * HP + c] = g[goff + o];
+  }
+  goff += H * H;
+  for (int o = tid; o < H; o += nthreads) l1[HP * HP + o] = g[goff + o];
+  goff += H;
+  float* l2 = sw + SL::lin2_off(L);
+  for (int o = tid; o < 9 * H; o += nthreads) {
+    const int a = o / H, k = o - a * H;
+    l2[k * SL::kW2Cols + a] = g[goff + o];
+  }
+  goff += 9 * H;
+  for (int o = tid; o < 9; o += nthreads) l2[HP * SL::kW2Cols + o] = g[goff + o];
+}
+
+struct StackSmem {
+  int w, st, h, asrc, inl, kv, total;
+};
+template <int HP>
+__host__ __device__ inline StackSmem stack_smem(int L, int n, int k, int maxdeg, int graph_mode) {
+  StackSmem s;
+  int off = 0;
+  s.w = off;    off = tile_align16(off + StackLayout<HP>::total(L) * 4);
+  s.st = off;   off = tile_align16(off + kTileThreads * 16);
+  s.h = off;    off = tile_align16(off + kTileThreads * (HP + 4) * 4);
+  s.asrc = off; off = tile_align16(off + kTileThreads * 4);
+  s.inl = off;  off = tile_align16(off + maxdeg * kTileThreads);
+  s.kv = off;   off = tile_align16(off + (graph_mode == SWARM_GRAPH_KNN ? kTileThreads * 4 : 0));
+  s.total = off;
+  return s;
+}
+
+template <int HP>
+__global__ void __launch_bounds__(kTileThreads) gatstack_forward_kernel(const __grid_constant__ StackParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  using SL = StackLayout<HP>;
+  constexpr int kRow = HP + 4;
+  const SwarmConfig& c = p.cfg;
+  const SwarmStackSpec& sp = p.spec;
+  const int T = kTileThreads, N = c.n_agents, K = c.knn_k, L = sp.n_layers;
+  const TileThread t = tile_thread(N, p.epb, c.num_envs);
+  const int tid = t.tid;
+  const StackSmem S = stack_smem<HP>(L, N, K, p.maxdeg, c.graph_mode);
+  float* sw = reinterpret_cast<float*>(smem + S.w);
+  float4* sst = reinterpret_cast<float4*>(smem + S.st);
+  float* sh = reinterpret_cast<float*>(smem + S.h);
+  TileGraphSmem g = {};
+  g.sas = reinterpret_cast<float*>(smem + S.asrc);
+  g.sin = smem + S.inl;
+  g.skv = reinterpret_cast<float*>(smem + S.kv);
+
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t.active) s = p.state[t.gidx];
+  stack_stage_weights<HP>(sp, p.weights, sw, tid, T);
+  sst[tid] = s;
+  __syncthreads();
+
+  // ---- graph: in-edge list of this node in edge-list order, once for all layers ------------------------------------
+  int deg = 0;
+  if (c.graph_mode == SWARM_GRAPH_KNN) {
+    uint64_t cache_rank = ~0ull, cache_nbr = 0;
+    const uint64_t nbr = tile_knn_small(t, sst, s, N, K, cache_rank, cache_nbr);
+    deg = tile_in_edges_knn_small(g, t, N, K, nbr, reinterpret_cast<uint32_t*>(g.skv));
+  } else if (c.graph_mode == SWARM_GRAPH_RADIUS) {
+    if (t.active) deg = tile_in_edges_radius(g, t, sst, s, N, p.qmax_r);
+  } else if (t.active) {
+    deg = tile_in_edges_complete(g, t, N);
+  }
+
+  // ---- node features (train:95-99) ------------------------------------------------------------------------------
+  float x[HP];
+#pragma unroll
+  for (int k = 0; k < HP; ++k) x[k] = 0.0f;
+  x[0] = s.x; x[1] = s.y; x[2] = s.z; x[3] = s.w;
+  if (sp.in_features == 7) {
+    x[4] = c.goal_x; x[5] = c.goal_y; x[6] = (float)t.i;
+  } else {
+    x[4] = (float)t.i;
+  }
+
+  const uint8_t* sin = g.sin + tid;
+  for (int l = 0; l < L; ++l) {
+    const float* base = sw + SL::layer_off(l);
+    const int cinp = l == 0 ? SL::kIn0 : HP;
+    const float* vec = base + cinp * HP;
+    // h = x W^T (sequential-k FFMA chains), alpha terms
+    float h[HP];
+#pragma unroll
+    for (int cc = 0; cc < HP; ++cc) h[cc] = 0.0f;
+    if (l == 0) {
+#pragma unroll
+      for (int k = 0; k < SL::kIn0; ++k) {
+#pragma unroll
+        for (int cc = 0; cc < HP; ++cc) h[cc] = fmaf(x[k], base[k * HP + cc], h[cc]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < HP; ++k) {
+#pragma unroll
+        for (int cc = 0; cc < HP; ++cc) h[cc] = fmaf(x[k], base[k * HP + cc], h[cc]);
+      }
+    }
+    float asrc = 0.0f, adst = 0.0f;
+#pragma unroll
+    for (int cc = 0; cc < HP; ++cc) {
+      asrc = __fadd_rn(asrc, __fmul_rn(h[cc], vec[cc]));
+      adst = __fadd_rn(adst, __fmul_rn(h[cc], vec[HP + cc]));
+    }
+    if (l > 0) __syncthreads();                       // the previous layer's rows are no longer read
+#pragma unroll
+    for (int cc = 0; cc < HP; cc += 4)
+      *reinterpret_cast<float4*>(sh + tid * kRow + cc) = make_float4(h[cc], h[cc + 1], h[cc + 2], h[cc + 3]);
+    g.sas[tid] = asrc;
+    __syncthreads();
+    // softmax over the in-edges (max, denominator, messages), sources read from the env's rows
+    const float* rows = sh + t.envbase * kRow;
+    const float* as_env = g.sas + t.envbase;
+    float m = -INFINITY;
+    for (int e = 0; e < deg; ++e) m = fmaxf(m, gat_logit(as_env[sin[e * T]], adst));
+    float den = 0.0f;
+    for (int e = 0; e < deg; ++e) den = __fadd_rn(den, expf(__fsub_rn(gat_logit(as_env[sin[e * T]], adst), m)));
+    den = __fadd_rn(den, 1e-16f);
+#pragma unroll
+    for (int cc = 0; cc < HP; ++cc) x[cc] = 0.0f;
+    for (int e = 0; e < deg; ++e) {
+      const int j = sin[e * T];
+      const float a = __fdiv_rn(expf(__fsub_rn(gat_logit(as_env[j], adst), m)), den);
+      const float* hj = rows + j * kRow;
+#pragma unroll
+      for (int cc = 0; cc < HP; cc += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(hj + cc);
+        x[cc + 0] = __fadd_rn(x[cc + 0], __fmul_rn(a, v.x));
+        x[cc + 1] = __fadd_rn(x[cc + 1], __fmul_rn(a, v.y));
+        x[cc + 2] = __fadd_rn(x[cc + 2], __fmul_rn(a, v.z));
+        x[cc + 3] = __fadd_rn(x[cc + 3], __fmul_rn(a, v.w));
+      }
+    }
+    const bool relu = sp.activation[l] == 1;
+#pragma unroll
+    for (int cc = 0; cc < HP; ++cc) {
+      const float v = __fadd_rn(x[cc], vec[2 * HP + cc]);
+      x[cc] = relu ? fmaxf(v, 0.0f) : tanhf(v);       // padded channels: weights and bias are 0, tanh(0) = relu(0) = 0
+    }
+  }
+
+  // ---- head: lin1 -> ReLU -> lin2, argmax (first maximum wins) ----------------------------------------------------
+  const float* l1 = sw + SL::lin1_off(L);
+  float r[HP];
+#pragma unroll
+  for (int cc = 0; cc < HP; ++cc) r[cc] = 0.0f;
+#pragma unroll
+  for (int k = 0; k < HP; ++k) {
+#pragma unroll
+    for (int cc = 0; cc < HP; ++cc) r[cc] = fmaf(x[k], l1[k * HP + cc], r[cc]);
+  }
+#pragma unroll
+  for (int cc = 0; cc < HP; ++cc) r[cc] = fmaxf(__fadd_rn(r[cc], l1[HP * HP + cc]), 0.0f);
+  const float* l2 = sw + SL::lin2_off(L);
+  float q[9];
+#pragma unroll
+  for (int a = 0; a < 9; ++a) q[a] = 0.0f;
+#pragma unroll
+  for (int k = 0; k < HP; ++k) {
+#pragma unroll
+    for (int a = 0; a < 9; ++a) q[a] = fmaf(r[k], l2[k * SL::kW2Cols + a], q[a]);
+  }
+  float best = 0.0f;
+  int action = 0;
+#pragma unroll
+  for (int a = 0; a < 9; ++a) {
+    q[a] = __fadd_rn(q[a], l2[HP * SL::kW2Cols + a]);
+    if (a == 0 || q[a] > best) { best = q[a]; action = a; }
+  }
+  if (t.active) {
+    if (p.q_out) {
+#pragma unroll
+      for (int a = 0; a < 9; ++a) p.q_out[t.gidx * 9 + a] = q[a];
+    }
+    if (p.act_out) p.act_out[t.gidx] = action;
+  }
+}
+
+template <int HP>
+static cudaError_t launch_stack_hp(const StackParams& p, cudaStream_t stream) {
+  const SwarmConfig& c = p.cfg;
+  const StackSmem S = stack_smem<HP>(p.spec.n_layers, c.n_agents, c.knn_k, p.maxdeg, c.graph_mode);
+  if (S.total > 227 * 1024) return cudaErrorInvalidConfiguration;
+  if (S.total > 48 * 1024) {
+    cudaError_t err = cudaFuncSetAttribute(gatstack_forward_kernel<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total);
+    if (err != cudaSuccess) return err;
+  }
+  const int grid = (c.num_envs + p.epb - 1) / p.epb;
+  gatstack_forward_kernel<HP><<<grid, kTileThreads, S.total, stream>>>(p);
+  return cudaGetLastError();
+}
+
+int stack_weight_count_host(const SwarmStackSpec& s) { return stack_weight_count(s); }
+
+cudaError_t launch_gatstack_forward(const SwarmConfig& c, const SwarmStackSpec& spec, const float* weights, const float* state,
+                                    float* q, int32_t* actions, cudaStream_t stream) {
+  StackParams p;
+  p.cfg = c;
+  p.spec = spec;
+  p.weights = weights;
+  p.state = reinterpret_cast<const float4*>(state);
+  p.q_out = q;
+  p.act_out = actions;
+  p.epb = kTileThreads / c.n_agents;
+  p.maxdeg = c.graph_mode == SWARM_GRAPH_KNN ? (c.n_agents + c.knn_k + 1) : c.n_agents;
+  p.qmax_r = c.graph_mode == SWARM_GRAPH_RADIUS ? sq_threshold(c.graph_radius) : 0.0f;
+  if (spec.hidden <= 8) return launch_stack_hp<8>(p, stream);
+  if (spec.hidden <= 16) return launch_stack_hp<16>(p, stream);
+  return launch_stack_hp<32>(p, stream);
+}
+
+// returns[b][i] += reward (per agent, or the env's collective reward); hits[b] += agents inside hit_distance this tick
+__global__ void __launch_bounds__(256) stack_accumulate_kernel(long long total, int N, const float* __restrict__ rewards,
+                                                               int per_env, const uint8_t* __restrict__ flags,
+                                                               float* __restrict__ returns, int32_t* __restrict__ hits) {
+  for (long long gI = (long long)blockIdx.x * blockDim.x + threadIdx.x; gI < total; gI += (long long)gridDim.x * blockDim.x) {
+    const long long b = gI / N;
+    if (returns) returns[gI] = __fadd_rn(returns[gI], per_env ? rewards[b] : rewards[gI]);
+    if (hits && flags && (flags[gI] & SWARM_FLAG_HIT)) atomicAdd(&hits[b], 1);        // integer: order-independent
+  }
+}
+
+cudaError_t launch_stack_accumulate(long long total, int N, const float* rewards, int per_env, const uint8_t* flags,
+                                    float* returns, int32_t* hits, cudaStream_t stream) {
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  stack_accumulate_kernel<<<(int)(blocks < 1 ? 1 : blocks), 256, 0, stream>>>(total, N, rewards, per_env, flags, returns, hits);
+  return cudaGetLastError();
+}
+
+}  // namespace swarm

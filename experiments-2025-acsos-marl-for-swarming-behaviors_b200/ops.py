@@ -538,6 +538,80 @@ def graph_build_radius_csr(cfg: SwarmConfig, state: torch.Tensor) -> Tuple[torch
     return row_ptr, src[:int(total[-1])]
 
 
+def stack_spec(n_layers: int, hidden: int, in_features: int = 7, activations=None) -> "_lib.SwarmStackSpec":
+    """Multi-layer GAT Q-network description; ``activations`` per conv layer ("tanh" / "relu"), default the reference's
+    commented forward (train:61-67): tanh after conv1, relu after the others."""
+    sp = _lib.SwarmStackSpec()
+    sp.n_layers, sp.hidden, sp.in_features = int(n_layers), int(hidden), int(in_features)
+    acts = activations or (["tanh"] + ["relu"] * (n_layers - 1))
+    if len(acts) != n_layers:
+        raise ValueError("one activation per conv layer")
+    for l, a in enumerate(acts):
+        sp.activation[l] = {"tanh": _lib.ACT_TANH, "relu": _lib.ACT_RELU}[a]
+    return sp
+
+
+def pack_stack_weights(state_dict, spec, device) -> torch.Tensor:
+    """state dict with the reference's key names (conv{l}.att_src / att_dst / bias / lin.weight, lin1.*, lin2.*; the
+    layout of data/models/experiment_Flocking-seed_*.pth) -> the packed float32 vector of SwarmStackSpec."""
+    parts = []
+    H = spec.hidden
+    for l in range(1, spec.n_layers + 1):
+        cin = spec.in_features if l == 1 else H
+        w = state_dict[f"conv{l}.lin.weight"]
+        if tuple(w.shape) != (H, cin):
+            raise ValueError(f"conv{l}.lin.weight has shape {tuple(w.shape)}, expected {(H, cin)}")
+        parts += [state_dict[f"conv{l}.att_src"].reshape(-1), state_dict[f"conv{l}.att_dst"].reshape(-1),
+                  state_dict[f"conv{l}.bias"].reshape(-1), w.reshape(-1)]
+    parts += [state_dict["lin1.weight"].reshape(-1), state_dict["lin1.bias"].reshape(-1),
+              state_dict["lin2.weight"].reshape(-1), state_dict["lin2.bias"].reshape(-1)]
+    packed = torch.cat([p.detach().to(torch.float32).cpu() for p in parts]).contiguous()
+    if packed.numel() != int(lib().swarm_stack_weight_count(C.byref(spec))):
+        raise ValueError("state dict does not match the stack spec")
+    return packed.to(device)
+
+
+def gatstack_forward(cfg: SwarmConfig, spec, weights: torch.Tensor, state: torch.Tensor, want_q: bool = True,
+                     want_actions: bool = False):
+    """A whole multi-layer GAT Q-network forward on the per-env graph in one launch: q f32[B,N,9], actions int32[B,N]."""
+    B, N = cfg.num_envs, cfg.n_agents
+    _expect(state, torch.float32, B * N * 4, "state")
+    _expect(weights, torch.float32, int(lib().swarm_stack_weight_count(C.byref(spec))), "weights")
+    dev = state.device
+    q = torch.empty(B, N, 9, dtype=torch.float32, device=dev) if want_q else None
+    act = torch.empty(B, N, dtype=torch.int32, device=dev) if want_actions else None
+    check(lib().swarm_gatstack_forward(C.byref(cfg), C.byref(spec), ptr(weights), ptr(state), ptr(q), ptr(act), stream_ptr(dev)))
+    if want_q and want_actions:
+        return q, act
+    return q if want_q else act
+
+
+def rollout_stack(cfg: SwarmConfig, spec, weights: torch.Tensor, state: torch.Tensor, ticks: int,
+                  reward: Optional["_lib.SwarmRewardSpec"] = None, shaping: Optional[torch.Tensor] = None,
+                  returns: Optional[torch.Tensor] = None, hits: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """Greedy rollout of a stacked network, in place on ``state``: per tick forward -> world step -> reward (the world's,
+    or the Flocking / Cohesion reward of ``reward``) -> running totals, all launched from the library."""
+    B, N = cfg.num_envs, cfg.n_agents
+    _expect(state, torch.float32, B * N * 4, "state")
+    _expect(weights, torch.float32, int(lib().swarm_stack_weight_count(C.byref(spec))), "weights")
+    dev = state.device
+    if returns is None:
+        returns = torch.zeros(B, N, dtype=torch.float32, device=dev)
+    if hits is None:
+        hits = torch.zeros(B, dtype=torch.int32, device=dev)
+    if shaping is not None:
+        _expect(shaping, torch.float32, B * N * 2, "shaping")
+    wb = int(lib().swarm_rollout_stack_workspace_bytes(C.byref(cfg)))
+    ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+    check(lib().swarm_rollout_stack(C.byref(cfg), C.byref(spec), ptr(weights), ptr(state), int(ticks),
+                                    C.addressof(reward) if reward is not None else None, ptr(shaping), ptr(returns), ptr(hits),
+                                    ptr(ws), wb, stream_ptr(dev)))
+    out = {"state": state, "returns": returns, "hits": hits}
+    if shaping is not None:
+        out["shaping"] = shaping
+    return out
+
+
 def gatconv_forward_csr(weights: torch.Tensor, x: torch.Tensor, row_ptr: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
     """The GATConv layer alone: x f32[n,7] + CSR-by-target -> f32[n,32] (aggregate + bias)."""
     n = x.shape[0]

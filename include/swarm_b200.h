@@ -466,6 +466,44 @@ void swarm_default_reward_spec(SwarmRewardSpec* spec, int32_t kind, int32_t num_
 int swarm_scenario_reward(const SwarmRewardSpec* spec, const float* state, float* shaping, float* reward, float* terms,
                           void* stream);
 
+/* ---- multi-layer GAT Q-networks -------------------------------------------------------------
+ * The reference's GCN class carries conv2 / conv3 in comments (train_gcn_dqn.py:54-55, 64-67) and ships checkpoints of
+ * that form: data/models/experiment_Flocking-seed_*.pth = conv1 (7 -> 8), conv2, conv3 (8 -> 8), lin1 (8 -> 8), lin2
+ * (8 -> 9).  A stack is n_layers single-head GATConv layers (add_self_loops = False, bias) of one width, each followed
+ * by an activation, then lin1 -> ReLU -> lin2 as in GCN.forward (train:59-70).
+ * weights: state-dict order, float32 -- per layer att_src[H], att_dst[H], bias[H], lin.weight[H][Cin] (Cin = in_features
+ * for conv1, H above), then lin1.weight[H][H], lin1.bias[H], lin2.weight[9][H], lin2.bias[9];
+ * swarm_stack_weight_count(spec) floats. */
+#define SWARM_ACT_TANH 0
+#define SWARM_ACT_RELU 1
+typedef struct SwarmStackSpec {
+  int32_t n_layers;        /* 1 .. 4                                                                                  */
+  int32_t hidden;          /* H: 1 .. 32                                                                              */
+  int32_t in_features;     /* 7: [pos, vel, goal, agent id] (train:95-99); 5: [pos, vel, agent id] for scenarios whose
+                              observation() is cat[pos, vel] (cohesion_scenario.py:87-94)                            */
+  int32_t activation[4];   /* SWARM_ACT_* after conv l (train:62,65,67: tanh, relu, relu)                             */
+  int32_t pad;
+} SwarmStackSpec;
+int64_t swarm_stack_weight_count(const SwarmStackSpec* spec);
+
+/* The whole forward of a stack on the per-env graph named by cfg->graph_mode (complete; radius; kNN for n_agents <= 16)
+ * in ONE launch: in-edge lists built once in shared memory, layer outputs never leave the chip.  n_agents <= 128.
+ * q float[B*N][9] and actions int32[B*N] (argmax, first maximum wins) are optional. */
+int swarm_gatstack_forward(const SwarmConfig* cfg, const SwarmStackSpec* spec, const float* weights, const float* state,
+                           float* q, int32_t* actions, void* stream);
+
+/* `ticks` greedy evaluation ticks (simulator.py:59-93) of a stacked network, launched back to back from the library:
+ * per tick swarm_gatstack_forward (argmax) -> swarm_sim_step in place -> the tick's reward -> returns float[B*N] (+=),
+ * hits int32[B] (+=, obstacles_hits()).  reward == NULL: the world's own reward (GoTo / ObstacleAvoidance); a
+ * SwarmRewardSpec selects the Flocking collective reward (shaping float[B][N][2] required, initialised by a reset call
+ * of swarm_scenario_reward) or Cohesion's per-agent reward on the GoTo world, evaluated by the swarm_scenario_reward
+ * kernel after every step.  No host work, allocation or tensor-library op between the launches (graph capturable).
+ * workspace: swarm_rollout_stack_workspace_bytes(cfg). */
+int64_t swarm_rollout_stack_workspace_bytes(const SwarmConfig* cfg);
+int swarm_rollout_stack(const SwarmConfig* cfg, const SwarmStackSpec* spec, const float* weights, float* state,
+                        int32_t ticks, const SwarmRewardSpec* reward, float* shaping, float* returns, int32_t* hits,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
