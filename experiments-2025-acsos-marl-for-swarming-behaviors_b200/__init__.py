@@ -9,12 +9,12 @@ from . import _build, _lib, ops                                   # noqa: F401
 from ._lib import SwarmConfig, SwarmError, pack_weights, unpack_weights   # noqa: F401
 from .dqn import DQNTrainer, GraphReplayBuffer, set_seed          # noqa: F401
 from .env import Environment, make_env                            # noqa: F401
-from .gcn import GCN, GATConv                                     # noqa: F401
+from .gcn import GCN, GATConv, StackedGCN                                     # noqa: F401
 from .graph import Batch, Data, create_graph_from_observations    # noqa: F401
 from .scenarios import (Agent, BaseScenario, CohesionScenario, Color, FlockingScenario,   # noqa: F401
                         GoToPositionScenario, Landmark, ObstacleAvoidanceScenario, Sphere, World)
 from .simulator import Simulator                                   # noqa: F401
 
-__all__ = ["make_env", "Environment", "GCN", "GATConv", "Data", "Batch", "create_graph_from_observations",
+__all__ = ["make_env", "Environment", "GCN", "GATConv", "StackedGCN", "Data", "Batch", "create_graph_from_observations",
            "BaseScenario", "GoToPositionScenario", "ObstacleAvoidanceScenario", "FlockingScenario", "CohesionScenario", "World", "Agent", "Landmark", "Sphere", "Color", "SwarmConfig", "SwarmError",
            "pack_weights", "unpack_weights", "ops", "DQNTrainer", "GraphReplayBuffer", "set_seed", "Simulator"]

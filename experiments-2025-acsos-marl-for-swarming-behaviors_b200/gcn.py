@@ -209,3 +209,47 @@ class GCN(nn.Module):
         if edge_index.dtype != torch.int64:
             edge_index = edge_index.to(torch.int64)
         return _GatQFunction.apply(self.packed_weights(), x.contiguous(), edge_index.contiguous())
+
+
+class StackedGCN(nn.Module):
+    """The multi-layer form of ``GCN`` the reference keeps in comments (train_gcn_dqn.py:54-55, 64-67) and ships as
+    data/models/experiment_Flocking-seed_*.pth: ``conv1 .. convL`` (single-head GATConv, one width), ``lin1``, ``lin2``;
+    tanh after conv1, relu after the others unless ``activations`` says otherwise.  ``forward(data)`` stacks the generic
+    layer kernels under torch autograd (any graph, trainable); greedy evaluation goes through ONE launch per forward
+    (``ops.gatstack_forward`` / ``ops.rollout_stack``; ``Simulator`` picks that path for instances of this class)."""
+
+    def __init__(self, input_dim: int = _FEAT, hidden_dim: int = 8, output_dim: int = _ACTIONS, n_layers: int = 3,
+                 activations=None):
+        super().__init__()
+        if output_dim != _ACTIONS or input_dim not in (5, 7) or not 1 <= hidden_dim <= 32 or not 1 <= n_layers <= 4:
+            raise NotImplementedError("StackedGCN: input_dim 7 or 5, 1 <= hidden_dim <= 32, 1 <= n_layers <= 4, 9 actions")
+        self.n_layers = n_layers
+        self.activations = list(activations) if activations else ["tanh"] + ["relu"] * (n_layers - 1)
+        for l in range(1, n_layers + 1):
+            setattr(self, f"conv{l}", GATConv(input_dim if l == 1 else hidden_dim, hidden_dim, add_self_loops=False, bias=True))
+        self.lin1 = nn.Linear(hidden_dim, hidden_dim)
+        self.lin2 = nn.Linear(hidden_dim, output_dim)
+
+    @classmethod
+    def from_state_dict(cls, sd, activations=None) -> "StackedGCN":
+        """Shapes from the checkpoint itself (``torch.load`` of an experiment_Flocking-seed_*.pth)."""
+        n_layers = sum(1 for k in sd if k.endswith(".lin.weight"))
+        hidden, input_dim = sd["conv1.lin.weight"].shape
+        model = cls(int(input_dim), int(hidden), int(sd["lin2.weight"].shape[0]), n_layers, activations)
+        model.load_state_dict(sd)
+        return model
+
+    def stack_spec(self):
+        from . import ops
+        return ops.stack_spec(self.n_layers, self.lin1.in_features, self.conv1.lin.weight.shape[1], self.activations)
+
+    def packed_stack_weights(self, device) -> torch.Tensor:
+        from . import ops
+        return ops.pack_stack_weights(self.state_dict(), self.stack_spec(), device)
+
+    def forward(self, data) -> torch.Tensor:
+        h, edge_index = data.x, data.edge_index
+        for l in range(1, self.n_layers + 1):
+            h = getattr(self, f"conv{l}")(h, edge_index)
+            h = torch.tanh(h) if self.activations[l - 1] == "tanh" else torch.relu(h)
+        return self.lin2(torch.relu(self.lin1(h)))

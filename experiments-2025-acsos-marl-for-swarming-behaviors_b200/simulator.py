@@ -20,6 +20,7 @@ from typing import Dict
 import torch
 
 from . import _lib, ops
+from .gcn import StackedGCN
 from .graph import Data, create_graph_from_observations as _create_graph
 from .scenarios import FlockingScenario
 
@@ -61,15 +62,20 @@ class Simulator:
         world = env.world
         gm = {"complete": _lib.GRAPH_COMPLETE, "knn": _lib.GRAPH_KNN}[self.graph_mode]
         cfg = ops.clone_config(world.cfg, graph_mode=gm, knn_k=self.k)
-        weights = _lib.pack_weights(self.model.state_dict(), world.device)
+        stacked = isinstance(self.model, StackedGCN)
+        weights = self.model.packed_stack_weights(world.device) if stacked else \
+            _lib.pack_weights(self.model.state_dict(), world.device)
         is_oa = world.cfg.scenario == _lib.SCENARIO_OBSTACLE_AVOIDANCE
         for episode in range(self.episodes):
             env.reset()
             init_time = time.time()
             flock = isinstance(env.scenario, FlockingScenario)      # its collective reward replaces GoTo's on the fused path
-            out = ops.rollout(cfg, weights, world.state, T, trace=dict(state=True, rewards=True, flags=True, dist=True),
-                              flocking=env.scenario._spec() if flock else None,
-                              shaping=env.scenario.shaping if flock else None)
+            if stacked:
+                out = self._rollout_stacked(cfg, weights, world, T, env.scenario if flock else None)
+            else:
+                out = ops.rollout(cfg, weights, world.state, T, trace=dict(state=True, rewards=True, flags=True, dist=True),
+                                  flocking=env.scenario._spec() if flock else None,
+                                  shaping=env.scenario.shaping if flock else None)
             env.steps += T
             world.adopt_rollout(out)         # scenario metrics / observation() / reward() now describe the final tick
             st = out["trace_state"][:, 0].cpu()                   # [T, n, 4]
@@ -102,6 +108,25 @@ class Simulator:
             self.distance_at_the_end.append(torch.mean(torch.stack([dgoal[T - 1, j:j + 1] for j in range(n)])))
             self.episode_rewards.append((total_reward / T).item())
         self.save_metrics_to_csv()
+
+    def _rollout_stacked(self, cfg, weights, world, T, flocking_scenario):
+        """The same per-tick traces for a multi-layer network: one forward launch (graph -> L GAT layers -> head ->
+        argmax) and one world step per tick, the Flocking reward from its kernel."""
+        spec = self.model.stack_spec()
+        B, N = cfg.num_envs, cfg.n_agents
+        tr = {k: [] for k in ("state", "rewards", "flags", "dist")}
+        for _ in range(T):
+            act = ops.gatstack_forward(cfg, spec, weights, world.state, want_q=False, want_actions=True)
+            o = ops.sim_step(cfg, world.state, act, state_out=world.state, want_obs=False)
+            rewards = o["rewards"]
+            if flocking_scenario is not None:
+                r = ops.scenario_reward(flocking_scenario._spec(), world.state, flocking_scenario.shaping)
+                rewards = r.view(B, 1).expand(B, N).contiguous()
+            tr["state"].append(world.state.clone())
+            tr["rewards"].append(rewards)
+            tr["flags"].append(o["flags"])
+            tr["dist"].append(o["dist"])
+        return {"state": world.state, **{"trace_" + k: torch.stack(v) for k, v in tr.items()}}
 
     def save_metrics_to_csv(self):
         """simulator.py:111-166."""

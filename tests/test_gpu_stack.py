@@ -203,3 +203,46 @@ def test_stack_argument_errors():
     oa = ops.make_config(L.SCENARIO_OBSTACLE_AVOIDANCE, 4, 9, L.GRAPH_COMPLETE)
     with pytest.raises(ValueError, match="GoTo world"):
         ops.rollout_stack(oa, spec, w, torch.zeros(4, 9, 4, device=dev), 1, reward=ops.reward_spec(L.REWARD_COHESION, 4, 9))
+
+
+def test_simulator_runs_the_shipped_flocking_checkpoint(tmp_path):
+    """Simulator (simulator.py:28-166) with a StackedGCN built from a shipped three-layer Flocking checkpoint on a
+    FlockingScenario env: the one-launch forward + world step per tick writes the reference's CSV tree, and the trajectory
+    equals the script-level loop (create_graph_from_observations -> model(data) through the generic layer kernels ->
+    argmax -> env.step) wherever that loop's top-2 Q gap is outside the tolerance band."""
+    import csv
+    import swarm_b200 as sb
+    n, T, k = 5, 12, 5
+    model = sb.StackedGCN.from_state_dict(_flocking_sd(1)).to(_dev()).eval()
+    assert model.n_layers == 3 and model.lin1.in_features == 8
+
+    def make():
+        return sb.make_env(scenario=sb.FlockingScenario(), num_envs=1, device=_dev(), continuous_actions=False,
+                           max_steps=T, dict_spaces=True, seed=3, n_agents=n)
+
+    env = make()
+    sim = sb.Simulator(env, model, 1, "flocking", 3, output_dir=str(tmp_path / "stats"), k=k)
+    torch.manual_seed(11)
+    sim.run_simulation()
+    with open(tmp_path / "stats" / "positions" / "positions_episode_0_x.csv") as f:
+        rows = list(csv.reader(f))
+    assert rows[0] == ["Tick"] + [f"X{a}" for a in range(n)] and len(rows) == T + 1
+    xs = torch.tensor([[float(v) for v in r[1:]] for r in rows[1:]])
+    # the script-level loop on a fresh env from the same generator state
+    env2 = make()
+    torch.manual_seed(11)
+    obs = env2.reset()
+    safe = True
+    for t in range(T):
+        data = sb.create_graph_from_observations(obs, n, mode="knn", k=k)
+        with torch.no_grad():
+            q = model(data)
+        top2 = torch.topk(q, 2, dim=1).values
+        if ((top2[:, 0] - top2[:, 1]) <= 4 * Q_RTOL * q.abs().amax(dim=1)).any():
+            safe = False                                  # a near-tie: the two float32 forwards may pick different actions
+        act = torch.argmax(q, dim=1)
+        obs, rew, done, info = env2.step({f"agent{i}": act[i:i + 1] for i in range(n)})
+        if safe:
+            got = torch.stack([obs[f"agent{i}"][0, 0] for i in range(n)]).cpu()
+            assert torch.equal(got, xs[t]), f"tick {t}"
+    assert safe or t > 0
