@@ -633,6 +633,9 @@ cudaError_t launch_gatq_knn_large(const SwarmConfig& c, const float* weights, co
 }
 
 // ---- launchers ------------------------------------------------------------------------------
+bool sim_step_grid_enabled(int n_agents);
+cudaError_t launch_sim_step_grid(const TileParams& tp, cudaStream_t stream);
+
 cudaError_t launch_sim_step_large(const TileParams& tp, cudaStream_t stream) {
   const SwarmConfig& c = tp.cfg;
   LargeStepParams p;
@@ -651,7 +654,12 @@ cudaError_t launch_sim_step_large(const TileParams& tp, cudaStream_t stream) {
   p.qmax_ao = tp.qmax_ao;
   p.returns = tp.returns;
   p.hits = tp.hits;
-  sim_step_large_kernel<<<c.num_envs, kLargeThreads, c.n_agents * sizeof(float2), stream>>>(p);
+  // contact partners from the uniform grid (grid_kernels.cu; same bits) unless SWARM_STEP_GRID=0 asks for the full sweep
+  if (sim_step_grid_enabled(c.n_agents) && c.n_agents <= 4096) {
+    if (cudaError_t e = launch_sim_step_grid(tp, stream); e != cudaSuccess) return e;
+  } else {
+    sim_step_large_kernel<<<c.num_envs, kLargeThreads, c.n_agents * sizeof(float2), stream>>>(p);
+  }
   if (c.scenario == SWARM_SCENARIO_GOTO && (tp.rewards_out || tp.returns))
     goto_reward_large_kernel<<<c.num_envs, kLargeThreads, c.n_agents * sizeof(float), stream>>>(
         c, reinterpret_cast<const float4*>(tp.state_out), tp.rewards_out, tp.returns);

@@ -191,3 +191,32 @@ def test_rollout_large_radius_and_complete(mode, N, B, radius):
     cg = ops.make_config(L.SCENARIO_GOTO, B, N, gm, graph_radius=radius if mode == "radius" else 0.35)
     r2 = ops.rollout_large(cg, w, rx["state"].clone(), 2, returns=rx["returns"].clone(), hits=rx["hits"].clone())
     assert (r2["returns"] < rx["returns"]).all() and torch.equal(r2["hits"], rx["hits"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scenario", ["obstacle_avoidance", "go_to"])
+@pytest.mark.parametrize("N,B,spread", [(1024, 6, 0.5), (300, 5, 0.45), (4096, 2, 0.55), (640, 3, 0.02), (129, 4, 0.6)])
+def test_grid_world_step_equals_full_sweep(scenario, N, B, spread, monkeypatch):
+    """World step of a large env with its contact partners from the uniform grid (visited in ascending agent order) ==
+    the full partner sweep (SWARM_STEP_GRID=0; pinned against the oracle in test_gpu_large.py), bit for bit: squeezed
+    swarms full of contacts, a collapsed swarm (more candidates than the merge handles: per-agent fallback), in place."""
+    import swarm_b200 as sb
+    ops, L = sb.ops, sb._lib
+    dev = _dev()
+    pos, vel = _swarm(B, N, seed=N + 3, spread=spread, jitter=0.01)
+    if scenario == "obstacle_avoidance":
+        pos[0] += torch.tensor([-0.1, 0.1]) - pos[0].mean(dim=0)        # park one swarm on the obstacle
+    state = torch.cat([pos, vel], 2).contiguous().to(dev)
+    actions = torch.randint(0, 9, (B, N), generator=torch.Generator().manual_seed(2)).to(torch.int32).to(dev)
+    cfg = ops.make_config(L.SCENARIO_GOTO if scenario == "go_to" else L.SCENARIO_OBSTACLE_AVOIDANCE, B, N)
+    d = torch.cdist(pos[-1], pos[-1]) + 10 * torch.eye(N)
+    assert (d <= 0.1).any(), "the fixture must contain agent-agent contacts"
+    monkeypatch.setenv("SWARM_STEP_GRID", "0")
+    ref = ops.sim_step(cfg, state, actions)
+    monkeypatch.setenv("SWARM_STEP_GRID", "1")                        # forced: the default starts at 512 agents
+    out = ops.sim_step(cfg, state, actions)
+    for key in ("state", "rewards", "flags", "dist", "obs"):
+        assert torch.equal(out[key], ref[key]), key
+    work = state.clone()
+    inplace = ops.sim_step(cfg, work, actions, state_out=work, want_obs=False)
+    assert torch.equal(inplace["state"], ref["state"]) and torch.equal(inplace["rewards"], ref["rewards"])
