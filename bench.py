@@ -416,6 +416,26 @@ def measure_extra(sb, ops, dev):
         torch.cuda.synchronize(dev)
         out[f"c4_oa_1024x1024_{name}"] = {"agent_steps_per_s": B4 * N4 * T4 / (a.elapsed_time(b) * 1e-3),
                                           "ms_per_tick": a.elapsed_time(b) / T4}
+    # the shipped three-layer Flocking checkpoints (conv1-3 of width 8) on the C2 shape with the Flocking reward:
+    # one forward launch + world step + reward kernel + totals per tick, launched from the library
+    fz = np.load(os.path.join(ROOT, "tests", "golden", "flocking_models.npz"))
+    sd = {k[2:]: torch.from_numpy(fz[k]) for k in fz.files if k.startswith("0/")}
+    spec = ops.stack_spec(3, 8, 7)
+    ws = ops.pack_stack_weights(sd, spec, dev)
+    cfg = ops.make_config(L.SCENARIO_GOTO, ENVS_PER_GPU, N_AGENTS, L.GRAPH_KNN, 5)
+    rs = ops.reward_spec(L.REWARD_FLOCKING, ENVS_PER_GPU, N_AGENTS)
+    st = ops.reset_grid(cfg, draw_centers(7, ENVS_PER_GPU).to(dev))
+    shaping = torch.zeros(ENVS_PER_GPU, N_AGENTS, 2, device=dev)
+    ops.scenario_reward(rs, st, shaping, reset=True)
+    ops.rollout_stack(cfg, spec, ws, st, 5, reward=rs, shaping=shaping)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    ops.rollout_stack(cfg, spec, ws, st, TICKS, reward=rs, shaping=shaping)
+    b.record()
+    torch.cuda.synchronize(dev)
+    out["flocking_3layer_checkpoint_c2_shape_knn_k5"] = {
+        "agent_steps_per_s": ENVS_PER_GPU * N_AGENTS * TICKS / (a.elapsed_time(b) * 1e-3),
+        "us_per_tick": a.elapsed_time(b) * 1e3 / TICKS}
     return out
 
 
