@@ -203,9 +203,14 @@ def run_ours(args):
     state = torch.empty(B, N, 4, device=dev)
     returns = torch.zeros(B, N, device=dev)
     hits = torch.zeros(B, dtype=torch.int32, device=dev)
-    returns_host = torch.empty(B, N).pin_memory()
-    hits_host = torch.empty(B, dtype=torch.int32).pin_memory()
-    state_host = torch.empty(B, N, 4).pin_memory()
+    # end-to-end leg: the three results of a rollout (final states, returns, hits) live in ONE device allocation and come
+    # back with ONE device->host copy into pinned memory
+    pack = torch.empty(B * N * 4 + B * N + B, device=dev)
+    pack_host = torch.empty(B * N * 4 + B * N + B).pin_memory()
+    e_state = pack[:B * N * 4].view(B, N, 4)
+    e_returns = pack[B * N * 4:B * N * 5].view(B, N)
+    e_hits = pack[B * N * 5:].view(torch.int32)
+    returns_host = pack_host[B * N * 4:B * N * 5].view(B, N)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
 
@@ -215,13 +220,10 @@ def run_ours(args):
 
     def step_e2e():
         c = centers_host.to(dev, non_blocking=True)
-        returns.zero_()
-        hits.zero_()
-        ops.reset_grid(cfg, c, out=state)
-        ops.rollout(cfg, weights, state, T, returns=returns, hits=hits)
-        returns_host.copy_(returns, non_blocking=True)
-        hits_host.copy_(hits, non_blocking=True)
-        state_host.copy_(state, non_blocking=True)            # what a caller of rollout() gets back: final states too
+        pack[B * N * 4:].zero_()                               # returns and hits
+        ops.reset_grid(cfg, c, out=e_state)
+        ops.rollout(cfg, weights, e_state, T, returns=e_returns, hits=e_hits)
+        pack_host.copy_(pack, non_blocking=True)               # what a caller of rollout() gets back: final states too
         stream.synchronize()
         return float(returns_host[0, 0])
 
