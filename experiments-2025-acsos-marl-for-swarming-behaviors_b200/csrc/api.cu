@@ -34,6 +34,9 @@ cudaError_t launch_episode_end(const SwarmConfig& c, SwarmTrainCtl* ctl, float* 
 int stack_weight_count_host(const SwarmStackSpec& s);
 cudaError_t launch_gatstack_forward(const SwarmConfig& c, const SwarmStackSpec& spec, const float* weights, const float* state,
                                     float* q, int32_t* actions, cudaStream_t stream);
+cudaError_t launch_gatstack_rollout(const SwarmConfig& c, const SwarmStackSpec& spec, const float* weights, float* state,
+                                    int ticks, const TileParams& step, const SwarmRewardSpec* flock, float* shaping,
+                                    float* returns, int32_t* hits, cudaStream_t stream);
 cudaError_t launch_stack_accumulate(long long total, int N, const float* rewards, int per_env, const uint8_t* flags,
                                     float* returns, int32_t* hits, cudaStream_t stream);
 bool gatq_knn_large_fits(int N, int K);
@@ -822,6 +825,13 @@ int swarm_rollout_stack(const SwarmConfig* cfg, const SwarmStackSpec* spec, cons
   p.rewards_out = rewards;
   p.flags_out = flags;
   cudaStream_t st = (cudaStream_t)stream;
+  // world reward / Flocking: the whole loop is ONE launch with the state in registers (stack_kernels.cu
+  // gatstack_kernel<HP, true>); Cohesion's reward (and SWARM_STACK_FUSED=0) takes the launch sequence below
+  const char* fused_env = std::getenv("SWARM_STACK_FUSED");
+  if (!(fused_env && fused_env[0] == '0') && (!reward || rs.kind == SWARM_REWARD_FLOCKING))
+    return check_cuda(launch_gatstack_rollout(*cfg, *spec, weights, state, ticks, p, reward ? &rs : nullptr, shaping, returns,
+                                              hits, st),
+                      "swarm_rollout_stack");
   for (int t = 0; t < ticks; ++t) {
     if (cudaError_t e = launch_gatstack_forward(*cfg, *spec, weights, state, nullptr, actions, st); e != cudaSuccess)
       return check_cuda(e, "swarm_rollout_stack (forward)");

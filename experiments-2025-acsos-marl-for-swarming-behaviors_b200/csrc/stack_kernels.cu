@@ -11,6 +11,8 @@
 // cat[pos, vel] (cohesion_scenario.py:87-94).  Per layer the arithmetic follows torch_geometric's GATConv like the
 // one-layer kernels: h = x W^T, alpha = <h, att>, LeakyReLU(0.2) logits, max-subtracted softmax with the 1e-16
 // denominator, messages alpha * h_src summed in edge-list order, + bias.
+#include <cstring>
+
 #include "tile_device.cuh"
 
 namespace swarm {
@@ -24,6 +26,15 @@ struct StackParams {
   int32_t* act_out;          // [B*N] or nullptr
   int32_t epb, maxdeg;
   float qmax_r;
+  // fused rollout (gatstack_rollout_kernel): `ticks` x [forward -> argmax -> world step -> reward], state in registers
+  TileParams step;           // physics constants of the world step (cfg, contact thresholds, drag)
+  float4* state_rw;          // [B*N] advanced in place
+  float* returns;            // [B*N] += (optional)
+  int32_t* hits;             // [B] += (optional)
+  SwarmRewardSpec flock;     // use_flock: the Flocking collective reward instead of the world's
+  float2* shaping;           // [B*N] Flocking memory, read at launch, written back
+  int32_t use_flock;
+  int32_t ticks;
 };
 
 constexpr int kStackMaxLayers = 4;
@@ -89,14 +100,15 @@ __device__ __forceinline__ void stack_stage_weights(const SwarmStackSpec& s, con
 }
 
 struct StackSmem {
-  int w, st, h, asrc, inl, kv, total;
+  int w, st, red, h, asrc, inl, kv, total;
 };
 template <int HP>
 __host__ __device__ inline StackSmem stack_smem(int L, int n, int k, int maxdeg, int graph_mode) {
   StackSmem s;
   int off = 0;
   s.w = off;    off = tile_align16(off + StackLayout<HP>::total(L) * 4);
-  s.st = off;   off = tile_align16(off + kTileThreads * 16);
+  s.st = off;   off = tile_align16(off + 2 * kTileThreads * 16);
+  s.red = off;  off = tile_align16(off + kTileThreads * 4);
   s.h = off;    off = tile_align16(off + kTileThreads * (HP + 4) * 4);
   s.asrc = off; off = tile_align16(off + kTileThreads * 4);
   s.inl = off;  off = tile_align16(off + maxdeg * kTileThreads);
@@ -105,8 +117,12 @@ __host__ __device__ inline StackSmem stack_smem(int L, int n, int k, int maxdeg,
   return s;
 }
 
-template <int HP>
-__global__ void __launch_bounds__(kTileThreads) gatstack_forward_kernel(const __grid_constant__ StackParams p) {
+// ROLLOUT = false: one forward (swarm_gatstack_forward).  ROLLOUT = true: the evaluation loop simulator.py:59-93 for a
+// stacked network -- p.ticks x [forward -> argmax -> world step -> reward] with the agent's state, running return and
+// Flocking memory in registers, exactly the tick of tile_kernels.cu's rollout (same world-step and reward device code,
+// so it equals forward + swarm_sim_step + swarm_scenario_reward composed by hand bit for bit).
+template <int HP, bool ROLLOUT>
+__global__ void __launch_bounds__(kTileThreads) gatstack_kernel(const __grid_constant__ StackParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   using SL = StackLayout<HP>;
   constexpr int kRow = HP + 4;
@@ -124,21 +140,32 @@ __global__ void __launch_bounds__(kTileThreads) gatstack_forward_kernel(const __
   g.sin = smem + S.inl;
   g.skv = reinterpret_cast<float*>(smem + S.kv);
 
+  float* sred = reinterpret_cast<float*>(smem + S.red);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (t.active) s = p.state[t.gidx];
+  float ret0 = 0.0f, ret = 0.0f;
+  float2 shp = make_float2(0.0f, 0.0f);
+  int myhits = 0;
+  if (t.active) {
+    s = ROLLOUT ? p.state_rw[t.gidx] : p.state[t.gidx];
+    if (ROLLOUT && p.returns) ret0 = p.returns[t.gidx];
+    if (ROLLOUT && p.use_flock) shp = p.shaping[t.gidx];
+  }
   stack_stage_weights<HP>(sp, p.weights, sw, tid, T);
-  sst[tid] = s;
+  uint64_t cache_rank = ~0ull, cache_nbr = 0;
+  int deg = 0;
+  const int n_ticks = ROLLOUT ? p.ticks : 1;
+  for (int tick = 0; tick < n_ticks; ++tick) {
+  const float4* pos = sst + (tick & 1) * T;
+  sst[(tick & 1) * T + tid] = s;
   __syncthreads();
 
   // ---- graph: in-edge list of this node in edge-list order, once for all layers ------------------------------------
-  int deg = 0;
   if (c.graph_mode == SWARM_GRAPH_KNN) {
-    uint64_t cache_rank = ~0ull, cache_nbr = 0;
-    const uint64_t nbr = tile_knn_small(t, sst, s, N, K, cache_rank, cache_nbr);
+    const uint64_t nbr = tile_knn_small(t, pos, s, N, K, cache_rank, cache_nbr);
     deg = tile_in_edges_knn_small(g, t, N, K, nbr, reinterpret_cast<uint32_t*>(g.skv));
   } else if (c.graph_mode == SWARM_GRAPH_RADIUS) {
-    if (t.active) deg = tile_in_edges_radius(g, t, sst, s, N, p.qmax_r);
-  } else if (t.active) {
+    if (t.active) deg = tile_in_edges_radius(g, t, pos, s, N, p.qmax_r);
+  } else if (t.active && tick == 0) {
     deg = tile_in_edges_complete(g, t, N);
   }
 
@@ -246,12 +273,85 @@ __global__ void __launch_bounds__(kTileThreads) gatstack_forward_kernel(const __
     q[a] = __fadd_rn(q[a], l2[HP * SL::kW2Cols + a]);
     if (a == 0 || q[a] > best) { best = q[a]; action = a; }
   }
-  if (t.active) {
-    if (p.q_out) {
+  if (!ROLLOUT) {
+    if (t.active) {
+      if (p.q_out) {
 #pragma unroll
-      for (int a = 0; a < 9; ++a) p.q_out[t.gidx * 9 + a] = q[a];
+        for (int a = 0; a < 9; ++a) p.q_out[t.gidx * 9 + a] = q[a];
+      }
+      if (p.act_out) p.act_out[t.gidx] = action;
     }
-    if (p.act_out) p.act_out[t.gidx] = action;
+  } else {
+    // ---- world step + reward: the tick of tile_kernels.cu ------------------------------------------------------------
+    float reward = 0.0f;
+    if (t.active) {
+      uint8_t flags = 0;
+      uint32_t cmask = 0;
+      tile_world_step(p.step, t, pos, action, s, flags, cmask);
+      const float dgoal = goal_distance(s.x, s.y, c);
+      if (c.scenario == SWARM_SCENARIO_OBSTACLE_AVOIDANCE) {
+        const float dobs = obstacle_distance(s.x, s.y, c);
+        reward = oa_reward(dgoal, dobs, c, flags);
+        myhits += (flags & SWARM_FLAG_HIT) ? 1 : 0;
+      } else if (!p.use_flock) {
+        sred[tid] = dgoal;     // GoTo's collective reward needs every agent's distance: finished below
+      }
+    }
+    if (p.use_flock) {
+      // Flocking (flocking:124-171): every agent's term from the POST-step positions of its env, then the collective sum
+      // in agent order (the op sequence of reward_kernels.cu / the FLOCK tile kernel)
+      const SwarmRewardSpec& fs = p.flock;
+      float4* post = sst + ((tick + 1) & 1) * T;
+      post[tid] = s;
+      __syncthreads();
+      float term = 0.0f;
+      if (t.active) {
+        const float d_goal = norm2(__fsub_rn(s.x, fs.goal_x), __fsub_rn(s.y, fs.goal_y));
+        const float shaped_goal = __fmul_rn(d_goal, fs.pos_shaping);
+        const float4* others = post + t.envbase;
+        float sum;
+        int close;
+        flocking_partner_sweep(s.x, s.y, t.i, N, [&](int j) { return xy_of(others[j]); }, fs.desired_distance,
+                               fs.agent_radius, fs.min_collision_distance, sum, close);
+        const float spacing = __fmul_rn(__fdiv_rn(sum, (float)(N - 1)), fs.dist_shaping);
+        const float pos_rew = __fsub_rn(shp.x, shaped_goal);
+        float r = pos_rew;
+        if (d_goal < fs.goal_radius) r = __fadd_rn(r, fs.on_goal_bonus);
+        const float avoid = close ? __fmul_rn((float)close, fs.collision_reward) : 0.0f;
+        const float dist_rew = __fsub_rn(shp.y, spacing);
+        shp = make_float2(shaped_goal, spacing);
+        term = __fadd_rn(__fadd_rn(r, avoid), dist_rew);
+      }
+      sred[tid] = term;
+      __syncthreads();
+      if (t.active)
+        for (int a = 0; a < N; ++a) reward = __fadd_rn(reward, sred[t.envbase + a]);
+    } else if (c.scenario == SWARM_SCENARIO_GOTO) {
+      // collective reward (go_to:108-115): 0 + (-d_0) + (-d_1) + ... in agent order, same for all agents
+      __syncthreads();
+      if (t.active)
+        for (int a = 0; a < N; ++a) reward = __fadd_rn(reward, -sred[t.envbase + a]);
+    }
+    ret = __fadd_rn(ret, reward);
+  }
+  }   // tick loop
+
+  if (ROLLOUT) {
+    if (t.active) {
+      p.state_rw[t.gidx] = s;
+      if (p.returns) p.returns[t.gidx] = __fadd_rn(ret0, ret);
+      if (p.use_flock) p.shaping[t.gidx] = shp;
+    }
+    if (p.hits) {
+      __syncthreads();
+      reinterpret_cast<int*>(sred)[tid] = myhits;
+      __syncthreads();
+      if (t.active && t.i == 0) {
+        int tot = 0;
+        for (int a = 0; a < N; ++a) tot += reinterpret_cast<int*>(sred)[t.envbase + a];
+        p.hits[t.env] += tot;
+      }
+    }
   }
 }
 
@@ -261,19 +361,59 @@ static cudaError_t launch_stack_hp(const StackParams& p, cudaStream_t stream) {
   const StackSmem S = stack_smem<HP>(p.spec.n_layers, c.n_agents, c.knn_k, p.maxdeg, c.graph_mode);
   if (S.total > 227 * 1024) return cudaErrorInvalidConfiguration;
   if (S.total > 48 * 1024) {
-    cudaError_t err = cudaFuncSetAttribute(gatstack_forward_kernel<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total);
+    cudaError_t err = p.ticks > 0
+        ? cudaFuncSetAttribute(gatstack_kernel<HP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total)
+        : cudaFuncSetAttribute(gatstack_kernel<HP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total);
     if (err != cudaSuccess) return err;
   }
   const int grid = (c.num_envs + p.epb - 1) / p.epb;
-  gatstack_forward_kernel<HP><<<grid, kTileThreads, S.total, stream>>>(p);
+  if (p.ticks > 0) gatstack_kernel<HP, true><<<grid, kTileThreads, S.total, stream>>>(p);
+  else gatstack_kernel<HP, false><<<grid, kTileThreads, S.total, stream>>>(p);
   return cudaGetLastError();
 }
 
 int stack_weight_count_host(const SwarmStackSpec& s) { return stack_weight_count(s); }
 
+static cudaError_t launch_stack(const StackParams& p, cudaStream_t stream) {
+  if (p.spec.hidden <= 8) return launch_stack_hp<8>(p, stream);
+  if (p.spec.hidden <= 16) return launch_stack_hp<16>(p, stream);
+  return launch_stack_hp<32>(p, stream);
+}
+
+static void stack_fill(StackParams& p, const SwarmConfig& c, const SwarmStackSpec& spec, const float* weights) {
+  std::memset(&p, 0, sizeof(p));
+  p.cfg = c;
+  p.spec = spec;
+  p.weights = weights;
+  p.epb = kTileThreads / c.n_agents;
+  p.maxdeg = c.graph_mode == SWARM_GRAPH_KNN ? (c.n_agents + c.knn_k + 1) : c.n_agents;
+  p.qmax_r = c.graph_mode == SWARM_GRAPH_RADIUS ? sq_threshold(c.graph_radius) : 0.0f;
+}
+
+// the fused evaluation loop; `step` carries the physics constants (api.cu fill_params), flock == nullptr: world reward
+cudaError_t launch_gatstack_rollout(const SwarmConfig& c, const SwarmStackSpec& spec, const float* weights, float* state,
+                                    int ticks, const TileParams& step, const SwarmRewardSpec* flock, float* shaping,
+                                    float* returns, int32_t* hits, cudaStream_t stream) {
+  if (ticks <= 0) return cudaSuccess;
+  StackParams p;
+  stack_fill(p, c, spec, weights);
+  p.step = step;
+  p.state_rw = reinterpret_cast<float4*>(state);
+  p.returns = returns;
+  p.hits = hits;
+  p.ticks = ticks;
+  if (flock) {
+    p.flock = *flock;
+    p.shaping = reinterpret_cast<float2*>(shaping);
+    p.use_flock = 1;
+  }
+  return launch_stack(p, stream);
+}
+
 cudaError_t launch_gatstack_forward(const SwarmConfig& c, const SwarmStackSpec& spec, const float* weights, const float* state,
                                     float* q, int32_t* actions, cudaStream_t stream) {
   StackParams p;
+  std::memset(&p, 0, sizeof(p));
   p.cfg = c;
   p.spec = spec;
   p.weights = weights;

@@ -51,6 +51,28 @@ __device__ __forceinline__ TileThread tile_thread(int n_agents, int epb, long lo
   return t;
 }
 
+// One world step for the agent of this thread: action decode, contact forces (obstacle first, then
+// agents in entity order), integration.  `pos` = pre-step states of the tile.
+__device__ __forceinline__ void tile_world_step(const TileParams& p, const TileThread& t, const float4* pos, int action,
+                                                float4& s, uint8_t& flags, uint32_t& cmask) {
+  const SwarmConfig& c = p.cfg;
+  float fx, fy, gx, gy;
+  decode_action(action, fx, fy);          // F = 0 + u
+  if (c.scenario == SWARM_SCENARIO_OBSTACLE_AVOIDANCE) {
+    const float dx = __fsub_rn(s.x, c.obstacle_x), dy = __fsub_rn(s.y, c.obstacle_y);
+    if (__fmaf_rn(dy, dy, __fmul_rn(dx, dx)) <= p.qmax_ao) {
+      if (contact_force(s.x, s.y, c.obstacle_x, c.obstacle_y, p.dmin_ao, c.collision_force, c.contact_margin, gx, gy)) {
+        fx = __fadd_rn(fx, gx);
+        fy = __fadd_rn(fy, gy);
+        flags |= SWARM_FLAG_OBSTACLE_CONTACT;
+      }
+    }
+  }
+  agent_contacts(pos + t.envbase, c.n_agents, t.i, s.x, s.y, p.qmax_aa, p.dmin_aa, c.collision_force, c.contact_margin,
+                 fx, fy, cmask);
+  integrate(s, fx, fy, c.dt, p.one_minus_drag);
+}
+
 // Shared-memory views used by the graph + GAT forward
 struct TileGraphSmem {
   float* sh;        // [T][kHPad] projected features

@@ -134,8 +134,9 @@ def test_five_feature_input_matches_oracle(hidden, layers):
     _check_q(q, q_ref)
 
 
+@pytest.mark.parametrize("graph", ["knn", "complete", "radius"])
 @pytest.mark.parametrize("reward", ["world_oa", "world_goto", "flocking", "cohesion"])
-def test_rollout_stack_equals_composed_calls(reward):
+def test_rollout_stack_equals_composed_calls(reward, graph, monkeypatch):
     """swarm_rollout_stack (forward -> step -> reward -> totals, launched from the library) == the same calls composed by
     hand, bit for bit; Flocking carries its shaping memory, Cohesion uses the 5-feature input."""
     import swarm_b200 as sb
@@ -143,7 +144,8 @@ def test_rollout_stack_equals_composed_calls(reward):
     dev = _dev()
     B, N, T = 300, 9, 12
     scen = L.SCENARIO_OBSTACLE_AVOIDANCE if reward == "world_oa" else L.SCENARIO_GOTO
-    cfg = ops.make_config(scen, B, N, L.GRAPH_KNN, 5)
+    gm = {"knn": L.GRAPH_KNN, "complete": L.GRAPH_COMPLETE, "radius": L.GRAPH_RADIUS}[graph]
+    cfg = ops.make_config(scen, B, N, gm, 5, graph_radius=0.25)
     sd = _flocking_sd(0)
     in_features = 5 if reward == "cohesion" else 7
     if in_features == 5:
@@ -176,10 +178,17 @@ def test_rollout_stack_equals_composed_calls(reward):
         else:
             ret += out["rewards"]
         hits += ((out["flags"] & L.FLAG_HIT) != 0).sum(dim=1, dtype=torch.int32)
-    res = ops.rollout_stack(cfg, spec, w, state0.clone(), T, reward=rs, shaping=shaping0.clone() if shaping0 is not None else None)
-    assert torch.equal(res["state"], st) and torch.equal(res["returns"], ret) and torch.equal(res["hits"], hits)
-    if reward == "flocking":
-        assert torch.equal(res["shaping"], sh)
+    # default: ONE launch for the whole loop (world reward / Flocking); SWARM_STACK_FUSED=0: the launch sequence
+    for fused in ("1", "0"):
+        monkeypatch.setenv("SWARM_STACK_FUSED", fused)
+        res = ops.rollout_stack(cfg, spec, w, state0.clone(), T, reward=rs,
+                                shaping=shaping0.clone() if shaping0 is not None else None)
+        assert torch.equal(res["state"], st), f"fused={fused}: state"
+        assert torch.equal(res["returns"], ret), f"fused={fused}: returns"
+        assert torch.equal(res["hits"], hits), f"fused={fused}: hits"
+        if reward == "flocking":
+            assert torch.equal(res["shaping"], sh), f"fused={fused}: shaping"
+    monkeypatch.delenv("SWARM_STACK_FUSED")
     assert (st != state0).any() and torch.isfinite(ret).all()
     # running totals continue
     res2 = ops.rollout_stack(cfg, spec, w, res["state"].clone(), 3, reward=rs, shaping=res.get("shaping"),
