@@ -341,8 +341,13 @@ def run_ours(args):
     if strong is not None:
         line["strong_scaling_point"] = strong
     if world == 1:
-        line["memory_bound_kernels"] = measure_streaming_kernels(sb, ops, dev, peak_gbs)
-        line["extra"] = measure_extra(sb, ops, dev)
+        # side measurements must never cost the headline line: a failure is reported in place of the numbers
+        for key, fn in (("memory_bound_kernels", lambda: measure_streaming_kernels(sb, ops, dev, peak_gbs)),
+                        ("extra", lambda: measure_extra(sb, ops, dev))):
+            try:
+                line[key] = fn()
+            except Exception as exc:                                   # noqa: BLE001
+                line[key] = {"error": f"{type(exc).__name__}: {exc}"}
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_single()
     emit(line)
