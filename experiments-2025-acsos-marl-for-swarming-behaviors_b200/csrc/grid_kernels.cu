@@ -411,7 +411,7 @@ __host__ __device__ inline size_t large_x_smem_bytes(int N, bool radius) {
 }
 
 template <bool RADIUS>
-__global__ void __launch_bounds__(kGridThreads) gatq_large_x_kernel(const __grid_constant__ LargeXParams p) {
+__global__ void __launch_bounds__(kGridThreads, 2) gatq_large_x_kernel(const __grid_constant__ LargeXParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SwarmConfig& c = p.cfg;
   const int N = c.n_agents, P = grid_pow2(N);
