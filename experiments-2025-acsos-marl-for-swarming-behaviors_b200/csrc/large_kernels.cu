@@ -448,7 +448,7 @@ __host__ __device__ inline size_t large_qx_smem_bytes(int N, int K) {
   return b + 64;
 }
 
-__global__ void __launch_bounds__(kQLThreads) gatq_knn_large_x_kernel(const __grid_constant__ LargeQParams p) {
+__global__ void __launch_bounds__(kQLThreads, 2) gatq_knn_large_x_kernel(const __grid_constant__ LargeQParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SwarmConfig& c = p.cfg;
   const int N = c.n_agents, K = c.knn_k;
