@@ -265,3 +265,56 @@ def test_flocking_option_of_the_fused_tick_is_validated(sb):
     assert lib.swarm_rollout(C.byref(knn), 8, 8, 1, C.byref(opts2), None, None, None, None) == -1
     assert b"power of two" in lib.swarm_last_error()
     assert L.SwarmTrainHyper.flocking.offset + 16 == C.sizeof(L.SwarmTrainHyper)
+
+
+def test_stack_spec_layout_weight_count_and_validation(sb, tmp_path):
+    """SwarmStackSpec (multi-layer GAT Q-networks): byte layout against the header, the packed weight count against the
+    checkpoints the reference ships for Flocking (conv1 7 -> 8, conv2 / conv3 8 -> 8, lin1 8 -> 8, lin2 8 -> 9), and the
+    argument errors of the stack / large-swarm entry points, all without a device."""
+    import numpy as np
+    import torch
+    L, lib = sb._lib, sb._lib.lib()
+    src = tmp_path / "s.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "swarm_b200.h"\nint main(){printf("%zu %zu %zu\\n", '
+                   'sizeof(SwarmStackSpec), offsetof(SwarmStackSpec, activation), offsetof(SwarmStackSpec, in_features));return 0;}')
+    exe = tmp_path / "s"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [C.sizeof(L.SwarmStackSpec), L.SwarmStackSpec.activation.offset, L.SwarmStackSpec.in_features.offset]
+    z = np.load(os.path.join(ROOT, "tests", "golden", "flocking_models.npz"))
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("0/")}
+    spec = sb.ops.stack_spec(3, 8, 7)
+    assert int(lib.swarm_stack_weight_count(C.byref(spec))) == sum(v.numel() for v in sd.values()) == 409
+    assert list(spec.activation)[:3] == [L.ACT_TANH, L.ACT_RELU, L.ACT_RELU]
+    packed = sb.ops.pack_stack_weights(sd, spec, "cpu")
+    assert packed.numel() == 409 and torch.equal(packed[:8], sd["conv1.att_src"].reshape(-1))
+    assert torch.equal(packed[-9:], sd["lin2.bias"])
+    model = sb.StackedGCN.from_state_dict(sd)
+    assert model.n_layers == 3 and model.stack_spec().hidden == 8 and model.stack_spec().in_features == 7
+    with pytest.raises(ValueError, match="expected"):
+        sb.ops.pack_stack_weights(sd, sb.ops.stack_spec(3, 8, 5), "cpu")
+    bad = sb.ops.stack_spec(3, 8, 7)
+    bad.n_layers = 5
+    assert int(lib.swarm_stack_weight_count(C.byref(bad))) == 0
+    cfg = sb.ops.make_config(L.SCENARIO_GOTO, 4, 12, L.GRAPH_COMPLETE)
+    assert lib.swarm_gatstack_forward(C.byref(cfg), C.byref(bad), 8, 8, 8, None, None) == -1
+    assert b"n_layers" in lib.swarm_last_error()
+    assert lib.swarm_gatstack_forward(C.byref(cfg), C.byref(spec), 8, 8, None, None, None) == -1
+    assert b"no output" in lib.swarm_last_error()
+    knn20 = sb.ops.make_config(L.SCENARIO_GOTO, 4, 20, L.GRAPH_KNN, 5)
+    assert lib.swarm_gatstack_forward(C.byref(knn20), C.byref(spec), 8, 8, 8, None, None) == -2
+    assert lib.swarm_rollout_stack(C.byref(cfg), C.byref(spec), 8, 8, 1, None, None, None, None, 8, 0, None) == -1
+    assert b"workspace too small" in lib.swarm_last_error()
+    # large-swarm entry points
+    rad = sb.ops.make_config(L.SCENARIO_GOTO, 2, 1024, L.GRAPH_RADIUS, graph_radius=0.35)
+    assert lib.swarm_graph_build_radius_csr(C.byref(rad), 8, None, None, None, None) == -1
+    assert b"count pass" in lib.swarm_last_error()
+    assert lib.swarm_graph_build_radius_csr(C.byref(rad), 8, 8, 8, 8, None) == -1
+    assert lib.swarm_graph_build_radius_csr(C.byref(cfg), 8, 8, None, None, None) == -1 and b"SWARM_GRAPH_RADIUS" in lib.swarm_last_error()
+    knn = sb.ops.make_config(L.SCENARIO_GOTO, 2, 1024, L.GRAPH_KNN, 10)
+    assert lib.swarm_gatq_forward_large(C.byref(knn), 8, 8, 8, None, None) == -1 and b"knn_large" in lib.swarm_last_error()
+    assert lib.swarm_gatq_forward_large(C.byref(rad), 8, 8, None, None, None) == -1 and b"no output" in lib.swarm_last_error()
+    assert int(lib.swarm_rollout_large_workspace_bytes(C.byref(rad))) == 2 * 1024 * 4 + 512
+    assert int(lib.swarm_rollout_large_workspace_bytes(C.byref(knn))) == 2 * 1024 * 10 * 4 + 2 * 1024 * 4 + 512
+    big = sb.ops.make_config(L.SCENARIO_GOTO, 1, 5000, L.GRAPH_RADIUS, graph_radius=0.35)
+    assert lib.swarm_gatq_forward_large(C.byref(big), 8, 8, 8, None, None) == -2
