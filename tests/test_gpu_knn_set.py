@@ -69,3 +69,35 @@ def test_set_path_trace_edges_still_ordered():
     assert torch.equal(out["trace_edges"][0], edges0)
     plain = ops.rollout(cfg, w, state0.clone(), 2)
     assert torch.equal(plain["state"], out["state"])
+
+
+@pytest.mark.parametrize("N", [2, 3, 5, 6, 9, 12, 13, 16])
+def test_set_path_fuzz_on_tie_heavy_states(N, monkeypatch):
+    """Positions snapped to a coarse lattice (many exactly equal distances, co-located agents -- zero distances that tie
+    with the row's own entry), every k from 1 to N: rollouts with the order-free rows equal the ordered rows bit for
+    bit, with no table, a tiny (evicting) table and a table shared across different start states."""
+    import swarm_b200 as sb
+    ops, L = sb.ops, sb._lib
+    dev = _dev()
+    w = sb.pack_weights(load_params("GoTo", 1), dev)
+    B, T = 400, 6
+    g = torch.Generator().manual_seed(N)
+    pos = (torch.randn(B, N, 2, generator=g) * 0.25 / 0.05).round() * 0.05 + torch.tensor([0.9, -0.9])
+    vel = (torch.randn(B, N, 2, generator=g) * 0.2 / 0.1).round() * 0.1
+    state0 = torch.cat([pos, vel], 2).contiguous().to(dev)
+    for K in sorted({1, 2, N // 2, N - 1, N} - {0}):
+        cfg = ops.make_config(L.SCENARIO_GOTO, B, N, L.GRAPH_KNN, K)
+        monkeypatch.setenv("SWARM_KNN_ORDERED", "1")
+        ref = ops.rollout(cfg, w, state0.clone(), T, knn_memo=None)
+        monkeypatch.delenv("SWARM_KNN_ORDERED")
+        table = torch.zeros(64, dtype=torch.int64, device=dev)
+        for kw in (dict(knn_memo=None), dict(knn_memo=table), dict(knn_memo=table)):
+            got = ops.rollout(cfg, w, state0.clone(), T, **kw)
+            assert torch.equal(got["state"], ref["state"]) and torch.equal(got["returns"], ref["returns"]), (N, K, kw.keys())
+        # the same table, different states (other patterns hash into the same 64 slots)
+        other = state0.roll(1, dims=0).contiguous()
+        monkeypatch.setenv("SWARM_KNN_ORDERED", "1")
+        ref2 = ops.rollout(cfg, w, other.clone(), T, knn_memo=None)
+        monkeypatch.delenv("SWARM_KNN_ORDERED")
+        got2 = ops.rollout(cfg, w, other.clone(), T, knn_memo=table)
+        assert torch.equal(got2["state"], ref2["state"]), (N, K, "shared table")
