@@ -825,10 +825,10 @@ int swarm_rollout_stack(const SwarmConfig* cfg, const SwarmStackSpec* spec, cons
   p.rewards_out = rewards;
   p.flags_out = flags;
   cudaStream_t st = (cudaStream_t)stream;
-  // world reward / Flocking: the whole loop is ONE launch with the state in registers (stack_kernels.cu
-  // gatstack_kernel<HP, true>); Cohesion's reward (and SWARM_STACK_FUSED=0) takes the launch sequence below
+  // the whole loop is ONE launch with the state in registers (stack_kernels.cu gatstack_kernel<HP, true>);
+  // SWARM_STACK_FUSED=0 takes the launch sequence below (forward, step, reward kernel, totals per tick)
   const char* fused_env = std::getenv("SWARM_STACK_FUSED");
-  if (!(fused_env && fused_env[0] == '0') && (!reward || rs.kind == SWARM_REWARD_FLOCKING))
+  if (!(fused_env && fused_env[0] == '0'))
     return check_cuda(launch_gatstack_rollout(*cfg, *spec, weights, state, ticks, p, reward ? &rs : nullptr, shaping, returns,
                                               hits, st),
                       "swarm_rollout_stack");

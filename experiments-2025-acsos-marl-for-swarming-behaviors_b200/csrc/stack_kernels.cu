@@ -32,7 +32,7 @@ struct StackParams {
   float4* state_rw;          // [B*N] advanced in place
   float* returns;            // [B*N] += (optional)
   int32_t* hits;             // [B] += (optional)
-  SwarmRewardSpec flock;     // use_flock: the Flocking collective reward instead of the world's
+  SwarmRewardSpec flock;     // use_flock 1: the Flocking collective reward, 2: Cohesion's per-agent reward, instead of the world's
   float2* shaping;           // [B*N] Flocking memory, read at launch, written back
   int32_t use_flock;
   int32_t ticks;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kTileThreads) gatstack_kernel(const __grid_con
   if (t.active) {
     s = ROLLOUT ? p.state_rw[t.gidx] : p.state[t.gidx];
     if (ROLLOUT && p.returns) ret0 = p.returns[t.gidx];
-    if (ROLLOUT && p.use_flock) shp = p.shaping[t.gidx];
+    if (ROLLOUT && p.use_flock == 1) shp = p.shaping[t.gidx];
   }
   stack_stage_weights<HP>(sp, p.weights, sw, tid, T);
   uint64_t cache_rank = ~0ull, cache_nbr = 0;
@@ -298,7 +298,31 @@ __global__ void __launch_bounds__(kTileThreads) gatstack_kernel(const __grid_con
         sred[tid] = dgoal;     // GoTo's collective reward needs every agent's distance: finished below
       }
     }
-    if (p.use_flock) {
+    if (p.use_flock == 2) {
+      // Cohesion (cohesion:66-85): smallest / largest surface distance to the other agents at their POST-step positions;
+      // the op sequence of reward_kernels.cu (extreme squared distances, two exact square roots)
+      const SwarmRewardSpec& fs = p.flock;
+      float4* post = sst + ((tick + 1) & 1) * T;
+      post[tid] = s;
+      __syncthreads();
+      if (t.active) {
+        const float4* others = post + t.envbase;
+        float lo = INFINITY, hi = 0.0f;
+#pragma unroll 4
+        for (int j = 0; j < N; ++j) {
+          const float2 q = xy_of(others[j]);
+          const float dx = __fsub_rn(s.x, q.x), dy = __fsub_rn(s.y, q.y);
+          const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+          lo = fminf(lo, j == t.i ? INFINITY : d2);
+          hi = fmaxf(hi, d2);
+        }
+        const float mn = __fsub_rn(__fsub_rn(__fsqrt_rn(lo), fs.agent_radius), fs.agent_radius);
+        const float mx = __fsub_rn(__fsub_rn(__fsqrt_rn(hi), fs.agent_radius), fs.agent_radius);
+        const float collision = mn > fs.sigma ? 0.0f : expf(-__fdiv_rn(mn, fs.sigma));    // cohesion:79-80
+        const float cohesion = mn < fs.sigma ? 0.0f : -__fsub_rn(mx, fs.sigma);           // cohesion:82-83
+        reward = __fadd_rn(collision, cohesion);
+      }
+    } else if (p.use_flock) {
       // Flocking (flocking:124-171): every agent's term from the POST-step positions of its env, then the collective sum
       // in agent order (the op sequence of reward_kernels.cu / the FLOCK tile kernel)
       const SwarmRewardSpec& fs = p.flock;
@@ -341,7 +365,7 @@ __global__ void __launch_bounds__(kTileThreads) gatstack_kernel(const __grid_con
     if (t.active) {
       p.state_rw[t.gidx] = s;
       if (p.returns) p.returns[t.gidx] = __fadd_rn(ret0, ret);
-      if (p.use_flock) p.shaping[t.gidx] = shp;
+      if (p.use_flock == 1) p.shaping[t.gidx] = shp;
     }
     if (p.hits) {
       __syncthreads();
@@ -410,7 +434,7 @@ cudaError_t launch_gatstack_rollout(const SwarmConfig& c, const SwarmStackSpec& 
   if (flock) {
     p.flock = *flock;
     p.shaping = reinterpret_cast<float2*>(shaping);
-    p.use_flock = 1;
+    p.use_flock = flock->kind == SWARM_REWARD_COHESION ? 2 : 1;
   }
   return launch_stack(p, stream);
 }

@@ -497,9 +497,9 @@ int swarm_gatstack_forward(const SwarmConfig* cfg, const SwarmStackSpec* spec, c
  * hits int32[B] (+=, obstacles_hits()).  reward == NULL: the world's own reward (GoTo / ObstacleAvoidance); a
  * SwarmRewardSpec selects the Flocking collective reward (shaping float[B][N][2] required, initialised by a reset call
  * of swarm_scenario_reward) or Cohesion's per-agent reward on the GoTo world, evaluated by the swarm_scenario_reward
- * kernel after every step.  With the world's reward or Flocking the whole loop is ONE launch (state, running return
- * and Flocking memory in registers across the ticks, same tick as swarm_rollout); Cohesion -- and SWARM_STACK_FUSED=0 --
- * take the launch sequence.  No host work, allocation or tensor-library op between the launches (graph capturable).
+ * arithmetic after every step.  The whole loop is ONE launch (state, running return and Flocking memory in registers
+ * across the ticks, same tick as swarm_rollout); SWARM_STACK_FUSED=0 launches forward, world step, reward kernel and
+ * totals per tick instead (same results, bit for bit).  No host work or allocation inside (graph capturable).
  * workspace: swarm_rollout_stack_workspace_bytes(cfg). */
 int64_t swarm_rollout_stack_workspace_bytes(const SwarmConfig* cfg);
 int swarm_rollout_stack(const SwarmConfig* cfg, const SwarmStackSpec* spec, const float* weights, float* state,
