@@ -12,6 +12,15 @@
 
 namespace swarm {
 
+// acc[0..3] += x * w  as two packed FFMA2 (sm_100): each lane is the same IEEE fused multiply-add as fmaf, so the
+// results are bit-identical to four scalar FFMAs at half the issue slots
+__device__ __forceinline__ void fma4_packed(float x, const float4& w, float& a0, float& a1, float& a2, float& a3) {
+  const float2 xx = make_float2(x, x);
+  const float2 lo = __ffma2_rn(xx, make_float2(w.x, w.y), make_float2(a0, a1));
+  const float2 hi = __ffma2_rn(xx, make_float2(w.z, w.w), make_float2(a2, a3));
+  a0 = lo.x; a1 = lo.y; a2 = hi.x; a3 = hi.y;
+}
+
 // h = x W0^T (GATConv.lin, no bias); alpha_src = <h, att_src>, alpha_dst = <h, att_dst>
 __device__ __forceinline__ void gat_project(const float (&x)[7], const float* __restrict__ sw, float (&h)[32],
                                             float& asrc, float& adst) {
@@ -22,11 +31,7 @@ __device__ __forceinline__ void gat_project(const float (&x)[7], const float* __
   for (int k = 0; k < 7; ++k) {
 #pragma unroll
     for (int c4 = 0; c4 < 8; ++c4) {
-      const float4 w = w0[k * 8 + c4];
-      h[4 * c4 + 0] = fmaf(x[k], w.x, h[4 * c4 + 0]);
-      h[4 * c4 + 1] = fmaf(x[k], w.y, h[4 * c4 + 1]);
-      h[4 * c4 + 2] = fmaf(x[k], w.z, h[4 * c4 + 2]);
-      h[4 * c4 + 3] = fmaf(x[k], w.w, h[4 * c4 + 3]);
+      fma4_packed(x[k], w0[k * 8 + c4], h[4 * c4 + 0], h[4 * c4 + 1], h[4 * c4 + 2], h[4 * c4 + 3]);
     }
   }
   asrc = 0.0f;
@@ -117,11 +122,7 @@ __device__ __forceinline__ int gat_head_keep(float (&a1)[32], float (&a2)[32], c
   for (int k = 0; k < 32; ++k) {
 #pragma unroll
     for (int c4 = 0; c4 < 8; ++c4) {
-      const float4 w = w1[k * 8 + c4];
-      a2[4 * c4 + 0] = fmaf(a1[k], w.x, a2[4 * c4 + 0]);
-      a2[4 * c4 + 1] = fmaf(a1[k], w.y, a2[4 * c4 + 1]);
-      a2[4 * c4 + 2] = fmaf(a1[k], w.z, a2[4 * c4 + 2]);
-      a2[4 * c4 + 3] = fmaf(a1[k], w.w, a2[4 * c4 + 3]);
+      fma4_packed(a1[k], w1[k * 8 + c4], a2[4 * c4 + 0], a2[4 * c4 + 1], a2[4 * c4 + 2], a2[4 * c4 + 3]);
     }
   }
   const float* b1 = sw + TW_B1;
@@ -136,11 +137,7 @@ __device__ __forceinline__ int gat_head_keep(float (&a1)[32], float (&a2)[32], c
   for (int k = 0; k < 32; ++k) {
 #pragma unroll
     for (int a4 = 0; a4 < 3; ++a4) {
-      const float4 w = w2[k * 3 + a4];
-      qq[4 * a4 + 0] = fmaf(a2[k], w.x, qq[4 * a4 + 0]);
-      qq[4 * a4 + 1] = fmaf(a2[k], w.y, qq[4 * a4 + 1]);
-      qq[4 * a4 + 2] = fmaf(a2[k], w.z, qq[4 * a4 + 2]);
-      qq[4 * a4 + 3] = fmaf(a2[k], w.w, qq[4 * a4 + 3]);
+      fma4_packed(a2[k], w2[k * 3 + a4], qq[4 * a4 + 0], qq[4 * a4 + 1], qq[4 * a4 + 2], qq[4 * a4 + 3]);
     }
   }
   const float* b2 = sw + TW_B2;

@@ -466,7 +466,6 @@ __global__ void __launch_bounds__(kGridThreads, 2) gatq_large_x_kernel(const __g
       const int oi = __shfl_xor_sync(0xffffffffu, t1i, sh);
       merge(o1, oi, o2);
     }
-    __syncthreads();                                        // sred was grid_build's scratch
     if (lane == 0) {
       sred[warp * 3 + 0] = t1;
       sred[warp * 3 + 1] = __int_as_float(t1i);
@@ -543,11 +542,7 @@ __global__ void __launch_bounds__(kGridThreads, 2) gatq_large_x_kernel(const __g
     for (int k = 0; k < 7; ++k) {
 #pragma unroll
       for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 w = w0[k * 8 + c4];
-        a1[4 * c4 + 0] = fmaf(xm[k], w.x, a1[4 * c4 + 0]);
-        a1[4 * c4 + 1] = fmaf(xm[k], w.y, a1[4 * c4 + 1]);
-        a1[4 * c4 + 2] = fmaf(xm[k], w.z, a1[4 * c4 + 2]);
-        a1[4 * c4 + 3] = fmaf(xm[k], w.w, a1[4 * c4 + 3]);
+        fma4_packed(xm[k], w0[k * 8 + c4], a1[4 * c4 + 0], a1[4 * c4 + 1], a1[4 * c4 + 2], a1[4 * c4 + 3]);
       }
     }
     float q[9];

@@ -578,11 +578,7 @@ __global__ void __launch_bounds__(kQLThreads, 2) gatq_knn_large_x_kernel(const _
     for (int k = 0; k < 7; ++k) {
 #pragma unroll
       for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 w = w0[k * 8 + c4];
-        a1[4 * c4 + 0] = fmaf(xm[k], w.x, a1[4 * c4 + 0]);
-        a1[4 * c4 + 1] = fmaf(xm[k], w.y, a1[4 * c4 + 1]);
-        a1[4 * c4 + 2] = fmaf(xm[k], w.z, a1[4 * c4 + 2]);
-        a1[4 * c4 + 3] = fmaf(xm[k], w.w, a1[4 * c4 + 3]);
+        fma4_packed(xm[k], w0[k * 8 + c4], a1[4 * c4 + 0], a1[4 * c4 + 1], a1[4 * c4 + 2], a1[4 * c4 + 3]);
       }
     }
     float q[9];
