@@ -10,7 +10,8 @@
 // reference's [pos, vel, goal, agent id] (train:95-99) or [pos, vel, agent id] for scenarios whose observation() is
 // cat[pos, vel] (cohesion_scenario.py:87-94).  Per layer the arithmetic follows torch_geometric's GATConv like the
 // one-layer kernels: h = x W^T, alpha = <h, att>, LeakyReLU(0.2) logits, max-subtracted softmax with the 1e-16
-// denominator, messages alpha * h_src summed in edge-list order, + bias.
+// denominator, messages alpha * h_src summed in edge-list order, + bias (alpha = weight x reciprocal of the sum and fused
+// multiply-adds: float32-level different rounding than torch's separately rounded ops, like the tensor-core path).
 #include <cstdlib>
 #include <cstring>
 
@@ -101,7 +102,7 @@ __device__ __forceinline__ void stack_stage_weights(const SwarmStackSpec& s, con
 }
 
 struct StackSmem {
-  int w, st, red, h, asrc, inl, kv, total;
+  int w, st, red, h, asrc, inl, wt, kv, total;
 };
 template <int HP>
 __host__ __device__ inline StackSmem stack_smem(int L, int n, int k, int maxdeg, int graph_mode) {
@@ -113,6 +114,7 @@ __host__ __device__ inline StackSmem stack_smem(int L, int n, int k, int maxdeg,
   s.h = off;    off = tile_align16(off + kTileThreads * (HP + 4) * 4);
   s.asrc = off; off = tile_align16(off + kTileThreads * 4);
   s.inl = off;  off = tile_align16(off + maxdeg * kTileThreads);
+  s.wt = off;   off = tile_align16(off + maxdeg * kTileThreads * 4);
   s.kv = off;   off = tile_align16(off + (graph_mode == SWARM_GRAPH_KNN ? kTileThreads * 4 : 0));
   s.total = off;
   return s;
@@ -182,6 +184,7 @@ __global__ void __launch_bounds__(kTileThreads) gatstack_kernel(const __grid_con
   }
 
   const uint8_t* sin = g.sin + tid;
+  float* swt = reinterpret_cast<float*>(smem + S.wt) + tid;
   for (int l = 0; l < L; ++l) {
     const float* base = sw + SL::layer_off(l);
     const int cinp = l == 0 ? SL::kIn0 : HP;
@@ -190,17 +193,20 @@ __global__ void __launch_bounds__(kTileThreads) gatstack_kernel(const __grid_con
     float h[HP];
 #pragma unroll
     for (int cc = 0; cc < HP; ++cc) h[cc] = 0.0f;
+    // (float4 weight loads + packed FFMA2: per element the same sequential-k chain of IEEE fused multiply-adds)
     if (l == 0) {
 #pragma unroll
       for (int k = 0; k < SL::kIn0; ++k) {
 #pragma unroll
-        for (int cc = 0; cc < HP; ++cc) h[cc] = fmaf(x[k], base[k * HP + cc], h[cc]);
+        for (int cc = 0; cc < HP; cc += 4)
+          fma4_packed(x[k], *reinterpret_cast<const float4*>(base + k * HP + cc), h[cc], h[cc + 1], h[cc + 2], h[cc + 3]);
       }
     } else {
 #pragma unroll
       for (int k = 0; k < HP; ++k) {
 #pragma unroll
-        for (int cc = 0; cc < HP; ++cc) h[cc] = fmaf(x[k], base[k * HP + cc], h[cc]);
+        for (int cc = 0; cc < HP; cc += 4)
+          fma4_packed(x[k], *reinterpret_cast<const float4*>(base + k * HP + cc), h[cc], h[cc + 1], h[cc + 2], h[cc + 3]);
       }
     }
     float asrc = 0.0f, adst = 0.0f;
@@ -220,23 +226,23 @@ __global__ void __launch_bounds__(kTileThreads) gatstack_kernel(const __grid_con
     const float* as_env = g.sas + t.envbase;
     float m = -INFINITY;
     for (int e = 0; e < deg; ++e) m = fmaxf(m, gat_logit(as_env[sin[e * T]], adst));
+    // unnormalised weights once (kept in the per-thread scratch column), one reciprocal, messages as fused
+    // multiply-adds in edge-list order
     float den = 0.0f;
-    for (int e = 0; e < deg; ++e) den = __fadd_rn(den, expf(__fsub_rn(gat_logit(as_env[sin[e * T]], adst), m)));
-    den = __fadd_rn(den, 1e-16f);
+    for (int e = 0; e < deg; ++e) {
+      const float we = expf(__fsub_rn(gat_logit(as_env[sin[e * T]], adst), m));
+      swt[e * T] = we;
+      den = __fadd_rn(den, we);
+    }
+    const float inv = __fdiv_rn(1.0f, __fadd_rn(den, 1e-16f));
 #pragma unroll
     for (int cc = 0; cc < HP; ++cc) x[cc] = 0.0f;
     for (int e = 0; e < deg; ++e) {
-      const int j = sin[e * T];
-      const float a = __fdiv_rn(expf(__fsub_rn(gat_logit(as_env[j], adst), m)), den);
-      const float* hj = rows + j * kRow;
+      const float a = __fmul_rn(swt[e * T], inv);
+      const float* hj = rows + sin[e * T] * kRow;
 #pragma unroll
-      for (int cc = 0; cc < HP; cc += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(hj + cc);
-        x[cc + 0] = __fadd_rn(x[cc + 0], __fmul_rn(a, v.x));
-        x[cc + 1] = __fadd_rn(x[cc + 1], __fmul_rn(a, v.y));
-        x[cc + 2] = __fadd_rn(x[cc + 2], __fmul_rn(a, v.z));
-        x[cc + 3] = __fadd_rn(x[cc + 3], __fmul_rn(a, v.w));
-      }
+      for (int cc = 0; cc < HP; cc += 4)
+        fma4_packed(a, *reinterpret_cast<const float4*>(hj + cc), x[cc], x[cc + 1], x[cc + 2], x[cc + 3]);
     }
     const bool relu = sp.activation[l] == 1;
 #pragma unroll
@@ -254,18 +260,20 @@ __global__ void __launch_bounds__(kTileThreads) gatstack_kernel(const __grid_con
 #pragma unroll
   for (int k = 0; k < HP; ++k) {
 #pragma unroll
-    for (int cc = 0; cc < HP; ++cc) r[cc] = fmaf(x[k], l1[k * HP + cc], r[cc]);
+    for (int cc = 0; cc < HP; cc += 4)
+      fma4_packed(x[k], *reinterpret_cast<const float4*>(l1 + k * HP + cc), r[cc], r[cc + 1], r[cc + 2], r[cc + 3]);
   }
 #pragma unroll
   for (int cc = 0; cc < HP; ++cc) r[cc] = fmaxf(__fadd_rn(r[cc], l1[HP * HP + cc]), 0.0f);
   const float* l2 = sw + SL::lin2_off(L);
-  float q[9];
+  float q[SL::kW2Cols];                                  // 9 actions + 3 zero-padded columns
 #pragma unroll
-  for (int a = 0; a < 9; ++a) q[a] = 0.0f;
+  for (int a = 0; a < SL::kW2Cols; ++a) q[a] = 0.0f;
 #pragma unroll
   for (int k = 0; k < HP; ++k) {
 #pragma unroll
-    for (int a = 0; a < 9; ++a) q[a] = fmaf(r[k], l2[k * SL::kW2Cols + a], q[a]);
+    for (int a = 0; a < SL::kW2Cols; a += 4)
+      fma4_packed(r[k], *reinterpret_cast<const float4*>(l2 + k * SL::kW2Cols + a), q[a], q[a + 1], q[a + 2], q[a + 3]);
   }
   float best = 0.0f;
   int action = 0;
