@@ -12,7 +12,6 @@
 // one-layer kernels: h = x W^T, alpha = <h, att>, LeakyReLU(0.2) logits, max-subtracted softmax with the 1e-16
 // denominator, messages alpha * h_src summed in edge-list order, + bias (alpha = weight x reciprocal of the sum and fused
 // multiply-adds: float32-level different rounding than torch's separately rounded ops, like the tensor-core path).
-#include <cstdlib>
 #include <cstring>
 
 #include "tile_device.cuh"
@@ -419,10 +418,6 @@ static void stack_fill(StackParams& p, const SwarmConfig& c, const SwarmStackSpe
   p.spec = spec;
   p.weights = weights;
   p.epb = kTileThreads / c.n_agents;
-  if (const char* e = std::getenv("SWARM_STACK_EPB")) {
-    const int v = std::atoi(e);
-    if (v >= 1 && v < p.epb) p.epb = v;
-  }
   p.maxdeg = c.graph_mode == SWARM_GRAPH_KNN ? (c.n_agents + c.knn_k + 1) : c.n_agents;
   p.qmax_r = c.graph_mode == SWARM_GRAPH_RADIUS ? sq_threshold(c.graph_radius) : 0.0f;
 }
