@@ -110,10 +110,16 @@ __device__ __forceinline__ float rcp_approx(float x) {
 
 // (aggregate + conv1.bias) -> tanh -> lin1 -> ReLU -> lin2; returns argmax (first maximum wins).
 // On return a1 holds u = tanh(agg + b0) and a2 holds r = relu(W1 u + b1) (kept for the backward pass).
+// FAST: tanh on the SFU (tanh_fast, absolute error ~1e-7) -- for the input-space forwards of large swarms, whose
+// attention already runs on SFU exponentials; the bit-faithful paths keep tanhf.
+template <bool FAST = false>
 __device__ __forceinline__ int gat_head_keep(float (&a1)[32], float (&a2)[32], const float* __restrict__ sw, float (&q)[9]) {
   const float* b0 = sw + TW_B0;
 #pragma unroll
-  for (int cc = 0; cc < 32; ++cc) a1[cc] = tanhf(__fadd_rn(a1[cc], b0[cc]));
+  for (int cc = 0; cc < 32; ++cc) {
+    const float v = __fadd_rn(a1[cc], b0[cc]);
+    a1[cc] = FAST ? tanh_fast(v) : tanhf(v);
+  }
 
 #pragma unroll
   for (int cc = 0; cc < 32; ++cc) a2[cc] = 0.0f;
@@ -156,7 +162,11 @@ __device__ __forceinline__ int gat_head_keep(float (&a1)[32], float (&a2)[32], c
 
 __device__ __forceinline__ int gat_head(float (&a1)[32], const float* __restrict__ sw, float (&q)[9]) {
   float a2[32];
-  return gat_head_keep(a1, a2, sw, q);
+  return gat_head_keep<false>(a1, a2, sw, q);
+}
+__device__ __forceinline__ int gat_head_fast(float (&a1)[32], const float* __restrict__ sw, float (&q)[9]) {
+  float a2[32];
+  return gat_head_keep<true>(a1, a2, sw, q);
 }
 
 }  // namespace swarm

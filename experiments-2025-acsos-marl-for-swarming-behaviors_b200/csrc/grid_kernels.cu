@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(kGridThreads, 2) gatq_large_x_kernel(const __g
       }
     }
     float q[9];
-    const int action = gat_head(a1, sw, q);
+    const int action = gat_head_fast(a1, sw, q);
     const long long gi = env * N + i;
     if (p.q_out) {
 #pragma unroll
@@ -554,6 +554,320 @@ __global__ void __launch_bounds__(kGridThreads, 2) gatq_large_x_kernel(const __g
     }
     if (p.act_out) p.act_out[gi] = action;
   }
+}
+
+// ---- complete graph in O(N log N) ---------------------------------------------------------------------------------
+// On the complete graph (train:94-110) the attention logit of edge (j -> i) is LeakyReLU(a_j + d_i) with a = alpha_src,
+// d = alpha_dst: for a fixed target the sources split by the SIGN of a_j + d_i, i.e. -- with the sources sorted by a --
+// into a prefix (slope 0.2) and a suffix (slope 1), and inside each part the weight factorises:
+//     exp(a_j + d_i - m_i)       = exp(d_i + A - m_i)           * exp(a_j - A)             (suffix, a_j > -d_i)
+//     exp(0.2 (a_j + d_i) - m_i) = exp(0.2 (d_i + A) - m_i)     * exp(0.2 (a_j - A))       (prefix)
+// with A = the env's largest a and m_i the softmax shift (largest logit of the row).  So one sort of the env's a values,
+// one suffix scan and one prefix scan of the six weighted quantities (1, x, y, vx, vy, id), and per target a binary
+// search, two scan look-ups, and the removal of its own term (no self loop except node 0's (0, 0)).  Everything that is
+// added is positive and the two factors are <= 1 (m_i = LeakyReLU(A + d_i) is the row's largest logit), so there is no
+// overflow and no cancellation -- except for the ONE node that holds A itself (its row's largest logit comes from the
+// second largest a): that node sums its row directly.  1 M pair evaluations per env at N = 1 024 become ~20 k operations.
+// Same mathematics as gatq_large_x_kernel<false>, float32-level different rounding (tests: Q within 1e-5).
+struct SortedScan {
+  float v[6];
+};
+
+__host__ __device__ inline size_t large_sorted_smem_bytes(int N) {
+  size_t b = (size_t)((TW_COUNT + 3) & ~3) * 4 + 64;        // weights, v_s / v_d
+  b += (size_t)N * 16 + (size_t)N * 4 * 2;                   // states, alpha_src, alpha_dst
+  b += 64 * 4;                                               // reduction scratch
+  b += (size_t)grid_pow2(N) * 4 + (size_t)grid_pow2(N) * 2;  // sort keys, permutation
+  b += (size_t)N * 4;                                        // sorted a
+  b += (size_t)(N + 1) * 6 * 4 * 2;                          // prefix / suffix scans of six quantities
+  b += 32 * 6 * 4 * 2;                                       // warp totals of the scans
+  return b + 128;
+}
+
+// monotone map float -> uint32 (ascending)
+__device__ __forceinline__ uint32_t float_order_key(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(kGridThreads, 2) gatq_large_sorted_kernel(const __grid_constant__ LargeXParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SwarmConfig& c = p.cfg;
+  const int N = c.n_agents, P = grid_pow2(N);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kGridThreads / 32;
+  const long long env = blockIdx.x;
+  float* sw = reinterpret_cast<float*>(smem_raw);
+  float* sv = sw + ((TW_COUNT + 3) & ~3);                 // v_s[8], v_d[8]
+  float4* sst = reinterpret_cast<float4*>(sv + 16);
+  float* sas = reinterpret_cast<float*>(sst + N);
+  float* sad = sas + N;
+  float* sred = sad + N;                                  // [64]
+  uint32_t* keys = reinterpret_cast<uint32_t*>(sred + 64);
+  float* sa_sorted = reinterpret_cast<float*>(keys + P);
+  float* pre = sa_sorted + N;                             // [N + 1][6]  exclusive prefix, slope-0.2 weights
+  float* suf = pre + (size_t)(N + 1) * 6;                 // [N + 1][6]  suffix sums, slope-1 weights
+  float* wtot = suf + (size_t)(N + 1) * 6;                // [2][kWarps][6]
+  uint16_t* perm = reinterpret_cast<uint16_t*>(wtot + 2 * 32 * 6);
+
+  stage_weights(p.weights, sw, tid, kGridThreads);
+  for (int i = tid; i < N; i += kGridThreads) sst[i] = p.state[env * N + i];
+  __syncthreads();
+  if (tid < 16) {
+    const int k = tid & 7;
+    const float* att = sw + (tid < 8 ? TW_ATT_S : TW_ATT_D);
+    float v = 0.0f;
+    if (k < 7)
+      for (int cc = 0; cc < 32; ++cc) v = fmaf(att[cc], sw[TW_W0T + k * 32 + cc], v);
+    sv[tid] = v;
+  }
+  __syncthreads();
+  // alpha terms, sort keys, the two largest alpha_src
+  float t1 = -INFINITY, t2 = -INFINITY;
+  int t1i = -1;
+  for (int i = tid; i < P; i += kGridThreads) {
+    uint32_t key = 0xFFFFFFFFu;
+    if (i < N) {
+      const float4 st = sst[i];
+      const float a = fmaf(st.x, sv[0], fmaf(st.y, sv[1], fmaf(st.z, sv[2], fmaf(st.w, sv[3],
+                      fmaf(c.goal_x, sv[4], fmaf(c.goal_y, sv[5], (float)i * sv[6]))))));
+      const float d = fmaf(st.x, sv[8], fmaf(st.y, sv[9], fmaf(st.z, sv[10], fmaf(st.w, sv[11],
+                      fmaf(c.goal_x, sv[12], fmaf(c.goal_y, sv[13], (float)i * sv[14]))))));
+      sas[i] = a;
+      sad[i] = d;
+      key = float_order_key(a);
+      if (key == 0xFFFFFFFFu) key = 0xFFFFFFFEu;            // padding stays last
+      if (a > t1) { t2 = t1; t1 = a; t1i = i; }
+      else if (a > t2) t2 = a;
+    }
+    keys[i] = key;
+    perm[i] = (uint16_t)(i < N ? i : 0);
+  }
+  {
+    auto merge = [&](float o1, int oi, float o2) {
+      if (o1 > t1) { t2 = fmaxf(t1, o2); t1 = o1; t1i = oi; }
+      else t2 = fmaxf(t2, o1);
+    };
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) {
+      const float o1 = __shfl_xor_sync(0xffffffffu, t1, sh), o2 = __shfl_xor_sync(0xffffffffu, t2, sh);
+      const int oi = __shfl_xor_sync(0xffffffffu, t1i, sh);
+      merge(o1, oi, o2);
+    }
+    if (lane == 0) {
+      sred[warp * 3 + 0] = t1;
+      sred[warp * 3 + 1] = __int_as_float(t1i);
+      sred[warp * 3 + 2] = t2;
+    }
+    __syncthreads();
+    t1 = -INFINITY; t2 = -INFINITY; t1i = -1;
+    for (int w = 0; w < kWarps; ++w) merge(sred[w * 3 + 0], __float_as_int(sred[w * 3 + 1]), sred[w * 3 + 2]);
+  }
+  const float A = t1;
+  // bitonic sort of (key, index) pairs (see grid_build for the barrier scheme)
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (P >> 1); t += kGridThreads) {
+        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int hi = lo | j;
+        const bool up = (lo & k) == 0;
+        const uint32_t ka = keys[lo], kb = keys[hi];
+        if ((ka > kb) == up) {
+          keys[lo] = kb; keys[hi] = ka;
+          const uint16_t pa = perm[lo];
+          perm[lo] = perm[hi]; perm[hi] = pa;
+        }
+      }
+      const int jn = (j > 1) ? (j >> 1) : k;
+      if (j > 32 || jn > 32) __syncthreads(); else __syncwarp();
+    }
+  }
+  __syncthreads();
+  // scans over the sorted order: thread t owns the contiguous positions [t * per, (t + 1) * per)
+  const int per = (N + kGridThreads - 1) / kGridThreads;
+  const int p0 = tid * per;
+  {
+    SortedScan lp, ls;                                      // this thread's chunk totals: prefix weights, suffix weights
+#pragma unroll
+    for (int q = 0; q < 6; ++q) { lp.v[q] = 0.0f; ls.v[q] = 0.0f; }
+    for (int k = 0; k < per; ++k) {
+      const int pp = p0 + k;
+      if (pp < N) {
+        const int j = perm[pp];
+        const float a = sas[j];
+        sa_sorted[pp] = a;
+        const float4 sj = sst[j];
+        const float e2 = __expf(0.2f * (a - A)), e1 = __expf(a - A);
+        const float qv[6] = {1.0f, sj.x, sj.y, sj.z, sj.w, (float)j};
+#pragma unroll
+        for (int q = 0; q < 6; ++q) { lp.v[q] = fmaf(e2, qv[q], lp.v[q]); ls.v[q] = fmaf(e1, qv[q], ls.v[q]); }
+      }
+    }
+    // inclusive warp scans: prefix ascending in tid, suffix descending in tid
+    SortedScan ip = lp, is = ls;
+#pragma unroll
+    for (int sh = 1; sh < 32; sh <<= 1) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const float up = __shfl_up_sync(0xffffffffu, ip.v[q], sh);
+        const float dn = __shfl_down_sync(0xffffffffu, is.v[q], sh);
+        if (lane >= sh) ip.v[q] += up;
+        if (lane + sh < 32) is.v[q] += dn;
+      }
+    }
+    if (lane == 31)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) wtot[(0 * 32 + warp) * 6 + q] = ip.v[q];
+    if (lane == 0)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) wtot[(1 * 32 + warp) * 6 + q] = is.v[q];
+    __syncthreads();
+    SortedScan bp, bs;                                      // totals of the warps before / after this one
+#pragma unroll
+    for (int q = 0; q < 6; ++q) { bp.v[q] = 0.0f; bs.v[q] = 0.0f; }
+    for (int w = 0; w < warp; ++w)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) bp.v[q] += wtot[(0 * 32 + w) * 6 + q];
+    for (int w = kWarps - 1; w > warp; --w)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) bs.v[q] += wtot[(1 * 32 + w) * 6 + q];
+    // exclusive prefix at the chunk start / suffix just after the chunk end (the neighbour lane's inclusive value: no
+    // subtraction), then walk the chunk
+    SortedScan runp, runs;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const float upx = __shfl_up_sync(0xffffffffu, ip.v[q], 1);
+      const float dnx = __shfl_down_sync(0xffffffffu, is.v[q], 1);
+      runp.v[q] = bp.v[q] + (lane > 0 ? upx : 0.0f);
+      runs.v[q] = bs.v[q] + (lane < 31 ? dnx : 0.0f);
+    }
+    // prefix: ascending walk writes pre[pp] = sum over positions < pp
+    for (int k = 0; k < per; ++k) {
+      const int pp = p0 + k;
+      if (pp < N) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) pre[(size_t)pp * 6 + q] = runp.v[q];
+        const int j = perm[pp];
+        const float a = sas[j];
+        const float4 sj = sst[j];
+        const float e2 = __expf(0.2f * (a - A));
+        const float qv[6] = {1.0f, sj.x, sj.y, sj.z, sj.w, (float)j};
+#pragma unroll
+        for (int q = 0; q < 6; ++q) runp.v[q] = fmaf(e2, qv[q], runp.v[q]);
+      }
+    }
+    if (p0 <= N - 1 && N - 1 < p0 + per) {                  // the owner of the last position: the total
+#pragma unroll
+      for (int q = 0; q < 6; ++q) pre[(size_t)N * 6 + q] = runp.v[q];
+    }
+    // suffix: descending walk writes suf[pp] = sum over positions >= pp
+    for (int k = per - 1; k >= 0; --k) {
+      const int pp = p0 + k;
+      if (pp < N) {
+        const int j = perm[pp];
+        const float a = sas[j];
+        const float4 sj = sst[j];
+        const float e1 = __expf(a - A);
+        const float qv[6] = {1.0f, sj.x, sj.y, sj.z, sj.w, (float)j};
+#pragma unroll
+        for (int q = 0; q < 6; ++q) runs.v[q] = fmaf(e1, qv[q], runs.v[q]);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) suf[(size_t)pp * 6 + q] = runs.v[q];
+      }
+    }
+    if (tid == 0) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) suf[(size_t)N * 6 + q] = 0.0f;
+    }
+  }
+  if (warp == 0 && t1i > 0) {
+    // direct row of the holder of the largest alpha_src, 32 lanes over the sources (fixed lane order: deterministic)
+    const float adst = sad[t1i];
+    const float m = gat_logit(t2, adst);
+    float ds[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) ds[q] = 0.0f;
+    for (int j = lane; j < N; j += 32) {
+      if (j == t1i) continue;
+      const float4 sj = sst[j];
+      const float w = __expf(gat_logit(sas[j], adst) - m);
+      ds[0] += w;
+      ds[1] = fmaf(w, sj.x, ds[1]); ds[2] = fmaf(w, sj.y, ds[2]);
+      ds[3] = fmaf(w, sj.z, ds[3]); ds[4] = fmaf(w, sj.w, ds[4]);
+      ds[5] = fmaf(w, (float)j, ds[5]);
+    }
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) ds[q] += __shfl_xor_sync(0xffffffffu, ds[q], sh);
+    if (lane == 0)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) sred[48 + q] = ds[q];
+  }
+  __syncthreads();
+
+  for (int i = tid; i < N; i += kGridThreads) {
+    const float4 st = sst[i];
+    const float adst = sad[i], ai = sas[i];
+    float sum[6];
+    if (i == t1i && i != 0) {
+      // the holder of the largest alpha_src: its row's largest logit comes from the second largest.  Its row was summed
+      // directly by warp 0 (below the scans): pick the sums up
+#pragma unroll
+      for (int q = 0; q < 6; ++q) sum[q] = sred[48 + q];
+    } else {
+      const float zA = A + adst;
+      const float m = zA > 0.0f ? zA : 0.2f * zA;             // the row's largest logit (node 0 keeps its own source)
+      // split position: number of sorted a values <= -adst (their logits take the 0.2 slope)
+      int lo = 0, hi = N;
+      const float thr = -adst;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sa_sorted[mid] <= thr) lo = mid + 1; else hi = mid;
+      }
+      const float c1 = __expf(zA - m), c2 = __expf(0.2f * zA - m);
+      const float* ps = pre + (size_t)lo * 6;
+      const float* ss = suf + (size_t)lo * 6;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) sum[q] = fmaf(c1, ss[q], c2 * ps[q]);
+      if (i != 0) {
+        const float wown = __expf(gat_logit(ai, adst) - m);
+        sum[0] -= wown;
+        sum[1] = fmaf(-wown, st.x, sum[1]); sum[2] = fmaf(-wown, st.y, sum[2]);
+        sum[3] = fmaf(-wown, st.z, sum[3]); sum[4] = fmaf(-wown, st.w, sum[4]);
+        sum[5] = fmaf(-wown, (float)i, sum[5]);
+      }
+    }
+    const float den = sum[0];
+    const float inv = 1.0f / __fadd_rn(den, 1e-16f);
+    const float wsum = den * inv;
+    const float xm[7] = {sum[1] * inv, sum[2] * inv, sum[3] * inv, sum[4] * inv, c.goal_x * wsum, c.goal_y * wsum,
+                         sum[5] * inv};
+    float a1[32];
+#pragma unroll
+    for (int cc = 0; cc < 32; ++cc) a1[cc] = 0.0f;
+    const float4* w0 = reinterpret_cast<const float4*>(sw + TW_W0T);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4)
+        fma4_packed(xm[k], w0[k * 8 + c4], a1[4 * c4 + 0], a1[4 * c4 + 1], a1[4 * c4 + 2], a1[4 * c4 + 3]);
+    }
+    float q[9];
+    const int action = gat_head_fast(a1, sw, q);
+    const long long gi = env * N + i;
+    if (p.q_out) {
+#pragma unroll
+      for (int a = 0; a < 9; ++a) p.q_out[gi * 9 + a] = q[a];
+    }
+    if (p.act_out) p.act_out[gi] = action;
+  }
+}
+
+bool gatq_large_sorted_enabled(int N) {
+  const char* e = std::getenv("SWARM_COMPLETE_SORTED");
+  if (e && e[0] == '0') return false;
+  return large_sorted_smem_bytes(N) <= 227 * 1024;
 }
 
 bool gatq_large_x_fits(int N, bool radius) { return N <= (1 << kIdxBits) && large_x_smem_bytes(N, radius) <= 227 * 1024; }
@@ -573,6 +887,12 @@ cudaError_t launch_gatq_large_x(const SwarmConfig& c, const float* weights, cons
     cudaError_t err = cudaFuncSetAttribute(gatq_large_x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     gatq_large_x_kernel<true><<<c.num_envs, kGridThreads, smem, stream>>>(p);
+  } else if (gatq_large_sorted_enabled(c.n_agents)) {
+    // complete graph in O(N log N): sorted sources, prefix / suffix scans (SWARM_COMPLETE_SORTED=0: the pairwise kernel)
+    const size_t ssm = large_sorted_smem_bytes(c.n_agents);
+    cudaError_t err = cudaFuncSetAttribute(gatq_large_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
+    if (err != cudaSuccess) return err;
+    gatq_large_sorted_kernel<<<c.num_envs, kGridThreads, ssm, stream>>>(p);
   } else {
     cudaError_t err = cudaFuncSetAttribute(gatq_large_x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;

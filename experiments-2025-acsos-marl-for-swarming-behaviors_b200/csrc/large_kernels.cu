@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(kQLThreads, 2) gatq_knn_large_x_kernel(const _
       }
     }
     float q[9];
-    const int action = gat_head(a1, sw, q);
+    const int action = gat_head_fast(a1, sw, q);
     const long long g = env * N + i;
     if (p.q_out) {
 #pragma unroll

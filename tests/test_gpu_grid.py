@@ -220,3 +220,42 @@ def test_grid_world_step_equals_full_sweep(scenario, N, B, spread, monkeypatch):
     work = state.clone()
     inplace = ops.sim_step(cfg, work, actions, state_out=work, want_obs=False)
     assert torch.equal(inplace["state"], ref["state"]) and torch.equal(inplace["rewards"], ref["rewards"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,B,vscale", [(1024, 3, 0.2), (129, 5, 0.2), (1000, 2, 3.0), (2048, 2, 1.0), (300, 4, 30.0),
+                                        (640, 2, 0.0)])
+def test_complete_graph_sorted_forward_equals_pairwise(N, B, vscale, monkeypatch):
+    """Complete graph of a large env in O(N log N) (sources sorted by alpha_src, prefix / suffix scans of the factorised
+    softmax weights, own term removed, the holder of the largest alpha_src summed directly) against the pairwise
+    O(N^2) kernel (SWARM_COMPLETE_SORTED=0) and the bit-faithful CSR forward: Q within 1e-5 of the row's largest
+    magnitude, also with velocities that stretch the attention logits over hundreds of units."""
+    import swarm_b200 as sb
+    ops, L = sb.ops, sb._lib
+    dev = _dev()
+    pos, vel = _swarm(B, N, seed=N + 7, spread=0.8)
+    vel = vel * (vscale / 0.2)
+    if vscale == 0.0:
+        pos[0] = pos[0, :1]                                   # an env whose agents all share one state: every alpha ties
+    state = torch.cat([pos, vel], 2).contiguous().to(dev)
+    cfg = ops.make_config(L.SCENARIO_OBSTACLE_AVOIDANCE, B, N, L.GRAPH_COMPLETE)
+    for model in (0, 3):
+        w = sb.pack_weights(load_params("ObstacleAvoidance", model), dev)
+        monkeypatch.setenv("SWARM_COMPLETE_SORTED", "0")
+        q_pair = ops.gatq_forward_large(cfg, w, state)
+        monkeypatch.delenv("SWARM_COMPLETE_SORTED")
+        q_sort, a_sort = ops.gatq_forward_large(cfg, w, state, want_q=True, want_actions=True)
+        assert torch.isfinite(q_sort).all()
+        scale = q_pair.abs().amax(dim=-1, keepdim=True).clamp_min(1e-3)
+        err = ((q_sort.double() - q_pair.double()).abs() / scale.double()).max().item()
+        assert err <= Q_RTOL, f"model {model}: sorted vs pairwise Q relative error {err:.3e}"
+        assert torch.equal(a_sort.long(), torch.argmax(q_sort, dim=-1))
+    if N <= 1024:
+        edges, _ = ops.graph_build(cfg, state)
+        offs = (torch.arange(B, device=dev, dtype=torch.int64) * N).view(B, 1, 1)
+        ei = (edges.to(torch.int64) + offs).permute(1, 0, 2).reshape(2, -1).contiguous()
+        row_ptr, src, _ = ops.csr_from_edges(ei, B * N)
+        q_ref = ops.gatq_forward_csr(w, _x(cfg, state), row_ptr, src, want_q=True, want_actions=False)
+        scale = q_ref.abs().amax(dim=1, keepdim=True).clamp_min(1e-3)
+        err = ((q_sort.view(B * N, 9).double() - q_ref.double()).abs() / scale.double()).max().item()
+        assert err <= Q_RTOL, f"sorted vs CSR forward: {err:.3e}"
