@@ -579,7 +579,7 @@ __host__ __device__ inline size_t large_sorted_smem_bytes(int N) {
   b += 64 * 4;                                               // reduction scratch
   b += (size_t)grid_pow2(N) * 4 + (size_t)grid_pow2(N) * 2;  // sort keys, permutation
   b += (size_t)N * 4;                                        // sorted a
-  b += (size_t)(N + 1) * 6 * 4 * 2;                          // prefix / suffix scans of six quantities
+  b += (size_t)((N >> 2) + 2) * 6 * 4 * 2;                   // prefix / suffix scans of six quantities, every 4th position
   b += 32 * 6 * 4 * 2;                                       // warp totals of the scans
   return b + 128;
 }
@@ -605,9 +605,12 @@ __global__ void __launch_bounds__(kGridThreads, 2) gatq_large_sorted_kernel(cons
   float* sred = sad + N;                                  // [64]
   uint32_t* keys = reinterpret_cast<uint32_t*>(sred + 64);
   float* sa_sorted = reinterpret_cast<float*>(keys + P);
-  float* pre = sa_sorted + N;                             // [N + 1][6]  exclusive prefix, slope-0.2 weights
-  float* suf = pre + (size_t)(N + 1) * 6;                 // [N + 1][6]  suffix sums, slope-1 weights
-  float* wtot = suf + (size_t)(N + 1) * 6;                // [2][kWarps][6]
+  // scans are kept at every FOURTH sorted position (12 B per agent instead of 48: envs of 4 096 agents fit); a look-up
+  // adds the at most three elements between the stored position and the one asked for
+  const int NC = (N >> 2) + 2;
+  float* pre = sa_sorted + N;                             // [NC][6]  pre[c] = sum over positions <  4 c, slope-0.2 weights
+  float* suf = pre + (size_t)NC * 6;                      // [NC][6]  suf[c] = sum over positions >= 4 c, slope-1 weights
+  float* wtot = suf + (size_t)NC * 6;                     // [2][kWarps][6]
   uint16_t* perm = reinterpret_cast<uint16_t*>(wtot + 2 * 32 * 6);
 
   stage_weights(p.weights, sw, tid, kGridThreads);
@@ -745,8 +748,10 @@ __global__ void __launch_bounds__(kGridThreads, 2) gatq_large_sorted_kernel(cons
     for (int k = 0; k < per; ++k) {
       const int pp = p0 + k;
       if (pp < N) {
+        if ((pp & 3) == 0) {
 #pragma unroll
-        for (int q = 0; q < 6; ++q) pre[(size_t)pp * 6 + q] = runp.v[q];
+          for (int q = 0; q < 6; ++q) pre[(size_t)(pp >> 2) * 6 + q] = runp.v[q];
+        }
         const int j = perm[pp];
         const float a = sas[j];
         const float4 sj = sst[j];
@@ -756,9 +761,9 @@ __global__ void __launch_bounds__(kGridThreads, 2) gatq_large_sorted_kernel(cons
         for (int q = 0; q < 6; ++q) runp.v[q] = fmaf(e2, qv[q], runp.v[q]);
       }
     }
-    if (p0 <= N - 1 && N - 1 < p0 + per) {                  // the owner of the last position: the total
+    if ((N & 3) == 0 && p0 <= N - 1 && N - 1 < p0 + per) {  // the owner of the last position: the total at position N
 #pragma unroll
-      for (int q = 0; q < 6; ++q) pre[(size_t)N * 6 + q] = runp.v[q];
+      for (int q = 0; q < 6; ++q) pre[(size_t)(N >> 2) * 6 + q] = runp.v[q];
     }
     // suffix: descending walk writes suf[pp] = sum over positions >= pp
     for (int k = per - 1; k >= 0; --k) {
@@ -771,13 +776,15 @@ __global__ void __launch_bounds__(kGridThreads, 2) gatq_large_sorted_kernel(cons
         const float qv[6] = {1.0f, sj.x, sj.y, sj.z, sj.w, (float)j};
 #pragma unroll
         for (int q = 0; q < 6; ++q) runs.v[q] = fmaf(e1, qv[q], runs.v[q]);
+        if ((pp & 3) == 0) {
 #pragma unroll
-        for (int q = 0; q < 6; ++q) suf[(size_t)pp * 6 + q] = runs.v[q];
+          for (int q = 0; q < 6; ++q) suf[(size_t)(pp >> 2) * 6 + q] = runs.v[q];
+        }
       }
     }
-    if (tid == 0) {
+    if (tid == 0) {                                         // positions >= 4 ceil(N / 4): nothing
 #pragma unroll
-      for (int q = 0; q < 6; ++q) suf[(size_t)N * 6 + q] = 0.0f;
+      for (int q = 0; q < 6; ++q) suf[(size_t)((N + 3) >> 2) * 6 + q] = 0.0f;
     }
   }
   if (warp == 0 && t1i > 0) {
@@ -826,8 +833,31 @@ __global__ void __launch_bounds__(kGridThreads, 2) gatq_large_sorted_kernel(cons
         if (sa_sorted[mid] <= thr) lo = mid + 1; else hi = mid;
       }
       const float c1 = __expf(zA - m), c2 = __expf(0.2f * zA - m);
-      const float* ps = pre + (size_t)lo * 6;
-      const float* ss = suf + (size_t)lo * 6;
+      // prefix over positions < lo = stored prefix at 4 floor(lo / 4) + the positions up to lo - 1;
+      // suffix over positions >= lo = stored suffix at 4 ceil(lo / 4) + the positions from lo up to it
+      float ps[6], ss[6];
+      const int cp = lo >> 2, cs = (lo + 3) >> 2;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) { ps[q] = pre[(size_t)cp * 6 + q]; ss[q] = suf[(size_t)cs * 6 + q]; }
+      for (int pp = cp << 2; pp < lo; ++pp) {
+        const int j = perm[pp];
+        const float4 sj = sst[j];
+        const float e2 = __expf(0.2f * (sa_sorted[pp] - A));
+        ps[0] += e2;
+        ps[1] = fmaf(e2, sj.x, ps[1]); ps[2] = fmaf(e2, sj.y, ps[2]);
+        ps[3] = fmaf(e2, sj.z, ps[3]); ps[4] = fmaf(e2, sj.w, ps[4]);
+        ps[5] = fmaf(e2, (float)j, ps[5]);
+      }
+      const int top = min(cs << 2, N);
+      for (int pp = top - 1; pp >= lo; --pp) {
+        const int j = perm[pp];
+        const float4 sj = sst[j];
+        const float e1 = __expf(sa_sorted[pp] - A);
+        ss[0] += e1;
+        ss[1] = fmaf(e1, sj.x, ss[1]); ss[2] = fmaf(e1, sj.y, ss[2]);
+        ss[3] = fmaf(e1, sj.z, ss[3]); ss[4] = fmaf(e1, sj.w, ss[4]);
+        ss[5] = fmaf(e1, (float)j, ss[5]);
+      }
 #pragma unroll
       for (int q = 0; q < 6; ++q) sum[q] = fmaf(c1, ss[q], c2 * ps[q]);
       if (i != 0) {

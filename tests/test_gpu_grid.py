@@ -224,7 +224,7 @@ def test_grid_world_step_equals_full_sweep(scenario, N, B, spread, monkeypatch):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("N,B,vscale", [(1024, 3, 0.2), (129, 5, 0.2), (1000, 2, 3.0), (2048, 2, 1.0), (300, 4, 30.0),
-                                        (640, 2, 0.0)])
+                                        (640, 2, 0.0), (4096, 2, 0.5), (1022, 2, 1.0), (131, 3, 5.0), (5, 64, 1.0)])
 def test_complete_graph_sorted_forward_equals_pairwise(N, B, vscale, monkeypatch):
     """Complete graph of a large env in O(N log N) (sources sorted by alpha_src, prefix / suffix scans of the factorised
     softmax weights, own term removed, the holder of the largest alpha_src summed directly) against the pairwise
