@@ -546,9 +546,11 @@ def measure_dqn(sb, ops, dev, cfg, weights, centers, dist, barrier, stream, rank
         nccl = world > 1 and tt.peers is None
 
         def tick():
+            if not nccl:
+                tt.tick(w, w_t, m, v, state, returns, hits)
+                return
             tt.grad_phase(w, w_t, state, returns, hits)
-            if nccl:
-                dist.all_reduce(tt.grad_loss)
+            dist.all_reduce(tt.grad_loss)
             tt.apply_phase(w, w_t, m, v)
 
         def timed(fn):

@@ -166,6 +166,9 @@ _SIGNATURES = {
                                                                                  C.c_double, C.c_void_p]),
     "swarm_train_tick_apply": (C.c_int, [C.POINTER(SwarmConfig), C.POINTER(SwarmTrainHyper)] + [C.c_void_p] * 6
                                + [C.c_int64, C.POINTER(SwarmPeerExchange), C.c_void_p]),
+    "swarm_train_tick": (C.c_int, [C.POINTER(SwarmConfig), C.POINTER(SwarmTrainHyper)] + [C.c_void_p] * 8
+                         + [C.POINTER(SwarmReplay)] + [C.c_void_p] * 3 + [C.c_int64, C.POINTER(SwarmPeerExchange),
+                                                                          C.c_void_p]),
 }
 
 

@@ -69,15 +69,19 @@ cudaError_t launch_replay_gather(const SwarmReplay& r, const int64_t* indices, i
                                  int32_t* actions, float* rewards, float* next_state, cudaStream_t stream);
 long long dqn_workspace_bytes(const SwarmConfig& c, int n_graphs);
 int dqn_smem_bytes(const SwarmConfig& c);
+bool dqn_fuse_reduce(const SwarmConfig& c, int n_graphs);
 cudaError_t launch_dqn_grad(const SwarmConfig& c, const float* w_online, const float* w_target, const SwarmReplay& batch,
                             const int64_t* indices, int n_graphs, float gamma, float loss_scale, float* grad, float* loss,
                             float* td, void* workspace, cudaStream_t stream, SwarmTrainCtl* ctl = nullptr,
-                            int64_t* indices_out = nullptr, unsigned long long sample_seed = 0, int pushed_envs = 0);
+                            int64_t* indices_out = nullptr, unsigned long long sample_seed = 0, int pushed_envs = 0,
+                            bool skip_reduce = false);
 cudaError_t launch_adam_clip(float* w, const float* grad, float* m, float* v, long long step, double lr, double beta1,
                              double beta2, double eps, double max_norm, float* target, float* grad_norm,
                              cudaStream_t stream, SwarmTrainCtl* ctl = nullptr, int num_envs = 0,
                              long long ring_capacity = 1, int update_target_every = 1,
-                             const SwarmPeerExchange* peers = nullptr, float* grad_rw = nullptr);
+                             const SwarmPeerExchange* peers = nullptr, float* grad_rw = nullptr,
+                             const SwarmConfig* reduce_cfg = nullptr, const void* reduce_workspace = nullptr,
+                             int reduce_graphs = 0, float loss_scale = 0.0f);
 
 namespace {
 thread_local std::string g_last_error;
@@ -640,10 +644,11 @@ static int validate_hyper(const SwarmTrainHyper* h) {
   return SWARM_OK;
 }
 
-int swarm_train_tick_grad(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, SwarmTrainCtl* ctl, const float* weights,
-                          const float* target_weights, float* state, float* returns, int32_t* hits,
-                          const SwarmReplay* ring, int64_t* indices, float* grad, float* loss, void* workspace,
-                          int64_t workspace_bytes, void* stream) {
+// shared argument checks and rollout-tick parameters of swarm_train_tick_grad / swarm_train_tick
+static int train_tick_rollout(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, SwarmTrainCtl* ctl, const float* weights,
+                              const float* target_weights, float* state, float* returns, int32_t* hits,
+                              const SwarmReplay* ring, float* grad, float* loss, void* workspace, int64_t workspace_bytes,
+                              cudaStream_t st, const char* what) {
   if (int rc = validate(cfg, true)) return rc;
   if (int rc = validate_hyper(hyper)) return rc;
   if (int rc = validate_dqn(cfg, hyper->graphs_per_update)) return rc;
@@ -667,8 +672,26 @@ int swarm_train_tick_grad(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, 
   p.replay = *ring;
   p.ctl = ctl;
   if (int rc = attach_flocking(p, cfg, hyper->flocking, hyper->flocking_shaping)) return rc;
+  return check_cuda(launch_tile(MODE_ROLLOUT, p, st), what);
+}
+
+static int validate_peers(const SwarmPeerExchange* peers) {
+  if (!peers) return SWARM_OK;
+  if (peers->world_size < 1 || peers->world_size > SWARM_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world_size)
+    return fail(SWARM_ERR_INVALID_ARG, "peer exchange: bad world_size / rank");
+  for (int r = 0; r < peers->world_size; ++r)
+    if (!peers->data[r]) return fail(SWARM_ERR_INVALID_ARG, "peer exchange: NULL peer buffer");
+  return SWARM_OK;
+}
+
+int swarm_train_tick_grad(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, SwarmTrainCtl* ctl, const float* weights,
+                          const float* target_weights, float* state, float* returns, int32_t* hits,
+                          const SwarmReplay* ring, int64_t* indices, float* grad, float* loss, void* workspace,
+                          int64_t workspace_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (int rc = check_cuda(launch_tile(MODE_ROLLOUT, p, st), "swarm_train_tick_grad(rollout)")) return rc;
+  if (int rc = train_tick_rollout(cfg, hyper, ctl, weights, target_weights, state, returns, hits, ring, grad, loss,
+                                  workspace, workspace_bytes, st, "swarm_train_tick_grad(rollout)"))
+    return rc;
   return check_cuda(launch_dqn_grad(*cfg, weights, target_weights, *ring, nullptr, hyper->graphs_per_update, hyper->gamma,
                                     hyper->loss_scale, grad, loss, nullptr, workspace, st, ctl, indices,
                                     hyper->sample_seed, cfg->num_envs),
@@ -682,16 +705,38 @@ int swarm_train_tick_apply(const SwarmConfig* cfg, const SwarmTrainHyper* hyper,
   if (int rc = validate_hyper(hyper)) return rc;
   if (!ctl || !weights || !target_weights || !exp_avg || !exp_avg_sq || !grad) return fail(SWARM_ERR_INVALID_ARG, "NULL argument");
   if (ring_capacity < cfg->num_envs) return fail(SWARM_ERR_INVALID_ARG, "ring_capacity must be >= num_envs");
-  if (peers) {
-    if (peers->world_size < 1 || peers->world_size > SWARM_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world_size)
-      return fail(SWARM_ERR_INVALID_ARG, "peer exchange: bad world_size / rank");
-    for (int r = 0; r < peers->world_size; ++r)
-      if (!peers->data[r]) return fail(SWARM_ERR_INVALID_ARG, "peer exchange: NULL peer buffer");
-  }
+  if (int rc = validate_peers(peers)) return rc;
   return check_cuda(launch_adam_clip(weights, grad, exp_avg, exp_avg_sq, 1, hyper->lr, hyper->beta1, hyper->beta2,
                                      hyper->eps, hyper->max_norm, target_weights, nullptr, (cudaStream_t)stream, ctl,
                                      cfg->num_envs, ring_capacity, hyper->update_target_every, peers, grad),
                     "swarm_train_tick_apply");
+}
+
+int swarm_train_tick(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, SwarmTrainCtl* ctl, float* weights,
+                     float* target_weights, float* exp_avg, float* exp_avg_sq, float* state, float* returns,
+                     int32_t* hits, const SwarmReplay* ring, int64_t* indices, float* grad, void* workspace,
+                     int64_t workspace_bytes, const SwarmPeerExchange* peers, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!exp_avg || !exp_avg_sq) return fail(SWARM_ERR_INVALID_ARG, "NULL argument");
+  if (int rc = validate_peers(peers)) return rc;
+  if (int rc = train_tick_rollout(cfg, hyper, ctl, weights, target_weights, state, returns, hits, ring, grad,
+                                  grad ? grad + SWARM_W_COUNT : nullptr, workspace, workspace_bytes, st,
+                                  "swarm_train_tick(rollout)"))
+    return rc;
+  const int G = hyper->graphs_per_update;
+  // one GPU, gradient kernel on few CTAs: partial reduction + clip + Adam as one cluster launch; with a peer exchange
+  // or a large update batch the reduce launch and the (exchanging) clip + Adam kernel
+  const bool fuse = !(peers && peers->world_size > 1) && dqn_fuse_reduce(*cfg, G);
+  if (int rc = check_cuda(launch_dqn_grad(*cfg, weights, target_weights, *ring, nullptr, G, hyper->gamma, hyper->loss_scale,
+                                          grad, grad + SWARM_W_COUNT, nullptr, workspace, st, ctl, indices,
+                                          hyper->sample_seed, cfg->num_envs, fuse),
+                          "swarm_train_tick(grad)"))
+    return rc;
+  return check_cuda(launch_adam_clip(weights, grad, exp_avg, exp_avg_sq, 1, hyper->lr, hyper->beta1, hyper->beta2,
+                                     hyper->eps, hyper->max_norm, target_weights, nullptr, st, ctl, cfg->num_envs,
+                                     ring->capacity, hyper->update_target_every, peers, grad, fuse ? cfg : nullptr,
+                                     fuse ? workspace : nullptr, G, hyper->loss_scale),
+                    "swarm_train_tick(apply)");
 }
 
 int swarm_reset_random(const SwarmConfig* cfg, const SwarmResetSpec* spec, const SwarmTrainCtl* ctl, int64_t episode,

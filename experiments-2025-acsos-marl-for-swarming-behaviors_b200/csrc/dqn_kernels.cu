@@ -8,6 +8,8 @@
 // (target, source) pair), and all weight gradients are tile GEMMs  dW = L^T R  over the CTA's 128 node
 // rows; per-CTA partials are then summed in CTA order by dqn_reduce_kernel.  No atomics anywhere, so the
 // gradient is bit-reproducible from run to run.
+#include <cooperative_groups.h>
+
 #include "dqn_common.cuh"
 
 namespace swarm {
@@ -512,7 +514,82 @@ struct AdamParams {
   // fused one-shot all-reduce over peer memory (ctl mode only); world_size <= 1: off
   SwarmPeerExchange peers;
   float* grad_rw;          // same buffer as `grad` (gradient + loss), written back after the exchange
+  // reduce_clip_adam_kernel only: the gradient kernel's per-CTA partials
+  const float* partials;   // [n_ctas][kPartialStride]
+  int32_t n_ctas;
+  int32_t n_graphs;
+  float loss_scale;
 };
+
+constexpr int kAdamPer = (SWARM_W_COUNT + 1 + 255) / 256;      // elements per thread; + 1: the loss rides along
+
+// torch.nn.utils.clip_grad_norm_: norms = [||g_t||_2 for each parameter tensor]; total = ||norms||_2.  g_[i] is element
+// tid + 256 i of the gradient (0 beyond it); returns the clip coefficient on every thread (one block barrier inside).
+// Shared by the two clip + Adam kernels so that both form the sums in the same order.
+__device__ __forceinline__ float clip_coefficient(const float (&g_)[kAdamPer], double (&swarp)[8][8], float& s_coef,
+                                                  float max_norm, float* grad_norm_out, bool pre_synced = false) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int seg_off[9] = {SWARM_W_CONV_LIN, SWARM_W_ATT_SRC, SWARM_W_ATT_DST, SWARM_W_CONV_BIAS, SWARM_W_LIN1,
+                          SWARM_W_LIN1_BIAS, SWARM_W_LIN2, SWARM_W_LIN2_BIAS, SWARM_W_COUNT};
+#pragma unroll
+  for (int sgi = 0; sgi < 8; ++sgi) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < kAdamPer; ++i) {
+      const int o = tid + 256 * i;
+      if (o >= seg_off[sgi] && o < seg_off[sgi + 1]) acc += (double)g_[i] * (double)g_[i];
+    }
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+    if (lane == 0) swarp[sgi][warp] = acc;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int sgi = 0; sgi < 8; ++sgi) {
+      double ss = 0.0;
+      for (int w = 0; w < 8; ++w) ss += swarp[sgi][w];
+      const float nrm = (float)sqrt(ss);
+      tot += (double)nrm * (double)nrm;
+    }
+    const float total_norm = (float)sqrt(tot);
+    float coef = 1.0f;
+    if (max_norm > 0.0f) {
+      coef = max_norm / (total_norm + 1e-6f);
+      coef = coef > 1.0f ? 1.0f : coef;
+    }
+    s_coef = coef;
+    if (grad_norm_out) grad_norm_out[0] = total_norm;
+  }
+  __syncthreads();
+  return s_coef;
+}
+
+// one Adam step of one element, op for op as torch.optim.Adam (single-tensor path)
+struct AdamScalars {
+  float lerp_w, beta2, one_minus_beta2, neg_step_size, bc2_sqrt, eps;
+};
+__device__ __forceinline__ void adam_element(const AdamScalars& a, float g, float coef, float& m_io, float& v_io, float& w_io) {
+  const float gval = __fmul_rn(g, coef);
+  // exp_avg.lerp_(grad, 1 - beta1)
+  const float m = __fadd_rn(m_io, __fmul_rn(a.lerp_w, __fsub_rn(gval, m_io)));
+  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
+  float v = __fmul_rn(v_io, a.beta2);
+  v = __fadd_rn(v, __fmul_rn(__fmul_rn(a.one_minus_beta2, gval), gval));
+  // denom = sqrt(v) / sqrt(bias_correction2) + eps ; param.addcdiv_(exp_avg, denom, value = -step_size)
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), a.bc2_sqrt), a.eps);
+  w_io = __fadd_rn(w_io, __fdiv_rn(__fmul_rn(a.neg_step_size, m), denom));
+  m_io = m;
+  v_io = v;
+}
+
+__device__ __forceinline__ void train_ctl_advance(SwarmTrainCtl* ctl, int num_envs, long long capacity, bool stepped) {
+  ctl->tick += 1;
+  ctl->ring_cursor = (ctl->ring_cursor + num_envs) % capacity;
+  const long long sz = ctl->ring_size + num_envs;
+  ctl->ring_size = sz < capacity ? sz : capacity;
+  if (stepped) ctl->opt_step += 1;
+}
 
 // one naturally aligned 64-bit word = (epoch << 32 | float bits): single-copy atomic, so the word itself is the flag
 __device__ __forceinline__ void st_relaxed_sys_u64(uint64_t* p, uint64_t v) {
@@ -531,9 +608,7 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
   __shared__ double swarp[8][8];            // [segment][warp] partial sums of squares
   __shared__ float s_coef, s_neg_step, s_bc2_sqrt;
   __shared__ int s_update, s_sync;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int seg_off[9] = {SWARM_W_CONV_LIN, SWARM_W_ATT_SRC, SWARM_W_ATT_DST, SWARM_W_CONV_BIAS, SWARM_W_LIN1,
-                          SWARM_W_LIN1_BIAS, SWARM_W_LIN2, SWARM_W_LIN2_BIAS, SWARM_W_COUNT};
+  const int tid = threadIdx.x;
   if (p.ctl && tid == 255) {
     // step-dependent scalars from the device cursor (overlaps with the norm sums of the other threads)
     const long long step = p.ctl->opt_step + 1;
@@ -546,7 +621,7 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
   }
   // every thread owns the elements tid, tid + 256, ...: one round trip to memory for grad / m / v / w, everything
   // else from registers
-  constexpr int kPer = (SWARM_W_COUNT + 1 + 255) / 256;      // + 1: the loss rides along in the exchange
+  constexpr int kPer = kAdamPer;                             // + 1: the loss rides along in the exchange
   float g_[kPer], m_[kPer], v_[kPer], w_[kPer];
 #pragma unroll
   for (int i = 0; i < kPer; ++i) {
@@ -624,77 +699,112 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
       }
     }
   }
-  // torch.nn.utils.clip_grad_norm_: norms = [||g_t||_2 for each parameter tensor]; total = ||norms||_2
-#pragma unroll
-  for (int sgi = 0; sgi < 8; ++sgi) {
-    double acc = 0.0;
-#pragma unroll
-    for (int i = 0; i < kPer; ++i) {
-      const int o = tid + 256 * i;
-      if (o >= seg_off[sgi] && o < seg_off[sgi + 1]) acc += (double)g_[i] * (double)g_[i];
-    }
-#pragma unroll
-    for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
-    if (lane == 0) swarp[sgi][warp] = acc;
-  }
   __syncthreads();
   if (p.ctl) {
     p.neg_step_size = s_neg_step;
     p.bc2_sqrt = s_bc2_sqrt;
     if (!s_sync) p.target = nullptr;
     if (!s_update) {
-      if (tid == 0) {
-        p.ctl->tick += 1;
-        p.ctl->ring_cursor = (p.ctl->ring_cursor + p.num_envs) % p.ring_capacity;
-        const long long sz = p.ctl->ring_size + p.num_envs;
-        p.ctl->ring_size = sz < p.ring_capacity ? sz : p.ring_capacity;
-      }
+      if (tid == 0) train_ctl_advance(p.ctl, p.num_envs, p.ring_capacity, false);
       return;
     }
   }
-  if (tid == 0) {
-    double tot = 0.0;
-    for (int sgi = 0; sgi < 8; ++sgi) {
-      double ss = 0.0;
-      for (int w = 0; w < 8; ++w) ss += swarp[sgi][w];
-      const float nrm = (float)sqrt(ss);
-      tot += (double)nrm * (double)nrm;
-    }
-    const float total_norm = (float)sqrt(tot);
-    float coef = 1.0f;
-    if (p.max_norm > 0.0f) {
-      coef = p.max_norm / (total_norm + 1e-6f);
-      coef = coef > 1.0f ? 1.0f : coef;
-    }
-    s_coef = coef;
-    if (p.grad_norm) p.grad_norm[0] = total_norm;
-  }
-  __syncthreads();
-  const float coef = s_coef;
+  const float coef = clip_coefficient(g_, swarp, s_coef, p.max_norm, p.grad_norm);
+  const AdamScalars sc{p.lerp_w, p.beta2, p.one_minus_beta2, p.neg_step_size, p.bc2_sqrt, p.eps};
 #pragma unroll
   for (int i = 0; i < kPer; ++i) {
     const int o = tid + 256 * i;
     if (o >= SWARM_W_COUNT) break;
-    const float gval = __fmul_rn(g_[i], coef);
-    // exp_avg.lerp_(grad, 1 - beta1)
-    const float m = __fadd_rn(m_[i], __fmul_rn(p.lerp_w, __fsub_rn(gval, m_[i])));
-    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
-    float v = __fmul_rn(v_[i], p.beta2);
-    v = __fadd_rn(v, __fmul_rn(__fmul_rn(p.one_minus_beta2, gval), gval));
-    // denom = sqrt(v) / sqrt(bias_correction2) + eps ; param.addcdiv_(exp_avg, denom, value = -step_size)
-    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), p.bc2_sqrt), p.eps);
-    const float w = __fadd_rn(w_[i], __fdiv_rn(__fmul_rn(p.neg_step_size, m), denom));
+    adam_element(sc, g_[i], coef, m_[i], v_[i], w_[i]);
+    p.m[o] = m_[i];
+    p.v[o] = v_[i];
+    p.w[o] = w_[i];
+    if (p.target) p.target[o] = w_[i];
+  }
+  if (p.ctl && tid == 0) train_ctl_advance(p.ctl, p.num_envs, p.ring_capacity, true);
+}
+
+// ---- partial reduction + clip + Adam as ONE launch (swarm_train_tick on one GPU) ----------------------------------
+// The two small launches at the end of a tick (dqn_reduce_kernel on 7 CTAs, adam_clip_kernel on one) as a single
+// thread-block cluster of 7 working CTAs x 256 threads (launched as the portable size 8; the last CTA only joins the
+// barrier), one gradient element per thread:
+//   1. element o = 256 c + t: the sum of the gradient kernel's partials in CTA order (dqn_reduce_kernel's sum);
+//   2. every CTA pushes its 256 sums into the shared memory of all seven (distributed shared memory), one cluster
+//      barrier, and every CTA holds the whole gradient laid out as adam_clip_kernel's registers are ([i][tid]), so the
+//      clip coefficient is formed by the same code in the same order on every CTA -- no second exchange;
+//   3. Adam on the CTA's own 256 elements; CTA 0 advances the device cursor.
+// Same bits as the two launches.  A single CTA cannot do step 1 at this speed: the 32 x 6.7 KB of partials through one
+// SM's L2 port cost as much as the launch they would save (tried: 34.8 vs 34.6 us per tick).
+constexpr int kAdamCluster = 8;
+static_assert(kAdamPer <= kAdamCluster, "one CTA per 256 gradient elements");
+__global__ void __cluster_dims__(kAdamCluster, 1, 1) __launch_bounds__(256) reduce_clip_adam_kernel(AdamParams p) {
+  namespace cg = cooperative_groups;
+  __shared__ float sg[kAdamPer][256];
+  __shared__ double swarp[8][8];
+  __shared__ float s_coef, s_neg_step, s_bc2_sqrt;
+  __shared__ int s_sync;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x, c = (int)cluster.block_rank();
+  if (c >= kAdamPer) {
+    cluster.sync();
+    return;
+  }
+  const int o = 256 * c + tid;
+  const bool upd = train_ring_size(p.ctl, p.num_envs, p.ring_capacity) >= p.n_graphs;
+  if (tid == 255) {
+    const long long step = p.ctl->opt_step + 1;
+    const double bc1 = 1.0 - pow(p.beta1, (double)step);
+    const double bc2 = 1.0 - pow(p.beta2d, (double)step);
+    s_neg_step = (float)(-(p.lr / bc1));
+    s_bc2_sqrt = (float)sqrt(bc2);
+    s_sync = ((p.ctl->tick + 1) % p.update_target_every) == 0;
+  }
+  const bool in = o < SWARM_W_COUNT;
+  float m = in ? p.m[o] : 0.0f, v = in ? p.v[o] : 0.0f, w = in ? p.w[o] : 0.0f;
+  float g = 0.0f;
+  if (upd && o <= SWARM_W_COUNT) {
+    const float* src = p.partials + o;
+    constexpr int kBatch = 32;       // the reference's 32 graphs: one CTA each, all partials of an element in flight
+    for (int b0 = 0; b0 < p.n_ctas; b0 += kBatch) {
+      float part[kBatch];
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) part[b] = (b0 + b < p.n_ctas) ? __ldcg(src + (size_t)(b0 + b) * kPartialStride) : 0.0f;
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b)
+        if (b0 + b < p.n_ctas) g += part[b];
+    }
+    if (o == SWARM_W_COUNT) {
+      p.grad_rw[o] = g * p.loss_scale;      // the loss, for the caller's statistics
+      g = 0.0f;
+    } else {
+      p.grad_rw[o] = g;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kAdamPer; ++r) *cluster.map_shared_rank(&sg[c][tid], r) = g;
+  cluster.sync();       // every read of *ctl above precedes CTA 0's writes below
+  if (!upd) {
+    if (c == 0 && tid == 0) {
+      p.ctl->updating = 0;
+      train_ctl_advance(p.ctl, p.num_envs, p.ring_capacity, false);
+    }
+    return;
+  }
+  float g_[kAdamPer];
+#pragma unroll
+  for (int i = 0; i < kAdamPer; ++i) g_[i] = sg[i][tid];
+  const float coef = clip_coefficient(g_, swarp, s_coef, p.max_norm, c == 0 ? p.grad_norm : nullptr);
+  if (in) {
+    const AdamScalars sc{p.lerp_w, p.beta2, p.one_minus_beta2, s_neg_step, s_bc2_sqrt, p.eps};
+    adam_element(sc, g, coef, m, v, w);
     p.m[o] = m;
     p.v[o] = v;
     p.w[o] = w;
-    if (p.target) p.target[o] = w;
+    if (s_sync && p.target) p.target[o] = w;
   }
-  if (p.ctl && tid == 0) {
-    p.ctl->tick += 1;
-    p.ctl->ring_cursor = (p.ctl->ring_cursor + p.num_envs) % p.ring_capacity;
-    const long long sz = p.ctl->ring_size + p.num_envs;
-    p.ctl->ring_size = sz < p.ring_capacity ? sz : p.ring_capacity;
-    p.ctl->opt_step += 1;
+  if (c == 0 && tid == 0) {
+    p.ctl->updating = 1;
+    train_ctl_advance(p.ctl, p.num_envs, p.ring_capacity, true);
   }
 }
 
@@ -1096,7 +1206,7 @@ int dqn_smem_bytes(const SwarmConfig& c) {
 cudaError_t launch_dqn_grad(const SwarmConfig& c, const float* w_online, const float* w_target, const SwarmReplay& batch,
                             const int64_t* indices, int n_graphs, float gamma, float loss_scale, float* grad, float* loss,
                             float* td, void* workspace, cudaStream_t stream, SwarmTrainCtl* ctl, int64_t* indices_out,
-                            unsigned long long sample_seed, int pushed_envs) {
+                            unsigned long long sample_seed, int pushed_envs, bool skip_reduce) {
   DqnParams p;
   p.ctl = ctl;
   p.indices_out = indices_out;
@@ -1127,16 +1237,38 @@ cudaError_t launch_dqn_grad(const SwarmConfig& c, const float* w_online, const f
     if (err != cudaSuccess) return err;
     dqn_grad_kernel<<<ctas, kTileThreads, smem, stream>>>(p);
   }
-  dqn_reduce_kernel<<<(SWARM_W_COUNT + 1 + 255) / 256, 256, 0, stream>>>(p.partials, ctas, loss_scale, grad, loss, ctl,
-                                                                         pushed_envs, batch.capacity, n_graphs);
+  // skip_reduce: the caller sums the partials inside launch_reduce_clip_adam
+  if (!skip_reduce)
+    dqn_reduce_kernel<<<(SWARM_W_COUNT + 1 + 255) / 256, 256, 0, stream>>>(p.partials, ctas, loss_scale, grad, loss, ctl,
+                                                                           pushed_envs, batch.capacity, n_graphs);
   return cudaGetLastError();
+}
+
+// The cluster launch sums an element's partials on one thread, 32 loads in flight: a win over the reduce launch while
+// the gradient kernel ran on few CTAs (the reference's 32 graphs: 33.2 vs 34.8 us per tick); for the 410 CTAs of a
+// 4 096-graph update seven SMs pull 2.7 MB and the tick is slower (69 vs 63.6 us), so those keep the separate launches.
+bool dqn_fuse_reduce(const SwarmConfig& c, int n_graphs) {
+  const int epb = dqn_epb(c, n_graphs);
+  return (n_graphs + epb - 1) / epb <= 64;
 }
 
 cudaError_t launch_adam_clip(float* w, const float* grad, float* m, float* v, long long step, double lr, double beta1,
                              double beta2, double eps, double max_norm, float* target, float* grad_norm,
                              cudaStream_t stream, SwarmTrainCtl* ctl, int num_envs, long long ring_capacity,
-                             int update_target_every, const SwarmPeerExchange* peers, float* grad_rw) {
+                             int update_target_every, const SwarmPeerExchange* peers, float* grad_rw,
+                             const SwarmConfig* reduce_cfg, const void* reduce_workspace, int reduce_graphs,
+                             float loss_scale) {
   AdamParams p;
+  p.partials = nullptr;
+  p.n_ctas = 0;
+  p.n_graphs = reduce_graphs;
+  p.loss_scale = loss_scale;
+  if (reduce_workspace && reduce_cfg && ctl && dqn_fuse_reduce(*reduce_cfg, reduce_graphs)) {
+    // the partials of launch_dqn_grad(..., skip_reduce = true) on the same workspace
+    const int epb = dqn_epb(*reduce_cfg, reduce_graphs);
+    p.n_ctas = (reduce_graphs + epb - 1) / epb;
+    p.partials = reinterpret_cast<const float*>((reinterpret_cast<uintptr_t>(reduce_workspace) + 255) & ~(uintptr_t)255);
+  }
   if (peers && ctl) p.peers = *peers;
   else p.peers.world_size = 0;
   p.grad_rw = grad_rw;
@@ -1164,7 +1296,8 @@ cudaError_t launch_adam_clip(float* w, const float* grad, float* m, float* v, lo
   p.bc2_sqrt = (float)sqrt(bc2);
   p.eps = (float)eps;
   p.max_norm = (float)max_norm;
-  if (p.peers.world_size > 1) adam_clip_kernel<true><<<1, 256, 0, stream>>>(p);
+  if (p.partials) reduce_clip_adam_kernel<<<kAdamCluster, 256, 0, stream>>>(p);
+  else if (p.peers.world_size > 1) adam_clip_kernel<true><<<1, 256, 0, stream>>>(p);
   else adam_clip_kernel<false><<<1, 256, 0, stream>>>(p);
   return cudaGetLastError();
 }

@@ -266,9 +266,11 @@ class DQNTrainer:
         nccl = multi and tt.peers is None
 
         def tick():
+            if not nccl:
+                tt.tick(self.w, self.w_target, self.exp_avg, self.exp_avg_sq, world.state, returns, hits)
+                return
             tt.grad_phase(self.w, self.w_target, world.state, returns, hits)
-            if nccl:
-                torch.distributed.all_reduce(tt.grad_loss)
+            torch.distributed.all_reduce(tt.grad_loss)
             tt.apply_phase(self.w, self.w_target, self.exp_avg, self.exp_avg_sq)
 
         graph = None
@@ -419,9 +421,11 @@ class DQNTrainer:
                 # (flocking:101-121), on the device: the same reset launch the host-side reset_world_at issues
                 ops.scenario_reward(flock_spec, world.state, env.scenario.shaping, reset=True)
             for _ in range(env.max_steps):
+                if not nccl:
+                    tt.tick(self.w, self.w_target, self.exp_avg, self.exp_avg_sq, world.state, returns, hits)
+                    continue
                 tt.grad_phase(self.w, self.w_target, world.state, returns, hits)
-                if nccl:
-                    torch.distributed.all_reduce(tt.grad_loss)
+                torch.distributed.all_reduce(tt.grad_loss)
                 tt.apply_phase(self.w, self.w_target, self.exp_avg, self.exp_avg_sq)
             tt.episode_end(returns, hits, stats, config["epsilon"], config["epsilon_decay"], config["min_epsilon"])
 

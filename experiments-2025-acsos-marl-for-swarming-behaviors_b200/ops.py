@@ -448,6 +448,17 @@ class TrainTick:
                                            ptr(exp_avg), ptr(exp_avg_sq), ptr(self.grad_loss), self.ring.capacity, peers,
                                            stream_ptr(weights.device)))
 
+    def tick(self, weights: torch.Tensor, target: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
+             state: torch.Tensor, returns: torch.Tensor, hits: torch.Tensor) -> None:
+        """``grad_phase`` + ``apply_phase`` as one library call (swarm_train_tick): the same bits, one launch less per
+        tick for small update batches (the partial gradients are summed inside the clip + Adam kernel).  For trainers
+        that need nothing between the phases: one GPU, or ``self.peers`` set."""
+        peers = C.byref(self.peers.struct) if self.peers is not None else None
+        check(lib().swarm_train_tick(C.byref(self.cfg), C.byref(self.hyper), ptr(self.ctl), ptr(weights), ptr(target),
+                                     ptr(exp_avg), ptr(exp_avg_sq), ptr(state), ptr(returns), ptr(hits),
+                                     C.byref(self._rstruct), ptr(self.indices), ptr(self.grad_loss), ptr(self.workspace),
+                                     self._ws_bytes, peers, stream_ptr(state.device)))
+
 
 def csr_from_edges(edge_index: torch.Tensor, n_nodes: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """edge_index int64[2,E] -> (row_ptr int32[n+1], src int32[E], perm int32[E]), edges grouped by target,

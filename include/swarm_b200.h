@@ -402,6 +402,20 @@ int swarm_train_tick_apply(const SwarmConfig* cfg, const SwarmTrainHyper* hyper,
                            float* target_weights, float* exp_avg, float* exp_avg_sq, float* grad,
                            int64_t ring_capacity, const SwarmPeerExchange* peers, void* stream);
 
+/* Both phases as one call, for trainers that need nothing between them (one GPU, or the fused peer exchange): the same
+ * loop body (train_gcn_dqn.py:153-178) and the same bits as swarm_train_tick_grad followed by swarm_train_tick_apply.
+ * On one GPU, when the gradient kernel ran on at most 64 CTAs (the reference's 32 graphs per update: one CTA each), the
+ * two small launches at the end of the tick (sum of the gradient kernel's per-CTA partials; clip + Adam) run as ONE
+ * thread-block cluster -- the partials are summed in CTA order as before, the sums are exchanged through
+ * distributed shared memory, every CTA forms the clip coefficient in the same order and steps its 256 elements --
+ * three launches per tick instead of four.  `grad` is float[1674] (gradient followed by the loss; written for the
+ * caller's statistics, summed over the ranks with `peers`); `workspace` as for swarm_train_tick_grad; `ring->capacity`
+ * is the ring_capacity of the apply phase. */
+int swarm_train_tick(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, SwarmTrainCtl* ctl, float* weights,
+                     float* target_weights, float* exp_avg, float* exp_avg_sq, float* state, float* returns,
+                     int32_t* hits, const SwarmReplay* ring, int64_t* indices, float* grad, void* workspace,
+                     int64_t workspace_bytes, const SwarmPeerExchange* peers, void* stream);
+
 /* ---- device-side episode boundary -------------------------------------------------------
  * The reference resets with one CPU torch.normal draw per episode (go_to:84-88, oa:100-102) and does its episode
  * bookkeeping in Python (train:179-199).  These two calls keep both on the device so that reset + max_steps ticks +

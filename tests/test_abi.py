@@ -164,6 +164,18 @@ def test_training_argument_validation_without_device(sb):
     assert b"peer exchange" in lib.swarm_last_error()
     px.rank = 1                                                        # NULL peer buffers
     assert lib.swarm_train_tick_apply(C.byref(cfg), C.byref(h), 8, 8, 8, 8, 8, 8, 1000, C.byref(px), None) == -1
+    # the one-call tick: both phases' checks
+    one = lambda peers: lib.swarm_train_tick(C.byref(cfg), C.byref(h), 8, 8, 8, 8, 8, 8, None, None, C.byref(ring), None, 8, 8,
+                                             1 << 30, peers, None)
+    assert one(C.byref(px)) == -1 and b"peer exchange" in lib.swarm_last_error()
+    h.graphs_per_update = 0
+    assert one(None) == -1 and b"graphs_per_update" in lib.swarm_last_error()
+    h.graphs_per_update = 32
+    ring.capacity = 10
+    assert one(None) == -1 and b"capacity" in lib.swarm_last_error()
+    ring.capacity = 1000
+    assert lib.swarm_train_tick(C.byref(cfg), C.byref(h), 8, 8, 8, 8, 8, 8, None, None, C.byref(ring), None, 8, 8, 16, None,
+                                None) == -1 and b"workspace" in lib.swarm_last_error()
     # reset / episode end
     sp = sb.ops.reset_spec(L.SCENARIO_GOTO)
     assert (sp.base_x, sp.base_y, sp.mean_x, sp.mean_y) == (1.5, -1.5, pytest.approx(-0.6), pytest.approx(0.6))   # go_to:84-88

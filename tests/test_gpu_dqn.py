@@ -257,6 +257,48 @@ def test_train_tick_matches_composed_calls(B, N, G, capacity):
     assert tt.indices.unique().numel() > G // 2
 
 
+@pytest.mark.parametrize("B,N,G,capacity,graph", [(64, 12, 32, 1000, "complete"), (16, 5, 32, 40, "complete"),
+                                                   (64, 12, 32, 1000, "knn"), (256, 12, 1024, 4096, "complete")])
+def test_one_call_tick_equals_the_two_phases(B, N, G, capacity, graph):
+    """swarm_train_tick (partials summed inside clip + Adam for <= 64 gradient CTAs, else the reduce launch) leaves the
+    same bits as swarm_train_tick_grad + swarm_train_tick_apply: state, ring, cursor, gradient, loss, moments, weights,
+    over 'not enough samples' ticks, updates, the ring wrap-around and target syncs."""
+    import swarm_b200 as sb
+    from swarm_b200 import ops
+    dev = _dev()
+    cfg, state_a, w_a, ring_a = _tick_setup(sb, B, N, G, capacity, sb._lib.SCENARIO_OBSTACLE_AVOIDANCE)
+    if graph == "knn":
+        cfg = ops.clone_config(cfg, graph_mode=sb._lib.GRAPH_KNN, knn_k=5)
+    ring_b = ops.ReplayRing(capacity, N, dev)
+    state_b, w_b = state_a.clone(), w_a.clone()
+
+    def track(ring):
+        tt = ops.TrainTick(cfg, ring, graphs_per_update=G, update_target_every=3, rng_seed=11, sample_seed=5, env_offset=7)
+        tt.load_cursor(0, 0, 0.4)
+        return tt
+    tt_a, tt_b = track(ring_a), track(ring_b)
+    bufs = lambda w: (w.clone(), torch.zeros_like(w), torch.zeros_like(w), torch.zeros(B, N, device=dev),
+                      torch.zeros(B, dtype=torch.int32, device=dev))
+    wt_a, m_a, v_a, ret_a, hits_a = bufs(w_a)
+    wt_b, m_b, v_b, ret_b, hits_b = bufs(w_b)
+    updates = 0
+    for tick in range(1, 13):
+        tt_a.grad_phase(w_a, wt_a, state_a, ret_a, hits_a)
+        tt_a.apply_phase(w_a, wt_a, m_a, v_a)
+        tt_b.tick(w_b, wt_b, m_b, v_b, state_b, ret_b, hits_b)
+        ca, cb = tt_a.read_cursor(), tt_b.read_cursor()
+        assert ca == cb and ca["tick"] == tick
+        updates += ca["updating"]
+        pairs = [(state_a, state_b), (ret_a, ret_b), (hits_a, hits_b), (w_a, w_b), (wt_a, wt_b), (m_a, m_b), (v_a, v_b),
+                 (ring_a.state, ring_b.state), (ring_a.actions, ring_b.actions), (ring_a.rewards, ring_b.rewards),
+                 (tt_a.indices, tt_b.indices)]
+        if ca["updating"]:
+            pairs.append((tt_a.grad_loss, tt_b.grad_loss))
+        for x, y in pairs:
+            assert torch.equal(x, y), tick
+    assert updates >= 8 and ca["opt_step"] == updates
+
+
 def test_train_model_batched_graph_equals_eager():
     """An episode replayed from the captured CUDA graph gives bit-identical weights to eager launches."""
     import swarm_b200 as sb
