@@ -597,8 +597,8 @@ def measure_dqn(sb, ops, dev, cfg, weights, centers, dist, barrier, stream, rank
 "graphs_per_update_per_gpu": G, "updates_per_s": ticks / (ms * 1e-3),
                         "train_agent_steps_per_s": world * B * N * ticks / (ms * 1e-3),
                         "transitions_trained_per_s": world * G * ticks / (ms * 1e-3), "ms_per_tick": ms / ticks,
-                        "ms_per_tick_eager": ms_eager / ticks, "kernels_per_tick": 4 + (1 if nccl else 0),
-                        "grad_allreduce": ("none" if world == 1 else ("nccl" if nccl else "fused into clip+Adam over NVLink peer memory")),
+                        "ms_per_tick_eager": ms_eager / ticks, "kernels_per_tick": 5 if nccl else (3 if G <= 64 else 4),
+                        "grad_allreduce": ("none" if world == 1 else ("nccl" if nccl else "one-shot push over NVLink peer memory inside the reduce + clip + Adam launch")),
                         "ticks_done": cur["tick"], "opt_steps_done": cur["opt_step"], "loss": float(tt.loss.item())}
     out["note"] = ("one train tick = rollout tick of all envs (eps 0.3) + replay push + on-device sample + TD target/loss/"
                    "backward + grad all-reduce (N>1) + clip + Adam (+ target sync every 200 ticks); %d ticks captured in "

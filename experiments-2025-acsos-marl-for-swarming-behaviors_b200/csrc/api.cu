@@ -724,9 +724,9 @@ int swarm_train_tick(const SwarmConfig* cfg, const SwarmTrainHyper* hyper, Swarm
                                   "swarm_train_tick(rollout)"))
     return rc;
   const int G = hyper->graphs_per_update;
-  // one GPU, gradient kernel on few CTAs: partial reduction + clip + Adam as one cluster launch; with a peer exchange
-  // or a large update batch the reduce launch and the (exchanging) clip + Adam kernel
-  const bool fuse = !(peers && peers->world_size > 1) && dqn_fuse_reduce(*cfg, G);
+  // gradient kernel on few CTAs: partial reduction (+ peer exchange) + clip + Adam as one cluster launch; a large update
+  // batch keeps the reduce launch and the single-CTA clip + Adam kernel
+  const bool fuse = dqn_fuse_reduce(*cfg, G);
   if (int rc = check_cuda(launch_dqn_grad(*cfg, weights, target_weights, *ring, nullptr, G, hyper->gamma, hyper->loss_scale,
                                           grad, grad + SWARM_W_COUNT, nullptr, workspace, st, ctl, indices,
                                           hyper->sample_seed, cfg->num_envs, fuse),

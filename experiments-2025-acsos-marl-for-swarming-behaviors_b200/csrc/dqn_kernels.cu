@@ -737,6 +737,10 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
 // SM's L2 port cost as much as the launch they would save (tried: 34.8 vs 34.6 us per tick).
 constexpr int kAdamCluster = 8;
 static_assert(kAdamPer <= kAdamCluster, "one CTA per 256 gradient elements");
+// PEERS: the one-shot PUSH all-reduce of adam_clip_kernel<true> (same slots, same words, same rank-order sums -- see
+// there), with one element per thread: every thread pushes ONE word per peer and polls world_size local words, all in
+// flight together, and the seven CTAs use seven SMs' worth of NVLink store and poll bandwidth.
+template <bool PEERS>
 __global__ void __cluster_dims__(kAdamCluster, 1, 1) __launch_bounds__(256) reduce_clip_adam_kernel(AdamParams p) {
   namespace cg = cooperative_groups;
   __shared__ float sg[kAdamPer][256];
@@ -773,12 +777,34 @@ __global__ void __cluster_dims__(kAdamCluster, 1, 1) __launch_bounds__(256) redu
       for (int b = 0; b < kBatch; ++b)
         if (b0 + b < p.n_ctas) g += part[b];
     }
-    if (o == SWARM_W_COUNT) {
-      p.grad_rw[o] = g * p.loss_scale;      // the loss, for the caller's statistics
+    if (o == SWARM_W_COUNT) g *= p.loss_scale;      // the loss rides along (exchange, caller's statistics)
+    if (PEERS) {
+      const uint32_t epoch = (uint32_t)(p.ctl->tick + 1);
+      const int W = p.peers.world_size;
+      const size_t par_base = (size_t)(epoch & 1u) * W * SWARM_XCHG_STRIDE;
+      const uint64_t word = ((uint64_t)epoch << 32) | (uint64_t)__float_as_uint(g);
+      for (int q = 0; q < W; ++q) {
+        const int peer = (p.peers.rank + q) % W;            // own buffer first, then ring order: spreads the links
+        st_relaxed_sys_u64(p.peers.data[peer] + par_base + (size_t)p.peers.rank * SWARM_XCHG_STRIDE + o, word);
+      }
+      const uint64_t* mine = p.peers.data[p.peers.rank] + par_base + o;
+      uint64_t got[SWARM_MAX_PEERS];
+      bool ok = false;
+      for (long long it = 0; it < (1ll << 26) && !ok; ++it) {       // bounded: a lost peer traps instead of hanging
+        ok = true;
+#pragma unroll
+        for (int r = 0; r < SWARM_MAX_PEERS; ++r)
+          got[r] = (r < W) ? ld_relaxed_sys_u64(mine + (size_t)r * SWARM_XCHG_STRIDE) : ((uint64_t)epoch << 32);
+#pragma unroll
+        for (int r = 0; r < SWARM_MAX_PEERS; ++r) ok = ok && ((uint32_t)(got[r] >> 32) == epoch);
+      }
+      if (!ok) __trap();
       g = 0.0f;
-    } else {
-      p.grad_rw[o] = g;
+#pragma unroll
+      for (int r = 0; r < SWARM_MAX_PEERS; ++r) g += __uint_as_float((uint32_t)got[r]);     // rank order; absent ranks add +0
     }
+    p.grad_rw[o] = g;
+    if (o == SWARM_W_COUNT) g = 0.0f;
   }
 #pragma unroll
   for (int r = 0; r < kAdamPer; ++r) *cluster.map_shared_rank(&sg[c][tid], r) = g;
@@ -1296,7 +1322,8 @@ cudaError_t launch_adam_clip(float* w, const float* grad, float* m, float* v, lo
   p.bc2_sqrt = (float)sqrt(bc2);
   p.eps = (float)eps;
   p.max_norm = (float)max_norm;
-  if (p.partials) reduce_clip_adam_kernel<<<kAdamCluster, 256, 0, stream>>>(p);
+  if (p.partials && p.peers.world_size > 1) reduce_clip_adam_kernel<true><<<kAdamCluster, 256, 0, stream>>>(p);
+  else if (p.partials) reduce_clip_adam_kernel<false><<<kAdamCluster, 256, 0, stream>>>(p);
   else if (p.peers.world_size > 1) adam_clip_kernel<true><<<1, 256, 0, stream>>>(p);
   else adam_clip_kernel<false><<<1, 256, 0, stream>>>(p);
   return cudaGetLastError();

@@ -37,7 +37,7 @@ def _worker(rank, world, port, out):
     pre = "ObstacleAvoidance/0/"
     w0 = sb.pack_weights({k[len(pre):]: torch.from_numpy(models[k]) for k in models.files if k.startswith(pre)}, dev)
     res = {}
-    for mode in ("nccl", "peer", "peer_graph"):
+    for mode in ("nccl", "peer", "peer_graph", "peer_one_call"):
         g = torch.Generator().manual_seed(rank)
         centers = (torch.tensor([0.6, -0.6]) + 0.1 * torch.randn(B, 2, generator=g)).to(dev)
         state = ops.reset_grid(cfg, centers)
@@ -53,6 +53,9 @@ def _worker(rank, world, port, out):
             tt.peers = parallel.PeerExchange(dev)
 
         def tick():
+            if mode == "peer_one_call":     # swarm_train_tick: reduction + exchange + clip + Adam as one cluster launch
+                tt.tick(w, w_t, m, v, state, returns, hits)
+                return
             tt.grad_phase(w, w_t, state, returns, hits)
             if mode == "nccl":
                 dist.all_reduce(tt.grad_loss)
@@ -80,8 +83,9 @@ def _worker(rank, world, port, out):
         gathered = [torch.empty_like(w) for _ in range(world)]
         dist.all_gather(gathered, w)
         assert all(torch.equal(gathered[0], x) for x in gathered), f"{mode}: ranks diverged"
-    for x, y in zip(res["peer"], res["peer_graph"]):
-        assert torch.equal(x, y), f"peer vs peer_graph differ: {(x - y).abs().max().item():.3e}"
+    for other in ("peer_graph", "peer_one_call"):
+        for x, y in zip(res["peer"], res[other]):
+            assert torch.equal(x, y), f"peer vs {other} differ: {(x - y).abs().max().item():.3e}"
     for x, y in zip(res["nccl"], res["peer"]):
         if world == 2:
             assert torch.equal(x, y), f"nccl vs peer differ: {(x - y).abs().max().item():.3e}"
