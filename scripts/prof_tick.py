@@ -20,7 +20,6 @@ returns = torch.zeros(B, N, device=dev); hits = torch.zeros(B, dtype=torch.int32
 tt = ops.TrainTick(cfg, ring, graphs_per_update=G)
 tt.load_cursor(0, 0, 0.3)
 for _ in range(12):
-    tt.grad_phase(w, w_t, state, returns, hits)
-    tt.apply_phase(w, w_t, m, v)
+    tt.tick(w, w_t, m, v, state, returns, hits)
 torch.cuda.synchronize()
 print('ok', tt.read_cursor())
