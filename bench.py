@@ -368,7 +368,7 @@ def measure_extra(sb, ops, dev):
 
     w_oa, w_goto = weights("ObstacleAvoidance/0/"), weights("GoTo/0/")
 
-    def rollout_rate(scen, B, N, graph, k, ticks, reps=3):
+    def rollout_rate(scen, B, N, graph, k, ticks, reps=3, fresh_memo=True):
         # kNN rows: the memo table of boundary-tie patterns (ops.knn_memo_table) is cleared before every timed launch, so
         # the figure is that of a first encounter with these states, not of a replay of a remembered episode
         cfg = ops.make_config(scen, B, N, graph, k)
@@ -381,7 +381,7 @@ def measure_extra(sb, ops, dev):
         ms = 0.0
         for _ in range(reps):
             ops.reset_grid(cfg, centers, out=state)
-            if graph == L.GRAPH_KNN and N <= 12:
+            if graph == L.GRAPH_KNN and N <= 12 and fresh_memo:
                 ops.knn_memo_table(dev, N, k, fresh=True)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -393,6 +393,9 @@ def measure_extra(sb, ops, dev):
 
     out = {"unit": "agent-steps/s"}
     out["c2_knn_k5"] = rollout_rate(L.SCENARIO_OBSTACLE_AVOIDANCE, ENVS_PER_GPU, N_AGENTS, L.GRAPH_KNN, 5, TICKS)
+    # the same launches with the memo table kept between them (what a Simulator running episode after episode sees)
+    out["c2_knn_k5_warm_memo_table"] = rollout_rate(L.SCENARIO_OBSTACLE_AVOIDANCE, ENVS_PER_GPU, N_AGENTS, L.GRAPH_KNN, 5,
+                                                    TICKS, fresh_memo=False)
     sweep = {}
     for n in (5, 8, 12):
         sweep[f"N{n}_complete"] = rollout_rate(L.SCENARIO_GOTO, 65536, n, L.GRAPH_COMPLETE, 5, 50)
