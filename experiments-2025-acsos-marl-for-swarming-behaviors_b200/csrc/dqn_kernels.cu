@@ -544,14 +544,21 @@ __device__ __forceinline__ float clip_coefficient(const float (&g_)[kAdamPer], d
     if (lane == 0) swarp[sgi][warp] = acc;
   }
   __syncthreads();
-  if (tid == 0) {
-    double tot = 0.0;
-    for (int sgi = 0; sgi < 8; ++sgi) {
+  if (tid < 32) {
+    // lane s < 8: the norm of parameter tensor s (its warps' partial sums in warp order); lane 0 then adds the eight
+    // squares in tensor order -- the sums of the serial loop, with the eight tensors' chains side by side
+    double sq = 0.0;
+    if (tid < 8) {
       double ss = 0.0;
-      for (int w = 0; w < 8; ++w) ss += swarp[sgi][w];
+#pragma unroll
+      for (int w = 0; w < 8; ++w) ss += swarp[tid][w];
       const float nrm = (float)sqrt(ss);
-      tot += (double)nrm * (double)nrm;
+      sq = (double)nrm * (double)nrm;
     }
+    double tot = 0.0;
+#pragma unroll
+    for (int sgi = 0; sgi < 8; ++sgi) tot += __shfl_sync(0xffffffffu, sq, sgi);
+    if (tid == 0) {
     const float total_norm = (float)sqrt(tot);
     float coef = 1.0f;
     if (max_norm > 0.0f) {
@@ -560,6 +567,7 @@ __device__ __forceinline__ float clip_coefficient(const float (&g_)[kAdamPer], d
     }
     s_coef = coef;
     if (grad_norm_out) grad_norm_out[0] = total_norm;
+    }
   }
   __syncthreads();
   return s_coef;
@@ -750,23 +758,32 @@ __global__ void __cluster_dims__(kAdamCluster, 1, 1) __launch_bounds__(256) redu
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, c = (int)cluster.block_rank();
   if (c >= kAdamPer) {
+    // the spare CTA of the cluster: the step-dependent scalars (two double-precision pow chains, about a microsecond on
+    // one thread each) computed beside the other CTAs' loads and delivered into their shared memory
+    if (tid == 0 || tid == 32 || tid == 64) {
+      const long long step = p.ctl->opt_step + 1;
+      if (tid == 0) {
+        const float v = (float)(-(p.lr / (1.0 - pow(p.beta1, (double)step))));
+        for (int r = 0; r < kAdamPer; ++r) *cluster.map_shared_rank(&s_neg_step, r) = v;
+      } else if (tid == 32) {
+        const float v = (float)sqrt(1.0 - pow(p.beta2d, (double)step));
+        for (int r = 0; r < kAdamPer; ++r) *cluster.map_shared_rank(&s_bc2_sqrt, r) = v;
+      } else {
+        const int v = ((p.ctl->tick + 1) % p.update_target_every) == 0;
+        for (int r = 0; r < kAdamPer; ++r) *cluster.map_shared_rank(&s_sync, r) = v;
+      }
+    }
     cluster.sync();
     return;
   }
   const int o = 256 * c + tid;
   const bool upd = train_ring_size(p.ctl, p.num_envs, p.ring_capacity) >= p.n_graphs;
-  if (tid == 255) {
-    const long long step = p.ctl->opt_step + 1;
-    const double bc1 = 1.0 - pow(p.beta1, (double)step);
-    const double bc2 = 1.0 - pow(p.beta2d, (double)step);
-    s_neg_step = (float)(-(p.lr / bc1));
-    s_bc2_sqrt = (float)sqrt(bc2);
-    s_sync = ((p.ctl->tick + 1) % p.update_target_every) == 0;
-  }
   const bool in = o < SWARM_W_COUNT;
   float m = in ? p.m[o] : 0.0f, v = in ? p.v[o] : 0.0f, w = in ? p.w[o] : 0.0f;
   float g = 0.0f;
-  if (upd && o <= SWARM_W_COUNT) {
+  if (o <= SWARM_W_COUNT) {
+    // not conditional on `upd`: the loads go out beside the cursor's (a tick that does not update reads stale partials
+    // and drops them)
     const float* src = p.partials + o;
     constexpr int kBatch = 32;       // the reference's 32 graphs: one CTA each, all partials of an element in flight
     for (int b0 = 0; b0 < p.n_ctas; b0 += kBatch) {
@@ -777,6 +794,9 @@ __global__ void __cluster_dims__(kAdamCluster, 1, 1) __launch_bounds__(256) redu
       for (int b = 0; b < kBatch; ++b)
         if (b0 + b < p.n_ctas) g += part[b];
     }
+  }
+  if (!upd) g = 0.0f;
+  if (upd && o <= SWARM_W_COUNT) {
     if (o == SWARM_W_COUNT) g *= p.loss_scale;      // the loss rides along (exchange, caller's statistics)
     if (PEERS) {
       const uint32_t epoch = (uint32_t)(p.ctl->tick + 1);
