@@ -743,6 +743,11 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
 //   3. Adam on the CTA's own 256 elements; CTA 0 advances the device cursor.
 // Same bits as the two launches.  A single CTA cannot do step 1 at this speed: the 32 x 6.7 KB of partials through one
 // SM's L2 port cost as much as the launch they would save (tried: 34.8 vs 34.6 us per tick).
+// split cluster barrier: every CTA arrives when it starts and waits just before its first store into a peer CTA's shared
+// memory -- a CTA must have started executing before its shared memory is written remotely
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 constexpr int kAdamCluster = 8;
 static_assert(kAdamPer <= kAdamCluster, "one CTA per 256 gradient elements");
 // PEERS: the one-shot PUSH all-reduce of adam_clip_kernel<true> (same slots, same words, same rank-order sums -- see
@@ -757,20 +762,25 @@ __global__ void __cluster_dims__(kAdamCluster, 1, 1) __launch_bounds__(256) redu
   __shared__ int s_sync;
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, c = (int)cluster.block_rank();
+  cluster_arrive_relaxed();
   if (c >= kAdamPer) {
     // the spare CTA of the cluster: the step-dependent scalars (two double-precision pow chains, about a microsecond on
     // one thread each) computed beside the other CTAs' loads and delivered into their shared memory
+    float fv = 0.0f;
+    int iv = 0;
     if (tid == 0 || tid == 32 || tid == 64) {
       const long long step = p.ctl->opt_step + 1;
-      if (tid == 0) {
-        const float v = (float)(-(p.lr / (1.0 - pow(p.beta1, (double)step))));
-        for (int r = 0; r < kAdamPer; ++r) *cluster.map_shared_rank(&s_neg_step, r) = v;
-      } else if (tid == 32) {
-        const float v = (float)sqrt(1.0 - pow(p.beta2d, (double)step));
-        for (int r = 0; r < kAdamPer; ++r) *cluster.map_shared_rank(&s_bc2_sqrt, r) = v;
-      } else {
-        const int v = ((p.ctl->tick + 1) % p.update_target_every) == 0;
-        for (int r = 0; r < kAdamPer; ++r) *cluster.map_shared_rank(&s_sync, r) = v;
+      if (tid == 0) fv = (float)(-(p.lr / (1.0 - pow(p.beta1, (double)step))));
+      else if (tid == 32) fv = (float)sqrt(1.0 - pow(p.beta2d, (double)step));
+      else iv = ((p.ctl->tick + 1) % p.update_target_every) == 0;
+    }
+    __syncwarp();
+    cluster_wait();
+    if (tid == 0 || tid == 32 || tid == 64) {
+      for (int r = 0; r < kAdamPer; ++r) {
+        if (tid == 0) *cluster.map_shared_rank(&s_neg_step, r) = fv;
+        else if (tid == 32) *cluster.map_shared_rank(&s_bc2_sqrt, r) = fv;
+        else *cluster.map_shared_rank(&s_sync, r) = iv;
       }
     }
     cluster.sync();
@@ -826,6 +836,8 @@ __global__ void __cluster_dims__(kAdamCluster, 1, 1) __launch_bounds__(256) redu
     p.grad_rw[o] = g;
     if (o == SWARM_W_COUNT) g = 0.0f;
   }
+  __syncwarp();
+  cluster_wait();
 #pragma unroll
   for (int r = 0; r < kAdamPer; ++r) *cluster.map_shared_rank(&sg[c][tid], r) = g;
   cluster.sync();       // every read of *ctl above precedes CTA 0's writes below
