@@ -617,16 +617,6 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
   __shared__ float s_coef, s_neg_step, s_bc2_sqrt;
   __shared__ int s_update, s_sync;
   const int tid = threadIdx.x;
-  if (p.ctl && tid == 255) {
-    // step-dependent scalars from the device cursor (overlaps with the norm sums of the other threads)
-    const long long step = p.ctl->opt_step + 1;
-    const double bc1 = 1.0 - pow(p.beta1, (double)step);
-    const double bc2 = 1.0 - pow(p.beta2d, (double)step);
-    s_neg_step = (float)(-(p.lr / bc1));
-    s_bc2_sqrt = (float)sqrt(bc2);
-    s_update = p.ctl->updating;
-    s_sync = ((p.ctl->tick + 1) % p.update_target_every) == 0;
-  }
   // every thread owns the elements tid, tid + 256, ...: one round trip to memory for grad / m / v / w, everything
   // else from registers
   constexpr int kPer = kAdamPer;                             // + 1: the loss rides along in the exchange
@@ -639,6 +629,17 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
     m_[i] = in ? p.m[o] : 0.0f;
     v_[i] = in ? p.v[o] : 0.0f;
     w_[i] = in ? p.w[o] : 0.0f;
+  }
+  if (p.ctl && tid == 255) {
+    // step-dependent scalars from the device cursor (after this warp's loads went out: the two pow chains run
+    // under their latency)
+    const long long step = p.ctl->opt_step + 1;
+    const double bc1 = 1.0 - pow(p.beta1, (double)step);
+    const double bc2 = 1.0 - pow(p.beta2d, (double)step);
+    s_neg_step = (float)(-(p.lr / bc1));
+    s_bc2_sqrt = (float)sqrt(bc2);
+    s_update = p.ctl->updating;
+    s_sync = ((p.ctl->tick + 1) % p.update_target_every) == 0;
   }
   if (PEERS && p.ctl) {
     // ---- one-shot PUSH all-reduce over NVLink peer memory ("low-latency" protocol) ---------------------------

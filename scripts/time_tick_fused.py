@@ -1,6 +1,6 @@
 """A/B of the train tick as two library calls (four launches) and as swarm_train_tick (three launches for G <= 64 CTAs),
 100 ticks per CUDA-graph replay: python scripts/time_tick_fused.py [G]"""
-import json, sys, torch
+import json, os, sys, torch
 sys.path.insert(0, '.')
 import numpy as np
 import swarm_b200 as sb
@@ -10,7 +10,7 @@ B, N = 4096, 12
 out = {}
 for G in ([int(a) for a in sys.argv[1:]] or [32, 4096]):
     res = {}
-    for mode in ("two_calls", "one_call"):
+    for mode in (("one_call", "two_calls") if os.environ.get("REVERSE") else ("two_calls", "one_call")):
         cfg = ops.make_config(1, B, N)
         g = torch.Generator().manual_seed(0)
         centers = (torch.tensor([0.6, -0.6]) + 0.1 * torch.randn(B, 2, generator=g)).to(dev)
