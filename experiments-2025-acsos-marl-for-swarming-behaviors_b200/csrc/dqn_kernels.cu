@@ -733,10 +733,10 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
   if (p.ctl && tid == 0) train_ctl_advance(p.ctl, p.num_envs, p.ring_capacity, true);
 }
 
-// ---- partial reduction + clip + Adam as ONE launch (swarm_train_tick on one GPU) ----------------------------------
+// ---- partial reduction (+ peer exchange) + clip + Adam as ONE launch (swarm_train_tick) ----------------------------
 // The two small launches at the end of a tick (dqn_reduce_kernel on 7 CTAs, adam_clip_kernel on one) as a single
-// thread-block cluster of 7 working CTAs x 256 threads (launched as the portable size 8; the last CTA only joins the
-// barrier), one gradient element per thread:
+// thread-block cluster of 7 working CTAs x 256 threads (launched as the portable size 8; the spare CTA computes the
+// step's Adam scalars), one gradient element per thread:
 //   1. element o = 256 c + t: the sum of the gradient kernel's partials in CTA order (dqn_reduce_kernel's sum);
 //   2. every CTA pushes its 256 sums into the shared memory of all seven (distributed shared memory), one cluster
 //      barrier, and every CTA holds the whole gradient laid out as adam_clip_kernel's registers are ([i][tid]), so the
@@ -744,6 +744,7 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(AdamParams p) {
 //   3. Adam on the CTA's own 256 elements; CTA 0 advances the device cursor.
 // Same bits as the two launches.  A single CTA cannot do step 1 at this speed: the 32 x 6.7 KB of partials through one
 // SM's L2 port cost as much as the launch they would save (tried: 34.8 vs 34.6 us per tick).
+
 // split cluster barrier: every CTA arrives when it starts and waits just before its first store into a peer CTA's shared
 // memory -- a CTA must have started executing before its shared memory is written remotely
 __device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
